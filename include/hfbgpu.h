@@ -1,0 +1,214 @@
+/* hfbgpu.h -- C ABI of libhfbgpu: the B200-native Baum-Welch E-step behind HERest.
+ *
+ * This is the drop-in boundary.  HTK has no plugin/FFI layer; the
+ * seam this library replaces is the three-call API of HTKLib/HFB.h:
+ *
+ *   InitialiseForBack(fbInfo, heap, hset, uset, pruneInit, pruneInc, pruneLim, minFrwdP)
+ *                                             HTKLib/HFB.h:117-119  ->  hfbgpu_create()
+ *   FBFile(fbInfo, utt, datafn)               HTKLib/HFB.h:143      ->  hfbgpu_accumulate()
+ *   side effects into TrAcc/WtAcc/MuAcc/VaAcc HTKLib/HTrain.h:211-232,
+ *   hmm->hook (numEgs, HFB.c:1768-1772), utt->pr, totalT/totalPr
+ *   (HTKTools/HERest.c:779-780)                                     ->  hfbgpu_get_accs()
+ *
+ * Plain C structs, plain pointers and sizes; the caller owns every host buffer,
+ * the library owns device memory.  No call ever exits the process: errors come
+ * back as HFB_E* codes carrying the reference's own HError numbers where one
+ * exists.  There is NO CPU fallback: without a CUDA device every compute entry
+ * point returns HFB_ENODEVICE.
+ *
+ * All model arrays are 0-based.  State indices inside an HMM follow HTK: state 1
+ * is the non-emitting entry, state N the non-emitting exit, 2..N-1 emit.
+ */
+#ifndef HFBGPU_H_
+#define HFBGPU_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HFBGPU_ABI_VERSION 1
+
+/* log-arithmetic constants, HTKLib/HMath.h:42-45 and HTKLib/HModel.h:52-53 */
+#define HFB_LZERO   (-1.0E10)
+#define HFB_LSMALL  (-0.5E10)
+#define HFB_MINEARG (-708.3)
+#define HFB_MINLARG 2.45E-308
+#define HFB_MINMIX  1.0E-5
+#define HFB_LMINMIX (-11.5129254649702)
+#define HFB_NOPRUNE 1.0E20          /* HTKLib/HFB.h:31 */
+
+/* update flags, HTKLib/HTrain.h:44 (UPMEANS|UPVARS|UPTRANS|UPMIXES) */
+enum { HFB_UPMEANS = 1, HFB_UPVARS = 2, HFB_UPTRANS = 4, HFB_UPMIXES = 8 };
+
+/* return codes; positive values in the 73xx range are the reference's HError numbers */
+enum {
+   HFB_OK          = 0,
+   HFB_EINVAL      = -1,   /* malformed argument */
+   HFB_ENODEVICE   = -2,   /* no CUDA device / extension missing: never falls back to CPU */
+   HFB_ECUDA       = -3,   /* a CUDA call failed, see hfbgpu_last_error() */
+   HFB_ENOMEM      = -4,
+   HFB_EUNSUPPORTED= -5,   /* model uses a feature outside the path (S>1, full covariance...) */
+   HFB_ETEE        = 7332, /* CreateInsts: tee models first/last/successive, HFB.c:557-565 */
+   HFB_EALPHAPRUNE = 7390, /* StepAlpha: alpha prune failed, HFB.c:706,718 */
+   HFB_EBETAPRUNE  = 7323  /* SetBeta: beta prune failed, HFB.c:1257 */
+};
+
+/* per-utterance status */
+enum {
+   HFB_UTT_OK      = 0,
+   HFB_UTT_SKIPPED = 7324, /* warning -7324 + FBFile returns FALSE, HFB.c:1342,1354 */
+   HFB_UTT_EALPHA  = 7390,
+   HFB_UTT_EBETA   = 7323,
+   HFB_UTT_ETEE    = 7332
+};
+
+/* ---- flat, read-only model: what HERest holds after ConvDiagC + ConvLogWt --------
+ * (HTKTools/HERest.c:592-594,643-645; pointer map in SURVEY.md 8b).               */
+typedef struct hfb_model {
+   int32_t vecSize;              /* D = hset->vecSize (one stream)                   */
+
+   int32_t numGauss;             /* G distinct MixPDFs                               */
+   const float   *mean;          /* [G][D]  mp->mean                                 */
+   const float   *ivar;          /* [G][D]  mp->cov.var as INVERSE variances         */
+   const float   *gConst;        /* [G]     mp->gConst AS STORED (never recomputed)  */
+   const int32_t *meanId;        /* [G] -> mean accumulator (MuAcc) id, ~u sharing   */
+   const int32_t *varId;         /* [G] -> variance accumulator (VaAcc) id, ~v       */
+   int32_t numMeanAcc;
+   int32_t numVarAcc;
+
+   int32_t numStates;            /* J distinct StreamElems (tied states)             */
+   const int32_t *stateMixOff;   /* [J+1] offsets into mixGauss/mixLogWt             */
+   const int32_t *mixGauss;      /* [sum M] Gaussian index of component m            */
+   const float   *mixLogWt;      /* [sum M] log weight; <= HFB_LMINMIX means skipped */
+
+   int32_t numHmm;               /* P physical HMMs, in HMMScan (= dump) order       */
+   const int32_t *hmmNumStates;  /* [P] N_p including entry and exit                 */
+   const int32_t *hmmStateOff;   /* [P+1] offsets into hmmState                      */
+   const int32_t *hmmState;      /* [sum (N_p-2)] tied-state index of states 2..N-1  */
+   const int32_t *hmmTrans;      /* [P] transition-matrix id (~t sharing)            */
+
+   int32_t numTrans;
+   const int32_t *transN;        /* [numTrans] N of each matrix                      */
+   const int32_t *transOff;      /* [numTrans+1] offsets into transLogA (N*N each)   */
+   const float   *transLogA;     /* row-major [N][N] float logs, HFB_LZERO if absent */
+} hfb_model;
+
+typedef struct hfb_options {
+   double  pruneInit;            /* HFB_NOPRUNE = pruning off (HFB.c:83)             */
+   double  pruneInc;
+   double  pruneLim;
+   float   minFrwdP;             /* default 10.0 (HFB.c:83)                          */
+   int32_t uFlags;               /* HFB_UP* mask                                     */
+   int32_t device;               /* CUDA device ordinal                              */
+   int32_t gmmKernel;            /* 0 = auto, 1 = FP32 CUDA-core, 2 = tcgen05 3xTF32 */
+   int32_t reserved0;
+   size_t  workspaceBytes;       /* 0 = default; cap for per-wave beta/outprob pool  */
+} hfb_options;
+
+/* ---- one batch of loaded utterances ------------------------------------------- */
+typedef struct hfb_batch {
+   int32_t numUtt;
+   const int64_t *frameOff;      /* [numUtt+1] frame offsets into feat               */
+   const float   *feat;          /* [totalT][D] row-major, what ReadAsTable yields   */
+   const int32_t *labOff;        /* [numUtt+1] offsets into lab                      */
+   const int32_t *lab;           /* physical-HMM index per label (utt->tr resolved)  */
+} hfb_batch;
+
+typedef struct hfb_utt_result {
+   int32_t status;               /* HFB_UTT_*                                        */
+   int32_t retries;              /* beta passes repeated (HFB.c:1349-1361)           */
+   double  pr;                   /* utt->pr, total log likelihood                    */
+   double  pruneThresh;          /* threshold finally used                           */
+} hfb_utt_result;
+
+/* optional per-frame beams of the last batch (debug / parity): 1-based model numbers
+ * like the reference's "Beta Beam lo->hi" / "Alpha Beam sq->eq" trace lines.       */
+typedef struct hfb_beams {
+   int16_t *qLo, *qHi;           /* [totalT] beta beam                               */
+   int16_t *sq,  *eq;            /* [totalT] alpha beam                              */
+} hfb_beams;
+
+/* ---- layout of the flat FP64 accumulator buffer ------------------------------- */
+typedef struct hfb_acc_layout {
+   int64_t tran;      /* [sum N*N]  TrAcc.tran, row-major per matrix               */
+   int64_t tranOcc;   /* [sum N]    TrAcc.occ                                      */
+   int64_t wtC;       /* [sum M]    WtAcc.c                                        */
+   int64_t wtOcc;     /* [J]        WtAcc.occ                                      */
+   int64_t muSum;     /* [numMeanAcc][D]  MuAcc.mu, CENTRED on the current mean    */
+   int64_t muOcc;     /* [numMeanAcc]                                              */
+   int64_t vaSum;     /* [numVarAcc][D]   VaAcc.cov.var, centred                   */
+   int64_t vaOcc;     /* [numVarAcc]                                               */
+   int64_t numEgs;    /* [P]        hmm->hook counters (as doubles, exact < 2^53)  */
+   int64_t totalT;    /* [1]        frames of successful utterances                */
+   int64_t totalPr;   /* [1]        sum of utt->pr                                 */
+   int64_t numOk;     /* [1]        utterances accumulated                         */
+   int64_t numSkipped;/* [1]        utterances that returned FALSE                 */
+   int64_t count;     /* total doubles                                             */
+   int64_t tranOccStride; /* reserved                                              */
+} hfb_acc_layout;
+
+typedef struct hfbgpu_ctx hfbgpu_ctx;
+
+/* Host-only helpers (no device needed). */
+int  hfbgpu_abi_version(void);
+int  hfbgpu_acc_layout(const hfb_model *m, hfb_acc_layout *out);
+void hfbgpu_default_options(hfb_options *opt);
+const char *hfbgpu_strerror(int code);
+const char *hfbgpu_last_error(void);
+int  hfbgpu_device_count(void);
+
+/* Replaces InitialiseForBack (HFB.h:117): uploads the model, computes minimum
+ * durations (SetMinDurs, HFB.c:106-155), allocates zeroed accumulators.          */
+int hfbgpu_create(hfbgpu_ctx **ctx, const hfb_model *m, const hfb_options *opt);
+int hfbgpu_destroy(hfbgpu_ctx *ctx);
+
+/* ZeroAccs (HTrain.c:1072). */
+int hfbgpu_zero_accs(hfbgpu_ctx *ctx);
+
+/* Replaces the FBFile loop (HERest.c:502-534 / HFB.c:1923): forward-backward and
+ * accumulation for every utterance of the batch.  res[numUtt]; beams may be NULL.
+ * Host buffers in, copies are part of the call.                                   */
+int hfbgpu_accumulate(hfbgpu_ctx *ctx, const hfb_batch *batch,
+                      hfb_utt_result *res, const hfb_beams *beams);
+
+/* Same, but batch->feat is a DEVICE pointer already resident in HBM (the other
+ * arrays stay on the host).  `stream` is a cudaStream_t (NULL = library stream).
+ * Results stay on the device until hfbgpu_sync_results().                         */
+int hfbgpu_accumulate_device(hfbgpu_ctx *ctx, const hfb_batch *batch,
+                             hfb_utt_result *res, const hfb_beams *beams);
+
+/* Flat FP64 accumulators: device pointer (for an NCCL all-reduce by the caller)
+ * and host download.  Layout: hfbgpu_acc_layout().                                */
+double *hfbgpu_acc_device_ptr(hfbgpu_ctx *ctx);
+int64_t hfbgpu_acc_count(hfbgpu_ctx *ctx);
+int hfbgpu_get_accs(hfbgpu_ctx *ctx, double *hostOut);
+int hfbgpu_set_accs(hfbgpu_ctx *ctx, const double *hostIn);
+
+/* MOutP/OutP alone (HModel.c:5484, HFB.c:898-988): log b_j(o_t) for `n` tied
+ * states over T host frames -> out[T][n].  mixOut (optional) gets the per-mixture
+ * log densities laid out [T][sum M of the listed states].                         */
+int hfbgpu_state_loglik(hfbgpu_ctx *ctx, const float *feat, int32_t T,
+                        const int32_t *states, int32_t n, float *out, float *mixOut);
+
+/* Minimum durations per transition matrix as computed at create (TrAcc.minDur). */
+int hfbgpu_get_min_durs(hfbgpu_ctx *ctx, int32_t *out);
+
+/* Counters for bench.py: kernels launched / device time since the last reset. */
+typedef struct hfb_stats {
+   int64_t launches;
+   int64_t launchesGmm, launchesBeta, launchesAlpha, launchesStats, launchesMisc;
+   double  msGmm, msBeta, msAlpha, msStats;   /* CUDA-event time on the library stream */
+   int64_t betaCells, alphaCells, gmmPairs;   /* algorithmic units processed             */
+   int64_t h2dBytes, d2hBytes;
+} hfb_stats;
+int hfbgpu_get_stats(hfbgpu_ctx *ctx, hfb_stats *out);
+int hfbgpu_reset_stats(hfbgpu_ctx *ctx);
+int hfbgpu_set_timing(hfbgpu_ctx *ctx, int enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HFBGPU_H_ */
