@@ -1,0 +1,709 @@
+// hfbgpu.cu -- host side of libhfbgpu: the C ABI declared in include/hfbgpu.h.
+//
+// Replaces the reference's InitialiseForBack / FBFile seam (HTKLib/HFB.h:117-119, :143).
+// The batch is cut into waves that fit the device workspace; per wave the host builds the
+// per-utterance tables (CreateInsts, HFB.c:508-574), uploads them in one copy and launches
+//   K1 gmm  ->  K2 beta  ->  K3 alpha  ->  K4 stats
+// on the library stream.  Accumulators stay resident in HBM as one flat FP64 buffer
+// (layout: hfbgpu_acc_layout) until hfbgpu_get_accs() or the caller's all-reduce.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "hfb_common.h"
+#include "hfb_kernels.cuh"
+#include "gmm_tc.cuh"
+
+static thread_local std::string g_lastError;
+
+#define CK(call)                                                                                   \
+   do {                                                                                            \
+      cudaError_t e_ = (call);                                                                     \
+      if (e_ != cudaSuccess) {                                                                     \
+         char buf_[512];                                                                           \
+         snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,          \
+                  cudaGetErrorString(e_));                                                         \
+         g_lastError = buf_;                                                                       \
+         return HFB_ECUDA;                                                                         \
+      }                                                                                            \
+   } while (0)
+
+namespace {
+
+template <class T>
+struct DevBuf {
+   T *p = nullptr;
+   size_t cap = 0;
+   int reserve(size_t n)
+   {
+      if (n <= cap) return HFB_OK;
+      if (p) cudaFree(p);
+      p = nullptr; cap = 0;
+      size_t want = n + n / 4 + 16;
+      if (cudaMalloc(&p, want * sizeof(T)) != cudaSuccess) {
+         cudaGetLastError();
+         want = n;
+         if (cudaMalloc(&p, want * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return HFB_ENOMEM; }
+      }
+      cap = want;
+      return HFB_OK;
+   }
+   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostModel {
+   int D, G, J, P, numTrans, maxM, maxN;
+   std::vector<int> stateMixOff, hmmN, hmmStateOff, hmmState, hmmTrans, transN, transOff, minDur;
+   std::vector<long long> tranAccOff, tranOccOff;
+   std::vector<float> transLogA;
+};
+
+}  // namespace
+
+struct hfbgpu_ctx {
+   int device = 0;
+   hfb_options opt;
+   HostModel hm;
+   DevModel dm;
+   hfb_acc_layout L;
+   cudaStream_t stream = nullptr;
+   cudaEvent_t ev[8] = {};
+   bool timing = false;
+   hfb_stats stats;
+   // model on device
+   DevBuf<float> dMean, dIvar, dGconst, dMixLogWt, dTransLogA;
+   DevBuf<int> dMeanId, dVarId, dStateMixOff, dMixGauss;
+   GmmTcModel tc;                    // expanded / split operands for the tcgen05 path
+   // accumulators
+   DevBuf<double> dAcc;
+   // workspace
+   DevBuf<float> dFeat;              // only for host-feature calls
+   DevBuf<float> dB;
+   DevBuf<double> dBeta, dOcc;
+   DevBuf<short> dBeams;             // 4 * frames
+   DevBuf<unsigned char> dTables;
+   unsigned char *hTables = nullptr; // pinned staging
+   size_t hTablesCap = 0;
+   UttOut *hOut = nullptr;           // pinned
+   size_t hOutCap = 0;
+   short *hBeams = nullptr;          // pinned
+   size_t hBeamsCap = 0;
+   size_t workspaceBytes = 0;
+   int smCount = 148;
+   int maxSmemOptin = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+// host-only helpers
+// ------------------------------------------------------------------------------------------
+extern "C" int hfbgpu_abi_version(void) { return HFBGPU_ABI_VERSION; }
+
+extern "C" int hfbgpu_acc_layout(const hfb_model *m, hfb_acc_layout *L)
+{
+   if (!m || !L) return HFB_EINVAL;
+   long long o = 0, nn = 0, n = 0;
+   for (int i = 0; i < m->numTrans; i++) { nn += (long long)m->transN[i] * m->transN[i]; n += m->transN[i]; }
+   L->tran = o;    o += nn;
+   L->tranOcc = o; o += n;
+   L->wtC = o;     o += m->stateMixOff[m->numStates];
+   L->wtOcc = o;   o += m->numStates;
+   L->muSum = o;   o += (long long)m->numMeanAcc * m->vecSize;
+   L->muOcc = o;   o += m->numMeanAcc;
+   L->vaSum = o;   o += (long long)m->numVarAcc * m->vecSize;
+   L->vaOcc = o;   o += m->numVarAcc;
+   L->numEgs = o;  o += m->numHmm;
+   L->totalT = o++; L->totalPr = o++; L->numOk = o++; L->numSkipped = o++;
+   L->count = o; L->tranOccStride = 0;
+   return HFB_OK;
+}
+
+extern "C" void hfbgpu_default_options(hfb_options *o)
+{
+   if (!o) return;
+   memset(o, 0, sizeof(*o));
+   o->pruneInit = HFB_NOPRUNE; o->pruneInc = 0.0; o->pruneLim = HFB_NOPRUNE;   // HFB.c:83
+   o->minFrwdP = 10.0f;
+   o->uFlags = HFB_UPMEANS | HFB_UPVARS | HFB_UPTRANS | HFB_UPMIXES;
+   o->device = 0; o->gmmKernel = 0; o->workspaceBytes = 0;
+}
+
+extern "C" const char *hfbgpu_strerror(int code)
+{
+   switch (code) {
+   case HFB_OK: return "ok";
+   case HFB_EINVAL: return "invalid argument";
+   case HFB_ENODEVICE: return "no CUDA device (libhfbgpu has no CPU fallback)";
+   case HFB_ECUDA: return "CUDA error";
+   case HFB_ENOMEM: return "out of device memory";
+   case HFB_EUNSUPPORTED: return "model feature outside the accelerated path";
+   case HFB_ETEE: return "CreateInsts: tee model first, last or twice in a row (HError 7332)";
+   case HFB_EALPHAPRUNE: return "StepAlpha: alpha prune failed (HError 7390)";
+   case HFB_EBETAPRUNE: return "SetBeta: beta prune failed (HError 7323)";
+   case HFB_UTT_SKIPPED: return "StepBack: bad data or over pruning (HError -7324)";
+   default: return "unknown";
+   }
+}
+
+extern "C" const char *hfbgpu_last_error(void) { return g_lastError.c_str(); }
+
+extern "C" int hfbgpu_device_count(void)
+{
+   int n = 0;
+   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+   return n;
+}
+
+// FindStateOrder + SetMinDurs, HTKLib/HFB.c:91-155.
+static void order_states(const float *A, int N, std::vector<int> &ord, int s, int &cnt)
+{
+   ord[s] = 0;
+   for (int p = 0; p < N - 1; p++)
+      if (A[p * N + s] > HFB_LSMALL && p != s && ord[p] < 0) order_states(A, N, ord, p, cnt);
+   ord[s] = ++cnt;
+}
+
+static int min_duration(const float *A, int N)
+{
+   std::vector<int> ord(N, -1), byOrd(N + 1, -1), md(N, N);
+   int cnt = 0;
+   order_states(A, N, ord, N - 1, cnt);
+   for (int i = 0; i < N; i++) if (ord[i] > 0) byOrd[ord[i]] = i;
+   md[0] = 0;
+   for (int k = 1; k <= cnt; k++) {
+      int i = byOrd[k];
+      if (i < 0) continue;
+      for (int j = 0; j < N - 1; j++)
+         if (A[j * N + i] > HFB_LSMALL) {
+            int d = md[j] + ((i == N - 1) ? 0 : 1);
+            if (d < md[i]) md[i] = d;
+         }
+   }
+   if (md[N - 1] < 0 || md[N - 1] >= N) return (A[N - 1] > HFB_LSMALL) ? 0 : 1;   // HFB.c:144-149
+   return md[N - 1];
+}
+
+// ------------------------------------------------------------------------------------------
+// create / destroy
+// ------------------------------------------------------------------------------------------
+template <class T>
+static int upload(DevBuf<T> &b, const T *src, size_t n, cudaStream_t st)
+{
+   int rc = b.reserve(n ? n : 1);
+   if (rc) return rc;
+   if (n) CK(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+   return HFB_OK;
+}
+
+extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_options *opt)
+{
+   if (!out || !m || !opt) return HFB_EINVAL;
+   *out = nullptr;
+   if (m->vecSize < 1 || m->numGauss < 1 || m->numStates < 1 || m->numHmm < 1 || m->numTrans < 1) return HFB_EINVAL;
+   if (m->vecSize > 64) { g_lastError = "vecSize > 64 is outside the accelerated path"; return HFB_EUNSUPPORTED; }
+   int ndev = hfbgpu_device_count();
+   if (ndev <= 0) { g_lastError = "no CUDA device visible"; return HFB_ENODEVICE; }
+   if (opt->device < 0 || opt->device >= ndev) return HFB_EINVAL;
+   CK(cudaSetDevice(opt->device));
+
+   hfbgpu_ctx *c = new hfbgpu_ctx();
+   c->device = opt->device;
+   c->opt = *opt;
+   memset(&c->stats, 0, sizeof(c->stats));
+   hfbgpu_acc_layout(m, &c->L);
+   cudaDeviceProp prop;
+   CK(cudaGetDeviceProperties(&prop, c->device));
+   c->smCount = prop.multiProcessorCount;
+   c->maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
+   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+   for (auto &e : c->ev) CK(cudaEventCreate(&e));
+
+   HostModel &h = c->hm;
+   h.D = m->vecSize; h.G = m->numGauss; h.J = m->numStates; h.P = m->numHmm; h.numTrans = m->numTrans;
+   h.stateMixOff.assign(m->stateMixOff, m->stateMixOff + h.J + 1);
+   h.hmmN.assign(m->hmmNumStates, m->hmmNumStates + h.P);
+   h.hmmStateOff.assign(m->hmmStateOff, m->hmmStateOff + h.P + 1);
+   h.hmmState.assign(m->hmmState, m->hmmState + m->hmmStateOff[h.P]);
+   h.hmmTrans.assign(m->hmmTrans, m->hmmTrans + h.P);
+   h.transN.assign(m->transN, m->transN + h.numTrans);
+   h.transOff.assign(m->transOff, m->transOff + h.numTrans + 1);
+   h.transLogA.assign(m->transLogA, m->transLogA + m->transOff[h.numTrans]);
+   h.maxM = 0; h.maxN = 0;
+   for (int j = 0; j < h.J; j++) h.maxM = std::max(h.maxM, h.stateMixOff[j + 1] - h.stateMixOff[j]);
+   h.minDur.resize(h.numTrans);
+   h.tranAccOff.resize(h.numTrans); h.tranOccOff.resize(h.numTrans);
+   long long a = c->L.tran, b = c->L.tranOcc;
+   for (int i = 0; i < h.numTrans; i++) {
+      int N = h.transN[i];
+      h.maxN = std::max(h.maxN, N);
+      h.minDur[i] = min_duration(h.transLogA.data() + h.transOff[i], N);       // SetMinDurs
+      h.tranAccOff[i] = a; h.tranOccOff[i] = b;
+      a += (long long)N * N; b += N;
+   }
+   for (int p = 0; p < h.P; p++)
+      if (h.hmmN[p] != h.transN[h.hmmTrans[p]] || h.hmmStateOff[p + 1] - h.hmmStateOff[p] != h.hmmN[p] - 2) {
+         delete c; g_lastError = "hmmNumStates inconsistent with transN / hmmStateOff"; return HFB_EINVAL;
+      }
+   if (h.maxN > HFB_MAXN) { delete c; g_lastError = "HMM with more than 16 states"; return HFB_EUNSUPPORTED; }
+
+   // model upload (means / inverse variances padded to a multiple of 4 floats per row)
+   const int D = h.D, Dp = (D + 3) & ~3;
+   std::vector<float> mean((size_t)h.G * Dp, 0.f), ivar((size_t)h.G * Dp, 0.f);
+   for (int g = 0; g < h.G; g++)
+      for (int k = 0; k < D; k++) {
+         mean[(size_t)g * Dp + k] = m->mean[(size_t)g * D + k];
+         ivar[(size_t)g * Dp + k] = m->ivar[(size_t)g * D + k];
+      }
+   int rc;
+   const int sumM = h.stateMixOff[h.J];
+   if ((rc = upload(c->dMean, mean.data(), mean.size(), c->stream)) ||
+       (rc = upload(c->dIvar, ivar.data(), ivar.size(), c->stream)) ||
+       (rc = upload(c->dGconst, m->gConst, (size_t)h.G, c->stream)) ||
+       (rc = upload(c->dMeanId, m->meanId, (size_t)h.G, c->stream)) ||
+       (rc = upload(c->dVarId, m->varId, (size_t)h.G, c->stream)) ||
+       (rc = upload(c->dStateMixOff, m->stateMixOff, (size_t)h.J + 1, c->stream)) ||
+       (rc = upload(c->dMixGauss, m->mixGauss, (size_t)sumM, c->stream)) ||
+       (rc = upload(c->dMixLogWt, m->mixLogWt, (size_t)sumM, c->stream)) ||
+       (rc = upload(c->dTransLogA, h.transLogA.data(), h.transLogA.size(), c->stream))) {
+      hfbgpu_destroy(c); return rc;
+   }
+   CK(cudaStreamSynchronize(c->stream));
+   DevModel &d = c->dm;
+   d.D = D; d.Dp = Dp; d.G = h.G; d.J = h.J; d.P = h.P; d.numTrans = h.numTrans; d.maxM = h.maxM;
+   d.mean = c->dMean.p; d.ivar = c->dIvar.p; d.gconst = c->dGconst.p;
+   d.meanId = c->dMeanId.p; d.varId = c->dVarId.p;
+   d.stateMixOff = c->dStateMixOff.p; d.mixGauss = c->dMixGauss.p; d.mixLogWt = c->dMixLogWt.p;
+   d.transLogA = c->dTransLogA.p;
+   d.L = c->L;
+
+   if ((rc = c->dAcc.reserve((size_t)c->L.count))) { hfbgpu_destroy(c); return rc; }
+   CK(cudaMemsetAsync(c->dAcc.p, 0, (size_t)c->L.count * sizeof(double), c->stream));
+
+   // tensor-core operands (expanded quadratic form, 3xTF32 split)
+   if ((rc = gmm_tc_prepare(c->tc, m, c->stream))) { hfbgpu_destroy(c); return rc; }
+   if (opt->gmmKernel == 2 && !gmm_tc_available(c->tc)) {
+      hfbgpu_destroy(c); g_lastError = "tcgen05 GMM kernel requested but not available for this model";
+      return HFB_EUNSUPPORTED;
+   }
+
+   size_t freeB = 0, totalB = 0;
+   CK(cudaMemGetInfo(&freeB, &totalB));
+   size_t ws = opt->workspaceBytes ? opt->workspaceBytes : ((size_t)16 << 30);
+   if (ws > freeB * 6 / 10) ws = freeB * 6 / 10;
+   c->workspaceBytes = ws;
+
+   int maxOpt = c->maxSmemOptin;
+   cudaFuncSetAttribute(beta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
+   cudaFuncSetAttribute(beta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
+   cudaFuncSetAttribute(alpha_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
+   cudaFuncSetAttribute(alpha_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
+   CK(cudaStreamSynchronize(c->stream));
+   *out = c;
+   return HFB_OK;
+}
+
+extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
+{
+   if (!c) return HFB_EINVAL;
+   cudaSetDevice(c->device);
+   if (c->stream) cudaStreamSynchronize(c->stream);
+   c->dMean.release(); c->dIvar.release(); c->dGconst.release(); c->dMixLogWt.release(); c->dTransLogA.release();
+   c->dMeanId.release(); c->dVarId.release(); c->dStateMixOff.release(); c->dMixGauss.release();
+   gmm_tc_release(c->tc);
+   c->dAcc.release(); c->dFeat.release(); c->dB.release(); c->dBeta.release(); c->dOcc.release();
+   c->dBeams.release(); c->dTables.release();
+   if (c->hTables) cudaFreeHost(c->hTables);
+   if (c->hOut) cudaFreeHost(c->hOut);
+   if (c->hBeams) cudaFreeHost(c->hBeams);
+   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+   if (c->stream) cudaStreamDestroy(c->stream);
+   delete c;
+   return HFB_OK;
+}
+
+extern "C" int hfbgpu_zero_accs(hfbgpu_ctx *c)
+{
+   if (!c) return HFB_EINVAL;
+   CK(cudaSetDevice(c->device));
+   CK(cudaMemsetAsync(c->dAcc.p, 0, (size_t)c->L.count * sizeof(double), c->stream));
+   CK(cudaStreamSynchronize(c->stream));
+   return HFB_OK;
+}
+
+extern "C" double *hfbgpu_acc_device_ptr(hfbgpu_ctx *c) { return c ? c->dAcc.p : nullptr; }
+extern "C" int64_t hfbgpu_acc_count(hfbgpu_ctx *c) { return c ? c->L.count : 0; }
+
+extern "C" int hfbgpu_get_accs(hfbgpu_ctx *c, double *hostOut)
+{
+   if (!c || !hostOut) return HFB_EINVAL;
+   CK(cudaSetDevice(c->device));
+   CK(cudaStreamSynchronize(c->stream));
+   CK(cudaMemcpy(hostOut, c->dAcc.p, (size_t)c->L.count * sizeof(double), cudaMemcpyDeviceToHost));
+   c->stats.d2hBytes += c->L.count * (int64_t)sizeof(double);
+   return HFB_OK;
+}
+
+extern "C" int hfbgpu_set_accs(hfbgpu_ctx *c, const double *hostIn)
+{
+   if (!c || !hostIn) return HFB_EINVAL;
+   CK(cudaSetDevice(c->device));
+   CK(cudaStreamSynchronize(c->stream));
+   CK(cudaMemcpy(c->dAcc.p, hostIn, (size_t)c->L.count * sizeof(double), cudaMemcpyHostToDevice));
+   return HFB_OK;
+}
+
+extern "C" int hfbgpu_get_min_durs(hfbgpu_ctx *c, int32_t *out)
+{
+   if (!c || !out) return HFB_EINVAL;
+   for (int i = 0; i < c->hm.numTrans; i++) out[i] = c->hm.minDur[i];
+   return HFB_OK;
+}
+
+extern "C" int hfbgpu_get_stats(hfbgpu_ctx *c, hfb_stats *o) { if (!c || !o) return HFB_EINVAL; *o = c->stats; return HFB_OK; }
+extern "C" int hfbgpu_reset_stats(hfbgpu_ctx *c) { if (!c) return HFB_EINVAL; memset(&c->stats, 0, sizeof(c->stats)); return HFB_OK; }
+extern "C" int hfbgpu_set_timing(hfbgpu_ctx *c, int on) { if (!c) return HFB_EINVAL; c->timing = on != 0; return HFB_OK; }
+
+// ------------------------------------------------------------------------------------------
+// wave construction
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct WaveTables {
+   std::vector<UttDesc> utt;
+   std::vector<UttOut> out;
+   std::vector<int> mN, mTrans, mSoff, mPoff, mDms, mPre, mSuf, mHmm;
+   std::vector<long long> mTrAcc, mTrOcc;
+   std::vector<int> slotState, posSlot, posState;
+   std::vector<PosRef> pos;
+   std::vector<GmmTile> tiles;
+   std::vector<int> uttIndex;        // index in the caller's batch
+   long long bFloats = 0, betaDoubles = 0, occDoubles = 0;
+   int maxQ = 0, maxS = 0;
+   long long frames = 0, frame0 = 0;
+   void clear()
+   {
+      utt.clear(); out.clear(); mN.clear(); mTrans.clear(); mSoff.clear(); mPoff.clear(); mDms.clear();
+      mPre.clear(); mSuf.clear(); mHmm.clear(); mTrAcc.clear(); mTrOcc.clear();
+      slotState.clear(); posSlot.clear(); posState.clear(); pos.clear(); tiles.clear(); uttIndex.clear();
+      bFloats = betaDoubles = occDoubles = 0; maxQ = maxS = 0; frames = 0;
+   }
+};
+
+// CreateInsts (HFB.c:508-574) for one utterance; appends to the wave tables.
+// Returns the workspace bytes the utterance needs.
+size_t add_utterance(const HostModel &h, WaveTables &w, int uidx, int T, const int32_t *lab, int Q,
+                     long long featOff, long long frameBase, std::vector<int> &slotOf /* scratch [J], -1 */)
+{
+   UttDesc u;
+   memset(&u, 0, sizeof(u));
+   UttOut o; o.status = 0; o.retries = 0; o.pr = HFB_LZERO; o.thresh = 0.0;
+   u.T = T; u.Q = Q; u.modOff = (int)w.mN.size(); u.slotOff = (int)w.slotState.size();
+   u.posOff = (int)w.posSlot.size(); u.featOff = featOff; u.frameBase = frameBase;
+   int S = 0, Pp = 0, J = 0, qt = 0;
+   bool bad = (Q < 1 || T < 1);
+   const int uLocal = (int)w.utt.size();
+   for (int q = 0; q < Q && !bad; q++) {
+      int p = lab[q];
+      if (p < 0 || p >= h.P) { bad = true; break; }
+   }
+   if (!bad) {
+      for (int q = 0; q < Q; q++) {
+         int p = lab[q], tr = h.hmmTrans[p], N = h.hmmN[p], dms = h.minDur[tr];
+         w.mN.push_back(N); w.mTrans.push_back(h.transOff[tr]); w.mSoff.push_back(S); w.mPoff.push_back(Pp);
+         w.mDms.push_back(dms); w.mPre.push_back(qt); w.mHmm.push_back(p);
+         w.mTrAcc.push_back(h.tranAccOff[tr]); w.mTrOcc.push_back(h.tranOccOff[tr]);
+         if (q > 0 && dms == 0 && w.mDms[u.modOff + q - 1] == 0) o.status = HFB_UTT_ETEE;   // :557
+         for (int j = 0; j < N - 2; j++) {
+            int s = h.hmmState[h.hmmStateOff[p] + j];
+            if (slotOf[s] < 0) { slotOf[s] = J++; w.slotState.push_back(s); }
+            w.posSlot.push_back(slotOf[s]); w.posState.push_back(s);
+            w.pos.push_back(PosRef{uLocal, q, j});
+         }
+         S += N; Pp += N - 2; qt += dms;
+      }
+      for (int k = 0; k < J; k++) slotOf[w.slotState[u.slotOff + k]] = -1;
+      w.mSuf.resize(w.mN.size());
+      int acc = 0;
+      for (int q = Q - 1; q >= 0; q--) { w.mSuf[u.modOff + q] = acc; acc += w.mDms[u.modOff + q]; }
+      if (w.mDms[u.modOff] == 0 || w.mDms[u.modOff + Q - 1] == 0) o.status = HFB_UTT_ETEE;          // :564
+      if (o.status == 0 && qt > T) o.status = HFB_UTT_SKIPPED;                                      // :1339-1343
+   } else {
+      o.status = HFB_UTT_ETEE; Q = 0; u.Q = 0;
+   }
+   u.S = S; u.P = Pp; u.J = J;
+   size_t bytes = 0;
+   if (o.status == 0) {
+      u.bOff = w.bFloats; u.betaOff = w.betaDoubles; u.occOff = w.occDoubles;
+      w.bFloats += (long long)T * J; w.betaDoubles += (long long)T * S; w.occDoubles += (long long)T * Pp;
+      bytes = (size_t)T * ((size_t)J * 4 + (size_t)S * 8 + (size_t)Pp * 8);
+      for (int t0 = 0; t0 < T; t0 += GT_FR)
+         for (int s0 = 0; s0 < J; s0 += GT_SL) w.tiles.push_back(GmmTile{uLocal, t0, s0});
+      w.maxQ = std::max(w.maxQ, Q); w.maxS = std::max(w.maxS, S);
+   } else {
+      // keep table sizes consistent but give the kernels nothing to do
+      w.pos.resize(w.pos.size() - (size_t)Pp);
+   }
+   w.utt.push_back(u); w.out.push_back(o); w.uttIndex.push_back(uidx);
+   return bytes;
+}
+
+template <class T>
+size_t blob_put(std::vector<unsigned char> &blob, const std::vector<T> &v)
+{
+   size_t off = (blob.size() + 255) & ~(size_t)255;
+   blob.resize(off + v.size() * sizeof(T) + 8);
+   if (!v.empty()) memcpy(blob.data() + off, v.data(), v.size() * sizeof(T));
+   return off;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// run one wave
+// ------------------------------------------------------------------------------------------
+static int run_wave(hfbgpu_ctx *c, WaveTables &w, const float *dFeat, long long waveFrame0, long long waveFrames,
+                    hfb_utt_result *res, const hfb_beams *beams, long long batchFrame0)
+{
+   const int nU = (int)w.utt.size();
+   if (nU == 0) return HFB_OK;
+   int rc;
+   // ---- pack + upload tables
+   std::vector<unsigned char> blob;
+   size_t oUtt = blob_put(blob, w.utt), oOut = blob_put(blob, w.out);
+   size_t oN = blob_put(blob, w.mN), oTr = blob_put(blob, w.mTrans), oSo = blob_put(blob, w.mSoff),
+          oPo = blob_put(blob, w.mPoff), oDm = blob_put(blob, w.mDms), oPre = blob_put(blob, w.mPre),
+          oSuf = blob_put(blob, w.mSuf), oHm = blob_put(blob, w.mHmm), oTa = blob_put(blob, w.mTrAcc),
+          oTo = blob_put(blob, w.mTrOcc);
+   std::vector<int> tminmax(w.mN.size() * 2, 0);
+   size_t oTm = blob_put(blob, tminmax);
+   size_t oSs = blob_put(blob, w.slotState), oPs = blob_put(blob, w.posSlot), oPst = blob_put(blob, w.posState);
+   size_t oPos = blob_put(blob, w.pos), oTl = blob_put(blob, w.tiles);
+   if (blob.size() > c->hTablesCap) {
+      if (c->hTables) cudaFreeHost(c->hTables);
+      c->hTablesCap = blob.size() * 2;
+      CK(cudaMallocHost(&c->hTables, c->hTablesCap));
+   }
+   memcpy(c->hTables, blob.data(), blob.size());
+   if ((rc = c->dTables.reserve(blob.size()))) return rc;
+   CK(cudaMemcpyAsync(c->dTables.p, c->hTables, blob.size(), cudaMemcpyHostToDevice, c->stream));
+   c->stats.h2dBytes += (int64_t)blob.size();
+   if ((rc = c->dB.reserve((size_t)w.bFloats + 1)) || (rc = c->dBeta.reserve((size_t)w.betaDoubles + 1)) ||
+       (rc = c->dOcc.reserve((size_t)w.occDoubles + 1)) || (rc = c->dBeams.reserve((size_t)waveFrames * 4 + 4)))
+      return rc;
+
+   unsigned char *base = c->dTables.p;
+   Wave W;
+   memset(&W, 0, sizeof(W));
+   W.utt = (const UttDesc *)(base + oUtt); W.out = (UttOut *)(base + oOut); W.numUtt = nU;
+   W.mN = (const int *)(base + oN); W.mTrans = (const int *)(base + oTr); W.mSoff = (const int *)(base + oSo);
+   W.mPoff = (const int *)(base + oPo); W.mDms = (const int *)(base + oDm); W.mPre = (const int *)(base + oPre);
+   W.mSuf = (const int *)(base + oSuf); W.mHmm = (const int *)(base + oHm);
+   W.mTrAcc = (const long long *)(base + oTa); W.mTrOcc = (const long long *)(base + oTo);
+   W.mTmin = (int *)(base + oTm); W.mTmax = W.mTmin + w.mN.size();
+   W.slotState = (const int *)(base + oSs); W.posSlot = (const int *)(base + oPs); W.posState = (const int *)(base + oPst);
+   W.feat = dFeat;
+   W.b = c->dB.p; W.beta = c->dBeta.p; W.occ = c->dOcc.p;
+   W.qLo = c->dBeams.p; W.qHi = W.qLo + waveFrames; W.sq = W.qHi + waveFrames; W.eq = W.sq + waveFrames;
+   W.acc = c->dAcc.p;
+   W.pruneInit = c->opt.pruneInit; W.pruneInc = c->opt.pruneInc; W.pruneLim = c->opt.pruneLim;
+   W.minFrwdP = (double)c->opt.minFrwdP; W.uFlags = c->opt.uFlags;
+   const PosRef *dPos = (const PosRef *)(base + oPos);
+   const GmmTile *dTiles = (const GmmTile *)(base + oTl);
+
+   const bool tm = c->timing;
+   if (tm) cudaEventRecord(c->ev[0], c->stream);
+   // ---- K1
+   int gk = c->opt.gmmKernel;
+   if (gk == 0) gk = gmm_tc_available(c->tc) ? 2 : 1;
+   if (gk == 2) {
+      int nl = 0;
+      if ((rc = gmm_tc_launch(c->tc, c->dm, W, w.utt, c->stream, &nl))) return rc;
+      c->stats.launches += nl; c->stats.launchesGmm += nl;
+   } else if (!w.tiles.empty()) {
+      size_t smem = sizeof(float) * ((size_t)c->dm.D * GT_FR + (size_t)GT_FR * (GT_SL + 1));
+      gmm_fp32_kernel<<<(unsigned)w.tiles.size(), 128, smem, c->stream>>>(c->dm, W, dTiles);
+      c->stats.launches++; c->stats.launchesGmm++;
+   }
+   if (tm) cudaEventRecord(c->ev[1], c->stream);
+   // ---- K2 / K3
+   int nt = std::min(256, std::max(32, (w.maxQ + 31) & ~31));
+   size_t rsm = rec_smem_bytes(w.maxS, w.maxQ);
+   if (rsm > (size_t)c->maxSmemOptin) { g_lastError = "utterance too long for the shared-memory window"; return HFB_EUNSUPPORTED; }
+   const bool exact = getenv("HFBGPU_EXACT_LADD") != nullptr;
+   if (exact) beta_kernel<true><<<nU, nt, rsm, c->stream>>>(c->dm, W);
+   else beta_kernel<false><<<nU, nt, rsm, c->stream>>>(c->dm, W);
+   if (tm) cudaEventRecord(c->ev[2], c->stream);
+   if (exact) alpha_kernel<true><<<nU, nt, rsm, c->stream>>>(c->dm, W);
+   else alpha_kernel<false><<<nU, nt, rsm, c->stream>>>(c->dm, W);
+   if (tm) cudaEventRecord(c->ev[3], c->stream);
+   c->stats.launches += 2; c->stats.launchesBeta++; c->stats.launchesAlpha++;
+   // ---- K4
+   if (!w.pos.empty() && (c->opt.uFlags & (HFB_UPMEANS | HFB_UPVARS | HFB_UPMIXES))) {
+      int nPos = (int)w.pos.size();
+      stats_kernel<<<(nPos + 3) / 4, 128, 0, c->stream>>>(c->dm, W, dPos, nPos);
+      c->stats.launches++; c->stats.launchesStats++;
+   }
+   if (tm) cudaEventRecord(c->ev[4], c->stream);
+   CK(cudaGetLastError());
+
+   // ---- results back
+   if ((size_t)nU > c->hOutCap) {
+      if (c->hOut) cudaFreeHost(c->hOut);
+      c->hOutCap = (size_t)nU * 2;
+      CK(cudaMallocHost(&c->hOut, c->hOutCap * sizeof(UttOut)));
+   }
+   CK(cudaMemcpyAsync(c->hOut, W.out, (size_t)nU * sizeof(UttOut), cudaMemcpyDeviceToHost, c->stream));
+   c->stats.d2hBytes += (int64_t)nU * sizeof(UttOut);
+   const bool wantBeams = beams && (beams->qLo || beams->qHi || beams->sq || beams->eq);
+   if (wantBeams) {
+      if ((size_t)waveFrames * 4 > c->hBeamsCap) {
+         if (c->hBeams) cudaFreeHost(c->hBeams);
+         c->hBeamsCap = (size_t)waveFrames * 8;
+         CK(cudaMallocHost(&c->hBeams, c->hBeamsCap * sizeof(short)));
+      }
+      CK(cudaMemcpyAsync(c->hBeams, c->dBeams.p, (size_t)waveFrames * 4 * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
+      c->stats.d2hBytes += (int64_t)waveFrames * 8;
+   }
+   CK(cudaStreamSynchronize(c->stream));
+   if (tm) {
+      float ms;
+      cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->stats.msGmm += ms;
+      cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->stats.msBeta += ms;
+      cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->stats.msAlpha += ms;
+      cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->stats.msStats += ms;
+   }
+   for (int k = 0; k < nU; k++) {
+      hfb_utt_result &r = res[w.uttIndex[k]];
+      const UttOut &o = c->hOut[k];
+      r.status = o.status; r.retries = o.retries; r.pr = o.pr; r.pruneThresh = o.thresh;
+      const UttDesc &u = w.utt[k];
+      if (o.status == 0) c->stats.gmmPairs += (int64_t)u.T * u.J;
+      if (wantBeams) {
+         long long dst = batchFrame0 + u.frameBase + waveFrame0 - batchFrame0;   // frame index in the batch
+         const short *lo = c->hBeams + u.frameBase, *hi = lo + waveFrames, *s = hi + waveFrames, *e = s + waveFrames;
+         for (int t = 0; t < u.T; t++) {
+            bool okb = (o.status == 0 || o.status == HFB_UTT_EALPHA);
+            if (beams->qLo) beams->qLo[dst + t] = okb ? (int16_t)(lo[t] + 1) : 0;
+            if (beams->qHi) beams->qHi[dst + t] = okb ? (int16_t)(hi[t] + 1) : 0;
+            if (beams->sq) beams->sq[dst + t] = (o.status == 0) ? (int16_t)(s[t] + 1) : 0;
+            if (beams->eq) beams->eq[dst + t] = (o.status == 0) ? (int16_t)(e[t] + 1) : 0;
+            if (o.status == 0) { c->stats.betaCells += hi[t] - lo[t] + 1; c->stats.alphaCells += e[t] - s[t] + 1; }
+         }
+      }
+   }
+   return HFB_OK;
+}
+
+static int accumulate_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, const hfb_beams *beams,
+                           bool featOnDevice)
+{
+   if (!c || !b || !res) return HFB_EINVAL;
+   if (b->numUtt < 0 || (b->numUtt > 0 && (!b->frameOff || !b->feat || !b->labOff || !b->lab))) return HFB_EINVAL;
+   CK(cudaSetDevice(c->device));
+   const HostModel &h = c->hm;
+   const int D = h.D;
+   std::vector<int> slotOf((size_t)h.J, -1);
+   WaveTables w;
+   int u0 = 0;
+   while (u0 < b->numUtt) {
+      // ---- cut a wave that fits the workspace
+      w.clear();
+      const long long waveFrame0 = b->frameOff[u0];
+      size_t bytes = 0;
+      int u1 = u0;
+      while (u1 < b->numUtt) {
+         long long f0 = b->frameOff[u1], f1 = b->frameOff[u1 + 1];
+         int T = (int)(f1 - f0), Q = b->labOff[u1 + 1] - b->labOff[u1];
+         if (T > 32767 || Q > 32766) { g_lastError = "utterance beyond int16 beam range"; return HFB_EUNSUPPORTED; }
+         size_t perFrame = 0;
+         for (int q = 0; q < Q; q++) {
+            int p = b->lab[b->labOff[u1] + q];
+            int N = (p >= 0 && p < h.P) ? h.hmmN[p] : 2;
+            perFrame += (size_t)N * 8 + (size_t)(N - 2) * 12;
+         }
+         size_t need = (size_t)T * perFrame;
+         if (u1 > u0 && (bytes + need > c->workspaceBytes || u1 - u0 >= 16384)) break;
+         bytes += add_utterance(h, w, u1, T, b->lab + b->labOff[u1], Q, f0 - waveFrame0, f0 - waveFrame0, slotOf);
+         u1++;
+      }
+      const long long waveFrames = b->frameOff[u1] - waveFrame0;
+      const float *dFeat;
+      if (featOnDevice) dFeat = b->feat + (size_t)waveFrame0 * D;
+      else {
+         int rc = c->dFeat.reserve((size_t)waveFrames * D + 4);
+         if (rc) return rc;
+         CK(cudaMemcpyAsync(c->dFeat.p, b->feat + (size_t)waveFrame0 * D, (size_t)waveFrames * D * sizeof(float),
+                            cudaMemcpyHostToDevice, c->stream));
+         c->stats.h2dBytes += (int64_t)waveFrames * D * sizeof(float);
+         dFeat = c->dFeat.p;
+      }
+      int rc = run_wave(c, w, dFeat, waveFrame0, waveFrames, res, beams, 0);
+      if (rc) return rc;
+      u0 = u1;
+   }
+   return HFB_OK;
+}
+
+extern "C" int hfbgpu_accumulate(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, const hfb_beams *beams)
+{
+   return accumulate_impl(c, b, res, beams, false);
+}
+
+extern "C" int hfbgpu_accumulate_device(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, const hfb_beams *beams)
+{
+   return accumulate_impl(c, b, res, beams, true);
+}
+
+// ------------------------------------------------------------------------------------------
+// OutP alone
+// ------------------------------------------------------------------------------------------
+extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, const int32_t *states, int32_t n,
+                                   float *out, float *mixOut)
+{
+   if (!c || !feat || !states || !out || T < 1 || n < 1) return HFB_EINVAL;
+   if (mixOut) { g_lastError = "per-mixture output is not exported by the GPU path"; return HFB_EUNSUPPORTED; }
+   CK(cudaSetDevice(c->device));
+   const HostModel &h = c->hm;
+   for (int i = 0; i < n; i++) if (states[i] < 0 || states[i] >= h.J) return HFB_EINVAL;
+   WaveTables w;
+   UttDesc u;
+   memset(&u, 0, sizeof(u));
+   u.T = T; u.J = n;
+   w.utt.push_back(u);
+   w.out.push_back(UttOut{0, 0, 0.0, 0.0});
+   w.slotState.assign(states, states + n);
+   for (int t0 = 0; t0 < T; t0 += GT_FR)
+      for (int s0 = 0; s0 < n; s0 += GT_SL) w.tiles.push_back(GmmTile{0, t0, s0});
+   std::vector<unsigned char> blob;
+   size_t oUtt = blob_put(blob, w.utt), oSs = blob_put(blob, w.slotState), oTl = blob_put(blob, w.tiles);
+   int rc;
+   if ((rc = c->dTables.reserve(blob.size())) || (rc = c->dFeat.reserve((size_t)T * h.D + 4)) ||
+       (rc = c->dB.reserve((size_t)T * n + 1)))
+      return rc;
+   CK(cudaMemcpyAsync(c->dTables.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
+   CK(cudaMemcpyAsync(c->dFeat.p, feat, (size_t)T * h.D * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+   Wave W;
+   memset(&W, 0, sizeof(W));
+   W.utt = (const UttDesc *)(c->dTables.p + oUtt); W.numUtt = 1;
+   W.slotState = (const int *)(c->dTables.p + oSs);
+   W.feat = c->dFeat.p; W.b = c->dB.p;
+   int gk = c->opt.gmmKernel;
+   if (gk == 0) gk = gmm_tc_available(c->tc) ? 2 : 1;
+   if (gk == 2) {
+      int nl = 0;
+      if ((rc = gmm_tc_launch(c->tc, c->dm, W, w.utt, c->stream, &nl))) return rc;
+      c->stats.launches += nl; c->stats.launchesGmm += nl;
+   } else {
+      size_t smem = sizeof(float) * ((size_t)c->dm.D * GT_FR + (size_t)GT_FR * (GT_SL + 1));
+      gmm_fp32_kernel<<<(unsigned)w.tiles.size(), 128, smem, c->stream>>>(c->dm, W, (const GmmTile *)(c->dTables.p + oTl));
+      c->stats.launches++; c->stats.launchesGmm++;
+   }
+   CK(cudaGetLastError());
+   CK(cudaMemcpyAsync(out, c->dB.p, (size_t)T * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+   CK(cudaStreamSynchronize(c->stream));
+   return HFB_OK;
+}

@@ -1,0 +1,114 @@
+"""Host-side mirror of the reference's E-step interface, on top of the libhfbgpu C ABI.
+
+Names follow HTKLib/HFB.h so that the parity tests read like the reference's call sites:
+
+    fb = ForwardBackward(flat_model, prune=(250, 150, 1000))   # InitialiseForBack, HFB.h:117
+    results, beams = fb.FBFile(batch)                          # FBFile per utterance, HFB.h:143
+    acc = fb.GetAccs()                                         # TrAcc/WtAcc/MuAcc/VaAcc contents
+
+The compute is the CUDA library; this module only marshals numpy arrays / device pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import capi
+from .flat import Batch, Beams, FlatModel, hfb_stats, hfb_utt_result, make_options
+
+
+class UttResult(tuple):
+    """(status, retries, pr, pruneThresh)"""
+    status = property(lambda s: s[0])
+    retries = property(lambda s: s[1])
+    pr = property(lambda s: s[2])
+    pruneThresh = property(lambda s: s[3])
+
+
+class ForwardBackward:
+    def __init__(self, fm: FlatModel, prune=None, min_frwd_p: float = 10.0, uflags: int = 15,
+                 device: int = 0, gmm_kernel: int = 0, workspace_bytes: int = 0):
+        self.lib = capi.load()
+        self.fm = fm
+        self.opt = make_options(prune, min_frwd_p, uflags, device, gmm_kernel, workspace_bytes)
+        self._m = fm.c_struct()
+        h = C.c_void_p()
+        rc = self.lib.hfbgpu_create(C.byref(h), C.byref(self._m), C.byref(self.opt))
+        if rc != 0:
+            raise capi.HfbError(rc, "hfbgpu_create")
+        self.h = h
+        self.layout = fm.layout
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hfbgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- the FBFile loop over a batch ------------------------------------------------------
+    def FBFile(self, batch: Batch, want_beams: bool = False, device_feat_ptr: Optional[int] = None
+               ) -> Tuple[List[UttResult], Optional[Beams]]:
+        res = (hfb_utt_result * max(1, batch.numUtt))()
+        beams = Beams(batch.totalT) if want_beams else None
+        bs = beams.c_struct() if beams is not None else None
+        b = batch.c_struct(device_feat_ptr)
+        fn = self.lib.hfbgpu_accumulate if device_feat_ptr is None else self.lib.hfbgpu_accumulate_device
+        rc = fn(self.h, C.byref(b), res, C.byref(bs) if bs is not None else None)
+        if rc != 0:
+            raise capi.HfbError(rc, "hfbgpu_accumulate")
+        return [UttResult((r.status, r.retries, r.pr, r.pruneThresh)) for r in res[:batch.numUtt]], beams
+
+    def ZeroAccs(self):
+        rc = self.lib.hfbgpu_zero_accs(self.h)
+        if rc != 0:
+            raise capi.HfbError(rc, "hfbgpu_zero_accs")
+
+    def GetAccs(self) -> np.ndarray:
+        out = np.zeros(self.layout.count, np.float64)
+        rc = self.lib.hfbgpu_get_accs(self.h, out.ctypes.data)
+        if rc != 0:
+            raise capi.HfbError(rc, "hfbgpu_get_accs")
+        return out
+
+    def SetAccs(self, acc: np.ndarray):
+        acc = np.ascontiguousarray(acc, np.float64)
+        rc = self.lib.hfbgpu_set_accs(self.h, acc.ctypes.data)
+        if rc != 0:
+            raise capi.HfbError(rc, "hfbgpu_set_accs")
+
+    def acc_device_ptr(self) -> int:
+        return int(self.lib.hfbgpu_acc_device_ptr(self.h))
+
+    def OutP(self, feat: np.ndarray, states: np.ndarray) -> np.ndarray:
+        """log b_j(o_t) for the listed tied states (HModel.c OutP / HFB.c ShStrP)."""
+        feat = np.ascontiguousarray(feat, np.float32)
+        states = np.ascontiguousarray(states, np.int32)
+        out = np.zeros((feat.shape[0], len(states)), np.float32)
+        rc = self.lib.hfbgpu_state_loglik(self.h, feat.ctypes.data, feat.shape[0], states.ctypes.data,
+                                          len(states), out.ctypes.data, None)
+        if rc != 0:
+            raise capi.HfbError(rc, "hfbgpu_state_loglik")
+        return out
+
+    def MinDurs(self) -> np.ndarray:
+        out = np.zeros(self.fm.numTrans, np.int32)
+        self.lib.hfbgpu_get_min_durs(self.h, out.ctypes.data)
+        return out
+
+    def stats(self) -> hfb_stats:
+        s = hfb_stats()
+        self.lib.hfbgpu_get_stats(self.h, C.byref(s))
+        return s
+
+    def reset_stats(self):
+        self.lib.hfbgpu_reset_stats(self.h)
+
+    def set_timing(self, on: bool):
+        self.lib.hfbgpu_set_timing(self.h, 1 if on else 0)

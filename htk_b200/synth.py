@@ -136,3 +136,115 @@ def sample_corpus(flat, n_utts: int, T: int, Q: int, seed: int = 99, tee_index: 
         feats.append(sample_utterance(flat, lab_arr, Tu, rng))
         labs.append(lab_arr)
     return feats, labs
+
+
+# --------------------------------------------------------------------------- large sets
+
+def make_flat_tied(n_states: int = 5000, M: int = 16, n_phys: int = 8000, n_centre: int = 40, D: int = 39,
+                   seed: int = 1234, spread: float = 0.2, mix_spread: float = 0.25, self_loop: float = 0.6):
+    """Same construction as make_tied_triphone_set but straight into flat arrays (no Python
+    object per Gaussian), for the BASELINE-size sets: G = n_states * M Gaussians."""
+    from .flat import flat_from_arrays
+    rng = np.random.default_rng(seed)
+    G = n_states * M
+    centre = (spread * rng.standard_normal((n_states, 1, D))).astype(np.float32)
+    mean = (centre + mix_spread * rng.standard_normal((n_states, M, D)).astype(np.float32)).reshape(G, D)
+    var = rng.uniform(0.6, 1.6, (G, D)).astype(np.float32)
+    ivar = (np.float32(1.0) / var).astype(np.float32)
+    gconst = (np.float32(D * np.log(2 * np.pi)) + np.log(var.astype(np.float64)).sum(1)).astype(np.float32)
+    if M > 1:
+        w = rng.dirichlet(np.ones(M), size=n_states)
+        w = np.maximum(w, 1e-3)
+        w = w / w.sum(1, keepdims=True)
+    else:
+        w = np.ones((n_states, 1))
+    picks = rng.integers(0, n_states, size=(n_phys, 3))
+    cover = rng.permutation(n_states)[: min(n_states, n_phys * 3)]
+    picks.reshape(-1)[: len(cover)] = cover
+    N = 5
+    A = np.full((n_centre, N, N), -1.0e10, dtype=np.float32)
+    for c in range(n_centre):
+        sl = float(np.clip(self_loop + 0.1 * rng.standard_normal(), 0.3, 0.85))
+        A[c, 0, 1] = 0.0
+        for i in range(1, N - 1):
+            A[c, i, i] = np.float32(np.log(sl))
+            A[c, i, i + 1] = np.float32(np.log(1.0 - sl))
+    fm = flat_from_arrays(
+        D=D, mean=mean, ivar=ivar, gConst=gconst, meanId=np.arange(G), varId=np.arange(G),
+        stateMixOff=np.arange(n_states + 1) * M, mixGauss=np.arange(G),
+        mixLogWt=np.log(w).astype(np.float32).reshape(-1),
+        hmmNumStates=np.full(n_phys, N), hmmStateOff=np.arange(n_phys + 1) * 3, hmmState=picks.reshape(-1),
+        hmmTrans=np.arange(n_phys) % n_centre, transN=np.full(n_centre, N),
+        transOff=np.arange(n_centre + 1) * N * N, transLogA=A.reshape(-1),
+        names=["l%d-c%d+r%d" % (p // n_centre, p % n_centre, p) for p in range(n_phys)])
+    fm.var = var
+    return fm
+
+
+def make_flat_mono(n_phones: int = 40, M: int = 1, D: int = 39, seed: int = 1234, spread: float = 0.2,
+                   mix_spread: float = 0.25):
+    """Config #2: plain monophones, 3 emitting states, M Gaussians per state."""
+    fm = make_flat_tied(n_states=3 * n_phones, M=M, n_phys=n_phones, n_centre=n_phones, D=D, seed=seed,
+                        spread=spread, mix_spread=mix_spread)
+    fm.hmmState[:] = np.arange(3 * n_phones)
+    fm.names = ["p%02d" % p for p in range(n_phones)]
+    return fm
+
+
+def write_flat_as_mmf(path: str, list_path: str, fm, parm_kind: str = "MFCC_0_D_A") -> None:
+    """Text MMF + HMM list for a make_flat_* set (5-state models, tied states / transitions),
+    so the unmodified reference HERest can load the very same model."""
+    D = fm.D
+    var = getattr(fm, "var", None)
+    if var is None:
+        var = (1.0 / fm.ivar.astype(np.float64)).astype(np.float32)
+    with open(path, "w") as f:
+        f.write("~o\n<STREAMINFO> 1 %d\n<VECSIZE> %d<NULLD><%s><DIAGC>\n" % (D, D, parm_kind))
+        for c in range(fm.numTrans):
+            N = int(fm.transN[c])
+            A = fm.transLogA[fm.transOff[c]:fm.transOff[c + 1]].reshape(N, N).astype(np.float64)
+            P = np.where(A > -0.5e10, np.exp(A), 0.0)
+            f.write('~t "T_%d"\n<TRANSP> %d\n' % (c, N))
+            for i in range(N):
+                f.write(" " + " ".join("%.6e" % x for x in P[i]) + "\n")
+        for s in range(fm.J):
+            o, e = int(fm.stateMixOff[s]), int(fm.stateMixOff[s + 1])
+            f.write('~s "ST_%d"\n' % s)
+            if e - o > 1:
+                f.write("<NUMMIXES> %d\n" % (e - o))
+            for m in range(o, e):
+                g = int(fm.mixGauss[m])
+                if e - o > 1:
+                    f.write("<MIXTURE> %d %.6e\n" % (m - o + 1, float(np.exp(fm.mixLogWt[m]))))
+                f.write("<MEAN> %d\n " % D + " ".join("%.6e" % x for x in fm.mean[g]) + "\n")
+                f.write("<VARIANCE> %d\n " % D + " ".join("%.6e" % x for x in var[g]) + "\n")
+        for p in range(fm.P):
+            N = int(fm.hmmNumStates[p])
+            f.write('~h "%s"\n<BEGINHMM>\n<NUMSTATES> %d\n' % (fm.names[p], N))
+            for j in range(N - 2):
+                f.write('<STATE> %d\n~s "ST_%d"\n' % (j + 2, int(fm.hmmState[fm.hmmStateOff[p] + j])))
+            f.write('~t "T_%d"\n<ENDHMM>\n' % int(fm.hmmTrans[p]))
+    with open(list_path, "w") as f:
+        f.write("\n".join(fm.names) + "\n")
+
+
+def corpus_plan(fm, n_utts: int, T: int, Q: int, seed: int):
+    """Labels and the per-frame (state, mixture-component) plan of a synthetic corpus:
+    returns (lab[n_utts, Q] int32, gauss_of_frame[n_utts*T] int64)."""
+    rng = np.random.default_rng(seed)
+    lab = rng.integers(0, fm.P, size=(n_utts, Q)).astype(np.int32)
+    n = 3 * Q
+    states = fm.hmmState.reshape(fm.P, 3)[lab].reshape(n_utts, n)          # [U, 3Q]
+    # random composition of T into n positive parts
+    cuts = np.sort(rng.random((n_utts, n - 1)), axis=1)
+    edges = np.concatenate([np.zeros((n_utts, 1)), cuts, np.ones((n_utts, 1))], axis=1)
+    durs = np.diff(np.floor(edges * (T - n)).astype(np.int64), axis=1) + 1
+    durs[:, -1] += T - durs.sum(1)
+    st_of_t = np.repeat(states.reshape(-1), durs.reshape(-1))
+    Mn = int(fm.stateMixOff[1] - fm.stateMixOff[0])
+    w = np.exp(fm.mixLogWt.astype(np.float64)).reshape(fm.J, Mn)
+    cdf = np.cumsum(w, axis=1)
+    u = rng.random(len(st_of_t))
+    comp = (u[:, None] > cdf[st_of_t]).sum(1).clip(0, Mn - 1)
+    gauss = fm.mixGauss[fm.stateMixOff[st_of_t] + comp]
+    return lab, gauss.astype(np.int64)

@@ -175,8 +175,9 @@ int hfbgpu_accumulate(hfbgpu_ctx *ctx, const hfb_batch *batch,
                       hfb_utt_result *res, const hfb_beams *beams);
 
 /* Same, but batch->feat is a DEVICE pointer already resident in HBM (the other
- * arrays stay on the host).  `stream` is a cudaStream_t (NULL = library stream).
- * Results stay on the device until hfbgpu_sync_results().                         */
+ * arrays stay on the host).  The caller must have finished writing the features
+ * (synchronise its own stream) before the call; the call returns after the results
+ * have been copied back.                                                            */
 int hfbgpu_accumulate_device(hfbgpu_ctx *ctx, const hfb_batch *batch,
                              hfb_utt_result *res, const hfb_beams *beams);
 

@@ -1,0 +1,211 @@
+"""Parity of the CUDA path (through the libhfbgpu C ABI) with the reference.
+
+Three kinds of evidence:
+  * golden fixtures produced by the reference's own HERest (tests/golden/*.npz);
+  * the CPU oracle (pinned bit-exact to those fixtures) on the same seeded inputs;
+  * size-independent properties at larger sizes (occupancies sum to T, batch linearity,
+    idempotence of zeroing, transition counts vs state occupancies).
+
+Tolerances (BASELINE.json north_star): log-likelihoods, occupancies and accumulators within
+1e-4 relative; pruned-frame sets identical except for counted beam-boundary ties.
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, acc_errors, load_golden
+from htk_b200.flat import Batch, make_options
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def _fb(fm, **kw):
+    from htk_b200.estep import ForwardBackward
+    return ForwardBackward(fm, **kw)
+
+
+def _oracle(fm, b, kw, acc_double=True):
+    from oracle import oracle_lib as O
+    return O.accumulate(fm, make_options(**kw), b, acc_double=acc_double)
+
+
+@pytest.mark.parametrize("gmm_kernel", [1, 2])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_accumulators_and_beams(name, gmm_kernel):
+    z, fm, b, kw = load_golden(name)
+    try:
+        fb = _fb(fm, gmm_kernel=gmm_kernel, **kw)
+    except Exception as e:
+        if gmm_kernel == 2 and getattr(e, "code", 0) == -5:
+            pytest.skip("tcgen05 path not built")
+        raise
+    res, beams = fb.FBFile(b, want_beams=True)
+    acc = fb.GetAccs()
+    ref = z["ref_acc"]
+    T = np.diff(z["frameOff"])
+    n_ok = 0
+    for r, t, rpf, rthr, rret in zip(res, T, z["ref_pr_per_frame"], z["ref_thresh"], z["ref_retries"]):
+        if np.isnan(rpf):
+            assert r.status == 7324
+            continue
+        assert r.status == 0
+        n_ok += 1
+        assert abs(r.pr / t - rpf) <= RTOL * abs(rpf) + 1e-6      # reference prints 7 digits
+        assert r.pruneThresh == rthr and r.retries == rret
+    L = fm.layout
+    assert acc[L.numOk] == n_ok and acc[L.numSkipped] == len(res) - n_ok
+    e = acc_errors(acc, ref, fm)
+    assert max(e.values()) < RTOL, e
+    if bool(z["have_beams"]):
+        ties = 0
+        total = 0
+        for k, a in (("qLo", beams.qLo), ("qHi", beams.qHi), ("sq", beams.sq), ("eq", beams.eq)):
+            r = z["ref_" + k]
+            m = r > 0
+            total += int(m.sum())
+            ties += int(np.sum(a[m] != r[m]))
+        # identical pruned-frame sets except counted beam-boundary ties
+        assert ties <= max(1, total // 2000), "beam mismatches: %d of %d" % (ties, total)
+    fb.close()
+
+
+@pytest.mark.parametrize("name", ["synth_tee_m2", "synth_tied_m4"])
+def test_against_oracle_fp64(name):
+    """Same inputs through the oracle with FP64 accumulators: tighter than the float dump."""
+    z, fm, b, kw = load_golden(name)
+    fb = _fb(fm, **kw)
+    res, beams = fb.FBFile(b, want_beams=True)
+    acc = fb.GetAccs()
+    oacc, ores, obeams = _oracle(fm, b, kw)
+    for r, o in zip(res, ores):
+        assert r.status == o[0]
+        if o[0] == 0:
+            assert abs(r.pr - o[2]) <= 1e-6 * abs(o[2])
+            assert r.pruneThresh == o[3]
+    e = acc_errors(acc, oacc, fm)
+    assert max(e.values()) < RTOL, e
+    assert np.array_equal(beams.qLo, obeams.qLo) and np.array_equal(beams.qHi, obeams.qHi)
+    assert np.array_equal(beams.sq, obeams.sq) and np.array_equal(beams.eq, obeams.eq)
+    fb.close()
+
+
+@pytest.mark.parametrize("gmm_kernel", [1, 2])
+def test_outp_matches_oracle(gmm_kernel):
+    from oracle import oracle_lib as O
+    for name in ("htkdemo_t2000", "synth_tied_m4"):
+        z, fm, b, kw = load_golden(name)
+        try:
+            fb = _fb(fm, gmm_kernel=gmm_kernel, **kw)
+        except Exception as e:
+            if gmm_kernel == 2 and getattr(e, "code", 0) == -5:
+                pytest.skip("tcgen05 path not built")
+            raise
+        feat = z["feat"][:300]
+        states = np.arange(fm.J, dtype=np.int32)
+        got = fb.OutP(feat, states)
+        want = O.state_loglik(fm, feat, states)
+        # absolute error of a log-likelihood of magnitude ~60-100 (float eps there is ~8e-6)
+        assert np.max(np.abs(got - want)) < 2e-4, np.max(np.abs(got - want))
+        assert np.max(np.abs(got - want) / np.abs(want)) < 1e-5
+        fb.close()
+
+
+def test_update_flags_and_zero():
+    z, fm, b, kw = load_golden("synth_tied_m4")
+    L = fm.layout
+    for uf in (1, 2, 4, 8, 3, 15):
+        kw2 = dict(kw); kw2["uflags"] = uf
+        fb = _fb(fm, **kw2)
+        fb.FBFile(b)
+        acc = fb.GetAccs()
+        oacc, _, _ = _oracle(fm, b, kw2)
+        e = acc_errors(acc, oacc, fm)
+        assert max(e.values()) < RTOL, (uf, e)
+        if not uf & 4:
+            assert np.all(acc[L.tran:L.wtC] == 0)
+        if not uf & 1:
+            assert np.all(acc[L.muSum:L.vaSum] == 0)
+        fb.ZeroAccs()
+        assert np.all(fb.GetAccs() == 0)
+        fb.close()
+
+
+def test_batch_linearity_and_empty():
+    """acc(batch A + batch B) == acc(A) + acc(B); an empty batch is a no-op."""
+    z, fm, b, kw = load_golden("synth_mono_m1")
+    fo, lo = z["frameOff"], z["labOff"]
+    fb = _fb(fm, **kw)
+    fb.FBFile(b)
+    whole = fb.GetAccs()
+    fb.ZeroAccs()
+    k = 3
+    bA = Batch.from_arrays(z["feat"], fo[:k + 1], z["lab"], lo[:k + 1])
+    bB = Batch.from_arrays(z["feat"], fo[k:], z["lab"], lo[k:])
+    fb.FBFile(bA); fb.FBFile(bB)
+    parts = fb.GetAccs()
+    assert np.allclose(whole, parts, rtol=1e-9, atol=1e-9)
+    empty = Batch([], [], fm.D)
+    r, _ = fb.FBFile(empty)
+    assert r == [] and np.array_equal(parts, fb.GetAccs())
+    fb.close()
+
+
+def test_small_workspace_waves_equal_single_wave():
+    z, fm, b, kw = load_golden("synth_tied_m4")
+    fb = _fb(fm, **kw); fb.FBFile(b); a1 = fb.GetAccs(); fb.close()
+    fb = _fb(fm, workspace_bytes=3 << 20, **kw); fb.FBFile(b); a2 = fb.GetAccs(); fb.close()
+    assert np.allclose(a1, a2, rtol=1e-9, atol=1e-9)
+
+
+def test_properties_at_scale():
+    """Config-#3-shaped workload at a size the oracle would take minutes on: check the
+    invariants the domain offers instead."""
+    from htk_b200 import synth
+    from htk_b200.flat import flatten
+    hs = synth.make_tied_triphone_set(n_states=600, M=8, n_phys=400, n_logical=400, n_centre=20, seed=21, spread=0.2)
+    fm = flatten(hs)
+    feats, labs = synth.sample_corpus(fm, n_utts=24, T=600, Q=60, seed=3)
+    b = Batch(feats, labs, fm.D)
+    fb = _fb(fm)
+    res, _ = fb.FBFile(b)
+    acc = fb.GetAccs()
+    L = fm.layout
+    assert all(r.status == 0 for r in res)
+    T = b.totalT
+    assert acc[L.totalT] == T
+    # every frame distributes one unit of occupancy over emitting states (minus what the
+    # minimum-occupancy rule drops, < e^-10 per component)
+    assert abs(acc[L.wtOcc:L.muSum].sum() - T) < 2e-3 * T
+    assert abs(acc[L.muOcc:L.vaSum].sum() - acc[L.wtOcc:L.muSum].sum()) < 1e-6 * T
+    assert abs(acc[L.wtC:L.wtOcc].sum() - acc[L.wtOcc:L.muSum].sum()) < 1e-6 * T
+    # second-order sums are non-negative
+    assert acc[L.vaSum:L.vaOcc].min() >= 0.0
+    # each model instance is entered and left exactly once per utterance
+    N = 5
+    tr = acc[L.tran:L.tranOcc].reshape(-1, N, N)
+    n_inst = sum(len(l) for l in labs)
+    assert abs(tr[:, 0, 1:].sum() - n_inst) < 1e-3 * n_inst
+    assert abs(tr[:, 1:N - 1, N - 1].sum() - n_inst) < 1e-3 * n_inst
+    assert acc[L.numEgs:L.totalT].sum() == n_inst
+    # total log-likelihood equals the sum of per-utterance values
+    assert abs(acc[L.totalPr] - sum(r.pr for r in res)) < 1e-6 * abs(acc[L.totalPr])
+    # against the oracle on a 4-utterance subset
+    sub = Batch(feats[:4], labs[:4], fm.D)
+    fb.ZeroAccs(); fb.FBFile(sub); a = fb.GetAccs()
+    oacc, ores, _ = _oracle(fm, sub, dict(prune=None))
+    e = acc_errors(a, oacc, fm)
+    assert max(e.values()) < RTOL, e
+    fb.close()
+
+
+def test_exact_ladd_env(monkeypatch):
+    """FP64 exp/log in every log-add (HFBGPU_EXACT_LADD) vs the FP32 correction term."""
+    z, fm, b, kw = load_golden("htkdemo_t20_15_200")
+    fb = _fb(fm, **kw); r1, _ = fb.FBFile(b); a1 = fb.GetAccs(); fb.close()
+    monkeypatch.setenv("HFBGPU_EXACT_LADD", "1")
+    fb = _fb(fm, **kw); r2, _ = fb.FBFile(b); a2 = fb.GetAccs(); fb.close()
+    for x, y in zip(r1, r2):
+        assert abs(x.pr - y.pr) < 1e-4
+    e = acc_errors(a1, a2, fm)
+    assert max(e.values()) < 2e-5, e

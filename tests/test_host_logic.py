@@ -1,0 +1,120 @@
+"""Host-side logic that needs no GPU: file formats, flattening, the C-ABI library loading
+and exporting every symbol include/hfbgpu.h declares."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from htk_b200 import htkio, synth
+from htk_b200.flat import flatten, hfb_acc_layout
+
+
+def test_feature_file_roundtrip(tmp_path):
+    x = np.random.default_rng(0).standard_normal((17, 39)).astype(np.float32)
+    p = str(tmp_path / "a.mfc")
+    htkio.write_htk_features(p, x, "MFCC_0_D_A")
+    y, period, kind = htkio.read_htk_features(p)
+    assert np.array_equal(x, y) and period == 100000 and kind == 0o21406 - 0o20000 + 0o20000
+
+
+def test_mmf_roundtrip_and_flatten(tmp_path):
+    hs = synth.make_tied_triphone_set(n_states=20, M=3, n_phys=12, n_logical=20, n_centre=4, seed=3)
+    p = str(tmp_path / "mmf")
+    htkio.write_mmf(p, hs)
+    htkio.write_hmm_list(str(tmp_path / "list"), hs)
+    hs2 = htkio.read_mmf([p], hmm_list=open(str(tmp_path / "list")).read().splitlines())
+    f1, f2 = flatten(hs), flatten(hs2)
+    assert f1.J == f2.J == 20 and f1.G == f2.G == 60 and f1.P == f2.P == 12 and f1.numTrans == f2.numTrans == 4
+    assert np.allclose(f1.mean, f2.mean, rtol=1e-6, atol=1e-6)
+    assert np.array_equal(f1.hmmState, f2.hmmState) and np.array_equal(f1.hmmTrans, f2.hmmTrans)
+    assert len(hs2.logical) == 8
+    # log transitions: absent arcs are LZERO, rows of emitting states normalise
+    A = f1.transLogA[:25].reshape(5, 5)
+    assert A[0, 0] == np.float32(-1e10) and abs(np.exp(A[1, 1]) + np.exp(A[1, 2]) - 1) < 1e-6
+
+
+def test_gconst_and_logweights():
+    hs = synth.make_monophone_set(n_phones=2, M=2, seed=1)
+    fm = flatten(hs)
+    g = hs.hmms[0].states[0].mixes[0][1]
+    want = 39 * np.log(2 * np.pi) + np.sum(np.log(g.var.astype(np.float64)))
+    assert abs(fm.gConst[0] - want) < 1e-4
+    assert np.allclose(fm.ivar[0], 1.0 / g.var, rtol=1e-6)
+    w = hs.hmms[0].states[0].mixes[0][0]
+    assert abs(fm.mixLogWt[0] - np.log(w)) < 1e-6
+
+
+def test_scan_order_is_hash_order():
+    names = ["S", "C", "V", "N", "L"]
+    order = htkio.scan_order(names)
+    assert sorted(order) == sorted(names)
+    assert [htkio.htk_hash(n) for n in order] == sorted(htkio.htk_hash(n) for n in names)
+
+
+def test_acc_dump_roundtrip(tmp_path):
+    hs = synth.make_tied_triphone_set(n_states=10, M=2, n_phys=6, n_logical=6, n_centre=2, seed=4)
+    fm = flatten(hs)
+    rng = np.random.default_rng(1)
+    acc = rng.random(fm.layout.count) * 10
+    acc[fm.layout.numEgs:fm.layout.totalT] = rng.integers(0, 50, fm.P)
+    acc[fm.layout.totalT] = 1234
+    acc[fm.layout.numOk] = acc[fm.layout.numSkipped] = 0
+    p = str(tmp_path / "HER1.acc")
+    htkio.write_acc_dump(p, hs, fm, acc)
+    back, tp, tt = htkio.read_acc_dump(p, hs, fm)
+    assert tt == 1234
+    assert np.allclose(back[:fm.layout.numOk], acc[:fm.layout.numOk].astype(np.float32), rtol=1e-7)
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "hfbgpu.h")).read()
+    return sorted(set(re.findall(r"\b(hfbgpu_[a-z_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from htk_b200 import capi
+    lib = capi.load()
+    syms = _declared_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert set(syms) == set(capi.EXPORTS)
+    assert lib.hfbgpu_abi_version() == 1
+
+
+def test_layout_agrees_between_library_and_python():
+    from htk_b200 import capi
+    lib = capi.load()
+    for name in ("htkdemo_t2000", "synth_tied_m4"):
+        z, fm, b, kw = load_golden(name)
+        L = hfb_acc_layout()
+        m = fm.c_struct()
+        assert lib.hfbgpu_acc_layout(C.byref(m), C.byref(L)) == 0
+        for k in ("tran", "tranOcc", "wtC", "wtOcc", "muSum", "muOcc", "vaSum", "vaOcc", "numEgs", "totalT",
+                  "totalPr", "numOk", "numSkipped", "count"):
+            assert getattr(L, k) == getattr(fm.layout, k), k
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a GPU, create must fail loudly with HFB_ENODEVICE -- never compute on the CPU."""
+    from htk_b200 import capi
+    lib = capi.load()
+    if lib.hfbgpu_device_count() > 0:
+        pytest.skip("a device is present")
+    from htk_b200.estep import ForwardBackward
+    z, fm, b, kw = load_golden("htkdemo_t2000")
+    with pytest.raises(capi.HfbError) as e:
+        ForwardBackward(fm, **kw)
+    assert e.value.code == -2
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "htk_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".c")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle_lib" not in txt and "hfb_oracle" not in txt and "libhfboracle" not in txt, f
