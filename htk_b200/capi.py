@@ -19,7 +19,7 @@ EXPORTS = [
     "hfbgpu_last_error", "hfbgpu_device_count", "hfbgpu_create", "hfbgpu_destroy", "hfbgpu_zero_accs",
     "hfbgpu_accumulate", "hfbgpu_accumulate_device", "hfbgpu_acc_device_ptr", "hfbgpu_acc_count",
     "hfbgpu_get_accs", "hfbgpu_set_accs", "hfbgpu_state_loglik", "hfbgpu_get_min_durs",
-    "hfbgpu_get_stats", "hfbgpu_reset_stats", "hfbgpu_set_timing",
+    "hfbgpu_get_stats", "hfbgpu_reset_stats", "hfbgpu_set_timing", "hfbgpu_set_stream",
 ]
 
 _lib = None
@@ -67,5 +67,6 @@ def load():
     l.hfbgpu_get_stats.argtypes = [vp, C.POINTER(hfb_stats)]
     l.hfbgpu_reset_stats.argtypes = [vp]
     l.hfbgpu_set_timing.argtypes = [vp, C.c_int]
+    l.hfbgpu_set_stream.argtypes = [vp, vp]
     _lib = l
     return l

@@ -72,6 +72,7 @@ struct hfbgpu_ctx {
    DevModel dm;
    hfb_acc_layout L;
    cudaStream_t stream = nullptr;
+   cudaStream_t ownStream = nullptr;
    cudaEvent_t ev[8] = {};
    bool timing = false;
    hfb_stats stats;
@@ -219,7 +220,8 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
    CK(cudaGetDeviceProperties(&prop, c->device));
    c->smCount = prop.multiProcessorCount;
    c->maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
-   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+   CK(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
+   c->stream = c->ownStream;
    for (auto &e : c->ev) CK(cudaEventCreate(&e));
 
    HostModel &h = c->hm;
@@ -320,8 +322,17 @@ extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
    if (c->hOut) cudaFreeHost(c->hOut);
    if (c->hBeams) cudaFreeHost(c->hBeams);
    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
-   if (c->stream) cudaStreamDestroy(c->stream);
+   if (c->ownStream) cudaStreamDestroy(c->ownStream);
    delete c;
+   return HFB_OK;
+}
+
+extern "C" int hfbgpu_set_stream(hfbgpu_ctx *c, void *st)
+{
+   if (!c) return HFB_EINVAL;
+   CK(cudaSetDevice(c->device));
+   CK(cudaStreamSynchronize(c->stream));
+   c->stream = st ? (cudaStream_t)st : c->ownStream;
    return HFB_OK;
 }
 

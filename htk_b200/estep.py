@@ -110,5 +110,24 @@ class ForwardBackward:
     def reset_stats(self):
         self.lib.hfbgpu_reset_stats(self.h)
 
+    def set_stream(self, cuda_stream_handle: int):
+        rc = self.lib.hfbgpu_set_stream(self.h, C.c_void_p(cuda_stream_handle))
+        if rc != 0:
+            raise capi.HfbError(rc, "hfbgpu_set_stream")
+
+    def acc_tensor(self):
+        """The resident FP64 accumulator buffer as a torch CUDA tensor (no copy), for the
+        per-pass NCCL all-reduce (torch.distributed is plumbing, the buffer is the library's)."""
+        import torch
+
+        class _Wrap:
+            pass
+        w = _Wrap()
+        w.__cuda_array_interface__ = {"shape": (int(self.layout.count),), "typestr": "<f8",
+                                      "data": (self.acc_device_ptr(), False), "version": 2}
+        t = torch.as_tensor(w, device="cuda:%d" % self.opt.device)
+        t._hfb_owner = self
+        return t
+
     def set_timing(self, on: bool):
         self.lib.hfbgpu_set_timing(self.h, 1 if on else 0)

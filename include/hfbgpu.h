@@ -165,6 +165,10 @@ int  hfbgpu_device_count(void);
 int hfbgpu_create(hfbgpu_ctx **ctx, const hfb_model *m, const hfb_options *opt);
 int hfbgpu_destroy(hfbgpu_ctx *ctx);
 
+/* Run on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream) instead
+ * of the library's own, so the caller's events bracket the kernels.  NULL restores it. */
+int hfbgpu_set_stream(hfbgpu_ctx *ctx, void *cudaStream);
+
 /* ZeroAccs (HTrain.c:1072). */
 int hfbgpu_zero_accs(hfbgpu_ctx *ctx);
 
