@@ -1,16 +1,482 @@
-// gmm_tc.cuh -- tcgen05 (5th-gen tensor core) GMM log-likelihood path.  Placeholder
-// interface; the kernel lands in a later commit.  Until then gmm_tc_available() is false
-// and the FP32 CUDA-core kernel is the one that runs.
+// gmm_tc.cuh -- K1 on the 5th-generation tensor cores: GMM log-likelihoods as a dense
+// contraction  [x'^2, x', 1] (frames)  x  [-ivar/2, mu'*ivar, c] (mixture components)
+// with a 3xTF32 split and FP32 accumulation in TMEM, operands staged by TMA, and the
+// log-sum-exp over each state's mixtures fused into the TMEM epilogue.
+//
+// Replaces, for every (frame, distinct tied state) of an utterance, MOutP/IDOutP
+// (HTKLib/HModel.c:5484-5499, :5420-5431) and the mixture log-add of ShStrP
+// (HTKLib/HFB.c:949-960).
+//
+// Precision (stated choice): each FP32 operand v is split v = hi + lo with hi, lo exactly
+// representable in TF32 (cvt.rna.tf32.f32); the product is evaluated as
+// hi*hi + hi*lo + lo*hi -- three tcgen05.mma.kind::tf32 per K step -- and accumulated in
+// FP32.  The dropped lo*lo term is ~2^-22 relative.  Features and means are shifted by the
+// mean of the Gaussian means (x' = x - o, mu' = mu - o) to keep the x'^2 terms small.
+//
+// Tiling: one work item = (utterance, 128 consecutive frames).  The item's A operand
+// (128 x 96 floats, hi and lo = 96 KB) stays resident in shared memory while the B operand
+// of the utterance's states streams through a 3-stage TMA ring in [128 components x 32
+// floats] x {hi, lo} blocks (32 KB per stage).  Accumulators are double-buffered in TMEM
+// (2 x 128 columns) so the epilogue of tile n overlaps the MMAs of tile n+1.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 epilogue.
 #pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+#include <algorithm>
 #include <vector>
 #include "hfb_common.h"
 
+#define TC_KE 96            // expanded K, 2D+1 padded to 3 swizzle atoms of 32 floats
+#define TC_BM 128           // frames per work item (UMMA M)
+#define TC_BN 128           // mixture components per tile (UMMA N)
+#define TC_STAGES 3
+#define TC_A_BYTES (6 * 16384)
+#define TC_B_STAGE_BYTES 32768
+#define TC_SMEM_BYTES (TC_A_BYTES + TC_STAGES * TC_B_STAGE_BYTES + 256 + 1024)
+#define TC_NEG_BIG (-1.0e30f)
+
 struct GmmTcModel {
    bool ready = false;
+   int MP = 0;                 // mixture rows per state, padded to a power of two >= 8
+   int GPS = 0;                // 8-row groups per state = MP / 8
+   long long rows = 0;         // rows in Bhi/Blo (row group 0 is the all-"-inf" dummy)
+   float *dBhi = nullptr, *dBlo = nullptr, *dOffset = nullptr;
+   float *dAhi = nullptr, *dAlo = nullptr;
+   size_t aCapFrames = 0;
+   CUtensorMap mapBhi, mapBlo;
+   void *encodeFn = nullptr;
 };
 
-static inline int gmm_tc_prepare(GmmTcModel &, const hfb_model *, cudaStream_t) { return HFB_OK; }
-static inline void gmm_tc_release(GmmTcModel &) {}
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tc_mbar_init(uint64_t *bar, uint32_t count)
+{
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t *bar)
+{
+   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+   uint32_t done, addr = tc_smem_u32(bar);
+   do {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                   "selp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+   } while (!done);
+}
+__device__ __forceinline__ void tc_tma_load_2d(void *smemDst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
+{
+   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                ::"r"(tc_smem_u32(smemDst)), "l"((uint64_t)map), "r"(tc_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
+{
+   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                ::"r"(tmemD), "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, float *v)
+{
+   uint32_t *r = reinterpret_cast<uint32_t *>(v);
+   asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled operand block of [rows][32 floats]: 8-row groups 1024 B apart.
+// Field layout: cute::UMMA::SmemDescriptor (start>>4 | LBO<<16 | SBO<<32 | version=1<<46 | SWIZZLE_128B=2<<61).
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smemAddr)
+{
+   return (uint64_t)((smemAddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format TF32 (2<<7, 2<<10), K-major A and B,
+// n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24.
+__device__ __forceinline__ constexpr uint32_t tc_idesc(int M, int N)
+{
+   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float tc_tf32(float x)
+{
+   uint32_t r;
+   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+   return __uint_as_float(r);
+}
+
+// ------------------------------------------------------------------------------------------
+// feature expansion: A'hi / A'lo [frames][96] = split of [ (x-o)^2 | (x-o) | 1 | 0... ]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gmm_tc_expand_kernel(const float *__restrict__ feat, const float *__restrict__ off, int D, long long nFrames,
+                     float *__restrict__ Ahi, float *__restrict__ Alo)
+{
+   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (idx >= nFrames * TC_KE) return;
+   long long f = idx / TC_KE;
+   int k = (int)(idx - f * TC_KE);
+   float v = 0.f;
+   if (k < D) { float x = feat[f * D + k] - off[k]; v = x * x; }
+   else if (k < 2 * D) v = feat[f * D + (k - D)] - off[k - D];
+   else if (k == 2 * D) v = 1.f;
+   float hi = tc_tf32(v);
+   Ahi[idx] = hi;
+   Alo[idx] = tc_tf32(v - hi);
+}
+
+// ------------------------------------------------------------------------------------------
+// the GEMM + log-sum-exp kernel
+// ------------------------------------------------------------------------------------------
+struct TcParams {
+   const int2 *items;          // (utterance in wave, first frame of the 128-frame block)
+   int nItems;
+   const UttDesc *utt;
+   const int *slotState;
+   float *b;
+   int GPS;                    // 8-row groups per state
+};
+
+template <int MP>
+__global__ void __launch_bounds__(192, 1)
+gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+              const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, TcParams p)
+{
+   extern __shared__ uint8_t tc_smem_raw[];
+   uint8_t *base = (uint8_t *)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+   uint8_t *sA = base;                                  // [hi k0,k1,k2 | lo k0,k1,k2] x 16 KB
+   uint8_t *sB = base + TC_A_BYTES;                     // stages x [hi 16 KB | lo 16 KB]
+   uint64_t *bars = (uint64_t *)(sB + TC_STAGES * TC_B_STAGE_BYTES);
+   uint64_t *fullA = bars, *emptyA = bars + 1, *fullB = bars + 2, *emptyB = bars + 2 + TC_STAGES;
+   uint64_t *tmemFull = bars + 2 + 2 * TC_STAGES, *tmemEmpty = tmemFull + 2;
+   uint32_t *tmemSlot = (uint32_t *)(tmemEmpty + 2);
+   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+   if (warp == 0 && lane == 0) {
+      tc_mbar_init(fullA, 1); tc_mbar_init(emptyA, 1);
+      for (int s = 0; s < TC_STAGES; s++) { tc_mbar_init(&fullB[s], 1); tc_mbar_init(&emptyB[s], 1); }
+      for (int s = 0; s < 2; s++) { tc_mbar_init(&tmemFull[s], 1); tc_mbar_init(&tmemEmpty[s], 4); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   if (warp == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmemSlot)), "r"(256) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+   }
+   tc_fence_before();
+   __syncthreads();
+   tc_fence_after();
+   const uint32_t tmem = *tmemSlot;
+   constexpr int SPT = TC_BN / MP;                      // states per tile
+   constexpr int GPS = MP / 8;
+
+   if (warp == 0) {
+      // ================= TMA producer =================
+      if (lane == 0) {
+         uint32_t stage = 0, phB = 0, phA = 0;
+         for (int it = blockIdx.x; it < p.nItems; it += gridDim.x) {
+            const int2 item = p.items[it];
+            const UttDesc u = p.utt[item.x];
+            const int row0 = (int)u.featOff + item.y;
+            tc_mbar_wait(emptyA, phA ^ 1);
+            tc_mbar_expect_tx(fullA, TC_A_BYTES);
+            for (int k = 0; k < 3; k++) {
+               tc_tma_load_2d(sA + k * 16384, &mapAhi, fullA, k * 32, row0);
+               tc_tma_load_2d(sA + (3 + k) * 16384, &mapAlo, fullA, k * 32, row0);
+            }
+            phA ^= 1;
+            const int nTiles = (u.J + SPT - 1) / SPT;
+            const int *ss = p.slotState + u.slotOff;
+            for (int n = 0; n < nTiles; n++) {
+               int rows[TC_BN / 8];
+#pragma unroll
+               for (int g = 0; g < TC_BN / 8; g++) {
+                  int slot = n * SPT + g / GPS;
+                  rows[g] = (slot < u.J) ? (1 + ss[slot] * GPS + (g % GPS)) * 8 : 0;
+               }
+               for (int k = 0; k < 3; k++) {
+                  tc_mbar_wait(&emptyB[stage], phB ^ 1);
+                  tc_mbar_expect_tx(&fullB[stage], TC_B_STAGE_BYTES);
+                  uint8_t *dst = sB + stage * TC_B_STAGE_BYTES;
+#pragma unroll
+                  for (int g = 0; g < TC_BN / 8; g++) {
+                     tc_tma_load_2d(dst + g * 1024, &mapBhi, &fullB[stage], k * 32, rows[g]);
+                     tc_tma_load_2d(dst + 16384 + g * 1024, &mapBlo, &fullB[stage], k * 32, rows[g]);
+                  }
+                  if (++stage == TC_STAGES) { stage = 0; phB ^= 1; }
+               }
+            }
+         }
+      }
+   } else if (warp == 1) {
+      // ================= MMA issuer =================
+      if (lane == 0) {
+         const uint32_t idesc = tc_idesc(TC_BM, TC_BN);
+         const uint32_t aBase = tc_smem_u32(sA), bBase = tc_smem_u32(sB);
+         uint32_t stage = 0, phB = 0, phA = 0, tile = 0;
+         for (int it = blockIdx.x; it < p.nItems; it += gridDim.x) {
+            const int2 item = p.items[it];
+            const UttDesc u = p.utt[item.x];
+            const int nTiles = (u.J + SPT - 1) / SPT;
+            tc_mbar_wait(fullA, phA);
+            phA ^= 1;
+            for (int n = 0; n < nTiles; n++, tile++) {
+               const uint32_t as = tile & 1, phT = (tile >> 1) & 1;
+               tc_mbar_wait(&tmemEmpty[as], phT ^ 1);
+               tc_fence_after();
+               const uint32_t dAddr = tmem + as * TC_BN;
+               for (int k = 0; k < 3; k++) {
+                  tc_mbar_wait(&fullB[stage], phB);
+                  tc_fence_after();
+                  const uint32_t bHi = bBase + stage * TC_B_STAGE_BYTES, bLo = bHi + 16384;
+                  const uint32_t aHi = aBase + k * 16384, aLo = aBase + (3 + k) * 16384;
+#pragma unroll
+                  for (int kk = 0; kk < 4; kk++) {
+                     const uint64_t dAhi = tc_smem_desc(aHi + kk * 32), dAlo = tc_smem_desc(aLo + kk * 32);
+                     const uint64_t dBhi = tc_smem_desc(bHi + kk * 32), dBlo = tc_smem_desc(bLo + kk * 32);
+                     tc_mma_tf32(dAddr, dAhi, dBhi, idesc, (k | kk) ? 1u : 0u);
+                     tc_mma_tf32(dAddr, dAhi, dBlo, idesc, 1u);
+                     tc_mma_tf32(dAddr, dAlo, dBhi, idesc, 1u);
+                  }
+                  tc_commit(&emptyB[stage]);            // stage reusable once these MMAs retire
+                  if (++stage == TC_STAGES) { stage = 0; phB ^= 1; }
+               }
+               tc_commit(&tmemFull[as]);                // accumulator ready for the epilogue
+            }
+            tc_commit(emptyA);                          // A block reusable
+         }
+      }
+   } else {
+      // ================= epilogue: TMEM -> log-sum-exp over mixtures -> b[t][slot] =================
+      const int quad = warp & 3;                        // TMEM lane quadrant this warp may read
+      const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+      uint32_t tile = 0;
+      for (int it = blockIdx.x; it < p.nItems; it += gridDim.x) {
+         const int2 item = p.items[it];
+         const UttDesc u = p.utt[item.x];
+         const int nTiles = (u.J + SPT - 1) / SPT;
+         const int t = item.y + quad * 32 + lane;
+         float *brow = p.b + u.bOff + (size_t)t * u.J;
+         for (int n = 0; n < nTiles; n++, tile++) {
+            const uint32_t as = tile & 1, phT = (tile >> 1) & 1;
+            tc_mbar_wait(&tmemFull[as], phT);
+            tc_fence_after();
+            const uint32_t taddr = tmem + as * TC_BN + ((uint32_t)(quad * 32) << 16);
+            float cmx = -INFINITY, csum = 0.f;          // carry for states wider than one 32-column chunk
+#pragma unroll
+            for (int c = 0; c < TC_BN / 32; c++) {
+               float v[32];
+               tc_tmem_ld32(taddr + c * 32, v);
+               constexpr int G = (MP < 32) ? MP : 32;   // columns of one state inside this chunk
+#pragma unroll
+               for (int s0 = 0; s0 < 32; s0 += G) {
+                  float mx = v[s0];
+#pragma unroll
+                  for (int i = 1; i < G; i++) mx = fmaxf(mx, v[s0 + i]);
+                  float sum = 0.f;
+                  const float mb = mx * LOG2E;
+#pragma unroll
+                  for (int i = 0; i < G; i++) sum += exp2f(fmaf(v[s0 + i], LOG2E, -mb));
+                  if (MP > 32) {                        // merge into the carry
+                     float nm = fmaxf(cmx, mx);
+                     csum = csum * exp2f((cmx - nm) * LOG2E) + sum * exp2f((mx - nm) * LOG2E);
+                     cmx = nm; mx = cmx; sum = csum;
+                  }
+                  const int colEnd = c * 32 + s0 + G;   // columns consumed so far
+                  if (colEnd % MP == 0) {
+                     const int slot = n * SPT + colEnd / MP - 1;
+                     float val = (mx < -1.0e29f) ? (float)HFB_LZERO : fmaf(log2f(sum), LN2, mx);
+                     if (t < u.T && slot < u.J) brow[slot] = val;
+                     cmx = -INFINITY; csum = 0.f;
+                  }
+               }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&tmemEmpty[as]);
+         }
+      }
+   }
+   tc_fence_before();
+   __syncthreads();
+   if (warp == 1) {
+      tc_fence_after();
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+   }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*TcEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline int tc_make_map(void *fn, CUtensorMap *map, float *basePtr, long long rows, int boxRows)
+{
+   cuuint64_t dims[2] = {(cuuint64_t)TC_KE, (cuuint64_t)rows};
+   cuuint64_t strides[1] = {(cuuint64_t)TC_KE * sizeof(float)};
+   cuuint32_t box[2] = {32, (cuuint32_t)boxRows};
+   cuuint32_t estr[2] = {1, 1};
+   CUresult r = ((TcEncodeFn)fn)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, basePtr, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+   return r == CUDA_SUCCESS ? HFB_OK : HFB_ECUDA;
+}
+
+static inline float tc_host_tf32(float x)
+{
+   uint32_t u;
+   memcpy(&u, &x, 4);
+   u += 0x1000u; u &= 0xffffe000u;
+   float r;
+   memcpy(&r, &u, 4);
+   return r;
+}
+
+static inline void gmm_tc_release(GmmTcModel &t)
+{
+   if (t.dBhi) cudaFree(t.dBhi);
+   if (t.dBlo) cudaFree(t.dBlo);
+   if (t.dOffset) cudaFree(t.dOffset);
+   if (t.dAhi) cudaFree(t.dAhi);
+   if (t.dAlo) cudaFree(t.dAlo);
+   t = GmmTcModel();
+}
+
 static inline bool gmm_tc_available(const GmmTcModel &t) { return t.ready; }
-static inline int gmm_tc_launch(GmmTcModel &, const DevModel &, const Wave &, const std::vector<UttDesc> &,
-                                cudaStream_t, int *) { return HFB_EUNSUPPORTED; }
+
+// Builds the expanded, split B operand: one row per mixture component of each tied state, each
+// state padded to MP rows, row group 0 = dummy.  Row = [-ivar/2 | (mu-o)*ivar | c | 0...] with
+// c = -(gConst + sum (mu-o)^2 ivar)/2 + log weight (weight omitted for single-mixture states,
+// HFB.c:917-928; components with weight <= LMINMIX get c = -1e30, HFB.c:953).
+static inline int gmm_tc_prepare(GmmTcModel &t, const hfb_model *m, cudaStream_t st)
+{
+   t = GmmTcModel();
+   const int D = m->vecSize, J = m->numStates;
+   int maxM = 0;
+   for (int s = 0; s < J; s++) maxM = std::max(maxM, m->stateMixOff[s + 1] - m->stateMixOff[s]);
+   if (maxM < 2 || 2 * D + 1 > TC_KE) return HFB_OK;          // FP32 kernel handles these
+   int MP = 8;
+   while (MP < maxM) MP *= 2;
+   if (MP > TC_BN) return HFB_OK;
+   int dev = 0, major = 0;
+   cudaGetDevice(&dev);
+   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+   if (major != 10) return HFB_OK;                              // tcgen05 is sm_100 family only
+   void *fn = nullptr;
+   cudaDriverEntryPointQueryResult qr;
+   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
+      cudaGetLastError();
+      return HFB_OK;
+   }
+   t.encodeFn = fn;
+   t.MP = MP; t.GPS = MP / 8;
+   t.rows = (long long)(1 + (long long)J * t.GPS) * 8;
+   std::vector<double> off(D, 0.0);
+   for (int g = 0; g < m->numGauss; g++)
+      for (int k = 0; k < D; k++) off[k] += m->mean[(size_t)g * D + k];
+   std::vector<float> offF(D);
+   for (int k = 0; k < D; k++) offF[k] = (float)(off[k] / m->numGauss);
+   std::vector<float> hi((size_t)t.rows * TC_KE, 0.f), lo((size_t)t.rows * TC_KE, 0.f);
+   auto put = [&](long long r, int k, double v) {
+      float f = (float)v, h = tc_host_tf32(f);
+      hi[(size_t)r * TC_KE + k] = h;
+      lo[(size_t)r * TC_KE + k] = tc_host_tf32(f - h);
+   };
+   for (long long r = 0; r < t.rows; r++) put(r, 2 * D, TC_NEG_BIG);
+   for (int s = 0; s < J; s++) {
+      int mo = m->stateMixOff[s], Mn = m->stateMixOff[s + 1] - mo;
+      for (int k2 = 0; k2 < Mn; k2++) {
+         long long r = (long long)(1 + (long long)s * t.GPS) * 8 + k2;
+         float wt = m->mixLogWt[mo + k2];
+         if (Mn > 1 && !(wt > (float)HFB_LMINMIX)) continue;
+         int g = m->mixGauss[mo + k2];
+         double c = m->gConst[g];
+         for (int k = 0; k < D; k++) {
+            double iv = m->ivar[(size_t)g * D + k], mu = (double)m->mean[(size_t)g * D + k] - (double)offF[k];
+            put(r, k, -0.5 * iv);
+            put(r, D + k, mu * iv);
+            c += mu * mu * iv;
+         }
+         put(r, 2 * D, -0.5 * c + (Mn > 1 ? (double)wt : 0.0));
+      }
+   }
+   size_t bytes = hi.size() * sizeof(float);
+   if (cudaMalloc(&t.dBhi, bytes) != cudaSuccess || cudaMalloc(&t.dBlo, bytes) != cudaSuccess ||
+       cudaMalloc(&t.dOffset, D * sizeof(float)) != cudaSuccess) {
+      cudaGetLastError(); gmm_tc_release(t); return HFB_ENOMEM;
+   }
+   cudaMemcpyAsync(t.dBhi, hi.data(), bytes, cudaMemcpyHostToDevice, st);
+   cudaMemcpyAsync(t.dBlo, lo.data(), bytes, cudaMemcpyHostToDevice, st);
+   cudaMemcpyAsync(t.dOffset, offF.data(), D * sizeof(float), cudaMemcpyHostToDevice, st);
+   cudaStreamSynchronize(st);
+   if (tc_make_map(fn, &t.mapBhi, t.dBhi, t.rows, 8) || tc_make_map(fn, &t.mapBlo, t.dBlo, t.rows, 8)) {
+      gmm_tc_release(t); return HFB_OK;
+   }
+#define TC_SET_SMEM(MPV) cudaFuncSetAttribute(gmm_tc_kernel<MPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)
+   TC_SET_SMEM(8); TC_SET_SMEM(16); TC_SET_SMEM(32); TC_SET_SMEM(64); TC_SET_SMEM(128);
+#undef TC_SET_SMEM
+   t.ready = (cudaGetLastError() == cudaSuccess);
+   return HFB_OK;
+}
+
+// Launches expansion + GEMM for every utterance of the wave.  `items` lives in the wave blob.
+static inline int gmm_tc_launch(GmmTcModel &t, const DevModel &dm, const Wave &W, long long waveFrames,
+                                const int2 *dItems, int nItems, int smCount, cudaStream_t st, int *launches)
+{
+   if (!t.ready) return HFB_EUNSUPPORTED;
+   if (nItems == 0) return HFB_OK;
+   const size_t need = (size_t)waveFrames + TC_BM;
+   if (need > t.aCapFrames) {
+      if (t.dAhi) cudaFree(t.dAhi);
+      if (t.dAlo) cudaFree(t.dAlo);
+      t.dAhi = t.dAlo = nullptr;
+      size_t cap = need + need / 8;
+      if (cudaMalloc(&t.dAhi, cap * TC_KE * sizeof(float)) != cudaSuccess ||
+          cudaMalloc(&t.dAlo, cap * TC_KE * sizeof(float)) != cudaSuccess) { cudaGetLastError(); t.aCapFrames = 0; return HFB_ENOMEM; }
+      t.aCapFrames = cap;
+   }
+   CUtensorMap mapAhi, mapAlo;
+   // rows beyond the wave (at most TC_BM - 1) are allocated but stale: every output row depends on
+   // its own A row only and rows with t >= T are never stored
+   if (tc_make_map(t.encodeFn, &mapAhi, t.dAhi, waveFrames + TC_BM, TC_BM) ||
+       tc_make_map(t.encodeFn, &mapAlo, t.dAlo, waveFrames + TC_BM, TC_BM))
+      return HFB_ECUDA;
+   long long n = waveFrames * TC_KE;
+   gmm_tc_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W.feat, t.dOffset, dm.D, waveFrames, t.dAhi, t.dAlo);
+   TcParams p;
+   p.items = dItems; p.nItems = nItems; p.utt = W.utt; p.slotState = W.slotState; p.b = W.b; p.GPS = t.GPS;
+   int grid = std::min(nItems, smCount);
+   switch (t.MP) {
+   case 8: gmm_tc_kernel<8><<<grid, 192, TC_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhi, t.mapBlo, p); break;
+   case 16: gmm_tc_kernel<16><<<grid, 192, TC_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhi, t.mapBlo, p); break;
+   case 32: gmm_tc_kernel<32><<<grid, 192, TC_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhi, t.mapBlo, p); break;
+   case 64: gmm_tc_kernel<64><<<grid, 192, TC_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhi, t.mapBlo, p); break;
+   default: gmm_tc_kernel<128><<<grid, 192, TC_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhi, t.mapBlo, p); break;
+   }
+   if (launches) *launches = 2;
+   return HFB_OK;
+}

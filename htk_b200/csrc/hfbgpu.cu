@@ -391,6 +391,7 @@ struct WaveTables {
    std::vector<int> slotState, posSlot, posState;
    std::vector<PosRef> pos;
    std::vector<GmmTile> tiles;
+   std::vector<int2> tcItems;        // (utterance, first frame) blocks of TC_BM frames for the tcgen05 kernel
    std::vector<int> uttIndex;        // index in the caller's batch
    long long bFloats = 0, betaDoubles = 0, occDoubles = 0;
    int maxQ = 0, maxS = 0;
@@ -399,7 +400,7 @@ struct WaveTables {
    {
       utt.clear(); out.clear(); mN.clear(); mTrans.clear(); mSoff.clear(); mPoff.clear(); mDms.clear();
       mPre.clear(); mSuf.clear(); mHmm.clear(); mTrAcc.clear(); mTrOcc.clear();
-      slotState.clear(); posSlot.clear(); posState.clear(); pos.clear(); tiles.clear(); uttIndex.clear();
+      slotState.clear(); posSlot.clear(); posState.clear(); pos.clear(); tiles.clear(); tcItems.clear(); uttIndex.clear();
       bFloats = betaDoubles = occDoubles = 0; maxQ = maxS = 0; frames = 0;
    }
 };
@@ -453,6 +454,7 @@ size_t add_utterance(const HostModel &h, WaveTables &w, int uidx, int T, const i
       bytes = (size_t)T * ((size_t)J * 4 + (size_t)S * 8 + (size_t)Pp * 8);
       for (int t0 = 0; t0 < T; t0 += GT_FR)
          for (int s0 = 0; s0 < J; s0 += GT_SL) w.tiles.push_back(GmmTile{uLocal, t0, s0});
+      for (int t0 = 0; t0 < T; t0 += TC_BM) w.tcItems.push_back(make_int2(uLocal, t0));
       w.maxQ = std::max(w.maxQ, Q); w.maxS = std::max(w.maxS, S);
    } else {
       // keep table sizes consistent but give the kernels nothing to do
@@ -492,7 +494,7 @@ static int run_wave(hfbgpu_ctx *c, WaveTables &w, const float *dFeat, long long 
    std::vector<int> tminmax(w.mN.size() * 2, 0);
    size_t oTm = blob_put(blob, tminmax);
    size_t oSs = blob_put(blob, w.slotState), oPs = blob_put(blob, w.posSlot), oPst = blob_put(blob, w.posState);
-   size_t oPos = blob_put(blob, w.pos), oTl = blob_put(blob, w.tiles);
+   size_t oPos = blob_put(blob, w.pos), oTl = blob_put(blob, w.tiles), oIt = blob_put(blob, w.tcItems);
    if (blob.size() > c->hTablesCap) {
       if (c->hTables) cudaFreeHost(c->hTables);
       c->hTablesCap = blob.size() * 2;
@@ -532,7 +534,8 @@ static int run_wave(hfbgpu_ctx *c, WaveTables &w, const float *dFeat, long long 
    if (gk == 0) gk = gmm_tc_available(c->tc) ? 2 : 1;
    if (gk == 2) {
       int nl = 0;
-      if ((rc = gmm_tc_launch(c->tc, c->dm, W, w.utt, c->stream, &nl))) return rc;
+      if ((rc = gmm_tc_launch(c->tc, c->dm, W, waveFrames, (const int2 *)(base + oIt), (int)w.tcItems.size(),
+                              c->smCount, c->stream, &nl))) return rc;
       c->stats.launches += nl; c->stats.launchesGmm += nl;
    } else if (!w.tiles.empty()) {
       size_t smem = sizeof(float) * ((size_t)c->dm.D * GT_FR + (size_t)GT_FR * (GT_SL + 1));
@@ -689,8 +692,10 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
    w.slotState.assign(states, states + n);
    for (int t0 = 0; t0 < T; t0 += GT_FR)
       for (int s0 = 0; s0 < n; s0 += GT_SL) w.tiles.push_back(GmmTile{0, t0, s0});
+   for (int t0 = 0; t0 < T; t0 += TC_BM) w.tcItems.push_back(make_int2(0, t0));
    std::vector<unsigned char> blob;
-   size_t oUtt = blob_put(blob, w.utt), oSs = blob_put(blob, w.slotState), oTl = blob_put(blob, w.tiles);
+   size_t oUtt = blob_put(blob, w.utt), oSs = blob_put(blob, w.slotState), oTl = blob_put(blob, w.tiles),
+          oIt = blob_put(blob, w.tcItems);
    int rc;
    if ((rc = c->dTables.reserve(blob.size())) || (rc = c->dFeat.reserve((size_t)T * h.D + 4)) ||
        (rc = c->dB.reserve((size_t)T * n + 1)))
@@ -706,7 +711,8 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
    if (gk == 0) gk = gmm_tc_available(c->tc) ? 2 : 1;
    if (gk == 2) {
       int nl = 0;
-      if ((rc = gmm_tc_launch(c->tc, c->dm, W, w.utt, c->stream, &nl))) return rc;
+      if ((rc = gmm_tc_launch(c->tc, c->dm, W, T, (const int2 *)(c->dTables.p + oIt), (int)w.tcItems.size(),
+                              c->smCount, c->stream, &nl))) return rc;
       c->stats.launches += nl; c->stats.launchesGmm += nl;
    } else {
       size_t smem = sizeof(float) * ((size_t)c->dm.D * GT_FR + (size_t)GT_FR * (GT_SL + 1));

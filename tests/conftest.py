@@ -33,8 +33,10 @@ def acc_errors(acc, ref, fm):
     """Normalised deviations per accumulator block.
 
     Occupancy-like blocks: |a-b| / max(|b|, 1e-2).  Centred first/second-order sums are
-    near-cancelling: they are scaled by the occupancy of their Gaussian
-    (sigma ~ 1 on all fixtures), i.e. compared as mu/occ and var/occ."""
+    near-cancelling (SURVEY.md 8a "do not compare the centred mean sums element-wise"): they
+    are compared as the re-estimation formulae use them, mu/occ and var/occ in units of sigma
+    (sigma ~ 1 on all fixtures), with the occupancy floored at one frame -- below that the
+    reference's own float rounding of log b_j(o_t) (~1e-5 absolute) exceeds the tolerance."""
     L = fm.layout
     D = fm.D
     out = {}
@@ -49,8 +51,8 @@ def acc_errors(acc, ref, fm):
     out["wtOcc"] = rel(acc[L.wtOcc:L.muSum], ref[L.wtOcc:L.muSum])
     out["muOcc"] = rel(acc[L.muOcc:L.vaSum], ref[L.muOcc:L.vaSum])
     out["vaOcc"] = rel(acc[L.vaOcc:L.numEgs], ref[L.vaOcc:L.numEgs])
-    mocc = np.repeat(np.maximum(ref[L.muOcc:L.vaSum], 1e-2), D)
-    vocc = np.repeat(np.maximum(ref[L.vaOcc:L.numEgs], 1e-2), D)
+    mocc = np.repeat(np.maximum(ref[L.muOcc:L.vaSum], 1.0), D)
+    vocc = np.repeat(np.maximum(ref[L.vaOcc:L.numEgs], 1.0), D)
     out["muSum"] = float(np.max(np.abs(acc[L.muSum:L.muOcc] - ref[L.muSum:L.muOcc]) / mocc)) if mocc.size else 0.0
     out["vaSum"] = float(np.max(np.abs(acc[L.vaSum:L.vaOcc] - ref[L.vaSum:L.vaOcc]) /
                                 np.maximum(vocc, np.abs(ref[L.vaSum:L.vaOcc])))) if vocc.size else 0.0

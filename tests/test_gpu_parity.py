@@ -93,14 +93,10 @@ def test_against_oracle_fp64(name):
 @pytest.mark.parametrize("gmm_kernel", [1, 2])
 def test_outp_matches_oracle(gmm_kernel):
     from oracle import oracle_lib as O
-    for name in ("htkdemo_t2000", "synth_tied_m4"):
+    names = ("htkdemo_t2000", "synth_tied_m4") if gmm_kernel == 1 else ("synth_tied_m4", "synth_tee_m2", "synth_long_m3")
+    for name in names:
         z, fm, b, kw = load_golden(name)
-        try:
-            fb = _fb(fm, gmm_kernel=gmm_kernel, **kw)
-        except Exception as e:
-            if gmm_kernel == 2 and getattr(e, "code", 0) == -5:
-                pytest.skip("tcgen05 path not built")
-            raise
+        fb = _fb(fm, gmm_kernel=gmm_kernel, **kw)      # kernel 2 = tcgen05: must exist for M > 1 sets
         feat = z["feat"][:300]
         states = np.arange(fm.J, dtype=np.int32)
         got = fb.OutP(feat, states)
