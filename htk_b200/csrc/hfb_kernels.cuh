@@ -582,6 +582,7 @@ stats_kernel(DevModel M, Wave W, const PosRef *__restrict__ pos, int numPos)
       for (int t = tmin; t <= tmax; t++) {
          if (p.q < sqA[t] || p.q > eqA[t]) continue;
          double x = occ[(size_t)t * P];
+         if (x < -1.0e29) continue;                                       // pre-pruned by the alpha kernel
          const float *o = feat + (size_t)t * D;
          const float d0 = (k0 < D) ? o[k0] - mu0 : 0.f, d1 = (k1 < D) ? o[k1] - mu1 : 0.f;
          if (Mn > 1) {

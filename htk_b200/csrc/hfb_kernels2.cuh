@@ -1,0 +1,369 @@
+// hfb_kernels2.cuh -- second-generation forward pass and statistics kernels.
+//
+//   alpha_warp_kernel  one WARP per utterance (no block barriers): the lanes cover the window of
+//                      models around the alpha beam, [sq(t-1), eq(t-1)+3], which is all StepAlpha
+//                      can reach in one frame (HFB.c:701-722: the beam is re-derived from the
+//                      previous column).  Same arithmetic as alpha_kernel.
+//   stats2_kernel      one warp per emitting state position; component log-densities are evaluated
+//                      with the reference's own operation order (IDOutP, HModel.c:5425-5430:
+//                      float, sequential, separately rounded multiply/multiply/add) so that the
+//                      mixture posteriors match the reference to FP32 rounding of initx only.
+#pragma once
+#include "hfb_kernels.cuh"
+
+#define OCC_SKIP (-1.0e30)
+
+__host__ __device__ inline size_t alpha_warp_smem_bytes(int S, int Q)
+{
+   return sizeof(double) * ((size_t)2 * S + 2 * Q);
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(32) alpha_warp_kernel(DevModel M, Wave W)
+{
+   extern __shared__ __align__(16) unsigned char smraw[];
+   const UttDesc u = W.utt[blockIdx.x];
+   UttOut *out = &W.out[blockIdx.x];
+   if (out->status != 0) return;
+   const int lane = threadIdx.x;
+   const int T = u.T, Q = u.Q, S = u.S, J = u.J, P = u.P;
+   double *cur = (double *)smraw, *prev = cur + S, *mpSelf = prev + S, *exq = mpSelf + Q;
+   const int *mN = W.mN + u.modOff, *mSoff = W.mSoff + u.modOff, *mTr = W.mTrans + u.modOff;
+   const int *mPoff = W.mPoff + u.modOff, *mDms = W.mDms + u.modOff;
+   const float *A0 = M.transLogA;
+   const int *posSlot = W.posSlot + u.posOff, *posState = W.posState + u.posOff;
+   const float *bU = W.b + u.bOff;
+   const double *betaU = W.beta + u.betaOff;
+   double *occU = W.occ + u.occOff;
+   const short *qLo = W.qLo + u.frameBase, *qHi = W.qHi + u.frameBase;
+   short *sqA = W.sq + u.frameBase, *eqA = W.eq + u.frameBase;
+   const double pr = out->pr, minF = W.minFrwdP;
+   const int uf = W.uFlags;
+   const bool doMix = (uf & (HFB_UPMEANS | HFB_UPVARS | HFB_UPMIXES)) != 0;
+   const bool doTr = (uf & HFB_UPTRANS) != 0;
+
+   for (int q = lane; q < Q; q += 32) {
+      mpSelf[q] = LZERO_D; exq[q] = LZERO_D;
+      W.mTmin[u.modOff + q] = 0x7fffffff; W.mTmax[u.modOff + q] = -1;
+      atomicAdd(&W.acc[M.L.numEgs + W.mHmm[u.modOff + q]], 1.0);      // HFB.c:1768-1772
+   }
+   for (int i = lane; i < 2 * S; i += 32) cur[i] = LZERO_D;
+   __syncwarp();
+
+   int sq = 0, eq = 0, sqP2 = 0, eqP2 = -1;
+   for (int t = 0; t < T; t++) {
+      const int loT = qLo[t], hiT = qHi[t];
+      if (t == 0) {
+         // ---- InitAlpha, HFB.c:616-651
+         eq = hiT; sq = 0;
+         if (lane == 0) {
+            double a1 = 0.0, a1N = 0.0;
+            for (int q = 0; q <= eq; q++) {
+               a1 = (q == 0) ? 0.0 : a1 + a1N;
+               cur[mSoff[q]] = a1;
+               a1N = A0[mTr[q] + mN[q] - 1];
+            }
+         }
+         __syncwarp();
+         for (int q = lane; q <= eq; q += 32) {
+            const int N = mN[q], so = mSoff[q];
+            const float *A = A0 + mTr[q];
+            const int *ps = posSlot + mPoff[q];
+            const double a1 = cur[so];
+            for (int j = 1; j < N - 1; j++) {
+               double a = A[j];
+               cur[so + j] = (a > LSMALL_D) ? a1 + a + (double)bU[ps[j - 1]] : LZERO_D;
+            }
+            double x = LZERO_D;
+            for (int i = 1; i < N - 1; i++) {
+               double a = A[i * N + N - 1];
+               if (a > LSMALL_D) x = ladd<EXACT>(x, cur[so + i] + a);
+            }
+            cur[so + N - 1] = x;
+         }
+      } else {
+         { double *tmp = cur; cur = prev; prev = tmp; }
+         // ---- alpha beam, HFB.c:701-722; candidates can only lie in [sq, eq+3] of the previous frame
+         const int loP = qLo[t - 1], hiP = qHi[t - 1];
+         const int wLo = sq, wHi = min(Q - 1, eq + 3);
+         int mySq = 0x7fffffff;
+         for (int q = wLo + lane; q <= wHi; q += 32) {
+            if (q < loP) continue;
+            double mp = fmax((q > 0) ? exq[q - 1] : LZERO_D, mpSelf[q]);
+            if (!(pr - mp > minF)) mySq = min(mySq, q);
+         }
+         int nsq = warp_mini(mySq);
+         if (nsq > hiT) { if (lane == 0) out->status = HFB_UTT_EALPHA; return; }       // HError 7390
+         if (nsq < loT) nsq = loT;
+         const int eq0 = (hiP < Q - 1) ? hiP + 1 : hiP;
+         int myEq = -1;
+         for (int q = wLo + lane; q <= wHi; q += 32) {
+            if (q > eq0) continue;
+            double mp = (q > 0) ? exq[q - 1] : LZERO_D;
+            if (q > 0 && q - 1 > nsq && q >= 2) {
+               if ((double)A0[mTr[q - 1] + mN[q - 1] - 1] > LSMALL_D) mp = fmax(mp, exq[q - 2]);
+            }
+            mp = fmax(mp, mpSelf[q]);
+            if (!(pr - mp > minF)) myEq = max(myEq, q);
+         }
+         int neq = warp_maxi(myEq);
+         if (neq < nsq) { if (lane == 0) out->status = HFB_UTT_EALPHA; return; }
+         while (neq < Q - 1 && mDms[neq] == 0) neq++;
+         if (neq > hiT) neq = hiT;
+         // ---- alpha column, HFB.c:729-771; also clears what the column of frame t-2 left behind
+         const int cLo = sqP2, cHi = min(Q - 1, max(max(eqP2, eq), neq) + 3);
+         const float *bt = bU + (size_t)t * J;
+         for (int q = cLo + lane; q <= cHi; q += 32) {
+            const int N = mN[q], so = mSoff[q];
+            if (q < nsq || q > neq) { for (int i = 0; i < N; i++) cur[so + i] = LZERO_D; continue; }
+            const float *A = A0 + mTr[q];
+            const int *ps = posSlot + mPoff[q];
+            double a1 = LZERO_D;
+            if (q > 0) {
+               const int N1 = mN[q - 1];
+               a1 = prev[mSoff[q - 1] + N1 - 1];
+               const double a1N = A0[mTr[q - 1] + N1 - 1];
+               if (q > nsq && a1N > LSMALL_D) {
+                  double y = (q >= 2) ? prev[mSoff[q - 2] + mN[q - 2] - 1] : LZERO_D;
+                  a1 = ladd<EXACT>(a1, y + a1N);
+               }
+            }
+            cur[so] = a1;
+            for (int j = 1; j < N - 1; j++) {
+               double a = A[j];
+               double x = (a > LSMALL_D) ? a + a1 : LZERO_D;
+               for (int i = 1; i < N - 1; i++) {
+                  double aij = A[i * N + j], y = prev[so + i];
+                  if (aij > LSMALL_D && y > LSMALL_D) x = ladd<EXACT>(x, y + aij);
+               }
+               cur[so + j] = x + (double)bt[ps[j - 1]];
+            }
+            double x = LZERO_D;
+            for (int i = 1; i < N - 1; i++) {
+               double a = A[i * N + N - 1], y = cur[so + i];
+               if (a > LSMALL_D && y > LSMALL_D) x = ladd<EXACT>(x, y + a);
+            }
+            cur[so + N - 1] = x;
+         }
+         sqP2 = sq; eqP2 = eq;
+         sq = nsq; eq = neq;
+      }
+      __syncwarp();
+      if (lane == 0) { sqA[t] = (short)sq; eqA[t] = (short)eq; }
+
+      // ---- accumulation inside the alpha beam (StepForward, HFB.c:1790-1806)
+      const float *bt = bU + (size_t)t * J;
+      const bool haveT1 = (t + 1 < T);
+      const int loT1 = haveT1 ? qLo[t + 1] : 1, hiT1 = haveT1 ? qHi[t + 1] : 0;
+      const int aLo = (t == 0) ? 0 : sqP2, aHi = (t == 0) ? eq : min(Q - 1, max(eqP2, eq) + 3);
+      for (int q = aLo + lane; q <= aHi; q += 32) {
+         if (q < sq || q > eq) { mpSelf[q] = LZERO_D; exq[q] = LZERO_D; continue; }
+         const int N = mN[q], so = mSoff[q];
+         const float *A = A0 + mTr[q];
+         const int *ps = posSlot + mPoff[q];
+         const double *bq = betaU + (size_t)t * S + so;
+         const bool hasB1 = haveT1 && q >= loT1 && q <= hiT1;
+         const bool hasBq1 = (q < Q - 1) && (q + 1 >= loT) && (q + 1 <= hiT);
+         const double bq1 = hasBq1 ? betaU[(size_t)t * S + mSoff[q + 1]] : LZERO_D;
+         const double a1N = A[N - 1];
+         const int gq = u.modOff + q;
+         if (W.mTmin[gq] > t) W.mTmin[gq] = t;
+         W.mTmax[gq] = t;
+         double mps = LZERO_D;
+         for (int i = 0; i < N - 1; i++) mps = fmax(mps, cur[so + i] + bq[i]);
+         mpSelf[q] = mps;
+         exq[q] = cur[so + N - 1] + bq[N - 1];
+         if (doTr) {
+            double *tacc = W.acc + W.mTrAcc[gq], *oacc = W.acc + W.mTrOcc[gq];
+            for (int i = 0; i < N - 1; i++) {                               // SetOcct -> ta->occ
+               double x = cur[so + i] + bq[i];
+               if (i == 0 && hasBq1 && a1N > LSMALL_D) x = ladd<EXACT>(x, cur[so] + bq1 + a1N);
+               x -= pr;
+               if (x > -87.0) atomicAdd(&oacc[i], (double)expf((float)x));
+            }
+            for (int j = 1; j < N - 1; j++) {                               // UpTranParms
+               double x = cur[so] + (double)A[j] + (double)bt[ps[j - 1]] + bq[j] - pr;
+               if (x > -87.0) atomicAdd(&tacc[j], (double)expf((float)x));
+            }
+            if (hasB1) {
+               const double *bq1t = betaU + (size_t)(t + 1) * S + so;
+               const float *bt1 = bt + J;
+               for (int i = 1; i < N - 1; i++)
+                  for (int j = 1; j < N - 1; j++) {
+                     const float aij = A[i * N + j];
+                     if (!(aij > (float)LSMALL_D)) continue;
+                     double x = cur[so + i] + (double)aij + (double)bt1[ps[j - 1]] + bq1t[j] - pr;
+                     if (x > -87.0) atomicAdd(&tacc[i * N + j], (double)expf((float)x));
+                  }
+            }
+            for (int i = 1; i < N - 1; i++) {
+               double x = cur[so + i] + (double)A[i * N + N - 1] + bq[N - 1] - pr;
+               if (x > -87.0) atomicAdd(&tacc[i * N + N - 1], (double)expf((float)x));
+            }
+            if (a1N > LSMALL_D && hasBq1) {
+               double x = cur[so] + a1N + bq1 - pr;
+               if (x > -87.0) atomicAdd(&tacc[N - 1], (double)expf((float)x));
+            }
+         }
+         if (doMix) {
+            const int *pst = posState + mPoff[q];
+            double *oc = occU + (size_t)t * P + mPoff[q];
+            for (int j = 1; j < N - 1; j++) {
+               const double lg = cur[so + j] + bq[j] - pr;                  // log state occupancy
+               double x;
+               if (lg < -(minF + 0.25)) x = OCC_SKIP;                       // no component can pass :1606
+               else {
+                  int s = pst[j - 1];
+                  int Mn = M.stateMixOff[s + 1] - M.stateMixOff[s];
+                  if (Mn == 1) x = lg;                                      // :1575-1576
+                  else {                                                    // initx, :1480-1489
+                     x = (double)A[j] + cur[so];
+                     if (t > 0)
+                        for (int i = 1; i < N - 1; i++) {
+                           double a = A[i * N + j];
+                           if (a > LSMALL_D) x = ladd<EXACT>(x, prev[so + i] + a);
+                        }
+                     x += bq[j] - pr;
+                  }
+               }
+               oc[j - 1] = x;
+            }
+         }
+      }
+      __syncwarp();
+   }
+   if (lane == 0) {
+      atomicAdd(&W.acc[M.L.totalT], (double)T);                             // HERest.c:779-780
+      atomicAdd(&W.acc[M.L.totalPr], pr);
+      atomicAdd(&W.acc[M.L.numOk], 1.0);
+   }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4 v2
+// ------------------------------------------------------------------------------------------
+#define ST_WARPS 4
+__host__ __device__ inline int stats2_ostride(int D) { return D | 1; }
+__host__ __device__ inline size_t stats2_smem_bytes(int D)
+{
+   return ST_WARPS * (sizeof(float) * ((size_t)32 * stats2_ostride(D) + 32 * 33) + sizeof(double) * 32 + sizeof(int) * 32);
+}
+
+__global__ void __launch_bounds__(32 * ST_WARPS)
+stats2_kernel(DevModel M, Wave W, const PosRef *__restrict__ pos, int numPos)
+{
+   extern __shared__ __align__(16) unsigned char smraw[];
+   const int wInB = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const int wg = blockIdx.x * ST_WARPS + wInB;
+   if (wg >= numPos) return;
+   const PosRef p = pos[wg];
+   if (W.out[p.utt].status != 0) return;
+   const UttDesc u = W.utt[p.utt];
+   const int gq = u.modOff + p.q;
+   const int tmin = W.mTmin[gq], tmax = W.mTmax[gq];
+   if (tmin > tmax) return;
+   const int D = M.D, Dp = M.Dp, P = u.P, ostr = stats2_ostride(D);
+   const size_t perWarp = sizeof(float) * ((size_t)32 * ostr + 32 * 33) + sizeof(double) * 32 + sizeof(int) * 32;
+   unsigned char *mine = smraw + perWarp * wInB;
+   double *x0s = (double *)mine;                       // [32] initx / log occupancy per chunk frame
+   float *os = (float *)(x0s + 32);                    // [32][ostr] observation rows
+   float *lrs = os + 32 * ostr;                        // [32 mixtures][33] occupancies Lr
+   int *ts = (int *)(lrs + 32 * 33);                   // [32] frame numbers
+
+   const int pp = W.mPoff[gq] + p.j;
+   const int s = W.posState[u.posOff + pp];
+   const int mo = M.stateMixOff[s], Mn = M.stateMixOff[s + 1] - mo;
+   const double *occ = W.occ + u.occOff + pp;
+   const short *sqA = W.sq + u.frameBase, *eqA = W.eq + u.frameBase;
+   const float *feat = W.feat + (size_t)u.featOff * D;
+   const double minF = W.minFrwdP;
+   const int uf = W.uFlags;
+   const bool upM = (uf & HFB_UPMEANS) != 0, upV = (uf & HFB_UPVARS) != 0, upW = (uf & HFB_UPMIXES) != 0;
+   const int k0 = lane, k1 = lane + 32;                // D <= 64 (checked at create)
+   double wsum = 0.0;
+
+   for (int t0 = tmin; t0 <= tmax; t0 += 32) {
+      // ---- frames of this chunk that are inside the alpha beam and not pre-pruned
+      const int t = t0 + lane;
+      double x0 = OCC_SKIP;
+      bool valid = false;
+      if (t <= tmax && p.q >= sqA[t] && p.q <= eqA[t]) { x0 = occ[(size_t)t * P]; valid = x0 > -1.0e29; }
+      const unsigned mask = __ballot_sync(0xffffffffu, valid);
+      const int nT = __popc(mask);
+      if (nT == 0) continue;
+      if (valid) { int idx = __popc(mask & ((1u << lane) - 1)); ts[idx] = t; x0s[idx] = x0; }
+      __syncwarp();
+      for (int ti = 0; ti < nT; ti++) {
+         const float *o = feat + (size_t)ts[ti] * D;
+         if (k0 < D) os[ti * ostr + k0] = o[k0];
+         if (k1 < D) os[ti * ostr + k1] = o[k1];
+      }
+      __syncwarp();
+      for (int mb = 0; mb < Mn; mb += 32) {
+         const int Mc = min(32, Mn - mb);
+         // ---- phase 1: lanes <-> (mixture, frame) pairs; IDOutP in the reference's operation order
+         unsigned act = 0;                             // mixtures with any occupancy in this chunk
+         for (int pi = lane; pi < ((Mc * nT + 31) & ~31); pi += 32) {
+            float Lr = 0.f;
+            const int mi = pi / nT, ti = pi - mi * nT;
+            if (mi < Mc) {
+               const float wt = M.mixLogWt[mo + mb + mi];
+               if (wt > LMINMIX_F) {                                         // HFB.c:1573
+                  double x = x0s[ti];
+                  if (Mn > 1) {
+                     const int g = M.mixGauss[mo + mb + mi];
+                     const float *mu = M.mean + (size_t)g * Dp, *iv = M.ivar + (size_t)g * Dp;
+                     const float *o = os + ti * ostr;
+                     float sum = M.gconst[g];
+                     for (int k = 0; k < D; k++) {
+                        const float d = __fsub_rn(o[k], mu[k]);
+                        sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), iv[k]));
+                     }
+                     const float mixp = -0.5f * sum;
+                     x = (x + (double)wt) + (double)mixp;                    // :1581-1599
+                  }
+                  if (-x < minF) Lr = expf((float)x);                        // :1606, :1612
+               }
+               lrs[mi * 33 + ti] = Lr;
+            }
+            const unsigned nz = __ballot_sync(0xffffffffu, Lr > 0.f);
+            // fold the ballot into per-mixture bits (pairs are mixture-major)
+            for (unsigned b = nz; b; b &= b - 1) {
+               int l = __ffs(b) - 1;
+               act |= 1u << (((pi - lane) + l) / nT);
+            }
+         }
+         __syncwarp();
+         // ---- phase 2: lanes <-> feature dimensions, centred sums over the chunk's frames
+         for (unsigned b = act; b; b &= b - 1) {
+            const int mi = __ffs(b) - 1;
+            const int g = M.mixGauss[mo + mb + mi];
+            const float mu0 = (k0 < D) ? M.mean[(size_t)g * Dp + k0] : 0.f, mu1 = (k1 < D) ? M.mean[(size_t)g * Dp + k1] : 0.f;
+            float am0 = 0.f, am1 = 0.f, av0 = 0.f, av1 = 0.f, aocc = 0.f;
+            for (int ti = 0; ti < nT; ti++) {
+               const float Lr = lrs[mi * 33 + ti];
+               const float d0 = (k0 < D) ? os[ti * ostr + k0] - mu0 : 0.f, d1 = (k1 < D) ? os[ti * ostr + k1] - mu1 : 0.f;
+               const float z0 = d0 * Lr, z1 = d1 * Lr;                       // zmeanlr, :1675
+               aocc += Lr; am0 += z0; am1 += z1;
+               av0 = fmaf(z0, d0, av0); av1 = fmaf(z1, d1, av1);
+            }
+            if (upM) {
+               double *mu = W.acc + M.L.muSum + (size_t)M.meanId[g] * D;
+               if (k0 < D) atomicAdd(&mu[k0], (double)am0);
+               if (k1 < D) atomicAdd(&mu[k1], (double)am1);
+               if (lane == 0) atomicAdd(&W.acc[M.L.muOcc + M.meanId[g]], (double)aocc);
+            }
+            if (upV) {
+               double *va = W.acc + M.L.vaSum + (size_t)M.varId[g] * D;
+               if (k0 < D) atomicAdd(&va[k0], (double)av0);
+               if (k1 < D) atomicAdd(&va[k1], (double)av1);
+               if (lane == 0) atomicAdd(&W.acc[M.L.vaOcc + M.varId[g]], (double)aocc);
+            }
+            if (upW && lane == 0) atomicAdd(&W.acc[M.L.wtC + mo + mb + mi], (double)aocc);
+            wsum += (double)aocc;
+         }
+         __syncwarp();
+      }
+   }
+   if (lane == 0 && wsum > 0.0) atomicAdd(&W.acc[M.L.wtOcc + s], wsum);     // :1736
+}

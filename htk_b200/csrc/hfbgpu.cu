@@ -17,6 +17,7 @@
 
 #include "hfb_common.h"
 #include "hfb_kernels.cuh"
+#include "hfb_kernels2.cuh"
 #include "gmm_tc.cuh"
 
 static thread_local std::string g_lastError;
@@ -303,6 +304,9 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
    cudaFuncSetAttribute(beta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(alpha_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(alpha_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
+   cudaFuncSetAttribute(alpha_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
+   cudaFuncSetAttribute(alpha_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
+   cudaFuncSetAttribute(stats2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    CK(cudaStreamSynchronize(c->stream));
    *out = c;
    return HFB_OK;
@@ -551,14 +555,22 @@ static int run_wave(hfbgpu_ctx *c, WaveTables &w, const float *dFeat, long long 
    if (exact) beta_kernel<true><<<nU, nt, rsm, c->stream>>>(c->dm, W);
    else beta_kernel<false><<<nU, nt, rsm, c->stream>>>(c->dm, W);
    if (tm) cudaEventRecord(c->ev[2], c->stream);
-   if (exact) alpha_kernel<true><<<nU, nt, rsm, c->stream>>>(c->dm, W);
-   else alpha_kernel<false><<<nU, nt, rsm, c->stream>>>(c->dm, W);
+   static const bool oldAlpha = getenv("HFBGPU_OLD_ALPHA") != nullptr, oldStats = getenv("HFBGPU_OLD_STATS") != nullptr;
+   const size_t asm_ = alpha_warp_smem_bytes(w.maxS, w.maxQ);
+   if (oldAlpha || asm_ > (size_t)c->maxSmemOptin) {
+      if (exact) alpha_kernel<true><<<nU, nt, rsm, c->stream>>>(c->dm, W);
+      else alpha_kernel<false><<<nU, nt, rsm, c->stream>>>(c->dm, W);
+   } else {
+      if (exact) alpha_warp_kernel<true><<<nU, 32, asm_, c->stream>>>(c->dm, W);
+      else alpha_warp_kernel<false><<<nU, 32, asm_, c->stream>>>(c->dm, W);
+   }
    if (tm) cudaEventRecord(c->ev[3], c->stream);
    c->stats.launches += 2; c->stats.launchesBeta++; c->stats.launchesAlpha++;
    // ---- K4
    if (!w.pos.empty() && (c->opt.uFlags & (HFB_UPMEANS | HFB_UPVARS | HFB_UPMIXES))) {
       int nPos = (int)w.pos.size();
-      stats_kernel<<<(nPos + 3) / 4, 128, 0, c->stream>>>(c->dm, W, dPos, nPos);
+      if (oldStats) stats_kernel<<<(nPos + 3) / 4, 128, 0, c->stream>>>(c->dm, W, dPos, nPos);
+      else stats2_kernel<<<(nPos + ST_WARPS - 1) / ST_WARPS, 32 * ST_WARPS, stats2_smem_bytes(c->dm.D), c->stream>>>(c->dm, W, dPos, nPos);
       c->stats.launches++; c->stats.launchesStats++;
    }
    if (tm) cudaEventRecord(c->ev[4], c->stream);
