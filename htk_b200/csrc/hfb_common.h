@@ -20,6 +20,11 @@ struct DevModel {
    const int *mixGauss;             // [sumM]
    const float *mixLogWt;           // [sumM]
    const float *transLogA;          // all matrices, row-major N*N each
+   // per physical HMM / per transition matrix (read by the table-building kernel)
+   const int *hmmN, *hmmStateOff, *hmmState, *hmmTrans;
+   const int *transOffF;            // offset of the matrix in transLogA
+   const int *transMinDur;          // SetMinDurs, HFB.c:106-155
+   const long long *tranAccOff, *tranOccOff;   // offsets of TrAcc.tran / TrAcc.occ in the accumulators
    hfb_acc_layout L;
 };
 
@@ -27,7 +32,8 @@ struct UttDesc {
    int T, Q;
    int S;                           // sum of N_q: doubles per beta column
    int P;                           // sum of (N_q - 2): emitting positions
-   int J;                           // distinct tied states (output-probability slots)
+   int J;                           // distinct tied states (output-probability slots); set by prep_kernel
+   int labOff;                      // offset of the transcription in the wave's label array
    int modOff;                      // offset of model 0 in the per-model arrays
    int slotOff;                     // offset into slotState[]
    int posOff;                      // offset into posSlot[] / posState[]
@@ -38,35 +44,38 @@ struct UttDesc {
    long long frameBase;             // first frame in the per-frame beam arrays
 };
 
-struct UttOut {                     // mirrors hfb_utt_result
+struct UttOut {                     // hfb_utt_result + what the host wants back
    int status;
    int retries;
    double pr;
    double thresh;
+   int J;
+   int pad;
 };
 
-struct PosRef { int utt, q, j; };   // one emitting state position (stats kernel work item)
-struct GmmTile { int utt, t0, s0; };// one [frames x slots] tile of the FP32 GMM kernel
-
 struct Wave {                       // everything the kernels of one wave need
-   const UttDesc *utt;              // [numUtt in wave]
+   UttDesc *utt;                    // [numUtt in wave]
    UttOut *out;
    int numUtt;
-   // per-model arrays (concatenated over the wave's utterances)
-   const int *mN;                   // states of the model
-   const int *mTrans;               // offset of its matrix in transLogA
-   const int *mSoff;                // offset of its states inside a beta column
-   const int *mPoff;                // offset of its emitting states inside an occ row
-   const int *mDms;                 // minimum duration (qDms)
-   const int *mPre;                 // sum of mDms over preceding models
-   const int *mSuf;                 // sum of mDms over following models
-   const int *mHmm;                 // physical HMM index
-   const long long *mTrAcc;         // offset of its TrAcc.tran block in the accumulators
-   const long long *mTrOcc;         // offset of its TrAcc.occ block
+   const int *lab;                  // physical-HMM index per label, concatenated
+   const int *posPre;               // [numUtt+1] prefix sums of P (emitting positions)
+   const int *tilePre;              // [numUtt+1] prefix sums of FP32-GMM tiles
+   int totalPos;
+   // per-model arrays (concatenated over the wave's utterances), written by prep_kernel
+   int *mN;                         // states of the model
+   int *mTrans;                     // offset of its matrix in transLogA
+   int *mSoff;                      // offset of its states inside a beta column
+   int *mPoff;                      // offset of its emitting states inside an occ row
+   int *mDms;                       // minimum duration (qDms)
+   int *mPre;                       // sum of mDms over preceding models
+   int *mSuf;                       // sum of mDms over following models
+   int *mHmm;                       // physical HMM index
+   long long *mTrAcc;               // offset of its TrAcc.tran block in the accumulators
+   long long *mTrOcc;               // offset of its TrAcc.occ block
    int *mTmin, *mTmax;              // first / last frame inside the alpha beam
-   const int *slotState;            // tied state of each slot
-   const int *posSlot;              // slot of each emitting position
-   const int *posState;             // tied state of each emitting position
+   int *slotState;                  // tied state of each slot
+   int *posSlot;                    // slot of each emitting position
+   int *posState;                   // tied state of each emitting position
    const float *feat;               // [frames][D]
    float *b;
    double *beta;

@@ -65,14 +65,30 @@ __device__ __forceinline__ float warp_sumf(float v)
 #define GT_FR 64
 #define GT_SL 32
 
+struct GmmTile { int utt, t0, s0; };
+
+// largest i in [0, n) with pre[i] <= v (pre non-decreasing, pre[0] <= v)
+__device__ __forceinline__ int upper_index(const int *__restrict__ pre, int n, int v)
+{
+   int lo = 0, hi = n;
+   while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pre[mid] <= v) lo = mid; else hi = mid; }
+   return lo;
+}
+
 __global__ void __launch_bounds__(128)
-gmm_fp32_kernel(DevModel M, Wave W, const GmmTile *__restrict__ tiles)
+gmm_fp32_kernel(DevModel M, Wave W)
 {
    extern __shared__ float gsm[];
    float *xs = gsm;                              // [D][GT_FR]
    float *outT = gsm + M.D * GT_FR;              // [GT_FR][GT_SL+1]
-   const GmmTile tl = tiles[blockIdx.x];
+   GmmTile tl;
+   tl.utt = upper_index(W.tilePre, W.numUtt, (int)blockIdx.x);
    const UttDesc u = W.utt[tl.utt];
+   {
+      const int lt = (int)blockIdx.x - W.tilePre[tl.utt], nSl = (u.P + GT_SL - 1) / GT_SL;
+      tl.t0 = (lt / nSl) * GT_FR; tl.s0 = (lt % nSl) * GT_SL;
+   }
+   if (W.out[tl.utt].status != 0 || tl.s0 >= u.J) return;
    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
    const int D = M.D, Dp = M.Dp;
    const float *feat = W.feat + (size_t)u.featOff * D;
@@ -118,6 +134,71 @@ gmm_fp32_kernel(DevModel M, Wave W, const GmmTile *__restrict__ tiles)
    for (int idx = tid; idx < GT_FR * GT_SL; idx += 128) {
       int f = idx >> 5, sl = idx & 31, t = tl.t0 + f, slot = tl.s0 + sl;
       if (t < u.T && slot < u.J) b[(size_t)t * u.J + slot] = outT[f * (GT_SL + 1) + sl];
+   }
+}
+
+// ------------------------------------------------------------------------------------------
+// K0: per-utterance tables, CreateInsts (HFB.c:508-574) on the device.  One CTA per utterance.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) prep_kernel(DevModel M, Wave W)
+{
+   __shared__ int sStatus;
+   UttDesc *u = &W.utt[blockIdx.x];
+   UttOut *out = &W.out[blockIdx.x];
+   if (out->status != 0) return;                        // rejected by the host (bad label index ...)
+   const int tid = threadIdx.x, nt = blockDim.x;
+   const int Q = u->Q, T = u->T, P = u->P;
+   const int *lab = W.lab + u->labOff;
+   int *mN = W.mN + u->modOff, *mTrans = W.mTrans + u->modOff, *mSoff = W.mSoff + u->modOff;
+   int *mPoff = W.mPoff + u->modOff, *mDms = W.mDms + u->modOff, *mPre = W.mPre + u->modOff;
+   int *mSuf = W.mSuf + u->modOff, *mHmm = W.mHmm + u->modOff;
+   long long *mTrAcc = W.mTrAcc + u->modOff, *mTrOcc = W.mTrOcc + u->modOff;
+   int *posState = W.posState + u->posOff, *posSlot = W.posSlot + u->posOff, *slotState = W.slotState + u->slotOff;
+   for (int q = tid; q < Q; q += nt) {
+      const int p = lab[q], tr = M.hmmTrans[p];
+      mN[q] = M.hmmN[p]; mTrans[q] = M.transOffF[tr]; mDms[q] = M.transMinDur[tr]; mHmm[q] = p;
+      mTrAcc[q] = M.tranAccOff[tr]; mTrOcc[q] = M.tranOccOff[tr];
+   }
+   __syncthreads();
+   if (tid == 0) {
+      int S = 0, Pp = 0, qt = 0, bad = 0, prevD = 1;
+      for (int q = 0; q < Q; q++) {
+         const int N = mN[q], d = mDms[q];
+         mSoff[q] = S; mPoff[q] = Pp; mPre[q] = qt;
+         S += N; Pp += N - 2; qt += d;
+         if (q > 0 && d == 0 && prevD == 0) bad = HFB_UTT_ETEE;                // HFB.c:557
+         prevD = d;
+      }
+      int acc = 0;
+      for (int q = Q - 1; q >= 0; q--) { mSuf[q] = acc; acc += mDms[q]; }
+      if (mDms[0] == 0 || mDms[Q - 1] == 0) bad = HFB_UTT_ETEE;                // HFB.c:564
+      if (!bad && qt > T) bad = HFB_UTT_SKIPPED;                               // HFB.c:1339-1343
+      sStatus = bad;
+   }
+   __syncthreads();
+   if (sStatus != 0) { if (tid == 0) { out->status = sStatus; out->J = 0; } return; }
+   for (int q = tid; q < Q; q += nt) {
+      const int p = lab[q], n = mN[q] - 2, so = M.hmmStateOff[p], po = mPoff[q];
+      for (int j = 0; j < n; j++) posState[po + j] = M.hmmState[so + j];
+   }
+   __syncthreads();
+   // the reference evaluates each tied state once per frame (HFB.c:910-912): find the first
+   // position using the same state, then number the distinct states ("slots")
+   for (int pp = tid; pp < P; pp += nt) {
+      const int s = posState[pp];
+      int f = pp;
+      for (int p2 = 0; p2 < pp; p2++) if (posState[p2] == s) { f = p2; break; }
+      posSlot[pp] = f;
+   }
+   __syncthreads();
+   if (tid == 0) {
+      int J = 0;
+      for (int pp = 0; pp < P; pp++) {
+         const int f = posSlot[pp];
+         if (f == pp) { slotState[J] = posState[pp]; posSlot[pp] = J++; }
+         else posSlot[pp] = posSlot[f];
+      }
+      u->J = J; out->J = J;
    }
 }
 
@@ -319,301 +400,3 @@ __global__ void __launch_bounds__(256) beta_kernel(DevModel M, Wave W)
    }
 }
 
-// ------------------------------------------------------------------------------------------
-// K3: alpha pass, alpha beam, occupancies, transition counts
-// ------------------------------------------------------------------------------------------
-template <bool EXACT>
-__global__ void __launch_bounds__(256) alpha_kernel(DevModel M, Wave W)
-{
-   extern __shared__ __align__(16) unsigned char smraw[];
-   const UttDesc u = W.utt[blockIdx.x];
-   UttOut *out = &W.out[blockIdx.x];
-   if (out->status != 0) return;
-   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-   const int T = u.T, Q = u.Q, S = u.S, J = u.J, P = u.P;
-   RecSmem sm = rec_carve(smraw, S, Q);
-   for (int q = tid; q < Q; q += nt) {
-      sm.sN[q] = W.mN[u.modOff + q]; sm.sSoff[q] = W.mSoff[u.modOff + q];
-      sm.sTr[q] = W.mTrans[u.modOff + q]; sm.sPoff[q] = W.mPoff[u.modOff + q];
-      sm.sDms[q] = W.mDms[u.modOff + q];
-      sm.aux[q] = LZERO_D; sm.aux2[q] = LZERO_D;
-      W.mTmin[u.modOff + q] = 0x7fffffff; W.mTmax[u.modOff + q] = -1;
-      atomicAdd(&W.acc[M.L.numEgs + W.mHmm[u.modOff + q]], 1.0);       // HFB.c:1768-1772
-   }
-   const float *A0 = M.transLogA;
-   const int *posSlot = W.posSlot + u.posOff, *posState = W.posState + u.posOff;
-   const float *bU = W.b + u.bOff;
-   const double *betaU = W.beta + u.betaOff;
-   double *occU = W.occ + u.occOff;
-   const short *qLo = W.qLo + u.frameBase, *qHi = W.qHi + u.frameBase;
-   short *sqA = W.sq + u.frameBase, *eqA = W.eq + u.frameBase;
-   const double pr = out->pr, minF = W.minFrwdP;
-   const int uf = W.uFlags;
-   const bool doMix = (uf & (HFB_UPMEANS | HFB_UPVARS | HFB_UPMIXES)) != 0;
-   const bool doTr = (uf & HFB_UPTRANS) != 0;
-   double *cur = sm.colA, *prev = sm.colB;
-   double *mpSelf = sm.aux, *exq = sm.aux2;
-   __syncthreads();
-
-   int sq = 0, eq = 0;
-   for (int t = 0; t < T; t++) {
-      const int loT = qLo[t], hiT = qHi[t];
-      if (t == 0) {
-         // ---- InitAlpha, HFB.c:616-651 (entry chain through leading tee models is serial)
-         eq = hiT; sq = 0;
-         if (tid == 0) {
-            double a1 = 0.0, a1N = 0.0;
-            for (int q = 0; q <= eq; q++) {
-               a1 = (q == 0) ? 0.0 : a1 + a1N;
-               cur[sm.sSoff[q]] = a1;
-               a1N = A0[sm.sTr[q] + sm.sN[q] - 1];
-            }
-         }
-         __syncthreads();
-         for (int q = tid; q < Q; q += nt) {
-            const int N = sm.sN[q], so = sm.sSoff[q];
-            if (q > eq) { for (int i = 0; i < N; i++) cur[so + i] = LZERO_D; continue; }
-            const float *A = A0 + sm.sTr[q];
-            const int *ps = posSlot + sm.sPoff[q];
-            const double a1 = cur[so];
-            for (int j = 1; j < N - 1; j++) {
-               double a = A[j];
-               cur[so + j] = (a > LSMALL_D) ? a1 + a + (double)bU[ps[j - 1]] : LZERO_D;
-            }
-            double x = LZERO_D;
-            for (int i = 1; i < N - 1; i++) {
-               double a = A[i * N + N - 1];
-               if (a > LSMALL_D) x = ladd<EXACT>(x, cur[so + i] + a);
-            }
-            cur[so + N - 1] = x;
-         }
-      } else {
-         // ---- alpha beam, HFB.c:701-722, from mpSelf/exq of frame t-1
-         const int loP = qLo[t - 1], hiP = qHi[t - 1];
-         int mySq = 0x7fffffff;
-         for (int q = tid; q < Q; q += nt) {
-            if (q < loP) continue;
-            double mp = fmax((q > 0) ? exq[q - 1] : LZERO_D, mpSelf[q]);
-            if (!(pr - mp > minF)) mySq = min(mySq, q);
-         }
-         mySq = warp_mini(mySq);
-         if (lane == 0) sm.wlo[wid] = mySq;
-         __syncthreads();
-         int nsq = 0x7fffffff;
-         for (int w = 0; w < nw; w++) nsq = min(nsq, sm.wlo[w]);
-         if (nsq > hiT) { if (tid == 0) out->status = HFB_UTT_EALPHA; return; }   // HError 7390
-         if (nsq < loT) nsq = loT;
-         const int eq0 = (hiP < Q - 1) ? hiP + 1 : hiP;
-         int myEq = -1;
-         for (int q = tid; q < Q; q += nt) {
-            if (q > eq0) continue;
-            double mp = (q > 0) ? exq[q - 1] : LZERO_D;
-            if (q > 0 && q - 1 > nsq) {                                   // chain over a preceding tee model
-               const int N1 = sm.sN[q - 1];
-               if ((double)A0[sm.sTr[q - 1] + N1 - 1] > LSMALL_D && q >= 2) mp = fmax(mp, exq[q - 2]);
-            }
-            mp = fmax(mp, mpSelf[q]);
-            if (!(pr - mp > minF)) myEq = max(myEq, q);
-         }
-         myEq = warp_maxi(myEq);
-         if (lane == 0) sm.whi[wid] = myEq;
-         __syncthreads();
-         int neq = -1;
-         for (int w = 0; w < nw; w++) neq = max(neq, sm.whi[w]);
-         if (neq < nsq) { if (tid == 0) out->status = HFB_UTT_EALPHA; return; }
-         while (neq < Q - 1 && sm.sDms[neq] == 0) neq++;
-         if (neq > hiT) neq = hiT;
-         sq = nsq; eq = neq;
-         // ---- alpha column, HFB.c:729-771
-         for (int q = tid; q < Q; q += nt) {
-            const int N = sm.sN[q], so = sm.sSoff[q];
-            if (q < sq || q > eq) { for (int i = 0; i < N; i++) cur[so + i] = LZERO_D; continue; }
-            const float *A = A0 + sm.sTr[q];
-            const int *ps = posSlot + sm.sPoff[q];
-            const float *bt = bU + (size_t)t * J;
-            double a1 = LZERO_D;
-            if (q > 0) {
-               const int N1 = sm.sN[q - 1];
-               a1 = prev[sm.sSoff[q - 1] + N1 - 1];
-               const double a1N = A0[sm.sTr[q - 1] + N1 - 1];
-               if (q > sq && a1N > LSMALL_D) {                            // through a tee model this frame
-                  double y = (q >= 2) ? prev[sm.sSoff[q - 2] + sm.sN[q - 2] - 1] : LZERO_D;
-                  a1 = ladd<EXACT>(a1, y + a1N);
-               }
-            }
-            cur[so] = a1;
-            for (int j = 1; j < N - 1; j++) {
-               double a = A[j];
-               double x = (a > LSMALL_D) ? a + a1 : LZERO_D;
-               for (int i = 1; i < N - 1; i++) {
-                  double aij = A[i * N + j], y = prev[so + i];
-                  if (aij > LSMALL_D && y > LSMALL_D) x = ladd<EXACT>(x, y + aij);
-               }
-               cur[so + j] = x + (double)bt[ps[j - 1]];
-            }
-            double x = LZERO_D;
-            for (int i = 1; i < N - 1; i++) {
-               double a = A[i * N + N - 1], y = cur[so + i];
-               if (a > LSMALL_D && y > LSMALL_D) x = ladd<EXACT>(x, y + a);
-            }
-            cur[so + N - 1] = x;
-         }
-      }
-      if (tid == 0) { sqA[t] = (short)sq; eqA[t] = (short)eq; }
-
-      // ---- accumulation for the models inside the alpha beam (StepForward, HFB.c:1790-1806)
-      const float *bt = bU + (size_t)t * J;
-      const bool haveT1 = (t + 1 < T);
-      const int loT1 = haveT1 ? qLo[t + 1] : 1, hiT1 = haveT1 ? qHi[t + 1] : 0;
-      for (int q = tid; q < Q; q += nt) {
-         if (q < sq || q > eq) { mpSelf[q] = LZERO_D; exq[q] = LZERO_D; continue; }
-         const int N = sm.sN[q], so = sm.sSoff[q];
-         const float *A = A0 + sm.sTr[q];
-         const int *ps = posSlot + sm.sPoff[q];
-         const double *bq = betaU + (size_t)t * S + so;
-         const bool hasB1 = haveT1 && q >= loT1 && q <= hiT1;
-         const bool hasBq1 = (q < Q - 1) && (q + 1 >= loT) && (q + 1 <= hiT);
-         const double bq1 = hasBq1 ? betaU[(size_t)t * S + sm.sSoff[q + 1]] : LZERO_D;
-         const double a1N = A[N - 1];
-         const int gq = u.modOff + q;
-         if (W.mTmin[gq] > t) W.mTmin[gq] = t;
-         W.mTmax[gq] = t;
-         double mps = LZERO_D;
-         for (int i = 0; i < N - 1; i++) mps = fmax(mps, cur[so + i] + bq[i]);
-         mpSelf[q] = mps;
-         exq[q] = cur[so + N - 1] + bq[N - 1];
-         if (doTr) {
-            double *tacc = W.acc + W.mTrAcc[gq], *oacc = W.acc + W.mTrOcc[gq];
-            // SetOcct (:399-418) feeding ta->occ (:1388-1389)
-            for (int i = 0; i < N - 1; i++) {
-               double x = cur[so + i] + bq[i];
-               if (i == 0 && hasBq1 && a1N > LSMALL_D) x = ladd<EXACT>(x, cur[so] + bq1 + a1N);
-               x -= pr;
-               if (x > MINEARG_D) { float o = (float)exp(x); if (o != 0.f) atomicAdd(&oacc[i], (double)o); }
-            }
-            // UpTranParms (:1390-1410)
-            for (int j = 1; j < N - 1; j++) {
-               double x = cur[so] + (double)A[j] + (double)bt[ps[j - 1]] + bq[j] - pr;
-               if (x > MINEARG_D) atomicAdd(&tacc[j], exp(x));
-            }
-            if (hasB1) {
-               const double *bq1t = betaU + (size_t)(t + 1) * S + so;
-               const float *bt1 = bt + J;
-               for (int i = 1; i < N - 1; i++)
-                  for (int j = 1; j < N - 1; j++) {
-                     double x = cur[so + i] + (double)A[i * N + j] + (double)bt1[ps[j - 1]] + bq1t[j] - pr;
-                     if (x > MINEARG_D) atomicAdd(&tacc[i * N + j], exp(x));
-                  }
-            }
-            for (int i = 1; i < N - 1; i++) {
-               double x = cur[so + i] + (double)A[i * N + N - 1] + bq[N - 1] - pr;
-               if (x > MINEARG_D) atomicAdd(&tacc[i * N + N - 1], exp(x));
-            }
-            if (a1N > LSMALL_D && hasBq1) {
-               double x = cur[so] + a1N + bq1 - pr;
-               if (x > MINEARG_D) atomicAdd(&tacc[N - 1], exp(x));
-            }
-         }
-         if (doMix) {
-            const int *pst = posState + sm.sPoff[q];
-            double *oc = occU + (size_t)t * P + sm.sPoff[q];
-            for (int j = 1; j < N - 1; j++) {
-               int s = pst[j - 1];
-               int Mn = M.stateMixOff[s + 1] - M.stateMixOff[s];
-               double x;
-               if (Mn == 1) x = cur[so + j] + bq[j] - pr;                 // :1575-1576
-               else {                                                     // initx, :1480-1489
-                  x = (double)A[j] + cur[so];
-                  if (t > 0)
-                     for (int i = 1; i < N - 1; i++) {
-                        double a = A[i * N + j];
-                        if (a > LSMALL_D) x = ladd<EXACT>(x, prev[so + i] + a);
-                     }
-                  x += bq[j] - pr;
-               }
-               oc[j - 1] = x;
-            }
-         }
-      }
-      __syncthreads();
-      { double *tmp = cur; cur = prev; prev = tmp; }
-   }
-   if (tid == 0) {
-      atomicAdd(&W.acc[M.L.totalT], (double)T);                          // HERest.c:779-780
-      atomicAdd(&W.acc[M.L.totalPr], pr);
-      atomicAdd(&W.acc[M.L.numOk], 1.0);
-   }
-}
-
-// ------------------------------------------------------------------------------------------
-// K4: per-mixture statistics, one warp per emitting state position
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-stats_kernel(DevModel M, Wave W, const PosRef *__restrict__ pos, int numPos)
-{
-   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-   if (wg >= numPos) return;
-   const PosRef p = pos[wg];
-   if (W.out[p.utt].status != 0) return;
-   const UttDesc u = W.utt[p.utt];
-   const int gq = u.modOff + p.q;
-   const int tmin = W.mTmin[gq], tmax = W.mTmax[gq];
-   if (tmin > tmax) return;
-   const int D = M.D, Dp = M.Dp, P = u.P;
-   const int pp = W.mPoff[gq] + p.j;
-   const int s = W.posState[u.posOff + pp];
-   const int mo = M.stateMixOff[s], Mn = M.stateMixOff[s + 1] - mo;
-   const double *occ = W.occ + u.occOff + pp;
-   const short *sqA = W.sq + u.frameBase, *eqA = W.eq + u.frameBase;
-   const float *feat = W.feat + (size_t)u.featOff * D;
-   const double minF = W.minFrwdP;
-   const int uf = W.uFlags;
-   const bool upM = (uf & HFB_UPMEANS) != 0, upV = (uf & HFB_UPVARS) != 0, upW = (uf & HFB_UPMIXES) != 0;
-   const int k0 = lane, k1 = lane + 32;            // D <= 64 on this path (checked at create)
-   double wsum = 0.0;
-   for (int m = 0; m < Mn; m++) {
-      const float wt = M.mixLogWt[mo + m];
-      if (!(wt > LMINMIX_F)) continue;                                   // HFB.c:1573
-      const int g = M.mixGauss[mo + m];
-      const float mu0 = (k0 < D) ? M.mean[(size_t)g * Dp + k0] : 0.f, mu1 = (k1 < D) ? M.mean[(size_t)g * Dp + k1] : 0.f;
-      const float iv0 = (k0 < D) ? M.ivar[(size_t)g * Dp + k0] : 0.f, iv1 = (k1 < D) ? M.ivar[(size_t)g * Dp + k1] : 0.f;
-      const float gc = M.gconst[g];
-      double am0 = 0, am1 = 0, av0 = 0, av1 = 0, aocc = 0;
-      for (int t = tmin; t <= tmax; t++) {
-         if (p.q < sqA[t] || p.q > eqA[t]) continue;
-         double x = occ[(size_t)t * P];
-         if (x < -1.0e29) continue;                                       // pre-pruned by the alpha kernel
-         const float *o = feat + (size_t)t * D;
-         const float d0 = (k0 < D) ? o[k0] - mu0 : 0.f, d1 = (k1 < D) ? o[k1] - mu1 : 0.f;
-         if (Mn > 1) {
-            float part = warp_sumf(fmaf(d0 * d0, iv0, d1 * d1 * iv1));
-            float mixp = -0.5f * (gc + part);
-            x = x + (double)wt + (double)mixp;                            // :1581-1599
-         }
-         if (-x < minF) {                                                 // :1606
-            const double Lr = exp(x);
-            aocc += Lr;
-            const double z0 = (double)d0 * Lr, z1 = (double)d1 * Lr;
-            am0 += z0; am1 += z1;
-            av0 += z0 * (double)d0; av1 += z1 * (double)d1;
-         }
-      }
-      if (aocc > 0.0) {
-         if (upM) {
-            double *mu = W.acc + M.L.muSum + (size_t)M.meanId[g] * D;
-            if (k0 < D) atomicAdd(&mu[k0], am0);
-            if (k1 < D) atomicAdd(&mu[k1], am1);
-            if (lane == 0) atomicAdd(&W.acc[M.L.muOcc + M.meanId[g]], aocc);
-         }
-         if (upV) {
-            double *va = W.acc + M.L.vaSum + (size_t)M.varId[g] * D;
-            if (k0 < D) atomicAdd(&va[k0], av0);
-            if (k1 < D) atomicAdd(&va[k1], av1);
-            if (lane == 0) atomicAdd(&W.acc[M.L.vaOcc + M.varId[g]], aocc);
-         }
-         if (upW && lane == 0) atomicAdd(&W.acc[M.L.wtC + mo + m], aocc);
-         wsum += aocc;
-      }
-   }
-   if (lane == 0 && wsum > 0.0) atomicAdd(&W.acc[M.L.wtOcc + s], wsum);  // :1736
-}

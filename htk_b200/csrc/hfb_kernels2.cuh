@@ -250,15 +250,21 @@ __host__ __device__ inline size_t stats2_smem_bytes(int D)
 }
 
 __global__ void __launch_bounds__(32 * ST_WARPS)
-stats2_kernel(DevModel M, Wave W, const PosRef *__restrict__ pos, int numPos)
+stats2_kernel(DevModel M, Wave W)
 {
    extern __shared__ __align__(16) unsigned char smraw[];
    const int wInB = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const int wg = blockIdx.x * ST_WARPS + wInB;
-   if (wg >= numPos) return;
-   const PosRef p = pos[wg];
+   if (wg >= W.totalPos) return;
+   struct { int utt, q, j; } p;
+   p.utt = upper_index(W.posPre, W.numUtt, wg);
    if (W.out[p.utt].status != 0) return;
    const UttDesc u = W.utt[p.utt];
+   {
+      const int lp = wg - W.posPre[p.utt];
+      p.q = upper_index(W.mPoff + u.modOff, u.Q, lp);
+      p.j = lp - W.mPoff[u.modOff + p.q];
+   }
    const int gq = u.modOff + p.q;
    const int tmin = W.mTmin[gq], tmax = W.mTmax[gq];
    if (tmin > tmax) return;

@@ -88,7 +88,10 @@ struct hfbgpu_ctx {
    DevBuf<float> dB;
    DevBuf<double> dBeta, dOcc;
    DevBuf<short> dBeams;             // 4 * frames
-   DevBuf<unsigned char> dTables;
+   DevBuf<unsigned char> dTables, dScratch;
+   DevBuf<int> dHmmN, dHmmStateOff, dHmmState, dHmmTrans, dTransOffF, dTransMinDur;
+   DevBuf<long long> dTranAccOff, dTranOccOff;
+   std::vector<unsigned char> blobScratch;
    unsigned char *hTables = nullptr; // pinned staging
    size_t hTablesCap = 0;
    UttOut *hOut = nullptr;           // pinned
@@ -271,7 +274,15 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
        (rc = upload(c->dStateMixOff, m->stateMixOff, (size_t)h.J + 1, c->stream)) ||
        (rc = upload(c->dMixGauss, m->mixGauss, (size_t)sumM, c->stream)) ||
        (rc = upload(c->dMixLogWt, m->mixLogWt, (size_t)sumM, c->stream)) ||
-       (rc = upload(c->dTransLogA, h.transLogA.data(), h.transLogA.size(), c->stream))) {
+       (rc = upload(c->dTransLogA, h.transLogA.data(), h.transLogA.size(), c->stream)) ||
+       (rc = upload(c->dHmmN, h.hmmN.data(), h.hmmN.size(), c->stream)) ||
+       (rc = upload(c->dHmmStateOff, h.hmmStateOff.data(), h.hmmStateOff.size(), c->stream)) ||
+       (rc = upload(c->dHmmState, h.hmmState.data(), h.hmmState.size(), c->stream)) ||
+       (rc = upload(c->dHmmTrans, h.hmmTrans.data(), h.hmmTrans.size(), c->stream)) ||
+       (rc = upload(c->dTransOffF, h.transOff.data(), (size_t)h.numTrans, c->stream)) ||
+       (rc = upload(c->dTransMinDur, h.minDur.data(), h.minDur.size(), c->stream)) ||
+       (rc = upload(c->dTranAccOff, h.tranAccOff.data(), h.tranAccOff.size(), c->stream)) ||
+       (rc = upload(c->dTranOccOff, h.tranOccOff.data(), h.tranOccOff.size(), c->stream))) {
       hfbgpu_destroy(c); return rc;
    }
    CK(cudaStreamSynchronize(c->stream));
@@ -281,6 +292,9 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
    d.meanId = c->dMeanId.p; d.varId = c->dVarId.p;
    d.stateMixOff = c->dStateMixOff.p; d.mixGauss = c->dMixGauss.p; d.mixLogWt = c->dMixLogWt.p;
    d.transLogA = c->dTransLogA.p;
+   d.hmmN = c->dHmmN.p; d.hmmStateOff = c->dHmmStateOff.p; d.hmmState = c->dHmmState.p; d.hmmTrans = c->dHmmTrans.p;
+   d.transOffF = c->dTransOffF.p; d.transMinDur = c->dTransMinDur.p;
+   d.tranAccOff = c->dTranAccOff.p; d.tranOccOff = c->dTranOccOff.p;
    d.L = c->L;
 
    if ((rc = c->dAcc.reserve((size_t)c->L.count))) { hfbgpu_destroy(c); return rc; }
@@ -302,8 +316,6 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
    int maxOpt = c->maxSmemOptin;
    cudaFuncSetAttribute(beta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(beta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
-   cudaFuncSetAttribute(alpha_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
-   cudaFuncSetAttribute(alpha_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(alpha_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(alpha_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(stats2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
@@ -321,7 +333,9 @@ extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
    c->dMeanId.release(); c->dVarId.release(); c->dStateMixOff.release(); c->dMixGauss.release();
    gmm_tc_release(c->tc);
    c->dAcc.release(); c->dFeat.release(); c->dB.release(); c->dBeta.release(); c->dOcc.release();
-   c->dBeams.release(); c->dTables.release();
+   c->dBeams.release(); c->dTables.release(); c->dScratch.release();
+   c->dHmmN.release(); c->dHmmStateOff.release(); c->dHmmState.release(); c->dHmmTrans.release();
+   c->dTransOffF.release(); c->dTransMinDur.release(); c->dTranAccOff.release(); c->dTranOccOff.release();
    if (c->hTables) cudaFreeHost(c->hTables);
    if (c->hOut) cudaFreeHost(c->hOut);
    if (c->hBeams) cudaFreeHost(c->hBeams);
@@ -383,155 +397,149 @@ extern "C" int hfbgpu_reset_stats(hfbgpu_ctx *c) { if (!c) return HFB_EINVAL; me
 extern "C" int hfbgpu_set_timing(hfbgpu_ctx *c, int on) { if (!c) return HFB_EINVAL; c->timing = on != 0; return HFB_OK; }
 
 // ------------------------------------------------------------------------------------------
-// wave construction
+// wave construction: the host only sizes things; the tables are built by prep_kernel
 // ------------------------------------------------------------------------------------------
 namespace {
 
 struct WaveTables {
    std::vector<UttDesc> utt;
    std::vector<UttOut> out;
-   std::vector<int> mN, mTrans, mSoff, mPoff, mDms, mPre, mSuf, mHmm;
-   std::vector<long long> mTrAcc, mTrOcc;
-   std::vector<int> slotState, posSlot, posState;
-   std::vector<PosRef> pos;
-   std::vector<GmmTile> tiles;
+   std::vector<int> posPre, tilePre;
    std::vector<int2> tcItems;        // (utterance, first frame) blocks of TC_BM frames for the tcgen05 kernel
    std::vector<int> uttIndex;        // index in the caller's batch
    long long bFloats = 0, betaDoubles = 0, occDoubles = 0;
+   long long totalQ = 0, totalP = 0, tiles = 0;
    int maxQ = 0, maxS = 0;
-   long long frames = 0, frame0 = 0;
+   int lab0 = 0;                     // first label of the wave in the caller's label array
    void clear()
    {
-      utt.clear(); out.clear(); mN.clear(); mTrans.clear(); mSoff.clear(); mPoff.clear(); mDms.clear();
-      mPre.clear(); mSuf.clear(); mHmm.clear(); mTrAcc.clear(); mTrOcc.clear();
-      slotState.clear(); posSlot.clear(); posState.clear(); pos.clear(); tiles.clear(); tcItems.clear(); uttIndex.clear();
-      bFloats = betaDoubles = occDoubles = 0; maxQ = maxS = 0; frames = 0;
+      utt.clear(); out.clear(); posPre.clear(); tilePre.clear(); tcItems.clear(); uttIndex.clear();
+      bFloats = betaDoubles = occDoubles = 0; totalQ = totalP = tiles = 0; maxQ = maxS = 0; lab0 = 0;
    }
 };
 
-// CreateInsts (HFB.c:508-574) for one utterance; appends to the wave tables.
-// Returns the workspace bytes the utterance needs.
-size_t add_utterance(const HostModel &h, WaveTables &w, int uidx, int T, const int32_t *lab, int Q,
-                     long long featOff, long long frameBase, std::vector<int> &slotOf /* scratch [J], -1 */)
+// Sizes one utterance (sum of N over its labels) and appends its descriptor.
+// Returns the workspace bytes it needs.
+size_t add_utterance(const HostModel &h, WaveTables &w, int uidx, int T, const int32_t *lab, int Q, int labOff,
+                     long long featOff)
 {
    UttDesc u;
    memset(&u, 0, sizeof(u));
-   UttOut o; o.status = 0; o.retries = 0; o.pr = HFB_LZERO; o.thresh = 0.0;
-   u.T = T; u.Q = Q; u.modOff = (int)w.mN.size(); u.slotOff = (int)w.slotState.size();
-   u.posOff = (int)w.posSlot.size(); u.featOff = featOff; u.frameBase = frameBase;
-   int S = 0, Pp = 0, J = 0, qt = 0;
-   bool bad = (Q < 1 || T < 1);
+   UttOut o;
+   memset(&o, 0, sizeof(o));
+   o.pr = HFB_LZERO;
    const int uLocal = (int)w.utt.size();
+   int S = 0;
+   bool bad = (Q < 1 || T < 1);
    for (int q = 0; q < Q && !bad; q++) {
-      int p = lab[q];
-      if (p < 0 || p >= h.P) { bad = true; break; }
+      const int p = lab[q];
+      if (p < 0 || p >= h.P) bad = true; else S += h.hmmN[p];
    }
-   if (!bad) {
-      for (int q = 0; q < Q; q++) {
-         int p = lab[q], tr = h.hmmTrans[p], N = h.hmmN[p], dms = h.minDur[tr];
-         w.mN.push_back(N); w.mTrans.push_back(h.transOff[tr]); w.mSoff.push_back(S); w.mPoff.push_back(Pp);
-         w.mDms.push_back(dms); w.mPre.push_back(qt); w.mHmm.push_back(p);
-         w.mTrAcc.push_back(h.tranAccOff[tr]); w.mTrOcc.push_back(h.tranOccOff[tr]);
-         if (q > 0 && dms == 0 && w.mDms[u.modOff + q - 1] == 0) o.status = HFB_UTT_ETEE;   // :557
-         for (int j = 0; j < N - 2; j++) {
-            int s = h.hmmState[h.hmmStateOff[p] + j];
-            if (slotOf[s] < 0) { slotOf[s] = J++; w.slotState.push_back(s); }
-            w.posSlot.push_back(slotOf[s]); w.posState.push_back(s);
-            w.pos.push_back(PosRef{uLocal, q, j});
-         }
-         S += N; Pp += N - 2; qt += dms;
-      }
-      for (int k = 0; k < J; k++) slotOf[w.slotState[u.slotOff + k]] = -1;
-      w.mSuf.resize(w.mN.size());
-      int acc = 0;
-      for (int q = Q - 1; q >= 0; q--) { w.mSuf[u.modOff + q] = acc; acc += w.mDms[u.modOff + q]; }
-      if (w.mDms[u.modOff] == 0 || w.mDms[u.modOff + Q - 1] == 0) o.status = HFB_UTT_ETEE;          // :564
-      if (o.status == 0 && qt > T) o.status = HFB_UTT_SKIPPED;                                      // :1339-1343
-   } else {
-      o.status = HFB_UTT_ETEE; Q = 0; u.Q = 0;
-   }
-   u.S = S; u.P = Pp; u.J = J;
+   if (bad) { o.status = HFB_UTT_ETEE; Q = 0; S = 0; }
+   const int Pp = S - 2 * Q;
+   u.T = T; u.Q = Q; u.S = S; u.P = Pp; u.J = Pp;
+   u.labOff = labOff; u.modOff = (int)w.totalQ; u.slotOff = (int)w.totalP; u.posOff = (int)w.totalP;
+   u.featOff = featOff; u.frameBase = featOff;
+   u.bOff = w.bFloats; u.betaOff = w.betaDoubles; u.occOff = w.occDoubles;
+   w.posPre.push_back((int)w.totalP);
+   w.tilePre.push_back((int)w.tiles);
    size_t bytes = 0;
-   if (o.status == 0) {
-      u.bOff = w.bFloats; u.betaOff = w.betaDoubles; u.occOff = w.occDoubles;
-      w.bFloats += (long long)T * J; w.betaDoubles += (long long)T * S; w.occDoubles += (long long)T * Pp;
-      bytes = (size_t)T * ((size_t)J * 4 + (size_t)S * 8 + (size_t)Pp * 8);
-      for (int t0 = 0; t0 < T; t0 += GT_FR)
-         for (int s0 = 0; s0 < J; s0 += GT_SL) w.tiles.push_back(GmmTile{uLocal, t0, s0});
+   if (!bad) {
+      w.bFloats += (long long)T * Pp; w.betaDoubles += (long long)T * S; w.occDoubles += (long long)T * Pp;
+      bytes = (size_t)T * ((size_t)Pp * 12 + (size_t)S * 8);
+      w.totalQ += Q; w.totalP += Pp;
+      w.tiles += (long long)((T + GT_FR - 1) / GT_FR) * ((Pp + GT_SL - 1) / GT_SL);
       for (int t0 = 0; t0 < T; t0 += TC_BM) w.tcItems.push_back(make_int2(uLocal, t0));
       w.maxQ = std::max(w.maxQ, Q); w.maxS = std::max(w.maxS, S);
-   } else {
-      // keep table sizes consistent but give the kernels nothing to do
-      w.pos.resize(w.pos.size() - (size_t)Pp);
    }
    w.utt.push_back(u); w.out.push_back(o); w.uttIndex.push_back(uidx);
    return bytes;
 }
 
 template <class T>
-size_t blob_put(std::vector<unsigned char> &blob, const std::vector<T> &v)
+size_t blob_put(std::vector<unsigned char> &blob, const T *v, size_t n)
 {
    size_t off = (blob.size() + 255) & ~(size_t)255;
-   blob.resize(off + v.size() * sizeof(T) + 8);
-   if (!v.empty()) memcpy(blob.data() + off, v.data(), v.size() * sizeof(T));
+   blob.resize(off + n * sizeof(T) + 8);
+   if (n) memcpy(blob.data() + off, v, n * sizeof(T));
    return off;
 }
+template <class T>
+size_t blob_put(std::vector<unsigned char> &blob, const std::vector<T> &v) { return blob_put(blob, v.data(), v.size()); }
+
+// device scratch written by prep_kernel / alpha kernel
+struct ScratchLayout {
+   size_t mN, mTrans, mSoff, mPoff, mDms, mPre, mSuf, mHmm, mTmin, mTmax, mTrAcc, mTrOcc, slotState, posSlot, posState, bytes;
+   ScratchLayout(long long totalQ, long long totalP)
+   {
+      size_t o = 0;
+      auto take = [&](size_t n, size_t el) { size_t r = o; o += ((n * el + 255) & ~(size_t)255) + 256; return r; };
+      const size_t q = (size_t)totalQ + 1, pp = (size_t)totalP + 1;
+      mTrAcc = take(q, 8); mTrOcc = take(q, 8);
+      mN = take(q, 4); mTrans = take(q, 4); mSoff = take(q, 4); mPoff = take(q, 4); mDms = take(q, 4);
+      mPre = take(q, 4); mSuf = take(q, 4); mHmm = take(q, 4); mTmin = take(q, 4); mTmax = take(q, 4);
+      slotState = take(pp, 4); posSlot = take(pp, 4); posState = take(pp, 4);
+      bytes = o;
+   }
+};
 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
 // run one wave
 // ------------------------------------------------------------------------------------------
-static int run_wave(hfbgpu_ctx *c, WaveTables &w, const float *dFeat, long long waveFrame0, long long waveFrames,
-                    hfb_utt_result *res, const hfb_beams *beams, long long batchFrame0)
+static int run_wave(hfbgpu_ctx *c, WaveTables &w, const int32_t *labBase, const float *dFeat, long long waveFrame0,
+                    long long waveFrames, hfb_utt_result *res, const hfb_beams *beams)
 {
    const int nU = (int)w.utt.size();
    if (nU == 0) return HFB_OK;
    int rc;
-   // ---- pack + upload tables
-   std::vector<unsigned char> blob;
-   size_t oUtt = blob_put(blob, w.utt), oOut = blob_put(blob, w.out);
-   size_t oN = blob_put(blob, w.mN), oTr = blob_put(blob, w.mTrans), oSo = blob_put(blob, w.mSoff),
-          oPo = blob_put(blob, w.mPoff), oDm = blob_put(blob, w.mDms), oPre = blob_put(blob, w.mPre),
-          oSuf = blob_put(blob, w.mSuf), oHm = blob_put(blob, w.mHmm), oTa = blob_put(blob, w.mTrAcc),
-          oTo = blob_put(blob, w.mTrOcc);
-   std::vector<int> tminmax(w.mN.size() * 2, 0);
-   size_t oTm = blob_put(blob, tminmax);
-   size_t oSs = blob_put(blob, w.slotState), oPs = blob_put(blob, w.posSlot), oPst = blob_put(blob, w.posState);
-   size_t oPos = blob_put(blob, w.pos), oTl = blob_put(blob, w.tiles), oIt = blob_put(blob, w.tcItems);
+   // ---- pack + upload the (small) host tables
+   w.posPre.push_back((int)w.totalP);
+   w.tilePre.push_back((int)w.tiles);
+   std::vector<unsigned char> &blob = c->blobScratch;
+   blob.clear();
+   size_t oUtt = blob_put(blob, w.utt), oOut = blob_put(blob, w.out), oPp = blob_put(blob, w.posPre),
+          oTp = blob_put(blob, w.tilePre), oIt = blob_put(blob, w.tcItems);
+   const size_t nLab = (size_t)w.utt.back().labOff + (size_t)w.utt.back().Q;
+   size_t oLab = blob_put(blob, labBase, nLab);
    if (blob.size() > c->hTablesCap) {
       if (c->hTables) cudaFreeHost(c->hTables);
       c->hTablesCap = blob.size() * 2;
       CK(cudaMallocHost(&c->hTables, c->hTablesCap));
    }
    memcpy(c->hTables, blob.data(), blob.size());
-   if ((rc = c->dTables.reserve(blob.size()))) return rc;
+   const ScratchLayout sl(w.totalQ, w.totalP);
+   if ((rc = c->dTables.reserve(blob.size())) || (rc = c->dScratch.reserve(sl.bytes))) return rc;
    CK(cudaMemcpyAsync(c->dTables.p, c->hTables, blob.size(), cudaMemcpyHostToDevice, c->stream));
    c->stats.h2dBytes += (int64_t)blob.size();
    if ((rc = c->dB.reserve((size_t)w.bFloats + 1)) || (rc = c->dBeta.reserve((size_t)w.betaDoubles + 1)) ||
        (rc = c->dOcc.reserve((size_t)w.occDoubles + 1)) || (rc = c->dBeams.reserve((size_t)waveFrames * 4 + 4)))
       return rc;
 
-   unsigned char *base = c->dTables.p;
+   unsigned char *base = c->dTables.p, *sc = c->dScratch.p;
    Wave W;
    memset(&W, 0, sizeof(W));
-   W.utt = (const UttDesc *)(base + oUtt); W.out = (UttOut *)(base + oOut); W.numUtt = nU;
-   W.mN = (const int *)(base + oN); W.mTrans = (const int *)(base + oTr); W.mSoff = (const int *)(base + oSo);
-   W.mPoff = (const int *)(base + oPo); W.mDms = (const int *)(base + oDm); W.mPre = (const int *)(base + oPre);
-   W.mSuf = (const int *)(base + oSuf); W.mHmm = (const int *)(base + oHm);
-   W.mTrAcc = (const long long *)(base + oTa); W.mTrOcc = (const long long *)(base + oTo);
-   W.mTmin = (int *)(base + oTm); W.mTmax = W.mTmin + w.mN.size();
-   W.slotState = (const int *)(base + oSs); W.posSlot = (const int *)(base + oPs); W.posState = (const int *)(base + oPst);
+   W.utt = (UttDesc *)(base + oUtt); W.out = (UttOut *)(base + oOut); W.numUtt = nU;
+   W.lab = (const int *)(base + oLab); W.posPre = (const int *)(base + oPp); W.tilePre = (const int *)(base + oTp);
+   W.totalPos = (int)w.totalP;
+   W.mN = (int *)(sc + sl.mN); W.mTrans = (int *)(sc + sl.mTrans); W.mSoff = (int *)(sc + sl.mSoff);
+   W.mPoff = (int *)(sc + sl.mPoff); W.mDms = (int *)(sc + sl.mDms); W.mPre = (int *)(sc + sl.mPre);
+   W.mSuf = (int *)(sc + sl.mSuf); W.mHmm = (int *)(sc + sl.mHmm);
+   W.mTrAcc = (long long *)(sc + sl.mTrAcc); W.mTrOcc = (long long *)(sc + sl.mTrOcc);
+   W.mTmin = (int *)(sc + sl.mTmin); W.mTmax = (int *)(sc + sl.mTmax);
+   W.slotState = (int *)(sc + sl.slotState); W.posSlot = (int *)(sc + sl.posSlot); W.posState = (int *)(sc + sl.posState);
    W.feat = dFeat;
    W.b = c->dB.p; W.beta = c->dBeta.p; W.occ = c->dOcc.p;
    W.qLo = c->dBeams.p; W.qHi = W.qLo + waveFrames; W.sq = W.qHi + waveFrames; W.eq = W.sq + waveFrames;
    W.acc = c->dAcc.p;
    W.pruneInit = c->opt.pruneInit; W.pruneInc = c->opt.pruneInc; W.pruneLim = c->opt.pruneLim;
    W.minFrwdP = (double)c->opt.minFrwdP; W.uFlags = c->opt.uFlags;
-   const PosRef *dPos = (const PosRef *)(base + oPos);
-   const GmmTile *dTiles = (const GmmTile *)(base + oTl);
 
    const bool tm = c->timing;
+   // ---- K0: tables
+   prep_kernel<<<nU, 128, 0, c->stream>>>(c->dm, W);
+   c->stats.launches++; c->stats.launchesMisc++;
    if (tm) cudaEventRecord(c->ev[0], c->stream);
    // ---- K1
    int gk = c->opt.gmmKernel;
@@ -541,39 +549,36 @@ static int run_wave(hfbgpu_ctx *c, WaveTables &w, const float *dFeat, long long 
       if ((rc = gmm_tc_launch(c->tc, c->dm, W, waveFrames, (const int2 *)(base + oIt), (int)w.tcItems.size(),
                               c->smCount, c->stream, &nl))) return rc;
       c->stats.launches += nl; c->stats.launchesGmm += nl;
-   } else if (!w.tiles.empty()) {
+   } else if (w.tiles > 0) {
       size_t smem = sizeof(float) * ((size_t)c->dm.D * GT_FR + (size_t)GT_FR * (GT_SL + 1));
-      gmm_fp32_kernel<<<(unsigned)w.tiles.size(), 128, smem, c->stream>>>(c->dm, W, dTiles);
+      gmm_fp32_kernel<<<(unsigned)w.tiles, 128, smem, c->stream>>>(c->dm, W);
       c->stats.launches++; c->stats.launchesGmm++;
    }
    if (tm) cudaEventRecord(c->ev[1], c->stream);
    // ---- K2 / K3
-   int nt = std::min(256, std::max(32, (w.maxQ + 31) & ~31));
-   size_t rsm = rec_smem_bytes(w.maxS, w.maxQ);
-   if (rsm > (size_t)c->maxSmemOptin) { g_lastError = "utterance too long for the shared-memory window"; return HFB_EUNSUPPORTED; }
-   const bool exact = getenv("HFBGPU_EXACT_LADD") != nullptr;
-   if (exact) beta_kernel<true><<<nU, nt, rsm, c->stream>>>(c->dm, W);
-   else beta_kernel<false><<<nU, nt, rsm, c->stream>>>(c->dm, W);
-   if (tm) cudaEventRecord(c->ev[2], c->stream);
-   static const bool oldAlpha = getenv("HFBGPU_OLD_ALPHA") != nullptr, oldStats = getenv("HFBGPU_OLD_STATS") != nullptr;
-   const size_t asm_ = alpha_warp_smem_bytes(w.maxS, w.maxQ);
-   if (oldAlpha || asm_ > (size_t)c->maxSmemOptin) {
-      if (exact) alpha_kernel<true><<<nU, nt, rsm, c->stream>>>(c->dm, W);
-      else alpha_kernel<false><<<nU, nt, rsm, c->stream>>>(c->dm, W);
-   } else {
+   if (w.maxQ > 0) {
+      int nt = std::min(256, std::max(32, (w.maxQ + 31) & ~31));
+      size_t rsm = rec_smem_bytes(w.maxS, w.maxQ), asm_ = alpha_warp_smem_bytes(w.maxS, w.maxQ);
+      if (rsm > (size_t)c->maxSmemOptin || asm_ > (size_t)c->maxSmemOptin) {
+         g_lastError = "utterance too long for the shared-memory window"; return HFB_EUNSUPPORTED;
+      }
+      const bool exact = getenv("HFBGPU_EXACT_LADD") != nullptr;
+      if (exact) beta_kernel<true><<<nU, nt, rsm, c->stream>>>(c->dm, W);
+      else beta_kernel<false><<<nU, nt, rsm, c->stream>>>(c->dm, W);
+      if (tm) cudaEventRecord(c->ev[2], c->stream);
       if (exact) alpha_warp_kernel<true><<<nU, 32, asm_, c->stream>>>(c->dm, W);
       else alpha_warp_kernel<false><<<nU, 32, asm_, c->stream>>>(c->dm, W);
+      if (tm) cudaEventRecord(c->ev[3], c->stream);
+      c->stats.launches += 2; c->stats.launchesBeta++; c->stats.launchesAlpha++;
+      // ---- K4
+      if (w.totalP > 0 && (c->opt.uFlags & (HFB_UPMEANS | HFB_UPVARS | HFB_UPMIXES))) {
+         stats2_kernel<<<(unsigned)((w.totalP + ST_WARPS - 1) / ST_WARPS), 32 * ST_WARPS, stats2_smem_bytes(c->dm.D), c->stream>>>(c->dm, W);
+         c->stats.launches++; c->stats.launchesStats++;
+      }
+      if (tm) cudaEventRecord(c->ev[4], c->stream);
+   } else if (tm) {
+      for (int k = 2; k <= 4; k++) cudaEventRecord(c->ev[k], c->stream);
    }
-   if (tm) cudaEventRecord(c->ev[3], c->stream);
-   c->stats.launches += 2; c->stats.launchesBeta++; c->stats.launchesAlpha++;
-   // ---- K4
-   if (!w.pos.empty() && (c->opt.uFlags & (HFB_UPMEANS | HFB_UPVARS | HFB_UPMIXES))) {
-      int nPos = (int)w.pos.size();
-      if (oldStats) stats_kernel<<<(nPos + 3) / 4, 128, 0, c->stream>>>(c->dm, W, dPos, nPos);
-      else stats2_kernel<<<(nPos + ST_WARPS - 1) / ST_WARPS, 32 * ST_WARPS, stats2_smem_bytes(c->dm.D), c->stream>>>(c->dm, W, dPos, nPos);
-      c->stats.launches++; c->stats.launchesStats++;
-   }
-   if (tm) cudaEventRecord(c->ev[4], c->stream);
    CK(cudaGetLastError());
 
    // ---- results back
@@ -607,9 +612,9 @@ static int run_wave(hfbgpu_ctx *c, WaveTables &w, const float *dFeat, long long 
       const UttOut &o = c->hOut[k];
       r.status = o.status; r.retries = o.retries; r.pr = o.pr; r.pruneThresh = o.thresh;
       const UttDesc &u = w.utt[k];
-      if (o.status == 0) c->stats.gmmPairs += (int64_t)u.T * u.J;
+      if (o.status == 0) c->stats.gmmPairs += (int64_t)u.T * o.J;
       if (wantBeams) {
-         long long dst = batchFrame0 + u.frameBase + waveFrame0 - batchFrame0;   // frame index in the batch
+         const long long dst = waveFrame0 + u.frameBase;                           // frame index in the batch
          const short *lo = c->hBeams + u.frameBase, *hi = lo + waveFrames, *s = hi + waveFrames, *e = s + waveFrames;
          for (int t = 0; t < u.T; t++) {
             bool okb = (o.status == 0 || o.status == HFB_UTT_EALPHA);
@@ -632,12 +637,12 @@ static int accumulate_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *re
    CK(cudaSetDevice(c->device));
    const HostModel &h = c->hm;
    const int D = h.D;
-   std::vector<int> slotOf((size_t)h.J, -1);
    WaveTables w;
    int u0 = 0;
    while (u0 < b->numUtt) {
       // ---- cut a wave that fits the workspace
       w.clear();
+      w.lab0 = b->labOff[u0];
       const long long waveFrame0 = b->frameOff[u0];
       size_t bytes = 0;
       int u1 = u0;
@@ -653,7 +658,7 @@ static int accumulate_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *re
          }
          size_t need = (size_t)T * perFrame;
          if (u1 > u0 && (bytes + need > c->workspaceBytes || u1 - u0 >= 16384)) break;
-         bytes += add_utterance(h, w, u1, T, b->lab + b->labOff[u1], Q, f0 - waveFrame0, f0 - waveFrame0, slotOf);
+         bytes += add_utterance(h, w, u1, T, b->lab + b->labOff[u1], Q, b->labOff[u1] - w.lab0, f0 - waveFrame0);
          u1++;
       }
       const long long waveFrames = b->frameOff[u1] - waveFrame0;
@@ -667,7 +672,7 @@ static int accumulate_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *re
          c->stats.h2dBytes += (int64_t)waveFrames * D * sizeof(float);
          dFeat = c->dFeat.p;
       }
-      int rc = run_wave(c, w, dFeat, waveFrame0, waveFrames, res, beams, 0);
+      int rc = run_wave(c, w, b->lab + w.lab0, dFeat, waveFrame0, waveFrames, res, beams);
       if (rc) return rc;
       u0 = u1;
    }
@@ -695,19 +700,18 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
    CK(cudaSetDevice(c->device));
    const HostModel &h = c->hm;
    for (int i = 0; i < n; i++) if (states[i] < 0 || states[i] >= h.J) return HFB_EINVAL;
-   WaveTables w;
    UttDesc u;
    memset(&u, 0, sizeof(u));
-   u.T = T; u.J = n;
-   w.utt.push_back(u);
-   w.out.push_back(UttOut{0, 0, 0.0, 0.0});
-   w.slotState.assign(states, states + n);
-   for (int t0 = 0; t0 < T; t0 += GT_FR)
-      for (int s0 = 0; s0 < n; s0 += GT_SL) w.tiles.push_back(GmmTile{0, t0, s0});
-   for (int t0 = 0; t0 < T; t0 += TC_BM) w.tcItems.push_back(make_int2(0, t0));
+   u.T = T; u.J = n; u.P = n;
+   UttOut o;
+   memset(&o, 0, sizeof(o));
+   std::vector<int2> items;
+   for (int t0 = 0; t0 < T; t0 += TC_BM) items.push_back(make_int2(0, t0));
+   const int nTiles = ((T + GT_FR - 1) / GT_FR) * ((n + GT_SL - 1) / GT_SL);
+   const int tilePre[2] = {0, nTiles};
    std::vector<unsigned char> blob;
-   size_t oUtt = blob_put(blob, w.utt), oSs = blob_put(blob, w.slotState), oTl = blob_put(blob, w.tiles),
-          oIt = blob_put(blob, w.tcItems);
+   size_t oUtt = blob_put(blob, &u, 1), oOut = blob_put(blob, &o, 1), oSs = blob_put(blob, states, (size_t)n),
+          oTp = blob_put(blob, tilePre, 2), oIt = blob_put(blob, items);
    int rc;
    if ((rc = c->dTables.reserve(blob.size())) || (rc = c->dFeat.reserve((size_t)T * h.D + 4)) ||
        (rc = c->dB.reserve((size_t)T * n + 1)))
@@ -716,19 +720,19 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
    CK(cudaMemcpyAsync(c->dFeat.p, feat, (size_t)T * h.D * sizeof(float), cudaMemcpyHostToDevice, c->stream));
    Wave W;
    memset(&W, 0, sizeof(W));
-   W.utt = (const UttDesc *)(c->dTables.p + oUtt); W.numUtt = 1;
-   W.slotState = (const int *)(c->dTables.p + oSs);
+   W.utt = (UttDesc *)(c->dTables.p + oUtt); W.out = (UttOut *)(c->dTables.p + oOut); W.numUtt = 1;
+   W.slotState = (int *)(c->dTables.p + oSs); W.tilePre = (const int *)(c->dTables.p + oTp);
    W.feat = c->dFeat.p; W.b = c->dB.p;
    int gk = c->opt.gmmKernel;
    if (gk == 0) gk = gmm_tc_available(c->tc) ? 2 : 1;
    if (gk == 2) {
       int nl = 0;
-      if ((rc = gmm_tc_launch(c->tc, c->dm, W, T, (const int2 *)(c->dTables.p + oIt), (int)w.tcItems.size(),
+      if ((rc = gmm_tc_launch(c->tc, c->dm, W, T, (const int2 *)(c->dTables.p + oIt), (int)items.size(),
                               c->smCount, c->stream, &nl))) return rc;
       c->stats.launches += nl; c->stats.launchesGmm += nl;
    } else {
       size_t smem = sizeof(float) * ((size_t)c->dm.D * GT_FR + (size_t)GT_FR * (GT_SL + 1));
-      gmm_fp32_kernel<<<(unsigned)w.tiles.size(), 128, smem, c->stream>>>(c->dm, W, (const GmmTile *)(c->dTables.p + oTl));
+      gmm_fp32_kernel<<<(unsigned)nTiles, 128, smem, c->stream>>>(c->dm, W);
       c->stats.launches++; c->stats.launchesGmm++;
    }
    CK(cudaGetLastError());
