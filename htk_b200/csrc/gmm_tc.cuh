@@ -12,12 +12,19 @@
 // hi*hi + hi*lo + lo*hi -- three tcgen05.mma.kind::tf32 per K step -- and accumulated in
 // FP32.  The dropped lo*lo term is ~2^-22 relative.  Features and means are shifted by the
 // mean of the Gaussian means (x' = x - o, mu' = mu - o) to keep the x'^2 terms small.
+// The tensor core truncates its FP32 accumulator after every MMA; measured on B200 that is a
+// +2e-5 common-mode bias on log b ~ -60 when everything goes through one accumulator.  Two
+// measures remove it: (1) the large hi*hi terms and the small hi*lo + lo*hi corrections use
+// SEPARATE TMEM accumulators, so only 12 roundings touch the large one; (2) a constant column
+// +C0 ~ -E[log b]/2 is contracted FIRST, so the running sum crosses zero half way and the
+// truncation errors of the two halves cancel; the epilogue subtracts C0 again.
 //
 // Tiling: one work item = (utterance, 128 consecutive frames).  The item's A operand
 // (128 x 96 floats, hi and lo = 96 KB) stays resident in shared memory while the B operand
 // of the utterance's states streams through a 3-stage TMA ring in [128 components x 32
 // floats] x {hi, lo} blocks (32 KB per stage).  Accumulators are double-buffered in TMEM
-// (2 x 128 columns) so the epilogue of tile n overlaps the MMAs of tile n+1.
+// (2 x (128 main + 128 correction) columns = all 512) so the epilogue of tile n overlaps the
+// MMAs of tile n+1.
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 epilogue.
 #pragma once
 #include <cuda.h>
@@ -47,6 +54,7 @@ struct GmmTcModel {
    size_t aCapFrames = 0;
    CUtensorMap mapBhi, mapBlo;
    void *encodeFn = nullptr;
+   float C0 = 0.f;             // symmetrising constant contracted first, subtracted in the epilogue
 };
 
 // ------------------------------------------------------------------------------------------
@@ -129,7 +137,7 @@ __device__ __forceinline__ float tc_tf32(float x)
 }
 
 // ------------------------------------------------------------------------------------------
-// feature expansion: A'hi / A'lo [frames][96] = split of [ (x-o)^2 | (x-o) | 1 | 0... ]
+// feature expansion: A'hi / A'lo [frames][96] = split of [ 1 | (x-o)^2 | (x-o) | 1 | 0... ]
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gmm_tc_expand_kernel(const float *__restrict__ feat, const float *__restrict__ off, int D, long long nFrames,
@@ -140,9 +148,10 @@ gmm_tc_expand_kernel(const float *__restrict__ feat, const float *__restrict__ o
    long long f = idx / TC_KE;
    int k = (int)(idx - f * TC_KE);
    float v = 0.f;
-   if (k < D) { float x = feat[f * D + k] - off[k]; v = x * x; }
-   else if (k < 2 * D) v = feat[f * D + (k - D)] - off[k - D];
-   else if (k == 2 * D) v = 1.f;
+   if (k == 0) v = 1.f;                                   // pairs with the constant column C0
+   else if (k <= D) { float x = feat[f * D + k - 1] - off[k - 1]; v = x * x; }
+   else if (k <= 2 * D) v = feat[f * D + (k - D - 1)] - off[k - D - 1];
+   else if (k == 2 * D + 1) v = 1.f;                      // pairs with c
    float hi = tc_tf32(v);
    Ahi[idx] = hi;
    Alo[idx] = tc_tf32(v - hi);
@@ -158,6 +167,7 @@ struct TcParams {
    const int *slotState;
    float *b;
    int GPS;                    // 8-row groups per state
+   float C0;
 };
 
 template <int MP>
@@ -182,7 +192,7 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    if (warp == 1) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmemSlot)), "r"(256) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmemSlot)), "r"(512) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
    }
    tc_fence_before();
@@ -246,7 +256,7 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
                const uint32_t as = tile & 1, phT = (tile >> 1) & 1;
                tc_mbar_wait(&tmemEmpty[as], phT ^ 1);
                tc_fence_after();
-               const uint32_t dAddr = tmem + as * TC_BN;
+               const uint32_t dMain = tmem + as * (2 * TC_BN), dCorr = dMain + TC_BN;
                for (int k = 0; k < 3; k++) {
                   tc_mbar_wait(&fullB[stage], phB);
                   tc_fence_after();
@@ -256,9 +266,9 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
                   for (int kk = 0; kk < 4; kk++) {
                      const uint64_t dAhi = tc_smem_desc(aHi + kk * 32), dAlo = tc_smem_desc(aLo + kk * 32);
                      const uint64_t dBhi = tc_smem_desc(bHi + kk * 32), dBlo = tc_smem_desc(bLo + kk * 32);
-                     tc_mma_tf32(dAddr, dAhi, dBhi, idesc, (k | kk) ? 1u : 0u);
-                     tc_mma_tf32(dAddr, dAhi, dBlo, idesc, 1u);
-                     tc_mma_tf32(dAddr, dAlo, dBhi, idesc, 1u);
+                     tc_mma_tf32(dMain, dAhi, dBhi, idesc, (k | kk) ? 1u : 0u);
+                     tc_mma_tf32(dCorr, dAhi, dBlo, idesc, (k | kk) ? 1u : 0u);
+                     tc_mma_tf32(dCorr, dAlo, dBhi, idesc, 1u);
                   }
                   tc_commit(&emptyB[stage]);            // stage reusable once these MMAs retire
                   if (++stage == TC_STAGES) { stage = 0; phB ^= 1; }
@@ -283,12 +293,16 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
             const uint32_t as = tile & 1, phT = (tile >> 1) & 1;
             tc_mbar_wait(&tmemFull[as], phT);
             tc_fence_after();
-            const uint32_t taddr = tmem + as * TC_BN + ((uint32_t)(quad * 32) << 16);
+            const uint32_t taddr = tmem + as * (2 * TC_BN) + ((uint32_t)(quad * 32) << 16);
+            const float C0 = p.C0;
             float cmx = -INFINITY, csum = 0.f;          // carry for states wider than one 32-column chunk
 #pragma unroll
             for (int c = 0; c < TC_BN / 32; c++) {
-               float v[32];
+               float v[32], vc[32];
                tc_tmem_ld32(taddr + c * 32, v);
+               tc_tmem_ld32(taddr + TC_BN + c * 32, vc);
+#pragma unroll
+               for (int i = 0; i < 32; i++) v[i] = (v[i] + vc[i]) - C0;
                constexpr int G = (MP < 32) ? MP : 32;   // columns of one state inside this chunk
 #pragma unroll
                for (int s0 = 0; s0 < 32; s0 += G) {
@@ -323,7 +337,7 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
    __syncthreads();
    if (warp == 1) {
       tc_fence_after();
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
    }
 }
 
@@ -378,7 +392,7 @@ static inline int gmm_tc_prepare(GmmTcModel &t, const hfb_model *m, cudaStream_t
    const int D = m->vecSize, J = m->numStates;
    int maxM = 0;
    for (int s = 0; s < J; s++) maxM = std::max(maxM, m->stateMixOff[s + 1] - m->stateMixOff[s]);
-   if (maxM < 2 || 2 * D + 1 > TC_KE) return HFB_OK;          // FP32 kernel handles these
+   if (maxM < 2 || 2 * D + 2 > TC_KE) return HFB_OK;          // FP32 kernel handles these
    int MP = 8;
    while (MP < maxM) MP *= 2;
    if (MP > TC_BN) return HFB_OK;
@@ -406,7 +420,8 @@ static inline int gmm_tc_prepare(GmmTcModel &t, const hfb_model *m, cudaStream_t
       hi[(size_t)r * TC_KE + k] = h;
       lo[(size_t)r * TC_KE + k] = tc_host_tf32(f - h);
    };
-   for (long long r = 0; r < t.rows; r++) put(r, 2 * D, TC_NEG_BIG);
+   for (long long r = 0; r < t.rows; r++) put(r, 2 * D + 1, TC_NEG_BIG);
+   double cSum = 0.0; long long cCnt = 0;
    for (int s = 0; s < J; s++) {
       int mo = m->stateMixOff[s], Mn = m->stateMixOff[s + 1] - mo;
       for (int k2 = 0; k2 < Mn; k2++) {
@@ -417,12 +432,20 @@ static inline int gmm_tc_prepare(GmmTcModel &t, const hfb_model *m, cudaStream_t
          double c = m->gConst[g];
          for (int k = 0; k < D; k++) {
             double iv = m->ivar[(size_t)g * D + k], mu = (double)m->mean[(size_t)g * D + k] - (double)offF[k];
-            put(r, k, -0.5 * iv);
-            put(r, D + k, mu * iv);
+            put(r, 1 + k, -0.5 * iv);
+            put(r, 1 + D + k, mu * iv);
             c += mu * mu * iv;
          }
-         put(r, 2 * D, -0.5 * c + (Mn > 1 ? (double)wt : 0.0));
+         const double cc = -0.5 * c + (Mn > 1 ? (double)wt : 0.0);
+         put(r, 2 * D + 1, cc);
+         cSum += cc; cCnt++;
       }
+   }
+   // expected log b ~ mean(c) - D/2 (chi-square term of matched data): start the running sum at -half of it
+   {
+      double eb = (cCnt ? cSum / cCnt : 0.0) - 0.5 * D;
+      t.C0 = tc_host_tf32((float)(-0.5 * eb));
+      for (long long r = 0; r < t.rows; r++) { hi[(size_t)r * TC_KE] = t.C0; lo[(size_t)r * TC_KE] = 0.f; }
    }
    size_t bytes = hi.size() * sizeof(float);
    if (cudaMalloc(&t.dBhi, bytes) != cudaSuccess || cudaMalloc(&t.dBlo, bytes) != cudaSuccess ||
@@ -468,7 +491,7 @@ static inline int gmm_tc_launch(GmmTcModel &t, const DevModel &dm, const Wave &W
    long long n = waveFrames * TC_KE;
    gmm_tc_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W.feat, t.dOffset, dm.D, waveFrames, t.dAhi, t.dAlo);
    TcParams p;
-   p.items = dItems; p.nItems = nItems; p.utt = W.utt; p.slotState = W.slotState; p.b = W.b; p.GPS = t.GPS;
+   p.items = dItems; p.nItems = nItems; p.utt = W.utt; p.slotState = W.slotState; p.b = W.b; p.GPS = t.GPS; p.C0 = t.C0;
    int grid = std::min(nItems, smCount);
    switch (t.MP) {
    case 8: gmm_tc_kernel<8><<<grid, 192, TC_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhi, t.mapBlo, p); break;
