@@ -129,6 +129,18 @@ __device__ __forceinline__ constexpr uint32_t tc_idesc(int M, int N)
    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+__device__ __forceinline__ float tc_ex2(float x)
+{
+   float r;
+   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+   return r;
+}
+__device__ __forceinline__ float tc_lg2(float x)
+{
+   float r;
+   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+   return r;
+}
 __device__ __forceinline__ float tc_tf32(float x)
 {
    uint32_t r;
@@ -200,50 +212,38 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
    tc_fence_after();
    const uint32_t tmem = *tmemSlot;
    constexpr int SPT = TC_BN / MP;                      // states per tile
-   constexpr int GPS = MP / 8;
 
    if (warp == 0) {
-      // ================= TMA producer =================
-      if (lane == 0) {
-         uint32_t stage = 0, phB = 0, phA = 0;
-         for (int it = blockIdx.x; it < p.nItems; it += gridDim.x) {
-            const int2 item = p.items[it];
-            const UttDesc u = p.utt[item.x];
-            const int row0 = (int)u.featOff + item.y;
-            tc_mbar_wait(emptyA, phA ^ 1);
-            tc_mbar_expect_tx(fullA, TC_A_BYTES);
+      // ================= TMA producer: one box of MP rows per lane =================
+      uint32_t stage = 0, phB = 0, phA = 0;
+      for (int it = blockIdx.x; it < p.nItems; it += gridDim.x) {
+         const int2 item = p.items[it];
+         const UttDesc u = p.utt[item.x];
+         const int row0 = (int)u.featOff + item.y;
+         if (lane == 0) { tc_mbar_wait(emptyA, phA ^ 1); tc_mbar_expect_tx(fullA, TC_A_BYTES); }
+         __syncwarp();
+         if (lane < 6) tc_tma_load_2d(sA + lane * 16384, lane < 3 ? &mapAhi : &mapAlo, fullA, (lane % 3) * 32, row0);
+         phA ^= 1;
+         const int nTiles = (u.J + SPT - 1) / SPT;
+         const int *ss = p.slotState + u.slotOff;
+         const int half = lane / SPT, bi = lane % SPT;          // lanes [0,SPT): hi boxes, [SPT,2SPT): lo boxes
+         for (int n = 0; n < nTiles; n++) {
+            const int slot = n * SPT + bi;
+            const int row = (lane < 2 * SPT && slot < u.J) ? (1 + ss[slot]) * MP : 0;   // rows [0,MP) = dummy state
             for (int k = 0; k < 3; k++) {
-               tc_tma_load_2d(sA + k * 16384, &mapAhi, fullA, k * 32, row0);
-               tc_tma_load_2d(sA + (3 + k) * 16384, &mapAlo, fullA, k * 32, row0);
-            }
-            phA ^= 1;
-            const int nTiles = (u.J + SPT - 1) / SPT;
-            const int *ss = p.slotState + u.slotOff;
-            for (int n = 0; n < nTiles; n++) {
-               int rows[TC_BN / 8];
-#pragma unroll
-               for (int g = 0; g < TC_BN / 8; g++) {
-                  int slot = n * SPT + g / GPS;
-                  rows[g] = (slot < u.J) ? (1 + ss[slot] * GPS + (g % GPS)) * 8 : 0;
-               }
-               for (int k = 0; k < 3; k++) {
-                  tc_mbar_wait(&emptyB[stage], phB ^ 1);
-                  tc_mbar_expect_tx(&fullB[stage], TC_B_STAGE_BYTES);
-                  uint8_t *dst = sB + stage * TC_B_STAGE_BYTES;
-#pragma unroll
-                  for (int g = 0; g < TC_BN / 8; g++) {
-                     tc_tma_load_2d(dst + g * 1024, &mapBhi, &fullB[stage], k * 32, rows[g]);
-                     tc_tma_load_2d(dst + 16384 + g * 1024, &mapBlo, &fullB[stage], k * 32, rows[g]);
-                  }
-                  if (++stage == TC_STAGES) { stage = 0; phB ^= 1; }
-               }
+               if (lane == 0) { tc_mbar_wait(&emptyB[stage], phB ^ 1); tc_mbar_expect_tx(&fullB[stage], TC_B_STAGE_BYTES); }
+               __syncwarp();
+               if (lane < 2 * SPT)
+                  tc_tma_load_2d(sB + stage * TC_B_STAGE_BYTES + half * 16384 + bi * (MP * 128),
+                                 half ? &mapBlo : &mapBhi, &fullB[stage], k * 32, row);
+               if (++stage == TC_STAGES) { stage = 0; phB ^= 1; }
             }
          }
       }
    } else if (warp == 1) {
       // ================= MMA issuer =================
       if (lane == 0) {
-         const uint32_t idesc = tc_idesc(TC_BM, TC_BN);
+         const uint32_t idesc = tc_idesc(TC_BM, TC_BN), idesc2 = tc_idesc(TC_BM, 2 * TC_BN);
          const uint32_t aBase = tc_smem_u32(sA), bBase = tc_smem_u32(sB);
          uint32_t stage = 0, phB = 0, phA = 0, tile = 0;
          for (int it = blockIdx.x; it < p.nItems; it += gridDim.x) {
@@ -260,14 +260,15 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
                for (int k = 0; k < 3; k++) {
                   tc_mbar_wait(&fullB[stage], phB);
                   tc_fence_after();
-                  const uint32_t bHi = bBase + stage * TC_B_STAGE_BYTES, bLo = bHi + 16384;
+                  const uint32_t bHi = bBase + stage * TC_B_STAGE_BYTES;
                   const uint32_t aHi = aBase + k * 16384, aLo = aBase + (3 + k) * 16384;
 #pragma unroll
                   for (int kk = 0; kk < 4; kk++) {
                      const uint64_t dAhi = tc_smem_desc(aHi + kk * 32), dAlo = tc_smem_desc(aLo + kk * 32);
-                     const uint64_t dBhi = tc_smem_desc(bHi + kk * 32), dBlo = tc_smem_desc(bLo + kk * 32);
-                     tc_mma_tf32(dMain, dAhi, dBhi, idesc, (k | kk) ? 1u : 0u);
-                     tc_mma_tf32(dCorr, dAhi, dBlo, idesc, (k | kk) ? 1u : 0u);
+                     const uint64_t dBhi = tc_smem_desc(bHi + kk * 32);
+                     // A_hi x [B_hi ; B_lo]: the stage holds hi and lo back to back = one N=256 operand,
+                     // columns [0,128) -> main accumulator, [128,256) -> correction accumulator
+                     tc_mma_tf32(dMain, dAhi, dBhi, idesc2, (k | kk) ? 1u : 0u);
                      tc_mma_tf32(dCorr, dAlo, dBhi, idesc, 1u);
                   }
                   tc_commit(&emptyB[stage]);            // stage reusable once these MMAs retire
@@ -302,7 +303,7 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
                tc_tmem_ld32(taddr + c * 32, v);
                tc_tmem_ld32(taddr + TC_BN + c * 32, vc);
 #pragma unroll
-               for (int i = 0; i < 32; i++) v[i] = (v[i] + vc[i]) - C0;
+               for (int i = 0; i < 32; i++) v[i] += vc[i];
                constexpr int G = (MP < 32) ? MP : 32;   // columns of one state inside this chunk
 #pragma unroll
                for (int s0 = 0; s0 < 32; s0 += G) {
@@ -312,16 +313,16 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
                   float sum = 0.f;
                   const float mb = mx * LOG2E;
 #pragma unroll
-                  for (int i = 0; i < G; i++) sum += exp2f(fmaf(v[s0 + i], LOG2E, -mb));
+                  for (int i = 0; i < G; i++) sum += tc_ex2(fmaf(v[s0 + i], LOG2E, -mb));
                   if (MP > 32) {                        // merge into the carry
                      float nm = fmaxf(cmx, mx);
-                     csum = csum * exp2f((cmx - nm) * LOG2E) + sum * exp2f((mx - nm) * LOG2E);
+                     csum = csum * tc_ex2((cmx - nm) * LOG2E) + sum * tc_ex2((mx - nm) * LOG2E);
                      cmx = nm; mx = cmx; sum = csum;
                   }
                   const int colEnd = c * 32 + s0 + G;   // columns consumed so far
                   if (colEnd % MP == 0) {
                      const int slot = n * SPT + colEnd / MP - 1;
-                     float val = (mx < -1.0e29f) ? (float)HFB_LZERO : fmaf(log2f(sum), LN2, mx);
+                     float val = (mx < -1.0e29f) ? (float)HFB_LZERO : fmaf(tc_lg2(sum), LN2, mx - C0);
                      if (t < u.T && slot < u.J) brow[slot] = val;
                      cmx = -INFINITY; csum = 0.f;
                   }
@@ -408,7 +409,7 @@ static inline int gmm_tc_prepare(GmmTcModel &t, const hfb_model *m, cudaStream_t
    }
    t.encodeFn = fn;
    t.MP = MP; t.GPS = MP / 8;
-   t.rows = (long long)(1 + (long long)J * t.GPS) * 8;
+   t.rows = (long long)(1 + (long long)J) * MP;                 // rows [0, MP) = dummy state
    std::vector<double> off(D, 0.0);
    for (int g = 0; g < m->numGauss; g++)
       for (int k = 0; k < D; k++) off[k] += m->mean[(size_t)g * D + k];
@@ -425,7 +426,7 @@ static inline int gmm_tc_prepare(GmmTcModel &t, const hfb_model *m, cudaStream_t
    for (int s = 0; s < J; s++) {
       int mo = m->stateMixOff[s], Mn = m->stateMixOff[s + 1] - mo;
       for (int k2 = 0; k2 < Mn; k2++) {
-         long long r = (long long)(1 + (long long)s * t.GPS) * 8 + k2;
+         long long r = (long long)(1 + (long long)s) * MP + k2;
          float wt = m->mixLogWt[mo + k2];
          if (Mn > 1 && !(wt > (float)HFB_LMINMIX)) continue;
          int g = m->mixGauss[mo + k2];
@@ -456,7 +457,7 @@ static inline int gmm_tc_prepare(GmmTcModel &t, const hfb_model *m, cudaStream_t
    cudaMemcpyAsync(t.dBlo, lo.data(), bytes, cudaMemcpyHostToDevice, st);
    cudaMemcpyAsync(t.dOffset, offF.data(), D * sizeof(float), cudaMemcpyHostToDevice, st);
    cudaStreamSynchronize(st);
-   if (tc_make_map(fn, &t.mapBhi, t.dBhi, t.rows, 8) || tc_make_map(fn, &t.mapBlo, t.dBlo, t.rows, 8)) {
+   if (tc_make_map(fn, &t.mapBhi, t.dBhi, t.rows, MP) || tc_make_map(fn, &t.mapBlo, t.dBlo, t.rows, MP)) {
       gmm_tc_release(t); return HFB_OK;
    }
 #define TC_SET_SMEM(MPV) cudaFuncSetAttribute(gmm_tc_kernel<MPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES)
