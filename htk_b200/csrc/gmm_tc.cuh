@@ -50,11 +50,20 @@ struct GmmTcModel {
    int GPS = 0;                // 8-row groups per state = MP / 8
    long long rows = 0;         // rows in Bhi/Blo (row group 0 is the all-"-inf" dummy)
    float *dBhi = nullptr, *dBlo = nullptr, *dOffset = nullptr;
-   float *dAhi = nullptr, *dAlo = nullptr;
-   size_t aCapFrames = 0;
    CUtensorMap mapBhi, mapBlo;
    void *encodeFn = nullptr;
    float C0 = 0.f;             // symmetrising constant contracted first, subtracted in the epilogue
+};
+
+struct GmmTcWork {             // per-stream expanded feature operand
+   float *dAhi = nullptr, *dAlo = nullptr;
+   size_t aCapFrames = 0;
+   void release()
+   {
+      if (dAhi) cudaFree(dAhi);
+      if (dAlo) cudaFree(dAlo);
+      dAhi = dAlo = nullptr; aCapFrames = 0;
+   }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -376,8 +385,6 @@ static inline void gmm_tc_release(GmmTcModel &t)
    if (t.dBhi) cudaFree(t.dBhi);
    if (t.dBlo) cudaFree(t.dBlo);
    if (t.dOffset) cudaFree(t.dOffset);
-   if (t.dAhi) cudaFree(t.dAhi);
-   if (t.dAlo) cudaFree(t.dAlo);
    t = GmmTcModel();
 }
 
@@ -468,29 +475,27 @@ static inline int gmm_tc_prepare(GmmTcModel &t, const hfb_model *m, cudaStream_t
 }
 
 // Launches expansion + GEMM for every utterance of the wave.  `items` lives in the wave blob.
-static inline int gmm_tc_launch(GmmTcModel &t, const DevModel &dm, const Wave &W, long long waveFrames,
+static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm, const Wave &W, long long waveFrames,
                                 const int2 *dItems, int nItems, int smCount, cudaStream_t st, int *launches)
 {
    if (!t.ready) return HFB_EUNSUPPORTED;
    if (nItems == 0) return HFB_OK;
    const size_t need = (size_t)waveFrames + TC_BM;
-   if (need > t.aCapFrames) {
-      if (t.dAhi) cudaFree(t.dAhi);
-      if (t.dAlo) cudaFree(t.dAlo);
-      t.dAhi = t.dAlo = nullptr;
+   if (need > wk.aCapFrames) {
+      wk.release();
       size_t cap = need + need / 8;
-      if (cudaMalloc(&t.dAhi, cap * TC_KE * sizeof(float)) != cudaSuccess ||
-          cudaMalloc(&t.dAlo, cap * TC_KE * sizeof(float)) != cudaSuccess) { cudaGetLastError(); t.aCapFrames = 0; return HFB_ENOMEM; }
-      t.aCapFrames = cap;
+      if (cudaMalloc(&wk.dAhi, cap * TC_KE * sizeof(float)) != cudaSuccess ||
+          cudaMalloc(&wk.dAlo, cap * TC_KE * sizeof(float)) != cudaSuccess) { cudaGetLastError(); wk.release(); return HFB_ENOMEM; }
+      wk.aCapFrames = cap;
    }
    CUtensorMap mapAhi, mapAlo;
    // rows beyond the wave (at most TC_BM - 1) are allocated but stale: every output row depends on
    // its own A row only and rows with t >= T are never stored
-   if (tc_make_map(t.encodeFn, &mapAhi, t.dAhi, waveFrames + TC_BM, TC_BM) ||
-       tc_make_map(t.encodeFn, &mapAlo, t.dAlo, waveFrames + TC_BM, TC_BM))
+   if (tc_make_map(t.encodeFn, &mapAhi, wk.dAhi, waveFrames + TC_BM, TC_BM) ||
+       tc_make_map(t.encodeFn, &mapAlo, wk.dAlo, waveFrames + TC_BM, TC_BM))
       return HFB_ECUDA;
    long long n = waveFrames * TC_KE;
-   gmm_tc_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W.feat, t.dOffset, dm.D, waveFrames, t.dAhi, t.dAlo);
+   gmm_tc_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W.feat, t.dOffset, dm.D, waveFrames, wk.dAhi, wk.dAlo);
    TcParams p;
    p.items = dItems; p.nItems = nItems; p.utt = W.utt; p.slotState = W.slotState; p.b = W.b; p.GPS = t.GPS; p.C0 = t.C0;
    int grid = std::min(nItems, smCount);

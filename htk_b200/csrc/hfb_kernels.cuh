@@ -38,6 +38,11 @@ __device__ __forceinline__ double ladd(double x, double y)
    return x + (double)log1pf(expf((float)d));
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ double warp_max(double v)
 {
    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -318,7 +323,13 @@ __global__ void __launch_bounds__(256) beta_kernel(DevModel M, Wave W)
          const float *bt = bU + (size_t)t * J, *bt1 = bt + J;
          double myMax = LZERO_D;
          for (int q = tid; q < Q; q += nt) {
-            if (q < endq || q > startq) continue;
+            if (q < endq - 2 || q > startq) continue;
+            if (t >= 2) {                                  // b of frame t-2 is first touched two steps from now
+               const int *ps2 = posSlot + sm.sPoff[q];
+               const float *bt2 = bU + (size_t)(t - 2) * J;
+               for (int j = 0; j < sm.sN[q] - 2; j++) prefetch_l1(bt2 + ps2[j]);
+            }
+            if (q < endq) continue;
             const int N = sm.sN[q], so = sm.sSoff[q];
             const float *A = A0 + sm.sTr[q];
             const int *ps = posSlot + sm.sPoff[q];

@@ -15,8 +15,9 @@
 
 __host__ __device__ inline size_t alpha_warp_smem_bytes(int S, int Q)
 {
-   return sizeof(double) * ((size_t)2 * S + 2 * Q);
+   return sizeof(double) * ((size_t)2 * S + 2 * Q) + sizeof(int) * ((size_t)2 * Q);
 }
+
 
 template <bool EXACT>
 __global__ void __launch_bounds__(32) alpha_warp_kernel(DevModel M, Wave W)
@@ -28,6 +29,7 @@ __global__ void __launch_bounds__(32) alpha_warp_kernel(DevModel M, Wave W)
    const int lane = threadIdx.x;
    const int T = u.T, Q = u.Q, S = u.S, J = u.J, P = u.P;
    double *cur = (double *)smraw, *prev = cur + S, *mpSelf = prev + S, *exq = mpSelf + Q;
+   int *sTmin = (int *)(exq + Q), *sTmax = sTmin + Q;
    const int *mN = W.mN + u.modOff, *mSoff = W.mSoff + u.modOff, *mTr = W.mTrans + u.modOff;
    const int *mPoff = W.mPoff + u.modOff, *mDms = W.mDms + u.modOff;
    const float *A0 = M.transLogA;
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(32) alpha_warp_kernel(DevModel M, Wave W)
 
    for (int q = lane; q < Q; q += 32) {
       mpSelf[q] = LZERO_D; exq[q] = LZERO_D;
-      W.mTmin[u.modOff + q] = 0x7fffffff; W.mTmax[u.modOff + q] = -1;
+      sTmin[q] = 0x7fffffff; sTmax[q] = -1;
       atomicAdd(&W.acc[M.L.numEgs + W.mHmm[u.modOff + q]], 1.0);      // HFB.c:1768-1772
    }
    for (int i = lane; i < 2 * S; i += 32) cur[i] = LZERO_D;
@@ -150,6 +152,19 @@ __global__ void __launch_bounds__(32) alpha_warp_kernel(DevModel M, Wave W)
       }
       __syncwarp();
       if (lane == 0) { sqA[t] = (short)sq; eqA[t] = (short)eq; }
+      // pull what frame t+1 will touch for the first time (beta and b of frame t+2) towards L1 now:
+      // the T-step chain is latency bound and these addresses do not depend on the recursion
+      if (t + 2 < T) {
+         const int pHi = min(Q - 1, eq + 3);
+         const float *bt2 = bU + (size_t)(t + 2) * J;
+         for (int q = sq + lane; q <= pHi; q += 32) {
+            const int N = mN[q];
+            const double *b2 = betaU + (size_t)(t + 2) * S + mSoff[q];
+            prefetch_l1(b2); prefetch_l1(b2 + N - 1);
+            const int *ps = posSlot + mPoff[q];
+            for (int j = 0; j < N - 2; j++) prefetch_l1(bt2 + ps[j]);
+         }
+      }
 
       // ---- accumulation inside the alpha beam (StepForward, HFB.c:1790-1806)
       const float *bt = bU + (size_t)t * J;
@@ -167,8 +182,8 @@ __global__ void __launch_bounds__(32) alpha_warp_kernel(DevModel M, Wave W)
          const double bq1 = hasBq1 ? betaU[(size_t)t * S + mSoff[q + 1]] : LZERO_D;
          const double a1N = A[N - 1];
          const int gq = u.modOff + q;
-         if (W.mTmin[gq] > t) W.mTmin[gq] = t;
-         W.mTmax[gq] = t;
+         if (sTmin[q] > t) sTmin[q] = t;
+         sTmax[q] = t;
          double mps = LZERO_D;
          for (int i = 0; i < N - 1; i++) mps = fmax(mps, cur[so + i] + bq[i]);
          mpSelf[q] = mps;
@@ -232,6 +247,7 @@ __global__ void __launch_bounds__(32) alpha_warp_kernel(DevModel M, Wave W)
       }
       __syncwarp();
    }
+   for (int q = lane; q < Q; q += 32) { W.mTmin[u.modOff + q] = sTmin[q]; W.mTmax[u.modOff + q] = sTmax[q]; }
    if (lane == 0) {
       atomicAdd(&W.acc[M.L.totalT], (double)T);                             // HERest.c:779-780
       atomicAdd(&W.acc[M.L.totalPr], pr);

@@ -66,15 +66,35 @@ struct HostModel {
 
 }  // namespace
 
+namespace {
+struct WaveTables {
+   std::vector<UttDesc> utt;
+   std::vector<UttOut> out;
+   std::vector<int> posPre, tilePre;
+   std::vector<int2> tcItems;        // (utterance, first frame) blocks of TC_BM frames for the tcgen05 kernel
+   std::vector<int> uttIndex;        // index in the caller's batch
+   long long bFloats = 0, betaDoubles = 0, occDoubles = 0;
+   long long totalQ = 0, totalP = 0, tiles = 0;
+   int maxQ = 0, maxS = 0;
+   int lab0 = 0;                     // first label of the wave in the caller's label array
+   void clear()
+   {
+      utt.clear(); out.clear(); posPre.clear(); tilePre.clear(); tcItems.clear(); uttIndex.clear();
+      bFloats = betaDoubles = occDoubles = 0; totalQ = totalP = tiles = 0; maxQ = maxS = 0; lab0 = 0;
+   }
+};
+
+}  // namespace
+typedef WaveTables *WaveTablesPtr;
+
 struct hfbgpu_ctx {
    int device = 0;
    hfb_options opt;
    HostModel hm;
    DevModel dm;
    hfb_acc_layout L;
-   cudaStream_t stream = nullptr;
+   cudaStream_t stream = nullptr;    // stream of model uploads / accumulator copies (caller's if set)
    cudaStream_t ownStream = nullptr;
-   cudaEvent_t ev[8] = {};
    bool timing = false;
    hfb_stats stats;
    // model on device
@@ -83,21 +103,35 @@ struct hfbgpu_ctx {
    GmmTcModel tc;                    // expanded / split operands for the tcgen05 path
    // accumulators
    DevBuf<double> dAcc;
-   // workspace
-   DevBuf<float> dFeat;              // only for host-feature calls
-   DevBuf<float> dB;
-   DevBuf<double> dBeta, dOcc;
-   DevBuf<short> dBeams;             // 4 * frames
-   DevBuf<unsigned char> dTables, dScratch;
    DevBuf<int> dHmmN, dHmmStateOff, dHmmState, dHmmTrans, dTransOffF, dTransMinDur;
    DevBuf<long long> dTranAccOff, dTranOccOff;
-   std::vector<unsigned char> blobScratch;
-   unsigned char *hTables = nullptr; // pinned staging
-   size_t hTablesCap = 0;
-   UttOut *hOut = nullptr;           // pinned
-   size_t hOutCap = 0;
-   short *hBeams = nullptr;          // pinned
-   size_t hBeamsCap = 0;
+   // Waves of one call run on NSLOT streams with private workspaces: the latency-bound recursion
+   // kernels of one wave overlap the throughput-bound GMM / statistics kernels of the other.
+   struct Slot {
+      cudaStream_t stream = nullptr;
+      cudaEvent_t ev[6] = {};
+      DevBuf<float> dFeat;              // only for host-feature calls
+      DevBuf<float> dB;
+      DevBuf<double> dBeta, dOcc;
+      DevBuf<short> dBeams;             // 4 * frames
+      DevBuf<unsigned char> dTables, dScratch;
+      GmmTcWork tcw;
+      std::vector<unsigned char> blob;
+      unsigned char *hTables = nullptr; // pinned staging
+      size_t hTablesCap = 0;
+      UttOut *hOut = nullptr;           // pinned
+      size_t hOutCap = 0;
+      short *hBeams = nullptr;          // pinned
+      size_t hBeamsCap = 0;
+      // in-flight wave
+      bool busy = false;
+      WaveTablesPtr w = nullptr;
+      long long waveFrame0 = 0, waveFrames = 0;
+      bool wantBeams = false;
+   };
+   static const int NSLOT = 2;
+   Slot slot[NSLOT];
+   int numSlots = NSLOT;
    size_t workspaceBytes = 0;
    int smCount = 148;
    int maxSmemOptin = 0;
@@ -226,7 +260,11 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
    c->maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
    CK(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
    c->stream = c->ownStream;
-   for (auto &e : c->ev) CK(cudaEventCreate(&e));
+   for (auto &sl : c->slot) {
+      CK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+      for (auto &e : sl.ev) CK(cudaEventCreate(&e));
+   }
+   if (const char *ns = getenv("HFBGPU_STREAMS")) c->numSlots = std::max(1, std::min((int)hfbgpu_ctx::NSLOT, atoi(ns)));
 
    HostModel &h = c->hm;
    h.D = m->vecSize; h.G = m->numGauss; h.J = m->numStates; h.P = m->numHmm; h.numTrans = m->numTrans;
@@ -332,14 +370,20 @@ extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
    c->dMean.release(); c->dIvar.release(); c->dGconst.release(); c->dMixLogWt.release(); c->dTransLogA.release();
    c->dMeanId.release(); c->dVarId.release(); c->dStateMixOff.release(); c->dMixGauss.release();
    gmm_tc_release(c->tc);
-   c->dAcc.release(); c->dFeat.release(); c->dB.release(); c->dBeta.release(); c->dOcc.release();
-   c->dBeams.release(); c->dTables.release(); c->dScratch.release();
+   c->dAcc.release();
+   for (auto &sl : c->slot) {
+      if (sl.stream) cudaStreamSynchronize(sl.stream);
+      sl.dFeat.release(); sl.dB.release(); sl.dBeta.release(); sl.dOcc.release(); sl.dBeams.release();
+      sl.dTables.release(); sl.dScratch.release(); sl.tcw.release();
+      if (sl.hTables) cudaFreeHost(sl.hTables);
+      if (sl.hOut) cudaFreeHost(sl.hOut);
+      if (sl.hBeams) cudaFreeHost(sl.hBeams);
+      for (auto &e : sl.ev) if (e) cudaEventDestroy(e);
+      if (sl.stream) cudaStreamDestroy(sl.stream);
+      delete sl.w;
+   }
    c->dHmmN.release(); c->dHmmStateOff.release(); c->dHmmState.release(); c->dHmmTrans.release();
    c->dTransOffF.release(); c->dTransMinDur.release(); c->dTranAccOff.release(); c->dTranOccOff.release();
-   if (c->hTables) cudaFreeHost(c->hTables);
-   if (c->hOut) cudaFreeHost(c->hOut);
-   if (c->hBeams) cudaFreeHost(c->hBeams);
-   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
    if (c->ownStream) cudaStreamDestroy(c->ownStream);
    delete c;
    return HFB_OK;
@@ -400,23 +444,6 @@ extern "C" int hfbgpu_set_timing(hfbgpu_ctx *c, int on) { if (!c) return HFB_EIN
 // wave construction: the host only sizes things; the tables are built by prep_kernel
 // ------------------------------------------------------------------------------------------
 namespace {
-
-struct WaveTables {
-   std::vector<UttDesc> utt;
-   std::vector<UttOut> out;
-   std::vector<int> posPre, tilePre;
-   std::vector<int2> tcItems;        // (utterance, first frame) blocks of TC_BM frames for the tcgen05 kernel
-   std::vector<int> uttIndex;        // index in the caller's batch
-   long long bFloats = 0, betaDoubles = 0, occDoubles = 0;
-   long long totalQ = 0, totalP = 0, tiles = 0;
-   int maxQ = 0, maxS = 0;
-   int lab0 = 0;                     // first label of the wave in the caller's label array
-   void clear()
-   {
-      utt.clear(); out.clear(); posPre.clear(); tilePre.clear(); tcItems.clear(); uttIndex.clear();
-      bFloats = betaDoubles = occDoubles = 0; totalQ = totalP = tiles = 0; maxQ = maxS = 0; lab0 = 0;
-   }
-};
 
 // Sizes one utterance (sum of N over its labels) and appends its descriptor.
 // Returns the workspace bytes it needs.
@@ -486,38 +513,52 @@ struct ScratchLayout {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
-// run one wave
+// one wave: launch (asynchronous) and finish (synchronise + hand results to the caller)
 // ------------------------------------------------------------------------------------------
-static int run_wave(hfbgpu_ctx *c, WaveTables &w, const int32_t *labBase, const float *dFeat, long long waveFrame0,
-                    long long waveFrames, hfb_utt_result *res, const hfb_beams *beams)
+static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBase, const float *feat, bool featOnDevice,
+                       long long waveFrame0, long long waveFrames, bool wantBeams)
 {
+   WaveTables &w = *S.w;
    const int nU = (int)w.utt.size();
-   if (nU == 0) return HFB_OK;
+   cudaStream_t st = S.stream;
    int rc;
+   const int D = c->hm.D;
+   S.waveFrame0 = waveFrame0; S.waveFrames = waveFrames; S.wantBeams = wantBeams;
+   S.busy = true;
+   // ---- features
+   const float *dFeat;
+   if (featOnDevice) dFeat = feat + (size_t)waveFrame0 * D;
+   else {
+      if ((rc = S.dFeat.reserve((size_t)waveFrames * D + 4))) return rc;
+      CK(cudaMemcpyAsync(S.dFeat.p, feat + (size_t)waveFrame0 * D, (size_t)waveFrames * D * sizeof(float),
+                         cudaMemcpyHostToDevice, st));
+      c->stats.h2dBytes += (int64_t)waveFrames * D * sizeof(float);
+      dFeat = S.dFeat.p;
+   }
    // ---- pack + upload the (small) host tables
    w.posPre.push_back((int)w.totalP);
    w.tilePre.push_back((int)w.tiles);
-   std::vector<unsigned char> &blob = c->blobScratch;
+   std::vector<unsigned char> &blob = S.blob;
    blob.clear();
    size_t oUtt = blob_put(blob, w.utt), oOut = blob_put(blob, w.out), oPp = blob_put(blob, w.posPre),
           oTp = blob_put(blob, w.tilePre), oIt = blob_put(blob, w.tcItems);
    const size_t nLab = (size_t)w.utt.back().labOff + (size_t)w.utt.back().Q;
    size_t oLab = blob_put(blob, labBase, nLab);
-   if (blob.size() > c->hTablesCap) {
-      if (c->hTables) cudaFreeHost(c->hTables);
-      c->hTablesCap = blob.size() * 2;
-      CK(cudaMallocHost(&c->hTables, c->hTablesCap));
+   if (blob.size() > S.hTablesCap) {
+      if (S.hTables) cudaFreeHost(S.hTables);
+      S.hTablesCap = blob.size() * 2;
+      CK(cudaMallocHost(&S.hTables, S.hTablesCap));
    }
-   memcpy(c->hTables, blob.data(), blob.size());
+   memcpy(S.hTables, blob.data(), blob.size());
    const ScratchLayout sl(w.totalQ, w.totalP);
-   if ((rc = c->dTables.reserve(blob.size())) || (rc = c->dScratch.reserve(sl.bytes))) return rc;
-   CK(cudaMemcpyAsync(c->dTables.p, c->hTables, blob.size(), cudaMemcpyHostToDevice, c->stream));
+   if ((rc = S.dTables.reserve(blob.size())) || (rc = S.dScratch.reserve(sl.bytes))) return rc;
+   CK(cudaMemcpyAsync(S.dTables.p, S.hTables, blob.size(), cudaMemcpyHostToDevice, st));
    c->stats.h2dBytes += (int64_t)blob.size();
-   if ((rc = c->dB.reserve((size_t)w.bFloats + 1)) || (rc = c->dBeta.reserve((size_t)w.betaDoubles + 1)) ||
-       (rc = c->dOcc.reserve((size_t)w.occDoubles + 1)) || (rc = c->dBeams.reserve((size_t)waveFrames * 4 + 4)))
+   if ((rc = S.dB.reserve((size_t)w.bFloats + 1)) || (rc = S.dBeta.reserve((size_t)w.betaDoubles + 1)) ||
+       (rc = S.dOcc.reserve((size_t)w.occDoubles + 1)) || (rc = S.dBeams.reserve((size_t)waveFrames * 4 + 4)))
       return rc;
 
-   unsigned char *base = c->dTables.p, *sc = c->dScratch.p;
+   unsigned char *base = S.dTables.p, *sc = S.dScratch.p;
    Wave W;
    memset(&W, 0, sizeof(W));
    W.utt = (UttDesc *)(base + oUtt); W.out = (UttOut *)(base + oOut); W.numUtt = nU;
@@ -530,31 +571,31 @@ static int run_wave(hfbgpu_ctx *c, WaveTables &w, const int32_t *labBase, const 
    W.mTmin = (int *)(sc + sl.mTmin); W.mTmax = (int *)(sc + sl.mTmax);
    W.slotState = (int *)(sc + sl.slotState); W.posSlot = (int *)(sc + sl.posSlot); W.posState = (int *)(sc + sl.posState);
    W.feat = dFeat;
-   W.b = c->dB.p; W.beta = c->dBeta.p; W.occ = c->dOcc.p;
-   W.qLo = c->dBeams.p; W.qHi = W.qLo + waveFrames; W.sq = W.qHi + waveFrames; W.eq = W.sq + waveFrames;
+   W.b = S.dB.p; W.beta = S.dBeta.p; W.occ = S.dOcc.p;
+   W.qLo = S.dBeams.p; W.qHi = W.qLo + waveFrames; W.sq = W.qHi + waveFrames; W.eq = W.sq + waveFrames;
    W.acc = c->dAcc.p;
    W.pruneInit = c->opt.pruneInit; W.pruneInc = c->opt.pruneInc; W.pruneLim = c->opt.pruneLim;
    W.minFrwdP = (double)c->opt.minFrwdP; W.uFlags = c->opt.uFlags;
 
    const bool tm = c->timing;
    // ---- K0: tables
-   prep_kernel<<<nU, 128, 0, c->stream>>>(c->dm, W);
+   prep_kernel<<<nU, 128, 0, st>>>(c->dm, W);
    c->stats.launches++; c->stats.launchesMisc++;
-   if (tm) cudaEventRecord(c->ev[0], c->stream);
+   if (tm) cudaEventRecord(S.ev[0], st);
    // ---- K1
    int gk = c->opt.gmmKernel;
    if (gk == 0) gk = gmm_tc_available(c->tc) ? 2 : 1;
    if (gk == 2) {
       int nl = 0;
-      if ((rc = gmm_tc_launch(c->tc, c->dm, W, waveFrames, (const int2 *)(base + oIt), (int)w.tcItems.size(),
-                              c->smCount, c->stream, &nl))) return rc;
+      if ((rc = gmm_tc_launch(c->tc, S.tcw, c->dm, W, waveFrames, (const int2 *)(base + oIt), (int)w.tcItems.size(),
+                              c->smCount, st, &nl))) return rc;
       c->stats.launches += nl; c->stats.launchesGmm += nl;
    } else if (w.tiles > 0) {
       size_t smem = sizeof(float) * ((size_t)c->dm.D * GT_FR + (size_t)GT_FR * (GT_SL + 1));
-      gmm_fp32_kernel<<<(unsigned)w.tiles, 128, smem, c->stream>>>(c->dm, W);
+      gmm_fp32_kernel<<<(unsigned)w.tiles, 128, smem, st>>>(c->dm, W);
       c->stats.launches++; c->stats.launchesGmm++;
    }
-   if (tm) cudaEventRecord(c->ev[1], c->stream);
+   if (tm) cudaEventRecord(S.ev[1], st);
    // ---- K2 / K3
    if (w.maxQ > 0) {
       int nt = std::min(256, std::max(32, (w.maxQ + 31) & ~31));
@@ -563,59 +604,68 @@ static int run_wave(hfbgpu_ctx *c, WaveTables &w, const int32_t *labBase, const 
          g_lastError = "utterance too long for the shared-memory window"; return HFB_EUNSUPPORTED;
       }
       const bool exact = getenv("HFBGPU_EXACT_LADD") != nullptr;
-      if (exact) beta_kernel<true><<<nU, nt, rsm, c->stream>>>(c->dm, W);
-      else beta_kernel<false><<<nU, nt, rsm, c->stream>>>(c->dm, W);
-      if (tm) cudaEventRecord(c->ev[2], c->stream);
-      if (exact) alpha_warp_kernel<true><<<nU, 32, asm_, c->stream>>>(c->dm, W);
-      else alpha_warp_kernel<false><<<nU, 32, asm_, c->stream>>>(c->dm, W);
-      if (tm) cudaEventRecord(c->ev[3], c->stream);
+      if (exact) beta_kernel<true><<<nU, nt, rsm, st>>>(c->dm, W);
+      else beta_kernel<false><<<nU, nt, rsm, st>>>(c->dm, W);
+      if (tm) cudaEventRecord(S.ev[2], st);
+      if (exact) alpha_warp_kernel<true><<<nU, 32, asm_, st>>>(c->dm, W);
+      else alpha_warp_kernel<false><<<nU, 32, asm_, st>>>(c->dm, W);
+      if (tm) cudaEventRecord(S.ev[3], st);
       c->stats.launches += 2; c->stats.launchesBeta++; c->stats.launchesAlpha++;
       // ---- K4
       if (w.totalP > 0 && (c->opt.uFlags & (HFB_UPMEANS | HFB_UPVARS | HFB_UPMIXES))) {
-         stats2_kernel<<<(unsigned)((w.totalP + ST_WARPS - 1) / ST_WARPS), 32 * ST_WARPS, stats2_smem_bytes(c->dm.D), c->stream>>>(c->dm, W);
+         stats2_kernel<<<(unsigned)((w.totalP + ST_WARPS - 1) / ST_WARPS), 32 * ST_WARPS, stats2_smem_bytes(c->dm.D), st>>>(c->dm, W);
          c->stats.launches++; c->stats.launchesStats++;
       }
-      if (tm) cudaEventRecord(c->ev[4], c->stream);
+      if (tm) cudaEventRecord(S.ev[4], st);
    } else if (tm) {
-      for (int k = 2; k <= 4; k++) cudaEventRecord(c->ev[k], c->stream);
+      for (int k = 2; k <= 4; k++) cudaEventRecord(S.ev[k], st);
    }
    CK(cudaGetLastError());
 
-   // ---- results back
-   if ((size_t)nU > c->hOutCap) {
-      if (c->hOut) cudaFreeHost(c->hOut);
-      c->hOutCap = (size_t)nU * 2;
-      CK(cudaMallocHost(&c->hOut, c->hOutCap * sizeof(UttOut)));
+   // ---- results back (asynchronous; consumed by finish_wave)
+   if ((size_t)nU > S.hOutCap) {
+      if (S.hOut) cudaFreeHost(S.hOut);
+      S.hOutCap = (size_t)nU * 2;
+      CK(cudaMallocHost(&S.hOut, S.hOutCap * sizeof(UttOut)));
    }
-   CK(cudaMemcpyAsync(c->hOut, W.out, (size_t)nU * sizeof(UttOut), cudaMemcpyDeviceToHost, c->stream));
+   CK(cudaMemcpyAsync(S.hOut, W.out, (size_t)nU * sizeof(UttOut), cudaMemcpyDeviceToHost, st));
    c->stats.d2hBytes += (int64_t)nU * sizeof(UttOut);
-   const bool wantBeams = beams && (beams->qLo || beams->qHi || beams->sq || beams->eq);
    if (wantBeams) {
-      if ((size_t)waveFrames * 4 > c->hBeamsCap) {
-         if (c->hBeams) cudaFreeHost(c->hBeams);
-         c->hBeamsCap = (size_t)waveFrames * 8;
-         CK(cudaMallocHost(&c->hBeams, c->hBeamsCap * sizeof(short)));
+      if ((size_t)waveFrames * 4 > S.hBeamsCap) {
+         if (S.hBeams) cudaFreeHost(S.hBeams);
+         S.hBeamsCap = (size_t)waveFrames * 8;
+         CK(cudaMallocHost(&S.hBeams, S.hBeamsCap * sizeof(short)));
       }
-      CK(cudaMemcpyAsync(c->hBeams, c->dBeams.p, (size_t)waveFrames * 4 * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(S.hBeams, S.dBeams.p, (size_t)waveFrames * 4 * sizeof(short), cudaMemcpyDeviceToHost, st));
       c->stats.d2hBytes += (int64_t)waveFrames * 8;
    }
-   CK(cudaStreamSynchronize(c->stream));
-   if (tm) {
+   return HFB_OK;
+}
+
+static int finish_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, hfb_utt_result *res, const hfb_beams *beams)
+{
+   if (!S.busy) return HFB_OK;
+   S.busy = false;
+   WaveTables &w = *S.w;
+   const int nU = (int)w.utt.size();
+   CK(cudaStreamSynchronize(S.stream));
+   if (c->timing) {
       float ms;
-      cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->stats.msGmm += ms;
-      cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->stats.msBeta += ms;
-      cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->stats.msAlpha += ms;
-      cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->stats.msStats += ms;
+      cudaEventElapsedTime(&ms, S.ev[0], S.ev[1]); c->stats.msGmm += ms;
+      cudaEventElapsedTime(&ms, S.ev[1], S.ev[2]); c->stats.msBeta += ms;
+      cudaEventElapsedTime(&ms, S.ev[2], S.ev[3]); c->stats.msAlpha += ms;
+      cudaEventElapsedTime(&ms, S.ev[3], S.ev[4]); c->stats.msStats += ms;
    }
+   const long long waveFrames = S.waveFrames;
    for (int k = 0; k < nU; k++) {
       hfb_utt_result &r = res[w.uttIndex[k]];
-      const UttOut &o = c->hOut[k];
+      const UttOut &o = S.hOut[k];
       r.status = o.status; r.retries = o.retries; r.pr = o.pr; r.pruneThresh = o.thresh;
       const UttDesc &u = w.utt[k];
       if (o.status == 0) c->stats.gmmPairs += (int64_t)u.T * o.J;
-      if (wantBeams) {
-         const long long dst = waveFrame0 + u.frameBase;                           // frame index in the batch
-         const short *lo = c->hBeams + u.frameBase, *hi = lo + waveFrames, *s = hi + waveFrames, *e = s + waveFrames;
+      if (S.wantBeams) {
+         const long long dst = S.waveFrame0 + u.frameBase;                         // frame index in the batch
+         const short *lo = S.hBeams + u.frameBase, *hi = lo + waveFrames, *s = hi + waveFrames, *e = s + waveFrames;
          for (int t = 0; t < u.T; t++) {
             bool okb = (o.status == 0 || o.status == HFB_UTT_EALPHA);
             if (beams->qLo) beams->qLo[dst + t] = okb ? (int16_t)(lo[t] + 1) : 0;
@@ -635,12 +685,22 @@ static int accumulate_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *re
    if (!c || !b || !res) return HFB_EINVAL;
    if (b->numUtt < 0 || (b->numUtt > 0 && (!b->frameOff || !b->feat || !b->labOff || !b->lab))) return HFB_EINVAL;
    CK(cudaSetDevice(c->device));
+   CK(cudaStreamSynchronize(c->stream));               // accumulator zeroing / model uploads are done
    const HostModel &h = c->hm;
-   const int D = h.D;
-   WaveTables w;
-   int u0 = 0;
+   const bool wantBeams = beams && (beams->qLo || beams->qHi || beams->sq || beams->eq);
+   // timing mode serialises the waves so that the per-kernel events do not overlap
+   const int ns = c->timing ? 1 : c->numSlots;
+   // aim at `ns` waves of equal frame count (one per stream), more if the workspace is too small
+   const long long totalFrames = b->numUtt ? b->frameOff[b->numUtt] - b->frameOff[0] : 0;
+   const long long targetFrames = (b->numUtt >= 64 * ns) ? (totalFrames + ns - 1) / ns : totalFrames;
+   const size_t wsPerSlot = c->workspaceBytes / (size_t)ns;
+   int u0 = 0, k = 0, rcAll = HFB_OK;
    while (u0 < b->numUtt) {
-      // ---- cut a wave that fits the workspace
+      hfbgpu_ctx::Slot &S = c->slot[k % ns];
+      int rc = finish_wave(c, S, res, beams);
+      if (rc) { rcAll = rc; break; }
+      if (!S.w) S.w = new WaveTables();
+      WaveTables &w = *S.w;
       w.clear();
       w.lab0 = b->labOff[u0];
       const long long waveFrame0 = b->frameOff[u0];
@@ -649,7 +709,7 @@ static int accumulate_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *re
       while (u1 < b->numUtt) {
          long long f0 = b->frameOff[u1], f1 = b->frameOff[u1 + 1];
          int T = (int)(f1 - f0), Q = b->labOff[u1 + 1] - b->labOff[u1];
-         if (T > 32767 || Q > 32766) { g_lastError = "utterance beyond int16 beam range"; return HFB_EUNSUPPORTED; }
+         if (T > 32767 || Q > 32766) { g_lastError = "utterance beyond int16 beam range"; rcAll = HFB_EUNSUPPORTED; break; }
          size_t perFrame = 0;
          for (int q = 0; q < Q; q++) {
             int p = b->lab[b->labOff[u1] + q];
@@ -657,26 +717,21 @@ static int accumulate_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *re
             perFrame += (size_t)N * 8 + (size_t)(N - 2) * 12;
          }
          size_t need = (size_t)T * perFrame;
-         if (u1 > u0 && (bytes + need > c->workspaceBytes || u1 - u0 >= 16384)) break;
+         if (u1 > u0 && (bytes + need > wsPerSlot || u1 - u0 >= 16384 || f0 - waveFrame0 >= targetFrames)) break;
          bytes += add_utterance(h, w, u1, T, b->lab + b->labOff[u1], Q, b->labOff[u1] - w.lab0, f0 - waveFrame0);
          u1++;
       }
+      if (rcAll) break;
       const long long waveFrames = b->frameOff[u1] - waveFrame0;
-      const float *dFeat;
-      if (featOnDevice) dFeat = b->feat + (size_t)waveFrame0 * D;
-      else {
-         int rc = c->dFeat.reserve((size_t)waveFrames * D + 4);
-         if (rc) return rc;
-         CK(cudaMemcpyAsync(c->dFeat.p, b->feat + (size_t)waveFrame0 * D, (size_t)waveFrames * D * sizeof(float),
-                            cudaMemcpyHostToDevice, c->stream));
-         c->stats.h2dBytes += (int64_t)waveFrames * D * sizeof(float);
-         dFeat = c->dFeat.p;
-      }
-      int rc = run_wave(c, w, b->lab + w.lab0, dFeat, waveFrame0, waveFrames, res, beams);
-      if (rc) return rc;
-      u0 = u1;
+      rc = launch_wave(c, S, b->lab + w.lab0, b->feat, featOnDevice, waveFrame0, waveFrames, wantBeams);
+      if (rc) { rcAll = rc; break; }
+      u0 = u1; k++;
    }
-   return HFB_OK;
+   for (int i = 0; i < hfbgpu_ctx::NSLOT; i++) {
+      int rc = finish_wave(c, c->slot[(k + i) % hfbgpu_ctx::NSLOT], res, beams);
+      if (rc && !rcAll) rcAll = rc;
+   }
+   return rcAll;
 }
 
 extern "C" int hfbgpu_accumulate(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, const hfb_beams *beams)
@@ -699,6 +754,8 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
    if (mixOut) { g_lastError = "per-mixture output is not exported by the GPU path"; return HFB_EUNSUPPORTED; }
    CK(cudaSetDevice(c->device));
    const HostModel &h = c->hm;
+   hfbgpu_ctx::Slot &S0 = c->slot[0];
+   cudaStream_t st0 = S0.stream;
    for (int i = 0; i < n; i++) if (states[i] < 0 || states[i] >= h.J) return HFB_EINVAL;
    UttDesc u;
    memset(&u, 0, sizeof(u));
@@ -713,30 +770,30 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
    size_t oUtt = blob_put(blob, &u, 1), oOut = blob_put(blob, &o, 1), oSs = blob_put(blob, states, (size_t)n),
           oTp = blob_put(blob, tilePre, 2), oIt = blob_put(blob, items);
    int rc;
-   if ((rc = c->dTables.reserve(blob.size())) || (rc = c->dFeat.reserve((size_t)T * h.D + 4)) ||
-       (rc = c->dB.reserve((size_t)T * n + 1)))
+   if ((rc = S0.dTables.reserve(blob.size())) || (rc = S0.dFeat.reserve((size_t)T * h.D + 4)) ||
+       (rc = S0.dB.reserve((size_t)T * n + 1)))
       return rc;
-   CK(cudaMemcpyAsync(c->dTables.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
-   CK(cudaMemcpyAsync(c->dFeat.p, feat, (size_t)T * h.D * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+   CK(cudaMemcpyAsync(S0.dTables.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, st0));
+   CK(cudaMemcpyAsync(S0.dFeat.p, feat, (size_t)T * h.D * sizeof(float), cudaMemcpyHostToDevice, st0));
    Wave W;
    memset(&W, 0, sizeof(W));
-   W.utt = (UttDesc *)(c->dTables.p + oUtt); W.out = (UttOut *)(c->dTables.p + oOut); W.numUtt = 1;
-   W.slotState = (int *)(c->dTables.p + oSs); W.tilePre = (const int *)(c->dTables.p + oTp);
-   W.feat = c->dFeat.p; W.b = c->dB.p;
+   W.utt = (UttDesc *)(S0.dTables.p + oUtt); W.out = (UttOut *)(S0.dTables.p + oOut); W.numUtt = 1;
+   W.slotState = (int *)(S0.dTables.p + oSs); W.tilePre = (const int *)(S0.dTables.p + oTp);
+   W.feat = S0.dFeat.p; W.b = S0.dB.p;
    int gk = c->opt.gmmKernel;
    if (gk == 0) gk = gmm_tc_available(c->tc) ? 2 : 1;
    if (gk == 2) {
       int nl = 0;
-      if ((rc = gmm_tc_launch(c->tc, c->dm, W, T, (const int2 *)(c->dTables.p + oIt), (int)items.size(),
-                              c->smCount, c->stream, &nl))) return rc;
+      if ((rc = gmm_tc_launch(c->tc, S0.tcw, c->dm, W, T, (const int2 *)(S0.dTables.p + oIt), (int)items.size(),
+                              c->smCount, st0, &nl))) return rc;
       c->stats.launches += nl; c->stats.launchesGmm += nl;
    } else {
       size_t smem = sizeof(float) * ((size_t)c->dm.D * GT_FR + (size_t)GT_FR * (GT_SL + 1));
-      gmm_fp32_kernel<<<(unsigned)nTiles, 128, smem, c->stream>>>(c->dm, W);
+      gmm_fp32_kernel<<<(unsigned)nTiles, 128, smem, st0>>>(c->dm, W);
       c->stats.launches++; c->stats.launchesGmm++;
    }
    CK(cudaGetLastError());
-   CK(cudaMemcpyAsync(out, c->dB.p, (size_t)T * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-   CK(cudaStreamSynchronize(c->stream));
+   CK(cudaMemcpyAsync(out, S0.dB.p, (size_t)T * n * sizeof(float), cudaMemcpyDeviceToHost, st0));
+   CK(cudaStreamSynchronize(st0));
    return HFB_OK;
 }
