@@ -1,0 +1,358 @@
+/* hfbgpu_bridge.c -- see hfbgpu_bridge.h.  Compiled against the reference's headers:
+ *   gcc -I$REF/HTKLib -I include -c bridge/hfbgpu_bridge.c
+ * Pointer map between HTK memory and the flat hfb_model: SURVEY.md 8(b).
+ */
+#include "HShell.h"
+#include "HMem.h"
+#include "HMath.h"
+#include "HSigP.h"
+#include "HAudio.h"
+#include "HWave.h"
+#include "HVQ.h"
+#include "HParm.h"
+#include "HLabel.h"
+#include "HModel.h"
+#include "HTrain.h"
+#include "HUtil.h"
+#include "HAdapt.h"
+#include "HFB.h"
+
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+#include "hfbgpu.h"
+#include "hfbgpu_bridge.h"
+
+/* ------------------------------------------------------------------ pointer -> index map */
+typedef struct { const void **key; int *val; int cap, n; } PMap;
+
+static void pm_init(PMap *m, int cap)
+{
+   int c = 64;
+   while (c < cap * 2) c *= 2;
+   m->cap = c; m->n = 0;
+   m->key = (const void **)calloc(c, sizeof(void *));
+   m->val = (int *)calloc(c, sizeof(int));
+}
+static int pm_slot(const PMap *m, const void *p)
+{
+   size_t h = ((size_t)p >> 4) * 2654435761u;
+   int i = (int)(h & (size_t)(m->cap - 1));
+   while (m->key[i] && m->key[i] != p) i = (i + 1) & (m->cap - 1);
+   return i;
+}
+static int pm_get(const PMap *m, const void *p) { int i = pm_slot(m, p); return m->key[i] ? m->val[i] : -1; }
+static int pm_add(PMap *m, const void *p)          /* returns index, new or existing */
+{
+   int i = pm_slot(m, p);
+   if (!m->key[i]) { m->key[i] = p; m->val[i] = m->n++; }
+   return m->val[i];
+}
+
+/* ------------------------------------------------------------------ state */
+static struct {
+   HMMSet *hset;
+   hfbgpu_ctx *ctx;
+   hfb_model m;
+   hfb_acc_layout L;
+   int D, batchUtts;
+   long batchFrames;
+   UPDSet uFlags;
+   /* HTK objects in flat order */
+   HLink *hmm; StreamElem **ste; MixPDF **mp; SVector *meanV, *varV; SMatrix *trans;
+   PMap pmHmm, pmSte, pmMp, pmMean, pmVar, pmTr;
+   int nHmm, nSte, nMp, nMean, nVar, nTr;
+   /* pending batch */
+   float *feat; long featCap, nFrames;
+   int64_t *frameOff; int32_t *labOff, *lab; int nUtt, labCap, nLab;
+   char **names;
+   /* totals */
+   long nOk, nSkipped;
+} B;
+
+static void *xrealloc(void *p, size_t n)
+{
+   void *q = realloc(p, n);
+   if (!q) HError(7399, "hfbgpu bridge: out of host memory");
+   return q;
+}
+
+/* ------------------------------------------------------------------ flatten the HMMSet */
+static void Flatten(HMMSet *hset)
+{
+   HMMScanState hss;
+   int p, j, m, k, D = hset->vecSize, sumM = 0, sumE = 0, sumNN = 0;
+   int32_t *stateMixOff, *mixGauss, *hmmN, *hmmStateOff, *hmmState, *hmmTrans, *transN, *transOff, *meanId, *varId;
+   float *mixLogWt, *mean, *ivar, *gConst, *transLogA;
+
+   if (hset->swidth[0] != 1) HError(7399, "hfbgpu bridge: only single-stream sets are accelerated");
+   if (hset->hsKind != PLAINHS && hset->hsKind != SHAREDHS)
+      HError(7399, "hfbgpu bridge: only PLAINHS/SHAREDHS sets are accelerated");
+   pm_init(&B.pmHmm, hset->numPhyHMM); pm_init(&B.pmSte, hset->numStates + 16);
+   pm_init(&B.pmMp, hset->numMix + 16); pm_init(&B.pmMean, hset->numMix + 16);
+   pm_init(&B.pmVar, hset->numMix + 16); pm_init(&B.pmTr, hset->numPhyHMM);
+   B.hmm = (HLink *)calloc(hset->numPhyHMM + 1, sizeof(HLink));
+
+   /* pass 1: number physical HMMs (HMMScan order = dump order), states, pdfs, vectors, matrices */
+   NewHMMScan(hset, &hss);
+   do {
+      HLink hmm = hss.hmm;
+      p = pm_add(&B.pmHmm, hmm); B.hmm[p] = hmm;
+      pm_add(&B.pmTr, hmm->transP);
+      for (j = 2; j < hmm->numStates; j++) {
+         StreamElem *ste = hmm->svec[j].info->pdf + 1;
+         int M = ste->nMix < 0 ? -ste->nMix : ste->nMix;
+         if (pm_get(&B.pmSte, ste) < 0) {
+            pm_add(&B.pmSte, ste);
+            for (m = 1; m <= M; m++) {
+               MixPDF *mp = ste->spdf.cpdf[m].mpdf;
+               if (mp->ckind != INVDIAGC && mp->ckind != DIAGC)
+                  HError(7399, "hfbgpu bridge: only diagonal covariances are accelerated");
+               pm_add(&B.pmMp, mp); pm_add(&B.pmMean, mp->mean); pm_add(&B.pmVar, mp->cov.var);
+            }
+            sumM += M;
+         }
+         sumE++;
+      }
+   } while (GoNextHMM(&hss));
+   EndHMMScan(&hss);
+   B.nHmm = B.pmHmm.n; B.nSte = B.pmSte.n; B.nMp = B.pmMp.n; B.nMean = B.pmMean.n; B.nVar = B.pmVar.n; B.nTr = B.pmTr.n;
+
+   B.ste = (StreamElem **)calloc(B.nSte + 1, sizeof(void *)); B.mp = (MixPDF **)calloc(B.nMp + 1, sizeof(void *));
+   B.meanV = (SVector *)calloc(B.nMean + 1, sizeof(SVector)); B.varV = (SVector *)calloc(B.nVar + 1, sizeof(SVector));
+   B.trans = (SMatrix *)calloc(B.nTr + 1, sizeof(SMatrix));
+   stateMixOff = (int32_t *)calloc(B.nSte + 1, sizeof(int32_t));
+   mixGauss = (int32_t *)calloc(sumM + 1, sizeof(int32_t)); mixLogWt = (float *)calloc(sumM + 1, sizeof(float));
+   mean = (float *)calloc((size_t)B.nMp * D + 1, sizeof(float)); ivar = (float *)calloc((size_t)B.nMp * D + 1, sizeof(float));
+   gConst = (float *)calloc(B.nMp + 1, sizeof(float));
+   meanId = (int32_t *)calloc(B.nMp + 1, sizeof(int32_t)); varId = (int32_t *)calloc(B.nMp + 1, sizeof(int32_t));
+   hmmN = (int32_t *)calloc(B.nHmm + 1, sizeof(int32_t)); hmmStateOff = (int32_t *)calloc(B.nHmm + 2, sizeof(int32_t));
+   hmmState = (int32_t *)calloc(sumE + 1, sizeof(int32_t)); hmmTrans = (int32_t *)calloc(B.nHmm + 1, sizeof(int32_t));
+   transN = (int32_t *)calloc(B.nTr + 1, sizeof(int32_t)); transOff = (int32_t *)calloc(B.nTr + 2, sizeof(int32_t));
+
+   /* pass 2: fill (state / pdf numbering follows first-use order of pass 1, so offsets are
+      assigned by walking the states in index order) */
+   {
+      int *mOfState = (int *)calloc(B.nSte + 1, sizeof(int));
+      for (p = 0; p < B.nHmm; p++) {
+         HLink hmm = B.hmm[p];
+         for (j = 2; j < hmm->numStates; j++) {
+            StreamElem *ste = hmm->svec[j].info->pdf + 1;
+            int s = pm_get(&B.pmSte, ste);
+            B.ste[s] = ste; mOfState[s] = ste->nMix < 0 ? -ste->nMix : ste->nMix;
+         }
+      }
+      for (j = 0; j < B.nSte; j++) stateMixOff[j + 1] = stateMixOff[j] + mOfState[j];
+      free(mOfState);
+   }
+   for (j = 0; j < B.nSte; j++) {
+      StreamElem *ste = B.ste[j];
+      int M = stateMixOff[j + 1] - stateMixOff[j];
+      for (m = 1; m <= M; m++) {
+         MixPDF *mp = ste->spdf.cpdf[m].mpdf;
+         int g = pm_get(&B.pmMp, mp), o = stateMixOff[j] + m - 1;
+         mixGauss[o] = g;
+         mixLogWt[o] = MixLogWeight(hset, ste->spdf.cpdf[m].weight);     /* log weight (ConvLogWt done) */
+         if (!B.mp[g]) {
+            B.mp[g] = mp;
+            meanId[g] = pm_get(&B.pmMean, mp->mean); varId[g] = pm_get(&B.pmVar, mp->cov.var);
+            B.meanV[meanId[g]] = mp->mean; B.varV[varId[g]] = mp->cov.var;
+            gConst[g] = mp->gConst;                                      /* as stored, never recomputed */
+            for (k = 1; k <= D; k++) {
+               mean[(size_t)g * D + k - 1] = mp->mean[k];
+               ivar[(size_t)g * D + k - 1] = (mp->ckind == INVDIAGC) ? mp->cov.var[k] : 1.0f / mp->cov.var[k];
+            }
+         }
+      }
+   }
+   for (p = 0; p < B.nHmm; p++) {
+      HLink hmm = B.hmm[p];
+      int t = pm_get(&B.pmTr, hmm->transP);
+      hmmN[p] = hmm->numStates; hmmTrans[p] = t;
+      hmmStateOff[p + 1] = hmmStateOff[p] + hmm->numStates - 2;
+      for (j = 2; j < hmm->numStates; j++) hmmState[hmmStateOff[p] + j - 2] = pm_get(&B.pmSte, hmm->svec[j].info->pdf + 1);
+      if (!B.trans[t]) { B.trans[t] = hmm->transP; transN[t] = hmm->numStates; }
+   }
+   for (j = 0; j < B.nTr; j++) { transOff[j + 1] = transOff[j] + transN[j] * transN[j]; }
+   sumNN = transOff[B.nTr];
+   transLogA = (float *)calloc(sumNN + 1, sizeof(float));
+   for (j = 0; j < B.nTr; j++) {
+      int N = transN[j], a, b2;
+      for (a = 1; a <= N; a++) for (b2 = 1; b2 <= N; b2++) transLogA[transOff[j] + (a - 1) * N + b2 - 1] = B.trans[j][a][b2];
+   }
+   memset(&B.m, 0, sizeof(B.m));
+   B.m.vecSize = D; B.m.numGauss = B.nMp; B.m.mean = mean; B.m.ivar = ivar; B.m.gConst = gConst;
+   B.m.meanId = meanId; B.m.varId = varId; B.m.numMeanAcc = B.nMean; B.m.numVarAcc = B.nVar;
+   B.m.numStates = B.nSte; B.m.stateMixOff = stateMixOff; B.m.mixGauss = mixGauss; B.m.mixLogWt = mixLogWt;
+   B.m.numHmm = B.nHmm; B.m.hmmNumStates = hmmN; B.m.hmmStateOff = hmmStateOff; B.m.hmmState = hmmState;
+   B.m.hmmTrans = hmmTrans; B.m.numTrans = B.nTr; B.m.transN = transN; B.m.transOff = transOff; B.m.transLogA = transLogA;
+   B.D = D;
+}
+
+/* ------------------------------------------------------------------ public */
+void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pruneInc,
+                 LogDouble pruneLim, float minFrwdP, UPDSet uFlags)
+{
+   hfb_options opt;
+   ConfParam *cParm[MAXGLOBS];
+   int nParm, rc;
+   double d;
+   char *env;
+
+   memset(&B, 0, sizeof(B));
+   B.hset = hset; B.uFlags = uFlags;
+   if (fbInfo->twoModels) HError(7399, "hfbgpu bridge: 2-model re-estimation is not accelerated");
+   if (hset->xf != NULL || (uFlags & (UPXFORM | UPSEMIT | UPMAP)))
+      HError(7399, "hfbgpu bridge: transforms / MAP updates are not accelerated");
+   if (!hset->logWt) HError(7399, "hfbgpu bridge: expected log weights (ConvLogWt)");
+   Flatten(hset);
+   hfbgpu_default_options(&opt);
+   /* same precedence as InitFB + InitialiseForBack (HFB.c:221-233, :270-276): config file first,
+      command line overrides */
+   nParm = GetConfig("HFB", TRUE, cParm, MAXGLOBS);
+   if (nParm > 0) {
+      if (GetConfFlt(cParm, nParm, "PRUNEINIT", &d)) opt.pruneInit = d;
+      if (GetConfFlt(cParm, nParm, "PRUNEINC", &d)) opt.pruneInc = d;
+      if (GetConfFlt(cParm, nParm, "PRUNELIM", &d)) opt.pruneLim = d;
+      if (GetConfFlt(cParm, nParm, "MINFORPROB", &d)) opt.minFrwdP = (float)d;
+   }
+   if (pruneInit < NOPRUNE) { opt.pruneInit = pruneInit; opt.pruneInc = pruneInc; opt.pruneLim = pruneLim; }
+   if (minFrwdP < NOPRUNE) opt.minFrwdP = minFrwdP;
+   opt.uFlags = 0;
+   if (uFlags & UPMEANS) opt.uFlags |= HFB_UPMEANS;
+   if (uFlags & UPVARS) opt.uFlags |= HFB_UPVARS;
+   if (uFlags & UPTRANS) opt.uFlags |= HFB_UPTRANS;
+   if (uFlags & UPMIXES) opt.uFlags |= HFB_UPMIXES;
+   env = getenv("HFBGPU_DEVICE"); opt.device = env ? atoi(env) : 0;
+   env = getenv("HFBGPU_BATCH_UTTS"); B.batchUtts = env ? atoi(env) : 2048;
+   env = getenv("HFBGPU_BATCH_FRAMES"); B.batchFrames = env ? atol(env) : 4000000L;
+   rc = hfbgpu_create(&B.ctx, &B.m, &opt);
+   if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_create failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
+   hfbgpu_acc_layout(&B.m, &B.L);
+   printf("hfbgpu: %d physical HMMs, %d tied states, %d Gaussians, %d transition matrices on device %d\n",
+          B.nHmm, B.nSte, B.nMp, B.nTr, opt.device);
+   fflush(stdout);
+}
+
+static void Flush(void)
+{
+   hfb_batch b;
+   hfb_utt_result *res;
+   int u, rc;
+   if (B.nUtt == 0) return;
+   B.frameOff[B.nUtt] = B.nFrames; B.labOff[B.nUtt] = B.nLab;
+   b.numUtt = B.nUtt; b.frameOff = B.frameOff; b.feat = B.feat; b.labOff = B.labOff; b.lab = B.lab;
+   res = (hfb_utt_result *)calloc(B.nUtt, sizeof(hfb_utt_result));
+   rc = hfbgpu_accumulate(B.ctx, &b, res, NULL);
+   if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_accumulate failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
+   for (u = 0; u < B.nUtt; u++) {
+      if (res[u].status == HFB_UTT_OK) B.nOk++;
+      else if (res[u].status == HFB_UTT_SKIPPED) {                      /* HFB.c:1342, :1354 */
+         HError(-7324, "StepBack: File %s - bad data or over pruning\n", B.names[u]);
+         B.nSkipped++;
+      } else if (res[u].status == HFB_UTT_ETEE)
+         HError(7332, "CreateInsts: Cannot have Tee models at start or end of transcription / successive Tee models (%s)", B.names[u]);
+      else
+         HError(res[u].status, "hfbgpu: forward-backward failed for %s (%s)", B.names[u], hfbgpu_strerror(res[u].status));
+      free(B.names[u]);
+   }
+   free(res);
+   B.nUtt = 0; B.nFrames = 0; B.nLab = 0;
+}
+
+/* Replaces FBFile (HFB.c:1923): the utterance is only buffered here.  Always returns FALSE so
+   that the caller's own totalT/totalPr update (HERest.c:777-786) is skipped; HFBGPU_Finish sets
+   the totals from the device accumulators instead. */
+Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
+{
+   LLink lab;
+   int q, t, k, T = utt->T, Q = utt->Q, D = B.D;
+   if (utt->twoDataFiles) HError(7399, "hfbgpu bridge: single-pass retraining is not accelerated");
+   if (B.nUtt == 0 && !B.frameOff) {
+      B.frameOff = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (B.batchUtts + 2));
+      B.labOff = (int32_t *)xrealloc(NULL, sizeof(int32_t) * (B.batchUtts + 2));
+      B.names = (char **)xrealloc(NULL, sizeof(char *) * (B.batchUtts + 2));
+   }
+   if (B.nFrames + T > B.featCap) {
+      B.featCap = (B.nFrames + T) * 2 + 1024;
+      B.feat = (float *)xrealloc(B.feat, sizeof(float) * (size_t)B.featCap * D);
+   }
+   if (B.nLab + Q > B.labCap) {
+      B.labCap = (B.nLab + Q) * 2 + 1024;
+      B.lab = (int32_t *)xrealloc(B.lab, sizeof(int32_t) * (size_t)B.labCap);
+   }
+   B.frameOff[B.nUtt] = B.nFrames; B.labOff[B.nUtt] = B.nLab;
+   /* labels -> physical HMM indices (CreateInsts, HFB.c:538-542) */
+   for (lab = utt->tr->head->head->succ, q = 0; lab->succ != NULL; lab = lab->succ, q++) {
+      MLink ml = FindMacroName(B.hset, 'l', lab->labid);
+      int p;
+      if (ml == NULL) HError(7321, "CreateInsts: Unknown label %s", lab->labid->name);
+      p = pm_get(&B.pmHmm, ml->structure);
+      if (p < 0) HError(7321, "hfbgpu bridge: label %s maps to an unknown physical HMM", lab->labid->name);
+      B.lab[B.nLab + q] = p;
+   }
+   /* observations exactly as the reference reads them, frame by frame (HFB.c:1009, :1778) */
+   for (t = 0; t < T; t++) {
+      ReadAsTable(utt->pbuf, t, &utt->ot);
+      for (k = 1; k <= D; k++) B.feat[(size_t)(B.nFrames + t) * D + k - 1] = utt->ot.fv[1][k];
+   }
+   B.names[B.nUtt] = strdup(datafn);
+   B.nFrames += T; B.nLab += Q; B.nUtt++;
+   if (B.nUtt >= B.batchUtts || B.nFrames >= B.batchFrames) Flush();
+   return FALSE;
+}
+
+/* Scatter the device accumulators into HTK's (float) accumulators. */
+void HFBGPU_Finish(int *totalT, LogDouble *totalPr)
+{
+   double *acc;
+   int p, s, g, t, i, j, k, D = B.D, rc;
+   long long o;
+   Flush();
+   acc = (double *)calloc((size_t)B.L.count, sizeof(double));
+   rc = hfbgpu_get_accs(B.ctx, acc);
+   if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_get_accs failed: %s", hfbgpu_strerror(rc));
+   for (p = 0; p < B.nHmm; p++) {
+      long n = (long)B.hmm[p]->hook + (long)(acc[B.L.numEgs + p] + 0.5);
+      B.hmm[p]->hook = (void *)n;                                       /* HFB.c:1768-1772 */
+   }
+   for (t = 0, o = 0; t < B.nTr; t++) {
+      TrAcc *ta = (TrAcc *)GetHook(B.trans[t]);
+      int N = B.m.transN[t];
+      if (ta != NULL && (B.uFlags & UPTRANS))
+         for (i = 1; i <= N; i++)
+            for (j = 1; j <= N; j++) ta->tran[i][j] += (float)acc[B.L.tran + o + (i - 1) * N + j - 1];
+      o += (long long)N * N;
+   }
+   for (t = 0, o = 0; t < B.nTr; t++) {
+      TrAcc *ta = (TrAcc *)GetHook(B.trans[t]);
+      int N = B.m.transN[t];
+      if (ta != NULL && (B.uFlags & UPTRANS)) for (i = 1; i <= N; i++) ta->occ[i] += (float)acc[B.L.tranOcc + o + i - 1];
+      o += N;
+   }
+   for (s = 0; s < B.nSte; s++) {
+      WtAcc *wa = (WtAcc *)B.ste[s]->hook;
+      int M = B.m.stateMixOff[s + 1] - B.m.stateMixOff[s];
+      if (wa == NULL) continue;
+      for (k = 1; k <= M; k++) wa->c[k] += (float)acc[B.L.wtC + B.m.stateMixOff[s] + k - 1];
+      wa->occ += (float)acc[B.L.wtOcc + s];
+   }
+   for (g = 0; g < B.nMean; g++) {
+      MuAcc *ma = (MuAcc *)GetHook(B.meanV[g]);
+      if (ma == NULL) continue;
+      for (k = 1; k <= D; k++) ma->mu[k] += (float)acc[B.L.muSum + (long long)g * D + k - 1];
+      ma->occ += (float)acc[B.L.muOcc + g];
+   }
+   for (g = 0; g < B.nVar; g++) {
+      VaAcc *va = (VaAcc *)GetHook(B.varV[g]);
+      if (va == NULL) continue;
+      for (k = 1; k <= D; k++) va->cov.var[k] += (float)acc[B.L.vaSum + (long long)g * D + k - 1];
+      va->occ += (float)acc[B.L.vaOcc + g];
+   }
+   *totalT += (int)(acc[B.L.totalT] + 0.5);                             /* HERest.c:779-780 */
+   *totalPr += acc[B.L.totalPr];
+   free(acc);
+   hfbgpu_destroy(B.ctx);
+   B.ctx = NULL;
+}

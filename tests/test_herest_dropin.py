@@ -1,0 +1,101 @@
+"""Drop-in test: the reference's own HERest (C, unmodified apart from the 4-line call-site patch
+applied locally by bridge/make_herest_gpu.sh) driving libhfbgpu through bridge/hfbgpu_bridge.c,
+against the stock HERest, on the same MMF / MLF / feature files:
+
+  * `-p 1` accumulator dumps (HER1.acc) within 1e-4,
+  * the MMF re-estimated by the STOCK `HERest -p 0` from either dump within 1e-4 relative on
+    means and variances (BASELINE.json north_star),
+  * the skipped-utterance warning path.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, acc_errors
+from htk_b200 import htkio, synth
+from htk_b200.flat import flatten
+
+pytestmark = pytest.mark.gpu
+
+BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
+HEREST, HEREST_GPU = os.path.join(BIN, "HERest"), os.path.join(BIN, "HERest_gpu")
+
+
+def _run(cmd, cwd):
+    p = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert p.returncode == 0, p.stdout[-3000:]
+    return p.stdout
+
+
+def _setup(tmp, hs, n_utts, T, Q, seed, tee=False, add_short=False):
+    htkio.write_mmf(os.path.join(tmp, "mmf"), hs)
+    htkio.write_hmm_list(os.path.join(tmp, "list"), hs)
+    hs2 = htkio.read_mmf([os.path.join(tmp, "mmf")], hmm_list=open(os.path.join(tmp, "list")).read().splitlines())
+    fm = flatten(hs2)
+    feats, labs = synth.sample_corpus(fm, n_utts, T, Q, seed=seed, tee_index=fm.hmm_index["sp"] if tee else None,
+                                      T_jitter=T // 10)
+    if add_short:
+        rng = np.random.default_rng(seed)
+        labs.insert(1, rng.integers(0, fm.P - (1 if tee else 0), size=Q).astype(np.int32))
+        feats.insert(1, rng.standard_normal((Q, fm.D)).astype(np.float32))
+    os.makedirs(os.path.join(tmp, "feat"))
+    mlf, scp = {}, []
+    for i, (f, l) in enumerate(zip(feats, labs)):
+        fn = os.path.join(tmp, "feat", "u%03d.mfc" % i)
+        htkio.write_htk_features(fn, f, hs.parm_kind)
+        mlf["u%03d" % i] = [fm.names[j] for j in l]
+        scp.append(fn)
+    htkio.write_mlf(os.path.join(tmp, "labs.mlf"), mlf)
+    open(os.path.join(tmp, "scp"), "w").write("\n".join(scp) + "\n")
+    return hs2, fm
+
+
+def _mmf_params(path, names):
+    hs = htkio.read_mmf([path], hmm_list=names)
+    fm = flatten(hs)
+    var = 1.0 / fm.ivar.astype(np.float64)
+    return fm.mean.astype(np.float64), var, fm.transLogA.astype(np.float64), fm.mixLogWt.astype(np.float64)
+
+
+@pytest.mark.parametrize("case", ["tied_m4", "tee_m2_pruned"])
+def test_herest_gpu_matches_stock_herest(tmp_path, case):
+    if not (os.path.exists(HEREST) and os.path.exists(HEREST_GPU)):
+        pytest.skip("reference binaries not built (bridge/make_herest_gpu.sh needs /root/reference)")
+    tmp = str(tmp_path)
+    if case == "tied_m4":
+        hs = synth.make_tied_triphone_set(n_states=50, M=4, n_phys=30, n_logical=45, n_centre=6, seed=31, spread=0.2)
+        hs2, fm = _setup(tmp, hs, n_utts=10, T=300, Q=30, seed=4)
+        targs = []
+    else:
+        hs = synth.make_monophone_set(n_phones=10, M=2, seed=32, tee_model=True, entry_skip=0.1, spread=0.15)
+        hs2, fm = _setup(tmp, hs, n_utts=10, T=250, Q=18, seed=5, tee=True, add_short=True)
+        targs = ["-t", "40.0", "20.0", "400.0"]
+    base = ["-T", "1", "-u", "tmvw"] + targs + ["-p", "1", "-H", "mmf", "-I", "labs.mlf", "-S", "scp"]
+    for exe, d in ((HEREST, "accA"), (HEREST_GPU, "accB")):
+        os.makedirs(os.path.join(tmp, d))
+        out = _run([exe] + base + ["-M", d, "list"], tmp)
+        if case != "tied_m4":
+            assert "7324" in out                       # the too-short utterance is skipped with a warning
+    a, prA, tA = htkio.read_acc_dump(os.path.join(tmp, "accA", "HER1.acc"), hs2, fm)
+    b, prB, tB = htkio.read_acc_dump(os.path.join(tmp, "accB", "HER1.acc"), hs2, fm)
+    assert tA == tB and abs(prA - prB) <= 1e-6 * abs(prA)
+    L = fm.layout
+    e = acc_errors(b, a, fm)
+    e.pop("totalPr"); e.pop("totalT")
+    assert max(e.values()) < 1e-4, e
+    # M-step by the stock tool from each dump
+    names = open(os.path.join(tmp, "list")).read().splitlines()
+    for d, o in (("accA", "outA"), ("accB", "outB")):
+        os.makedirs(os.path.join(tmp, o))
+        _run([HEREST, "-u", "tmvw", "-p", "0", "-H", "mmf", "-M", o, "list", os.path.join(d, "HER1.acc")], tmp)
+    mA, vA, tA_, wA = _mmf_params(os.path.join(tmp, "outA", "mmf"), names)
+    mB, vB, tB_, wB = _mmf_params(os.path.join(tmp, "outB", "mmf"), names)
+    # MMF text carries 7 significant digits: allow one unit of that on top of the 1e-4 bar
+    assert np.max(np.abs(mA - mB) / np.sqrt(vA)) < 1e-4 + 2e-6
+    assert np.max(np.abs(vA - vB) / vA) < 1e-4 + 2e-6
+    ok = tA_ > -1e9
+    assert np.array_equal(ok, tB_ > -1e9)
+    assert np.max(np.abs(np.exp(tA_[ok]) - np.exp(tB_[ok]))) < 1e-4
+    assert np.max(np.abs(np.exp(wA) - np.exp(wB))) < 1e-4
