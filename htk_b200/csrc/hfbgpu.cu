@@ -18,6 +18,7 @@
 #include "hfb_common.h"
 #include "hfb_kernels.cuh"
 #include "hfb_kernels2.cuh"
+#include "hfb_fast.cuh"
 #include "gmm_tc.cuh"
 
 static thread_local std::string g_lastError;
@@ -75,12 +76,12 @@ struct WaveTables {
    std::vector<int> uttIndex;        // index in the caller's batch
    long long bFloats = 0, betaDoubles = 0, occDoubles = 0;
    long long totalQ = 0, totalP = 0, tiles = 0;
-   int maxQ = 0, maxS = 0;
+   int maxQ = 0, maxS = 0, maxN = 0;
    int lab0 = 0;                     // first label of the wave in the caller's label array
    void clear()
    {
       utt.clear(); out.clear(); posPre.clear(); tilePre.clear(); tcItems.clear(); uttIndex.clear();
-      bFloats = betaDoubles = occDoubles = 0; totalQ = totalP = tiles = 0; maxQ = maxS = 0; lab0 = 0;
+      bFloats = betaDoubles = occDoubles = 0; totalQ = totalP = tiles = 0; maxQ = maxS = maxN = 0; lab0 = 0;
    }
 };
 
@@ -460,7 +461,7 @@ size_t add_utterance(const HostModel &h, WaveTables &w, int uidx, int T, const i
    bool bad = (Q < 1 || T < 1);
    for (int q = 0; q < Q && !bad; q++) {
       const int p = lab[q];
-      if (p < 0 || p >= h.P) bad = true; else S += h.hmmN[p];
+      if (p < 0 || p >= h.P) bad = true; else { S += h.hmmN[p]; w.maxN = std::max(w.maxN, h.hmmN[p]); }
    }
    if (bad) { o.status = HFB_UTT_ETEE; Q = 0; S = 0; }
    const int Pp = S - 2 * Q;
@@ -604,7 +605,18 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
          g_lastError = "utterance too long for the shared-memory window"; return HFB_EUNSUPPORTED;
       }
       const bool exact = getenv("HFBGPU_EXACT_LADD") != nullptr;
-      if (exact) beta_kernel<true><<<nU, nt, rsm, st>>>(c->dm, W);
+      static const bool noFast = getenv("HFBGPU_NO_FAST") != nullptr;
+      const bool fastOk = !noFast && w.maxQ <= 256 && w.maxN <= 8;
+      if (fastOk) {
+         const size_t fsm = beta_fast_smem_bytes(w.maxQ);
+         if (w.maxN <= 5) {
+            if (exact) beta_fast_kernel<true, 3><<<nU, nt, fsm, st>>>(c->dm, W);
+            else beta_fast_kernel<false, 3><<<nU, nt, fsm, st>>>(c->dm, W);
+         } else {
+            if (exact) beta_fast_kernel<true, 6><<<nU, nt, fsm, st>>>(c->dm, W);
+            else beta_fast_kernel<false, 6><<<nU, nt, fsm, st>>>(c->dm, W);
+         }
+      } else if (exact) beta_kernel<true><<<nU, nt, rsm, st>>>(c->dm, W);
       else beta_kernel<false><<<nU, nt, rsm, st>>>(c->dm, W);
       if (tm) cudaEventRecord(S.ev[2], st);
       if (exact) alpha_warp_kernel<true><<<nU, 32, asm_, st>>>(c->dm, W);
