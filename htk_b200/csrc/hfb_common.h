@@ -40,7 +40,8 @@ struct UttDesc {
    long long featOff;               // first frame in the feature matrix
    long long bOff;                  // floats : [T][J] state log-likelihoods
    long long betaOff;               // doubles: [T][S]
-   long long occOff;                // doubles: [T][P] log occupancies / initx
+   long long occOff;                // doubles: [T][P] alpha of the emitting states (inside the alpha beam)
+   long long aentOff;               // doubles: [T][Q] alpha of the entry states (inside the alpha beam)
    long long frameBase;             // first frame in the per-frame beam arrays
 };
 
@@ -50,7 +51,7 @@ struct UttOut {                     // hfb_utt_result + what the host wants back
    double pr;
    double thresh;
    int J;
-   int pad;
+   int redo;                        // fast alpha kernel gave up (window > 32 models): generic kernel redoes it
 };
 
 struct Wave {                       // everything the kernels of one wave need
@@ -80,6 +81,7 @@ struct Wave {                       // everything the kernels of one wave need
    float *b;
    double *beta;
    double *occ;
+   double *aent;
    short *qLo, *qHi, *sq, *eq;      // per-frame beams (0-based)
    double *acc;
    // options

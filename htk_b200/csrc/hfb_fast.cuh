@@ -241,3 +241,170 @@ __global__ void __launch_bounds__(256) beta_fast_kernel(DevModel M, Wave W)
       if (status == HFB_UTT_SKIPPED) atomicAdd(&W.acc[M.L.numSkipped], 1.0);
    }
 }
+
+// ------------------------------------------------------------------------------------------
+// K3 fast: alpha recursion + alpha beam, one WARP per utterance, lane L owns the model q with
+// q = L (mod 32) inside the sliding 32-model window that starts at the beam's lower end.
+// Neighbour values travel by warp shuffles; nothing but alpha, the beams and first/last active
+// frame per model is written.  Falls back (out->redo) if a beam ever needs more than 32 models.
+// ------------------------------------------------------------------------------------------
+template <bool EXACT, int E>
+__global__ void __launch_bounds__(32) alpha_fast_kernel(DevModel M, Wave W, int forceRedo)
+{
+   const UttDesc u = W.utt[blockIdx.x];
+   UttOut *out = &W.out[blockIdx.x];
+   if (out->status != 0) return;
+   if (forceRedo) { if (threadIdx.x == 0) out->redo = 1; return; }
+   const unsigned FULL = 0xffffffffu;
+   const int lane = threadIdx.x;
+   const int T = u.T, Q = u.Q, S = u.S, J = u.J, P = u.P;
+   const float *bU = W.b + u.bOff;
+   const double *betaU = W.beta + u.betaOff;
+   double *occU = W.occ + u.occOff, *aentU = W.aent + u.aentOff;
+   const short *qLo = W.qLo + u.frameBase, *qHi = W.qHi + u.frameBase;
+   short *sqA = W.sq + u.frameBase, *eqA = W.eq + u.frameBase;
+   const double pr = out->pr, minF = W.minFrwdP;
+   int *gTmin = W.mTmin + u.modOff, *gTmax = W.mTmax + u.modOff;
+   for (int q = lane; q < Q; q += 32) { gTmin[q] = 0x7fffffff; gTmax[q] = -1; }
+
+   ModelRegs<E> r;
+   int myq = lane;
+   bool have = myq < Q;
+   if (have) load_model<E>(r, M, W, u, myq);
+   else { r.N = 2; r.so = 0; r.po = 0; r.dms = 1; r.aTee = (float)LZERO_D; }
+   double aEm[E], aEx = LZERO_D, mpS = LZERO_D, exv = LZERO_D;
+#pragma unroll
+   for (int j = 0; j < E; j++) aEm[j] = LZERO_D;
+   int tmin = 0x7fffffff, tmax = -1;
+   int sq = 0, eq = 0;
+
+   for (int t = 0; t < T; t++) {
+      const int loT = qLo[t], hiT = qHi[t];
+      const int ne = r.N - 2;
+      // loads that do not depend on the recursion go first
+      const bool inWin = have && myq >= sq && myq <= ((t == 0) ? hiT : min(Q - 1, eq + 3));
+      float b0[E];
+      double bEn = LZERO_D, bEm[E], bX = LZERO_D;
+#pragma unroll
+      for (int j = 0; j < E; j++) { b0[j] = 0.f; bEm[j] = LZERO_D; }
+      if (inWin && myq >= loT && myq <= hiT) {
+         const float *bt = bU + (size_t)t * J;
+         const double *bq = betaU + (size_t)t * S + r.so;
+         bEn = bq[0]; bX = bq[r.N - 1];
+#pragma unroll
+         for (int j = 0; j < E; j++) if (j < ne) { b0[j] = bt[r.slot[j]]; bEm[j] = bq[1 + j]; }
+      }
+      double a1 = LZERO_D, nEm[E], nEx = LZERO_D;
+#pragma unroll
+      for (int j = 0; j < E; j++) nEm[j] = LZERO_D;
+      int nsq, neq;
+      if (t == 0) {
+         // ---- InitAlpha, HFB.c:616-651
+         nsq = 0; neq = hiT;
+         if (neq + 3 >= 32) { if (lane == 0) out->redo = 1; return; }
+         if (lane == 0) a1 = 0.0;
+         for (int qq = 1; qq <= neq; qq++) {                  // entry chain through leading tee models
+            double v = __shfl_sync(FULL, a1, qq - 1) + (double)__shfl_sync(FULL, r.aTee, qq - 1);
+            if (lane == qq) a1 = v;
+         }
+         if (have && myq <= neq) {
+#pragma unroll
+            for (int j = 0; j < E; j++)
+               if (j < ne) nEm[j] = (r.aEnt[j] > (float)LSMALL_D) ? a1 + (double)r.aEnt[j] + (double)b0[j] : LZERO_D;
+            double x = LZERO_D;
+#pragma unroll
+            for (int i = 0; i < E; i++)
+               if (i < ne && r.aExit[i] > (float)LSMALL_D) x = ladd<EXACT>(x, nEm[i] + (double)r.aExit[i]);
+            nEx = x;
+         } else a1 = LZERO_D;
+      } else {
+         // ---- alpha beam, HFB.c:701-722
+         const int loP = qLo[t - 1], hiP = qHi[t - 1];
+         const int q1 = __shfl_sync(FULL, myq, (lane + 31) & 31), q2 = __shfl_sync(FULL, myq, (lane + 30) & 31);
+         const double ex1 = __shfl_sync(FULL, exv, (lane + 31) & 31), ex2 = __shfl_sync(FULL, exv, (lane + 30) & 31);
+         const double ax1 = __shfl_sync(FULL, aEx, (lane + 31) & 31), ax2 = __shfl_sync(FULL, aEx, (lane + 30) & 31);
+         const float tee1 = __shfl_sync(FULL, r.aTee, (lane + 31) & 31);
+         const bool ok1 = (q1 == myq - 1), ok2 = (q2 == myq - 2);
+         const double e1 = ok1 ? ex1 : LZERO_D, e2 = ok2 ? ex2 : LZERO_D;
+         double mp = fmax(e1, mpS);
+         int c = (inWin && myq >= loP && !(pr - mp > minF)) ? myq : 0x7fffffff;
+         nsq = __reduce_min_sync(FULL, c);
+         if (nsq > hiT) { if (lane == 0) out->status = HFB_UTT_EALPHA; return; }        // HError 7390
+         if (nsq < loT) nsq = loT;
+         const int eq0 = (hiP < Q - 1) ? hiP + 1 : hiP;
+         double mp2 = e1;
+         if (myq >= 2 && myq - 1 > nsq && ok1 && tee1 > (float)LSMALL_D) mp2 = fmax(mp2, e2);
+         mp2 = fmax(mp2, mpS);
+         c = (inWin && myq <= eq0 && !(pr - mp2 > minF)) ? myq : -1;
+         neq = __reduce_max_sync(FULL, c);
+         if (neq < nsq) { if (lane == 0) out->status = HFB_UTT_EALPHA; return; }
+         while (neq < Q - 1) {                                 // while (eq<Q && qDms[eq]==0) eq++
+            const int hq = __shfl_sync(FULL, myq, neq & 31), hd = __shfl_sync(FULL, r.dms, neq & 31);
+            if (hq != neq) { if (lane == 0) out->redo = 1; return; }
+            if (hd == 0) neq++; else break;
+         }
+         if (neq > hiT) neq = hiT;
+         if (neq + 3 - nsq >= 32) { if (lane == 0) out->redo = 1; return; }
+         // ---- alpha column, HFB.c:729-771
+         if (have && myq >= nsq && myq <= neq) {
+            a1 = (myq > 0 && ok1) ? ax1 : LZERO_D;
+            if (myq > nsq && ok1 && tee1 > (float)LSMALL_D) {
+               double y = (myq >= 2 && ok2) ? ax2 : LZERO_D;
+               a1 = ladd<EXACT>(a1, y + (double)tee1);
+            }
+#pragma unroll
+            for (int j = 0; j < E; j++) {
+               if (j < ne) {
+                  double x = (r.aEnt[j] > (float)LSMALL_D) ? (double)r.aEnt[j] + a1 : LZERO_D;
+#pragma unroll
+                  for (int i = 0; i < E; i++)
+                     if (r.aInt[i][j] > (float)LSMALL_D && aEm[i] > LSMALL_D) x = lacc<EXACT>(x, aEm[i] + (double)r.aInt[i][j]);
+                  nEm[j] = x + (double)b0[j];
+               }
+            }
+            double x = LZERO_D;
+#pragma unroll
+            for (int i = 0; i < E; i++)
+               if (i < ne && r.aExit[i] > (float)LSMALL_D && nEm[i] > LSMALL_D) x = lacc<EXACT>(x, nEm[i] + (double)r.aExit[i]);
+            nEx = x;
+         }
+      }
+      sq = nsq; eq = neq;
+      const bool inBeam = have && myq >= sq && myq <= eq;
+      if (lane == 0) { sqA[t] = (short)sq; eqA[t] = (short)eq; }
+      aEx = nEx;
+      mpS = LZERO_D; exv = LZERO_D;
+      if (inBeam) {
+         double m = a1 + bEn;
+#pragma unroll
+         for (int j = 0; j < E; j++) if (j < ne) m = fmax(m, nEm[j] + bEm[j]);
+         mpS = m; exv = nEx + bX;
+         double *oc = occU + (size_t)t * P + r.po;
+#pragma unroll
+         for (int j = 0; j < E; j++) if (j < ne) oc[j] = nEm[j];
+         aentU[(size_t)t * Q + myq] = a1;
+         if (tmin > t) tmin = t;
+         tmax = t;
+      }
+#pragma unroll
+      for (int j = 0; j < E; j++) aEm[j] = nEm[j];
+      // ---- slide: a lane whose model fell below the beam takes the model 32 further on
+      if (have && myq < sq) {
+         if (tmax >= 0) { gTmin[myq] = tmin; gTmax[myq] = tmax; }
+         myq += 32; have = myq < Q;
+         tmin = 0x7fffffff; tmax = -1;
+         aEx = LZERO_D; mpS = LZERO_D; exv = LZERO_D;
+#pragma unroll
+         for (int j = 0; j < E; j++) aEm[j] = LZERO_D;
+         if (have) load_model<E>(r, M, W, u, myq);
+         else { r.N = 2; r.so = 0; r.po = 0; r.dms = 1; r.aTee = (float)LZERO_D; }
+      }
+   }
+   if (have && tmax >= 0) { gTmin[myq] = tmin; gTmax[myq] = tmax; }
+   for (int q = lane; q < Q; q += 32) atomicAdd(&W.acc[M.L.numEgs + W.mHmm[u.modOff + q]], 1.0);   // HFB.c:1768-1772
+   if (lane == 0) {
+      atomicAdd(&W.acc[M.L.totalT], (double)T);                             // HERest.c:779-780
+      atomicAdd(&W.acc[M.L.totalPr], pr);
+      atomicAdd(&W.acc[M.L.numOk], 1.0);
+   }
+}

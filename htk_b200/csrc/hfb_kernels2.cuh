@@ -20,12 +20,13 @@ __host__ __device__ inline size_t alpha_warp_smem_bytes(int S, int Q)
 
 
 template <bool EXACT>
-__global__ void __launch_bounds__(32) alpha_warp_kernel(DevModel M, Wave W)
+__global__ void __launch_bounds__(32) alpha_warp_kernel(DevModel M, Wave W, int onlyRedo)
 {
    extern __shared__ __align__(16) unsigned char smraw[];
    const UttDesc u = W.utt[blockIdx.x];
    UttOut *out = &W.out[blockIdx.x];
    if (out->status != 0) return;
+   if (onlyRedo && !out->redo) return;
    const int lane = threadIdx.x;
    const int T = u.T, Q = u.Q, S = u.S, J = u.J, P = u.P;
    double *cur = (double *)smraw, *prev = cur + S, *mpSelf = prev + S, *exq = mpSelf + Q;
@@ -33,21 +34,17 @@ __global__ void __launch_bounds__(32) alpha_warp_kernel(DevModel M, Wave W)
    const int *mN = W.mN + u.modOff, *mSoff = W.mSoff + u.modOff, *mTr = W.mTrans + u.modOff;
    const int *mPoff = W.mPoff + u.modOff, *mDms = W.mDms + u.modOff;
    const float *A0 = M.transLogA;
-   const int *posSlot = W.posSlot + u.posOff, *posState = W.posState + u.posOff;
+   const int *posSlot = W.posSlot + u.posOff;
    const float *bU = W.b + u.bOff;
    const double *betaU = W.beta + u.betaOff;
-   double *occU = W.occ + u.occOff;
+   double *occU = W.occ + u.occOff, *aentU = W.aent + u.aentOff;
    const short *qLo = W.qLo + u.frameBase, *qHi = W.qHi + u.frameBase;
    short *sqA = W.sq + u.frameBase, *eqA = W.eq + u.frameBase;
    const double pr = out->pr, minF = W.minFrwdP;
-   const int uf = W.uFlags;
-   const bool doMix = (uf & (HFB_UPMEANS | HFB_UPVARS | HFB_UPMIXES)) != 0;
-   const bool doTr = (uf & HFB_UPTRANS) != 0;
 
    for (int q = lane; q < Q; q += 32) {
       mpSelf[q] = LZERO_D; exq[q] = LZERO_D;
       sTmin[q] = 0x7fffffff; sTmax[q] = -1;
-      atomicAdd(&W.acc[M.L.numEgs + W.mHmm[u.modOff + q]], 1.0);      // HFB.c:1768-1772
    }
    for (int i = lane; i < 2 * S; i += 32) cur[i] = LZERO_D;
    __syncwarp();
@@ -166,88 +163,28 @@ __global__ void __launch_bounds__(32) alpha_warp_kernel(DevModel M, Wave W)
          }
       }
 
-      // ---- accumulation inside the alpha beam (StepForward, HFB.c:1790-1806)
-      const float *bt = bU + (size_t)t * J;
-      const bool haveT1 = (t + 1 < T);
-      const int loT1 = haveT1 ? qLo[t + 1] : 1, hiT1 = haveT1 ? qHi[t + 1] : 0;
+      // ---- what the next frame's beam needs (MaxModelProb, HFB.c:655-682) + alpha for stats3_kernel
       const int aLo = (t == 0) ? 0 : sqP2, aHi = (t == 0) ? eq : min(Q - 1, max(eqP2, eq) + 3);
       for (int q = aLo + lane; q <= aHi; q += 32) {
          if (q < sq || q > eq) { mpSelf[q] = LZERO_D; exq[q] = LZERO_D; continue; }
          const int N = mN[q], so = mSoff[q];
-         const float *A = A0 + mTr[q];
-         const int *ps = posSlot + mPoff[q];
          const double *bq = betaU + (size_t)t * S + so;
-         const bool hasB1 = haveT1 && q >= loT1 && q <= hiT1;
-         const bool hasBq1 = (q < Q - 1) && (q + 1 >= loT) && (q + 1 <= hiT);
-         const double bq1 = hasBq1 ? betaU[(size_t)t * S + mSoff[q + 1]] : LZERO_D;
-         const double a1N = A[N - 1];
-         const int gq = u.modOff + q;
          if (sTmin[q] > t) sTmin[q] = t;
          sTmax[q] = t;
          double mps = LZERO_D;
          for (int i = 0; i < N - 1; i++) mps = fmax(mps, cur[so + i] + bq[i]);
          mpSelf[q] = mps;
          exq[q] = cur[so + N - 1] + bq[N - 1];
-         if (doTr) {
-            double *tacc = W.acc + W.mTrAcc[gq], *oacc = W.acc + W.mTrOcc[gq];
-            for (int i = 0; i < N - 1; i++) {                               // SetOcct -> ta->occ
-               double x = cur[so + i] + bq[i];
-               if (i == 0 && hasBq1 && a1N > LSMALL_D) x = ladd<EXACT>(x, cur[so] + bq1 + a1N);
-               x -= pr;
-               if (x > -87.0) atomicAdd(&oacc[i], (double)expf((float)x));
-            }
-            for (int j = 1; j < N - 1; j++) {                               // UpTranParms
-               double x = cur[so] + (double)A[j] + (double)bt[ps[j - 1]] + bq[j] - pr;
-               if (x > -87.0) atomicAdd(&tacc[j], (double)expf((float)x));
-            }
-            if (hasB1) {
-               const double *bq1t = betaU + (size_t)(t + 1) * S + so;
-               const float *bt1 = bt + J;
-               for (int i = 1; i < N - 1; i++)
-                  for (int j = 1; j < N - 1; j++) {
-                     const float aij = A[i * N + j];
-                     if (!(aij > (float)LSMALL_D)) continue;
-                     double x = cur[so + i] + (double)aij + (double)bt1[ps[j - 1]] + bq1t[j] - pr;
-                     if (x > -87.0) atomicAdd(&tacc[i * N + j], (double)expf((float)x));
-                  }
-            }
-            for (int i = 1; i < N - 1; i++) {
-               double x = cur[so + i] + (double)A[i * N + N - 1] + bq[N - 1] - pr;
-               if (x > -87.0) atomicAdd(&tacc[i * N + N - 1], (double)expf((float)x));
-            }
-            if (a1N > LSMALL_D && hasBq1) {
-               double x = cur[so] + a1N + bq1 - pr;
-               if (x > -87.0) atomicAdd(&tacc[N - 1], (double)expf((float)x));
-            }
-         }
-         if (doMix) {
-            const int *pst = posState + mPoff[q];
-            double *oc = occU + (size_t)t * P + mPoff[q];
-            for (int j = 1; j < N - 1; j++) {
-               const double lg = cur[so + j] + bq[j] - pr;                  // log state occupancy
-               double x;
-               if (lg < -(minF + 0.25)) x = OCC_SKIP;                       // no component can pass :1606
-               else {
-                  int s = pst[j - 1];
-                  int Mn = M.stateMixOff[s + 1] - M.stateMixOff[s];
-                  if (Mn == 1) x = lg;                                      // :1575-1576
-                  else {                                                    // initx, :1480-1489
-                     x = (double)A[j] + cur[so];
-                     if (t > 0)
-                        for (int i = 1; i < N - 1; i++) {
-                           double a = A[i * N + j];
-                           if (a > LSMALL_D) x = ladd<EXACT>(x, prev[so + i] + a);
-                        }
-                     x += bq[j] - pr;
-                  }
-               }
-               oc[j - 1] = x;
-            }
-         }
+         double *oc = occU + (size_t)t * P + mPoff[q];
+         for (int j = 1; j < N - 1; j++) oc[j - 1] = cur[so + j];
+         aentU[(size_t)t * Q + q] = cur[so];
       }
       __syncwarp();
    }
-   for (int q = lane; q < Q; q += 32) { W.mTmin[u.modOff + q] = sTmin[q]; W.mTmax[u.modOff + q] = sTmax[q]; }
+   for (int q = lane; q < Q; q += 32) {
+      W.mTmin[u.modOff + q] = sTmin[q]; W.mTmax[u.modOff + q] = sTmax[q];
+      atomicAdd(&W.acc[M.L.numEgs + W.mHmm[u.modOff + q]], 1.0);            // HFB.c:1768-1772
+   }
    if (lane == 0) {
       atomicAdd(&W.acc[M.L.totalT], (double)T);                             // HERest.c:779-780
       atomicAdd(&W.acc[M.L.totalPr], pr);
@@ -256,35 +193,50 @@ __global__ void __launch_bounds__(32) alpha_warp_kernel(DevModel M, Wave W)
 }
 
 // ------------------------------------------------------------------------------------------
-// K4 v2
+// K4: every accumulation of StepForward, in parallel over emitting state positions.
+//
+// One warp per position (q, j).  For the frames where q is inside the alpha beam (lanes <-> frames
+// of a 32-frame chunk) it forms, from the stored alpha / beta / b:
+//   * SetOcct + UpTranParms (HFB.c:399-418, :1371-1423): occupancy of state j, transitions
+//     entry->j, j->j2 (all j2), j->exit; the warp handling the FIRST emitting state also does the
+//     model-level terms (entry occupancy incl. the tee path, entry->exit); partial sums are reduced
+//     over the warp so that one atomic per chunk reaches the (hot) transition accumulators;
+//   * UpMixParms (HFB.c:1426-1744): x = alpha_j + beta_j - pr for single-mixture states, else
+//     initx + log weight + component log-density with initx = alpha_j - b_j + beta_j - pr (equal to
+//     HFB.c:1480-1489 because alpha_j(t) = [that sum] + b_j(o_t)), the minimum-occupancy rule
+//     -x < minFrwdP, and the centred mean / variance / weight sums.
+// Component log-densities use the reference's operation order (IDOutP, HModel.c:5425-5430).
 // ------------------------------------------------------------------------------------------
 #define ST_WARPS 4
-__host__ __device__ inline int stats2_ostride(int D) { return D | 1; }
-__host__ __device__ inline size_t stats2_smem_bytes(int D)
+__host__ __device__ inline int stats_ostride(int D) { return D | 1; }
+__host__ __device__ inline size_t stats_smem_bytes(int D)
 {
-   return ST_WARPS * (sizeof(float) * ((size_t)32 * stats2_ostride(D) + 32 * 33) + sizeof(double) * 32 + sizeof(int) * 32);
+   return ST_WARPS * (sizeof(float) * ((size_t)32 * stats_ostride(D) + 32 * 33) + sizeof(double) * 32 + sizeof(int) * 32);
+}
+
+__device__ __forceinline__ float warp_sum_nz(float v)
+{
+   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+   return v;
 }
 
 __global__ void __launch_bounds__(32 * ST_WARPS)
-stats2_kernel(DevModel M, Wave W)
+stats3_kernel(DevModel M, Wave W)
 {
    extern __shared__ __align__(16) unsigned char smraw[];
    const int wInB = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const int wg = blockIdx.x * ST_WARPS + wInB;
    if (wg >= W.totalPos) return;
-   struct { int utt, q, j; } p;
-   p.utt = upper_index(W.posPre, W.numUtt, wg);
-   if (W.out[p.utt].status != 0) return;
-   const UttDesc u = W.utt[p.utt];
-   {
-      const int lp = wg - W.posPre[p.utt];
-      p.q = upper_index(W.mPoff + u.modOff, u.Q, lp);
-      p.j = lp - W.mPoff[u.modOff + p.q];
-   }
-   const int gq = u.modOff + p.q;
+   const int ui = upper_index(W.posPre, W.numUtt, wg);
+   if (W.out[ui].status != 0) return;
+   const UttDesc u = W.utt[ui];
+   const int lp = wg - W.posPre[ui];
+   const int q = upper_index(W.mPoff + u.modOff, u.Q, lp);
+   const int gq = u.modOff + q;
+   const int j = lp - W.mPoff[gq];                     // emitting index 0..N-3
    const int tmin = W.mTmin[gq], tmax = W.mTmax[gq];
    if (tmin > tmax) return;
-   const int D = M.D, Dp = M.Dp, P = u.P, ostr = stats2_ostride(D);
+   const int D = M.D, Dp = M.Dp, P = u.P, S = u.S, Q = u.Q, J = u.J, T = u.T, ostr = stats_ostride(D);
    const size_t perWarp = sizeof(float) * ((size_t)32 * ostr + 32 * 33) + sizeof(double) * 32 + sizeof(int) * 32;
    unsigned char *mine = smraw + perWarp * wInB;
    double *x0s = (double *)mine;                       // [32] initx / log occupancy per chunk frame
@@ -292,24 +244,96 @@ stats2_kernel(DevModel M, Wave W)
    float *lrs = os + 32 * ostr;                        // [32 mixtures][33] occupancies Lr
    int *ts = (int *)(lrs + 32 * 33);                   // [32] frame numbers
 
-   const int pp = W.mPoff[gq] + p.j;
-   const int s = W.posState[u.posOff + pp];
+   const int N = W.mN[gq], so = W.mSoff[gq];
+   const int s = W.posState[u.posOff + lp];
    const int mo = M.stateMixOff[s], Mn = M.stateMixOff[s + 1] - mo;
-   const double *occ = W.occ + u.occOff + pp;
+   const float *A = M.transLogA + W.mTrans[gq];
+   const int *ps = W.posSlot + u.posOff + W.mPoff[gq];
+   const double *alphaJ = W.occ + u.occOff + lp, *aent = W.aent + u.aentOff + q;
+   const double *betaU = W.beta + u.betaOff;
+   const float *bU = W.b + u.bOff;
    const short *sqA = W.sq + u.frameBase, *eqA = W.eq + u.frameBase;
+   const short *qLo = W.qLo + u.frameBase, *qHi = W.qHi + u.frameBase;
    const float *feat = W.feat + (size_t)u.featOff * D;
-   const double minF = W.minFrwdP;
+   const double pr = W.out[ui].pr, minF = W.minFrwdP;
    const int uf = W.uFlags;
    const bool upM = (uf & HFB_UPMEANS) != 0, upV = (uf & HFB_UPVARS) != 0, upW = (uf & HFB_UPMIXES) != 0;
+   const bool doMix = upM || upV || upW, doTr = (uf & HFB_UPTRANS) != 0;
+   const float aEntJ = A[1 + j], aExitJ = A[(1 + j) * N + N - 1], aTee = A[N - 1];
+   const int sq1 = (q < Q - 1) ? W.mSoff[gq + 1] : 0;  // column offset of the next model
+   double *tacc = W.acc + W.mTrAcc[gq], *oacc = W.acc + W.mTrOcc[gq];
    const int k0 = lane, k1 = lane + 32;                // D <= 64 (checked at create)
    double wsum = 0.0;
 
    for (int t0 = tmin; t0 <= tmax; t0 += 32) {
-      // ---- frames of this chunk that are inside the alpha beam and not pre-pruned
       const int t = t0 + lane;
+      const bool inb = (t <= tmax) && q >= sqA[t] && q <= eqA[t];
       double x0 = OCC_SKIP;
-      bool valid = false;
-      if (t <= tmax && p.q >= sqA[t] && p.q <= eqA[t]) { x0 = occ[(size_t)t * P]; valid = x0 > -1.0e29; }
+      if (inb) {
+         const double aj = alphaJ[(size_t)t * P];
+         const double *bq = betaU + (size_t)t * S + so;
+         const float bjt = bU[(size_t)t * J + ps[j]];
+         const double lg = aj + bq[1 + j] - pr;                              // log occupancy of state j
+         if (!(lg < -(minF + 0.25))) x0 = (Mn == 1) ? lg : lg - (double)bjt;  // :1575-1576 / initx :1480-1489
+      }
+      if (doTr) {
+         // ---- SetOcct / UpTranParms for this state (and, for j == 0, the model-level terms)
+         float oJ = 0.f, tEnt = 0.f, tExit = 0.f, oEnt = 0.f, tTee = 0.f;
+         const bool hasB1 = inb && (t + 1 < T) && q >= qLo[t + 1] && q <= qHi[t + 1];   // bqt1 != NULL
+         if (inb) {
+            const double aj = alphaJ[(size_t)t * P], ae = aent[(size_t)t * Q];
+            const double *bq = betaU + (size_t)t * S + so;
+            const float bjt = bU[(size_t)t * J + ps[j]];
+            double x = aj + bq[1 + j] - pr;
+            if (x > -87.0) oJ = expf((float)x);                              // occt[j] -> ta->occ
+            x = ae + (double)aEntJ + (double)bjt + bq[1 + j] - pr;           // entry -> j
+            if (x > -87.0) tEnt = expf((float)x);
+            x = aj + (double)aExitJ + bq[N - 1] - pr;                        // j -> exit
+            if (x > -87.0) tExit = expf((float)x);
+            if (j == 0) {
+               const bool hasBq1 = (q < Q - 1) && (q + 1 >= qLo[t]) && (q + 1 <= qHi[t]);   // bq1t != NULL
+               const double bnx = hasBq1 ? betaU[(size_t)t * S + sq1] : LZERO_D;
+               x = ae + bq[0];
+               if (hasBq1 && aTee > (float)LSMALL_D) x = ladd<false>(x, ae + bnx + (double)aTee);
+               x -= pr;
+               if (x > -87.0) oEnt = expf((float)x);                         // occt[1]
+               if (hasBq1 && aTee > (float)LSMALL_D) {
+                  x = ae + (double)aTee + bnx - pr;
+                  if (x > -87.0) tTee = expf((float)x);
+               }
+            }
+         }
+         if (__ballot_sync(0xffffffffu, inb)) {
+            oJ = warp_sum_nz(oJ); tEnt = warp_sum_nz(tEnt); tExit = warp_sum_nz(tExit);
+            if (lane == 0) {
+               if (oJ != 0.f) atomicAdd(&oacc[1 + j], (double)oJ);
+               if (tEnt != 0.f) atomicAdd(&tacc[1 + j], (double)tEnt);
+               if (tExit != 0.f) atomicAdd(&tacc[(1 + j) * N + N - 1], (double)tExit);
+            }
+            for (int j2 = 0; j2 < N - 2; j2++) {                             // j -> j2 (internal)
+               const float a = A[(1 + j) * N + 1 + j2];
+               if (!(a > (float)LSMALL_D)) continue;
+               float v = 0.f;
+               if (hasB1) {
+                  const double x = alphaJ[(size_t)t * P] + (double)a + (double)bU[(size_t)(t + 1) * J + ps[j2]] +
+                                   betaU[(size_t)(t + 1) * S + so + 1 + j2] - pr;
+                  if (x > -87.0) v = expf((float)x);
+               }
+               v = warp_sum_nz(v);
+               if (lane == 0 && v != 0.f) atomicAdd(&tacc[(1 + j) * N + 1 + j2], (double)v);
+            }
+            if (j == 0) {
+               oEnt = warp_sum_nz(oEnt); tTee = warp_sum_nz(tTee);
+               if (lane == 0) {
+                  if (oEnt != 0.f) atomicAdd(&oacc[0], (double)oEnt);
+                  if (tTee != 0.f) atomicAdd(&tacc[N - 1], (double)tTee);
+               }
+            }
+         }
+      }
+      if (!doMix) continue;
+      // ---- frames of this chunk that can contribute to the mixture statistics
+      const bool valid = inb && x0 > -1.0e29;
       const unsigned mask = __ballot_sync(0xffffffffu, valid);
       const int nT = __popc(mask);
       if (nT == 0) continue;
@@ -323,7 +347,7 @@ stats2_kernel(DevModel M, Wave W)
       __syncwarp();
       for (int mb = 0; mb < Mn; mb += 32) {
          const int Mc = min(32, Mn - mb);
-         // ---- phase 1: lanes <-> (mixture, frame) pairs; IDOutP in the reference's operation order
+         // ---- phase 1: lanes <-> (mixture, frame) pairs
          unsigned act = 0;                             // mixtures with any occupancy in this chunk
          for (int pi = lane; pi < ((Mc * nT + 31) & ~31); pi += 32) {
             float Lr = 0.f;
@@ -349,7 +373,6 @@ stats2_kernel(DevModel M, Wave W)
                lrs[mi * 33 + ti] = Lr;
             }
             const unsigned nz = __ballot_sync(0xffffffffu, Lr > 0.f);
-            // fold the ballot into per-mixture bits (pairs are mixture-major)
             for (unsigned b = nz; b; b &= b - 1) {
                int l = __ffs(b) - 1;
                act |= 1u << (((pi - lane) + l) / nT);

@@ -74,14 +74,14 @@ struct WaveTables {
    std::vector<int> posPre, tilePre;
    std::vector<int2> tcItems;        // (utterance, first frame) blocks of TC_BM frames for the tcgen05 kernel
    std::vector<int> uttIndex;        // index in the caller's batch
-   long long bFloats = 0, betaDoubles = 0, occDoubles = 0;
+   long long bFloats = 0, betaDoubles = 0, occDoubles = 0, aentDoubles = 0;
    long long totalQ = 0, totalP = 0, tiles = 0;
    int maxQ = 0, maxS = 0, maxN = 0;
    int lab0 = 0;                     // first label of the wave in the caller's label array
    void clear()
    {
       utt.clear(); out.clear(); posPre.clear(); tilePre.clear(); tcItems.clear(); uttIndex.clear();
-      bFloats = betaDoubles = occDoubles = 0; totalQ = totalP = tiles = 0; maxQ = maxS = maxN = 0; lab0 = 0;
+      bFloats = betaDoubles = occDoubles = aentDoubles = 0; totalQ = totalP = tiles = 0; maxQ = maxS = maxN = 0; lab0 = 0;
    }
 };
 
@@ -113,7 +113,7 @@ struct hfbgpu_ctx {
       cudaEvent_t ev[6] = {};
       DevBuf<float> dFeat;              // only for host-feature calls
       DevBuf<float> dB;
-      DevBuf<double> dBeta, dOcc;
+      DevBuf<double> dBeta, dOcc, dAent;
       DevBuf<short> dBeams;             // 4 * frames
       DevBuf<unsigned char> dTables, dScratch;
       GmmTcWork tcw;
@@ -357,7 +357,7 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
    cudaFuncSetAttribute(beta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(alpha_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(alpha_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
-   cudaFuncSetAttribute(stats2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
+   cudaFuncSetAttribute(stats3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    CK(cudaStreamSynchronize(c->stream));
    *out = c;
    return HFB_OK;
@@ -374,7 +374,7 @@ extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
    c->dAcc.release();
    for (auto &sl : c->slot) {
       if (sl.stream) cudaStreamSynchronize(sl.stream);
-      sl.dFeat.release(); sl.dB.release(); sl.dBeta.release(); sl.dOcc.release(); sl.dBeams.release();
+      sl.dFeat.release(); sl.dB.release(); sl.dBeta.release(); sl.dOcc.release(); sl.dAent.release(); sl.dBeams.release();
       sl.dTables.release(); sl.dScratch.release(); sl.tcw.release();
       if (sl.hTables) cudaFreeHost(sl.hTables);
       if (sl.hOut) cudaFreeHost(sl.hOut);
@@ -468,13 +468,14 @@ size_t add_utterance(const HostModel &h, WaveTables &w, int uidx, int T, const i
    u.T = T; u.Q = Q; u.S = S; u.P = Pp; u.J = Pp;
    u.labOff = labOff; u.modOff = (int)w.totalQ; u.slotOff = (int)w.totalP; u.posOff = (int)w.totalP;
    u.featOff = featOff; u.frameBase = featOff;
-   u.bOff = w.bFloats; u.betaOff = w.betaDoubles; u.occOff = w.occDoubles;
+   u.bOff = w.bFloats; u.betaOff = w.betaDoubles; u.occOff = w.occDoubles; u.aentOff = w.aentDoubles;
    w.posPre.push_back((int)w.totalP);
    w.tilePre.push_back((int)w.tiles);
    size_t bytes = 0;
    if (!bad) {
       w.bFloats += (long long)T * Pp; w.betaDoubles += (long long)T * S; w.occDoubles += (long long)T * Pp;
-      bytes = (size_t)T * ((size_t)Pp * 12 + (size_t)S * 8);
+      w.aentDoubles += (long long)T * Q;
+      bytes = (size_t)T * ((size_t)Pp * 12 + (size_t)S * 8 + (size_t)Q * 8);
       w.totalQ += Q; w.totalP += Pp;
       w.tiles += (long long)((T + GT_FR - 1) / GT_FR) * ((Pp + GT_SL - 1) / GT_SL);
       for (int t0 = 0; t0 < T; t0 += TC_BM) w.tcItems.push_back(make_int2(uLocal, t0));
@@ -556,7 +557,8 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
    CK(cudaMemcpyAsync(S.dTables.p, S.hTables, blob.size(), cudaMemcpyHostToDevice, st));
    c->stats.h2dBytes += (int64_t)blob.size();
    if ((rc = S.dB.reserve((size_t)w.bFloats + 1)) || (rc = S.dBeta.reserve((size_t)w.betaDoubles + 1)) ||
-       (rc = S.dOcc.reserve((size_t)w.occDoubles + 1)) || (rc = S.dBeams.reserve((size_t)waveFrames * 4 + 4)))
+       (rc = S.dOcc.reserve((size_t)w.occDoubles + 1)) || (rc = S.dAent.reserve((size_t)w.aentDoubles + 1)) ||
+       (rc = S.dBeams.reserve((size_t)waveFrames * 4 + 4)))
       return rc;
 
    unsigned char *base = S.dTables.p, *sc = S.dScratch.p;
@@ -572,7 +574,7 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
    W.mTmin = (int *)(sc + sl.mTmin); W.mTmax = (int *)(sc + sl.mTmax);
    W.slotState = (int *)(sc + sl.slotState); W.posSlot = (int *)(sc + sl.posSlot); W.posState = (int *)(sc + sl.posState);
    W.feat = dFeat;
-   W.b = S.dB.p; W.beta = S.dBeta.p; W.occ = S.dOcc.p;
+   W.b = S.dB.p; W.beta = S.dBeta.p; W.occ = S.dOcc.p; W.aent = S.dAent.p;
    W.qLo = S.dBeams.p; W.qHi = W.qLo + waveFrames; W.sq = W.qHi + waveFrames; W.eq = W.sq + waveFrames;
    W.acc = c->dAcc.p;
    W.pruneInit = c->opt.pruneInit; W.pruneInc = c->opt.pruneInc; W.pruneLim = c->opt.pruneLim;
@@ -605,7 +607,8 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
          g_lastError = "utterance too long for the shared-memory window"; return HFB_EUNSUPPORTED;
       }
       const bool exact = getenv("HFBGPU_EXACT_LADD") != nullptr;
-      static const bool noFast = getenv("HFBGPU_NO_FAST") != nullptr;
+      const bool noFast = getenv("HFBGPU_NO_FAST") != nullptr;        // test hooks: generic kernels only /
+      const int forceRedo = getenv("HFBGPU_FORCE_REDO") ? 1 : 0;      // fast alpha gives up immediately
       const bool fastOk = !noFast && w.maxQ <= 256 && w.maxN <= 8;
       if (fastOk) {
          const size_t fsm = beta_fast_smem_bytes(w.maxQ);
@@ -619,13 +622,23 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
       } else if (exact) beta_kernel<true><<<nU, nt, rsm, st>>>(c->dm, W);
       else beta_kernel<false><<<nU, nt, rsm, st>>>(c->dm, W);
       if (tm) cudaEventRecord(S.ev[2], st);
-      if (exact) alpha_warp_kernel<true><<<nU, 32, asm_, st>>>(c->dm, W);
-      else alpha_warp_kernel<false><<<nU, 32, asm_, st>>>(c->dm, W);
+      if (fastOk) {                                    // register/shuffle kernel; generic one redoes overflows
+         if (w.maxN <= 5) {
+            if (exact) alpha_fast_kernel<true, 3><<<nU, 32, 0, st>>>(c->dm, W, forceRedo);
+            else alpha_fast_kernel<false, 3><<<nU, 32, 0, st>>>(c->dm, W, forceRedo);
+         } else {
+            if (exact) alpha_fast_kernel<true, 6><<<nU, 32, 0, st>>>(c->dm, W, forceRedo);
+            else alpha_fast_kernel<false, 6><<<nU, 32, 0, st>>>(c->dm, W, forceRedo);
+         }
+         c->stats.launches++; c->stats.launchesAlpha++;
+      }
+      if (exact) alpha_warp_kernel<true><<<nU, 32, asm_, st>>>(c->dm, W, fastOk ? 1 : 0);
+      else alpha_warp_kernel<false><<<nU, 32, asm_, st>>>(c->dm, W, fastOk ? 1 : 0);
       if (tm) cudaEventRecord(S.ev[3], st);
       c->stats.launches += 2; c->stats.launchesBeta++; c->stats.launchesAlpha++;
       // ---- K4
-      if (w.totalP > 0 && (c->opt.uFlags & (HFB_UPMEANS | HFB_UPVARS | HFB_UPMIXES))) {
-         stats2_kernel<<<(unsigned)((w.totalP + ST_WARPS - 1) / ST_WARPS), 32 * ST_WARPS, stats2_smem_bytes(c->dm.D), st>>>(c->dm, W);
+      if (w.totalP > 0 && c->opt.uFlags != 0) {
+         stats3_kernel<<<(unsigned)((w.totalP + ST_WARPS - 1) / ST_WARPS), 32 * ST_WARPS, stats_smem_bytes(c->dm.D), st>>>(c->dm, W);
          c->stats.launches++; c->stats.launchesStats++;
       }
       if (tm) cudaEventRecord(S.ev[4], st);
@@ -726,7 +739,7 @@ static int accumulate_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *re
          for (int q = 0; q < Q; q++) {
             int p = b->lab[b->labOff[u1] + q];
             int N = (p >= 0 && p < h.P) ? h.hmmN[p] : 2;
-            perFrame += (size_t)N * 8 + (size_t)(N - 2) * 12;
+            perFrame += (size_t)N * 8 + (size_t)(N - 2) * 12 + 8;
          }
          size_t need = (size_t)T * perFrame;
          if (u1 > u0 && (bytes + need > wsPerSlot || u1 - u0 >= 16384 || f0 - waveFrame0 >= targetFrames)) break;

@@ -205,3 +205,24 @@ def test_exact_ladd_env(monkeypatch):
         assert abs(x.pr - y.pr) < 1e-4
     e = acc_errors(a1, a2, fm)
     assert max(e.values()) < 2e-5, e
+
+
+@pytest.mark.parametrize("hook", ["HFBGPU_NO_FAST", "HFBGPU_FORCE_REDO"])
+@pytest.mark.parametrize("name", ["htkdemo_t20_15_200", "synth_tee_m2", "synth_tied_m4", "synth_long_m3"])
+def test_generic_kernels_and_redo_path(name, hook, monkeypatch):
+    """The generic (any N, any Q) recursion kernels and the fast->generic alpha fallback give the
+    same beams and accumulators as the register-resident fast path."""
+    z, fm, b, kw = load_golden(name)
+    fb = _fb(fm, **kw); r1, b1 = fb.FBFile(b, want_beams=True); a1 = fb.GetAccs(); fb.close()
+    monkeypatch.setenv(hook, "1")
+    fb = _fb(fm, **kw); r2, b2 = fb.FBFile(b, want_beams=True); a2 = fb.GetAccs(); fb.close()
+    for x, y in zip(r1, r2):
+        assert x.status == y.status and x.pruneThresh == y.pruneThresh
+        if x.status == 0:
+            assert abs(x.pr - y.pr) <= 1e-9 * abs(x.pr)
+    for k in ("qLo", "qHi", "sq", "eq"):
+        assert np.array_equal(getattr(b1, k), getattr(b2, k)), k
+    e = acc_errors(a2, a1, fm)
+    assert max(e.values()) < 1e-6, e
+    e = acc_errors(a2, z["ref_acc"], fm)
+    assert max(e.values()) < RTOL, e
