@@ -205,19 +205,27 @@ __global__ void __launch_bounds__(256) beta_fast_kernel(DevModel M, Wave W)
             bg[r.N - 1] = ex;
             cur[q] = x;
          }
-         double gMax = warp_max(lMax);
-         if (lane == 0) wred[wid] = gMax;
-         __syncthreads();
-         gMax = LZERO_D;
-         for (int w = 0; w < nw; w++) gMax = fmax(gMax, wred[w]);
-         // ---- pruning (:1254-1272)
-         const bool keep = active && !(gMax - lMax > thresh);
-         int myHi = keep ? q : -1, myLo = keep ? q : 0x7fffffff;
-         myHi = warp_maxi(myHi); myLo = warp_mini(myLo);
-         if (lane == 0) { whi[wid] = myHi; wlo[wid] = myLo; }
-         __syncthreads();
-         int nhi = -1, nlo = 0x7fffffff;
-         for (int w = 0; w < nw; w++) { nhi = max(nhi, whi[w]); nlo = min(nlo, wlo[w]); }
+         int nhi, nlo;
+         if (thresh >= 0.5 * HFB_NOPRUNE) {
+            // pruning off: gMax - maxP[q] > thresh is never true (finite log values), the beam is
+            // the candidate range; only the entry values need to become visible to the neighbours
+            nhi = startq; nlo = endq;
+            __syncthreads();
+         } else {
+            double gMax = warp_max(lMax);
+            if (lane == 0) wred[wid] = gMax;
+            __syncthreads();
+            gMax = LZERO_D;
+            for (int w = 0; w < nw; w++) gMax = fmax(gMax, wred[w]);
+            // ---- pruning (:1254-1272)
+            const bool keep = active && !(gMax - lMax > thresh);
+            int myHi = __reduce_max_sync(0xffffffffu, keep ? q : -1);
+            int myLo = __reduce_min_sync(0xffffffffu, keep ? q : 0x7fffffff);
+            if (lane == 0) { whi[wid] = myHi; wlo[wid] = myLo; }
+            __syncthreads();
+            nhi = -1; nlo = 0x7fffffff;
+            for (int w = 0; w < nw; w++) { nhi = max(nhi, whi[w]); nlo = min(nlo, wlo[w]); }
+         }
          if (nhi < 0) { fail = true; status = HFB_UTT_EBETA; break; }
          if (nhi > tapHi) nhi = tapHi;
          if (nlo > nhi) { fail = true; break; }
@@ -293,6 +301,13 @@ __global__ void __launch_bounds__(32) alpha_fast_kernel(DevModel M, Wave W, int 
          bEn = bq[0]; bX = bq[r.N - 1];
 #pragma unroll
          for (int j = 0; j < E; j++) if (j < ne) { b0[j] = bt[r.slot[j]]; bEm[j] = bq[1 + j]; }
+      }
+      if (inWin && t + 2 < T) {                              // first touched two frames from now
+         const float *bt2 = bU + (size_t)(t + 2) * J;
+         const double *bq2 = betaU + (size_t)(t + 2) * S + r.so;
+         prefetch_l1(bq2); prefetch_l1(bq2 + r.N - 1);
+#pragma unroll
+         for (int j = 0; j < E; j++) if (j < ne) prefetch_l1(bt2 + r.slot[j]);
       }
       double a1 = LZERO_D, nEm[E], nEx = LZERO_D;
 #pragma unroll

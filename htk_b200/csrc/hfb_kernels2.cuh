@@ -339,10 +339,9 @@ stats3_kernel(DevModel M, Wave W)
       if (nT == 0) continue;
       if (valid) { int idx = __popc(mask & ((1u << lane) - 1)); ts[idx] = t; x0s[idx] = x0; }
       __syncwarp();
-      for (int ti = 0; ti < nT; ti++) {
-         const float *o = feat + (size_t)ts[ti] * D;
-         if (k0 < D) os[ti * ostr + k0] = o[k0];
-         if (k1 < D) os[ti * ostr + k1] = o[k1];
+      for (int e = lane; e < nT * D; e += 32) {               // all loads of the chunk in flight at once
+         const int ti = e / D, k = e - ti * D;
+         os[ti * ostr + k] = feat[(size_t)ts[ti] * D + k];
       }
       __syncwarp();
       for (int mb = 0; mb < Mn; mb += 32) {
@@ -361,7 +360,16 @@ stats3_kernel(DevModel M, Wave W)
                      const float *mu = M.mean + (size_t)g * Dp, *iv = M.ivar + (size_t)g * Dp;
                      const float *o = os + ti * ostr;
                      float sum = M.gconst[g];
-                     for (int k = 0; k < D; k++) {
+                     int k = 0;
+                     for (; k + 4 <= D; k += 4) {                            // rows are 16-byte aligned (Dp % 4 == 0)
+                        const float4 m4 = *reinterpret_cast<const float4 *>(mu + k);
+                        const float4 v4 = *reinterpret_cast<const float4 *>(iv + k);
+                        float d = __fsub_rn(o[k], m4.x);     sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), v4.x));
+                        d = __fsub_rn(o[k + 1], m4.y);       sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), v4.y));
+                        d = __fsub_rn(o[k + 2], m4.z);       sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), v4.z));
+                        d = __fsub_rn(o[k + 3], m4.w);       sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), v4.w));
+                     }
+                     for (; k < D; k++) {
                         const float d = __fsub_rn(o[k], mu[k]);
                         sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), iv[k]));
                      }
