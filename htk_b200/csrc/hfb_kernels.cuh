@@ -237,7 +237,7 @@ __device__ __forceinline__ RecSmem rec_carve(unsigned char *raw, int S, int Q)
 // K2: beta pass with beam pruning and the whole-utterance retry loop
 // ------------------------------------------------------------------------------------------
 template <bool EXACT>
-__global__ void __launch_bounds__(256) beta_kernel(DevModel M, Wave W)
+__global__ void __launch_bounds__(1024) beta_kernel(DevModel M, Wave W)
 {
    extern __shared__ __align__(16) unsigned char smraw[];
    const UttDesc u = W.utt[blockIdx.x];

@@ -348,7 +348,7 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
 
    size_t freeB = 0, totalB = 0;
    CK(cudaMemGetInfo(&freeB, &totalB));
-   size_t ws = opt->workspaceBytes ? opt->workspaceBytes : ((size_t)16 << 30);
+   size_t ws = opt->workspaceBytes ? opt->workspaceBytes : ((size_t)48 << 30);
    if (ws > freeB * 6 / 10) ws = freeB * 6 / 10;
    c->workspaceBytes = ws;
 
@@ -602,6 +602,7 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
    // ---- K2 / K3
    if (w.maxQ > 0) {
       int nt = std::min(256, std::max(32, (w.maxQ + 31) & ~31));
+      const int ntGeneric = std::min(1024, std::max(32, (w.maxQ + 31) & ~31));   // long transcriptions: still 1 model/thread
       size_t rsm = rec_smem_bytes(w.maxS, w.maxQ), asm_ = alpha_warp_smem_bytes(w.maxS, w.maxQ);
       if (rsm > (size_t)c->maxSmemOptin || asm_ > (size_t)c->maxSmemOptin) {
          g_lastError = "utterance too long for the shared-memory window"; return HFB_EUNSUPPORTED;
@@ -609,8 +610,9 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
       const bool exact = getenv("HFBGPU_EXACT_LADD") != nullptr;
       const bool noFast = getenv("HFBGPU_NO_FAST") != nullptr;        // test hooks: generic kernels only /
       const int forceRedo = getenv("HFBGPU_FORCE_REDO") ? 1 : 0;      // fast alpha gives up immediately
-      const bool fastOk = !noFast && w.maxQ <= 256 && w.maxN <= 8;
-      if (fastOk) {
+      const bool fastOk = !noFast && w.maxN <= 8;                      // alpha: any Q (32-model sliding window)
+      const bool betaFastOk = fastOk && w.maxQ <= 256;                 // beta: one thread per model
+      if (betaFastOk) {
          const size_t fsm = beta_fast_smem_bytes(w.maxQ);
          if (w.maxN <= 5) {
             if (exact) beta_fast_kernel<true, 3><<<nU, nt, fsm, st>>>(c->dm, W);
@@ -619,8 +621,8 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
             if (exact) beta_fast_kernel<true, 6><<<nU, nt, fsm, st>>>(c->dm, W);
             else beta_fast_kernel<false, 6><<<nU, nt, fsm, st>>>(c->dm, W);
          }
-      } else if (exact) beta_kernel<true><<<nU, nt, rsm, st>>>(c->dm, W);
-      else beta_kernel<false><<<nU, nt, rsm, st>>>(c->dm, W);
+      } else if (exact) beta_kernel<true><<<nU, ntGeneric, rsm, st>>>(c->dm, W);
+      else beta_kernel<false><<<nU, ntGeneric, rsm, st>>>(c->dm, W);
       if (tm) cudaEventRecord(S.ev[2], st);
       if (fastOk) {                                    // register/shuffle kernel; generic one redoes overflows
          if (w.maxN <= 5) {

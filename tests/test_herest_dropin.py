@@ -99,3 +99,43 @@ def test_herest_gpu_matches_stock_herest(tmp_path, case):
     assert np.array_equal(ok, tB_ > -1e9)
     assert np.max(np.abs(np.exp(tA_[ok]) - np.exp(tB_[ok]))) < 1e-4
     assert np.max(np.abs(np.exp(wA) - np.exp(wB))) < 1e-4
+
+
+def test_python_dump_feeds_stock_mstep(tmp_path):
+    """accumulators from the Python/ctypes path written with htkio.write_acc_dump load
+    into the STOCK `HERest -p 0` and give the same re-estimated MMF as the stock E-step."""
+    if not os.path.exists(HEREST):
+        pytest.skip("reference binaries not built")
+    from htk_b200.estep import ForwardBackward
+    from htk_b200.flat import Batch
+    tmp = str(tmp_path)
+    hs = synth.make_tied_triphone_set(n_states=40, M=3, n_phys=24, n_logical=30, n_centre=5, seed=41, spread=0.2)
+    hs2, fm = _setup(tmp, hs, n_utts=8, T=280, Q=28, seed=9)
+    names = open(os.path.join(tmp, "list")).read().splitlines()
+    os.makedirs(os.path.join(tmp, "accA")); os.makedirs(os.path.join(tmp, "accB"))
+    _run([HEREST, "-u", "tmvw", "-p", "1", "-H", "mmf", "-I", "labs.mlf", "-S", "scp", "-M", "accA", "list"], tmp)
+    # same utterances through the library, in scan order so that the dump is loadable
+    order = htkio.scan_order(hs2.physical_names())
+    fmS = flatten(hs2, order=order)
+    scp = open(os.path.join(tmp, "scp")).read().split()
+    feats = [htkio.read_htk_features(f)[0] for f in scp]
+    labs = []
+    import re
+    mlf = open(os.path.join(tmp, "labs.mlf")).read()
+    for f in scp:
+        u = os.path.basename(f)[:-4]
+        block = re.search(r'"\*/%s\.lab"\n(.*?)\n\.\n' % u, mlf, re.S).group(1).split("\n")
+        labs.append(np.array([fmS.hmm_index[l] for l in block], dtype=np.int32))
+    fb = ForwardBackward(fmS)
+    res, _ = fb.FBFile(Batch(feats, labs, fmS.D))
+    assert all(r.status == 0 for r in res)
+    acc = fb.GetAccs(); fb.close()
+    htkio.write_acc_dump(os.path.join(tmp, "accB", "HER1.acc"), hs2, fmS, acc, order=order)
+    for d, o in (("accA", "outA"), ("accB", "outB")):
+        os.makedirs(os.path.join(tmp, o))
+        _run([HEREST, "-u", "tmvw", "-p", "0", "-H", "mmf", "-M", o, "list", os.path.join(d, "HER1.acc")], tmp)
+    mA, vA, tA_, wA = _mmf_params(os.path.join(tmp, "outA", "mmf"), names)
+    mB, vB, tB_, wB = _mmf_params(os.path.join(tmp, "outB", "mmf"), names)
+    assert np.max(np.abs(mA - mB) / np.sqrt(vA)) < 1e-4 + 2e-6
+    assert np.max(np.abs(vA - vB) / vA) < 1e-4 + 2e-6
+    assert np.max(np.abs(np.exp(wA) - np.exp(wB))) < 1e-4
