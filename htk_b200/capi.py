@@ -19,7 +19,7 @@ EXPORTS = [
     "hfbgpu_last_error", "hfbgpu_device_count", "hfbgpu_create", "hfbgpu_destroy", "hfbgpu_zero_accs",
     "hfbgpu_accumulate", "hfbgpu_accumulate_device", "hfbgpu_acc_device_ptr", "hfbgpu_acc_count",
     "hfbgpu_get_accs", "hfbgpu_set_accs", "hfbgpu_state_loglik", "hfbgpu_get_min_durs",
-    "hfbgpu_get_stats", "hfbgpu_reset_stats", "hfbgpu_set_timing", "hfbgpu_set_stream",
+    "hfbgpu_get_stats", "hfbgpu_reset_stats", "hfbgpu_set_timing", "hfbgpu_set_stream", "hfbgpu_submit", "hfbgpu_wait",
 ]
 
 _lib = None
@@ -56,6 +56,8 @@ def load():
     l.hfbgpu_zero_accs.argtypes = [vp]
     l.hfbgpu_accumulate.argtypes = [vp, C.POINTER(hfb_batch), C.POINTER(hfb_utt_result), C.POINTER(hfb_beams)]
     l.hfbgpu_accumulate_device.argtypes = l.hfbgpu_accumulate.argtypes
+    l.hfbgpu_submit.argtypes = l.hfbgpu_accumulate.argtypes + [C.c_int]
+    l.hfbgpu_wait.argtypes = [vp]
     l.hfbgpu_acc_device_ptr.argtypes = [vp]
     l.hfbgpu_acc_device_ptr.restype = vp
     l.hfbgpu_acc_count.argtypes = [vp]

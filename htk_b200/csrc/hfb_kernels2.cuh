@@ -220,6 +220,8 @@ __device__ __forceinline__ float warp_sum_nz(float v)
    return v;
 }
 
+__device__ unsigned long long g_dbg[8];
+
 __global__ void __launch_bounds__(32 * ST_WARPS)
 stats3_kernel(DevModel M, Wave W)
 {
@@ -336,6 +338,10 @@ stats3_kernel(DevModel M, Wave W)
       const bool valid = inb && x0 > -1.0e29;
       const unsigned mask = __ballot_sync(0xffffffffu, valid);
       const int nT = __popc(mask);
+#ifdef HFB_DEBUG_COUNT
+      { const unsigned ib = __ballot_sync(0xffffffffu, inb);
+        if (lane == 0) { atomicAdd(&g_dbg[0], (unsigned long long)__popc(ib)); atomicAdd(&g_dbg[1], (unsigned long long)nT); atomicAdd(&g_dbg[4], 1ull); } }
+#endif
       if (nT == 0) continue;
       if (valid) { int idx = __popc(mask & ((1u << lane) - 1)); ts[idx] = t; x0s[idx] = x0; }
       __syncwarp();
@@ -387,6 +393,9 @@ stats3_kernel(DevModel M, Wave W)
             }
          }
          __syncwarp();
+#ifdef HFB_DEBUG_COUNT
+         if (lane == 0) { atomicAdd(&g_dbg[2], (unsigned long long)(Mc * nT)); atomicAdd(&g_dbg[3], (unsigned long long)__popc(act)); }
+#endif
          // ---- phase 2: lanes <-> feature dimensions, centred sums over the chunk's frames
          for (unsigned b = act; b; b &= b - 1) {
             const int mi = __ffs(b) - 1;

@@ -126,6 +126,8 @@ struct hfbgpu_ctx {
       size_t hBeamsCap = 0;
       // in-flight wave
       bool busy = false;
+      hfb_utt_result *res = nullptr;    // where the in-flight wave's results go
+      hfb_beams beams = {};
       WaveTablesPtr w = nullptr;
       long long waveFrame0 = 0, waveFrames = 0;
       bool wantBeams = false;
@@ -133,6 +135,7 @@ struct hfbgpu_ctx {
    static const int NSLOT = 2;
    Slot slot[NSLOT];
    int numSlots = NSLOT;
+   unsigned nextSlot = 0;
    size_t workspaceBytes = 0;
    int smCount = 148;
    int maxSmemOptin = 0;
@@ -399,10 +402,13 @@ extern "C" int hfbgpu_set_stream(hfbgpu_ctx *c, void *st)
    return HFB_OK;
 }
 
+static int wait_impl(hfbgpu_ctx *c);
+
 extern "C" int hfbgpu_zero_accs(hfbgpu_ctx *c)
 {
    if (!c) return HFB_EINVAL;
    CK(cudaSetDevice(c->device));
+   { int rc = wait_impl(c); if (rc) return rc; }
    CK(cudaMemsetAsync(c->dAcc.p, 0, (size_t)c->L.count * sizeof(double), c->stream));
    CK(cudaStreamSynchronize(c->stream));
    return HFB_OK;
@@ -411,10 +417,13 @@ extern "C" int hfbgpu_zero_accs(hfbgpu_ctx *c)
 extern "C" double *hfbgpu_acc_device_ptr(hfbgpu_ctx *c) { return c ? c->dAcc.p : nullptr; }
 extern "C" int64_t hfbgpu_acc_count(hfbgpu_ctx *c) { return c ? c->L.count : 0; }
 
+static int wait_impl(hfbgpu_ctx *c);
+
 extern "C" int hfbgpu_get_accs(hfbgpu_ctx *c, double *hostOut)
 {
    if (!c || !hostOut) return HFB_EINVAL;
    CK(cudaSetDevice(c->device));
+   { int rc = wait_impl(c); if (rc) return rc; }
    CK(cudaStreamSynchronize(c->stream));
    CK(cudaMemcpy(hostOut, c->dAcc.p, (size_t)c->L.count * sizeof(double), cudaMemcpyDeviceToHost));
    c->stats.d2hBytes += c->L.count * (int64_t)sizeof(double);
@@ -669,10 +678,12 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
    return HFB_OK;
 }
 
-static int finish_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, hfb_utt_result *res, const hfb_beams *beams)
+static int finish_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S)
 {
    if (!S.busy) return HFB_OK;
    S.busy = false;
+   hfb_utt_result *res = S.res;
+   const hfb_beams *beams = &S.beams;
    WaveTables &w = *S.w;
    const int nU = (int)w.utt.size();
    CK(cudaStreamSynchronize(S.stream));
@@ -706,8 +717,11 @@ static int finish_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, hfb_utt_result *res, 
    return HFB_OK;
 }
 
-static int accumulate_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, const hfb_beams *beams,
-                           bool featOnDevice)
+// Enqueues the batch (one or more waves) without waiting for it.  `splitWaves` = how many
+// waves to aim at (the blocking call splits a batch over the streams; the asynchronous one keeps
+// a batch in one wave so that consecutive calls overlap instead).
+static int submit_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, const hfb_beams *beams,
+                       bool featOnDevice, int splitWaves)
 {
    if (!c || !b || !res) return HFB_EINVAL;
    if (b->numUtt < 0 || (b->numUtt > 0 && (!b->frameOff || !b->feat || !b->labOff || !b->lab))) return HFB_EINVAL;
@@ -717,14 +731,14 @@ static int accumulate_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *re
    const bool wantBeams = beams && (beams->qLo || beams->qHi || beams->sq || beams->eq);
    // timing mode serialises the waves so that the per-kernel events do not overlap
    const int ns = c->timing ? 1 : c->numSlots;
-   // aim at `ns` waves of equal frame count (one per stream), more if the workspace is too small
+   const int want = std::max(1, std::min(ns, splitWaves));
    const long long totalFrames = b->numUtt ? b->frameOff[b->numUtt] - b->frameOff[0] : 0;
-   const long long targetFrames = (b->numUtt >= 64 * ns) ? (totalFrames + ns - 1) / ns : totalFrames;
+   const long long targetFrames = (b->numUtt >= 64 * want) ? (totalFrames + want - 1) / want : totalFrames;
    const size_t wsPerSlot = c->workspaceBytes / (size_t)ns;
-   int u0 = 0, k = 0, rcAll = HFB_OK;
+   int u0 = 0, rcAll = HFB_OK;
    while (u0 < b->numUtt) {
-      hfbgpu_ctx::Slot &S = c->slot[k % ns];
-      int rc = finish_wave(c, S, res, beams);
+      hfbgpu_ctx::Slot &S = c->slot[c->nextSlot % ns];
+      int rc = finish_wave(c, S);
       if (rc) { rcAll = rc; break; }
       if (!S.w) S.w = new WaveTables();
       WaveTables &w = *S.w;
@@ -750,12 +764,23 @@ static int accumulate_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *re
       }
       if (rcAll) break;
       const long long waveFrames = b->frameOff[u1] - waveFrame0;
+      S.res = res;
+      if (wantBeams) S.beams = *beams; else memset(&S.beams, 0, sizeof(S.beams));
       rc = launch_wave(c, S, b->lab + w.lab0, b->feat, featOnDevice, waveFrame0, waveFrames, wantBeams);
       if (rc) { rcAll = rc; break; }
-      u0 = u1; k++;
+      u0 = u1; c->nextSlot++;
+      if (c->timing) { rc = finish_wave(c, S); if (rc) { rcAll = rc; break; } }
    }
-   for (int i = 0; i < hfbgpu_ctx::NSLOT; i++) {
-      int rc = finish_wave(c, c->slot[(k + i) % hfbgpu_ctx::NSLOT], res, beams);
+   return rcAll;
+}
+
+static int wait_impl(hfbgpu_ctx *c)
+{
+   if (!c) return HFB_EINVAL;
+   CK(cudaSetDevice(c->device));
+   int rcAll = HFB_OK;
+   for (int i = 0; i < hfbgpu_ctx::NSLOT; i++) {        // oldest first
+      int rc = finish_wave(c, c->slot[(c->nextSlot + i) % hfbgpu_ctx::NSLOT]);
       if (rc && !rcAll) rcAll = rc;
    }
    return rcAll;
@@ -763,13 +788,24 @@ static int accumulate_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *re
 
 extern "C" int hfbgpu_accumulate(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, const hfb_beams *beams)
 {
-   return accumulate_impl(c, b, res, beams, false);
+   int rc = submit_impl(c, b, res, beams, false, hfbgpu_ctx::NSLOT);
+   int rc2 = wait_impl(c);
+   return rc ? rc : rc2;
 }
 
 extern "C" int hfbgpu_accumulate_device(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, const hfb_beams *beams)
 {
-   return accumulate_impl(c, b, res, beams, true);
+   int rc = submit_impl(c, b, res, beams, true, hfbgpu_ctx::NSLOT);
+   int rc2 = wait_impl(c);
+   return rc ? rc : rc2;
 }
+
+extern "C" int hfbgpu_submit(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, const hfb_beams *beams, int featOnDevice)
+{
+   return submit_impl(c, b, res, beams, featOnDevice != 0, 1);
+}
+
+extern "C" int hfbgpu_wait(hfbgpu_ctx *c) { return wait_impl(c); }
 
 // ------------------------------------------------------------------------------------------
 // OutP alone
@@ -824,3 +860,11 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
    CK(cudaStreamSynchronize(st0));
    return HFB_OK;
 }
+
+#ifdef HFB_DEBUG_COUNT
+extern "C" int hfbgpu_debug_counters(unsigned long long *out)
+{
+   cudaDeviceSynchronize();
+   return cudaMemcpyFromSymbol(out, g_dbg, sizeof(unsigned long long) * 8) == cudaSuccess ? 0 : -3;
+}
+#endif

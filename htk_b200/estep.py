@@ -27,6 +27,16 @@ class UttResult(tuple):
     pruneThresh = property(lambda s: s[3])
 
 
+class _Ticket:
+    """Keeps the buffers of an in-flight batch alive."""
+
+    def __init__(self, batch, cb, res, beams, bs):
+        self.batch, self._cb, self._res, self.beams, self._bs = batch, cb, res, beams, bs
+
+    def results(self) -> List[UttResult]:
+        return [UttResult((r.status, r.retries, r.pr, r.pruneThresh)) for r in self._res[:self.batch.numUtt]]
+
+
 class ForwardBackward:
     def __init__(self, fm: FlatModel, prune=None, min_frwd_p: float = 10.0, uflags: int = 15,
                  device: int = 0, gmm_kernel: int = 0, workspace_bytes: int = 0):
@@ -40,9 +50,12 @@ class ForwardBackward:
             raise capi.HfbError(rc, "hfbgpu_create")
         self.h = h
         self.layout = fm.layout
+        self._inflight = []
 
     def close(self):
         if getattr(self, "h", None):
+            self.lib.hfbgpu_wait(self.h)
+            self._inflight = []
             self.lib.hfbgpu_destroy(self.h)
             self.h = None
 
@@ -65,6 +78,27 @@ class ForwardBackward:
             raise capi.HfbError(rc, "hfbgpu_accumulate")
         return [UttResult((r.status, r.retries, r.pr, r.pruneThresh)) for r in res[:batch.numUtt]], beams
 
+    # -- asynchronous form: consecutive batches overlap on the library's two streams --------
+    def Submit(self, batch: Batch, device_feat_ptr: Optional[int] = None, want_beams: bool = False):
+        """Enqueue a batch; returns a ticket whose .results() is valid after Wait()."""
+        res = (hfb_utt_result * max(1, batch.numUtt))()
+        beams = Beams(batch.totalT) if want_beams else None
+        bs = beams.c_struct() if beams is not None else None
+        b = batch.c_struct(device_feat_ptr)
+        rc = self.lib.hfbgpu_submit(self.h, C.byref(b), res, C.byref(bs) if bs is not None else None,
+                                    0 if device_feat_ptr is None else 1)
+        if rc != 0:
+            raise capi.HfbError(rc, "hfbgpu_submit")
+        tk = _Ticket(batch, b, res, beams, bs)
+        self._inflight.append(tk)          # the library writes into these buffers until Wait()
+        return tk
+
+    def Wait(self):
+        rc = self.lib.hfbgpu_wait(self.h)
+        self._inflight = []
+        if rc != 0:
+            raise capi.HfbError(rc, "hfbgpu_wait")
+
     def ZeroAccs(self):
         rc = self.lib.hfbgpu_zero_accs(self.h)
         if rc != 0:
@@ -73,6 +107,7 @@ class ForwardBackward:
     def GetAccs(self) -> np.ndarray:
         out = np.zeros(self.layout.count, np.float64)
         rc = self.lib.hfbgpu_get_accs(self.h, out.ctypes.data)
+        self._inflight = []
         if rc != 0:
             raise capi.HfbError(rc, "hfbgpu_get_accs")
         return out

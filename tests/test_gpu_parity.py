@@ -226,3 +226,20 @@ def test_generic_kernels_and_redo_path(name, hook, monkeypatch):
     assert max(e.values()) < 1e-6, e
     e = acc_errors(a2, z["ref_acc"], fm)
     assert max(e.values()) < RTOL, e
+
+
+def test_submit_wait_equals_blocking_call():
+    """hfbgpu_submit / hfbgpu_wait (batches overlapping on two streams) == hfbgpu_accumulate."""
+    z, fm, b, kw = load_golden("synth_tied_m4")
+    fb = _fb(fm, **kw)
+    r0, _ = fb.FBFile(b); r0b, _ = fb.FBFile(b); r0c, _ = fb.FBFile(b)
+    a0 = fb.GetAccs()
+    fb.ZeroAccs()
+    tickets = [fb.Submit(b, want_beams=(i == 1)) for i in range(3)]
+    a1 = fb.GetAccs()                      # waits implicitly
+    for tk in tickets:
+        for x, y in zip(tk.results(), r0):
+            assert x.status == y.status and abs(x.pr - y.pr) <= 1e-12 * abs(y.pr)
+    assert np.allclose(a1, a0, rtol=1e-9, atol=1e-9)
+    assert tickets[1].beams.qHi.max() > 0
+    fb.close()
