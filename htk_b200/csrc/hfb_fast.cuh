@@ -18,8 +18,8 @@
 template <bool EXACT>
 __device__ __forceinline__ double lacc(double x, double term)
 {
-   if (x < LSMALL_D && term > LSMALL_D) return term;      // LAdd(x, term) returns term exactly here
-   return ladd<EXACT>(x, term);
+   if (EXACT && x < LSMALL_D && term > LSMALL_D) return term;      // LAdd(x, term) returns term exactly here
+   return EXACT ? ladd<EXACT>(x, term) : ladd_nz(x, term);         // (the branch-free form does so by itself)
 }
 
 template <int E>

@@ -28,14 +28,50 @@
 
 // LAdd, HTKLib/HMath.c:1576-1590.  EXACT=false keeps the magnitude in FP64 and evaluates the
 // bounded correction log(1+exp(d)), d in [-23.03, 0], in FP32 (<= 1e-7 absolute).
+//
+// The FP32 correction is branch-free and uses the two special-function-unit approximations
+// directly: e = ex2.approx(d log2 e) (relative error <= 2^-22), then lg2.approx(1 + e) (absolute
+// error <= 2^-22 on [1, 2]) -- together <= 3.5e-7 absolute on the correction, which is bounded by
+// log 2.  With d < minLogExp the correction is dropped, so LAdd(log zero, y) == y exactly as in
+// the reference (HMath.c:1584-1585).  ~18 instructions instead of ~50 for log1pf(expf(d)).
+__device__ __forceinline__ float ex2_approx(float x)
+{
+   float r;
+   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+   return r;
+}
+__device__ __forceinline__ float lg2_approx(float x)
+{
+   float r;
+   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+   return r;
+}
+
 template <bool EXACT>
 __device__ __forceinline__ double ladd(double x, double y)
 {
-   if (x < y) { double t = x; x = y; y = t; }
-   double d = y - x;
-   if (d < MINLOGEXP) return (x < LSMALL_D) ? LZERO_D : x;
-   if (EXACT) return x + log(1.0 + exp(d));
-   return x + (double)log1pf(expf((float)d));
+   if (EXACT) {
+      if (x < y) { double t = x; x = y; y = t; }
+      double d = y - x;
+      if (d < MINLOGEXP) return (x < LSMALL_D) ? LZERO_D : x;
+      return x + log(1.0 + exp(d));
+   }
+   const double hi = (x > y) ? x : y;
+   const float d = -fabsf((float)(x - y));
+   float c = lg2_approx(1.0f + ex2_approx(d * 1.4426950408889634f)) * 0.6931471805599453f;
+   c = (d < (float)MINLOGEXP) ? 0.f : c;
+   return (hi < LSMALL_D) ? LZERO_D : hi + (double)c;
+}
+
+// The same for callers that have already checked one operand against LSMALL (every guarded
+// `if (term > LSMALL) x = LAdd(x, term)` of HFB.c): the result cannot be log zero.
+__device__ __forceinline__ double ladd_nz(double x, double y)
+{
+   const double hi = (x > y) ? x : y;
+   const float d = -fabsf((float)(x - y));
+   float c = lg2_approx(1.0f + ex2_approx(d * 1.4426950408889634f)) * 0.6931471805599453f;
+   c = (d < (float)MINLOGEXP) ? 0.f : c;
+   return hi + (double)c;
 }
 
 __device__ __forceinline__ void prefetch_l1(const void *p)

@@ -386,11 +386,7 @@ stats3_kernel(DevModel M, Wave W)
                }
                lrs[mi * 33 + ti] = Lr;
             }
-            const unsigned nz = __ballot_sync(0xffffffffu, Lr > 0.f);
-            for (unsigned b = nz; b; b &= b - 1) {
-               int l = __ffs(b) - 1;
-               act |= 1u << (((pi - lane) + l) / nT);
-            }
+            act |= __reduce_or_sync(0xffffffffu, (Lr > 0.f) ? (1u << mi) : 0u);
          }
          __syncwarp();
 #ifdef HFB_DEBUG_COUNT
