@@ -1,0 +1,304 @@
+// hfb_l2r.cuh -- recursion kernels specialised for HTK's standard topology: every HMM of the set
+// has 5 states (3 emitting) and the only transitions are entry->2, i->i, i->i+1 and 4->exit
+// (what MakeProtoHMMSet / HInit produce and what all BASELINE configs use; checked once per
+// model set in hfbgpu_create, see model_is_l2r()).  No tee models, no skips, so
+//
+//   * SetBeta   (HFB.c:1205-1277) is three log-adds per (model, frame):
+//        beta_4(t) = (a_4N + beta_N(t))          (+) (a_44 + u_4)        u_j = b_j(o_t+1) + beta_j(t+1)
+//        beta_3(t) = (a_33 + u_3)                (+) (a_34 + u_4)
+//        beta_2(t) = (a_22 + u_2)                (+) (a_23 + u_3)
+//        beta_1(t) =  a_12 + b_2(o_t) + beta_2(t)
+//   * StepAlpha (HFB.c:729-771) likewise:
+//        alpha_2(t) = [(a_12 + alpha_1(t)) (+) (alpha_2(t-1) + a_22)] + b_2(o_t)   etc.
+//
+// The transition logs live in registers as doubles (no per-frame conversions), the structural
+// "log zero" tests of the generic code disappear at compile time, and the guarded
+// `if (y > LSMALL) x = LAdd(x, y)` of the reference becomes an unconditional branch-free log-add:
+// with one operand at log zero the other is returned exactly, with both the result stays below
+// LSMALL, i.e. log zero for every later test.  Same numbers as beta_fast/alpha_fast_kernel for
+// every value above LSMALL; ~2.5x fewer instructions per frame.
+#pragma once
+#include "hfb_fast.cuh"
+
+struct L2RRegs {
+   double aE, a00, a01, a11, a12, a22, a2x;    // entry->0, i->i, i->i+1, 2->exit (emitting states 0..2)
+   int s0, s1, s2;                             // output-probability slots of the emitting states
+};
+
+__device__ __forceinline__ void load_l2r(L2RRegs &r, const DevModel &M, const Wave &W, const UttDesc &u, int q)
+{
+   const float *A = M.transLogA + W.mTrans[u.modOff + q];      // 5 x 5, row-major
+   r.aE = (double)A[1];
+   r.a00 = (double)A[6];  r.a01 = (double)A[7];
+   r.a11 = (double)A[12]; r.a12 = (double)A[13];
+   r.a22 = (double)A[18]; r.a2x = (double)A[19];
+   const int *ps = W.posSlot + u.posOff + 3 * q;
+   r.s0 = ps[0]; r.s1 = ps[1]; r.s2 = ps[2];
+}
+
+__device__ __forceinline__ double dmax(double a, double b) { return (a > b) ? a : b; }
+
+// ------------------------------------------------------------------------------------------
+// K2 (standard topology): one CTA per utterance, one thread per model
+// ------------------------------------------------------------------------------------------
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1024 / MAXT) beta_l2r_kernel(DevModel M, Wave W)
+{
+   extern __shared__ __align__(16) unsigned char smraw[];
+   const UttDesc &u = W.utt[blockIdx.x];
+   UttOut *out = &W.out[blockIdx.x];
+   if (out->status != 0) {
+      if (threadIdx.x == 0 && out->status == HFB_UTT_SKIPPED) atomicAdd(&W.acc[M.L.numSkipped], 1.0);
+      return;
+   }
+   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+   const int T = u.T, Q = u.Q, J = u.J;
+   const size_t S = (size_t)5 * Q;
+   double *entA = (double *)smraw, *entB = entA + (Q + 2), *wred = entB + (Q + 2);
+   int *wlo = (int *)(wred + 32), *whi = wlo + 32;
+   const int q = tid;
+   const bool mine = q < Q;
+   L2RRegs r;
+   if (mine) load_l2r(r, M, W, u, q);
+   else { r.aE = r.a00 = r.a01 = r.a11 = r.a12 = r.a22 = r.a2x = LZERO_D; r.s0 = r.s1 = r.s2 = 0; }
+   const float *bU = W.b + u.bOff;
+   double *betaQ = W.beta + u.betaOff + 5 * q;
+   short *qLo = W.qLo + u.frameBase, *qHi = W.qHi + u.frameBase;
+   const int *pre = W.mPre + u.modOff, *suf = W.mSuf + u.modOff;
+
+   double thresh = W.pruneInit, pr = LZERO_D;
+   int retries = 0, status = 0;
+
+   for (;;) {
+      // ---- SetBeamTaper (closed form, see beta_kernel)
+      for (int t = tid; t < T; t += nt) {
+         int lo = 0, hi = Q;
+         while (lo < hi) { int mid = (lo + hi) >> 1; if (pre[mid] <= t) lo = mid + 1; else hi = mid; }
+         qHi[t] = (short)(lo - 1);
+         int rr = T - 1 - t; lo = 0; hi = Q;
+         while (lo < hi) { int mid = (lo + hi) >> 1; if (suf[mid] > rr) lo = mid + 1; else hi = mid; }
+         qLo[t] = (short)lo;
+      }
+      __syncthreads();
+      const bool noPrune = thresh >= 0.5 * HFB_NOPRUNE;
+
+      double *cur = entA, *prev = entB;                // entry-state beta of every model, frames t / t+1
+      double u0 = LZERO_D, u1 = LZERO_D, u2 = LZERO_D; // b_j(o_{t+1}) + beta_j(t+1), log zero outside the beam
+
+      // ---- t = T-1, HFB.c:1176-1198
+      int lo1 = qLo[T - 1], hi1 = Q - 1, lastq = lo1;
+      if (tid == 0) qHi[T - 1] = (short)(Q - 1);
+      if (mine && q >= lo1) {
+         const float *bt = bU + (size_t)(T - 1) * J;
+         const double bExit = (q == Q - 1) ? 0.0 : LZERO_D;
+         const double n0 = LZERO_D + bExit, n1 = LZERO_D + bExit, n2 = r.a2x + bExit;
+         u0 = (double)bt[r.s0] + n0; u1 = (double)bt[r.s1] + n1; u2 = (double)bt[r.s2] + n2;
+         const double x = (n0 > LSMALL_D) ? r.aE + u0 : LZERO_D;
+         double *bg = betaQ + (size_t)(T - 1) * S;
+         bg[0] = x; bg[1] = n0; bg[2] = n1; bg[3] = n2; bg[4] = bExit;
+         cur[q] = x;
+      }
+      // output probabilities travel two frames ahead of their use, in registers
+      float bA0 = 0.f, bA1 = 0.f, bA2 = 0.f, bB0 = 0.f, bB1 = 0.f, bB2 = 0.f;
+      if (mine) {
+         if (T >= 2) { const float *b2 = bU + (size_t)(T - 2) * J; bA0 = b2[r.s0]; bA1 = b2[r.s1]; bA2 = b2[r.s2]; }
+         if (T >= 3) { const float *b2 = bU + (size_t)(T - 3) * J; bB0 = b2[r.s0]; bB1 = b2[r.s1]; bB2 = b2[r.s2]; }
+      }
+      __syncthreads();
+      { double *tmp = cur; cur = prev; prev = tmp; }
+
+      // ---- t = T-2 .. 0, HFB.c:1205-1277
+      bool fail = false;
+      double *bg = betaQ + (size_t)(T - 1) * S;        // running pointers: this model's beta column at t,
+      const float *bp = bU + (size_t)(T - 3) * J;      // the output-probability row of frame t-2
+      const short *pLo = qLo + (T - 1), *pHi = qHi + (T - 1);
+      for (int t = T - 2; t >= 0; t--) {
+         bg -= S; bp -= J; pLo--; pHi--;
+         const int tapLo = *pLo, tapHi = *pHi;
+         const int startq = hi1;
+         const int endq = (lo1 == 0) ? 0 : ((tapLo >= lo1) ? tapLo : lo1 - 1);
+         lastq = endq;
+         const bool active = mine && q >= endq && q <= startq;
+         const float c0 = bA0, c1 = bA1, c2 = bA2;
+         bA0 = bB0; bA1 = bB1; bA2 = bB2;
+         if (t >= 2 && mine && q >= endq - 2 && q <= startq) { bB0 = bp[r.s0]; bB1 = bp[r.s1]; bB2 = bp[r.s2]; }
+         double lMax = LZERO_D, un0 = LZERO_D, un1 = LZERO_D, un2 = LZERO_D;
+         if (active) {
+            const double ex = (q + 1 >= lo1 && q + 1 <= hi1) ? prev[q + 1] : LZERO_D;      // :1225
+            const double n2 = ladd_nz(r.a2x + ex, r.a22 + u2);                             // :1228-1236
+            const double n1 = ladd_nz(r.a11 + u1, r.a12 + u2);
+            const double n0 = ladd_nz(r.a00 + u0, r.a01 + u1);
+            un0 = (double)c0 + n0; un1 = (double)c1 + n1; un2 = (double)c2 + n2;
+            const double x = r.aE + un0;                                                   // :1242-1250
+            bg[0] = x; bg[1] = n0; bg[2] = n1; bg[3] = n2; bg[4] = ex;
+            cur[q] = x;
+            lMax = dmax(dmax(n0, n1), n2);
+         }
+         int nhi, nlo;
+         if (noPrune) {
+            // gMax - maxP[q] > thresh is never true for finite log values: the beam is the candidate
+            // range and only the entry values have to become visible to the neighbours
+            nhi = startq; nlo = endq;
+            __syncthreads();
+         } else {
+            double gMax = warp_max(lMax);
+            if (lane == 0) wred[wid] = gMax;
+            __syncthreads();
+            gMax = LZERO_D;
+            for (int w = 0; w < nw; w++) gMax = dmax(gMax, wred[w]);
+            // ---- pruning (:1254-1272)
+            const bool keep = active && !(gMax - lMax > thresh);
+            const int myHi = __reduce_max_sync(0xffffffffu, keep ? q : -1);
+            const int myLo = __reduce_min_sync(0xffffffffu, keep ? q : 0x7fffffff);
+            if (lane == 0) { whi[wid] = myHi; wlo[wid] = myLo; }
+            __syncthreads();
+            nhi = -1; nlo = 0x7fffffff;
+            for (int w = 0; w < nw; w++) { nhi = max(nhi, whi[w]); nlo = min(nlo, wlo[w]); }
+         }
+         if (nhi < 0) { fail = true; status = HFB_UTT_EBETA; break; }
+         if (nhi > tapHi) nhi = tapHi;
+         if (nlo > nhi) { fail = true; break; }
+         if (tid == 0) { qHi[t] = (short)nhi; qLo[t] = (short)nlo; }
+         hi1 = nhi; lo1 = nlo;
+         const bool inNew = active && q >= nlo && q <= nhi;
+         u0 = inNew ? un0 : LZERO_D; u1 = inNew ? un1 : LZERO_D; u2 = inNew ? un2 : LZERO_D;
+         { double *tmp = cur; cur = prev; prev = tmp; }
+      }
+      if (status != 0) break;
+      if (!fail) {
+         pr = prev[lastq];                             // utt->pr = bqt[1] (:1280)
+         if (pr > LSMALL_D) break;
+      }
+      thresh += W.pruneInc;                            // StepBack retry (:1349-1361)
+      if (thresh > W.pruneLim || W.pruneInc == 0.0) { status = HFB_UTT_SKIPPED; break; }
+      retries++;
+      __syncthreads();
+   }
+   if (tid == 0) {
+      out->status = status; out->retries = retries; out->pr = (status == 0) ? pr : LZERO_D;
+      out->thresh = thresh;
+      if (status == HFB_UTT_SKIPPED) atomicAdd(&W.acc[M.L.numSkipped], 1.0);
+   }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 (standard topology): one WARP per utterance, lane L owns the model q = L (mod 32) of the
+// sliding window that starts at the alpha beam's lower end.  Without tee models StepAlpha can
+// reach [sq(t-1), eq(t-1)+1] only.  Writes alpha, the beams and first/last active frame per
+// model; gives up (out->redo) if a beam ever needs more than 32 models.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) alpha_l2r_kernel(DevModel M, Wave W, int forceRedo)
+{
+   const UttDesc &u = W.utt[blockIdx.x];
+   UttOut *out = &W.out[blockIdx.x];
+   if (out->status != 0) return;
+   if (forceRedo) { if (threadIdx.x == 0) out->redo = 1; return; }
+   const unsigned FULL = 0xffffffffu;
+   const int lane = threadIdx.x;
+   const int T = u.T, Q = u.Q, J = u.J;
+   const size_t S = (size_t)5 * Q, P = (size_t)3 * Q;
+   const float *bU = W.b + u.bOff;
+   const double *betaU = W.beta + u.betaOff;
+   double *occU = W.occ + u.occOff, *aentU = W.aent + u.aentOff;
+   const short *qLo = W.qLo + u.frameBase, *qHi = W.qHi + u.frameBase;
+   short *sqA = W.sq + u.frameBase, *eqA = W.eq + u.frameBase;
+   const double pr = out->pr, minF = W.minFrwdP;
+   int *gTmin = W.mTmin + u.modOff, *gTmax = W.mTmax + u.modOff;
+   for (int q = lane; q < Q; q += 32) { gTmin[q] = 0x7fffffff; gTmax[q] = -1; }
+
+   L2RRegs r;
+   int myq = lane;
+   bool have = myq < Q;
+   if (have) load_l2r(r, M, W, u, myq);
+   else { r.aE = r.a00 = r.a01 = r.a11 = r.a12 = r.a22 = r.a2x = LZERO_D; r.s0 = r.s1 = r.s2 = 0; }
+   double e0 = LZERO_D, e1 = LZERO_D, e2 = LZERO_D;     // alpha of the emitting states at t-1
+   double aEx = LZERO_D, mpS = LZERO_D, exv = LZERO_D;  // alpha_N(t-1); max_i alpha_i+beta_i; alpha_N+beta_N
+   int tmin = 0x7fffffff, tmax = -1;
+   int sq = 0, eq = 0;
+
+   for (int t = 0; t < T; t++) {
+      const int loT = qLo[t], hiT = qHi[t];
+      // loads that do not depend on the recursion go first
+      const bool inWin = have && myq >= sq && myq <= ((t == 0) ? hiT : min(Q - 1, eq + 1));
+      float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+      double bEn = LZERO_D, bE0 = LZERO_D, bE1 = LZERO_D, bE2 = LZERO_D, bX = LZERO_D;
+      if (inWin && myq >= loT && myq <= hiT) {
+         const float *bt = bU + (size_t)t * J;
+         const double *bq = betaU + (size_t)t * S + 5 * myq;
+         bEn = bq[0]; bE0 = bq[1]; bE1 = bq[2]; bE2 = bq[3]; bX = bq[4];
+         b0 = bt[r.s0]; b1 = bt[r.s1]; b2 = bt[r.s2];
+      }
+      if (inWin && t + 2 < T) {                              // first touched two frames from now
+         const float *bt2 = bU + (size_t)(t + 2) * J;
+         const double *bq2 = betaU + (size_t)(t + 2) * S + 5 * myq;
+         prefetch_l1(bq2); prefetch_l1(bq2 + 4);
+         prefetch_l1(bt2 + r.s0); prefetch_l1(bt2 + r.s1); prefetch_l1(bt2 + r.s2);
+      }
+      double a1 = LZERO_D, n0 = LZERO_D, n1 = LZERO_D, n2 = LZERO_D, nEx = LZERO_D;
+      int nsq, neq;
+      if (t == 0) {
+         // ---- InitAlpha, HFB.c:616-651 (no tee models: only the first model can start)
+         nsq = 0; neq = hiT;
+         if (neq + 1 >= 32) { if (lane == 0) out->redo = 1; return; }
+         if (have && myq <= neq) {
+            a1 = (myq == 0) ? 0.0 : LZERO_D;
+            n0 = a1 + r.aE + (double)b0;
+         }
+      } else {
+         // ---- alpha beam, HFB.c:701-722
+         const int loP = qLo[t - 1], hiP = qHi[t - 1];
+         const int q1 = __shfl_sync(FULL, myq, (lane + 31) & 31);
+         const double ex1 = __shfl_sync(FULL, exv, (lane + 31) & 31);
+         const double ax1 = __shfl_sync(FULL, aEx, (lane + 31) & 31);
+         const bool ok1 = (q1 == myq - 1);
+         const double mp = dmax(ok1 ? ex1 : LZERO_D, mpS);                  // MaxModelProb(q, t-1), :655-682
+         const bool keep = inWin && !(pr - mp > minF);
+         nsq = __reduce_min_sync(FULL, (keep && myq >= loP) ? myq : 0x7fffffff);
+         if (nsq > hiT) { if (lane == 0) out->status = HFB_UTT_EALPHA; return; }        // HError 7390
+         if (nsq < loT) nsq = loT;
+         const int eq0 = (hiP < Q - 1) ? hiP + 1 : hiP;
+         neq = __reduce_max_sync(FULL, (keep && myq <= eq0) ? myq : -1);
+         if (neq < nsq) { if (lane == 0) out->status = HFB_UTT_EALPHA; return; }
+         if (neq > hiT) neq = hiT;
+         if (neq + 1 - nsq >= 32) { if (lane == 0) out->redo = 1; return; }
+         // ---- alpha column, HFB.c:729-771
+         if (have && myq >= nsq && myq <= neq) {
+            a1 = (myq > 0 && ok1) ? ax1 : LZERO_D;
+            n0 = ladd_nz(r.aE + a1, e0 + r.a00) + (double)b0;
+            n1 = ladd_nz(e0 + r.a01, e1 + r.a11) + (double)b1;
+            n2 = ladd_nz(e1 + r.a12, e2 + r.a22) + (double)b2;
+            nEx = (n2 > LSMALL_D) ? n2 + r.a2x : LZERO_D;
+         }
+      }
+      sq = nsq; eq = neq;
+      const bool inBeam = have && myq >= sq && myq <= eq;
+      if (lane == 0) { sqA[t] = (short)sq; eqA[t] = (short)eq; }
+      aEx = nEx; e0 = n0; e1 = n1; e2 = n2;
+      mpS = LZERO_D; exv = LZERO_D;
+      if (inBeam) {
+         mpS = dmax(dmax(a1 + bEn, n0 + bE0), dmax(n1 + bE1, n2 + bE2));
+         exv = nEx + bX;
+         double *oc = occU + (size_t)t * P + 3 * myq;
+         oc[0] = n0; oc[1] = n1; oc[2] = n2;
+         aentU[(size_t)t * Q + myq] = a1;
+         if (tmin > t) tmin = t;
+         tmax = t;
+      }
+      // ---- slide: a lane whose model fell below the beam takes the model 32 further on
+      if (have && myq < sq) {
+         if (tmax >= 0) { gTmin[myq] = tmin; gTmax[myq] = tmax; }
+         myq += 32; have = myq < Q;
+         tmin = 0x7fffffff; tmax = -1;
+         aEx = LZERO_D; mpS = LZERO_D; exv = LZERO_D; e0 = e1 = e2 = LZERO_D;
+         if (have) load_l2r(r, M, W, u, myq);
+         else { r.aE = r.a00 = r.a01 = r.a11 = r.a12 = r.a22 = r.a2x = LZERO_D; r.s0 = r.s1 = r.s2 = 0; }
+      }
+   }
+   if (have && tmax >= 0) { gTmin[myq] = tmin; gTmax[myq] = tmax; }
+   for (int q = lane; q < Q; q += 32) atomicAdd(&W.acc[M.L.numEgs + W.mHmm[u.modOff + q]], 1.0);   // HFB.c:1768-1772
+   if (lane == 0) {
+      atomicAdd(&W.acc[M.L.totalT], (double)T);                             // HERest.c:779-780
+      atomicAdd(&W.acc[M.L.totalPr], pr);
+      atomicAdd(&W.acc[M.L.numOk], 1.0);
+   }
+}

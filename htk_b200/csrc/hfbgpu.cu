@@ -19,6 +19,7 @@
 #include "hfb_kernels.cuh"
 #include "hfb_kernels2.cuh"
 #include "hfb_fast.cuh"
+#include "hfb_l2r.cuh"
 #include "gmm_tc.cuh"
 
 static thread_local std::string g_lastError;
@@ -60,6 +61,7 @@ struct DevBuf {
 
 struct HostModel {
    int D, G, J, P, numTrans, maxM, maxN;
+   bool l2r;                         // every HMM has HTK's standard 5-state left-to-right topology (hfb_l2r.cuh)
    std::vector<int> stateMixOff, hmmN, hmmStateOff, hmmState, hmmTrans, transN, transOff, minDur;
    std::vector<long long> tranAccOff, tranOccOff;
    std::vector<float> transLogA;
@@ -230,6 +232,19 @@ static int min_duration(const float *A, int N)
    return md[N - 1];
 }
 
+// Standard topology test for the specialised recursion kernels (hfb_l2r.cuh): N = 5 and every
+// transition other than entry->2, i->i, i->i+1 (i = 2..4) is log zero.
+static bool matrix_is_l2r(const float *A, int N)
+{
+   if (N != 5) return false;
+   for (int i = 0; i < N; i++)
+      for (int j = 0; j < N; j++) {
+         const bool structural = (i == 0 && j == 1) || (i >= 1 && i <= 3 && (j == i || j == i + 1));
+         if (!structural && A[i * N + j] > HFB_LSMALL) return false;
+      }
+   return true;
+}
+
 // ------------------------------------------------------------------------------------------
 // create / destroy
 // ------------------------------------------------------------------------------------------
@@ -280,7 +295,7 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
    h.transN.assign(m->transN, m->transN + h.numTrans);
    h.transOff.assign(m->transOff, m->transOff + h.numTrans + 1);
    h.transLogA.assign(m->transLogA, m->transLogA + m->transOff[h.numTrans]);
-   h.maxM = 0; h.maxN = 0;
+   h.maxM = 0; h.maxN = 0; h.l2r = true;
    for (int j = 0; j < h.J; j++) h.maxM = std::max(h.maxM, h.stateMixOff[j + 1] - h.stateMixOff[j]);
    h.minDur.resize(h.numTrans);
    h.tranAccOff.resize(h.numTrans); h.tranOccOff.resize(h.numTrans);
@@ -289,6 +304,7 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
       int N = h.transN[i];
       h.maxN = std::max(h.maxN, N);
       h.minDur[i] = min_duration(h.transLogA.data() + h.transOff[i], N);       // SetMinDurs
+      if (!matrix_is_l2r(h.transLogA.data() + h.transOff[i], N) || h.minDur[i] != 3) h.l2r = false;
       h.tranAccOff[i] = a; h.tranOccOff[i] = b;
       a += (long long)N * N; b += N;
    }
@@ -361,6 +377,7 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
    cudaFuncSetAttribute(alpha_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(alpha_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(stats3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
+   cudaFuncSetAttribute(beta_l2r_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    CK(cudaStreamSynchronize(c->stream));
    *out = c;
    return HFB_OK;
@@ -621,7 +638,13 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
       const int forceRedo = getenv("HFBGPU_FORCE_REDO") ? 1 : 0;      // fast alpha gives up immediately
       const bool fastOk = !noFast && w.maxN <= 8;                      // alpha: any Q (32-model sliding window)
       const bool betaFastOk = fastOk && w.maxQ <= 256;                 // beta: one thread per model
-      if (betaFastOk) {
+      const bool l2r = fastOk && !exact && c->hm.l2r && !getenv("HFBGPU_NO_L2R");   // standard topology
+      if (l2r && w.maxQ <= 1024) {
+         const size_t fsm = beta_fast_smem_bytes(w.maxQ);
+         if (w.maxQ <= 256) beta_l2r_kernel<256><<<nU, nt, fsm, st>>>(c->dm, W);
+         else beta_l2r_kernel<1024><<<nU, ntGeneric, fsm, st>>>(c->dm, W);
+         c->stats.launchesL2R++;
+      } else if (betaFastOk) {
          const size_t fsm = beta_fast_smem_bytes(w.maxQ);
          if (w.maxN <= 5) {
             if (exact) beta_fast_kernel<true, 3><<<nU, nt, fsm, st>>>(c->dm, W);
@@ -634,7 +657,8 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
       else beta_kernel<false><<<nU, ntGeneric, rsm, st>>>(c->dm, W);
       if (tm) cudaEventRecord(S.ev[2], st);
       if (fastOk) {                                    // register/shuffle kernel; generic one redoes overflows
-         if (w.maxN <= 5) {
+         if (l2r) { alpha_l2r_kernel<<<nU, 32, 0, st>>>(c->dm, W, forceRedo); c->stats.launchesL2R++; }
+         else if (w.maxN <= 5) {
             if (exact) alpha_fast_kernel<true, 3><<<nU, 32, 0, st>>>(c->dm, W, forceRedo);
             else alpha_fast_kernel<false, 3><<<nU, 32, 0, st>>>(c->dm, W, forceRedo);
          } else {

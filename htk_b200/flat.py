@@ -80,7 +80,7 @@ class hfb_stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "launches", "launchesGmm", "launchesBeta", "launchesAlpha", "launchesStats", "launchesMisc")] + \
         [(n, C.c_double) for n in ("msGmm", "msBeta", "msAlpha", "msStats")] + \
-        [(n, C.c_int64) for n in ("betaCells", "alphaCells", "gmmPairs", "h2dBytes", "d2hBytes")]
+        [(n, C.c_int64) for n in ("betaCells", "alphaCells", "gmmPairs", "h2dBytes", "d2hBytes", "launchesL2R")]
 
 
 NOPRUNE = 1.0e20

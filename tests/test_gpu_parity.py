@@ -207,15 +207,18 @@ def test_exact_ladd_env(monkeypatch):
     assert max(e.values()) < 2e-5, e
 
 
-@pytest.mark.parametrize("hook", ["HFBGPU_NO_FAST", "HFBGPU_FORCE_REDO"])
+@pytest.mark.parametrize("hook", ["HFBGPU_NO_FAST", "HFBGPU_FORCE_REDO", "HFBGPU_NO_L2R"])
 @pytest.mark.parametrize("name", ["htkdemo_t20_15_200", "synth_tee_m2", "synth_tied_m4", "synth_long_m3"])
 def test_generic_kernels_and_redo_path(name, hook, monkeypatch):
     """The generic (any N, any Q) recursion kernels and the fast->generic alpha fallback give the
     same beams and accumulators as the register-resident fast path."""
     z, fm, b, kw = load_golden(name)
-    fb = _fb(fm, **kw); r1, b1 = fb.FBFile(b, want_beams=True); a1 = fb.GetAccs(); fb.close()
+    fb = _fb(fm, **kw); r1, b1 = fb.FBFile(b, want_beams=True); a1 = fb.GetAccs(); st1 = fb.stats(); fb.close()
     monkeypatch.setenv(hook, "1")
-    fb = _fb(fm, **kw); r2, b2 = fb.FBFile(b, want_beams=True); a2 = fb.GetAccs(); fb.close()
+    fb = _fb(fm, **kw); r2, b2 = fb.FBFile(b, want_beams=True); a2 = fb.GetAccs(); st2 = fb.stats(); fb.close()
+    # the standard-topology kernels (hfb_l2r.cuh) run exactly on the sets without tee models / skips
+    assert (st1.launchesL2R > 0) == (name != "synth_tee_m2"), (name, st1.launchesL2R)
+    assert hook == "HFBGPU_FORCE_REDO" or st2.launchesL2R == 0
     for x, y in zip(r1, r2):
         assert x.status == y.status and x.pruneThresh == y.pruneThresh
         if x.status == 0:
