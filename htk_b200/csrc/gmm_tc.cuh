@@ -50,7 +50,9 @@ struct GmmTcModel {
    int GPS = 0;                // 8-row groups per state = MP / 8
    long long rows = 0;         // rows in Bhi/Blo (row group 0 is the all-"-inf" dummy)
    float *dBhi = nullptr, *dBlo = nullptr, *dOffset = nullptr;
-   CUtensorMap mapBhi, mapBlo;
+   CUtensorMap mapBhi, mapBlo;         // boxes of MP rows (one state)
+   CUtensorMap mapBhiP, mapBloP;       // boxes of min(MP, 64) rows for the CTA-pair kernel
+   bool pairReady = false;
    void *encodeFn = nullptr;
    float C0 = 0.f;             // symmetrising constant contracted first, subtracted in the epilogue
 };
@@ -189,7 +191,13 @@ struct TcParams {
    float *b;
    int GPS;                    // 8-row groups per state
    float C0;
+   int kSteps;                 // 8-float K steps that hold data: ceil((2D+2)/8) <= 12; the zero padding is skipped
+   int dbg;                    // timing experiments only (HFBGPU_TC_DEBUG): 1 = no A_lo x B_hi, 2 = no epilogue math
+   long long *trace;           // HFBGPU_TC_TRACE: clock64() timeline of the first pair (tools/tc_trace.py); else null
 };
+#define TC_TRACE_TILES 512
+#define TC_TR(role, tile, slot) do { if (p.trace && pair == 0 && (tile) < TC_TRACE_TILES) \
+      p.trace[((size_t)((role) * 2 + rank) * TC_TRACE_TILES + (tile)) * 16 + (slot)] = clock64(); } while (0)
 
 template <int MP>
 __global__ void __launch_bounds__(192, 1)
@@ -221,6 +229,7 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
    tc_fence_after();
    const uint32_t tmem = *tmemSlot;
    constexpr int SPT = TC_BN / MP;                      // states per tile
+   const int nChunks = (p.kSteps + 3) >> 2;             // 32-float K chunks that hold data
 
    if (warp == 0) {
       // ================= TMA producer: one box of MP rows per lane =================
@@ -239,10 +248,10 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
          for (int n = 0; n < nTiles; n++) {
             const int slot = n * SPT + bi;
             const int row = (lane < 2 * SPT && slot < u.J) ? (1 + ss[slot]) * MP : 0;   // rows [0,MP) = dummy state
-            for (int k = 0; k < 3; k++) {
-               if (lane == 0) { tc_mbar_wait(&emptyB[stage], phB ^ 1); tc_mbar_expect_tx(&fullB[stage], TC_B_STAGE_BYTES); }
+            for (int k = 0; k < nChunks; k++) {
+               if (lane == 0) { tc_mbar_wait(&emptyB[stage], phB ^ 1); tc_mbar_expect_tx(&fullB[stage], (p.dbg & 16) ? 0 : TC_B_STAGE_BYTES); }
                __syncwarp();
-               if (lane < 2 * SPT)
+               if (lane < 2 * SPT && !(p.dbg & 16))
                   tc_tma_load_2d(sB + stage * TC_B_STAGE_BYTES + half * 16384 + bi * (MP * 128),
                                  half ? &mapBlo : &mapBhi, &fullB[stage], k * 32, row);
                if (++stage == TC_STAGES) { stage = 0; phB ^= 1; }
@@ -266,19 +275,20 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
                tc_mbar_wait(&tmemEmpty[as], phT ^ 1);
                tc_fence_after();
                const uint32_t dMain = tmem + as * (2 * TC_BN), dCorr = dMain + TC_BN;
-               for (int k = 0; k < 3; k++) {
+               for (int k = 0; k < nChunks; k++) {
                   tc_mbar_wait(&fullB[stage], phB);
                   tc_fence_after();
                   const uint32_t bHi = bBase + stage * TC_B_STAGE_BYTES;
                   const uint32_t aHi = aBase + k * 16384, aLo = aBase + (3 + k) * 16384;
 #pragma unroll
                   for (int kk = 0; kk < 4; kk++) {
+                     if (k * 4 + kk >= p.kSteps) break;  // columns >= 2D+2 are zero padding
                      const uint64_t dAhi = tc_smem_desc(aHi + kk * 32), dAlo = tc_smem_desc(aLo + kk * 32);
                      const uint64_t dBhi = tc_smem_desc(bHi + kk * 32);
                      // A_hi x [B_hi ; B_lo]: the stage holds hi and lo back to back = one N=256 operand,
                      // columns [0,128) -> main accumulator, [128,256) -> correction accumulator
-                     tc_mma_tf32(dMain, dAhi, dBhi, idesc2, (k | kk) ? 1u : 0u);
-                     tc_mma_tf32(dCorr, dAlo, dBhi, idesc, 1u);
+                     if (!(p.dbg & 8)) tc_mma_tf32(dMain, dAhi, dBhi, idesc2, (k | kk) ? 1u : 0u);
+                     if (!(p.dbg & 9)) tc_mma_tf32(dCorr, dAlo, dBhi, idesc, 1u);
                   }
                   tc_commit(&emptyB[stage]);            // stage reusable once these MMAs retire
                   if (++stage == TC_STAGES) { stage = 0; phB ^= 1; }
@@ -308,6 +318,7 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
             float cmx = -INFINITY, csum = 0.f;          // carry for states wider than one 32-column chunk
 #pragma unroll
             for (int c = 0; c < TC_BN / 32; c++) {
+               if (p.dbg & 2) break;
                float v[32], vc[32];
                tc_tmem_ld32(taddr + c * 32, v);
                tc_tmem_ld32(taddr + TC_BN + c * 32, vc);
@@ -348,6 +359,277 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
    if (warp == 1) {
       tc_fence_after();
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+   }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair version (tcgen05 cta_group::2, UMMA M = 256)
+//
+// Measured on B200 (tools/tc_experiments.sh): the single-CTA kernel above is bound by the B
+// operand stream -- 96 KB from L2 per 128 x 128 tile, 6.6 TB/s chip-wide -- not by the MMAs
+// (dropping 17 % or 33 % of them does not change its time) nor by the epilogue.  A CTA pair shares
+// one B tile between two 128-frame blocks of the same utterance: each CTA keeps its own A block
+// and loads only HALF of every B stage (64 of the 128 mixture components, hi and lo = 16 KB),
+// the leader CTA issues M = 256 MMAs that read both halves, and each CTA's TMEM receives the
+// accumulators of its own 128 frames.  L2 -> SM bytes and shared-memory fill per SM halve, and the
+// smaller stage allows an 8-deep TMA ring.
+//
+// Three N = 128 MMAs per K step (instead of N = 256 + N = 128): A_hi x B_hi -> main accumulator,
+// A_hi x B_lo and A_lo x B_hi -> correction accumulator; in cta_group::2 mode each CTA supplies
+// N/2 = 64 rows of B at the descriptor address, so the stage is laid out [hi half | lo half].
+// Barrier protocol (CUTLASS PipelineTmaUmmaAsync): TMA loads of both CTAs complete on the LEADER's
+// full barriers (which expect the bytes of both), the leader's tcgen05.commit multicasts the
+// "stage empty" / "accumulator full" arrivals to both CTAs, and the epilogue warps of both CTAs
+// arrive on the leader's "accumulator empty" barrier.
+// ------------------------------------------------------------------------------------------
+#define TC2_STAGES 8
+#define TC2_B_STAGE_BYTES 16384
+#define TC2_SMEM_BYTES (TC_A_BYTES + TC2_STAGES * TC2_B_STAGE_BYTES + 512 + 1024)
+#define TC_PEER_MASK 0xFEFFFFFFu      // clears the CTA-rank bit of a shared::cluster address (cute::Sm100MmaPeerBitMask)
+
+__device__ __forceinline__ uint32_t tc_cluster_ctarank()
+{
+   uint32_t r;
+   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+   return r;
+}
+__device__ __forceinline__ void tc_cluster_sync()
+{
+   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion is signalled on the barrier of the pair's leader CTA
+__device__ __forceinline__ void tc_tma_load_2d_pair(void *smemDst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
+{
+   asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                ::"r"(tc_smem_u32(smemDst)), "l"((uint64_t)map), "r"(tc_smem_u32(bar) & TC_PEER_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
+{
+   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                ::"r"(tmemD), "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (once all prior MMAs of the pair have retired) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar)
+{
+   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                ::"r"(tc_smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on the leader CTA's copy of the barrier (works from either CTA of the pair)
+__device__ __forceinline__ void tc_mbar_arrive_leader(uint64_t *bar)
+{
+   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(tc_smem_u32(bar) & TC_PEER_MASK) : "memory");
+}
+
+template <int MP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+               const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, TcParams p)
+{
+   extern __shared__ uint8_t tc_smem_raw[];
+   uint8_t *base = (uint8_t *)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+   uint8_t *sA = base;                                  // [hi k0,k1,k2 | lo k0,k1,k2] x 16 KB: this CTA's 128 frames
+   uint8_t *sB = base + TC_A_BYTES;                     // stages x [hi 8 KB | lo 8 KB]: this CTA's 64 components
+   uint64_t *bars = (uint64_t *)(sB + TC2_STAGES * TC2_B_STAGE_BYTES);
+   uint64_t *fullA = bars, *emptyA = bars + 1, *fullB = bars + 2, *emptyB = bars + 2 + TC2_STAGES;
+   uint64_t *tmemFull = bars + 2 + 2 * TC2_STAGES, *tmemEmpty = tmemFull + 2;
+   uint32_t *tmemSlot = (uint32_t *)(tmemEmpty + 2);
+   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const uint32_t rank = tc_cluster_ctarank();          // 0 = leader (issues the MMAs)
+   const int pair = blockIdx.x >> 1, nPairs = gridDim.x >> 1;
+
+   if (warp == 0 && lane == 0) {
+      tc_mbar_init(fullA, 1); tc_mbar_init(emptyA, 1);
+      for (int s = 0; s < TC2_STAGES; s++) { tc_mbar_init(&fullB[s], 1); tc_mbar_init(&emptyB[s], 1); }
+      for (int s = 0; s < 2; s++) { tc_mbar_init(&tmemFull[s], 1); tc_mbar_init(&tmemEmpty[s], 8); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   if (warp == 1) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmemSlot)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+   }
+   tc_fence_before();
+   tc_cluster_sync();                                   // barriers initialised and TMEM allocated in both CTAs
+   tc_fence_after();
+   const uint32_t tmem = *tmemSlot;
+   constexpr int SPT = TC_BN / MP;                      // states per tile
+   constexpr int HB = (SPT >= 2) ? SPT / 2 : 1;         // B boxes per operand half held by one CTA
+   constexpr int BOXR = (MP < 64) ? MP : 64;            // rows per box (the B tensor maps are built with this)
+   const int nChunks = (p.kSteps + 3) >> 2;
+
+   if (warp == 0) {
+      // ================= TMA producer (both CTAs): own A block, own half of every B stage =================
+      // The warp stays converged: every lane knows the row of "its" box, the rows travel by shuffle and ONE
+      // elected lane issues all copies of a stage back to back with warp-uniform operands.  (Per-lane issue
+      // from a divergent warp costs ~100 cycles per cp.async.bulk.tensor -- the compiler serialises the
+      // lanes through ELECT + R2UR.BROADCAST -- and made the producer, not the MMAs, the bottleneck.)
+      uint32_t elected;
+      asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
+      uint32_t stage = 0, phB = 0, phA = 0, ptile = 0;
+      for (int it = pair; it < p.nItems; it += nPairs) {
+         const int2 item = p.items[it];
+         const UttDesc u = p.utt[item.x];
+         const int row0 = (int)u.featOff + item.y + (int)rank * TC_BM;
+         tc_mbar_wait(emptyA, phA ^ 1);
+         if (elected) {
+            if (rank == 0) tc_mbar_expect_tx(fullA, 2 * TC_A_BYTES);
+#pragma unroll
+            for (int j = 0; j < 6; j++) tc_tma_load_2d_pair(sA + j * 16384, j < 3 ? &mapAhi : &mapAlo, fullA, (j % 3) * 32, row0);
+         }
+         __syncwarp();
+         phA ^= 1;
+         const int nTiles = (u.J + SPT - 1) / SPT;
+         const int *ss = p.slotState + u.slotOff;
+         const int bi = lane % HB;                              // lanes [0,HB): hi boxes, [HB,2HB): lo boxes
+         auto box_row = [&](int n) {
+            int row = 0;                                        // rows [0,MP) = dummy state
+            if (lane < 2 * HB && n < nTiles) {
+               if (SPT >= 2) { const int slot = n * SPT + (int)rank * HB + bi; if (slot < u.J) row = (1 + ss[slot]) * MP; }
+               else row = (1 + ss[n]) * MP + (int)rank * 64;    // MP = 128: each CTA takes 64 rows of the state
+            }
+            return row;
+         };
+         int rowNext = box_row(0);
+         for (int n = 0; n < nTiles; n++, ptile++) {
+            const int row = rowNext;
+            rowNext = box_row(n + 1);                           // the state lookup of the next tile is in flight meanwhile
+            for (int k = 0; k < nChunks; k++) {
+               if (elected) TC_TR(2, ptile, k * 2);
+               tc_mbar_wait(&emptyB[stage], phB ^ 1);
+               if (elected) TC_TR(2, ptile, k * 2 + 1);
+               if (elected && rank == 0) tc_mbar_expect_tx(&fullB[stage], 2 * TC2_B_STAGE_BYTES);
+               uint8_t *dst = sB + stage * TC2_B_STAGE_BYTES;
+#pragma unroll
+               for (int j = 0; j < 2 * HB; j++) {
+                  const int rj = __shfl_sync(0xffffffffu, row, j);
+                  if (elected)
+                     tc_tma_load_2d_pair(dst + (j / HB) * 8192 + (j % HB) * (BOXR * 128), (j / HB) ? &mapBlo : &mapBhi,
+                                         &fullB[stage], k * 32, rj);
+               }
+               __syncwarp();
+               if (++stage == TC2_STAGES) { stage = 0; phB ^= 1; }
+            }
+         }
+      }
+   } else if (warp == 1) {
+      // ================= MMA issuer: one thread of the leader CTA =================
+      // The whole warp runs the loop so that the descriptor arithmetic stays warp-uniform (uniform
+      // datapath, no per-MMA R2UR chains: measured 130 -> ~103 cycles per MMA); one elected lane issues.
+      if (rank == 0) {
+         uint32_t elected;
+         asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
+         const uint32_t idesc = tc_idesc(2 * TC_BM, TC_BN);
+         const uint32_t aBase = tc_smem_u32(sA), bBase = tc_smem_u32(sB);
+         uint32_t stage = 0, phB = 0, phA = 0, tile = 0;
+         for (int it = pair; it < p.nItems; it += nPairs) {
+            const int2 item = p.items[it];
+            const UttDesc u = p.utt[item.x];
+            const int nTiles = (u.J + SPT - 1) / SPT;
+            tc_mbar_wait(fullA, phA);
+            phA ^= 1;
+            for (int n = 0; n < nTiles; n++, tile++) {
+               const uint32_t as = tile & 1, phT = (tile >> 1) & 1;
+               if (elected) TC_TR(0, tile, 0);
+               tc_mbar_wait(&tmemEmpty[as], phT ^ 1);
+               if (elected) TC_TR(0, tile, 1);
+               tc_fence_after();
+               const uint32_t dMain = tmem + as * (2 * TC_BN), dCorr = dMain + TC_BN;
+               for (int k = 0; k < nChunks; k++) {
+                  if (elected) TC_TR(0, tile, 2 + 2 * k);
+                  tc_mbar_wait(&fullB[stage], phB);
+                  if (elected) TC_TR(0, tile, 3 + 2 * k);
+                  tc_fence_after();
+                  const uint32_t bHi = bBase + stage * TC2_B_STAGE_BYTES, bLo = bHi + 8192;
+                  const uint32_t aHi = aBase + k * 16384, aLo = aBase + (3 + k) * 16384;
+#pragma unroll
+                  for (int kk = 0; kk < 4; kk++) {
+                     if (k * 4 + kk >= p.kSteps) break;  // columns >= 2D+2 are zero padding
+                     const uint64_t dAhi = tc_smem_desc(aHi + kk * 32), dAlo = tc_smem_desc(aLo + kk * 32);
+                     const uint64_t dBhi = tc_smem_desc(bHi + kk * 32), dBlo = tc_smem_desc(bLo + kk * 32);
+                     if (elected) {
+                        tc_mma_tf32_pair(dMain, dAhi, dBhi, idesc, (k | kk) ? 1u : 0u);
+                        tc_mma_tf32_pair(dCorr, dAhi, dBlo, idesc, (k | kk) ? 1u : 0u);
+                        tc_mma_tf32_pair(dCorr, dAlo, dBhi, idesc, 1u);
+                     }
+                  }
+                  if (elected) tc_commit_pair(&emptyB[stage]);   // stage reusable (in both CTAs) once these MMAs retire
+                  __syncwarp();
+                  if (++stage == TC2_STAGES) { stage = 0; phB ^= 1; }
+               }
+               if (elected) tc_commit_pair(&tmemFull[as]);       // accumulators ready for both CTAs' epilogues
+               __syncwarp();
+               if (elected) TC_TR(0, tile, 8);
+            }
+            if (elected) tc_commit_pair(emptyA);                 // A blocks reusable
+            __syncwarp();
+         }
+      }
+   } else {
+      // ================= epilogue (both CTAs): own 128 frames x 128 components =================
+      const int quad = warp & 3;                        // TMEM lane quadrant this warp may read
+      const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+      uint32_t tile = 0;
+      for (int it = pair; it < p.nItems; it += nPairs) {
+         const int2 item = p.items[it];
+         const UttDesc u = p.utt[item.x];
+         const int nTiles = (u.J + SPT - 1) / SPT;
+         const int t = item.y + (int)rank * TC_BM + quad * 32 + lane;
+         float *brow = p.b + u.bOff + (size_t)t * u.J;
+         for (int n = 0; n < nTiles; n++, tile++) {
+            const uint32_t as = tile & 1, phT = (tile >> 1) & 1;
+            if (warp == 2 && lane == 0) TC_TR(1, tile, 0);
+            tc_mbar_wait(&tmemFull[as], phT);
+            if (warp == 2 && lane == 0) TC_TR(1, tile, 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem + as * (2 * TC_BN) + ((uint32_t)(quad * 32) << 16);
+            const float C0 = p.C0;
+            float cmx = -INFINITY, csum = 0.f;          // carry for states wider than one 32-column chunk
+#pragma unroll
+            for (int c = 0; c < TC_BN / 32; c++) {
+               if (p.dbg & 2) break;
+               float v[32], vc[32];
+               tc_tmem_ld32(taddr + c * 32, v);
+               tc_tmem_ld32(taddr + TC_BN + c * 32, vc);
+#pragma unroll
+               for (int i = 0; i < 32; i++) v[i] += vc[i];
+               constexpr int G = (MP < 32) ? MP : 32;   // columns of one state inside this chunk
+#pragma unroll
+               for (int s0 = 0; s0 < 32; s0 += G) {
+                  float mx = v[s0];
+#pragma unroll
+                  for (int i = 1; i < G; i++) mx = fmaxf(mx, v[s0 + i]);
+                  float sum = 0.f;
+                  const float mb = mx * LOG2E;
+#pragma unroll
+                  for (int i = 0; i < G; i++) sum += tc_ex2(fmaf(v[s0 + i], LOG2E, -mb));
+                  if (MP > 32) {                        // merge into the carry
+                     float nm = fmaxf(cmx, mx);
+                     csum = csum * tc_ex2((cmx - nm) * LOG2E) + sum * tc_ex2((mx - nm) * LOG2E);
+                     cmx = nm; mx = cmx; sum = csum;
+                  }
+                  const int colEnd = c * 32 + s0 + G;   // columns consumed so far
+                  if (colEnd % MP == 0) {
+                     const int slot = n * SPT + colEnd / MP - 1;
+                     float val = (mx < -1.0e29f) ? (float)HFB_LZERO : fmaf(tc_lg2(sum), LN2, mx - C0);
+                     if (t < u.T && slot < u.J) brow[slot] = val;
+                     cmx = -INFINITY; csum = 0.f;
+                  }
+               }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive_leader(&tmemEmpty[as]);
+            if (warp == 2 && lane == 0) TC_TR(1, tile, 2);
+         }
+      }
+   }
+   tc_fence_before();
+   tc_cluster_sync();                                   // neither CTA leaves while the other may still signal it
+   if (warp == 1) {
+      tc_fence_after();
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
    }
 }
 
@@ -471,12 +753,20 @@ static inline int gmm_tc_prepare(GmmTcModel &t, const hfb_model *m, cudaStream_t
    TC_SET_SMEM(8); TC_SET_SMEM(16); TC_SET_SMEM(32); TC_SET_SMEM(64); TC_SET_SMEM(128);
 #undef TC_SET_SMEM
    t.ready = (cudaGetLastError() == cudaSuccess);
+   if (t.ready && tc_make_map(fn, &t.mapBhiP, t.dBhi, t.rows, std::min(MP, 64)) == HFB_OK &&
+       tc_make_map(fn, &t.mapBloP, t.dBlo, t.rows, std::min(MP, 64)) == HFB_OK) {
+#define TC_SET_SMEM(MPV) cudaFuncSetAttribute(gmm_tc2_kernel<MPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES)
+      TC_SET_SMEM(8); TC_SET_SMEM(16); TC_SET_SMEM(32); TC_SET_SMEM(64); TC_SET_SMEM(128);
+#undef TC_SET_SMEM
+      t.pairReady = (cudaGetLastError() == cudaSuccess);
+   }
    return HFB_OK;
 }
 
 // Launches expansion + GEMM for every utterance of the wave.  `items` lives in the wave blob.
 static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm, const Wave &W, long long waveFrames,
-                                const int2 *dItems, int nItems, int smCount, cudaStream_t st, int *launches)
+                                const int2 *dItems, int nItems, const int2 *dItems2, int nItems2, int smCount,
+                                cudaStream_t st, int *launches)
 {
    if (!t.ready) return HFB_EUNSUPPORTED;
    if (nItems == 0) return HFB_OK;
@@ -498,6 +788,33 @@ static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm
    gmm_tc_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W.feat, t.dOffset, dm.D, waveFrames, wk.dAhi, wk.dAlo);
    TcParams p;
    p.items = dItems; p.nItems = nItems; p.utt = W.utt; p.slotState = W.slotState; p.b = W.b; p.GPS = t.GPS; p.C0 = t.C0;
+   p.kSteps = (2 * dm.D + 2 + 7) / 8;
+   { const char *e = getenv("HFBGPU_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; if (p.dbg & 4) p.kSteps = 12; }
+   p.trace = nullptr;
+   const char *traceFile = getenv("HFBGPU_TC_TRACE");
+   const size_t traceN = (size_t)6 * TC_TRACE_TILES * 16;
+   if (traceFile) { cudaMalloc(&p.trace, traceN * sizeof(long long)); cudaMemsetAsync(p.trace, 0, traceN * sizeof(long long), st); }
+   if (launches) *launches = 2;
+   if (t.pairReady && smCount >= 2 && !getenv("HFBGPU_NO_PAIR")) {
+      // CTA pairs: one work item = (utterance, 256 frames), 128 per CTA
+      p.items = dItems2; p.nItems = nItems2;
+      const int grid2 = 2 * std::min(nItems2, smCount / 2);
+      switch (t.MP) {
+      case 8: gmm_tc2_kernel<8><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
+      case 16: gmm_tc2_kernel<16><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
+      case 32: gmm_tc2_kernel<32><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
+      case 64: gmm_tc2_kernel<64><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
+      default: gmm_tc2_kernel<128><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
+      }
+      if (traceFile) {                                  // diagnostics only: synchronous dump of the timeline
+         std::vector<long long> h(traceN);
+         cudaStreamSynchronize(st);
+         cudaMemcpy(h.data(), p.trace, traceN * sizeof(long long), cudaMemcpyDeviceToHost);
+         cudaFree(p.trace);
+         if (FILE *f = fopen(traceFile, "wb")) { fwrite(h.data(), sizeof(long long), traceN, f); fclose(f); }
+      }
+      return HFB_OK;
+   }
    int grid = std::min(nItems, smCount);
    switch (t.MP) {
    case 8: gmm_tc_kernel<8><<<grid, 192, TC_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhi, t.mapBlo, p); break;
@@ -506,6 +823,5 @@ static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm
    case 64: gmm_tc_kernel<64><<<grid, 192, TC_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhi, t.mapBlo, p); break;
    default: gmm_tc_kernel<128><<<grid, 192, TC_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhi, t.mapBlo, p); break;
    }
-   if (launches) *launches = 2;
    return HFB_OK;
 }
