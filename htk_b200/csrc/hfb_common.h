@@ -77,6 +77,7 @@ struct Wave {                       // everything the kernels of one wave need
    int *slotState;                  // tied state of each slot
    int *posSlot;                    // slot of each emitting position
    int *posState;                   // tied state of each emitting position
+   int *posQ;                       // model (label) index of each emitting position
    const float *feat;               // [frames][D]
    float *b;
    double *beta;

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(128) prep_kernel(DevModel M, Wave W)
    if (sStatus != 0) { if (tid == 0) { out->status = sStatus; out->J = 0; } return; }
    for (int q = tid; q < Q; q += nt) {
       const int p = lab[q], n = mN[q] - 2, so = M.hmmStateOff[p], po = mPoff[q];
-      for (int j = 0; j < n; j++) posState[po + j] = M.hmmState[so + j];
+      for (int j = 0; j < n; j++) { posState[po + j] = M.hmmState[so + j]; W.posQ[u->posOff + po + j] = q; }
    }
    __syncthreads();
    // the reference evaluates each tied state once per frame (HFB.c:910-912): find the first

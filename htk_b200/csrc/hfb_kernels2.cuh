@@ -220,65 +220,33 @@ __device__ __forceinline__ float warp_sum_nz(float v)
    return v;
 }
 
-__device__ unsigned long long g_dbg[8];
 
-__global__ void __launch_bounds__(32 * ST_WARPS)
-stats3_kernel(DevModel M, Wave W)
+// Everything stats3/stats4 need to know about "their" emitting state position
+struct StatPos {
+   const double *alphaJ, *aent, *betaU;
+   const float *bU, *A;
+   const int *ps;
+   const short *qLo, *qHi;
+   double *tacc, *oacc;
+   double pr;
+   int P, S, Q, J, T, N, so, sq1, j, q;
+   float aEntJ, aExitJ, aTee;
+};
+
+// SetOcct + UpTranParms (HFB.c:399-418, :1371-1423) for frame t = chunk start + lane of one position:
+// occupancy of state j, transitions entry->j, j->j2, j->exit and, for the first emitting state, the
+// model-level terms; warp-reduced so that one atomic per chunk reaches the (hot) transition accumulators.
+__device__ __forceinline__ void stats_tran_chunk(const StatPos &c, int t, bool inb, int lane)
 {
-   extern __shared__ __align__(16) unsigned char smraw[];
-   const int wInB = threadIdx.x >> 5, lane = threadIdx.x & 31;
-   const int wg = blockIdx.x * ST_WARPS + wInB;
-   if (wg >= W.totalPos) return;
-   const int ui = upper_index(W.posPre, W.numUtt, wg);
-   if (W.out[ui].status != 0) return;
-   const UttDesc u = W.utt[ui];
-   const int lp = wg - W.posPre[ui];
-   const int q = upper_index(W.mPoff + u.modOff, u.Q, lp);
-   const int gq = u.modOff + q;
-   const int j = lp - W.mPoff[gq];                     // emitting index 0..N-3
-   const int tmin = W.mTmin[gq], tmax = W.mTmax[gq];
-   if (tmin > tmax) return;
-   const int D = M.D, Dp = M.Dp, P = u.P, S = u.S, Q = u.Q, J = u.J, T = u.T, ostr = stats_ostride(D);
-   const size_t perWarp = sizeof(float) * ((size_t)32 * ostr + 32 * 33) + sizeof(double) * 32 + sizeof(int) * 32;
-   unsigned char *mine = smraw + perWarp * wInB;
-   double *x0s = (double *)mine;                       // [32] initx / log occupancy per chunk frame
-   float *os = (float *)(x0s + 32);                    // [32][ostr] observation rows
-   float *lrs = os + 32 * ostr;                        // [32 mixtures][33] occupancies Lr
-   int *ts = (int *)(lrs + 32 * 33);                   // [32] frame numbers
-
-   const int N = W.mN[gq], so = W.mSoff[gq];
-   const int s = W.posState[u.posOff + lp];
-   const int mo = M.stateMixOff[s], Mn = M.stateMixOff[s + 1] - mo;
-   const float *A = M.transLogA + W.mTrans[gq];
-   const int *ps = W.posSlot + u.posOff + W.mPoff[gq];
-   const double *alphaJ = W.occ + u.occOff + lp, *aent = W.aent + u.aentOff + q;
-   const double *betaU = W.beta + u.betaOff;
-   const float *bU = W.b + u.bOff;
-   const short *sqA = W.sq + u.frameBase, *eqA = W.eq + u.frameBase;
-   const short *qLo = W.qLo + u.frameBase, *qHi = W.qHi + u.frameBase;
-   const float *feat = W.feat + (size_t)u.featOff * D;
-   const double pr = W.out[ui].pr, minF = W.minFrwdP;
-   const int uf = W.uFlags;
-   const bool upM = (uf & HFB_UPMEANS) != 0, upV = (uf & HFB_UPVARS) != 0, upW = (uf & HFB_UPMIXES) != 0;
-   const bool doMix = upM || upV || upW, doTr = (uf & HFB_UPTRANS) != 0;
-   const float aEntJ = A[1 + j], aExitJ = A[(1 + j) * N + N - 1], aTee = A[N - 1];
-   const int sq1 = (q < Q - 1) ? W.mSoff[gq + 1] : 0;  // column offset of the next model
-   double *tacc = W.acc + W.mTrAcc[gq], *oacc = W.acc + W.mTrOcc[gq];
-   const int k0 = lane, k1 = lane + 32;                // D <= 64 (checked at create)
-   double wsum = 0.0;
-
-   for (int t0 = tmin; t0 <= tmax; t0 += 32) {
-      const int t = t0 + lane;
-      const bool inb = (t <= tmax) && q >= sqA[t] && q <= eqA[t];
-      double x0 = OCC_SKIP;
-      if (inb) {
-         const double aj = alphaJ[(size_t)t * P];
-         const double *bq = betaU + (size_t)t * S + so;
-         const float bjt = bU[(size_t)t * J + ps[j]];
-         const double lg = aj + bq[1 + j] - pr;                              // log occupancy of state j
-         if (!(lg < -(minF + 0.25))) x0 = (Mn == 1) ? lg : lg - (double)bjt;  // :1575-1576 / initx :1480-1489
-      }
-      if (doTr) {
+   const double *alphaJ = c.alphaJ, *aent = c.aent, *betaU = c.betaU;
+   const float *bU = c.bU, *A = c.A;
+   const int *ps = c.ps;
+   const short *qLo = c.qLo, *qHi = c.qHi;
+   double *tacc = c.tacc, *oacc = c.oacc;
+   const double pr = c.pr;
+   const int P = c.P, S = c.S, Q = c.Q, J = c.J, T = c.T, N = c.N, so = c.so, sq1 = c.sq1, j = c.j, q = c.q;
+   const float aEntJ = c.aEntJ, aExitJ = c.aExitJ, aTee = c.aTee;
+   {
          // ---- SetOcct / UpTranParms for this state (and, for j == 0, the model-level terms)
          float oJ = 0.f, tEnt = 0.f, tExit = 0.f, oEnt = 0.f, tTee = 0.f;
          const bool hasB1 = inb && (t + 1 < T) && q >= qLo[t + 1] && q <= qHi[t + 1];   // bqt1 != NULL
@@ -332,7 +300,72 @@ stats3_kernel(DevModel M, Wave W)
                }
             }
          }
+         }
+}
+
+__device__ unsigned long long g_dbg[8];
+
+__global__ void __launch_bounds__(32 * ST_WARPS)
+stats3_kernel(DevModel M, Wave W)
+{
+   extern __shared__ __align__(16) unsigned char smraw[];
+   const int wInB = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const int wg = blockIdx.x * ST_WARPS + wInB;
+   if (wg >= W.totalPos) return;
+   const int ui = upper_index(W.posPre, W.numUtt, wg);
+   if (W.out[ui].status != 0) return;
+   const UttDesc u = W.utt[ui];
+   const int lp = wg - W.posPre[ui];
+   const int q = upper_index(W.mPoff + u.modOff, u.Q, lp);
+   const int gq = u.modOff + q;
+   const int j = lp - W.mPoff[gq];                     // emitting index 0..N-3
+   const int tmin = W.mTmin[gq], tmax = W.mTmax[gq];
+   if (tmin > tmax) return;
+   const int D = M.D, Dp = M.Dp, P = u.P, S = u.S, Q = u.Q, J = u.J, T = u.T, ostr = stats_ostride(D);
+   const size_t perWarp = sizeof(float) * ((size_t)32 * ostr + 32 * 33) + sizeof(double) * 32 + sizeof(int) * 32;
+   unsigned char *mine = smraw + perWarp * wInB;
+   double *x0s = (double *)mine;                       // [32] initx / log occupancy per chunk frame
+   float *os = (float *)(x0s + 32);                    // [32][ostr] observation rows
+   float *lrs = os + 32 * ostr;                        // [32 mixtures][33] occupancies Lr
+   int *ts = (int *)(lrs + 32 * 33);                   // [32] frame numbers
+
+   const int N = W.mN[gq], so = W.mSoff[gq];
+   const int s = W.posState[u.posOff + lp];
+   const int mo = M.stateMixOff[s], Mn = M.stateMixOff[s + 1] - mo;
+   const float *A = M.transLogA + W.mTrans[gq];
+   const int *ps = W.posSlot + u.posOff + W.mPoff[gq];
+   const double *alphaJ = W.occ + u.occOff + lp, *aent = W.aent + u.aentOff + q;
+   const double *betaU = W.beta + u.betaOff;
+   const float *bU = W.b + u.bOff;
+   const short *sqA = W.sq + u.frameBase, *eqA = W.eq + u.frameBase;
+   const short *qLo = W.qLo + u.frameBase, *qHi = W.qHi + u.frameBase;
+   const float *feat = W.feat + (size_t)u.featOff * D;
+   const double pr = W.out[ui].pr, minF = W.minFrwdP;
+   const int uf = W.uFlags;
+   const bool upM = (uf & HFB_UPMEANS) != 0, upV = (uf & HFB_UPVARS) != 0, upW = (uf & HFB_UPMIXES) != 0;
+   const bool doMix = upM || upV || upW, doTr = (uf & HFB_UPTRANS) != 0;
+   const float aEntJ = A[1 + j], aExitJ = A[(1 + j) * N + N - 1], aTee = A[N - 1];
+   const int sq1 = (q < Q - 1) ? W.mSoff[gq + 1] : 0;  // column offset of the next model
+   double *tacc = W.acc + W.mTrAcc[gq], *oacc = W.acc + W.mTrOcc[gq];
+   const int k0 = lane, k1 = lane + 32;                // D <= 64 (checked at create)
+   double wsum = 0.0;
+   StatPos sp;
+   sp.alphaJ = alphaJ; sp.aent = aent; sp.betaU = betaU; sp.bU = bU; sp.A = A; sp.ps = ps; sp.qLo = qLo; sp.qHi = qHi;
+   sp.tacc = tacc; sp.oacc = oacc; sp.pr = pr; sp.P = P; sp.S = S; sp.Q = Q; sp.J = J; sp.T = T; sp.N = N; sp.so = so;
+   sp.sq1 = sq1; sp.j = j; sp.q = q; sp.aEntJ = aEntJ; sp.aExitJ = aExitJ; sp.aTee = aTee;
+
+   for (int t0 = tmin; t0 <= tmax; t0 += 32) {
+      const int t = t0 + lane;
+      const bool inb = (t <= tmax) && q >= sqA[t] && q <= eqA[t];
+      double x0 = OCC_SKIP;
+      if (inb) {
+         const double aj = alphaJ[(size_t)t * P];
+         const double *bq = betaU + (size_t)t * S + so;
+         const float bjt = bU[(size_t)t * J + ps[j]];
+         const double lg = aj + bq[1 + j] - pr;                              // log occupancy of state j
+         if (!(lg < -(minF + 0.25))) x0 = (Mn == 1) ? lg : lg - (double)bjt;  // :1575-1576 / initx :1480-1489
       }
+      if (doTr) stats_tran_chunk(sp, t, inb, lane);
       if (!doMix) continue;
       // ---- frames of this chunk that can contribute to the mixture statistics
       const bool valid = inb && x0 > -1.0e29;

@@ -1,0 +1,363 @@
+// hfb_stats_mma.cuh -- K4 with the occupancy-weighted sums on the tensor cores.
+//
+// UpMixParms (HTKLib/HFB.c:1426-1744) accumulates, per mixture component m of state j,
+//     occ += Lr,   mu[k] += Lr (o_t[k] - mean_m[k]),   var[k] += Lr (o_t[k] - mean_m[k])^2
+// over the frames where the state is inside the alpha beam and the component passes the
+// minimum-occupancy rule.  stats3_kernel does these sums on the FP32 pipe, ~14 warp instructions
+// per (component, frame).  Here they are the matrix product north_star asks for,
+//     [ S0 | S1 | S2 ](m, :) = Lr[m, t] x [ 1 | o_t - c_j | (o_t - c_j)^2 ][t, :],
+// evaluated with mma.sync.m16n8k8 (16 components x 8 frames x 8 dims), 3xTF32 (hi*hi + hi*lo + lo*hi,
+// FP32 accumulate, ~2^-21 relative).  The occupancy matrix of an utterance is ~2 % dense (alpha beam,
+// HFB.c:701-722), so the product runs only over the frames that survive -- a dense tcgen05 GEMM over
+// [all states x all frames] would do ~50x the work.
+//
+// STATE-MAJOR ORDER.  A position (one emitting state of one label) is inside the alpha beam for ~17
+// frames, but it updates 16 x (2 D + 3) accumulators: per-position flushing made the atomics and their
+// address arithmetic a third of the kernel.  So the positions of the whole wave are first bucketed by
+// tied state (statpos_* kernels: histogram, scan, scatter -- a counting sort), a warp takes a slice of
+// S5_CAP consecutive entries of the sorted list, keeps the accumulator fragments in registers across
+// positions and flushes only when the state changes: ~20x fewer flushes, and the Gaussian parameters
+// of a state are read by neighbouring warps at the same time.
+//
+// The reference centres on each component's own mean.  A matrix product needs ONE centre per row
+// block, so the sums are taken about the state's centre c_j (mean of its component means, uploaded
+// once) and moved to the component mean at flush time in FP64:
+//     mu  = S1 - d S0,    var = S2 - 2 d S1 + d^2 S0,    d = mean_m - c_j .
+// |d| is the spread of the components inside one state (~sigma), so the cancellation costs about
+// one bit -- unlike un-centred sums, which would lose mean^2/sigma^2.
+//
+// The component posteriors themselves (phase 1) keep stats3's code: reference operation order on the
+// FP32 pipe (IDOutP, HModel.c:5425-5430), lanes <-> (component, frame) pairs.
+#pragma once
+#include "hfb_kernels2.cuh"
+
+#define S4_WARPS 4
+#define S4_LSTR 36                    // row stride of the Lr tile: conflict-free A-fragment loads
+#define S4_CSTR 40                    // row stride of the state-centre table
+
+// TF32 split without the (quarter-rate) cvt.rna.tf32: the tensor core reads only the upper 19 bits of
+// an operand register, so v itself serves as "hi" (= v truncated) and lo = v - trunc(v) is exact in FP32
+// (13 significant bits, of which the tensor core keeps 11: ~2^-21 relative to v).
+__device__ __forceinline__ uint32_t s4_hi(float x) { return __float_as_uint(x); }
+__device__ __forceinline__ uint32_t s4_lo(float x)
+{
+   return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
+}
+__device__ __forceinline__ void s4_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+
+#define S5_CAP 16                     // sorted positions per warp
+
+// ---- counting sort of the wave's positions by tied state ------------------------------------------
+// cnt[J] must be zero on entry.  Only positions whose model was ever inside the alpha beam are listed.
+__global__ void __launch_bounds__(128) statpos_count_kernel(Wave W, int *__restrict__ cnt)
+{
+   const UttDesc &u = W.utt[blockIdx.x];
+   if (W.out[blockIdx.x].status != 0) return;
+   const int *posState = W.posState + u.posOff, *posQ = W.posQ + u.posOff;
+   const int *tmin = W.mTmin + u.modOff, *tmax = W.mTmax + u.modOff;
+   for (int pp = threadIdx.x; pp < u.P; pp += blockDim.x) {
+      const int q = posQ[pp];
+      if (tmin[q] <= tmax[q]) atomicAdd(&cnt[posState[pp]], 1);
+   }
+}
+// off[s] = exclusive prefix sum of cnt, off[J] = total; fill[] zeroed.  One CTA.
+__global__ void __launch_bounds__(1024) statpos_scan_kernel(const int *__restrict__ cnt, int *__restrict__ off,
+                                                            int *__restrict__ fill, int J)
+{
+   __shared__ int part[1024];
+   const int tid = threadIdx.x, per = (J + 1023) / 1024, b = tid * per, e = min(J, b + per);
+   int sum = 0;
+   for (int i = b; i < e; i++) sum += cnt[i];
+   part[tid] = sum;
+   __syncthreads();
+   for (int o = 1; o < 1024; o <<= 1) {
+      int v = (tid >= o) ? part[tid - o] : 0;
+      __syncthreads();
+      part[tid] += v;
+      __syncthreads();
+   }
+   int run = part[tid] - sum;
+   for (int i = b; i < e; i++) { off[i] = run; run += cnt[i]; fill[i] = 0; }
+   if (tid == 1023) off[J] = part[1023];
+}
+// Everything stats5 needs about one listed position, gathered here (in parallel over positions) so that
+// the statistics warp reads ONE flat record instead of chasing ~15 dependent table look-ups per position.
+struct __align__(16) PosRec {
+   long long alphaOff, aentOff, betaOff, bOff, frameBase, featOff, trAcc, trOcc;   // element offsets into the wave arrays
+   double pr;
+   int s, q, j, tmin, tmax, N, so, sq1, P, S, Q, J, T, transOff, utt, pad;
+   int ps[HFB_MAXN];                // output-probability slots of the model's emitting states
+};
+
+__global__ void __launch_bounds__(128) statpos_scatter_kernel(Wave W, const int *__restrict__ off, int *__restrict__ fill,
+                                                              PosRec *__restrict__ list)
+{
+   const UttDesc &u = W.utt[blockIdx.x];
+   if (W.out[blockIdx.x].status != 0) return;
+   const int *posState = W.posState + u.posOff, *posQ = W.posQ + u.posOff;
+   const int *tmin = W.mTmin + u.modOff, *tmax = W.mTmax + u.modOff;
+   for (int pp = threadIdx.x; pp < u.P; pp += blockDim.x) {
+      const int q = posQ[pp], gq = u.modOff + q;
+      if (tmin[q] <= tmax[q]) {
+         const int s = posState[pp];
+         PosRec r;
+         r.s = s; r.q = q; r.j = pp - W.mPoff[gq]; r.tmin = tmin[q]; r.tmax = tmax[q];
+         r.N = W.mN[gq]; r.so = W.mSoff[gq]; r.sq1 = (q < u.Q - 1) ? W.mSoff[gq + 1] : 0;
+         r.P = u.P; r.S = u.S; r.Q = u.Q; r.J = u.J; r.T = u.T; r.transOff = W.mTrans[gq]; r.utt = (int)blockIdx.x; r.pad = 0;
+         r.alphaOff = u.occOff + pp; r.aentOff = u.aentOff + q; r.betaOff = u.betaOff; r.bOff = u.bOff;
+         r.frameBase = u.frameBase; r.featOff = u.featOff; r.trAcc = W.mTrAcc[gq]; r.trOcc = W.mTrOcc[gq];
+         r.pr = W.out[blockIdx.x].pr;
+         const int *ps = W.posSlot + u.posOff + W.mPoff[gq];
+#pragma unroll
+         for (int i = 0; i < HFB_MAXN; i++) r.ps[i] = (i < r.N - 2) ? ps[i] : 0;
+         list[off[s] + atomicAdd(&fill[s], 1)] = r;
+      }
+   }
+}
+
+#define S5_GSTR 44                    // row stride (floats) of the staged Gaussian parameters: 16-byte aligned rows
+template <int NT>
+__host__ __device__ inline size_t stats5_warp_bytes(int D)
+{
+   const size_t work = sizeof(float) * ((size_t)32 * stats_ostride(D) + 16 * S4_LSTR);   // observations + Lr tile
+   const size_t flush = sizeof(float) * 16 * 16 * NT;                                    // [16][S1 | S2] staging
+   const size_t gauss = sizeof(float) * (2 * 16 * S5_GSTR + 32);                         // means, inverse variances, gconst, log weights
+   return sizeof(double) * 32 + sizeof(int) * 32 + ((((work > flush) ? work : flush) + 15) & ~(size_t)15) + gauss;
+}
+
+// NT = 8-column tiles of the right-hand side: columns 0..D-1 the dimensions, column D the ones column (D + 1 <= 8 NT)
+template <int NT>
+__global__ void __launch_bounds__(32 * S4_WARPS, 4)
+stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec *__restrict__ list,
+              const int *__restrict__ listEnd)
+{
+   extern __shared__ __align__(16) unsigned char smraw[];
+   const int wInB = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const int nSorted = *listEnd;
+   const int i0 = (blockIdx.x * S4_WARPS + wInB) * S5_CAP, i1 = min(nSorted, i0 + S5_CAP);
+   if (i0 >= i1) return;
+   const int D = M.D, Dp = M.Dp, ostr = stats_ostride(D);
+   unsigned char *mine = smraw + stats5_warp_bytes<NT>(D) * wInB;
+   double *x0s = (double *)mine;                       // [32] initx / log occupancy per chunk frame
+   int *ts = (int *)(x0s + 32);                        // [32] frame numbers
+   float *os = (float *)(ts + 32);                     // [32][ostr] observation rows
+   float *lrs = os + 32 * ostr;                        // [16 components][S4_LSTR] occupancies Lr
+   float *fb = os;                                     // flush staging [16][16 NT]
+   constexpr int FSTR = 16 * NT;
+   float *gmu = (float *)(mine + stats5_warp_bytes<NT>(D) - sizeof(float) * (2 * 16 * S5_GSTR + 32));
+   float *giv = gmu + 16 * S5_GSTR, *ggc = giv + 16 * S5_GSTR, *gwt = ggc + 16;   // the current state's 16 components
+   const double minF = W.minFrwdP;
+   const int uf = W.uFlags;
+   const bool upM = (uf & HFB_UPMEANS) != 0, upV = (uf & HFB_UPVARS) != 0, upW = (uf & HFB_UPMIXES) != 0;
+   const bool doMix = upM || upV || upW, doTr = (uf & HFB_UPTRANS) != 0;
+   // fragment coordinates (PTX ISA, mma.m16n8k8 .tf32): A rows g / g+8, cols c / c+4; B rows c / c+4, col g
+   const int fg = lane >> 2, fc = lane & 3;
+
+   for (int mb = 0; mb < M.maxM; mb += 16) {           // component tiles of 16 (one pass for M <= 16)
+      float acc1[NT][4], acc2[NT][4];                  // sum Lr (o - c), sum Lr (o - c)^2; column D of acc1 = sum Lr
+      float cenB[NT];                                  // centre of "my" right-hand-side column in each tile
+      int curS = -1, mo = 0, Mn = 0, Mc = 0;
+      bool any = false;
+
+      // moves the accumulated fragments of state curS to the FP64 accumulators (HFB.c:1665-1678, :1724-1736)
+      auto flush = [&]() {
+         __syncwarp();
+#pragma unroll
+         for (int nt = 0; nt < NT; nt++) {
+            const int col = nt * 8 + 2 * fc;
+            fb[fg * FSTR + col] = acc1[nt][0];            fb[fg * FSTR + col + 1] = acc1[nt][1];
+            fb[(fg + 8) * FSTR + col] = acc1[nt][2];      fb[(fg + 8) * FSTR + col + 1] = acc1[nt][3];
+            fb[fg * FSTR + 8 * NT + col] = acc2[nt][0];   fb[fg * FSTR + 8 * NT + col + 1] = acc2[nt][1];
+            fb[(fg + 8) * FSTR + 8 * NT + col] = acc2[nt][2]; fb[(fg + 8) * FSTR + 8 * NT + col + 1] = acc2[nt][3];
+         }
+         __syncwarp();
+         const float *cen = centre + (size_t)curS * S4_CSTR;
+         double wsum = 0.0;
+         for (int mi = 0; mi < Mc; mi++) {
+            const float *row = fb + mi * FSTR;
+            const double S0 = (double)row[D];
+            if (!(S0 > 0.0)) continue;                 // component never passed the minimum-occupancy rule
+            const int g = M.mixGauss[mo + mb + mi];
+            const int mId = M.meanId[g], vId = M.varId[g];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+               const int k = lane + 32 * h;
+               if (k < D) {
+                  const double d = (double)M.mean[(size_t)g * Dp + k] - (double)cen[k];
+                  const double s1 = (double)row[k], s2 = (double)row[8 * NT + k];
+                  if (upM) atomicAdd(&W.acc[M.L.muSum + (size_t)mId * D + k], s1 - d * S0);
+                  if (upV) atomicAdd(&W.acc[M.L.vaSum + (size_t)vId * D + k], s2 - 2.0 * d * s1 + d * d * S0);
+               }
+            }
+            if (lane == 0) {
+               if (upM) atomicAdd(&W.acc[M.L.muOcc + mId], S0);
+               if (upV) atomicAdd(&W.acc[M.L.vaOcc + vId], S0);
+               if (upW) atomicAdd(&W.acc[M.L.wtC + mo + mb + mi], S0);
+            }
+            wsum += S0;
+         }
+         if (lane == 0 && wsum > 0.0) atomicAdd(&W.acc[M.L.wtOcc + curS], wsum);
+         __syncwarp();
+      };
+
+      for (int it = i0; it < i1; it++) {
+         const PosRec &R = list[it];
+         if (it + 1 < i1) prefetch_l1(&list[it + 1]);
+         const int s = R.s;
+         if (s != curS) {
+            if (any) flush();
+            curS = s; any = false;
+            mo = M.stateMixOff[s]; Mn = M.stateMixOff[s + 1] - mo; Mc = min(16, Mn - mb);
+            const float *cen = centre + (size_t)s * S4_CSTR;
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) {
+               const int dim = nt * 8 + fg;
+               cenB[nt] = (dim < D) ? cen[dim] : 0.f;
+#pragma unroll
+               for (int i = 0; i < 4; i++) { acc1[nt][i] = 0.f; acc2[nt][i] = 0.f; }
+            }
+            // stage the tile's Gaussians in shared memory: every position of this state reads them from there
+            __syncwarp();
+            if (Mn > 1)
+               for (int e = lane; e < Mc * (Dp >> 2); e += 32) {
+                  const int mi = e / (Dp >> 2), k4 = e - mi * (Dp >> 2);
+                  const int g = M.mixGauss[mo + mb + mi];
+                  *reinterpret_cast<float4 *>(gmu + mi * S5_GSTR + 4 * k4) = *reinterpret_cast<const float4 *>(M.mean + (size_t)g * Dp + 4 * k4);
+                  *reinterpret_cast<float4 *>(giv + mi * S5_GSTR + 4 * k4) = *reinterpret_cast<const float4 *>(M.ivar + (size_t)g * Dp + 4 * k4);
+               }
+            if (lane < 16) {
+               const bool on = lane < Mc;
+               gwt[lane] = on ? M.mixLogWt[mo + mb + lane] : LZERO_D;
+               ggc[lane] = on ? M.gconst[M.mixGauss[mo + mb + lane]] : 0.f;
+            }
+            __syncwarp();
+         }
+         if (Mc <= 0) continue;                        // state has no components in this tile
+         const int q = R.q, j = R.j, tmin = R.tmin, tmax = R.tmax;
+         const int P = R.P, S = R.S, J = R.J, so = R.so;
+         const int *ps = R.ps;
+         const long long frameBase = R.frameBase;
+         const short *sqA = W.sq + frameBase, *eqA = W.eq + frameBase;
+         const float *feat = W.feat + (size_t)R.featOff * D;
+         StatPos sp;
+         const float *A = M.transLogA + R.transOff;
+         sp.alphaJ = W.occ + R.alphaOff; sp.aent = W.aent + R.aentOff; sp.betaU = W.beta + R.betaOff;
+         sp.bU = W.b + R.bOff; sp.A = A; sp.ps = ps; sp.qLo = W.qLo + frameBase; sp.qHi = W.qHi + frameBase;
+         sp.tacc = W.acc + R.trAcc; sp.oacc = W.acc + R.trOcc; sp.pr = R.pr;
+         sp.P = P; sp.S = S; sp.Q = R.Q; sp.J = J; sp.T = R.T; sp.N = R.N; sp.so = so;
+         sp.sq1 = R.sq1; sp.j = j; sp.q = q;
+         sp.aEntJ = A[1 + j]; sp.aExitJ = A[(1 + j) * R.N + R.N - 1]; sp.aTee = A[R.N - 1];
+         const double pr = sp.pr;
+
+         for (int t0 = tmin; t0 <= tmax; t0 += 32) {
+            const int t = t0 + lane;
+            const bool inb = (t <= tmax) && q >= sqA[t] && q <= eqA[t];
+            double x0 = OCC_SKIP;
+            if (inb) {
+               const double aj = sp.alphaJ[(size_t)t * P];
+               const double *bq = sp.betaU + (size_t)t * S + so;
+               const float bjt = sp.bU[(size_t)t * J + ps[j]];
+               const double lg = aj + bq[1 + j] - pr;                              // log occupancy of state j
+               if (!(lg < -(minF + 0.25))) x0 = (Mn == 1) ? lg : lg - (double)bjt;  // :1575-1576 / initx :1480-1489
+            }
+            if (doTr && mb == 0) stats_tran_chunk(sp, t, inb, lane);
+            if (!doMix) continue;
+            // ---- frames of this chunk that can contribute to the mixture statistics
+            const bool valid = inb && x0 > -1.0e29;
+            const unsigned mask = __ballot_sync(0xffffffffu, valid);
+            const int nT = __popc(mask);
+            if (nT == 0) continue;
+            const int nT8 = (nT + 7) & ~7;
+            __syncwarp();
+            if (valid) { int idx = __popc(mask & ((1u << lane) - 1)); ts[idx] = t; x0s[idx] = x0; }
+            for (int e = lane; e < 16 * S4_LSTR; e += 32) lrs[e] = 0.f;
+            __syncwarp();
+            for (int tb = 0; tb < nT8; tb += 8) {                  // observation rows, 8 at a time (16 loads in flight per
+               float v0[8], v1[8];                                 // lane); rows nT..nT8-1 are zero padding
+#pragma unroll
+               for (int r = 0; r < 8; r++) {
+                  const bool on = tb + r < nT;
+                  const float *src = feat + (size_t)ts[on ? tb + r : 0] * D;
+                  v0[r] = (on && lane < D) ? src[lane] : 0.f;
+                  v1[r] = (on && lane + 32 < D) ? src[lane + 32] : 0.f;
+               }
+#pragma unroll
+               for (int r = 0; r < 8; r++) {
+                  float *dst = os + (tb + r) * ostr;
+                  if (lane < D) dst[lane] = v0[r];
+                  if (lane + 32 < D) dst[lane + 32] = v1[r];
+               }
+            }
+            __syncwarp();
+            // ---- phase 1: lanes <-> (component, frame) pairs -> Lr tile
+            unsigned anyLr = 0;
+            for (int pi = lane; pi < ((Mc * nT + 31) & ~31); pi += 32) {
+               float Lr = 0.f;
+               const int mi = pi / nT, ti = pi - mi * nT;
+               if (mi < Mc) {
+                  const float wt = gwt[mi];
+                  if (wt > LMINMIX_F) {                                         // HFB.c:1573
+                     double x = x0s[ti];
+                     if (Mn > 1) {
+                        const float *mu = gmu + mi * S5_GSTR, *iv = giv + mi * S5_GSTR;
+                        const float *o = os + ti * ostr;
+                        float sum = ggc[mi];
+                        int k = 0;
+                        for (; k + 4 <= D; k += 4) {                            // staged rows are 16-byte aligned
+                           const float4 m4 = *reinterpret_cast<const float4 *>(mu + k);
+                           const float4 v4 = *reinterpret_cast<const float4 *>(iv + k);
+                           float d = __fsub_rn(o[k], m4.x);     sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), v4.x));
+                           d = __fsub_rn(o[k + 1], m4.y);       sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), v4.y));
+                           d = __fsub_rn(o[k + 2], m4.z);       sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), v4.z));
+                           d = __fsub_rn(o[k + 3], m4.w);       sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), v4.w));
+                        }
+                        for (; k < D; k++) {
+                           const float d = __fsub_rn(o[k], mu[k]);
+                           sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), iv[k]));
+                        }
+                     const float mixp = -0.5f * sum;
+                        x = (x + (double)wt) + (double)mixp;                    // :1581-1599
+                     }
+                     if (-x < minF) Lr = expf((float)x);                        // :1606, :1612
+                  }
+                  lrs[mi * S4_LSTR + ti] = Lr;
+               }
+               anyLr |= __ballot_sync(0xffffffffu, Lr > 0.f);
+            }
+            __syncwarp();
+            if (!anyLr) continue;
+            any = true;
+            // ---- phase 2: [16 components x nT frames] x [nT frames x (dims | 1)] on the tensor cores
+            for (int ks = 0; ks < nT8; ks += 8) {
+               uint32_t ah[4], al[4];
+               {
+                  const float a0 = lrs[fg * S4_LSTR + ks + fc], a1 = lrs[(fg + 8) * S4_LSTR + ks + fc];
+                  const float a2 = lrs[fg * S4_LSTR + ks + fc + 4], a3 = lrs[(fg + 8) * S4_LSTR + ks + fc + 4];
+                  ah[0] = s4_hi(a0); ah[1] = s4_hi(a1); ah[2] = s4_hi(a2); ah[3] = s4_hi(a3);
+                  al[0] = s4_lo(a0); al[1] = s4_lo(a1); al[2] = s4_lo(a2); al[3] = s4_lo(a3);
+               }
+               const float *o0 = os + (ks + fc) * ostr, *o1 = o0 + 4 * ostr;
+#pragma unroll
+               for (int nt = 0; nt < NT; nt++) {
+                  const int dim = nt * 8 + fg;
+                  float v0, v1;
+                  if (dim < D) { v0 = o0[dim] - cenB[nt]; v1 = o1[dim] - cenB[nt]; }
+                  else { v0 = v1 = (dim == D) ? 1.f : 0.f; }                    // the ones column gives sum Lr
+                  uint32_t h0 = s4_hi(v0), h1 = s4_hi(v1), l0 = s4_lo(v0), l1 = s4_lo(v1);
+                  s4_mma(acc1[nt], ah, h0, h1); s4_mma(acc1[nt], ah, l0, l1); s4_mma(acc1[nt], al, h0, h1);
+                  const float w0 = v0 * v0, w1 = v1 * v1;
+                  h0 = s4_hi(w0); h1 = s4_hi(w1); l0 = s4_lo(w0); l1 = s4_lo(w1);
+                  s4_mma(acc2[nt], ah, h0, h1); s4_mma(acc2[nt], ah, l0, l1); s4_mma(acc2[nt], al, h0, h1);
+               }
+            }
+         }
+      }
+      if (any) flush();
+   }
+}

@@ -20,6 +20,7 @@
 #include "hfb_kernels2.cuh"
 #include "hfb_fast.cuh"
 #include "hfb_l2r.cuh"
+#include "hfb_stats_mma.cuh"
 #include "gmm_tc.cuh"
 
 static thread_local std::string g_lastError;
@@ -103,6 +104,7 @@ struct hfbgpu_ctx {
    hfb_stats stats;
    // model on device
    DevBuf<float> dMean, dIvar, dGconst, dMixLogWt, dTransLogA;
+   DevBuf<float> dCentre;             // [J][S4_CSTR] centre of each tied state's component means (stats4_kernel)
    DevBuf<int> dMeanId, dVarId, dStateMixOff, dMixGauss;
    GmmTcModel tc;                    // expanded / split operands for the tcgen05 path
    // accumulators
@@ -119,6 +121,7 @@ struct hfbgpu_ctx {
       DevBuf<double> dBeta, dOcc, dAent;
       DevBuf<short> dBeams;             // 4 * frames
       DevBuf<unsigned char> dTables, dScratch;
+      DevBuf<int> dStateIdx;            // 3 x (J + 2): count / offset / fill arrays of the by-state position sort
       GmmTcWork tcw;
       std::vector<unsigned char> blob;
       unsigned char *hTables = nullptr; // pinned staging
@@ -344,6 +347,19 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
        (rc = upload(c->dTranOccOff, h.tranOccOff.data(), h.tranOccOff.size(), c->stream))) {
       hfbgpu_destroy(c); return rc;
    }
+   {  // state centres for the tensor-core statistics kernel (hfb_stats_mma.cuh)
+      std::vector<float> cen((size_t)h.J * S4_CSTR, 0.f);
+      if (D <= S4_CSTR)
+         for (int s2 = 0; s2 < h.J; s2++) {
+            const int o = h.stateMixOff[s2], n = h.stateMixOff[s2 + 1] - o;
+            for (int k = 0; k < D; k++) {
+               double a = 0.0;
+               for (int i = 0; i < n; i++) a += m->mean[(size_t)m->mixGauss[o + i] * D + k];
+               cen[(size_t)s2 * S4_CSTR + k] = (float)(a / std::max(n, 1));
+            }
+         }
+      if ((rc = upload(c->dCentre, cen.data(), cen.size(), c->stream))) { hfbgpu_destroy(c); return rc; }
+   }
    CK(cudaStreamSynchronize(c->stream));
    DevModel &d = c->dm;
    d.D = D; d.Dp = Dp; d.G = h.G; d.J = h.J; d.P = h.P; d.numTrans = h.numTrans; d.maxM = h.maxM;
@@ -379,6 +395,8 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
    cudaFuncSetAttribute(alpha_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(stats3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(beta_l2r_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
+   cudaFuncSetAttribute(stats5_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
+   cudaFuncSetAttribute(stats5_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    CK(cudaStreamSynchronize(c->stream));
    *out = c;
    return HFB_OK;
@@ -389,6 +407,7 @@ extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
    if (!c) return HFB_EINVAL;
    cudaSetDevice(c->device);
    if (c->stream) cudaStreamSynchronize(c->stream);
+   c->dCentre.release();
    c->dMean.release(); c->dIvar.release(); c->dGconst.release(); c->dMixLogWt.release(); c->dTransLogA.release();
    c->dMeanId.release(); c->dVarId.release(); c->dStateMixOff.release(); c->dMixGauss.release();
    gmm_tc_release(c->tc);
@@ -396,7 +415,7 @@ extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
    for (auto &sl : c->slot) {
       if (sl.stream) cudaStreamSynchronize(sl.stream);
       sl.dFeat.release(); sl.dB.release(); sl.dBeta.release(); sl.dOcc.release(); sl.dAent.release(); sl.dBeams.release();
-      sl.dTables.release(); sl.dScratch.release(); sl.tcw.release();
+      sl.dTables.release(); sl.dScratch.release(); sl.dStateIdx.release(); sl.tcw.release();
       if (sl.hTables) cudaFreeHost(sl.hTables);
       if (sl.hOut) cudaFreeHost(sl.hOut);
       if (sl.hBeams) cudaFreeHost(sl.hBeams);
@@ -526,7 +545,7 @@ size_t blob_put(std::vector<unsigned char> &blob, const std::vector<T> &v) { ret
 
 // device scratch written by prep_kernel / alpha kernel
 struct ScratchLayout {
-   size_t mN, mTrans, mSoff, mPoff, mDms, mPre, mSuf, mHmm, mTmin, mTmax, mTrAcc, mTrOcc, slotState, posSlot, posState, bytes;
+   size_t mN, mTrans, mSoff, mPoff, mDms, mPre, mSuf, mHmm, mTmin, mTmax, mTrAcc, mTrOcc, slotState, posSlot, posState, posQ, posList, bytes;
    ScratchLayout(long long totalQ, long long totalP)
    {
       size_t o = 0;
@@ -535,7 +554,7 @@ struct ScratchLayout {
       mTrAcc = take(q, 8); mTrOcc = take(q, 8);
       mN = take(q, 4); mTrans = take(q, 4); mSoff = take(q, 4); mPoff = take(q, 4); mDms = take(q, 4);
       mPre = take(q, 4); mSuf = take(q, 4); mHmm = take(q, 4); mTmin = take(q, 4); mTmax = take(q, 4);
-      slotState = take(pp, 4); posSlot = take(pp, 4); posState = take(pp, 4);
+      slotState = take(pp, 4); posSlot = take(pp, 4); posState = take(pp, 4); posQ = take(pp, 4); posList = take(pp, sizeof(PosRec));
       bytes = o;
    }
 };
@@ -600,7 +619,7 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
    W.mSuf = (int *)(sc + sl.mSuf); W.mHmm = (int *)(sc + sl.mHmm);
    W.mTrAcc = (long long *)(sc + sl.mTrAcc); W.mTrOcc = (long long *)(sc + sl.mTrOcc);
    W.mTmin = (int *)(sc + sl.mTmin); W.mTmax = (int *)(sc + sl.mTmax);
-   W.slotState = (int *)(sc + sl.slotState); W.posSlot = (int *)(sc + sl.posSlot); W.posState = (int *)(sc + sl.posState);
+   W.slotState = (int *)(sc + sl.slotState); W.posSlot = (int *)(sc + sl.posSlot); W.posState = (int *)(sc + sl.posState); W.posQ = (int *)(sc + sl.posQ);
    W.feat = dFeat;
    W.b = S.dB.p; W.beta = S.dBeta.p; W.occ = S.dOcc.p; W.aent = S.dAent.p;
    W.qLo = S.dBeams.p; W.qHi = W.qLo + waveFrames; W.sq = W.qHi + waveFrames; W.eq = W.sq + waveFrames;
@@ -676,7 +695,25 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
       c->stats.launches += 2; c->stats.launchesBeta++; c->stats.launchesAlpha++;
       // ---- K4
       if (w.totalP > 0 && c->opt.uFlags != 0) {
-         stats3_kernel<<<(unsigned)((w.totalP + ST_WARPS - 1) / ST_WARPS), 32 * ST_WARPS, stats_smem_bytes(c->dm.D), st>>>(c->dm, W);
+         const int Dd = c->dm.D;
+         // mixture sets: occupancy-weighted sums on the tensor cores (mma.sync 3xTF32); else the FP32 kernel
+         if (c->hm.maxM >= 4 && Dd + 1 <= 40 && !getenv("HFBGPU_STATS3")) {
+            // positions bucketed by tied state (counting sort), then S5_CAP sorted positions per warp
+            const int Jm = c->hm.J;
+            if ((rc = S.dStateIdx.reserve((size_t)3 * (Jm + 2)))) return rc;
+            int *cnt = S.dStateIdx.p, *off = cnt + (Jm + 2), *fill = off + (Jm + 2);
+            PosRec *list = (PosRec *)(sc + sl.posList);
+            CK(cudaMemsetAsync(cnt, 0, (size_t)(Jm + 2) * sizeof(int), st));
+            statpos_count_kernel<<<nU, 128, 0, st>>>(W, cnt);
+            statpos_scan_kernel<<<1, 1024, 0, st>>>(cnt, off, fill, Jm);
+            statpos_scatter_kernel<<<nU, 128, 0, st>>>(W, off, fill, list);
+            const unsigned nWarps = (unsigned)((w.totalP + S5_CAP - 1) / S5_CAP);
+            const unsigned grid = (nWarps + S4_WARPS - 1) / S4_WARPS;
+            if (Dd + 1 <= 32) stats5_kernel<4><<<grid, 32 * S4_WARPS, S4_WARPS * stats5_warp_bytes<4>(Dd), st>>>(c->dm, W, c->dCentre.p, list, off + Jm);
+            else stats5_kernel<5><<<grid, 32 * S4_WARPS, S4_WARPS * stats5_warp_bytes<5>(Dd), st>>>(c->dm, W, c->dCentre.p, list, off + Jm);
+            c->stats.launches += 3; c->stats.launchesStats += 3;
+         } else
+            stats3_kernel<<<(unsigned)((w.totalP + ST_WARPS - 1) / ST_WARPS), 32 * ST_WARPS, stats_smem_bytes(c->dm.D), st>>>(c->dm, W);
          c->stats.launches++; c->stats.launchesStats++;
       }
       if (tm) cudaEventRecord(S.ev[4], st);

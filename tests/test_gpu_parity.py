@@ -140,7 +140,10 @@ def test_batch_linearity_and_empty():
     bB = Batch.from_arrays(z["feat"], fo[k:], z["lab"], lo[k:])
     fb.FBFile(bA); fb.FBFile(bB)
     parts = fb.GetAccs()
-    assert np.allclose(whole, parts, rtol=1e-9, atol=1e-9)
+    # the statistics kernel sums FP32 fragments over the positions of a tied state in list order, which
+    # depends on how the utterances are grouped into calls: agreement to FP32 summation noise, not bitwise
+    e = acc_errors(parts, whole, fm)
+    assert max(e.values()) < 1e-5, e
     empty = Batch([], [], fm.D)
     r, _ = fb.FBFile(empty)
     assert r == [] and np.array_equal(parts, fb.GetAccs())
@@ -151,7 +154,8 @@ def test_small_workspace_waves_equal_single_wave():
     z, fm, b, kw = load_golden("synth_tied_m4")
     fb = _fb(fm, **kw); fb.FBFile(b); a1 = fb.GetAccs(); fb.close()
     fb = _fb(fm, workspace_bytes=3 << 20, **kw); fb.FBFile(b); a2 = fb.GetAccs(); fb.close()
-    assert np.allclose(a1, a2, rtol=1e-9, atol=1e-9)
+    e = acc_errors(a2, a1, fm)           # FP32 summation order differs between wave splits (see above)
+    assert max(e.values()) < 1e-5, e
 
 
 def test_properties_at_scale():
@@ -225,9 +229,23 @@ def test_generic_kernels_and_redo_path(name, hook, monkeypatch):
             assert abs(x.pr - y.pr) <= 1e-9 * abs(x.pr)
     for k in ("qLo", "qHi", "sq", "eq"):
         assert np.array_equal(getattr(b1, k), getattr(b2, k)), k
-    e = acc_errors(a2, a1, fm)
-    assert max(e.values()) < 1e-6, e
+    e = acc_errors(a2, a1, fm)             # identical alpha/beta; FP32 summation order of the statistics varies
+    assert max(e.values()) < 1e-5, e
     e = acc_errors(a2, z["ref_acc"], fm)
+    assert max(e.values()) < RTOL, e
+
+
+@pytest.mark.parametrize("name", ["synth_tied_m4", "synth_long_m3", "synth_tee_m2"])
+def test_tensor_core_statistics_equal_fp32_statistics(name, monkeypatch):
+    """stats4_kernel (occupancy-weighted sums as 3xTF32 mma products about the state centre) against
+    stats3_kernel (FP32 sums about each component's own mean, HFBGPU_STATS3) and the reference."""
+    z, fm, b, kw = load_golden(name)
+    fb = _fb(fm, **kw); fb.FBFile(b); a1 = fb.GetAccs(); fb.close()
+    monkeypatch.setenv("HFBGPU_STATS3", "1")
+    fb = _fb(fm, **kw); fb.FBFile(b); a2 = fb.GetAccs(); fb.close()
+    e = acc_errors(a1, a2, fm)
+    assert max(e.values()) < 5e-6, e
+    e = acc_errors(a1, z["ref_acc"], fm)
     assert max(e.values()) < RTOL, e
 
 
@@ -243,6 +261,7 @@ def test_submit_wait_equals_blocking_call():
     for tk in tickets:
         for x, y in zip(tk.results(), r0):
             assert x.status == y.status and abs(x.pr - y.pr) <= 1e-12 * abs(y.pr)
-    assert np.allclose(a1, a0, rtol=1e-9, atol=1e-9)
+    e = acc_errors(a1, a0, fm)
+    assert max(e.values()) < 1e-5, e
     assert tickets[1].beams.qHi.max() > 0
     fb.close()
