@@ -383,7 +383,7 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
 // "stage empty" / "accumulator full" arrivals to both CTAs, and the epilogue warps of both CTAs
 // arrive on the leader's "accumulator empty" barrier.
 // ------------------------------------------------------------------------------------------
-#define TC2_STAGES 8
+#define TC2_STAGES 6
 #define TC2_B_STAGE_BYTES 16384
 #define TC2_SMEM_BYTES (TC_A_BYTES + TC2_STAGES * TC2_B_STAGE_BYTES + 512 + 1024)
 #define TC_PEER_MASK 0xFEFFFFFFu      // clears the CTA-rank bit of a shared::cluster address (cute::Sm100MmaPeerBitMask)

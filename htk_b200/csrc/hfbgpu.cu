@@ -100,6 +100,10 @@ struct hfbgpu_ctx {
    hfb_acc_layout L;
    cudaStream_t stream = nullptr;    // stream of model uploads / accumulator copies (caller's if set)
    cudaStream_t ownStream = nullptr;
+   cudaStream_t gmmStream = nullptr;    // high priority: the tensor-core kernels of all waves, back to back
+   cudaEvent_t evRef = nullptr;         // HFBGPU_TRACE_KERNELS: time origin of the per-wave timeline on stderr
+   bool trace = false;
+   int waveUtts = 592;                  // utterances per wave (see launch_wave: recursions co-reside with the next GMM)
    bool timing = false;
    hfb_stats stats;
    // model on device
@@ -116,6 +120,7 @@ struct hfbgpu_ctx {
    struct Slot {
       cudaStream_t stream = nullptr;
       cudaEvent_t ev[6] = {};
+      cudaEvent_t evIn = nullptr, evGmm = nullptr;   // inputs uploaded / output probabilities ready
       DevBuf<float> dFeat;              // only for host-feature calls
       DevBuf<float> dB;
       DevBuf<double> dBeta, dOcc, dAent;
@@ -138,7 +143,7 @@ struct hfbgpu_ctx {
       long long waveFrame0 = 0, waveFrames = 0;
       bool wantBeams = false;
    };
-   static const int NSLOT = 2;
+   static const int NSLOT = 4;
    Slot slot[NSLOT];
    int numSlots = NSLOT;
    unsigned nextSlot = 0;
@@ -283,10 +288,21 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
    c->maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
    CK(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
    c->stream = c->ownStream;
+   {
+      int prLo = 0, prHi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+      CK(cudaStreamCreateWithPriority(&c->gmmStream, cudaStreamNonBlocking, prHi));
+   }
    for (auto &sl : c->slot) {
       CK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
       for (auto &e : sl.ev) CK(cudaEventCreate(&e));
+      CK(cudaEventCreateWithFlags(&sl.evIn, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&sl.evGmm, cudaEventDisableTiming));
    }
+   c->trace = getenv("HFBGPU_TRACE_KERNELS") != nullptr;
+   if (c->trace) { CK(cudaEventCreate(&c->evRef)); CK(cudaEventRecord(c->evRef, c->stream)); }
+   c->waveUtts = 16384;
+   if (const char *wu = getenv("HFBGPU_WAVE_UTTS")) c->waveUtts = std::max(1, atoi(wu));
    if (const char *ns = getenv("HFBGPU_STREAMS")) c->numSlots = std::max(1, std::min((int)hfbgpu_ctx::NSLOT, atoi(ns)));
 
    HostModel &h = c->hm;
@@ -420,11 +436,14 @@ extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
       if (sl.hOut) cudaFreeHost(sl.hOut);
       if (sl.hBeams) cudaFreeHost(sl.hBeams);
       for (auto &e : sl.ev) if (e) cudaEventDestroy(e);
+      if (sl.evIn) cudaEventDestroy(sl.evIn);
+      if (sl.evGmm) cudaEventDestroy(sl.evGmm);
       if (sl.stream) cudaStreamDestroy(sl.stream);
       delete sl.w;
    }
    c->dHmmN.release(); c->dHmmStateOff.release(); c->dHmmState.release(); c->dHmmTrans.release();
    c->dTransOffF.release(); c->dTransMinDur.release(); c->dTranAccOff.release(); c->dTranOccOff.release();
+   if (c->gmmStream) { cudaStreamSynchronize(c->gmmStream); cudaStreamDestroy(c->gmmStream); }
    if (c->ownStream) cudaStreamDestroy(c->ownStream);
    delete c;
    return HFB_OK;
@@ -628,10 +647,20 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
    W.minFrwdP = (double)c->opt.minFrwdP; W.uFlags = c->opt.uFlags;
 
    const bool tm = c->timing;
+   // Experiment kept behind HFBGPU_GMM_STREAM=1 (+ HFBGPU_WAVE_UTTS=592): the table-building and tensor-core
+   // kernels of ALL waves go through one high-priority stream, back to back, so that the latency-bound
+   // beta/alpha CTAs of wave w co-reside with gmm(w+1).  Measured on B200 (HFBGPU_TRACE_KERNELS timeline):
+   // the kernels do overlap, but every one of them slows down by about the overlap gained (alpha, one warp
+   // per utterance, 0.9 -> 4-6 ms; gmm 2.2 -> 3.6 ms) -- 110-112 M frames/s either way -- so the default
+   // keeps each wave on its own stream and lets the hardware overlap only copies and kernel tails.
+   cudaStream_t sg = (!tm && getenv("HFBGPU_GMM_STREAM")) ? c->gmmStream : st;
+   if (sg != st) { CK(cudaEventRecord(S.evIn, st)); CK(cudaStreamWaitEvent(sg, S.evIn, 0)); }
    // ---- K0: tables
-   prep_kernel<<<nU, 128, 0, st>>>(c->dm, W);
+   const bool tr = tm || c->trace;
+   if (c->trace) cudaEventRecord(S.ev[5], sg);
+   prep_kernel<<<nU, 128, 0, sg>>>(c->dm, W);
    c->stats.launches++; c->stats.launchesMisc++;
-   if (tm) cudaEventRecord(S.ev[0], st);
+   if (tr) cudaEventRecord(S.ev[0], sg);
    // ---- K1
    int gk = c->opt.gmmKernel;
    if (gk == 0) gk = gmm_tc_available(c->tc) ? 2 : 1;
@@ -639,14 +668,15 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
       int nl = 0;
       if ((rc = gmm_tc_launch(c->tc, S.tcw, c->dm, W, waveFrames, (const int2 *)(base + oIt), (int)w.tcItems.size(),
                               (const int2 *)(base + oIt2), (int)w.tcItems2.size(),
-                              c->smCount, st, &nl))) return rc;
+                              c->smCount, sg, &nl))) return rc;
       c->stats.launches += nl; c->stats.launchesGmm += nl;
    } else if (w.tiles > 0) {
       size_t smem = sizeof(float) * ((size_t)c->dm.D * GT_FR + (size_t)GT_FR * (GT_SL + 1));
-      gmm_fp32_kernel<<<(unsigned)w.tiles, 128, smem, st>>>(c->dm, W);
+      gmm_fp32_kernel<<<(unsigned)w.tiles, 128, smem, sg>>>(c->dm, W);
       c->stats.launches++; c->stats.launchesGmm++;
    }
-   if (tm) cudaEventRecord(S.ev[1], st);
+   if (sg != st) { CK(cudaEventRecord(S.evGmm, sg)); CK(cudaStreamWaitEvent(st, S.evGmm, 0)); }
+   if (tr) cudaEventRecord(S.ev[1], st);
    // ---- K2 / K3
    if (w.maxQ > 0) {
       int nt = std::min(256, std::max(32, (w.maxQ + 31) & ~31));
@@ -677,7 +707,7 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
          }
       } else if (exact) beta_kernel<true><<<nU, ntGeneric, rsm, st>>>(c->dm, W);
       else beta_kernel<false><<<nU, ntGeneric, rsm, st>>>(c->dm, W);
-      if (tm) cudaEventRecord(S.ev[2], st);
+      if (tr) cudaEventRecord(S.ev[2], st);
       if (fastOk) {                                    // register/shuffle kernel; generic one redoes overflows
          if (l2r) { alpha_l2r_kernel<<<nU, 32, 0, st>>>(c->dm, W, forceRedo); c->stats.launchesL2R++; }
          else if (w.maxN <= 5) {
@@ -691,7 +721,7 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
       }
       if (exact) alpha_warp_kernel<true><<<nU, 32, asm_, st>>>(c->dm, W, fastOk ? 1 : 0);
       else alpha_warp_kernel<false><<<nU, 32, asm_, st>>>(c->dm, W, fastOk ? 1 : 0);
-      if (tm) cudaEventRecord(S.ev[3], st);
+      if (tr) cudaEventRecord(S.ev[3], st);
       c->stats.launches += 2; c->stats.launchesBeta++; c->stats.launchesAlpha++;
       // ---- K4
       if (w.totalP > 0 && c->opt.uFlags != 0) {
@@ -716,7 +746,7 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
             stats3_kernel<<<(unsigned)((w.totalP + ST_WARPS - 1) / ST_WARPS), 32 * ST_WARPS, stats_smem_bytes(c->dm.D), st>>>(c->dm, W);
          c->stats.launches++; c->stats.launchesStats++;
       }
-      if (tm) cudaEventRecord(S.ev[4], st);
+      if (tr) cudaEventRecord(S.ev[4], st);
    } else if (tm) {
       for (int k = 2; k <= 4; k++) cudaEventRecord(S.ev[k], st);
    }
@@ -757,6 +787,14 @@ static int finish_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S)
       cudaEventElapsedTime(&ms, S.ev[1], S.ev[2]); c->stats.msBeta += ms;
       cudaEventElapsedTime(&ms, S.ev[2], S.ev[3]); c->stats.msAlpha += ms;
       cudaEventElapsedTime(&ms, S.ev[3], S.ev[4]); c->stats.msStats += ms;
+   }
+   if (c->trace && !c->timing) {
+      float t5, t0, t1, t2, t3, t4;
+      cudaEventElapsedTime(&t5, c->evRef, S.ev[5]); cudaEventElapsedTime(&t0, c->evRef, S.ev[0]);
+      cudaEventElapsedTime(&t1, c->evRef, S.ev[1]); cudaEventElapsedTime(&t2, c->evRef, S.ev[2]);
+      cudaEventElapsedTime(&t3, c->evRef, S.ev[3]); cudaEventElapsedTime(&t4, c->evRef, S.ev[4]);
+      fprintf(stderr, "[hfbgpu trace] slot %d utts %4d | gmm stream reached %9.3f prep done %9.3f | gmm done %9.3f beta done %9.3f "
+                      "alpha done %9.3f stats done %9.3f ms\n", (int)(&S - c->slot), nU, t5, t0, t1, t2, t3, t4);
    }
    const long long waveFrames = S.waveFrames;
    for (int k = 0; k < nU; k++) {
@@ -799,6 +837,7 @@ static int submit_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, c
    const long long totalFrames = b->numUtt ? b->frameOff[b->numUtt] - b->frameOff[0] : 0;
    const long long targetFrames = (b->numUtt >= 64 * want) ? (totalFrames + want - 1) / want : totalFrames;
    const size_t wsPerSlot = c->workspaceBytes / (size_t)ns;
+   const int maxWaveUtts = c->timing ? 16384 : std::min(16384, c->waveUtts);
    int u0 = 0, rcAll = HFB_OK;
    while (u0 < b->numUtt) {
       hfbgpu_ctx::Slot &S = c->slot[c->nextSlot % ns];
@@ -822,7 +861,7 @@ static int submit_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, c
             perFrame += (size_t)N * 8 + (size_t)(N - 2) * 12 + 8;
          }
          size_t need = (size_t)T * perFrame;
-         if (u1 > u0 && (bytes + need > wsPerSlot || u1 - u0 >= 16384 || f0 - waveFrame0 >= targetFrames)) break;
+         if (u1 > u0 && (bytes + need > wsPerSlot || u1 - u0 >= maxWaveUtts || f0 - waveFrame0 >= targetFrames)) break;
          bytes += add_utterance(h, w, u1, T, b->lab + b->labOff[u1], Q, b->labOff[u1] - w.lab0, f0 - waveFrame0);
          u1++;
       }

@@ -185,11 +185,11 @@ int hfbgpu_accumulate(hfbgpu_ctx *ctx, const hfb_batch *batch,
 int hfbgpu_accumulate_device(hfbgpu_ctx *ctx, const hfb_batch *batch,
                              hfb_utt_result *res, const hfb_beams *beams);
 
-/* Asynchronous form: hfbgpu_submit() enqueues the batch on one of the library's streams and
- * returns; the next submit runs on the other stream, so the host->device copy and the
- * latency-bound recursion kernels of one batch overlap the tensor-core / statistics kernels
- * of the other.  The caller keeps `batch` arrays, `res` and `beams` alive until hfbgpu_wait()
- * (or the second-next submit) has returned; hfbgpu_get_accs / _zero_accs wait implicitly.
+/* Asynchronous form: hfbgpu_submit() enqueues the batch on one of the library's streams (four
+ * slots with private workspaces) and returns; consecutive submits run on different streams, so
+ * the host->device copy, table building and kernel tails of one batch overlap the kernels of
+ * the others.  The caller keeps `batch` arrays, `res` and `beams` alive until hfbgpu_wait()
+ * has returned; hfbgpu_get_accs / _zero_accs wait implicitly.
  * This is what the HERest bridge uses to load the next batch from disk while the GPU works. */
 int hfbgpu_submit(hfbgpu_ctx *ctx, const hfb_batch *batch, hfb_utt_result *res,
                   const hfb_beams *beams, int featOnDevice);
