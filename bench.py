@@ -61,7 +61,9 @@ def read_peaks():
     return dict(hbm=6650.0, tensor=1400.0, tensor_burst=1590.0, src="fallback")
 
 
-GMM_TRAFFIC_BYTES = None          # dram bytes of one gmm_tc_kernel launch from the ncu --set full capture (profiles/)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE gmm_tc2_kernel launch (1024 utterances) from the
+# `ncu --set full` capture of the same command, profiles/r1h_gmm_tc2_details.csv: 1.894 GB + 1.192 GB
+GMM_TRAFFIC_BYTES = {"cfg3": 3.086e9}
 
 
 def measure_tf32(dev):
@@ -387,20 +389,25 @@ def main():
         peaks = read_peaks()
         tf32 = measure_tf32(dev) if world == 1 else None
         kms = {"gmm": sk.msGmm / K, "beta": sk.msBeta / K, "alpha": sk.msAlpha / K, "stats": sk.msStats / K}
+        ms_expand = sk.msExpand / K                               # feature expansion, part of "gmm"
+        ms_gemm = kms["gmm"] - ms_expand                          # the tensor-core kernel alone
         M = cfg["M"]
         pairs = sk.gmmPairs / K                                  # (frame, distinct tied state) pairs per step
         gmm_flop = pairs * M * ALG_FLOP_PER_GAUSS_FRAME(fm.D)
         dom = max(kms, key=kms.get)
-        if dom == "gmm":
-            ach = gmm_flop / (kms["gmm"] * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "gmm_tc_kernel (tcgen05 3xTF32)", "achieved": ach, "peak": peaks["tensor"],
-                    "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": GMM_TRAFFIC_BYTES,
+        if dom == "gmm" and ms_gemm > 0 and M > 1:
+            ach = gmm_flop / (ms_gemm * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "gmm_tc2_kernel (tcgen05 cta_group::2, 3xTF32, M=256)", "achieved": ach,
+                    "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"],
+                    "traffic": GMM_TRAFFIC_BYTES.get(args.workload) if n_utts == 1024 else None,
+                    "ms_per_launch": ms_gemm, "launches_per_step": 1,
                     "tf32_tflops_measured": tf32,
                     "frac_of_tf32_over_3": (ach / (tf32 / 3.0)) if tf32 else None,
-                    "note": "algorithmic FLOP = (frame, distinct state) pairs x M x 2(2D+1) (SURVEY 8d); peak = bf16 %s (%s) as "
-                            "the contract asks; the honest ceiling of a 3xTF32 kernel is the TF32 rate / 3 -- "
-                            "tf32_tflops_measured is cuBLAS TF32 8192^3 measured in this run, frac_of_tf32_over_3 uses it"
-                            % ("sustained", peaks["src"])}
+                    "note": "algorithmic FLOP = (frame, distinct state) pairs x M x 2(2D+1) (SURVEY 8d), one launch per step; "
+                            "peak = bf16 %s (%s) as the contract asks; the ceiling of a 3xTF32 kernel is the TF32 rate / 3 -- "
+                            "tf32_tflops_measured is cuBLAS TF32 8192^3 measured in this run and frac_of_tf32_over_3 uses it; "
+                            "tools/mma_rate.cu measures 1264 MAC/clk/SM for the N=128 cta_group::2 TF32 MMAs this kernel issues "
+                            "(1563 at N=256), the kernel sustains ~1430" % ("sustained", peaks["src"])}
         else:
             # beta/alpha: SURVEY.md 8d per-cell bytes (beta written+read 2*8*N, state log-probs 2*4*(N-2))
             by = beta_cells * 104.0 + n_utts * T * fm.D * 4 * 2
@@ -425,7 +432,7 @@ def main():
                "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(n_utts * T * fm.D * 4),
                        "d2h_bytes_per_step": int(n_utts * 24), "ms_per_step": ms_host / K},
                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-               "kernels_ms_per_step": kms,
+               "kernels_ms_per_step": dict(kms, gmm_expand=ms_expand),
                "work_per_step": {"frames": n_utts * T, "gmm_state_frame_pairs": pairs, "beta_cells": beta_cells,
                                  "alpha_cells": alpha_cells, "gmm_algorithmic_gflop": gmm_flop / 1e9}}
         print(json.dumps(out))

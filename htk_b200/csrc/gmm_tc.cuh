@@ -766,7 +766,7 @@ static inline int gmm_tc_prepare(GmmTcModel &t, const hfb_model *m, cudaStream_t
 // Launches expansion + GEMM for every utterance of the wave.  `items` lives in the wave blob.
 static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm, const Wave &W, long long waveFrames,
                                 const int2 *dItems, int nItems, const int2 *dItems2, int nItems2, int smCount,
-                                cudaStream_t st, int *launches)
+                                cudaStream_t st, int *launches, cudaEvent_t afterExpand = nullptr)
 {
    if (!t.ready) return HFB_EUNSUPPORTED;
    if (nItems == 0) return HFB_OK;
@@ -786,6 +786,7 @@ static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm
       return HFB_ECUDA;
    long long n = waveFrames * TC_KE;
    gmm_tc_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W.feat, t.dOffset, dm.D, waveFrames, wk.dAhi, wk.dAlo);
+   if (afterExpand) cudaEventRecord(afterExpand, st);
    TcParams p;
    p.items = dItems; p.nItems = nItems; p.utt = W.utt; p.slotState = W.slotState; p.b = W.b; p.GPS = t.GPS; p.C0 = t.C0;
    p.kSteps = (2 * dm.D + 2 + 7) / 8;

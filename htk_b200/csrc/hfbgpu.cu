@@ -121,6 +121,8 @@ struct hfbgpu_ctx {
       cudaStream_t stream = nullptr;
       cudaEvent_t ev[6] = {};
       cudaEvent_t evIn = nullptr, evGmm = nullptr;   // inputs uploaded / output probabilities ready
+      cudaEvent_t evX = nullptr;        // timing mode: feature expansion done, tensor-core kernel starts
+      bool hasX = false;
       DevBuf<float> dFeat;              // only for host-feature calls
       DevBuf<float> dB;
       DevBuf<double> dBeta, dOcc, dAent;
@@ -298,6 +300,7 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
       for (auto &e : sl.ev) CK(cudaEventCreate(&e));
       CK(cudaEventCreateWithFlags(&sl.evIn, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&sl.evGmm, cudaEventDisableTiming));
+      CK(cudaEventCreate(&sl.evX));
    }
    c->trace = getenv("HFBGPU_TRACE_KERNELS") != nullptr;
    if (c->trace) { CK(cudaEventCreate(&c->evRef)); CK(cudaEventRecord(c->evRef, c->stream)); }
@@ -438,6 +441,7 @@ extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
       for (auto &e : sl.ev) if (e) cudaEventDestroy(e);
       if (sl.evIn) cudaEventDestroy(sl.evIn);
       if (sl.evGmm) cudaEventDestroy(sl.evGmm);
+      if (sl.evX) cudaEventDestroy(sl.evX);
       if (sl.stream) cudaStreamDestroy(sl.stream);
       delete sl.w;
    }
@@ -668,7 +672,8 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
       int nl = 0;
       if ((rc = gmm_tc_launch(c->tc, S.tcw, c->dm, W, waveFrames, (const int2 *)(base + oIt), (int)w.tcItems.size(),
                               (const int2 *)(base + oIt2), (int)w.tcItems2.size(),
-                              c->smCount, sg, &nl))) return rc;
+                              c->smCount, sg, &nl, tm ? S.evX : nullptr))) return rc;
+      S.hasX = tm;
       c->stats.launches += nl; c->stats.launchesGmm += nl;
    } else if (w.tiles > 0) {
       size_t smem = sizeof(float) * ((size_t)c->dm.D * GT_FR + (size_t)GT_FR * (GT_SL + 1));
@@ -784,6 +789,7 @@ static int finish_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S)
    if (c->timing) {
       float ms;
       cudaEventElapsedTime(&ms, S.ev[0], S.ev[1]); c->stats.msGmm += ms;
+      if (S.hasX) { cudaEventElapsedTime(&ms, S.ev[0], S.evX); c->stats.msExpand += ms; S.hasX = false; }
       cudaEventElapsedTime(&ms, S.ev[1], S.ev[2]); c->stats.msBeta += ms;
       cudaEventElapsedTime(&ms, S.ev[2], S.ev[3]); c->stats.msAlpha += ms;
       cudaEventElapsedTime(&ms, S.ev[3], S.ev[4]); c->stats.msStats += ms;

@@ -80,7 +80,8 @@ class hfb_stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "launches", "launchesGmm", "launchesBeta", "launchesAlpha", "launchesStats", "launchesMisc")] + \
         [(n, C.c_double) for n in ("msGmm", "msBeta", "msAlpha", "msStats")] + \
-        [(n, C.c_int64) for n in ("betaCells", "alphaCells", "gmmPairs", "h2dBytes", "d2hBytes", "launchesL2R")]
+        [(n, C.c_int64) for n in ("betaCells", "alphaCells", "gmmPairs", "h2dBytes", "d2hBytes", "launchesL2R")] + \
+        [("msExpand", C.c_double)]
 
 
 NOPRUNE = 1.0e20

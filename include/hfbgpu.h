@@ -219,6 +219,7 @@ typedef struct hfb_stats {
    int64_t betaCells, alphaCells, gmmPairs;   /* algorithmic units processed             */
    int64_t h2dBytes, d2hBytes;
    int64_t launchesL2R;                       /* of launchesBeta/Alpha: standard-topology kernels */
+   double  msExpand;                          /* part of msGmm: feature expansion before the tensor-core kernel */
 } hfb_stats;
 int hfbgpu_get_stats(hfbgpu_ctx *ctx, hfb_stats *out);
 int hfbgpu_reset_stats(hfbgpu_ctx *ctx);
