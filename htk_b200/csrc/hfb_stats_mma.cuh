@@ -35,14 +35,12 @@
 #define S4_LSTR 36                    // row stride of the Lr tile: conflict-free A-fragment loads
 #define S4_CSTR 40                    // row stride of the state-centre table
 
-// TF32 split without the (quarter-rate) cvt.rna.tf32: the tensor core reads only the upper 19 bits of
-// an operand register, so v itself serves as "hi" (= v truncated) and lo = v - trunc(v) is exact in FP32
-// (13 significant bits, of which the tensor core keeps 11: ~2^-21 relative to v).
-__device__ __forceinline__ uint32_t s4_hi(float x) { return __float_as_uint(x); }
-__device__ __forceinline__ uint32_t s4_lo(float x)
-{
-   return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
-}
+// TF32 split on the integer pipe (cvt.rna.tf32 is a quarter-rate conversion): hi = x rounded to the 19
+// bits the tensor core reads (add half an ulp, mask), lo = x - hi exactly (signed, <= 12 significant
+// bits, of which the tensor core keeps 11): |x - hi - lo_read| <= 2^-23 |x| and unbiased, unlike plain
+// truncation, whose always-towards-zero error would bias every occupancy sum.
+__device__ __forceinline__ uint32_t s4_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+__device__ __forceinline__ uint32_t s4_lo(float x) { return __float_as_uint(x - __uint_as_float(s4_hi(x))); }
 __device__ __forceinline__ void s4_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
 {
    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -122,12 +120,15 @@ __global__ void __launch_bounds__(128) statpos_scatter_kernel(Wave W, const int 
 }
 
 #define S5_GSTR 44                    // row stride (floats) of the staged Gaussian parameters: 16-byte aligned rows
+// Shared memory per warp: x0s[32] doubles, ts[32] ints, the observation tile [32][8 NT + 1] (columns: D
+// dimensions, a ones column, zero padding), the Lr tile [16][S4_LSTR] (both reused as flush staging
+// [16][16 NT]) and the state's Gaussians (means, inverse variances, gConst, log weights).
 template <int NT>
 __host__ __device__ inline size_t stats5_warp_bytes(int D)
 {
-   const size_t work = sizeof(float) * ((size_t)32 * stats_ostride(D) + 16 * S4_LSTR);   // observations + Lr tile
-   const size_t flush = sizeof(float) * 16 * 16 * NT;                                    // [16][S1 | S2] staging
-   const size_t gauss = sizeof(float) * (2 * 16 * S5_GSTR + 32);                         // means, inverse variances, gconst, log weights
+   const size_t work = sizeof(float) * ((size_t)32 * (8 * NT + 1) + 16 * S4_LSTR);
+   const size_t flush = sizeof(float) * 16 * 16 * NT;
+   const size_t gauss = sizeof(float) * (2 * 16 * S5_GSTR + 32);
    return sizeof(double) * 32 + sizeof(int) * 32 + ((((work > flush) ? work : flush) + 15) & ~(size_t)15) + gauss;
 }
 
@@ -142,11 +143,12 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
    const int nSorted = *listEnd;
    const int i0 = (blockIdx.x * S4_WARPS + wInB) * S5_CAP, i1 = min(nSorted, i0 + S5_CAP);
    if (i0 >= i1) return;
-   const int D = M.D, Dp = M.Dp, ostr = stats_ostride(D);
+   const int D = M.D, Dp = M.Dp;
+   constexpr int ostr = 8 * NT + 1;
    unsigned char *mine = smraw + stats5_warp_bytes<NT>(D) * wInB;
    double *x0s = (double *)mine;                       // [32] initx / log occupancy per chunk frame
    int *ts = (int *)(x0s + 32);                        // [32] frame numbers
-   float *os = (float *)(ts + 32);                     // [32][ostr] observation rows
+   float *os = (float *)(ts + 32);                     // [32][ostr] observations | 1 | 0...
    float *lrs = os + 32 * ostr;                        // [16 components][S4_LSTR] occupancies Lr
    float *fb = os;                                     // flush staging [16][16 NT]
    constexpr int FSTR = 16 * NT;
@@ -161,7 +163,7 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
 
    for (int mb = 0; mb < M.maxM; mb += 16) {           // component tiles of 16 (one pass for M <= 16)
       float acc1[NT][4], acc2[NT][4];                  // sum Lr (o - c), sum Lr (o - c)^2; column D of acc1 = sum Lr
-      float cenB[NT];                                  // centre of "my" right-hand-side column in each tile
+      float cenB[NT];                                  // state centre at "my" right-hand-side column of each tile
       int curS = -1, mo = 0, Mn = 0, Mc = 0;
       bool any = false;
 
@@ -218,7 +220,7 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
 #pragma unroll
             for (int nt = 0; nt < NT; nt++) {
                const int dim = nt * 8 + fg;
-               cenB[nt] = (dim < D) ? cen[dim] : 0.f;
+               cenB[nt] = (dim < D) ? cen[dim] : 0.f;             // 0 for the ones column and the padding
 #pragma unroll
                for (int i = 0; i < 4; i++) { acc1[nt][i] = 0.f; acc2[nt][i] = 0.f; }
             }
@@ -286,16 +288,20 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
                   const float *src = feat + (size_t)ts[on ? tb + r : 0] * D;
                   v0[r] = (on && lane < D) ? src[lane] : 0.f;
                   v1[r] = (on && lane + 32 < D) ? src[lane + 32] : 0.f;
+                  if (on && lane == D) v0[r] = 1.f;                // the ones column: sum Lr in phase 2
+                  if (on && lane + 32 == D) v1[r] = 1.f;
                }
 #pragma unroll
                for (int r = 0; r < 8; r++) {
                   float *dst = os + (tb + r) * ostr;
-                  if (lane < D) dst[lane] = v0[r];
-                  if (lane + 32 < D) dst[lane + 32] = v1[r];
+                  if (lane < 8 * NT) dst[lane] = v0[r];
+                  if (lane + 32 < 8 * NT) dst[lane + 32] = v1[r];
                }
             }
             __syncwarp();
-            // ---- phase 1: lanes <-> (component, frame) pairs -> Lr tile
+            // ---- phase 1: component posteriors on the FP32 pipe, lanes <-> (component, frame) pairs -> Lr tile.
+            //      (Tried as a second mma.sync 3xTF32 product: the tensor core's truncating FP32 accumulation
+            //      biased log N by ~5e-5 and pushed the mean sums past the 1e-4 parity bound -- reverted.)
             unsigned anyLr = 0;
             for (int pi = lane; pi < ((Mc * nT + 31) & ~31); pi += 32) {
                float Lr = 0.f;
@@ -309,7 +315,7 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
                         const float *o = os + ti * ostr;
                         float sum = ggc[mi];
                         int k = 0;
-                        for (; k + 4 <= D; k += 4) {                            // staged rows are 16-byte aligned
+                        for (; k + 4 <= D; k += 4) {                            // IDOutP's order of operations, HModel.c:5425-5430
                            const float4 m4 = *reinterpret_cast<const float4 *>(mu + k);
                            const float4 v4 = *reinterpret_cast<const float4 *>(iv + k);
                            float d = __fsub_rn(o[k], m4.x);     sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), v4.x));
@@ -321,7 +327,7 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
                            const float d = __fsub_rn(o[k], mu[k]);
                            sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), iv[k]));
                         }
-                     const float mixp = -0.5f * sum;
+                        const float mixp = -0.5f * sum;
                         x = (x + (double)wt) + (double)mixp;                    // :1581-1599
                      }
                      if (-x < minF) Lr = expf((float)x);                        // :1606, :1612
@@ -345,15 +351,19 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
                const float *o0 = os + (ks + fc) * ostr, *o1 = o0 + 4 * ostr;
 #pragma unroll
                for (int nt = 0; nt < NT; nt++) {
-                  const int dim = nt * 8 + fg;
-                  float v0, v1;
-                  if (dim < D) { v0 = o0[dim] - cenB[nt]; v1 = o1[dim] - cenB[nt]; }
-                  else { v0 = v1 = (dim == D) ? 1.f : 0.f; }                    // the ones column gives sum Lr
+                  const float v0 = o0[nt * 8 + fg] - cenB[nt], v1 = o1[nt * 8 + fg] - cenB[nt];   // column D of the tile holds 1
+                  // the tensor core forms the 8-frame partial products in a fresh fragment; the running sums are
+                  // kept on the FP32 pipe (round to nearest): its own accumulation truncates, which over the
+                  // ~100 MMAs of a flush interval would bias every occupancy sum by several 1e-6
                   uint32_t h0 = s4_hi(v0), h1 = s4_hi(v1), l0 = s4_lo(v0), l1 = s4_lo(v1);
-                  s4_mma(acc1[nt], ah, h0, h1); s4_mma(acc1[nt], ah, l0, l1); s4_mma(acc1[nt], al, h0, h1);
+                  float p[4] = {0.f, 0.f, 0.f, 0.f};
+                  s4_mma(p, ah, l0, l1); s4_mma(p, al, h0, h1); s4_mma(p, ah, h0, h1);
+                  acc1[nt][0] += p[0]; acc1[nt][1] += p[1]; acc1[nt][2] += p[2]; acc1[nt][3] += p[3];
                   const float w0 = v0 * v0, w1 = v1 * v1;
                   h0 = s4_hi(w0); h1 = s4_hi(w1); l0 = s4_lo(w0); l1 = s4_lo(w1);
-                  s4_mma(acc2[nt], ah, h0, h1); s4_mma(acc2[nt], ah, l0, l1); s4_mma(acc2[nt], al, h0, h1);
+                  p[0] = p[1] = p[2] = p[3] = 0.f;
+                  s4_mma(p, ah, l0, l1); s4_mma(p, al, h0, h1); s4_mma(p, ah, h0, h1);
+                  acc2[nt][0] += p[0]; acc2[nt][1] += p[1]; acc2[nt][2] += p[2]; acc2[nt][3] += p[3];
                }
             }
          }
