@@ -162,22 +162,22 @@ __device__ __forceinline__ float tc_tf32(float x)
 // ------------------------------------------------------------------------------------------
 // feature expansion: A'hi / A'lo [frames][96] = split of [ 1 | (x-o)^2 | (x-o) | 1 | 0... ]
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TC_KE * 4)
 gmm_tc_expand_kernel(const float *__restrict__ feat, const float *__restrict__ off, int D, long long nFrames,
                      float *__restrict__ Ahi, float *__restrict__ Alo)
 {
-   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-   if (idx >= nFrames * TC_KE) return;
-   long long f = idx / TC_KE;
-   int k = (int)(idx - f * TC_KE);
+   // thread (k, r): column k of frame 4 * blockIdx + r; rows are written as whole 384-byte lines
+   const int k = threadIdx.x;
+   const long long f = (long long)blockIdx.x * 4 + threadIdx.y;
+   if (f >= nFrames) return;
    float v = 0.f;
    if (k == 0) v = 1.f;                                   // pairs with the constant column C0
    else if (k <= D) { float x = feat[f * D + k - 1] - off[k - 1]; v = x * x; }
    else if (k <= 2 * D) v = feat[f * D + (k - D - 1)] - off[k - D - 1];
    else if (k == 2 * D + 1) v = 1.f;                      // pairs with c
-   float hi = tc_tf32(v);
-   Ahi[idx] = hi;
-   Alo[idx] = tc_tf32(v - hi);
+   const float hi = tc_tf32(v);
+   Ahi[f * TC_KE + k] = hi;
+   Alo[f * TC_KE + k] = tc_tf32(v - hi);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -784,8 +784,7 @@ static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm
    if (tc_make_map(t.encodeFn, &mapAhi, wk.dAhi, waveFrames + TC_BM, TC_BM) ||
        tc_make_map(t.encodeFn, &mapAlo, wk.dAlo, waveFrames + TC_BM, TC_BM))
       return HFB_ECUDA;
-   long long n = waveFrames * TC_KE;
-   gmm_tc_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W.feat, t.dOffset, dm.D, waveFrames, wk.dAhi, wk.dAlo);
+   gmm_tc_expand_kernel<<<(unsigned)((waveFrames + 3) / 4), dim3(TC_KE, 4), 0, st>>>(W.feat, t.dOffset, dm.D, waveFrames, wk.dAhi, wk.dAlo);
    if (afterExpand) cudaEventRecord(afterExpand, st);
    TcParams p;
    p.items = dItems; p.nItems = nItems; p.utt = W.utt; p.slotState = W.slotState; p.b = W.b; p.GPS = t.GPS; p.C0 = t.C0;

@@ -64,30 +64,22 @@ __global__ void __launch_bounds__(MAXT, 1024 / MAXT) beta_l2r_kernel(DevModel M,
    const float *bU = W.b + u.bOff;
    double *betaQ = W.beta + u.betaOff + 5 * q;
    short *qLo = W.qLo + u.frameBase, *qHi = W.qHi + u.frameBase;
-   const int *pre = W.mPre + u.modOff, *suf = W.mSuf + u.modOff;
 
    double thresh = W.pruneInit, pr = LZERO_D;
    int retries = 0, status = 0;
 
    for (;;) {
-      // ---- SetBeamTaper (closed form, see beta_kernel)
-      for (int t = tid; t < T; t += nt) {
-         int lo = 0, hi = Q;
-         while (lo < hi) { int mid = (lo + hi) >> 1; if (pre[mid] <= t) lo = mid + 1; else hi = mid; }
-         qHi[t] = (short)(lo - 1);
-         int rr = T - 1 - t; lo = 0; hi = Q;
-         while (lo < hi) { int mid = (lo + hi) >> 1; if (suf[mid] > rr) lo = mid + 1; else hi = mid; }
-         qLo[t] = (short)lo;
-      }
-      __syncthreads();
+      // ---- SetBeamTaper (HFB.c:1116-1145): every model has minimum duration 3 here, so the taper is
+      //      qHi(t) = min(Q-1, t / 3), qLo(t) = max(0, Q-1 - (T-1-t) / 3) -- evaluated in the frame loop
+      //      with running quotients, no table and no loads
       const bool noPrune = thresh >= 0.5 * HFB_NOPRUNE;
 
       double *cur = entA, *prev = entB;                // entry-state beta of every model, frames t / t+1
       double u0 = LZERO_D, u1 = LZERO_D, u2 = LZERO_D; // b_j(o_{t+1}) + beta_j(t+1), log zero outside the beam
 
       // ---- t = T-1, HFB.c:1176-1198
-      int lo1 = qLo[T - 1], hi1 = Q - 1, lastq = lo1;
-      if (tid == 0) qHi[T - 1] = (short)(Q - 1);
+      int lo1 = Q - 1, hi1 = Q - 1, lastq = lo1;
+      if (tid == 0) { qHi[T - 1] = (short)(Q - 1); qLo[T - 1] = (short)(Q - 1); }
       if (mine && q >= lo1) {
          const float *bt = bU + (size_t)(T - 1) * J;
          const double bExit = (q == Q - 1) ? 0.0 : LZERO_D;
@@ -111,10 +103,12 @@ __global__ void __launch_bounds__(MAXT, 1024 / MAXT) beta_l2r_kernel(DevModel M,
       bool fail = false;
       double *bg = betaQ + (size_t)(T - 1) * S;        // running pointers: this model's beta column at t,
       const float *bp = bU + (size_t)(T - 3) * J;      // the output-probability row of frame t-2
-      const short *pLo = qLo + (T - 1), *pHi = qHi + (T - 1);
+      int hiC = (T - 1) / 3, hiR = (T - 1) % 3, loC = 0, loR = 0;      // t / 3 and (T-1-t) / 3 with remainders, at t = T-1
       for (int t = T - 2; t >= 0; t--) {
-         bg -= S; bp -= J; pLo--; pHi--;
-         const int tapLo = *pLo, tapHi = *pHi;
+         bg -= S; bp -= J;
+         if (hiR == 0) { hiR = 2; hiC--; } else hiR--;
+         if (loR == 2) { loR = 0; loC++; } else loR++;
+         const int tapLo = max(0, Q - 1 - loC), tapHi = min(Q - 1, hiC);
          const int startq = hi1;
          const int endq = (lo1 == 0) ? 0 : ((tapLo >= lo1) ? tapLo : lo1 - 1);
          lastq = endq;
@@ -216,24 +210,30 @@ __global__ void __launch_bounds__(32) alpha_l2r_kernel(DevModel M, Wave W, int f
    int tmin = 0x7fffffff, tmax = -1;
    int sq = 0, eq = 0;
 
+   // running pointers: frame t of the beta column block, the output-probability row, the alpha rows
+   const double *bqT = betaU;
+   const float *btT = bU;
+   double *ocT = occU, *aeT = aentU;
+   int loP = 0, hiP = 0;                                   // beta beam of the previous frame
+   int loT = qLo[0], hiT = qHi[0];
    for (int t = 0; t < T; t++) {
-      const int loT = qLo[t], hiT = qHi[t];
       // loads that do not depend on the recursion go first
       const bool inWin = have && myq >= sq && myq <= ((t == 0) ? hiT : min(Q - 1, eq + 1));
       float b0 = 0.f, b1 = 0.f, b2 = 0.f;
       double bEn = LZERO_D, bE0 = LZERO_D, bE1 = LZERO_D, bE2 = LZERO_D, bX = LZERO_D;
       if (inWin && myq >= loT && myq <= hiT) {
-         const float *bt = bU + (size_t)t * J;
-         const double *bq = betaU + (size_t)t * S + 5 * myq;
+         const double *bq = bqT + 5 * myq;
          bEn = bq[0]; bE0 = bq[1]; bE1 = bq[2]; bE2 = bq[3]; bX = bq[4];
-         b0 = bt[r.s0]; b1 = bt[r.s1]; b2 = bt[r.s2];
+         b0 = btT[r.s0]; b1 = btT[r.s1]; b2 = btT[r.s2];
       }
       if (inWin && t + 2 < T) {                              // first touched two frames from now
-         const float *bt2 = bU + (size_t)(t + 2) * J;
-         const double *bq2 = betaU + (size_t)(t + 2) * S + 5 * myq;
+         const float *bt2 = btT + 2 * (size_t)J;
+         const double *bq2 = bqT + 2 * S + 5 * myq;
          prefetch_l1(bq2); prefetch_l1(bq2 + 4);
          prefetch_l1(bt2 + r.s0); prefetch_l1(bt2 + r.s1); prefetch_l1(bt2 + r.s2);
       }
+      int loN = 0, hiN = 0;                                  // next frame's beta beam (read early, used next iteration)
+      if (t + 1 < T) { loN = qLo[t + 1]; hiN = qHi[t + 1]; }
       double a1 = LZERO_D, n0 = LZERO_D, n1 = LZERO_D, n2 = LZERO_D, nEx = LZERO_D;
       int nsq, neq;
       if (t == 0) {
@@ -246,7 +246,6 @@ __global__ void __launch_bounds__(32) alpha_l2r_kernel(DevModel M, Wave W, int f
          }
       } else {
          // ---- alpha beam, HFB.c:701-722
-         const int loP = qLo[t - 1], hiP = qHi[t - 1];
          const int q1 = __shfl_sync(FULL, myq, (lane + 31) & 31);
          const double ex1 = __shfl_sync(FULL, exv, (lane + 31) & 31);
          const double ax1 = __shfl_sync(FULL, aEx, (lane + 31) & 31);
@@ -278,9 +277,9 @@ __global__ void __launch_bounds__(32) alpha_l2r_kernel(DevModel M, Wave W, int f
       if (inBeam) {
          mpS = dmax(dmax(a1 + bEn, n0 + bE0), dmax(n1 + bE1, n2 + bE2));
          exv = nEx + bX;
-         double *oc = occU + (size_t)t * P + 3 * myq;
+         double *oc = ocT + 3 * myq;
          oc[0] = n0; oc[1] = n1; oc[2] = n2;
-         aentU[(size_t)t * Q + myq] = a1;
+         aeT[myq] = a1;
          if (tmin > t) tmin = t;
          tmax = t;
       }
@@ -293,6 +292,8 @@ __global__ void __launch_bounds__(32) alpha_l2r_kernel(DevModel M, Wave W, int f
          if (have) load_l2r(r, M, W, u, myq);
          else { r.aE = r.a00 = r.a01 = r.a11 = r.a12 = r.a22 = r.a2x = LZERO_D; r.s0 = r.s1 = r.s2 = 0; }
       }
+      bqT += S; btT += J; ocT += P; aeT += Q;
+      loP = loT; hiP = hiT; loT = loN; hiT = hiN;
    }
    if (have && tmax >= 0) { gTmin[myq] = tmin; gTmax[myq] = tmax; }
    for (int q = lane; q < Q; q += 32) atomicAdd(&W.acc[M.L.numEgs + W.mHmm[u.modOff + q]], 1.0);   // HFB.c:1768-1772
