@@ -63,13 +63,22 @@ static struct {
    HLink *hmm; StreamElem **ste; MixPDF **mp; SVector *meanV, *varV; SMatrix *trans;
    PMap pmHmm, pmSte, pmMp, pmMean, pmVar, pmTr;
    int nHmm, nSte, nMp, nMean, nVar, nTr;
-   /* pending batch */
-   float *feat; long featCap, nFrames;
-   int64_t *frameOff; int32_t *labOff, *lab; int nUtt, labCap, nLab;
-   char **names;
    /* totals */
    long nOk, nSkipped;
 } B;
+
+/* Two pending batches: while the library works on one (hfbgpu_submit is asynchronous), HERest's own
+   file loop (LoadLabs / LoadData, HERest.c:753-787) fills the other.  Features live in pinned host
+   memory (hfbgpu_host_alloc) so that the upload is an asynchronous DMA. */
+typedef struct {
+   float *feat; long featCap, nFrames;
+   int64_t *frameOff; int32_t *labOff, *lab; int nUtt, labCap, nLab;
+   char **names;
+   hfb_utt_result *res;
+   int inflight;
+} Pending;
+static Pending P[2];
+static int cur = 0;
 
 static void *xrealloc(void *p, size_t n)
 {
@@ -235,30 +244,48 @@ void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pr
    fflush(stdout);
 }
 
+/* Completes everything in flight and reports per-utterance outcomes in submission order. */
+static void Drain(void)
+{
+   int k, u, rc;
+   if (!P[0].inflight && !P[1].inflight) return;
+   rc = hfbgpu_wait(B.ctx);
+   if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_wait failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
+   for (k = 0; k < 2; k++) {
+      Pending *p = &P[(cur + k) & 1];                       /* P[cur] was submitted before P[cur ^ 1] */
+      if (!p->inflight) continue;
+      for (u = 0; u < p->nUtt; u++) {
+         const hfb_utt_result *r = &p->res[u];
+         if (r->status == HFB_UTT_OK) B.nOk++;
+         else if (r->status == HFB_UTT_SKIPPED) {                      /* HFB.c:1342, :1354 */
+            HError(-7324, "StepBack: File %s - bad data or over pruning\n", p->names[u]);
+            B.nSkipped++;
+         } else if (r->status == HFB_UTT_ETEE)
+            HError(7332, "CreateInsts: Cannot have Tee models at start or end of transcription / successive Tee models (%s)", p->names[u]);
+         else
+            HError(r->status, "hfbgpu: forward-backward failed for %s (%s)", p->names[u], hfbgpu_strerror(r->status));
+         free(p->names[u]);
+      }
+      free(p->res); p->res = NULL;
+      p->inflight = 0; p->nUtt = 0; p->nFrames = 0; p->nLab = 0;
+   }
+}
+
+/* Hands the current batch to the library (asynchronously) and switches to the other buffer. */
 static void Flush(void)
 {
+   Pending *p = &P[cur];
    hfb_batch b;
-   hfb_utt_result *res;
-   int u, rc;
-   if (B.nUtt == 0) return;
-   B.frameOff[B.nUtt] = B.nFrames; B.labOff[B.nUtt] = B.nLab;
-   b.numUtt = B.nUtt; b.frameOff = B.frameOff; b.feat = B.feat; b.labOff = B.labOff; b.lab = B.lab;
-   res = (hfb_utt_result *)calloc(B.nUtt, sizeof(hfb_utt_result));
-   rc = hfbgpu_accumulate(B.ctx, &b, res, NULL);
-   if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_accumulate failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
-   for (u = 0; u < B.nUtt; u++) {
-      if (res[u].status == HFB_UTT_OK) B.nOk++;
-      else if (res[u].status == HFB_UTT_SKIPPED) {                      /* HFB.c:1342, :1354 */
-         HError(-7324, "StepBack: File %s - bad data or over pruning\n", B.names[u]);
-         B.nSkipped++;
-      } else if (res[u].status == HFB_UTT_ETEE)
-         HError(7332, "CreateInsts: Cannot have Tee models at start or end of transcription / successive Tee models (%s)", B.names[u]);
-      else
-         HError(res[u].status, "hfbgpu: forward-backward failed for %s (%s)", B.names[u], hfbgpu_strerror(res[u].status));
-      free(B.names[u]);
-   }
-   free(res);
-   B.nUtt = 0; B.nFrames = 0; B.nLab = 0;
+   int rc;
+   if (p->nUtt == 0) return;
+   p->frameOff[p->nUtt] = p->nFrames; p->labOff[p->nUtt] = p->nLab;
+   b.numUtt = p->nUtt; b.frameOff = p->frameOff; b.feat = p->feat; b.labOff = p->labOff; b.lab = p->lab;
+   p->res = (hfb_utt_result *)calloc(p->nUtt, sizeof(hfb_utt_result));
+   rc = hfbgpu_submit(B.ctx, &b, p->res, NULL, 0);
+   if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_submit failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
+   p->inflight = 1;
+   cur ^= 1;
+   if (P[cur].inflight) Drain();                            /* the buffer we are about to refill must be done */
 }
 
 /* Replaces FBFile (HFB.c:1923): the utterance is only buffered here.  Always returns FALSE so
@@ -267,39 +294,43 @@ static void Flush(void)
 Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
 {
    LLink lab;
+   Pending *p = &P[cur];
    int q, t, k, T = utt->T, Q = utt->Q, D = B.D;
    if (utt->twoDataFiles) HError(7399, "hfbgpu bridge: single-pass retraining is not accelerated");
-   if (B.nUtt == 0 && !B.frameOff) {
-      B.frameOff = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (B.batchUtts + 2));
-      B.labOff = (int32_t *)xrealloc(NULL, sizeof(int32_t) * (B.batchUtts + 2));
-      B.names = (char **)xrealloc(NULL, sizeof(char *) * (B.batchUtts + 2));
+   if (!p->frameOff) {
+      p->frameOff = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (B.batchUtts + 2));
+      p->labOff = (int32_t *)xrealloc(NULL, sizeof(int32_t) * (B.batchUtts + 2));
+      p->names = (char **)xrealloc(NULL, sizeof(char *) * (B.batchUtts + 2));
    }
-   if (B.nFrames + T > B.featCap) {
-      B.featCap = (B.nFrames + T) * 2 + 1024;
-      B.feat = (float *)xrealloc(B.feat, sizeof(float) * (size_t)B.featCap * D);
+   if (p->nFrames + T > p->featCap) {                       /* grow the pinned feature buffer */
+      long ncap = (p->nFrames + T) * 2 + 1024;
+      float *nf = (float *)hfbgpu_host_alloc(sizeof(float) * (size_t)ncap * D);
+      if (!nf) HError(7399, "hfbgpu bridge: out of pinned host memory");
+      if (p->feat) { memcpy(nf, p->feat, sizeof(float) * (size_t)p->nFrames * D); hfbgpu_host_free(p->feat); }
+      p->feat = nf; p->featCap = ncap;
    }
-   if (B.nLab + Q > B.labCap) {
-      B.labCap = (B.nLab + Q) * 2 + 1024;
-      B.lab = (int32_t *)xrealloc(B.lab, sizeof(int32_t) * (size_t)B.labCap);
+   if (p->nLab + Q > p->labCap) {
+      p->labCap = (p->nLab + Q) * 2 + 1024;
+      p->lab = (int32_t *)xrealloc(p->lab, sizeof(int32_t) * (size_t)p->labCap);
    }
-   B.frameOff[B.nUtt] = B.nFrames; B.labOff[B.nUtt] = B.nLab;
+   p->frameOff[p->nUtt] = p->nFrames; p->labOff[p->nUtt] = p->nLab;
    /* labels -> physical HMM indices (CreateInsts, HFB.c:538-542) */
    for (lab = utt->tr->head->head->succ, q = 0; lab->succ != NULL; lab = lab->succ, q++) {
       MLink ml = FindMacroName(B.hset, 'l', lab->labid);
-      int p;
+      int ph;
       if (ml == NULL) HError(7321, "CreateInsts: Unknown label %s", lab->labid->name);
-      p = pm_get(&B.pmHmm, ml->structure);
-      if (p < 0) HError(7321, "hfbgpu bridge: label %s maps to an unknown physical HMM", lab->labid->name);
-      B.lab[B.nLab + q] = p;
+      ph = pm_get(&B.pmHmm, ml->structure);
+      if (ph < 0) HError(7321, "hfbgpu bridge: label %s maps to an unknown physical HMM", lab->labid->name);
+      p->lab[p->nLab + q] = ph;
    }
    /* observations exactly as the reference reads them, frame by frame (HFB.c:1009, :1778) */
    for (t = 0; t < T; t++) {
       ReadAsTable(utt->pbuf, t, &utt->ot);
-      for (k = 1; k <= D; k++) B.feat[(size_t)(B.nFrames + t) * D + k - 1] = utt->ot.fv[1][k];
+      for (k = 1; k <= D; k++) p->feat[(size_t)(p->nFrames + t) * D + k - 1] = utt->ot.fv[1][k];
    }
-   B.names[B.nUtt] = strdup(datafn);
-   B.nFrames += T; B.nLab += Q; B.nUtt++;
-   if (B.nUtt >= B.batchUtts || B.nFrames >= B.batchFrames) Flush();
+   p->names[p->nUtt] = strdup(datafn);
+   p->nFrames += T; p->nLab += Q; p->nUtt++;
+   if (p->nUtt >= B.batchUtts || p->nFrames >= B.batchFrames) Flush();
    return FALSE;
 }
 
@@ -310,6 +341,7 @@ void HFBGPU_Finish(int *totalT, LogDouble *totalPr)
    int p, s, g, t, i, j, k, D = B.D, rc;
    long long o;
    Flush();
+   Drain();
    acc = (double *)calloc((size_t)B.L.count, sizeof(double));
    rc = hfbgpu_get_accs(B.ctx, acc);
    if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_get_accs failed: %s", hfbgpu_strerror(rc));
@@ -353,6 +385,7 @@ void HFBGPU_Finish(int *totalT, LogDouble *totalPr)
    *totalT += (int)(acc[B.L.totalT] + 0.5);                             /* HERest.c:779-780 */
    *totalPr += acc[B.L.totalPr];
    free(acc);
+   for (i = 0; i < 2; i++) { hfbgpu_host_free(P[i].feat); P[i].feat = NULL; P[i].featCap = 0; }
    hfbgpu_destroy(B.ctx);
    B.ctx = NULL;
 }

@@ -20,6 +20,7 @@ EXPORTS = [
     "hfbgpu_accumulate", "hfbgpu_accumulate_device", "hfbgpu_acc_device_ptr", "hfbgpu_acc_count",
     "hfbgpu_get_accs", "hfbgpu_set_accs", "hfbgpu_state_loglik", "hfbgpu_get_min_durs",
     "hfbgpu_get_stats", "hfbgpu_reset_stats", "hfbgpu_set_timing", "hfbgpu_set_stream", "hfbgpu_submit", "hfbgpu_wait",
+    "hfbgpu_host_alloc", "hfbgpu_host_free",
 ]
 
 _lib = None

@@ -916,6 +916,14 @@ extern "C" int hfbgpu_submit(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *
 
 extern "C" int hfbgpu_wait(hfbgpu_ctx *c) { return wait_impl(c); }
 
+extern "C" void *hfbgpu_host_alloc(size_t bytes)
+{
+   void *p = nullptr;
+   if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+   return p;
+}
+extern "C" void hfbgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 // ------------------------------------------------------------------------------------------
 // OutP alone
 // ------------------------------------------------------------------------------------------

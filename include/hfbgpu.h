@@ -195,6 +195,13 @@ int hfbgpu_submit(hfbgpu_ctx *ctx, const hfb_batch *batch, hfb_utt_result *res,
                   const hfb_beams *beams, int featOnDevice);
 int hfbgpu_wait(hfbgpu_ctx *ctx);
 
+/* Pinned (page-locked) host memory for the feature matrix of a batch: uploads from it are
+ * asynchronous DMAs that overlap the kernels of the previous batch.  Replaces nothing in the
+ * reference (its observations live in HTK's ParmBuf, HParm.c); the bridge copies frames out of
+ * ReadAsTable into such a buffer.  Returns NULL on failure.                          */
+void *hfbgpu_host_alloc(size_t bytes);
+void  hfbgpu_host_free(void *p);
+
 /* Flat FP64 accumulators: device pointer (for an NCCL all-reduce by the caller)
  * and host download.  Layout: hfbgpu_acc_layout().                                */
 double *hfbgpu_acc_device_ptr(hfbgpu_ctx *ctx);

@@ -59,11 +59,16 @@ def _mmf_params(path, names):
     return fm.mean.astype(np.float64), var, fm.transLogA.astype(np.float64), fm.mixLogWt.astype(np.float64)
 
 
-@pytest.mark.parametrize("case", ["tied_m4", "tee_m2_pruned"])
-def test_herest_gpu_matches_stock_herest(tmp_path, case):
+@pytest.mark.parametrize("case", ["tied_m4", "tee_m2_pruned", "tied_m4_batches_of_3"])
+def test_herest_gpu_matches_stock_herest(tmp_path, case, monkeypatch):
     if not (os.path.exists(HEREST) and os.path.exists(HEREST_GPU)):
         pytest.skip("reference binaries not built (bridge/make_herest_gpu.sh needs /root/reference)")
     tmp = str(tmp_path)
+    if case == "tied_m4_batches_of_3":
+        # 10 utterances in batches of 3: the bridge's two pinned buffers alternate, each refilled by HERest's
+        # file loop while the library works on the other (hfbgpu_submit / hfbgpu_wait), SURVEY 8(f).1
+        monkeypatch.setenv("HFBGPU_BATCH_UTTS", "3")
+        case = "tied_m4"
     if case == "tied_m4":
         hs = synth.make_tied_triphone_set(n_states=50, M=4, n_phys=30, n_logical=45, n_centre=6, seed=31, spread=0.2)
         hs2, fm = _setup(tmp, hs, n_utts=10, T=300, Q=30, seed=4)
