@@ -32,12 +32,14 @@ def _lr_trans(n_emit: int, self_loop: float, skip: float = 0.0, tee: float = 0.0
     return A
 
 
-def _make_state(rng, D, M, centre, mix_spread, name=None) -> State:
+def _make_state(rng, D, M, centre, mix_spread, name=None, dead_component: bool = False) -> State:
     if M == 1:
         w = np.ones(1)
     else:
         w = rng.dirichlet(np.ones(M))
         w = np.maximum(w, 1e-3)
+        if dead_component:
+            w[M - 1] = 5.0e-6         # below MINMIX = 1e-5: HTK skips the component everywhere (HFB.c:953, :1573)
         w = w / w.sum()
     mixes = []
     for m in range(M):
@@ -74,7 +76,11 @@ def make_tied_triphone_set(n_states: int = 5000, M: int = 16, n_phys: int = 8000
     ``n_logical`` logical names mapped onto the physical ones."""
     rng = np.random.default_rng(seed)
     hs = HMMSetDef(D, parm_kind)
-    pool = [_make_state(rng, D, M, spread * rng.standard_normal(D), mix_spread, "ST_%d" % j)
+    # M may be a sequence: per-state component counts, cycled; every 5th multi-component state then also
+    # gets one component below the weight floor
+    Ms = [M] * n_states if np.isscalar(M) else [int(M[j % len(M)]) for j in range(n_states)]
+    pool = [_make_state(rng, D, Ms[j], spread * rng.standard_normal(D), mix_spread, "ST_%d" % j,
+                        dead_component=(not np.isscalar(M) and Ms[j] > 1 and j % 5 == 0))
             for j in range(n_states)]
     tms = [TransMat(_lr_trans(3, float(np.clip(self_loop + 0.1 * rng.standard_normal(), 0.3, 0.85))),
                     "T_c%d" % c) for c in range(n_centre)]

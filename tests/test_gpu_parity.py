@@ -249,6 +249,37 @@ def test_tensor_core_statistics_equal_fp32_statistics(name, monkeypatch):
     assert max(e.values()) < RTOL, e
 
 
+@pytest.mark.parametrize("shape", [
+    dict(D=39, M=[1, 3, 4, 7, 16], parm="MFCC_0_D_A"),      # mixed component counts incl. single Gaussians, dead components
+    dict(D=39, M=20, parm="MFCC_0_D_A"),                    # two 16-component tiles in the statistics kernel, MP = 32
+    dict(D=26, M=5, parm="MFCC_E_D"),                       # 7 of 12 K steps, 4 right-hand-side tiles
+    dict(D=13, M=4, parm="MFCC_0"),                         # one K chunk
+])
+def test_model_shapes_against_oracle(shape):
+    """Kernel template / tiling variants the golden fixtures do not reach, against the C oracle."""
+    from htk_b200 import synth
+    from htk_b200.flat import flatten
+    hs = synth.make_tied_triphone_set(n_states=60, M=shape["M"], n_phys=40, n_logical=40, n_centre=6, D=shape["D"],
+                                      seed=77, spread=0.2, parm_kind=shape["parm"])
+    fm = flatten(hs)
+    feats, labs = synth.sample_corpus(fm, n_utts=6, T=260, Q=24, seed=8)
+    b = Batch(feats, labs, fm.D)
+    kw = dict(prune=(60.0, 30.0, 300.0))
+    fb = _fb(fm, **kw)
+    res, beams = fb.FBFile(b, want_beams=True)
+    acc = fb.GetAccs(); st = fb.stats(); fb.close()
+    oacc, ores, obeams = _oracle(fm, b, kw)
+    assert st.launchesL2R > 0
+    for r, o in zip(res, ores):
+        assert r.status == o[0] and r.pruneThresh == o[3]
+        if o[0] == 0:
+            assert abs(r.pr - o[2]) <= 1e-6 * abs(o[2])
+    for k in ("qLo", "qHi", "sq", "eq"):
+        assert np.array_equal(getattr(beams, k), getattr(obeams, k)), k
+    e = acc_errors(acc, oacc, fm)
+    assert max(e.values()) < RTOL, e
+
+
 def test_submit_wait_equals_blocking_call():
     """hfbgpu_submit / hfbgpu_wait (batches overlapping on two streams) == hfbgpu_accumulate."""
     z, fm, b, kw = load_golden("synth_tied_m4")
