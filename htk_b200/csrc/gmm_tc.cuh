@@ -28,6 +28,7 @@
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 epilogue.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <string.h>
@@ -53,11 +54,17 @@ struct GmmTcModel {
    CUtensorMap mapBhi, mapBlo;         // boxes of MP rows (one state)
    CUtensorMap mapBhiP, mapBloP;       // boxes of min(MP, 64) rows for the CTA-pair kernel
    bool pairReady = false;
+   // FP16 operands of the CTA-pair kernel (3xFP16 split, see gmm_tc2_kernel): rows of TC_KH halfs
+   __half *dBhiH = nullptr, *dBloH = nullptr;
+   float *dScale = nullptr;            // per-dimension power-of-two feature scale
+   CUtensorMap mapBhiH, mapBloH;
+   bool f16Ready = false;
+   float C0H = 0.f, C1H = 0.f;         // symmetrising constant / common part of the Gaussian constants
    void *encodeFn = nullptr;
    float C0 = 0.f;             // symmetrising constant contracted first, subtracted in the epilogue
 };
 
-struct GmmTcWork {             // per-stream expanded feature operand
+struct GmmTcWork {             // per-stream expanded feature operand (floats: TF32 split; halfs: FP16 split)
    float *dAhi = nullptr, *dAlo = nullptr;
    size_t aCapFrames = 0;
    void release()
@@ -67,6 +74,7 @@ struct GmmTcWork {             // per-stream expanded feature operand
       dAhi = dAlo = nullptr; aCapFrames = 0;
    }
 };
+#define TC_KH 128           // expanded K of the FP16 operands: 2 swizzle atoms of 64 halfs
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -135,9 +143,9 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smemAddr)
 }
 // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format TF32 (2<<7, 2<<10), K-major A and B,
 // n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24.
-__device__ __forceinline__ constexpr uint32_t tc_idesc(int M, int N)
+__device__ __forceinline__ constexpr uint32_t tc_idesc(int M, int N, uint32_t fmt = 2u /* TF32; F16 = 0, BF16 = 1 */)
 {
-   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ float tc_ex2(float x)
@@ -180,6 +188,26 @@ gmm_tc_expand_kernel(const float *__restrict__ feat, const float *__restrict__ o
    Alo[f * TC_KE + k] = tc_tf32(v - hi);
 }
 
+// FP16 variant: A'hi / A'lo [frames][128] halfs = split of [ 1 | ((x-o) s)^2 | (x-o) s | 1 | 0... ], s = per-dimension
+// power-of-two scale that brings every dimension to unit-order variance (exact; B carries 1/s, 1/s^2)
+__global__ void __launch_bounds__(TC_KH * 4)
+gmm_tc_expand_f16_kernel(const float *__restrict__ feat, const float *__restrict__ off, const float *__restrict__ scale,
+                         int D, long long nFrames, __half *__restrict__ Ahi, __half *__restrict__ Alo)
+{
+   const int k = threadIdx.x;
+   const long long f = (long long)blockIdx.x * 4 + threadIdx.y;
+   if (f >= nFrames) return;
+   float v = 0.f;
+   if (k == 0) v = 1.f;                                   // pairs with the constant column C0
+   else if (k <= D) { float x = (feat[f * D + k - 1] - off[k - 1]) * scale[k - 1]; v = x * x; }
+   else if (k <= 2 * D) v = (feat[f * D + (k - D - 1)] - off[k - D - 1]) * scale[k - D - 1];
+   else if (k == 2 * D + 1) v = 1.f;                      // pairs with c
+   v = fminf(fmaxf(v, -65000.f), 65000.f);                // outliers beyond 255 sigma saturate instead of becoming inf
+   const __half hi = __float2half_rn(v);
+   Ahi[f * TC_KH + k] = hi;
+   Alo[f * TC_KH + k] = __float2half_rn(v - __half2float(hi));
+}
+
 // ------------------------------------------------------------------------------------------
 // the GEMM + log-sum-exp kernel
 // ------------------------------------------------------------------------------------------
@@ -192,6 +220,7 @@ struct TcParams {
    int GPS;                    // 8-row groups per state
    float C0;
    int kSteps;                 // 8-float K steps that hold data: ceil((2D+2)/8) <= 12; the zero padding is skipped
+   float deadBelow;            // a column maximum below this means "no live component": output log zero
    int dbg;                    // timing experiments only (HFBGPU_TC_DEBUG): 1 = no A_lo x B_hi, 2 = no epilogue math
    long long *trace;           // HFBGPU_TC_TRACE: clock64() timeline of the first pair (tools/tc_trace.py); else null
 };
@@ -342,7 +371,7 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
                   const int colEnd = c * 32 + s0 + G;   // columns consumed so far
                   if (colEnd % MP == 0) {
                      const int slot = n * SPT + colEnd / MP - 1;
-                     float val = (mx < -1.0e29f) ? (float)HFB_LZERO : fmaf(tc_lg2(sum), LN2, mx - C0);
+                     float val = (mx < p.deadBelow) ? (float)HFB_LZERO : fmaf(tc_lg2(sum), LN2, mx - C0);
                      if (t < u.T && slot < u.J) brow[slot] = val;
                      cmx = -INFINITY; csum = 0.f;
                   }
@@ -405,11 +434,17 @@ __device__ __forceinline__ void tc_tma_load_2d_pair(void *smemDst, const CUtenso
    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                 ::"r"(tc_smem_u32(smemDst)), "l"((uint64_t)map), "r"(tc_smem_u32(bar) & TC_PEER_MASK), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
+template <bool F16>
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
 {
-   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                ::"r"(tmemD), "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate) : "memory");
+   if (F16)      // K = 16 halfs per instruction: twice the contraction depth of a TF32 MMA in the same time
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                   "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                   ::"r"(tmemD), "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate) : "memory");
+   else
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                   "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                   ::"r"(tmemD), "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate) : "memory");
 }
 // arrives (once all prior MMAs of the pair have retired) on the barrier at this offset in BOTH CTAs
 __device__ __forceinline__ void tc_commit_pair(uint64_t *bar)
@@ -423,15 +458,18 @@ __device__ __forceinline__ void tc_mbar_arrive_leader(uint64_t *bar)
    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(tc_smem_u32(bar) & TC_PEER_MASK) : "memory");
 }
 
-template <int MP>
+template <int MP, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, TcParams p)
 {
    extern __shared__ uint8_t tc_smem_raw[];
    uint8_t *base = (uint8_t *)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
-   uint8_t *sA = base;                                  // [hi k0,k1,k2 | lo k0,k1,k2] x 16 KB: this CTA's 128 frames
-   uint8_t *sB = base + TC_A_BYTES;                     // stages x [hi 8 KB | lo 8 KB]: this CTA's 64 components
+   constexpr int NCH = F16 ? 2 : 3;                     // 128-byte K chunks of the A block: 2 x 64 halfs or 3 x 32 floats
+   constexpr int KCH = F16 ? 64 : 32;                   // elements per chunk
+   constexpr uint32_t A_BYTES = 2 * NCH * 16384;
+   uint8_t *sA = base;                                  // [hi chunks | lo chunks] x 16 KB: this CTA's 128 frames
+   uint8_t *sB = base + A_BYTES;                        // stages x [hi 8 KB | lo 8 KB]: this CTA's 64 components
    uint64_t *bars = (uint64_t *)(sB + TC2_STAGES * TC2_B_STAGE_BYTES);
    uint64_t *fullA = bars, *emptyA = bars + 1, *fullB = bars + 2, *emptyB = bars + 2 + TC2_STAGES;
    uint64_t *tmemFull = bars + 2 + 2 * TC2_STAGES, *tmemEmpty = tmemFull + 2;
@@ -474,9 +512,10 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
          const int row0 = (int)u.featOff + item.y + (int)rank * TC_BM;
          tc_mbar_wait(emptyA, phA ^ 1);
          if (elected) {
-            if (rank == 0) tc_mbar_expect_tx(fullA, 2 * TC_A_BYTES);
+            if (rank == 0) tc_mbar_expect_tx(fullA, 2 * A_BYTES);
 #pragma unroll
-            for (int j = 0; j < 6; j++) tc_tma_load_2d_pair(sA + j * 16384, j < 3 ? &mapAhi : &mapAlo, fullA, (j % 3) * 32, row0);
+            for (int j = 0; j < 2 * NCH; j++)
+               tc_tma_load_2d_pair(sA + j * 16384, j < NCH ? &mapAhi : &mapAlo, fullA, (j % NCH) * KCH, row0);
          }
          __syncwarp();
          phA ^= 1;
@@ -506,7 +545,7 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                   const int rj = __shfl_sync(0xffffffffu, row, j);
                   if (elected)
                      tc_tma_load_2d_pair(dst + (j / HB) * 8192 + (j % HB) * (BOXR * 128), (j / HB) ? &mapBlo : &mapBhi,
-                                         &fullB[stage], k * 32, rj);
+                                         &fullB[stage], k * KCH, rj);
                }
                __syncwarp();
                if (++stage == TC2_STAGES) { stage = 0; phB ^= 1; }
@@ -520,7 +559,7 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
       if (rank == 0) {
          uint32_t elected;
          asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
-         const uint32_t idesc = tc_idesc(2 * TC_BM, TC_BN);
+         const uint32_t idesc = tc_idesc(2 * TC_BM, TC_BN, F16 ? 0u : 2u);
          const uint32_t aBase = tc_smem_u32(sA), bBase = tc_smem_u32(sB);
          uint32_t stage = 0, phB = 0, phA = 0, tile = 0;
          for (int it = pair; it < p.nItems; it += nPairs) {
@@ -542,16 +581,16 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                   if (elected) TC_TR(0, tile, 3 + 2 * k);
                   tc_fence_after();
                   const uint32_t bHi = bBase + stage * TC2_B_STAGE_BYTES, bLo = bHi + 8192;
-                  const uint32_t aHi = aBase + k * 16384, aLo = aBase + (3 + k) * 16384;
+                  const uint32_t aHi = aBase + k * 16384, aLo = aBase + (NCH + k) * 16384;
 #pragma unroll
                   for (int kk = 0; kk < 4; kk++) {
                      if (k * 4 + kk >= p.kSteps) break;  // columns >= 2D+2 are zero padding
                      const uint64_t dAhi = tc_smem_desc(aHi + kk * 32), dAlo = tc_smem_desc(aLo + kk * 32);
                      const uint64_t dBhi = tc_smem_desc(bHi + kk * 32), dBlo = tc_smem_desc(bLo + kk * 32);
                      if (elected) {
-                        tc_mma_tf32_pair(dMain, dAhi, dBhi, idesc, (k | kk) ? 1u : 0u);
-                        tc_mma_tf32_pair(dCorr, dAhi, dBlo, idesc, (k | kk) ? 1u : 0u);
-                        tc_mma_tf32_pair(dCorr, dAlo, dBhi, idesc, 1u);
+                        tc_mma_pair<F16>(dMain, dAhi, dBhi, idesc, (k | kk) ? 1u : 0u);
+                        tc_mma_pair<F16>(dCorr, dAhi, dBlo, idesc, (k | kk) ? 1u : 0u);
+                        tc_mma_pair<F16>(dCorr, dAlo, dBhi, idesc, 1u);
                      }
                   }
                   if (elected) tc_commit_pair(&emptyB[stage]);   // stage reusable (in both CTAs) once these MMAs retire
@@ -612,7 +651,7 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                   const int colEnd = c * 32 + s0 + G;   // columns consumed so far
                   if (colEnd % MP == 0) {
                      const int slot = n * SPT + colEnd / MP - 1;
-                     float val = (mx < -1.0e29f) ? (float)HFB_LZERO : fmaf(tc_lg2(sum), LN2, mx - C0);
+                     float val = (mx < p.deadBelow) ? (float)HFB_LZERO : fmaf(tc_lg2(sum), LN2, mx - C0);
                      if (t < u.T && slot < u.J) brow[slot] = val;
                      cmx = -INFINITY; csum = 0.f;
                   }
@@ -662,11 +701,26 @@ static inline float tc_host_tf32(float x)
    return r;
 }
 
+static inline int tc_make_map_f16(void *fn, CUtensorMap *map, __half *basePtr, long long rows, int boxRows)
+{
+   cuuint64_t dims[2] = {(cuuint64_t)TC_KH, (cuuint64_t)rows};
+   cuuint64_t strides[1] = {(cuuint64_t)TC_KH * sizeof(__half)};
+   cuuint32_t box[2] = {64, (cuuint32_t)boxRows};
+   cuuint32_t estr[2] = {1, 1};
+   CUresult r = ((TcEncodeFn)fn)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, basePtr, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+   return r == CUDA_SUCCESS ? HFB_OK : HFB_ECUDA;
+}
+
 static inline void gmm_tc_release(GmmTcModel &t)
 {
    if (t.dBhi) cudaFree(t.dBhi);
    if (t.dBlo) cudaFree(t.dBlo);
    if (t.dOffset) cudaFree(t.dOffset);
+   if (t.dBhiH) cudaFree(t.dBhiH);
+   if (t.dBloH) cudaFree(t.dBloH);
+   if (t.dScale) cudaFree(t.dScale);
    t = GmmTcModel();
 }
 
@@ -755,10 +809,81 @@ static inline int gmm_tc_prepare(GmmTcModel &t, const hfb_model *m, cudaStream_t
    t.ready = (cudaGetLastError() == cudaSuccess);
    if (t.ready && tc_make_map(fn, &t.mapBhiP, t.dBhi, t.rows, std::min(MP, 64)) == HFB_OK &&
        tc_make_map(fn, &t.mapBloP, t.dBlo, t.rows, std::min(MP, 64)) == HFB_OK) {
-#define TC_SET_SMEM(MPV) cudaFuncSetAttribute(gmm_tc2_kernel<MPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES)
+#define TC_SET_SMEM(MPV) cudaFuncSetAttribute(gmm_tc2_kernel<MPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES); \
+                         cudaFuncSetAttribute(gmm_tc2_kernel<MPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES)
       TC_SET_SMEM(8); TC_SET_SMEM(16); TC_SET_SMEM(32); TC_SET_SMEM(64); TC_SET_SMEM(128);
 #undef TC_SET_SMEM
       t.pairReady = (cudaGetLastError() == cudaSuccess);
+   }
+   if (t.pairReady && 2 * D + 2 <= TC_KH) {
+      // ---- FP16 operands (3xFP16 split): per-dimension power-of-two scale s_k ~ sqrt(mean inverse variance), so
+      //      that (x-o) s, -ivar / (2 s^2) and (mu-o) ivar / s are all of order one; the common part C1 of the
+      //      Gaussian constants is kept out of the product (added back exactly in the epilogue)
+      std::vector<float> sc(D);
+      for (int k = 0; k < D; k++) {
+         double a = 0.0;
+         for (int g = 0; g < m->numGauss; g++) a += m->ivar[(size_t)g * D + k];
+         a /= m->numGauss;
+         sc[k] = (float)ldexp(1.0, (int)lrint(0.5 * log2(a > 1e-30 ? a : 1e-30)));
+      }
+      std::vector<double> cRow((size_t)t.rows, 0.0);
+      std::vector<char> live((size_t)t.rows, 0);
+      double c1 = 0.0; long long nLive = 0;
+      for (int s2 = 0; s2 < J; s2++) {
+         int mo = m->stateMixOff[s2], Mn = m->stateMixOff[s2 + 1] - mo;
+         for (int k2 = 0; k2 < Mn; k2++) {
+            long long r = (long long)(1 + (long long)s2) * MP + k2;
+            float wt = m->mixLogWt[mo + k2];
+            if (Mn > 1 && !(wt > (float)HFB_LMINMIX)) continue;
+            int g = m->mixGauss[mo + k2];
+            double c = m->gConst[g];
+            for (int k = 0; k < D; k++) {
+               double iv = m->ivar[(size_t)g * D + k], mu = (double)m->mean[(size_t)g * D + k] - (double)offF[k];
+               c += mu * mu * iv;
+            }
+            cRow[r] = -0.5 * c + (Mn > 1 ? (double)wt : 0.0);
+            live[r] = 1; c1 += cRow[r]; nLive++;
+         }
+      }
+      c1 = nLive ? c1 / nLive : 0.0;
+      t.C1H = (float)c1;
+      std::vector<__half> hh((size_t)t.rows * TC_KH, __float2half_rn(0.f)), hl((size_t)t.rows * TC_KH, __float2half_rn(0.f));
+      auto putH = [&](long long r, int k, double v) {
+         float f = (float)v;
+         __half h = __float2half_rn(f);
+         hh[(size_t)r * TC_KH + k] = h;
+         hl[(size_t)r * TC_KH + k] = __float2half_rn(f - __half2float(h));
+      };
+      for (long long r = 0; r < t.rows; r++) if (!live[r]) putH(r, 2 * D + 1, -60000.0);     // dead rows: log zero
+      for (int s2 = 0; s2 < J; s2++) {
+         int mo = m->stateMixOff[s2], Mn = m->stateMixOff[s2 + 1] - mo;
+         for (int k2 = 0; k2 < Mn; k2++) {
+            long long r = (long long)(1 + (long long)s2) * MP + k2;
+            if (!live[r]) continue;
+            int g = m->mixGauss[mo + k2];
+            for (int k = 0; k < D; k++) {
+               double iv = m->ivar[(size_t)g * D + k], mu = (double)m->mean[(size_t)g * D + k] - (double)offF[k], sk = sc[k];
+               putH(r, 1 + k, -0.5 * iv / (sk * sk));
+               putH(r, 1 + D + k, mu * iv / sk);
+            }
+            putH(r, 2 * D + 1, cRow[r] - c1);
+         }
+      }
+      {
+         double eb = -0.5 * D;                                   // expected value of the product part of log b
+         t.C0H = __half2float(__float2half_rn((float)(-0.5 * eb)));
+         for (long long r = 0; r < t.rows; r++) { hh[(size_t)r * TC_KH] = __float2half_rn(t.C0H); hl[(size_t)r * TC_KH] = __float2half_rn(0.f); }
+      }
+      size_t hb = hh.size() * sizeof(__half);
+      if (cudaMalloc(&t.dBhiH, hb) == cudaSuccess && cudaMalloc(&t.dBloH, hb) == cudaSuccess &&
+          cudaMalloc(&t.dScale, D * sizeof(float)) == cudaSuccess) {
+         cudaMemcpyAsync(t.dBhiH, hh.data(), hb, cudaMemcpyHostToDevice, st);
+         cudaMemcpyAsync(t.dBloH, hl.data(), hb, cudaMemcpyHostToDevice, st);
+         cudaMemcpyAsync(t.dScale, sc.data(), D * sizeof(float), cudaMemcpyHostToDevice, st);
+         cudaStreamSynchronize(st);
+         t.f16Ready = tc_make_map_f16(fn, &t.mapBhiH, t.dBhiH, t.rows, std::min(MP, 64)) == HFB_OK &&
+                      tc_make_map_f16(fn, &t.mapBloH, t.dBloH, t.rows, std::min(MP, 64)) == HFB_OK;
+      } else cudaGetLastError();
    }
    return HFB_OK;
 }
@@ -778,33 +903,65 @@ static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm
           cudaMalloc(&wk.dAlo, cap * TC_KE * sizeof(float)) != cudaSuccess) { cudaGetLastError(); wk.release(); return HFB_ENOMEM; }
       wk.aCapFrames = cap;
    }
-   CUtensorMap mapAhi, mapAlo;
-   // rows beyond the wave (at most TC_BM - 1) are allocated but stale: every output row depends on
-   // its own A row only and rows with t >= T are never stored
-   if (tc_make_map(t.encodeFn, &mapAhi, wk.dAhi, waveFrames + TC_BM, TC_BM) ||
-       tc_make_map(t.encodeFn, &mapAlo, wk.dAlo, waveFrames + TC_BM, TC_BM))
-      return HFB_ECUDA;
-   gmm_tc_expand_kernel<<<(unsigned)((waveFrames + 3) / 4), dim3(TC_KE, 4), 0, st>>>(W.feat, t.dOffset, dm.D, waveFrames, wk.dAhi, wk.dAlo);
-   if (afterExpand) cudaEventRecord(afterExpand, st);
    TcParams p;
    p.items = dItems; p.nItems = nItems; p.utt = W.utt; p.slotState = W.slotState; p.b = W.b; p.GPS = t.GPS; p.C0 = t.C0;
    p.kSteps = (2 * dm.D + 2 + 7) / 8;
+   p.deadBelow = -1.0e29f;
    { const char *e = getenv("HFBGPU_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; if (p.dbg & 4) p.kSteps = 12; }
    p.trace = nullptr;
    const char *traceFile = getenv("HFBGPU_TC_TRACE");
    const size_t traceN = (size_t)6 * TC_TRACE_TILES * 16;
    if (traceFile) { cudaMalloc(&p.trace, traceN * sizeof(long long)); cudaMemsetAsync(p.trace, 0, traceN * sizeof(long long), st); }
    if (launches) *launches = 2;
-   if (t.pairReady && smCount >= 2 && !getenv("HFBGPU_NO_PAIR")) {
+   const bool pair = t.pairReady && smCount >= 2 && !getenv("HFBGPU_NO_PAIR");
+   const bool f16 = pair && t.f16Ready && !getenv("HFBGPU_TC_TF32");
+   CUtensorMap mapAhi, mapAlo;
+   // rows beyond the wave (at most 2 TC_BM - 1) are allocated but stale or out of bounds (zero fill): every output
+   // row depends on its own A row only and rows with t >= T are never stored
+   if (f16) {
+      // ---- 3xFP16 split: same buffers, rows of TC_KH halfs (256 B) instead of TC_KE floats (384 B)
+      __half *ahi = (__half *)wk.dAhi, *alo = (__half *)wk.dAlo;
+      if (tc_make_map_f16(t.encodeFn, &mapAhi, ahi, waveFrames + TC_BM, TC_BM) ||
+          tc_make_map_f16(t.encodeFn, &mapAlo, alo, waveFrames + TC_BM, TC_BM))
+         return HFB_ECUDA;
+      gmm_tc_expand_f16_kernel<<<(unsigned)((waveFrames + 3) / 4), dim3(TC_KH, 4), 0, st>>>(W.feat, t.dOffset, t.dScale, dm.D, waveFrames, ahi, alo);
+      if (afterExpand) cudaEventRecord(afterExpand, st);
+      p.items = dItems2; p.nItems = nItems2;
+      p.C0 = t.C0H - t.C1H;                              // the epilogue subtracts C0 and adds the common constant C1 back
+      p.kSteps = (2 * dm.D + 2 + 15) / 16;               // 16 halfs per MMA
+      p.deadBelow = -50000.f;
+      const int grid2 = 2 * std::min(nItems2, smCount / 2);
+      switch (t.MP) {
+      case 8: gmm_tc2_kernel<8, true><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
+      case 16: gmm_tc2_kernel<16, true><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
+      case 32: gmm_tc2_kernel<32, true><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
+      case 64: gmm_tc2_kernel<64, true><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
+      default: gmm_tc2_kernel<128, true><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
+      }
+      if (traceFile) {                                  // diagnostics only: synchronous dump of the timeline
+         std::vector<long long> h(traceN);
+         cudaStreamSynchronize(st);
+         cudaMemcpy(h.data(), p.trace, traceN * sizeof(long long), cudaMemcpyDeviceToHost);
+         cudaFree(p.trace);
+         if (FILE *f = fopen(traceFile, "wb")) { fwrite(h.data(), sizeof(long long), traceN, f); fclose(f); }
+      }
+      return HFB_OK;
+   }
+   if (tc_make_map(t.encodeFn, &mapAhi, wk.dAhi, waveFrames + TC_BM, TC_BM) ||
+       tc_make_map(t.encodeFn, &mapAlo, wk.dAlo, waveFrames + TC_BM, TC_BM))
+      return HFB_ECUDA;
+   gmm_tc_expand_kernel<<<(unsigned)((waveFrames + 3) / 4), dim3(TC_KE, 4), 0, st>>>(W.feat, t.dOffset, dm.D, waveFrames, wk.dAhi, wk.dAlo);
+   if (afterExpand) cudaEventRecord(afterExpand, st);
+   if (pair) {
       // CTA pairs: one work item = (utterance, 256 frames), 128 per CTA
       p.items = dItems2; p.nItems = nItems2;
       const int grid2 = 2 * std::min(nItems2, smCount / 2);
       switch (t.MP) {
-      case 8: gmm_tc2_kernel<8><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
-      case 16: gmm_tc2_kernel<16><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
-      case 32: gmm_tc2_kernel<32><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
-      case 64: gmm_tc2_kernel<64><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
-      default: gmm_tc2_kernel<128><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
+      case 8: gmm_tc2_kernel<8, false><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
+      case 16: gmm_tc2_kernel<16, false><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
+      case 32: gmm_tc2_kernel<32, false><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
+      case 64: gmm_tc2_kernel<64, false><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
+      default: gmm_tc2_kernel<128, false><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
       }
       if (traceFile) {                                  // diagnostics only: synchronous dump of the timeline
          std::vector<long long> h(traceN);

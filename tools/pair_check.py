@@ -1,4 +1,5 @@
-"""Compare the CTA-pair GMM kernel with the single-CTA one and with an FP64 evaluation (OutP only)."""
+"""Compare the GMM kernel variants (CTA pair 3xFP16 = default, CTA pair 3xTF32, single CTA 3xTF32) with each
+other and with an FP64 evaluation (OutP only)."""
 import os, sys, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from htk_b200.estep import ForwardBackward
@@ -21,10 +22,11 @@ for s in range(fm.J):
     lp = -0.5 * (gc[g][None] + np.sum(d * d * iv[g][None], axis=2)) + fm.mixLogWt[o:e].astype(np.float64)[None]
     m = lp.max(1); ex[:, s] = m + np.log(np.exp(lp - m[:, None]).sum(1))
 res = {}
-for name, env in (("pair", None), ("single", "HFBGPU_NO_PAIR")):
+for name, env in (("f16", None), ("pair", "HFBGPU_TC_TF32"), ("single", "HFBGPU_NO_PAIR")):
     if env: os.environ[env] = "1"
     fb = ForwardBackward(fm, gmm_kernel=2); got = fb.OutP(feat, states).astype(np.float64); fb.close()
     if env: del os.environ[env]
     res[name] = got
     print("%-6s vs exact: max %.2e mean %.2e" % (name, np.abs(got - ex).max(), np.abs(got - ex).mean()), flush=True)
 print("pair vs single: max %.2e" % np.abs(res["pair"] - res["single"]).max())
+print("f16 vs pair(tf32): max %.2e mean %.2e" % (np.abs(res["f16"] - res["pair"]).max(), np.abs(res["f16"] - res["pair"]).mean()))
