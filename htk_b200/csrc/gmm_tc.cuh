@@ -414,7 +414,8 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
 // ------------------------------------------------------------------------------------------
 #define TC2_STAGES 6
 #define TC2_B_STAGE_BYTES 16384
-#define TC2_SMEM_BYTES (TC_A_BYTES + TC2_STAGES * TC2_B_STAGE_BYTES + 512 + 1024)
+#define TC2_THREADS 320        // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue
+#define TC2_SMEM_BYTES (TC_A_BYTES + 8 * TC2_B_STAGE_BYTES + 512 + 1024)   // = 64 KB A + 5 x 32 KB tile stages for 3xFP16
 #define TC_PEER_MASK 0xFEFFFFFFu      // clears the CTA-rank bit of a shared::cluster address (cute::Sm100MmaPeerBitMask)
 
 __device__ __forceinline__ uint32_t tc_cluster_ctarank()
@@ -459,7 +460,7 @@ __device__ __forceinline__ void tc_mbar_arrive_leader(uint64_t *bar)
 }
 
 template <int MP, bool F16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, TcParams p)
 {
@@ -469,10 +470,16 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
    constexpr int KCH = F16 ? 64 : 32;                   // elements per chunk
    constexpr uint32_t A_BYTES = 2 * NCH * 16384;
    uint8_t *sA = base;                                  // [hi chunks | lo chunks] x 16 KB: this CTA's 128 frames
-   uint8_t *sB = base + A_BYTES;                        // stages x [hi 8 KB | lo 8 KB]: this CTA's 64 components
-   uint64_t *bars = (uint64_t *)(sB + TC2_STAGES * TC2_B_STAGE_BYTES);
-   uint64_t *fullA = bars, *emptyA = bars + 1, *fullB = bars + 2, *emptyB = bars + 2 + TC2_STAGES;
-   uint64_t *tmemFull = bars + 2 + 2 * TC2_STAGES, *tmemEmpty = tmemFull + 2;
+   // B ring.  3xTF32: one stage = one 128-byte K chunk [hi 8 KB | lo 8 KB] of this CTA's 64 components, separate main /
+   // correction accumulators.  3xFP16: one stage = the WHOLE tile (both K chunks), because the MMAs of a tile are issued
+   // corrections first, main products last, into ONE accumulator (see the MMA issuer) -- the epilogue then reads half
+   // as much TMEM, which at ~64 B/clk was the bound of the two-accumulator version (131 KB per tile = 2048 cycles).
+   constexpr int NST = F16 ? 5 : TC2_STAGES;
+   constexpr uint32_t ST_BYTES = F16 ? NCH * 16384 : TC2_B_STAGE_BYTES;
+   uint8_t *sB = base + A_BYTES;
+   uint64_t *bars = (uint64_t *)(sB + NST * ST_BYTES);
+   uint64_t *fullA = bars, *emptyA = bars + 1, *fullB = bars + 2, *emptyB = bars + 2 + NST;
+   uint64_t *tmemFull = bars + 2 + 2 * NST, *tmemEmpty = tmemFull + 2;
    uint32_t *tmemSlot = (uint32_t *)(tmemEmpty + 2);
    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const uint32_t rank = tc_cluster_ctarank();          // 0 = leader (issues the MMAs)
@@ -480,8 +487,8 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 
    if (warp == 0 && lane == 0) {
       tc_mbar_init(fullA, 1); tc_mbar_init(emptyA, 1);
-      for (int s = 0; s < TC2_STAGES; s++) { tc_mbar_init(&fullB[s], 1); tc_mbar_init(&emptyB[s], 1); }
-      for (int s = 0; s < 2; s++) { tc_mbar_init(&tmemFull[s], 1); tc_mbar_init(&tmemEmpty[s], 8); }
+      for (int s = 0; s < NST; s++) { tc_mbar_init(&fullB[s], 1); tc_mbar_init(&emptyB[s], 1); }
+      for (int s = 0; s < 2; s++) { tc_mbar_init(&tmemFull[s], 1); tc_mbar_init(&tmemEmpty[s], 2 * ((MP <= 64) ? 8 : 4)); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    if (warp == 1) {
@@ -493,6 +500,9 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
    tc_fence_after();
    const uint32_t tmem = *tmemSlot;
    constexpr int SPT = TC_BN / MP;                      // states per tile
+   // epilogue warps: 8 when a state's columns fit one 64-column half (two warps per TMEM lane quadrant, each
+   // taking half of the tile's columns: the epilogue, not the MMAs, bounds the FP16 kernel otherwise), else 4
+   constexpr int EPW = (MP <= 64) ? 8 : 4;
    constexpr int HB = (SPT >= 2) ? SPT / 2 : 1;         // B boxes per operand half held by one CTA
    constexpr int BOXR = (MP < 64) ? MP : 64;            // rows per box (the B tensor maps are built with this)
    const int nChunks = (p.kSteps + 3) >> 2;
@@ -534,6 +544,25 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
          for (int n = 0; n < nTiles; n++, ptile++) {
             const int row = rowNext;
             rowNext = box_row(n + 1);                           // the state lookup of the next tile is in flight meanwhile
+            if (F16) {
+               // one stage per tile: all K chunks of this CTA's half of the B tile
+               if (elected) TC_TR(2, ptile, 0);
+               tc_mbar_wait(&emptyB[stage], phB ^ 1);
+               if (elected) TC_TR(2, ptile, 1);
+               if (elected && rank == 0) tc_mbar_expect_tx(&fullB[stage], 2 * nChunks * 16384);
+               for (int k = 0; k < nChunks; k++) {
+                  uint8_t *dst = sB + stage * ST_BYTES + k * 16384;
+#pragma unroll
+                  for (int j = 0; j < 2 * HB; j++) {
+                     const int rj = __shfl_sync(0xffffffffu, row, j);
+                     if (elected)
+                        tc_tma_load_2d_pair(dst + (j / HB) * 8192 + (j % HB) * (BOXR * 128), (j / HB) ? &mapBlo : &mapBhi,
+                                            &fullB[stage], k * KCH, rj);
+                  }
+               }
+               __syncwarp();
+               if (++stage == NST) { stage = 0; phB ^= 1; }
+            } else
             for (int k = 0; k < nChunks; k++) {
                if (elected) TC_TR(2, ptile, k * 2);
                tc_mbar_wait(&emptyB[stage], phB ^ 1);
@@ -548,7 +577,7 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                                          &fullB[stage], k * KCH, rj);
                }
                __syncwarp();
-               if (++stage == TC2_STAGES) { stage = 0; phB ^= 1; }
+               if (++stage == NST) { stage = 0; phB ^= 1; }
             }
          }
       }
@@ -575,6 +604,37 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                if (elected) TC_TR(0, tile, 1);
                tc_fence_after();
                const uint32_t dMain = tmem + as * (2 * TC_BN), dCorr = dMain + TC_BN;
+               if (F16) {
+                  // 3xFP16, one accumulator: the small correction products (A_hi x B_lo, A_lo x B_hi) of ALL K steps
+                  // first -- the accumulator is still ~1e-2, so the tensor core's truncating accumulation costs
+                  // nothing -- then the five large A_hi x B_hi products, starting with the symmetrising constant column
+                  if (elected) TC_TR(0, tile, 2);
+                  tc_mbar_wait(&fullB[stage], phB);
+                  if (elected) TC_TR(0, tile, 3);
+                  tc_fence_after();
+                  const uint32_t bSt = bBase + stage * ST_BYTES;
+#pragma unroll
+                  for (int ks = 0; ks < 4 * NCH; ks++) {
+                     if (ks >= p.kSteps) break;
+                     const uint32_t o = (ks >> 2) * 16384 + (ks & 3) * 32;
+                     const uint64_t dAhi = tc_smem_desc(aBase + o), dAlo = tc_smem_desc(aBase + NCH * 16384 + o);
+                     const uint64_t dBhi = tc_smem_desc(bSt + o), dBlo = tc_smem_desc(bSt + o + 8192);
+                     if (elected) {
+                        tc_mma_pair<F16>(dMain, dAhi, dBlo, idesc, ks ? 1u : 0u);
+                        tc_mma_pair<F16>(dMain, dAlo, dBhi, idesc, 1u);
+                     }
+                  }
+#pragma unroll
+                  for (int ks = 0; ks < 4 * NCH; ks++) {
+                     if (ks >= p.kSteps) break;
+                     const uint32_t o = (ks >> 2) * 16384 + (ks & 3) * 32;
+                     const uint64_t dAhi = tc_smem_desc(aBase + o), dBhi = tc_smem_desc(bSt + o);
+                     if (elected) tc_mma_pair<F16>(dMain, dAhi, dBhi, idesc, 1u);
+                  }
+                  if (elected) tc_commit_pair(&emptyB[stage]);
+                  __syncwarp();
+                  if (++stage == NST) { stage = 0; phB ^= 1; }
+               } else
                for (int k = 0; k < nChunks; k++) {
                   if (elected) TC_TR(0, tile, 2 + 2 * k);
                   tc_mbar_wait(&fullB[stage], phB);
@@ -595,7 +655,7 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                   }
                   if (elected) tc_commit_pair(&emptyB[stage]);   // stage reusable (in both CTAs) once these MMAs retire
                   __syncwarp();
-                  if (++stage == TC2_STAGES) { stage = 0; phB ^= 1; }
+                  if (++stage == NST) { stage = 0; phB ^= 1; }
                }
                if (elected) tc_commit_pair(&tmemFull[as]);       // accumulators ready for both CTAs' epilogues
                __syncwarp();
@@ -605,9 +665,11 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             __syncwarp();
          }
       }
-   } else {
+   } else if (warp - 2 < EPW) {
       // ================= epilogue (both CTAs): own 128 frames x 128 components =================
       const int quad = warp & 3;                        // TMEM lane quadrant this warp may read
+      constexpr int CPW = (TC_BN / 32) * 4 / EPW;       // 32-column chunks per warp: 4, or 2 with eight warps
+      const int c0 = ((warp - 2) >> 2) * CPW;           // first chunk of this warp
       const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
       uint32_t tile = 0;
       for (int it = pair; it < p.nItems; it += nPairs) {
@@ -626,13 +688,17 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             const float C0 = p.C0;
             float cmx = -INFINITY, csum = 0.f;          // carry for states wider than one 32-column chunk
 #pragma unroll
-            for (int c = 0; c < TC_BN / 32; c++) {
+            for (int cc = 0; cc < CPW; cc++) {
                if (p.dbg & 2) break;
-               float v[32], vc[32];
+               const int c = c0 + cc;
+               float v[32];
                tc_tmem_ld32(taddr + c * 32, v);
-               tc_tmem_ld32(taddr + TC_BN + c * 32, vc);
+               if (!F16) {                              // 3xTF32: main + correction accumulator
+                  float vc[32];
+                  tc_tmem_ld32(taddr + TC_BN + c * 32, vc);
 #pragma unroll
-               for (int i = 0; i < 32; i++) v[i] += vc[i];
+                  for (int i = 0; i < 32; i++) v[i] += vc[i];
+               }
                constexpr int G = (MP < 32) ? MP : 32;   // columns of one state inside this chunk
 #pragma unroll
                for (int s0 = 0; s0 < 32; s0 += G) {
@@ -932,11 +998,11 @@ static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm
       p.deadBelow = -50000.f;
       const int grid2 = 2 * std::min(nItems2, smCount / 2);
       switch (t.MP) {
-      case 8: gmm_tc2_kernel<8, true><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
-      case 16: gmm_tc2_kernel<16, true><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
-      case 32: gmm_tc2_kernel<32, true><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
-      case 64: gmm_tc2_kernel<64, true><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
-      default: gmm_tc2_kernel<128, true><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
+      case 8: gmm_tc2_kernel<8, true><<<grid2, TC2_THREADS, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
+      case 16: gmm_tc2_kernel<16, true><<<grid2, TC2_THREADS, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
+      case 32: gmm_tc2_kernel<32, true><<<grid2, TC2_THREADS, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
+      case 64: gmm_tc2_kernel<64, true><<<grid2, TC2_THREADS, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
+      default: gmm_tc2_kernel<128, true><<<grid2, TC2_THREADS, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
       }
       if (traceFile) {                                  // diagnostics only: synchronous dump of the timeline
          std::vector<long long> h(traceN);
@@ -957,11 +1023,11 @@ static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm
       p.items = dItems2; p.nItems = nItems2;
       const int grid2 = 2 * std::min(nItems2, smCount / 2);
       switch (t.MP) {
-      case 8: gmm_tc2_kernel<8, false><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
-      case 16: gmm_tc2_kernel<16, false><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
-      case 32: gmm_tc2_kernel<32, false><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
-      case 64: gmm_tc2_kernel<64, false><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
-      default: gmm_tc2_kernel<128, false><<<grid2, 192, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
+      case 8: gmm_tc2_kernel<8, false><<<grid2, TC2_THREADS, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
+      case 16: gmm_tc2_kernel<16, false><<<grid2, TC2_THREADS, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
+      case 32: gmm_tc2_kernel<32, false><<<grid2, TC2_THREADS, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
+      case 64: gmm_tc2_kernel<64, false><<<grid2, TC2_THREADS, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
+      default: gmm_tc2_kernel<128, false><<<grid2, TC2_THREADS, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiP, t.mapBloP, p); break;
       }
       if (traceFile) {                                  // diagnostics only: synchronous dump of the timeline
          std::vector<long long> h(traceN);
