@@ -67,11 +67,12 @@ struct GmmTcModel {
 struct GmmTcWork {             // per-stream expanded feature operand (floats: TF32 split; halfs: FP16 split)
    float *dAhi = nullptr, *dAlo = nullptr;
    size_t aCapFrames = 0;
+   bool f16Init = false;       // constant / padding columns of the FP16 layout are in place
    void release()
    {
       if (dAhi) cudaFree(dAhi);
       if (dAlo) cudaFree(dAlo);
-      dAhi = dAlo = nullptr; aCapFrames = 0;
+      dAhi = dAlo = nullptr; aCapFrames = 0; f16Init = false;
    }
 };
 #define TC_KH 128           // expanded K of the FP16 operands: 2 swizzle atoms of 64 halfs
@@ -189,23 +190,33 @@ gmm_tc_expand_kernel(const float *__restrict__ feat, const float *__restrict__ o
 }
 
 // FP16 variant: A'hi / A'lo [frames][128] halfs = split of [ 1 | ((x-o) s)^2 | (x-o) s | 1 | 0... ], s = per-dimension
-// power-of-two scale that brings every dimension to unit-order variance (exact; B carries 1/s, 1/s^2)
-__global__ void __launch_bounds__(TC_KH * 4)
+// power-of-two scale that brings every dimension to unit-order variance (exact; B carries 1/s, 1/s^2).
+// The constant and padding columns never change: gmm_tc_init_f16_kernel writes them once per buffer, the per-wave
+// kernel only writes the 2 D data columns (thread = (dimension, frame)).
+__global__ void __launch_bounds__(256)
+gmm_tc_init_f16_kernel(int D, long long nRows, __half *__restrict__ Ahi, __half *__restrict__ Alo)
+{
+   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (idx >= nRows * TC_KH) return;
+   const int k = (int)(idx % TC_KH);
+   Ahi[idx] = __float2half_rn((k == 0 || k == 2 * D + 1) ? 1.f : 0.f);
+   Alo[idx] = __float2half_rn(0.f);
+}
+
+__global__ void __launch_bounds__(64 * 8)
 gmm_tc_expand_f16_kernel(const float *__restrict__ feat, const float *__restrict__ off, const float *__restrict__ scale,
                          int D, long long nFrames, __half *__restrict__ Ahi, __half *__restrict__ Alo)
 {
-   const int k = threadIdx.x;
-   const long long f = (long long)blockIdx.x * 4 + threadIdx.y;
-   if (f >= nFrames) return;
-   float v = 0.f;
-   if (k == 0) v = 1.f;                                   // pairs with the constant column C0
-   else if (k <= D) { float x = (feat[f * D + k - 1] - off[k - 1]) * scale[k - 1]; v = x * x; }
-   else if (k <= 2 * D) v = (feat[f * D + (k - D - 1)] - off[k - D - 1]) * scale[k - D - 1];
-   else if (k == 2 * D + 1) v = 1.f;                      // pairs with c
-   v = fminf(fmaxf(v, -65000.f), 65000.f);                // outliers beyond 255 sigma saturate instead of becoming inf
-   const __half hi = __float2half_rn(v);
-   Ahi[f * TC_KH + k] = hi;
-   Alo[f * TC_KH + k] = __float2half_rn(v - __half2float(hi));
+   const int d = threadIdx.x;
+   const long long f = (long long)blockIdx.x * 8 + threadIdx.y;
+   if (d >= D || f >= nFrames) return;
+   const float x = (feat[f * D + d] - off[d]) * scale[d];
+   // outliers beyond 255 sigma saturate instead of becoming inf
+   const float v1 = fminf(fmaxf(x, -65000.f), 65000.f), v2 = fminf(x * x, 65000.f);
+   const __half h1 = __float2half_rn(v1), h2 = __float2half_rn(v2);
+   __half *hi = Ahi + f * TC_KH, *lo = Alo + f * TC_KH;
+   hi[1 + d] = h2;     lo[1 + d] = __float2half_rn(v2 - __half2float(h2));
+   hi[1 + D + d] = h1; lo[1 + D + d] = __float2half_rn(v1 - __half2float(h1));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -468,13 +479,18 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
    uint8_t *base = (uint8_t *)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
    constexpr int NCH = F16 ? 2 : 3;                     // 128-byte K chunks of the A block: 2 x 64 halfs or 3 x 32 floats
    constexpr int KCH = F16 ? 64 : 32;                   // elements per chunk
-   constexpr uint32_t A_BYTES = 2 * NCH * 16384;
+   // 3xFP16: TWO 128-frame blocks per CTA (work item = 512 frames per pair) share every B stage -- half the L2 -> SM
+   // bytes per frame again (the B stream, ~6 TB/s chip-wide, is what bounds the kernel); with one accumulator per
+   // block, 2 blocks x 2 buffers x 128 columns = all 512 TMEM columns.
+   constexpr int NBLK = F16 ? 2 : 1;
+   constexpr uint32_t A_BLK = 2 * NCH * 16384;          // one block: [hi chunks | lo chunks]
+   constexpr uint32_t A_BYTES = NBLK * A_BLK;
    uint8_t *sA = base;                                  // [hi chunks | lo chunks] x 16 KB: this CTA's 128 frames
    // B ring.  3xTF32: one stage = one 128-byte K chunk [hi 8 KB | lo 8 KB] of this CTA's 64 components, separate main /
    // correction accumulators.  3xFP16: one stage = the WHOLE tile (both K chunks), because the MMAs of a tile are issued
    // corrections first, main products last, into ONE accumulator (see the MMA issuer) -- the epilogue then reads half
    // as much TMEM, which at ~64 B/clk was the bound of the two-accumulator version (131 KB per tile = 2048 cycles).
-   constexpr int NST = F16 ? 5 : TC2_STAGES;
+   constexpr int NST = F16 ? 3 : TC2_STAGES;
    constexpr uint32_t ST_BYTES = F16 ? NCH * 16384 : TC2_B_STAGE_BYTES;
    uint8_t *sB = base + A_BYTES;
    uint64_t *bars = (uint64_t *)(sB + NST * ST_BYTES);
@@ -519,13 +535,17 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
       for (int it = pair; it < p.nItems; it += nPairs) {
          const int2 item = p.items[it];
          const UttDesc u = p.utt[item.x];
-         const int row0 = (int)u.featOff + item.y + (int)rank * TC_BM;
+         // block b of CTA r holds frames item.y + (2 b + r) 128 ..; a block that starts beyond T is neither loaded nor used
+         const int nBlk = (NBLK == 2 && u.T - item.y > 2 * TC_BM) ? 2 : 1;
          tc_mbar_wait(emptyA, phA ^ 1);
          if (elected) {
-            if (rank == 0) tc_mbar_expect_tx(fullA, 2 * A_BYTES);
+            if (rank == 0) tc_mbar_expect_tx(fullA, 2 * nBlk * A_BLK);
+            for (int b = 0; b < nBlk; b++) {
+               const int row0 = (int)u.featOff + item.y + (2 * b + (int)rank) * TC_BM;
 #pragma unroll
-            for (int j = 0; j < 2 * NCH; j++)
-               tc_tma_load_2d_pair(sA + j * 16384, j < NCH ? &mapAhi : &mapAlo, fullA, (j % NCH) * KCH, row0);
+               for (int j = 0; j < 2 * NCH; j++)
+                  tc_tma_load_2d_pair(sA + b * A_BLK + j * 16384, j < NCH ? &mapAhi : &mapAlo, fullA, (j % NCH) * KCH, row0);
+            }
          }
          __syncwarp();
          phA ^= 1;
@@ -595,6 +615,7 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             const int2 item = p.items[it];
             const UttDesc u = p.utt[item.x];
             const int nTiles = (u.J + SPT - 1) / SPT;
+            const int nBlk = (NBLK == 2 && u.T - item.y > 2 * TC_BM) ? 2 : 1;
             tc_mbar_wait(fullA, phA);
             phA ^= 1;
             for (int n = 0; n < nTiles; n++, tile++) {
@@ -613,23 +634,26 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                   if (elected) TC_TR(0, tile, 3);
                   tc_fence_after();
                   const uint32_t bSt = bBase + stage * ST_BYTES;
+                  for (int b = 0; b < nBlk; b++) {
+                     const uint32_t aB = aBase + b * A_BLK, dAcc = dMain + b * TC_BN;
 #pragma unroll
-                  for (int ks = 0; ks < 4 * NCH; ks++) {
-                     if (ks >= p.kSteps) break;
-                     const uint32_t o = (ks >> 2) * 16384 + (ks & 3) * 32;
-                     const uint64_t dAhi = tc_smem_desc(aBase + o), dAlo = tc_smem_desc(aBase + NCH * 16384 + o);
-                     const uint64_t dBhi = tc_smem_desc(bSt + o), dBlo = tc_smem_desc(bSt + o + 8192);
-                     if (elected) {
-                        tc_mma_pair<F16>(dMain, dAhi, dBlo, idesc, ks ? 1u : 0u);
-                        tc_mma_pair<F16>(dMain, dAlo, dBhi, idesc, 1u);
+                     for (int ks = 0; ks < 4 * NCH; ks++) {
+                        if (ks >= p.kSteps) break;
+                        const uint32_t o = (ks >> 2) * 16384 + (ks & 3) * 32;
+                        const uint64_t dAhi = tc_smem_desc(aB + o), dAlo = tc_smem_desc(aB + NCH * 16384 + o);
+                        const uint64_t dBhi = tc_smem_desc(bSt + o), dBlo = tc_smem_desc(bSt + o + 8192);
+                        if (elected) {
+                           tc_mma_pair<F16>(dAcc, dAhi, dBlo, idesc, ks ? 1u : 0u);
+                           tc_mma_pair<F16>(dAcc, dAlo, dBhi, idesc, 1u);
+                        }
                      }
-                  }
 #pragma unroll
-                  for (int ks = 0; ks < 4 * NCH; ks++) {
-                     if (ks >= p.kSteps) break;
-                     const uint32_t o = (ks >> 2) * 16384 + (ks & 3) * 32;
-                     const uint64_t dAhi = tc_smem_desc(aBase + o), dBhi = tc_smem_desc(bSt + o);
-                     if (elected) tc_mma_pair<F16>(dMain, dAhi, dBhi, idesc, 1u);
+                     for (int ks = 0; ks < 4 * NCH; ks++) {
+                        if (ks >= p.kSteps) break;
+                        const uint32_t o = (ks >> 2) * 16384 + (ks & 3) * 32;
+                        const uint64_t dAhi = tc_smem_desc(aB + o), dBhi = tc_smem_desc(bSt + o);
+                        if (elected) tc_mma_pair<F16>(dAcc, dAhi, dBhi, idesc, 1u);
+                     }
                   }
                   if (elected) tc_commit_pair(&emptyB[stage]);
                   __syncwarp();
@@ -676,15 +700,17 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
          const int2 item = p.items[it];
          const UttDesc u = p.utt[item.x];
          const int nTiles = (u.J + SPT - 1) / SPT;
-         const int t = item.y + (int)rank * TC_BM + quad * 32 + lane;
-         float *brow = p.b + u.bOff + (size_t)t * u.J;
+         const int nBlk = (NBLK == 2 && u.T - item.y > 2 * TC_BM) ? 2 : 1;
          for (int n = 0; n < nTiles; n++, tile++) {
             const uint32_t as = tile & 1, phT = (tile >> 1) & 1;
             if (warp == 2 && lane == 0) TC_TR(1, tile, 0);
             tc_mbar_wait(&tmemFull[as], phT);
             if (warp == 2 && lane == 0) TC_TR(1, tile, 1);
             tc_fence_after();
-            const uint32_t taddr = tmem + as * (2 * TC_BN) + ((uint32_t)(quad * 32) << 16);
+            for (int blk = 0; blk < nBlk; blk++) {
+            const int t = item.y + (2 * blk + (int)rank) * TC_BM + quad * 32 + lane;
+            float *brow = p.b + u.bOff + (size_t)t * u.J;
+            const uint32_t taddr = tmem + as * (2 * TC_BN) + blk * TC_BN + ((uint32_t)(quad * 32) << 16);
             const float C0 = p.C0;
             float cmx = -INFINITY, csum = 0.f;          // carry for states wider than one 32-column chunk
 #pragma unroll
@@ -722,6 +748,7 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                      cmx = -INFINITY; csum = 0.f;
                   }
                }
+            }
             }
             tc_fence_before();
             __syncwarp();
@@ -956,7 +983,8 @@ static inline int gmm_tc_prepare(GmmTcModel &t, const hfb_model *m, cudaStream_t
 
 // Launches expansion + GEMM for every utterance of the wave.  `items` lives in the wave blob.
 static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm, const Wave &W, long long waveFrames,
-                                const int2 *dItems, int nItems, const int2 *dItems2, int nItems2, int smCount,
+                                const int2 *dItems, int nItems, const int2 *dItems2, int nItems2,
+                                const int2 *dItems4, int nItems4, int smCount,
                                 cudaStream_t st, int *launches, cudaEvent_t afterExpand = nullptr)
 {
    if (!t.ready) return HFB_EUNSUPPORTED;
@@ -990,13 +1018,18 @@ static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm
       if (tc_make_map_f16(t.encodeFn, &mapAhi, ahi, waveFrames + TC_BM, TC_BM) ||
           tc_make_map_f16(t.encodeFn, &mapAlo, alo, waveFrames + TC_BM, TC_BM))
          return HFB_ECUDA;
-      gmm_tc_expand_f16_kernel<<<(unsigned)((waveFrames + 3) / 4), dim3(TC_KH, 4), 0, st>>>(W.feat, t.dOffset, t.dScale, dm.D, waveFrames, ahi, alo);
+      if (!wk.f16Init) {
+         const long long n = (long long)wk.aCapFrames * TC_KH;
+         gmm_tc_init_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dm.D, (long long)wk.aCapFrames, ahi, alo);
+         wk.f16Init = true;
+      }
+      gmm_tc_expand_f16_kernel<<<(unsigned)((waveFrames + 7) / 8), dim3(64, 8), 0, st>>>(W.feat, t.dOffset, t.dScale, dm.D, waveFrames, ahi, alo);
       if (afterExpand) cudaEventRecord(afterExpand, st);
-      p.items = dItems2; p.nItems = nItems2;
+      p.items = dItems4; p.nItems = nItems4;            // work items of 4 x 128 frames: two blocks per CTA
       p.C0 = t.C0H - t.C1H;                              // the epilogue subtracts C0 and adds the common constant C1 back
       p.kSteps = (2 * dm.D + 2 + 15) / 16;               // 16 halfs per MMA
       p.deadBelow = -50000.f;
-      const int grid2 = 2 * std::min(nItems2, smCount / 2);
+      const int grid2 = 2 * std::min(nItems4, smCount / 2);
       switch (t.MP) {
       case 8: gmm_tc2_kernel<8, true><<<grid2, TC2_THREADS, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
       case 16: gmm_tc2_kernel<16, true><<<grid2, TC2_THREADS, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
@@ -1016,6 +1049,7 @@ static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm
    if (tc_make_map(t.encodeFn, &mapAhi, wk.dAhi, waveFrames + TC_BM, TC_BM) ||
        tc_make_map(t.encodeFn, &mapAlo, wk.dAlo, waveFrames + TC_BM, TC_BM))
       return HFB_ECUDA;
+   wk.f16Init = false;                                  // the float layout overwrites the FP16 constant columns
    gmm_tc_expand_kernel<<<(unsigned)((waveFrames + 3) / 4), dim3(TC_KE, 4), 0, st>>>(W.feat, t.dOffset, dm.D, waveFrames, wk.dAhi, wk.dAlo);
    if (afterExpand) cudaEventRecord(afterExpand, st);
    if (pair) {

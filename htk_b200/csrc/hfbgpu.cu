@@ -77,6 +77,7 @@ struct WaveTables {
    std::vector<int> posPre, tilePre;
    std::vector<int2> tcItems;        // (utterance, first frame) blocks of TC_BM frames for the tcgen05 kernel
    std::vector<int2> tcItems2;       // the same in blocks of 2*TC_BM frames for the CTA-pair kernel
+   std::vector<int2> tcItems4;       // ... and of 4*TC_BM frames (two blocks per CTA, 3xFP16 path)
    std::vector<int> uttIndex;        // index in the caller's batch
    long long bFloats = 0, betaDoubles = 0, occDoubles = 0, aentDoubles = 0;
    long long totalQ = 0, totalP = 0, tiles = 0;
@@ -84,7 +85,7 @@ struct WaveTables {
    int lab0 = 0;                     // first label of the wave in the caller's label array
    void clear()
    {
-      utt.clear(); out.clear(); posPre.clear(); tilePre.clear(); tcItems.clear(); tcItems2.clear(); uttIndex.clear();
+      utt.clear(); out.clear(); posPre.clear(); tilePre.clear(); tcItems.clear(); tcItems2.clear(); tcItems4.clear(); uttIndex.clear();
       bFloats = betaDoubles = occDoubles = aentDoubles = 0; totalQ = totalP = tiles = 0; maxQ = maxS = maxN = 0; lab0 = 0;
    }
 };
@@ -549,6 +550,7 @@ size_t add_utterance(const HostModel &h, WaveTables &w, int uidx, int T, const i
       w.tiles += (long long)((T + GT_FR - 1) / GT_FR) * ((Pp + GT_SL - 1) / GT_SL);
       for (int t0 = 0; t0 < T; t0 += TC_BM) w.tcItems.push_back(make_int2(uLocal, t0));
       for (int t0 = 0; t0 < T; t0 += 2 * TC_BM) w.tcItems2.push_back(make_int2(uLocal, t0));
+      for (int t0 = 0; t0 < T; t0 += 4 * TC_BM) w.tcItems4.push_back(make_int2(uLocal, t0));
       w.maxQ = std::max(w.maxQ, Q); w.maxS = std::max(w.maxS, S);
    }
    w.utt.push_back(u); w.out.push_back(o); w.uttIndex.push_back(uidx);
@@ -613,7 +615,7 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
    std::vector<unsigned char> &blob = S.blob;
    blob.clear();
    size_t oUtt = blob_put(blob, w.utt), oOut = blob_put(blob, w.out), oPp = blob_put(blob, w.posPre),
-          oTp = blob_put(blob, w.tilePre), oIt = blob_put(blob, w.tcItems), oIt2 = blob_put(blob, w.tcItems2);
+          oTp = blob_put(blob, w.tilePre), oIt = blob_put(blob, w.tcItems), oIt2 = blob_put(blob, w.tcItems2), oIt4 = blob_put(blob, w.tcItems4);
    const size_t nLab = (size_t)w.utt.back().labOff + (size_t)w.utt.back().Q;
    size_t oLab = blob_put(blob, labBase, nLab);
    if (blob.size() > S.hTablesCap) {
@@ -672,6 +674,7 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
       int nl = 0;
       if ((rc = gmm_tc_launch(c->tc, S.tcw, c->dm, W, waveFrames, (const int2 *)(base + oIt), (int)w.tcItems.size(),
                               (const int2 *)(base + oIt2), (int)w.tcItems2.size(),
+                              (const int2 *)(base + oIt4), (int)w.tcItems4.size(),
                               c->smCount, sg, &nl, tm ? S.evX : nullptr))) return rc;
       S.hasX = tm;
       c->stats.launches += nl; c->stats.launchesGmm += nl;
@@ -942,14 +945,15 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
    u.T = T; u.J = n; u.P = n;
    UttOut o;
    memset(&o, 0, sizeof(o));
-   std::vector<int2> items, items2;
+   std::vector<int2> items, items2, items4;
    for (int t0 = 0; t0 < T; t0 += TC_BM) items.push_back(make_int2(0, t0));
    for (int t0 = 0; t0 < T; t0 += 2 * TC_BM) items2.push_back(make_int2(0, t0));
+   for (int t0 = 0; t0 < T; t0 += 4 * TC_BM) items4.push_back(make_int2(0, t0));
    const int nTiles = ((T + GT_FR - 1) / GT_FR) * ((n + GT_SL - 1) / GT_SL);
    const int tilePre[2] = {0, nTiles};
    std::vector<unsigned char> blob;
    size_t oUtt = blob_put(blob, &u, 1), oOut = blob_put(blob, &o, 1), oSs = blob_put(blob, states, (size_t)n),
-          oTp = blob_put(blob, tilePre, 2), oIt = blob_put(blob, items), oIt2 = blob_put(blob, items2);
+          oTp = blob_put(blob, tilePre, 2), oIt = blob_put(blob, items), oIt2 = blob_put(blob, items2), oIt4 = blob_put(blob, items4);
    int rc;
    if ((rc = S0.dTables.reserve(blob.size())) || (rc = S0.dFeat.reserve((size_t)T * h.D + 4)) ||
        (rc = S0.dB.reserve((size_t)T * n + 1)))
@@ -966,7 +970,8 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
    if (gk == 2) {
       int nl = 0;
       if ((rc = gmm_tc_launch(c->tc, S0.tcw, c->dm, W, T, (const int2 *)(S0.dTables.p + oIt), (int)items.size(),
-                              (const int2 *)(S0.dTables.p + oIt2), (int)items2.size(), c->smCount, st0, &nl))) return rc;
+                              (const int2 *)(S0.dTables.p + oIt2), (int)items2.size(),
+                              (const int2 *)(S0.dTables.p + oIt4), (int)items4.size(), c->smCount, st0, &nl))) return rc;
       c->stats.launches += nl; c->stats.launchesGmm += nl;
    } else {
       size_t smem = sizeof(float) * ((size_t)c->dm.D * GT_FR + (size_t)GT_FR * (GT_SL + 1));
