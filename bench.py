@@ -62,8 +62,8 @@ def read_peaks():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE gmm_tc2_kernel launch (1024 utterances) from the
-# `ncu --set full` capture of the same command, profiles/r1h_gmm_tc2_details.csv: 1.894 GB + 1.192 GB
-GMM_TRAFFIC_BYTES = {"cfg3": 3.086e9}
+# `ncu --set full` capture of the same command, profiles/r1k_gmm_tc2_raw.txt: 1.121 GB + 1.256 GB
+GMM_TRAFFIC_BYTES = {"cfg3": 2.377e9}
 
 
 def measure_tf32(dev):
@@ -395,28 +395,42 @@ def main():
         pairs = sk.gmmPairs / K                                  # (frame, distinct tied state) pairs per step
         gmm_flop = pairs * M * ALG_FLOP_PER_GAUSS_FRAME(fm.D)
         dom = max(kms, key=kms.get)
-        if dom == "gmm" and ms_gemm > 0 and M > 1:
+        # ---- one roofline per kernel family (SURVEY.md 8d says which resource bounds which); `roofline` = the dominant one
+        rl = {}
+        if ms_gemm > 0 and M > 1:
             ach = gmm_flop / (ms_gemm * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "gmm_tc2_kernel (tcgen05 cta_group::2, 3xTF32, M=256)", "achieved": ach,
-                    "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"],
-                    "traffic": GMM_TRAFFIC_BYTES.get(args.workload) if n_utts == 1024 else None,
-                    "ms_per_launch": ms_gemm, "launches_per_step": 1,
-                    "tf32_tflops_measured": tf32,
-                    "frac_of_tf32_over_3": (ach / (tf32 / 3.0)) if tf32 else None,
-                    "note": "algorithmic FLOP = (frame, distinct state) pairs x M x 2(2D+1) (SURVEY 8d), one launch per step; "
-                            "peak = bf16 %s (%s) as the contract asks; the ceiling of a 3xTF32 kernel is the TF32 rate / 3 -- "
-                            "tf32_tflops_measured is cuBLAS TF32 8192^3 measured in this run and frac_of_tf32_over_3 uses it; "
-                            "tools/mma_rate.cu measures 1264 MAC/clk/SM for the N=128 cta_group::2 TF32 MMAs this kernel issues "
-                            "(1563 at N=256), the kernel sustains ~1430" % ("sustained", peaks["src"])}
-        else:
-            # beta/alpha: SURVEY.md 8d per-cell bytes (beta written+read 2*8*N, state log-probs 2*4*(N-2))
-            by = beta_cells * 104.0 + n_utts * T * fm.D * 4 * 2
-            ms = kms["beta"] + kms["alpha"]
+            rl["gmm"] = {"bound": "tensor", "kernel": "gmm_tc2_kernel (tcgen05 cta_group::2, 3xFP16 split, FP32 accumulate in TMEM)",
+                         "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"],
+                         "traffic": GMM_TRAFFIC_BYTES.get(args.workload) if n_utts == 1024 else None,
+                         "ms_per_launch": ms_gemm, "launches_per_step": 1,
+                         "frac_of_peak_over_3": ach / (peaks["tensor"] / 3.0),
+                         "tf32_tflops_measured": tf32,
+                         "note": "algorithmic FLOP = (frame, distinct state) pairs x M x 2(2D+1) (SURVEY 8d), one launch per step; "
+                                 "peak = bf16 %s (%s); every product costs 3 FP16 MMAs (hi*hi + hi*lo + lo*hi), so the ceiling of "
+                                 "this kernel is peak / 3 -- frac_of_peak_over_3.  ncu: 59 %% tensor-pipe active, 67 %% XU (ex2 of "
+                                 "the fused log-sum-exp), SM clock 1.62 GHz under this load" % ("sustained", peaks["src"])}
+        st_flop = alpha_cells * 3 * M * 2 * 2 * fm.D            # F_acc = sum over alpha cells (N-2) M 2 2D
+        if kms["stats"] > 0:
+            ach = st_flop / (kms["stats"] * 1e-3) / 1e12
+            rl["stats"] = {"bound": "tensor", "kernel": "stats5_kernel (state-major, mma.sync 3xTF32 sums) + statpos_* sort",
+                           "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": None,
+                           "ms_per_launch": kms["stats"], "launches_per_step": 4,
+                           "note": "SURVEY 8d classes the statistics as a tensor-pipe contraction with F_acc = alpha cells x (N-2) x M x 4D "
+                                   "algorithmic FLOP; the occupancy matrix is ~2 %% dense (alpha_cells / frames ~ 1.7 models per frame), so "
+                                   "that is %.1f GFLOP per step and the kernel is bound by recomputing the component posteriors on the FP32 "
+                                   "pipe (47 %% of its instructions) and by memory latency at 16 warps/SM, not by the tensor pipe "
+                                   "(profiles/README.md)" % (st_flop / 1e9)}
+        by = beta_cells * 104.0 + n_utts * T * fm.D * 4 * 2
+        ms = kms["beta"] + kms["alpha"]
+        if ms > 0:
             ach = by / (ms * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": "beta+alpha", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm"], "traffic": None,
-                    "note": "algorithmic bytes = 104 B per beta cell + features both passes; peak = %s copy bandwidth; "
-                            "these kernels are latency-bound by the T-step chain, see DESIGN.md" % peaks["src"]}
+            rl["recursions"] = {"bound": "hbm", "kernel": "beta_l2r_kernel + alpha_l2r_kernel", "achieved": ach, "peak": peaks["hbm"],
+                                "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None, "ms_per_launch": ms, "launches_per_step": 2,
+                                "note": "algorithmic bytes = 104 B per beta cell + features both passes (SURVEY 8d); peak = %s copy "
+                                        "bandwidth; latency-bound by the T-step chain (stall breakdown in profiles/README.md)" % peaks["src"]}
+        key = {"gmm": "gmm", "stats": "stats", "beta": "recursions", "alpha": "recursions"}[dom]
+        roof = dict(rl.get(key) or next(iter(rl.values())))
+        roof["dominant_of"] = {k: round(v, 3) for k, v in kms.items()}
         cpu = None
         if world == 1 and not args.no_cpu:
             try:
@@ -427,11 +441,11 @@ def main():
         e2e = frames_host / (ms_host * 1e-3)
         out = {"metric": "HERest E-step frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
                "warmup": max(3, args.warmup), "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": None, "dtype": "f32 GMM / f64 recursions+accumulators", "data": "synthetic",
+               "vs_baseline": None, "dtype": "f16x3 split GMM with f32 accumulate / f64 recursions+accumulators", "data": "synthetic",
                "config": config, "clocks": clocks,
                "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(n_utts * T * fm.D * 4),
                        "d2h_bytes_per_step": int(n_utts * 24), "ms_per_step": ms_host / K},
-               "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+               "gpu_launches": launches, "roofline": roof, "rooflines": rl, "cpu_baseline": cpu,
                "kernels_ms_per_step": dict(kms, gmm_expand=ms_expand),
                "work_per_step": {"frames": n_utts * T, "gmm_state_frame_pairs": pairs, "beta_cells": beta_cells,
                                  "alpha_cells": alpha_cells, "gmm_algorithmic_gflop": gmm_flop / 1e9}}
