@@ -300,8 +300,11 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
             }
             __syncwarp();
             // ---- phase 1: component posteriors on the FP32 pipe, lanes <-> (component, frame) pairs -> Lr tile.
-            //      (Tried as a second mma.sync 3xTF32 product: the tensor core's truncating FP32 accumulation
-            //      biased log N by ~5e-5 and pushed the mean sums past the 1e-4 parity bound -- reverted.)
+            //      (Tried twice as a second mma.sync 3xTF32 product about the state centre.  Accumulating in the
+            //      fragment: the tensor core's truncating FP32 accumulation biased log N by ~5e-5, past the parity
+            //      bound.  With fresh fragments and FP32-pipe running sums: parity fine (wtC 1.4e-5 vs 1.1e-5) and
+            //      3.7x fewer instructions for this phase, but the kernel got 9-14 % SLOWER on B200 -- the legacy
+            //      HMMA path cannot keep up; the tcgen05 version needs frames gathered per state, see DESIGN.md.)
             unsigned anyLr = 0;
             for (int pi = lane; pi < ((Mc * nT + 31) & ~31); pi += 32) {
                float Lr = 0.f;
