@@ -107,6 +107,42 @@ def test_outp_matches_oracle(gmm_kernel):
         fb.close()
 
 
+@pytest.mark.parametrize("variant", ["f16_pair", "tf32_pair", "tf32_single"])
+def test_outp_tensor_core_variants_on_badly_scaled_features(variant, monkeypatch):
+    """The three tcgen05 GMM kernels (CTA pair 3xFP16 = default, CTA pair 3xTF32, single CTA 3xTF32) against a
+    float64 evaluation on features whose dimensions span five decades of scale with offsets of hundreds --
+    what a real front end delivers; the FP16 split relies on its per-dimension power-of-two scaling here."""
+    from htk_b200 import synth
+    from htk_b200.flat import flatten
+    if variant == "tf32_pair":
+        monkeypatch.setenv("HFBGPU_TC_TF32", "1")
+    elif variant == "tf32_single":
+        monkeypatch.setenv("HFBGPU_NO_PAIR", "1")
+    hs = synth.make_tied_triphone_set(n_states=200, M=16, n_phys=120, n_logical=120, n_centre=10, seed=23, spread=0.2)
+    fm = flatten(hs)
+    rs = np.random.default_rng(5)
+    sc = (10.0 ** rs.uniform(-2, 3, fm.D)).astype(np.float32); of = rs.uniform(-500, 500, fm.D).astype(np.float32)
+    fm.mean[:, :fm.D] = fm.mean[:, :fm.D] * sc + of
+    fm.ivar[:, :fm.D] = fm.ivar[:, :fm.D] / (sc * sc)
+    fm.gConst[:] = (fm.D * np.log(2 * np.pi) - np.sum(np.log(fm.ivar[:, :fm.D].astype(np.float64)), axis=1)).astype(np.float32)
+    feats, _ = synth.sample_corpus(fm, n_utts=1, T=700, Q=60, seed=3)
+    x = feats[0].astype(np.float64)
+    states = np.arange(fm.J, dtype=np.int32)
+    mean = fm.mean.astype(np.float64); iv = fm.ivar.astype(np.float64); gc = fm.gConst.astype(np.float64)
+    ex = np.zeros((len(x), fm.J))
+    for s_ in range(fm.J):
+        o, e = fm.stateMixOff[s_], fm.stateMixOff[s_ + 1]
+        g = fm.mixGauss[o:e]
+        d = x[:, None, :] - mean[g][None][:, :, :fm.D]
+        lp = -0.5 * (gc[g][None] + np.sum(d * d * iv[g][None][:, :, :fm.D], axis=2)) + fm.mixLogWt[o:e].astype(np.float64)[None]
+        m = lp.max(1); ex[:, s_] = m + np.log(np.exp(lp - m[:, None]).sum(1))
+    fb = _fb(fm, gmm_kernel=2)
+    got = fb.OutP(feats[0], states).astype(np.float64)
+    fb.close()
+    err = np.abs(got - ex)
+    assert err.mean() < 1e-5 and err.max() < 1e-4, (err.mean(), err.max())
+
+
 def test_update_flags_and_zero():
     z, fm, b, kw = load_golden("synth_tied_m4")
     L = fm.layout

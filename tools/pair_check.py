@@ -10,6 +10,13 @@ M = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 600
 hs = synth.make_tied_triphone_set(n_states=600, M=M, n_phys=400, n_logical=400, n_centre=20, seed=21, spread=0.2)
 fm = flatten(hs)
+if len(sys.argv) > 3 and sys.argv[3] == "scaled":
+    # real front ends are not unit-variance: per-dimension scales over five decades and offsets of hundreds
+    rs = np.random.default_rng(5)
+    sc = (10.0 ** rs.uniform(-2, 3, fm.D)).astype(np.float32); of = rs.uniform(-500, 500, fm.D).astype(np.float32)
+    fm.mean[:, :fm.D] = fm.mean[:, :fm.D] * sc + of
+    fm.ivar[:, :fm.D] = fm.ivar[:, :fm.D] / (sc * sc)
+    fm.gConst[:] = (fm.D * np.log(2 * np.pi) - np.sum(np.log(fm.ivar[:, :fm.D].astype(np.float64)), axis=1)).astype(np.float32)
 feats, labs = synth.sample_corpus(fm, n_utts=1, T=T, Q=max(3, T // 10), seed=3)
 feat = feats[0]; states = np.arange(fm.J, dtype=np.int32)
 x = feat.astype(np.float64)
