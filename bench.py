@@ -409,6 +409,13 @@ def main():
                                  "peak = bf16 %s (%s); every product costs 3 FP16 MMAs (hi*hi + hi*lo + lo*hi), so the ceiling of "
                                  "this kernel is peak / 3 -- frac_of_peak_over_3.  ncu: 59 %% tensor-pipe active, 67 %% XU (ex2 of "
                                  "the fused log-sum-exp), SM clock 1.62 GHz under this load" % ("sustained", peaks["src"])}
+        elif kms["gmm"] > 0:
+            ach = gmm_flop / (kms["gmm"] * 1e-3) / 1e12
+            rl["gmm"] = {"bound": "tensor", "kernel": "gmm_fp32_kernel (single-Gaussian set: FP32 pipe, no tensor-core path)",
+                         "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": None,
+                         "ms_per_launch": kms["gmm"], "launches_per_step": 1,
+                         "note": "SURVEY 8d classes the output probabilities as tensor-pipe work; with one Gaussian per state there "
+                                 "is no mixture contraction worth a tcgen05 tile and the direct FP32 kernel is used"}
         st_flop = alpha_cells * 3 * M * 2 * 2 * fm.D            # F_acc = sum over alpha cells (N-2) M 2 2D
         if kms["stats"] > 0:
             ach = st_flop / (kms["stats"] * 1e-3) / 1e12
