@@ -365,6 +365,10 @@ def main():
     for _ in range(max(3, args.warmup)):          # warm-up through the same (asynchronous) path that is timed
         submit_device(); submit_host()
     fb.Wait()
+    if world > 1:                                 # ... including the collective (NCCL sets its channels up on first use)
+        for _ in range(2):
+            dist.all_reduce(acc_t)
+        torch.cuda.synchronize()
     K = max(1, args.steps)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     fb.reset_stats()
