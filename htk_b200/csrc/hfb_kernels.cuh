@@ -1,20 +1,16 @@
-// hfb_kernels.cuh -- the sm_100a kernels of the E-step (first correct path).
+// hfb_kernels.cuh -- shared device helpers (log-add, warp reductions) and the general kernels of the E-step.
 //
+//   ladd / ladd_nz    LAdd (HTKLib/HMath.c:1576-1590) with the correction term on the special-function unit
 //   gmm_fp32_kernel   log b_j(o_t) for every (frame, distinct tied state) of an utterance:
 //                     diagonal Gaussians (IDOutP, HTKLib/HModel.c:5420-5431) + log-sum-exp
-//                     over mixtures (ShStrP, HTKLib/HFB.c:898-988).  FP32 on CUDA cores; the
-//                     tcgen05 3xTF32 contraction in gmm_tc.cuh replaces it on the hot path.
-//   beta_kernel       SetBeamTaper + SetBeta + the StepBack retry loop
-//                     (HFB.c:1116-1145, :1149-1296, :1321-1366).
-//   alpha_kernel      InitAlpha / StepAlpha with the alpha beam, SetOcct, UpTranParms and the
-//                     per-state part of UpMixParms (HFB.c:616-784, :399-418, :1371-1423,
-//                     :1480-1489).
-//   stats_kernel      the per-mixture part of UpMixParms (HFB.c:1549-1736): minimum-occupancy
-//                     rule and the centred mean / variance / weight sums, FP64 accumulators.
-//
-// One CTA per utterance for the two recursions, one thread per model of the transcription:
-// the time-sliding window (two beta or alpha columns) lives in shared memory, the T-step
-// serial chain costs two block barriers per frame, and many utterances share an SM.
+//                     over mixtures (ShStrP, HTKLib/HFB.c:898-988) on the FP32 pipe: single-Gaussian
+//                     sets and D > 46; mixture sets use the tcgen05 kernels of gmm_tc.cuh.
+//   prep_kernel       CreateInsts (HFB.c:508-574): per-utterance tables, built on the device
+//   beta_kernel       SetBeamTaper + SetBeta + the StepBack retry loop (HFB.c:1116-1145, :1149-1296,
+//                     :1321-1366) for any topology (N <= 16) and any transcription length: one CTA per
+//                     utterance, one thread per model, two beta columns in shared memory, two block
+//                     barriers per frame.  The register-resident versions are in hfb_fast.cuh (N <= 8)
+//                     and hfb_l2r.cuh (HTK's standard topology).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>

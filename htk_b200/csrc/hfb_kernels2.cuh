@@ -1,13 +1,16 @@
-// hfb_kernels2.cuh -- second-generation forward pass and statistics kernels.
+// hfb_kernels2.cuh -- the general (any topology, any transcription length) forward pass and the FP32
+// statistics kernel.
 //
 //   alpha_warp_kernel  one WARP per utterance (no block barriers): the lanes cover the window of
 //                      models around the alpha beam, [sq(t-1), eq(t-1)+3], which is all StepAlpha
 //                      can reach in one frame (HFB.c:701-722: the beam is re-derived from the
-//                      previous column).  Same arithmetic as alpha_kernel.
-//   stats2_kernel      one warp per emitting state position; component log-densities are evaluated
-//                      with the reference's own operation order (IDOutP, HModel.c:5425-5430:
-//                      float, sequential, separately rounded multiply/multiply/add) so that the
-//                      mixture posteriors match the reference to FP32 rounding of initx only.
+//                      previous column); state columns in shared memory.  Redoes the utterances the
+//                      register-resident kernels (hfb_fast.cuh, hfb_l2r.cuh) gave up on.
+//   stats_tran_chunk   SetOcct + UpTranParms for one 32-frame chunk of a position (shared with stats5)
+//   stats3_kernel      one warp per emitting state position, all sums on the FP32 pipe; component
+//                      log-densities in the reference's own operation order (IDOutP,
+//                      HModel.c:5425-5430).  Used for single-Gaussian sets and D > 39; the
+//                      mixture sets go through stats5_kernel (hfb_stats_mma.cuh).
 #pragma once
 #include "hfb_kernels.cuh"
 
@@ -303,8 +306,6 @@ __device__ __forceinline__ void stats_tran_chunk(const StatPos &c, int t, bool i
          }
 }
 
-__device__ unsigned long long g_dbg[8];
-
 __global__ void __launch_bounds__(32 * ST_WARPS)
 stats3_kernel(DevModel M, Wave W)
 {
@@ -371,10 +372,6 @@ stats3_kernel(DevModel M, Wave W)
       const bool valid = inb && x0 > -1.0e29;
       const unsigned mask = __ballot_sync(0xffffffffu, valid);
       const int nT = __popc(mask);
-#ifdef HFB_DEBUG_COUNT
-      { const unsigned ib = __ballot_sync(0xffffffffu, inb);
-        if (lane == 0) { atomicAdd(&g_dbg[0], (unsigned long long)__popc(ib)); atomicAdd(&g_dbg[1], (unsigned long long)nT); atomicAdd(&g_dbg[4], 1ull); } }
-#endif
       if (nT == 0) continue;
       if (valid) { int idx = __popc(mask & ((1u << lane) - 1)); ts[idx] = t; x0s[idx] = x0; }
       __syncwarp();
@@ -422,9 +419,6 @@ stats3_kernel(DevModel M, Wave W)
             act |= __reduce_or_sync(0xffffffffu, (Lr > 0.f) ? (1u << mi) : 0u);
          }
          __syncwarp();
-#ifdef HFB_DEBUG_COUNT
-         if (lane == 0) { atomicAdd(&g_dbg[2], (unsigned long long)(Mc * nT)); atomicAdd(&g_dbg[3], (unsigned long long)__popc(act)); }
-#endif
          // ---- phase 2: lanes <-> feature dimensions, centred sums over the chunk's frames
          for (unsigned b = act; b; b &= b - 1) {
             const int mi = __ffs(b) - 1;

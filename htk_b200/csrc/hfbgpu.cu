@@ -1,10 +1,11 @@
 // hfbgpu.cu -- host side of libhfbgpu: the C ABI declared in include/hfbgpu.h.
 //
 // Replaces the reference's InitialiseForBack / FBFile seam (HTKLib/HFB.h:117-119, :143).
-// The batch is cut into waves that fit the device workspace; per wave the host builds the
-// per-utterance tables (CreateInsts, HFB.c:508-574), uploads them in one copy and launches
-//   K1 gmm  ->  K2 beta  ->  K3 alpha  ->  K4 stats
-// on the library stream.  Accumulators stay resident in HBM as one flat FP64 buffer
+// The batch is cut into waves that fit the device workspace (four wave slots, each with its own
+// stream and workspace); per wave the host only sizes things and uploads labels + descriptors in one
+// copy, then launches
+//   K0 prep (tables, CreateInsts HFB.c:508-574) -> K1 gmm -> K2 beta -> K3 alpha -> K4 stats
+// on the slot's stream.  Accumulators stay resident in HBM as one flat FP64 buffer
 // (layout: hfbgpu_acc_layout) until hfbgpu_get_accs() or the caller's all-reduce.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -984,10 +985,3 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
    return HFB_OK;
 }
 
-#ifdef HFB_DEBUG_COUNT
-extern "C" int hfbgpu_debug_counters(unsigned long long *out)
-{
-   cudaDeviceSynchronize();
-   return cudaMemcpyFromSymbol(out, g_dbg, sizeof(unsigned long long) * 8) == cudaSuccess ? 0 : -3;
-}
-#endif
