@@ -22,6 +22,7 @@
 #include "hfb_fast.cuh"
 #include "hfb_l2r.cuh"
 #include "hfb_stats_mma.cuh"
+#include "hfb_mstep.cuh"
 #include "gmm_tc.cuh"
 
 static thread_local std::string g_lastError;
@@ -65,6 +66,8 @@ struct HostModel {
    int D, G, J, P, numTrans, maxM, maxN;
    bool l2r;                         // every HMM has HTK's standard 5-state left-to-right topology (hfb_l2r.cuh)
    std::vector<int> stateMixOff, hmmN, hmmStateOff, hmmState, hmmTrans, transN, transOff, minDur;
+   std::vector<int> meanId, varId;   // per Gaussian (M-step)
+   int numMeanAcc = 0, numVarAcc = 0;
    std::vector<long long> tranAccOff, tranOccOff;
    std::vector<float> transLogA;
 };
@@ -320,6 +323,8 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
    h.transN.assign(m->transN, m->transN + h.numTrans);
    h.transOff.assign(m->transOff, m->transOff + h.numTrans + 1);
    h.transLogA.assign(m->transLogA, m->transLogA + m->transOff[h.numTrans]);
+   h.meanId.assign(m->meanId, m->meanId + h.G); h.varId.assign(m->varId, m->varId + h.G);
+   h.numMeanAcc = m->numMeanAcc; h.numVarAcc = m->numVarAcc;
    h.maxM = 0; h.maxN = 0; h.l2r = true;
    for (int j = 0; j < h.J; j++) h.maxM = std::max(h.maxM, h.stateMixOff[j + 1] - h.stateMixOff[j]);
    h.minDur.resize(h.numTrans);
@@ -919,6 +924,68 @@ extern "C" int hfbgpu_submit(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *
 }
 
 extern "C" int hfbgpu_wait(hfbgpu_ctx *c) { return wait_impl(c); }
+
+// ------------------------------------------------------------------------------------------
+// M-step on the device
+// ------------------------------------------------------------------------------------------
+extern "C" int hfbgpu_mstep(hfbgpu_ctx *c, const hfb_mstep_options *opt, hfb_mstep_result *out)
+{
+   if (!c || !opt || !out || !out->mean || !out->var || !out->gConst || !out->mixWeight || !out->transP || !opt->varFloor)
+      return HFB_EINVAL;
+   CK(cudaSetDevice(c->device));
+   { int rc = wait_impl(c); if (rc) return rc; }
+   const HostModel &h = c->hm;
+   const int D = h.D, G = h.G, J = h.J, nT = h.numTrans, nM = h.numMeanAcc, nV = h.numVarAcc;
+   const int sumM = h.stateMixOff[J];
+   const size_t sumNN = h.transLogA.size();
+   cudaStream_t st = c->stream;
+   CK(cudaStreamSynchronize(st));
+   // host-side index tables: use count of every variance vector, first Gaussian that uses it
+   std::vector<int> varUse(nV, 0), first(G, 0), seen(nV, 0);
+   for (int g = 0; g < G; g++) { varUse[h.varId[g]]++; if (!seen[h.varId[g]]) { seen[h.varId[g]] = 1; first[g] = 1; } }
+   int maxN = 1;
+   for (int n : h.transN) maxN = std::max(maxN, n);
+   DevBuf<int> dInts;        // transOn | stateOn | meanOn | varOn | counters | varUse | first | transN
+   DevBuf<float> dFl;        // vFloor | mean | var | gConst | mixWeight | transP
+   const size_t nFlags = (size_t)nT + J + nM + nV + 4;
+   int rc;
+   if ((rc = dInts.reserve(nFlags + nV + G + nT)) ||
+       (rc = dFl.reserve((size_t)D + 2 * (size_t)G * D + G + sumM + sumNN))) { dInts.release(); dFl.release(); return rc; }
+   int *transOn = dInts.p, *stateOn = transOn + nT, *meanOn = stateOn + J, *varOn = meanOn + nM, *counters = varOn + nV;
+   int *dVarUse = counters + 4, *dFirst = dVarUse + nV, *dTransN = dFirst + G;
+   float *vFloor = dFl.p, *oMean = vFloor + D, *oVar = oMean + (size_t)G * D, *oGc = oVar + (size_t)G * D,
+         *oW = oGc + G, *oT = oW + sumM;
+   cudaError_t e = cudaSuccess;
+   auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+   chk(cudaMemsetAsync(dInts.p, 0, nFlags * sizeof(int), st));
+   chk(cudaMemcpyAsync(dVarUse, varUse.data(), (size_t)nV * sizeof(int), cudaMemcpyHostToDevice, st));
+   chk(cudaMemcpyAsync(dFirst, first.data(), (size_t)G * sizeof(int), cudaMemcpyHostToDevice, st));
+   chk(cudaMemcpyAsync(dTransN, h.transN.data(), (size_t)nT * sizeof(int), cudaMemcpyHostToDevice, st));
+   chk(cudaMemcpyAsync(vFloor, opt->varFloor, (size_t)D * sizeof(float), cudaMemcpyHostToDevice, st));
+   MStepDev S;
+   S.acc = c->dAcc.p; S.minEgs = opt->minEgs; S.uFlags = c->opt.uFlags; S.maxM = h.maxM; S.mixWeightFloor = opt->mixWeightFloor;
+   S.vFloor = vFloor; S.transOn = transOn; S.stateOn = stateOn; S.meanOn = meanOn; S.varOn = varOn;
+   S.varUse = dVarUse; S.gaussFirstOfVar = dFirst; S.counters = counters;
+   S.mean = oMean; S.var = oVar; S.gConst = oGc; S.mixWeight = oW; S.transP = oT;
+   mstep_enable_kernel<<<(h.P + 127) / 128, 128, 0, st>>>(c->dm, S);
+   mstep_trans_kernel<<<nT, ((maxN + 31) / 32) * 32, 0, st>>>(c->dm, S, dTransN);
+   mstep_state_kernel<<<(J + 127) / 128, 128, 0, st>>>(c->dm, S);
+   mstep_gauss_kernel<<<(G + 127) / 128, 128, 0, st>>>(c->dm, S);
+   c->stats.launches += 4; c->stats.launchesMisc += 4;
+   chk(cudaGetLastError());
+   int hc[4] = {0, 0, 0, 0};
+   chk(cudaMemcpyAsync(out->mean, oMean, (size_t)G * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+   chk(cudaMemcpyAsync(out->var, oVar, (size_t)G * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+   chk(cudaMemcpyAsync(out->gConst, oGc, (size_t)G * sizeof(float), cudaMemcpyDeviceToHost, st));
+   chk(cudaMemcpyAsync(out->mixWeight, oW, (size_t)sumM * sizeof(float), cudaMemcpyDeviceToHost, st));
+   chk(cudaMemcpyAsync(out->transP, oT, sumNN * sizeof(float), cudaMemcpyDeviceToHost, st));
+   chk(cudaMemcpyAsync(hc, counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+   chk(cudaStreamSynchronize(st));
+   dInts.release(); dFl.release();
+   if (e != cudaSuccess) { g_lastError = std::string("hfbgpu_mstep: ") + cudaGetErrorString(e); return HFB_ECUDA; }
+   out->nFloorVar = hc[0]; out->nFloorVarMix = hc[1]; out->nCopied = hc[2]; out->nNoOcc = hc[3];
+   return HFB_OK;
+}
 
 extern "C" void *hfbgpu_host_alloc(size_t bytes)
 {

@@ -16,7 +16,8 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 from . import capi
-from .flat import Batch, Beams, FlatModel, hfb_stats, hfb_utt_result, make_options
+from .flat import (Batch, Beams, FlatModel, hfb_mstep_options, hfb_mstep_result, hfb_stats, hfb_utt_result,
+                   make_options)
 
 
 class UttResult(tuple):
@@ -117,6 +118,42 @@ class ForwardBackward:
         rc = self.lib.hfbgpu_set_accs(self.h, acc.ctypes.data)
         if rc != 0:
             raise capi.HfbError(rc, "hfbgpu_set_accs")
+
+    def MStep(self, min_egs: int = 3, min_var: float = 0.0, mix_weight_floor: float = 0.0,
+              var_floor: Optional[np.ndarray] = None) -> Tuple[FlatModel, dict]:
+        """MLUpdateModels (HTKTools/HERest.c:1262-1321) on the device, from the resident accumulators.
+
+        ``min_egs`` / ``min_var`` / ``mix_weight_floor`` are HERest's -m / -v / -w; ``var_floor`` is the
+        per-dimension floor of a ``~v varFloor1`` macro (overrides ``min_var``, HERest.c:623 SetVFloor).
+        Returns the re-estimated model in the flat layout (ready for a new ForwardBackward) and the
+        counters HERest reports."""
+        import copy
+        from .htkio import LZERO, MINLARG, MINMIX
+        fm = self.fm
+        vf = np.full(fm.D, min_var, np.float32) if var_floor is None else np.ascontiguousarray(var_floor, np.float32)
+        o = hfb_mstep_options(int(min_egs), float(mix_weight_floor) * MINMIX, vf.ctypes.data)
+        mean = np.zeros((fm.G, fm.D), np.float32); var = np.zeros((fm.G, fm.D), np.float32)
+        gc = np.zeros(fm.G, np.float32); w = np.zeros(int(fm.stateMixOff[-1]), np.float32)
+        tp = np.zeros(len(fm.transLogA), np.float32)
+        r = hfb_mstep_result(mean.ctypes.data, var.ctypes.data, gc.ctypes.data, w.ctypes.data, tp.ctypes.data, 0, 0, 0, 0)
+        rc = self.lib.hfbgpu_mstep(self.h, C.byref(o), C.byref(r))
+        if rc != 0:
+            raise capi.HfbError(rc, "hfbgpu_mstep")
+        new = copy.copy(fm)
+        new.mean = mean
+        new.ivar = (np.float32(1.0) / var).astype(np.float32)
+        new.gConst = gc
+        lw = np.full(w.shape, LZERO, np.float32)
+        nz = w >= MINMIX
+        lw[nz] = np.log(w[nz].astype(np.float64)).astype(np.float32)
+        new.mixLogWt = lw
+        lt = np.full(tp.shape, LZERO, np.float32)
+        nz = tp > MINLARG
+        lt[nz] = np.log(tp[nz].astype(np.float64)).astype(np.float32)
+        new.transLogA = lt
+        info = dict(nFloorVar=r.nFloorVar, nFloorVarMix=r.nFloorVarMix, nCopied=r.nCopied, nNoOcc=r.nNoOcc,
+                    var=var, mixWeight=w, transP=tp)
+        return new, info
 
     def acc_device_ptr(self) -> int:
         return int(self.lib.hfbgpu_acc_device_ptr(self.h))

@@ -53,6 +53,16 @@ class hfb_options(C.Structure):
     ]
 
 
+class hfb_mstep_options(C.Structure):
+    _fields_ = [("minEgs", C.c_int32), ("mixWeightFloor", C.c_float), ("varFloor", C.c_void_p)]
+
+
+class hfb_mstep_result(C.Structure):
+    _fields_ = [("mean", C.c_void_p), ("var", C.c_void_p), ("gConst", C.c_void_p), ("mixWeight", C.c_void_p),
+                ("transP", C.c_void_p), ("nFloorVar", C.c_int32), ("nFloorVarMix", C.c_int32),
+                ("nCopied", C.c_int32), ("nNoOcc", C.c_int32)]
+
+
 class hfb_batch(C.Structure):
     _fields_ = [
         ("numUtt", C.c_int32),

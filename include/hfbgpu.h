@@ -218,6 +218,31 @@ int hfbgpu_state_loglik(hfbgpu_ctx *ctx, const float *feat, int32_t T,
 /* Minimum durations per transition matrix as computed at create (TrAcc.minDur). */
 int hfbgpu_get_min_durs(hfbgpu_ctx *ctx, int32_t *out);
 
+/* ---- M-step on the device ----------------------------------------------------
+ * Replaces MLUpdateModels (HTKTools/HERest.c:1262-1321: UpdateTrans :795, UpdateWeights :897 with
+ * FloorMixes :819, UpdateVars :1045, UpdateMeans :974, FixGConsts HModel.c:5688) for the sets the
+ * library accelerates.  Reads the resident accumulators (after the caller's all-reduce) and writes the
+ * re-estimated parameters in the flat model's own order; parameters of structures that are not updated
+ * (too few examples, zero occupancy, update flag off) are returned unchanged.                       */
+typedef struct hfb_mstep_options {
+   int32_t minEgs;             /* HERest -m (default 3): models with fewer examples are copied       */
+   float   mixWeightFloor;     /* HERest -w f, already multiplied by MINMIX (default 0 = off)          */
+   const float *varFloor;      /* [vecSize] variance floor per dimension (HERest -v / ~v varFloor1)    */
+} hfb_mstep_options;
+
+typedef struct hfb_mstep_result {
+   float *mean;                /* [numGauss][vecSize]                                                  */
+   float *var;                 /* [numGauss][vecSize] variances (not inverse)                          */
+   float *gConst;              /* [numGauss]  D log 2 pi + sum log var                                 */
+   float *mixWeight;           /* [stateMixOff[numStates]] linear weights                              */
+   float *transP;              /* all matrices, row-major N*N each, linear probabilities               */
+   int32_t nFloorVar, nFloorVarMix;   /* floored variance elements / components (HERest.c:789-790)    */
+   int32_t nCopied;            /* physical HMMs with fewer than minEgs examples (warning -2331)        */
+   int32_t nNoOcc;             /* structures of updated models without occupancy (warnings -2326/-2330) */
+} hfb_mstep_result;
+
+int hfbgpu_mstep(hfbgpu_ctx *ctx, const hfb_mstep_options *opt, hfb_mstep_result *out);
+
 /* Counters for bench.py: kernels launched / device time since the last reset. */
 typedef struct hfb_stats {
    int64_t launches;

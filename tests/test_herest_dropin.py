@@ -144,3 +144,63 @@ def test_python_dump_feeds_stock_mstep(tmp_path):
     assert np.max(np.abs(mA - mB) / np.sqrt(vA)) < 1e-4 + 2e-6
     assert np.max(np.abs(vA - vB) / vA) < 1e-4 + 2e-6
     assert np.max(np.abs(np.exp(wA) - np.exp(wB))) < 1e-4
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(v=0.9, w=2.0, m=10)])
+def test_device_mstep_matches_stock_herest(tmp_path, opts):
+    """hfbgpu_mstep (MLUpdateModels on the device) from the accumulators of a stock `HERest -p 1`
+    dump against the MMF the stock `HERest -p 0` writes from the same dump -- defaults, and with variance floor,
+    mixture-weight floor and a minimum-example count that leaves part of the models un-updated."""
+    if not os.path.exists(HEREST):
+        pytest.skip("reference binaries not built")
+    from htk_b200.estep import ForwardBackward
+    tmp = str(tmp_path)
+    hs = synth.make_tied_triphone_set(n_states=50, M=4, n_phys=30, n_logical=45, n_centre=6, seed=31, spread=0.2)
+    hs2, fm = _setup(tmp, hs, n_utts=10, T=300, Q=30, seed=4)
+    names = open(os.path.join(tmp, "list")).read().splitlines()
+    order = htkio.scan_order(hs2.physical_names())
+    fmS = flatten(hs2, order=order)
+    os.makedirs(os.path.join(tmp, "acc")); os.makedirs(os.path.join(tmp, "out"))
+    _run([HEREST, "-u", "tmvw", "-p", "1", "-H", "mmf", "-I", "labs.mlf", "-S", "scp", "-M", "acc", "list"], tmp)
+    extra = []
+    if "v" in opts: extra += ["-v", str(opts["v"])]
+    if "w" in opts: extra += ["-w", str(opts["w"])]
+    if "m" in opts: extra += ["-m", str(opts["m"])]
+    log = _run([HEREST, "-T", "1", "-u", "tmvw"] + extra + ["-p", "0", "-H", "mmf", "-M", "out", "list",
+                os.path.join("acc", "HER1.acc")], tmp)
+    acc, pr, T = htkio.read_acc_dump(os.path.join(tmp, "acc", "HER1.acc"), hs2, fmS)
+    fb = ForwardBackward(fmS)
+    fb.SetAccs(acc)
+    new, info = fb.MStep(min_egs=opts.get("m", 3), min_var=opts.get("v", 0.0), mix_weight_floor=opts.get("w", 0.0))
+    fb.close()
+    # the stock result, flattened in the same order
+    hsO = htkio.read_mmf([os.path.join(tmp, "out", "mmf")], hmm_list=names)
+    fmO = flatten(hsO, order=order)
+    sd = np.sqrt(1.0 / fmO.ivar.astype(np.float64))
+    assert np.max(np.abs(new.mean.astype(np.float64) - fmO.mean) / sd) < 1e-4 + 2e-6       # MMF text: 7 digits
+    assert np.max(np.abs(1.0 / new.ivar.astype(np.float64) - 1.0 / fmO.ivar) * fmO.ivar) < 1e-4 + 2e-6
+    assert np.max(np.abs(np.exp(new.mixLogWt.astype(np.float64)) - np.exp(fmO.mixLogWt.astype(np.float64)))) < 1e-4
+    ok = fmO.transLogA > -1e9
+    assert np.array_equal(ok, new.transLogA > -1e9)
+    assert np.max(np.abs(np.exp(new.transLogA[ok].astype(np.float64)) - np.exp(fmO.transLogA[ok].astype(np.float64)))) < 1e-4
+    assert np.max(np.abs(new.gConst - fmO.gConst)) < 1e-3
+    if opts:
+        import re
+        mt = re.search(r"Total (\d+) floored variance elements in (\d+) different mixes", log)
+        assert mt and (int(mt.group(1)), int(mt.group(2))) == (info["nFloorVar"], info["nFloorVarMix"]), (log[-400:], info)
+        assert info["nCopied"] > 0 and log.count("copied: only") == info["nCopied"]
+    # a second EM pass with the re-estimated model runs and does not lower the likelihood
+    from htk_b200.flat import Batch
+    import re
+    scp = open(os.path.join(tmp, "scp")).read().split()
+    feats = [htkio.read_htk_features(f)[0] for f in scp]
+    mlf = open(os.path.join(tmp, "labs.mlf")).read()
+    labs = []
+    for f in scp:
+        u = os.path.basename(f)[:-4]
+        block = re.search(r'"\*/%s\.lab"\n(.*?)\n\.\n' % u, mlf, re.S).group(1).split("\n")
+        labs.append(np.array([fmS.hmm_index[l] for l in block], dtype=np.int32))
+    b = Batch(feats, labs, fmS.D)
+    fb = ForwardBackward(fmS); r0, _ = fb.FBFile(b); fb.close()
+    fb = ForwardBackward(new); r1, _ = fb.FBFile(b); fb.close()
+    assert sum(r.pr for r in r1) >= sum(r.pr for r in r0) - 1e-6 * abs(sum(r.pr for r in r0))
