@@ -362,8 +362,14 @@ def main():
             return float(tm[0]), float(ts[1])
         return float(t[0]), float(t[1])
 
-    for _ in range(max(3, args.warmup)):          # warm-up through the same (asynchronous) path that is timed
-        submit_device(); submit_host()
+    # warm-up through the same (asynchronous) paths that are timed; at least four submits of each kind so that every
+    # one of the library's four wave slots has grown its workspace AND its host-feature staging buffer (a first-use
+    # cudaMalloc inside the timed region serialises the whole device)
+    for _ in range(max(4, args.warmup)):
+        submit_device()
+    fb.Wait()
+    for _ in range(max(4, args.warmup)):
+        submit_host()
     fb.Wait()
     if world > 1:                                 # ... including the collective (NCCL sets its channels up on first use)
         for _ in range(2):
