@@ -230,7 +230,7 @@ def cpu_reference(fm, cfg, prune, cores, budget_s=25.0, want_merge=True):
                            "utterances per process (%.1f s vs %.1f s wall, MMF load excluded); `-p 0` merge+update of the "
                            "%d dumps took %s s and is a per-pass constant not amortised here"
                            % (cores, 1, n2, T, ta, tb, cores, ("%.1f" % merge_s) if merge_s is not None else "n/a"),
-                    merge_s=merge_s, mmf_write_s=t_mmf)
+                    merge_s=merge_s, mmf_write_s=t_mmf, sample_s=tb, sample_frames=cores * n2 * T)
     finally:
         shutil.rmtree(w, ignore_errors=True)
 
@@ -253,7 +253,8 @@ def cpu_port(fm, cfg, prune, cores, budget_s=20.0):
             break
         n = int(min(cores * 64, max(n * 2, n * budget_s / max(dt, 1e-3) / 2)))
     return dict(value=n * T / dt, unit="frames/s", cores=cores, kind="port",
-                sample="C oracle (oracle/hfb_oracle.c), %d pthreads, %d x %d-frame utterances in %.1f s" % (cores, n, T, dt))
+                sample="C oracle (oracle/hfb_oracle.c), %d pthreads, %d x %d-frame utterances in %.1f s" % (cores, n, T, dt),
+                sample_s=dt, sample_frames=n * T)
 
 
 # ------------------------------------------------------------------------------------ main
@@ -294,7 +295,7 @@ def main():
             return
         fm = make_model(cfg)
         K = max(1, args.steps)
-        vals = []
+        vals, secs = [], []
         base = None
         for i in range(args.warmup + K):
             if i < args.warmup and i > 0:
@@ -302,10 +303,12 @@ def main():
             r = cpu_reference(fm, cfg, prune, cores, budget_s=max(6.0, 90.0 / (K + 1)), want_merge=(i == args.warmup + K - 1))
             base = r
             if i >= args.warmup:
-                vals.append(r["value"])
+                vals.append(r["value"]); secs.append(r.get("sample_s") or 0.0)
         v = float(np.mean(vals))
         out = {"impl": "reference", "metric": "HERest E-step frames/sec", "value": v, "unit": "frames/s",
-               "n_gpus": args.gpus, "steps": K, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+               "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
+               "ms_per_step": (1e3 * float(np.mean(secs))) if secs and all(secs) else None,   # wall time of one bounded sample
+               "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic", "config": config,
                "cpu_baseline": {"value": v, "unit": "frames/s", "cores": base["cores"], "kind": base["kind"],
                                 "sample": base["sample"]},
