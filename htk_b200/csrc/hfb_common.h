@@ -9,6 +9,7 @@
 #include "../../include/hfbgpu.h"
 
 #define HFB_MAXN 16                 // max states per HMM handled by the recursion kernels
+#define HFB_UTT_BETAWIDE 30000       // internal: beam outgrew the sliding beta window, the wide kernel redoes the utterance
 
 struct DevModel {
    int D, Dp;                       // vector size, padded to a multiple of 4

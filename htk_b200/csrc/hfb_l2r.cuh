@@ -42,15 +42,17 @@ __device__ __forceinline__ double dmax(double a, double b) { return (a > b) ? a 
 // K2 (standard topology): one CTA per utterance, one thread per model
 // ------------------------------------------------------------------------------------------
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT, 1024 / MAXT) beta_l2r_kernel(DevModel M, Wave W)
+__global__ void __launch_bounds__(MAXT, 1024 / MAXT) beta_l2r_kernel(DevModel M, Wave W, int onlyRedo)
 {
    extern __shared__ __align__(16) unsigned char smraw[];
    const UttDesc &u = W.utt[blockIdx.x];
    UttOut *out = &W.out[blockIdx.x];
-   if (out->status != 0) {
-      if (threadIdx.x == 0 && out->status == HFB_UTT_SKIPPED) atomicAdd(&W.acc[M.L.numSkipped], 1.0);
+   // onlyRedo: second launch after beta_l2r_slide_kernel, for the utterances whose beam outgrew its window
+   if (onlyRedo ? (out->status != HFB_UTT_BETAWIDE) : (out->status != 0)) {
+      if (!onlyRedo && threadIdx.x == 0 && out->status == HFB_UTT_SKIPPED) atomicAdd(&W.acc[M.L.numSkipped], 1.0);
       return;
    }
+   __syncthreads();                                     // everybody has read the status before thread 0 rewrites it
    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
    const int T = u.T, Q = u.Q, J = u.J;
    const size_t S = (size_t)5 * Q;
@@ -157,6 +159,161 @@ __global__ void __launch_bounds__(MAXT, 1024 / MAXT) beta_l2r_kernel(DevModel M,
          const bool inNew = active && q >= nlo && q <= nhi;
          u0 = inNew ? un0 : LZERO_D; u1 = inNew ? un1 : LZERO_D; u2 = inNew ? un2 : LZERO_D;
          { double *tmp = cur; cur = prev; prev = tmp; }
+      }
+      if (status != 0) break;
+      if (!fail) {
+         pr = prev[lastq];                             // utt->pr = bqt[1] (:1280)
+         if (pr > LSMALL_D) break;
+      }
+      thresh += W.pruneInc;                            // StepBack retry (:1349-1361)
+      if (thresh > W.pruneLim || W.pruneInc == 0.0) { status = HFB_UTT_SKIPPED; break; }
+      retries++;
+      __syncthreads();
+   }
+   if (tid == 0) {
+      out->status = status; out->retries = retries; out->pr = (status == 0) ? pr : LZERO_D;
+      out->thresh = thresh;
+      if (status == HFB_UTT_SKIPPED) atomicAdd(&W.acc[M.L.numSkipped], 1.0);
+   }
+}
+
+// Long transcriptions with beam pruning (config #5: 667 labels, beam ~40 models): the same recursion with a SLIDING
+// window of blockDim models instead of one thread per label -- thread i owns the model q = i (mod blockDim) nearest
+// below the beam's upper end and moves blockDim models down when its model leaves the beam for good (the beta beam
+// only ever moves towards the start of the transcription).  Eight warps per barrier instead of 32.  If a beam ever
+// needs more than blockDim - 3 models the utterance is flagged HFB_UTT_BETAWIDE and beta_l2r_kernel<1024> redoes it.
+__global__ void __launch_bounds__(256, 4) beta_l2r_slide_kernel(DevModel M, Wave W)
+{
+   extern __shared__ __align__(16) unsigned char smraw[];
+   const UttDesc &u = W.utt[blockIdx.x];
+   UttOut *out = &W.out[blockIdx.x];
+   if (out->status != 0) {
+      if (threadIdx.x == 0 && out->status == HFB_UTT_SKIPPED) atomicAdd(&W.acc[M.L.numSkipped], 1.0);
+      return;
+   }
+   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+   const int T = u.T, Q = u.Q, J = u.J;
+   const size_t S = (size_t)5 * Q;
+   double *entA = (double *)smraw, *entB = entA + (Q + 2), *wred = entB + (Q + 2);
+   int *wlo = (int *)(wred + 32), *whi = wlo + 32;
+   int q = -1;
+   bool mine = false;
+   L2RRegs r;
+   const float *bU = W.b + u.bOff;
+   double *betaU = W.beta + u.betaOff;
+   short *qLo = W.qLo + u.frameBase, *qHi = W.qHi + u.frameBase;
+
+   double thresh = W.pruneInit, pr = LZERO_D;
+   int retries = 0, status = 0;
+
+   for (;;) {
+      // ---- SetBeamTaper (HFB.c:1116-1145): every model has minimum duration 3 here, so the taper is
+      //      qHi(t) = min(Q-1, t / 3), qLo(t) = max(0, Q-1 - (T-1-t) / 3) -- evaluated in the frame loop
+      //      with running quotients, no table and no loads
+      const bool noPrune = thresh >= 0.5 * HFB_NOPRUNE;
+      // window at the top of the transcription: the largest q <= Q-1 with q = tid (mod nt)
+      q = (tid <= Q - 1) ? tid + nt * ((Q - 1 - tid) / nt) : -1;
+      mine = q >= 0;
+      if (mine) load_l2r(r, M, W, u, q);
+      else { r.aE = r.a00 = r.a01 = r.a11 = r.a12 = r.a22 = r.a2x = LZERO_D; r.s0 = r.s1 = r.s2 = 0; }
+
+      double *cur = entA, *prev = entB;                // entry-state beta of every model, frames t / t+1
+      double u0 = LZERO_D, u1 = LZERO_D, u2 = LZERO_D; // b_j(o_{t+1}) + beta_j(t+1), log zero outside the beam
+
+      // ---- t = T-1, HFB.c:1176-1198
+      int lo1 = Q - 1, hi1 = Q - 1, lastq = lo1;
+      if (tid == 0) { qHi[T - 1] = (short)(Q - 1); qLo[T - 1] = (short)(Q - 1); }
+      if (mine && q >= lo1) {
+         const float *bt = bU + (size_t)(T - 1) * J;
+         const double bExit = (q == Q - 1) ? 0.0 : LZERO_D;
+         const double n0 = LZERO_D + bExit, n1 = LZERO_D + bExit, n2 = r.a2x + bExit;
+         u0 = (double)bt[r.s0] + n0; u1 = (double)bt[r.s1] + n1; u2 = (double)bt[r.s2] + n2;
+         const double x = (n0 > LSMALL_D) ? r.aE + u0 : LZERO_D;
+         double *bg = betaU + (size_t)(T - 1) * S + 5 * q;
+         bg[0] = x; bg[1] = n0; bg[2] = n1; bg[3] = n2; bg[4] = bExit;
+         cur[q] = x;
+      }
+      // output probabilities travel two frames ahead of their use, in registers
+      float bA0 = 0.f, bA1 = 0.f, bA2 = 0.f, bB0 = 0.f, bB1 = 0.f, bB2 = 0.f;
+      if (mine) {
+         if (T >= 2) { const float *b2 = bU + (size_t)(T - 2) * J; bA0 = b2[r.s0]; bA1 = b2[r.s1]; bA2 = b2[r.s2]; }
+         if (T >= 3) { const float *b2 = bU + (size_t)(T - 3) * J; bB0 = b2[r.s0]; bB1 = b2[r.s1]; bB2 = b2[r.s2]; }
+      }
+      __syncthreads();
+      { double *tmp = cur; cur = prev; prev = tmp; }
+
+      // ---- t = T-2 .. 0, HFB.c:1205-1277
+      bool fail = false;
+      double *bgRow = betaU + (size_t)(T - 1) * S;     // running pointers: the beta column block of frame t,
+      const float *bp = bU + (size_t)(T - 3) * J;      // the output-probability row of frame t-2
+      int hiC = (T - 1) / 3, hiR = (T - 1) % 3, loC = 0, loR = 0;      // t / 3 and (T-1-t) / 3 with remainders, at t = T-1
+      for (int t = T - 2; t >= 0; t--) {
+         bgRow -= S; bp -= J;
+         if (hiR == 0) { hiR = 2; hiC--; } else hiR--;
+         if (loR == 2) { loR = 0; loC++; } else loR++;
+         const int tapLo = max(0, Q - 1 - loC), tapHi = min(Q - 1, hiC);
+         const int startq = hi1;
+         const int endq = (lo1 == 0) ? 0 : ((tapLo >= lo1) ? tapLo : lo1 - 1);
+         lastq = endq;
+         const bool active = mine && q >= endq && q <= startq;
+         const float c0 = bA0, c1 = bA1, c2 = bA2;
+         bA0 = bB0; bA1 = bB1; bA2 = bB2;
+         if (t >= 2 && mine && q >= endq - 2 && q <= startq) { bB0 = bp[r.s0]; bB1 = bp[r.s1]; bB2 = bp[r.s2]; }
+         double lMax = LZERO_D, un0 = LZERO_D, un1 = LZERO_D, un2 = LZERO_D;
+         if (active) {
+            const double ex = (q + 1 >= lo1 && q + 1 <= hi1) ? prev[q + 1] : LZERO_D;      // :1225
+            const double n2 = ladd_nz(r.a2x + ex, r.a22 + u2);                             // :1228-1236
+            const double n1 = ladd_nz(r.a11 + u1, r.a12 + u2);
+            const double n0 = ladd_nz(r.a00 + u0, r.a01 + u1);
+            un0 = (double)c0 + n0; un1 = (double)c1 + n1; un2 = (double)c2 + n2;
+            const double x = r.aE + un0;                                                   // :1242-1250
+            double *bg = bgRow + 5 * q;
+            bg[0] = x; bg[1] = n0; bg[2] = n1; bg[3] = n2; bg[4] = ex;
+            cur[q] = x;
+            lMax = dmax(dmax(n0, n1), n2);
+         }
+         int nhi, nlo;
+         if (noPrune) {
+            // gMax - maxP[q] > thresh is never true for finite log values: the beam is the candidate
+            // range and only the entry values have to become visible to the neighbours
+            nhi = startq; nlo = endq;
+            __syncthreads();
+         } else {
+            double gMax = warp_max(lMax);
+            if (lane == 0) wred[wid] = gMax;
+            __syncthreads();
+            gMax = LZERO_D;
+            for (int w = 0; w < nw; w++) gMax = dmax(gMax, wred[w]);
+            // ---- pruning (:1254-1272)
+            const bool keep = active && !(gMax - lMax > thresh);
+            const int myHi = __reduce_max_sync(0xffffffffu, keep ? q : -1);
+            const int myLo = __reduce_min_sync(0xffffffffu, keep ? q : 0x7fffffff);
+            if (lane == 0) { whi[wid] = myHi; wlo[wid] = myLo; }
+            __syncthreads();
+            nhi = -1; nlo = 0x7fffffff;
+            for (int w = 0; w < nw; w++) { nhi = max(nhi, whi[w]); nlo = min(nlo, wlo[w]); }
+         }
+         if (nhi < 0) { fail = true; status = HFB_UTT_EBETA; break; }
+         if (nhi > tapHi) nhi = tapHi;
+         if (nlo > nhi) { fail = true; break; }
+         if (tid == 0) { qHi[t] = (short)nhi; qLo[t] = (short)nlo; }
+         hi1 = nhi; lo1 = nlo;
+         const bool inNew = active && q >= nlo && q <= nhi;
+         u0 = inNew ? un0 : LZERO_D; u1 = inNew ? un1 : LZERO_D; u2 = inNew ? un2 : LZERO_D;
+         { double *tmp = cur; cur = prev; prev = tmp; }
+         // ---- the window: everything the next frame can touch is [lo1 - 3, hi1] (beam, one model of growth, two of
+         //      output-probability look-ahead)
+         if (hi1 - lo1 + 4 > nt) { fail = true; status = HFB_UTT_BETAWIDE; break; }
+         if (mine && q > hi1) {                            // my model has left the beam for good: take the one nt below
+            do q -= nt; while (q > hi1);
+            mine = q >= 0;
+            u0 = u1 = u2 = LZERO_D;
+            if (mine) {
+               load_l2r(r, M, W, u, q);
+               if (t >= 1) { const float *b1 = bp + J; bA0 = b1[r.s0]; bA1 = b1[r.s1]; bA2 = b1[r.s2]; }
+               if (t >= 2) { bB0 = bp[r.s0]; bB1 = bp[r.s1]; bB2 = bp[r.s2]; }
+            }
+         }
       }
       if (status != 0) break;
       if (!fail) {

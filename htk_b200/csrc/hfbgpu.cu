@@ -707,8 +707,14 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
       const bool l2r = fastOk && !exact && c->hm.l2r && !getenv("HFBGPU_NO_L2R");   // standard topology
       if (l2r && w.maxQ <= 1024) {
          const size_t fsm = beta_fast_smem_bytes(w.maxQ);
-         if (w.maxQ <= 256) beta_l2r_kernel<256><<<nU, nt, fsm, st>>>(c->dm, W);
-         else beta_l2r_kernel<1024><<<nU, ntGeneric, fsm, st>>>(c->dm, W);
+         const bool pruning = c->opt.pruneInit < 0.5 * HFB_NOPRUNE;
+         if (w.maxQ <= 256) beta_l2r_kernel<256><<<nU, nt, fsm, st>>>(c->dm, W, 0);
+         else if (pruning && !getenv("HFBGPU_NO_SLIDE")) {
+            // long transcriptions under a beam: 256-model sliding window, the one-thread-per-label kernel redoes overflows
+            beta_l2r_slide_kernel<<<nU, 256, fsm, st>>>(c->dm, W);
+            beta_l2r_kernel<1024><<<nU, ntGeneric, fsm, st>>>(c->dm, W, 1);
+            c->stats.launches++; c->stats.launchesBeta++;
+         } else beta_l2r_kernel<1024><<<nU, ntGeneric, fsm, st>>>(c->dm, W, 0);
          c->stats.launchesL2R++;
       } else if (betaFastOk) {
          const size_t fsm = beta_fast_smem_bytes(w.maxQ);

@@ -316,6 +316,37 @@ def test_model_shapes_against_oracle(shape):
     assert max(e.values()) < RTOL, e
 
 
+@pytest.mark.parametrize("prune", [(120.0, 60.0, 600.0), (5000.0, 0.0, 5000.0)])
+def test_long_transcription_sliding_beta_window(prune, monkeypatch):
+    """Transcriptions longer than one CTA's 256 threads under a beam: beta_l2r_slide_kernel (256-model sliding
+    window) against the C oracle; with a beam too wide for the window every utterance takes the redo path through
+    the one-thread-per-label kernel (second parameter set); both against HFBGPU_NO_SLIDE."""
+    from htk_b200 import synth
+    from htk_b200.flat import flatten
+    hs = synth.make_tied_triphone_set(n_states=90, M=4, n_phys=60, n_logical=60, n_centre=8, seed=61, spread=0.2)
+    fm = flatten(hs)
+    feats, labs = synth.sample_corpus(fm, n_utts=3, T=2600, Q=330, seed=12)
+    b = Batch(feats, labs, fm.D)
+    kw = dict(prune=prune)
+    fb = _fb(fm, **kw); res, beams = fb.FBFile(b, want_beams=True); acc = fb.GetAccs(); st = fb.stats(); fb.close()
+    assert st.launchesL2R > 0 and st.launchesBeta == 2          # slide kernel + redo pass
+    oacc, ores, obeams = _oracle(fm, b, kw)
+    for r, o in zip(res, ores):
+        assert r.status == o[0] and r.pruneThresh == o[3] and r.retries == o[1]
+        if o[0] == 0:
+            assert abs(r.pr - o[2]) <= 1e-6 * abs(o[2])
+    for k in ("qLo", "qHi", "sq", "eq"):
+        assert np.array_equal(getattr(beams, k), getattr(obeams, k)), k
+    e = acc_errors(acc, oacc, fm)
+    assert max(e.values()) < RTOL, e
+    monkeypatch.setenv("HFBGPU_NO_SLIDE", "1")
+    fb = _fb(fm, **kw); res2, beams2 = fb.FBFile(b, want_beams=True); fb.close()
+    for x, y in zip(res, res2):
+        assert x.status == y.status and x.pruneThresh == y.pruneThresh and abs(x.pr - y.pr) <= 1e-12 * abs(y.pr)
+    for k in ("qLo", "qHi"):
+        assert np.array_equal(getattr(beams, k), getattr(beams2, k)), k
+
+
 def test_submit_wait_equals_blocking_call():
     """hfbgpu_submit / hfbgpu_wait (batches overlapping on two streams) == hfbgpu_accumulate."""
     z, fm, b, kw = load_golden("synth_tied_m4")
