@@ -316,6 +316,35 @@ def test_model_shapes_against_oracle(shape):
     assert max(e.values()) < RTOL, e
 
 
+def test_shared_variance_vectors_against_oracle():
+    """Variance vectors tied below the component level (~v macros: one VaAcc for several components,
+    HTrain.c:1001-1017): accumulators keyed by varId, against the C oracle."""
+    from htk_b200 import synth
+    from htk_b200.flat import flatten
+    hs = synth.make_tied_triphone_set(n_states=40, M=4, n_phys=30, n_logical=30, n_centre=5, seed=91, spread=0.2)
+    seen = set()
+    for h in hs.hmms:
+        for st in h.states:
+            if id(st) in seen:
+                continue
+            seen.add(id(st))
+            v = st.mixes[0][1].var
+            for _, g in st.mixes[1:]:
+                g.var = v                                  # all components of the state share one variance vector
+                g.gconst = None
+    fm = flatten(hs)
+    assert fm.numVarAcc == fm.J and fm.numMeanAcc == fm.G
+    feats, labs = synth.sample_corpus(fm, n_utts=5, T=240, Q=20, seed=14)
+    b = Batch(feats, labs, fm.D)
+    kw = dict(prune=None)
+    fb = _fb(fm, **kw); res, _ = fb.FBFile(b); acc = fb.GetAccs(); fb.close()
+    oacc, ores, _ = _oracle(fm, b, kw)
+    for r, o in zip(res, ores):
+        assert r.status == o[0] and abs(r.pr - o[2]) <= 1e-6 * abs(o[2])
+    e = acc_errors(acc, oacc, fm)
+    assert max(e.values()) < RTOL, e
+
+
 @pytest.mark.parametrize("prune", [(120.0, 60.0, 600.0), (5000.0, 0.0, 5000.0)])
 def test_long_transcription_sliding_beta_window(prune, monkeypatch):
     """Transcriptions longer than one CTA's 256 threads under a beam: beta_l2r_slide_kernel (256-model sliding
