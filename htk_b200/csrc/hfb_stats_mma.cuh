@@ -88,13 +88,15 @@ __global__ void __launch_bounds__(1024) statpos_scan_kernel(const int *__restric
 // the statistics warp reads ONE flat record instead of chasing ~15 dependent table look-ups per position.
 struct __align__(16) PosRec {
    long long alphaOff, aentOff, betaOff, bOff, frameBase, featOff, trAcc, trOcc;   // element offsets into the wave arrays
+   long long vOff;                  // first entry of this position in the valid-frame list (stats_pre_kernel), -1: none
    double pr;
    int s, q, j, tmin, tmax, N, so, sq1, P, S, Q, J, T, transOff, utt, pad;
    int ps[HFB_MAXN];                // output-probability slots of the model's emitting states
 };
 
 __global__ void __launch_bounds__(128) statpos_scatter_kernel(Wave W, const int *__restrict__ off, int *__restrict__ fill,
-                                                              PosRec *__restrict__ list)
+                                                              PosRec *__restrict__ list, unsigned long long *vCursor,
+                                                              long long vCap, int *__restrict__ posIdx)
 {
    const UttDesc &u = W.utt[blockIdx.x];
    if (W.out[blockIdx.x].status != 0) return;
@@ -111,11 +113,95 @@ __global__ void __launch_bounds__(128) statpos_scatter_kernel(Wave W, const int 
          r.alphaOff = u.occOff + pp; r.aentOff = u.aentOff + q; r.betaOff = u.betaOff; r.bOff = u.bOff;
          r.frameBase = u.frameBase; r.featOff = u.featOff; r.trAcc = W.mTrAcc[gq]; r.trOcc = W.mTrOcc[gq];
          r.pr = W.out[blockIdx.x].pr;
+         {  // room for one entry per frame of the model's alpha-beam span; positions that do not fit keep the inline path
+            const long long span = (long long)r.tmax - r.tmin + 1;
+            const long long o = vCap > 0 ? (long long)atomicAdd(vCursor, (unsigned long long)span) : vCap;
+            r.vOff = (o + span <= vCap) ? o : -1;
+         }
          const int *ps = W.posSlot + u.posOff + W.mPoff[gq];
 #pragma unroll
          for (int i = 0; i < HFB_MAXN; i++) r.ps[i] = (i < r.N - 2) ? ps[i] : 0;
-         list[off[s] + atomicAdd(&fill[s], 1)] = r;
+         const int at = off[s] + atomicAdd(&fill[s], 1);
+         list[at] = r;
+         posIdx[u.posOff + pp] = at;
+      } else
+         posIdx[u.posOff + pp] = -1;
+   }
+}
+
+// ---- front half of the statistics as its own kernel ------------------------------------------------------------
+// Alpha-beam test, state occupancy, SetOcct + UpTranParms, and per position the list of frames that can contribute
+// to the mixture statistics with their initx.  Inside the state-sorted stats5_kernel this part was 43 % of the stall
+// samples and 2.7 GB of DRAM reads per step: a position touches ~16 sectors per frame (alpha, entry alpha, two beta
+// columns, b at t and t+1, beams) and the three states of a model -- which share nearly all of them -- sit in
+// different corners of the sorted list.  Here one warp owns a MODEL of an utterance (lanes <-> frames of a 32-frame
+// window, loop over its emitting states), so those sectors are fetched once, at 64 registers and 32 warps/SM, and
+// stats5_kernel gets dense chunks of 32 VALID frames instead of 32-frame windows of the span.
+struct __align__(16) ValidFrame { double x0; int t; int pad; };
+
+#define SPRE_WARPS 4
+__global__ void __launch_bounds__(32 * SPRE_WARPS, 8) stats_pre_kernel(DevModel M, Wave W, const PosRec *__restrict__ list,
+                                                                       const int *__restrict__ posIdx,
+                                                                       ValidFrame *__restrict__ vbuf, int *__restrict__ vcnt)
+{
+   const UttDesc &u = W.utt[blockIdx.x];
+   if (W.out[blockIdx.x].status != 0) return;
+   const int lane = threadIdx.x & 31;
+   const int uf = W.uFlags;
+   const bool doMix = (uf & (HFB_UPMEANS | HFB_UPVARS | HFB_UPMIXES)) != 0, doTr = (uf & HFB_UPTRANS) != 0;
+   const double minF = W.minFrwdP;
+   const short *sqA = W.sq + u.frameBase, *eqA = W.eq + u.frameBase;
+   StatPos sp;
+   sp.betaU = W.beta + u.betaOff; sp.bU = W.b + u.bOff; sp.qLo = W.qLo + u.frameBase; sp.qHi = W.qHi + u.frameBase;
+   sp.pr = W.out[blockIdx.x].pr; sp.P = u.P; sp.S = u.S; sp.Q = u.Q; sp.J = u.J; sp.T = u.T;
+   const double pr = sp.pr;
+   for (int q = blockIdx.y * SPRE_WARPS + (threadIdx.x >> 5); q < u.Q; q += SPRE_WARPS * gridDim.y) {
+      const int gq = u.modOff + q, tmin = W.mTmin[gq], tmax = W.mTmax[gq];
+      if (tmin > tmax) continue;
+      const int N = W.mN[gq], nj = N - 2, pp0 = W.mPoff[gq];
+      const float *A = M.transLogA + W.mTrans[gq];
+      sp.aent = W.aent + u.aentOff + q; sp.A = A; sp.ps = W.posSlot + u.posOff + pp0;
+      sp.tacc = W.acc + W.mTrAcc[gq]; sp.oacc = W.acc + W.mTrOcc[gq];
+      sp.N = N; sp.so = W.mSoff[gq]; sp.sq1 = (q < u.Q - 1) ? W.mSoff[gq + 1] : 0; sp.q = q; sp.aTee = A[N - 1];
+      // lane j keeps what belongs to emitting state j: list index, list offset, single-Gaussian flag, entries so far
+      int myIdx = -1, myOne = 0, myCnt = 0;
+      long long myOff = -1;
+      if (lane < nj) {
+         myIdx = posIdx[u.posOff + pp0 + lane];
+         if (myIdx >= 0) myOff = list[myIdx].vOff;
+         const int st = W.posState[u.posOff + pp0 + lane];
+         myOne = (M.stateMixOff[st + 1] - M.stateMixOff[st]) == 1;
       }
+      for (int t0 = tmin; t0 <= tmax; t0 += 32) {
+         const int t = t0 + lane;
+         const bool inb = (t <= tmax) && q >= sqA[t] && q <= eqA[t];
+         if (!__ballot_sync(0xffffffffu, inb)) continue;
+         for (int j = 0; j < nj; j++) {
+            const long long vOff = __shfl_sync(0xffffffffu, myOff, j);
+            if (vOff < 0) continue;                    // no room in the list: stats5_kernel does this position inline
+            const int one = __shfl_sync(0xffffffffu, myOne, j), n = __shfl_sync(0xffffffffu, myCnt, j);
+            sp.alphaJ = W.occ + u.occOff + pp0 + j; sp.j = j;
+            sp.aEntJ = A[1 + j]; sp.aExitJ = A[(1 + j) * N + N - 1];
+            if (doTr) stats_tran_chunk(sp, t, inb, lane);
+            if (!doMix) continue;
+            double x0 = OCC_SKIP;
+            if (inb) {
+               const double aj = sp.alphaJ[(size_t)t * u.P];
+               const double *bq = sp.betaU + (size_t)t * u.S + sp.so;
+               const float bjt = sp.bU[(size_t)t * u.J + sp.ps[j]];
+               const double lg = aj + bq[1 + j] - pr;                              // log occupancy of state j
+               if (!(lg < -(minF + 0.25))) x0 = one ? lg : lg - (double)bjt;       // :1575-1576 / initx :1480-1489
+            }
+            const bool valid = inb && x0 > -1.0e29;
+            const unsigned mask = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+               ValidFrame v; v.x0 = x0; v.t = t; v.pad = 0;
+               vbuf[vOff + n + __popc(mask & ((1u << lane) - 1))] = v;
+            }
+            if (lane == j) myCnt += __popc(mask);
+         }
+      }
+      if (lane < nj && myOff >= 0) vcnt[myIdx] = myCnt;
    }
 }
 
@@ -136,7 +222,7 @@ __host__ __device__ inline size_t stats5_warp_bytes(int D)
 template <int NT>
 __global__ void __launch_bounds__(32 * S4_WARPS, 4)
 stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec *__restrict__ list,
-              const int *__restrict__ listEnd)
+              const int *__restrict__ listEnd, const ValidFrame *__restrict__ vbuf, const int *__restrict__ vcnt)
 {
    extern __shared__ __align__(16) unsigned char smraw[];
    const int wInB = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -257,27 +343,41 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
          sp.aEntJ = A[1 + j]; sp.aExitJ = A[(1 + j) * R.N + R.N - 1]; sp.aTee = A[R.N - 1];
          const double pr = sp.pr;
 
-         for (int t0 = tmin; t0 <= tmax; t0 += 32) {
-            const int t = t0 + lane;
-            const bool inb = (t <= tmax) && q >= sqA[t] && q <= eqA[t];
-            double x0 = OCC_SKIP;
-            if (inb) {
-               const double aj = sp.alphaJ[(size_t)t * P];
-               const double *bq = sp.betaU + (size_t)t * S + so;
-               const float bjt = sp.bU[(size_t)t * J + ps[j]];
-               const double lg = aj + bq[1 + j] - pr;                              // log occupancy of state j
-               if (!(lg < -(minF + 0.25))) x0 = (Mn == 1) ? lg : lg - (double)bjt;  // :1575-1576 / initx :1480-1489
+         // two fronts: the dense list of valid frames written by stats_pre_kernel (chunks of 32 valid frames), or -- for
+         // positions that did not fit into the list -- the inline version over 32-frame windows of the span
+         const long long vOff = R.vOff;
+         const int nV = (vOff >= 0) ? vcnt[it] : 0;
+         for (int ch = 0;; ch++) {
+            int nT;
+            if (vOff >= 0) {
+               if (ch * 32 >= nV) break;
+               nT = min(32, nV - ch * 32);
+               __syncwarp();
+               if (lane < nT) { const ValidFrame v = vbuf[vOff + ch * 32 + lane]; ts[lane] = v.t; x0s[lane] = v.x0; }
+            } else {
+               const int t0 = tmin + 32 * ch;
+               if (t0 > tmax) break;
+               const int t = t0 + lane;
+               const bool inb = (t <= tmax) && q >= sqA[t] && q <= eqA[t];
+               double x0 = OCC_SKIP;
+               if (inb) {
+                  const double aj = sp.alphaJ[(size_t)t * P];
+                  const double *bq = sp.betaU + (size_t)t * S + so;
+                  const float bjt = sp.bU[(size_t)t * J + ps[j]];
+                  const double lg = aj + bq[1 + j] - pr;                              // log occupancy of state j
+                  if (!(lg < -(minF + 0.25))) x0 = (Mn == 1) ? lg : lg - (double)bjt;  // :1575-1576 / initx :1480-1489
+               }
+               if (doTr && mb == 0) stats_tran_chunk(sp, t, inb, lane);
+               if (!doMix) continue;
+               // ---- frames of this chunk that can contribute to the mixture statistics
+               const bool valid = inb && x0 > -1.0e29;
+               const unsigned mask = __ballot_sync(0xffffffffu, valid);
+               nT = __popc(mask);
+               if (nT == 0) continue;
+               __syncwarp();
+               if (valid) { int idx = __popc(mask & ((1u << lane) - 1)); ts[idx] = t; x0s[idx] = x0; }
             }
-            if (doTr && mb == 0) stats_tran_chunk(sp, t, inb, lane);
-            if (!doMix) continue;
-            // ---- frames of this chunk that can contribute to the mixture statistics
-            const bool valid = inb && x0 > -1.0e29;
-            const unsigned mask = __ballot_sync(0xffffffffu, valid);
-            const int nT = __popc(mask);
-            if (nT == 0) continue;
             const int nT8 = (nT + 7) & ~7;
-            __syncwarp();
-            if (valid) { int idx = __popc(mask & ((1u << lane) - 1)); ts[idx] = t; x0s[idx] = x0; }
             for (int e = lane; e < 16 * S4_LSTR; e += 32) lrs[e] = 0.f;
             __syncwarp();
             for (int tb = 0; tb < nT8; tb += 8) {                  // observation rows, 8 at a time (16 loads in flight per

@@ -133,7 +133,9 @@ struct hfbgpu_ctx {
       DevBuf<double> dBeta, dOcc, dAent;
       DevBuf<short> dBeams;             // 4 * frames
       DevBuf<unsigned char> dTables, dScratch;
-      DevBuf<int> dStateIdx;            // 3 x (J + 2): count / offset / fill arrays of the by-state position sort
+      DevBuf<int> dStateIdx;            // 3 x (J + 2): count / offset / fill arrays of the by-state position sort, then
+                                        // the 8-byte cursor of the valid-frame list and one count per position
+      DevBuf<ValidFrame> dValid;        // valid-frame list of stats_pre_kernel
       GmmTcWork tcw;
       std::vector<unsigned char> blob;
       unsigned char *hTables = nullptr; // pinned staging
@@ -441,7 +443,7 @@ extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
    for (auto &sl : c->slot) {
       if (sl.stream) cudaStreamSynchronize(sl.stream);
       sl.dFeat.release(); sl.dB.release(); sl.dBeta.release(); sl.dOcc.release(); sl.dAent.release(); sl.dBeams.release();
-      sl.dTables.release(); sl.dScratch.release(); sl.dStateIdx.release(); sl.tcw.release();
+      sl.dTables.release(); sl.dScratch.release(); sl.dStateIdx.release(); sl.dValid.release(); sl.tcw.release();
       if (sl.hTables) cudaFreeHost(sl.hTables);
       if (sl.hOut) cudaFreeHost(sl.hOut);
       if (sl.hBeams) cudaFreeHost(sl.hBeams);
@@ -750,17 +752,36 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
          if (c->hm.maxM >= 4 && Dd + 1 <= 40 && !getenv("HFBGPU_STATS3")) {
             // positions bucketed by tied state (counting sort), then S5_CAP sorted positions per warp
             const int Jm = c->hm.J;
-            if ((rc = S.dStateIdx.reserve((size_t)3 * (Jm + 2)))) return rc;
+            const size_t nIdx = ((size_t)3 * (Jm + 2) + 3) & ~(size_t)3;
+            const bool pre = !getenv("HFBGPU_NO_STATS_PRE");
+            // list capacity: 48 entries per frame of the wave (measured need on the bench configurations: 10-25)
+            long long vCap = 0;
+            if (pre) {
+               long long frames = 0;
+               for (const auto &u : w.utt) frames += u.T;
+               const char *e = getenv("HFBGPU_STATS_PRE_CAP");
+               vCap = e ? atoll(e) : 48 * frames;
+               if (vCap < 1) vCap = 1;
+               if ((rc = S.dValid.reserve((size_t)vCap))) return rc;
+            }
+            if ((rc = S.dStateIdx.reserve(nIdx + 4 + 2 * (size_t)w.totalP))) return rc;
             int *cnt = S.dStateIdx.p, *off = cnt + (Jm + 2), *fill = off + (Jm + 2);
+            unsigned long long *vCursor = (unsigned long long *)(cnt + nIdx);
+            int *vcnt = cnt + nIdx + 4, *posIdx = vcnt + w.totalP;
             PosRec *list = (PosRec *)(sc + sl.posList);
-            CK(cudaMemsetAsync(cnt, 0, (size_t)(Jm + 2) * sizeof(int), st));
+            CK(cudaMemsetAsync(cnt, 0, (nIdx + 4) * sizeof(int), st));
             statpos_count_kernel<<<nU, 128, 0, st>>>(W, cnt);
             statpos_scan_kernel<<<1, 1024, 0, st>>>(cnt, off, fill, Jm);
-            statpos_scatter_kernel<<<nU, 128, 0, st>>>(W, off, fill, list);
+            statpos_scatter_kernel<<<nU, 128, 0, st>>>(W, off, fill, list, vCursor, vCap, posIdx);
+            if (pre) {
+               const int gy = std::max(1, std::min(16, (w.maxQ + SPRE_WARPS - 1) / SPRE_WARPS));
+               stats_pre_kernel<<<dim3(nU, gy), 32 * SPRE_WARPS, 0, st>>>(c->dm, W, list, posIdx, S.dValid.p, vcnt);
+               c->stats.launches++; c->stats.launchesStats++;
+            }
             const unsigned nWarps = (unsigned)((w.totalP + S5_CAP - 1) / S5_CAP);
             const unsigned grid = (nWarps + S4_WARPS - 1) / S4_WARPS;
-            if (Dd + 1 <= 32) stats5_kernel<4><<<grid, 32 * S4_WARPS, S4_WARPS * stats5_warp_bytes<4>(Dd), st>>>(c->dm, W, c->dCentre.p, list, off + Jm);
-            else stats5_kernel<5><<<grid, 32 * S4_WARPS, S4_WARPS * stats5_warp_bytes<5>(Dd), st>>>(c->dm, W, c->dCentre.p, list, off + Jm);
+            if (Dd + 1 <= 32) stats5_kernel<4><<<grid, 32 * S4_WARPS, S4_WARPS * stats5_warp_bytes<4>(Dd), st>>>(c->dm, W, c->dCentre.p, list, off + Jm, S.dValid.p, vcnt);
+            else stats5_kernel<5><<<grid, 32 * S4_WARPS, S4_WARPS * stats5_warp_bytes<5>(Dd), st>>>(c->dm, W, c->dCentre.p, list, off + Jm, S.dValid.p, vcnt);
             c->stats.launches += 3; c->stats.launchesStats += 3;
          } else
             stats3_kernel<<<(unsigned)((w.totalP + ST_WARPS - 1) / ST_WARPS), 32 * ST_WARPS, stats_smem_bytes(c->dm.D), st>>>(c->dm, W);

@@ -285,6 +285,24 @@ def test_tensor_core_statistics_equal_fp32_statistics(name, monkeypatch):
     assert max(e.values()) < RTOL, e
 
 
+@pytest.mark.parametrize("name", ["synth_tied_m4", "synth_long_m3", "synth_tee_m2"])
+@pytest.mark.parametrize("cap", [None, "700"])
+def test_statistics_front_kernel_equals_inline_front(name, cap, monkeypatch):
+    """stats_pre_kernel (transitions + list of valid frames per position) against the inline front of
+    stats5_kernel (HFBGPU_NO_STATS_PRE); with a list too small for the wave (HFBGPU_STATS_PRE_CAP) some positions
+    take one front and some the other inside the same launch."""
+    z, fm, b, kw = load_golden(name)
+    if cap:
+        monkeypatch.setenv("HFBGPU_STATS_PRE_CAP", cap)
+    fb = _fb(fm, **kw); fb.FBFile(b); a1 = fb.GetAccs(); fb.close()
+    monkeypatch.setenv("HFBGPU_NO_STATS_PRE", "1")
+    fb = _fb(fm, **kw); fb.FBFile(b); a2 = fb.GetAccs(); fb.close()
+    e = acc_errors(a1, a2, fm)             # chunks group other frames: FP32 summation order differs
+    assert max(e.values()) < 5e-6, e
+    e = acc_errors(a1, z["ref_acc"], fm)
+    assert max(e.values()) < RTOL, e
+
+
 @pytest.mark.parametrize("shape", [
     dict(D=39, M=[1, 3, 4, 7, 16], parm="MFCC_0_D_A"),      # mixed component counts incl. single Gaussians, dead components
     dict(D=39, M=20, parm="MFCC_0_D_A"),                    # two 16-component tiles in the statistics kernel, MP = 32
