@@ -129,6 +129,21 @@ __global__ void __launch_bounds__(128) statpos_scatter_kernel(Wave W, const int 
    }
 }
 
+// ---- packed FP32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100): two frames of one component per instruction in phase 1
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t f2_sub(f32x2_t a, f32x2_t b) { f32x2_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// one dimension of two frames: sum += ((o - mu)^2) * ivar, the product and the sum fused (one rounding fewer than
+// IDOutP, HModel.c:5425-5430: ~1e-7 relative on log N, three orders below the parity bound)
+__device__ __forceinline__ f32x2_t f2_step(f32x2_t sum, f32x2_t o, float mu, float iv)
+{
+   const f32x2_t d = f2_sub(o, f2_pack(mu, mu));
+   return f2_fma(f2_mul(d, d), f2_pack(iv, iv), sum);
+}
+
 // ---- front half of the statistics as its own kernel ------------------------------------------------------------
 // Alpha-beam test, state occupancy, SetOcct + UpTranParms, and per position the list of frames that can contribute
 // to the mixture statistics with their initx.  Inside the state-sorted stats5_kernel this part was 43 % of the stall
@@ -205,14 +220,19 @@ __global__ void __launch_bounds__(32 * SPRE_WARPS, 8) stats_pre_kernel(DevModel 
    }
 }
 
-#define S5_GSTR 44                    // row stride (floats) of the staged Gaussian parameters: 16-byte aligned rows
-// Shared memory per warp: x0s[32] doubles, ts[32] ints, the observation tile [32][8 NT + 1] (columns: D
+#define S5_GSTR 44                   // row stride (floats) of the staged Gaussian parameters: 16-byte aligned rows
+// observation tile: frames interleaved in pairs, os[(row >> 1) * S5_OPS + 2 * col + (row & 1)], so that phase 1 reads
+// {o_a[k], o_b[k], o_a[k+1], o_b[k+1]} of a frame pair with one 128-bit load; 84 = 2 * 40 columns + 4 (pair rows of a
+// quarter warp on distinct banks)
+#define S5_OPS 84
+#define S5_OS(row, col) ((((row) >> 1) * S5_OPS) + 2 * (col) + ((row) & 1))
+// Shared memory per warp: x0s[32] doubles, ts[32] ints, the observation tile (16 frame pairs x S5_OPS; columns: D
 // dimensions, a ones column, zero padding), the Lr tile [16][S4_LSTR] (both reused as flush staging
 // [16][16 NT]) and the state's Gaussians (means, inverse variances, gConst, log weights).
 template <int NT>
 __host__ __device__ inline size_t stats5_warp_bytes(int D)
 {
-   const size_t work = sizeof(float) * ((size_t)32 * (8 * NT + 1) + 16 * S4_LSTR);
+   const size_t work = sizeof(float) * ((size_t)16 * S5_OPS + 16 * S4_LSTR);
    const size_t flush = sizeof(float) * 16 * 16 * NT;
    const size_t gauss = sizeof(float) * (2 * 16 * S5_GSTR + 32);
    return sizeof(double) * 32 + sizeof(int) * 32 + ((((work > flush) ? work : flush) + 15) & ~(size_t)15) + gauss;
@@ -230,12 +250,11 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
    const int i0 = (blockIdx.x * S4_WARPS + wInB) * S5_CAP, i1 = min(nSorted, i0 + S5_CAP);
    if (i0 >= i1) return;
    const int D = M.D, Dp = M.Dp;
-   constexpr int ostr = 8 * NT + 1;
    unsigned char *mine = smraw + stats5_warp_bytes<NT>(D) * wInB;
    double *x0s = (double *)mine;                       // [32] initx / log occupancy per chunk frame
    int *ts = (int *)(x0s + 32);                        // [32] frame numbers
    float *os = (float *)(ts + 32);                     // [32][ostr] observations | 1 | 0...
-   float *lrs = os + 32 * ostr;                        // [16 components][S4_LSTR] occupancies Lr
+   float *lrs = os + 16 * S5_OPS;                        // [16 components][S4_LSTR] occupancies Lr
    float *fb = os;                                     // flush staging [16][16 NT]
    constexpr int FSTR = 16 * NT;
    float *gmu = (float *)(mine + stats5_warp_bytes<NT>(D) - sizeof(float) * (2 * 16 * S5_GSTR + 32));
@@ -393,9 +412,9 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
                }
 #pragma unroll
                for (int r = 0; r < 8; r++) {
-                  float *dst = os + (tb + r) * ostr;
-                  if (lane < 8 * NT) dst[lane] = v0[r];
-                  if (lane + 32 < 8 * NT) dst[lane + 32] = v1[r];
+                  float *dst = os + S5_OS(tb + r, 0);
+                  if (lane < 8 * NT) dst[2 * lane] = v0[r];
+                  if (lane + 32 < 8 * NT) dst[2 * (lane + 32)] = v1[r];
                }
             }
             __syncwarp();
@@ -406,38 +425,47 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
             //      3.7x fewer instructions for this phase, but the kernel got 9-14 % SLOWER on B200 -- the legacy
             //      HMMA path cannot keep up; the tcgen05 version needs frames gathered per state, see DESIGN.md.)
             unsigned anyLr = 0;
-            for (int pi = lane; pi < ((Mc * nT + 31) & ~31); pi += 32) {
-               float Lr = 0.f;
-               const int mi = pi / nT, ti = pi - mi * nT;
+            // lane <-> (component, frame pair): the two frames share the component's parameters and go through the
+            // packed FP32 pipe together; row nT of an odd chunk is zero padding and its result is dropped
+            const int nTh = (nT + 1) >> 1;
+            const float rnT = 1.0f / (float)nTh;                 // (pi + 0.5) / nTh is never within 1/32 of an integer
+            for (int pi = lane; pi < ((Mc * nTh + 31) & ~31); pi += 32) {
+               float Lr0 = 0.f, Lr1 = 0.f;
+               const int mi = (int)(((float)pi + 0.5f) * rnT), th = pi - mi * nTh, ti = 2 * th;
                if (mi < Mc) {
                   const float wt = gwt[mi];
+                  const bool two = ti + 1 < nT;
                   if (wt > LMINMIX_F) {                                         // HFB.c:1573
-                     double x = x0s[ti];
+                     double xa = x0s[ti], xb = two ? x0s[ti + 1] : 0.0;
                      if (Mn > 1) {
                         const float *mu = gmu + mi * S5_GSTR, *iv = giv + mi * S5_GSTR;
-                        const float *o = os + ti * ostr;
-                        float sum = ggc[mi];
+                        const float *o = os + th * S5_OPS;
+                        f32x2_t sum = f2_pack(ggc[mi], ggc[mi]);
                         int k = 0;
-                        for (; k + 4 <= D; k += 4) {                            // IDOutP's order of operations, HModel.c:5425-5430
+                        for (; k + 4 <= D; k += 4) {
                            const float4 m4 = *reinterpret_cast<const float4 *>(mu + k);
                            const float4 v4 = *reinterpret_cast<const float4 *>(iv + k);
-                           float d = __fsub_rn(o[k], m4.x);     sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), v4.x));
-                           d = __fsub_rn(o[k + 1], m4.y);       sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), v4.y));
-                           d = __fsub_rn(o[k + 2], m4.z);       sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), v4.z));
-                           d = __fsub_rn(o[k + 3], m4.w);       sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), v4.w));
+                           const ulonglong2 oa = *reinterpret_cast<const ulonglong2 *>(o + 2 * k);
+                           const ulonglong2 ob = *reinterpret_cast<const ulonglong2 *>(o + 2 * k + 4);
+                           sum = f2_step(sum, oa.x, m4.x, v4.x);
+                           sum = f2_step(sum, oa.y, m4.y, v4.y);
+                           sum = f2_step(sum, ob.x, m4.z, v4.z);
+                           sum = f2_step(sum, ob.y, m4.w, v4.w);
                         }
-                        for (; k < D; k++) {
-                           const float d = __fsub_rn(o[k], mu[k]);
-                           sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), iv[k]));
-                        }
-                        const float mixp = -0.5f * sum;
-                        x = (x + (double)wt) + (double)mixp;                    // :1581-1599
+                        for (; k < D; k++)
+                           sum = f2_step(sum, *reinterpret_cast<const f32x2_t *>(o + 2 * k), mu[k], iv[k]);
+                        float sa, sb;
+                        f2_unpack(sum, sa, sb);
+                        xa = (xa + (double)wt) + (double)(-0.5f * sa);          // :1581-1599
+                        xb = (xb + (double)wt) + (double)(-0.5f * sb);
                      }
-                     if (-x < minF) Lr = expf((float)x);                        // :1606, :1612
+                     if (-xa < minF) Lr0 = expf((float)xa);                     // :1606, :1612
+                     if (two && -xb < minF) Lr1 = expf((float)xb);
                   }
-                  lrs[mi * S4_LSTR + ti] = Lr;
+                  lrs[mi * S4_LSTR + ti] = Lr0;
+                  if (two) lrs[mi * S4_LSTR + ti + 1] = Lr1;
                }
-               anyLr |= __ballot_sync(0xffffffffu, Lr > 0.f);
+               anyLr |= __ballot_sync(0xffffffffu, Lr0 > 0.f || Lr1 > 0.f);
             }
             __syncwarp();
             if (!anyLr) continue;
@@ -451,10 +479,10 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
                   ah[0] = s4_hi(a0); ah[1] = s4_hi(a1); ah[2] = s4_hi(a2); ah[3] = s4_hi(a3);
                   al[0] = s4_lo(a0); al[1] = s4_lo(a1); al[2] = s4_lo(a2); al[3] = s4_lo(a3);
                }
-               const float *o0 = os + (ks + fc) * ostr, *o1 = o0 + 4 * ostr;
+               const float *o0 = os + S5_OS(ks + fc, 0), *o1 = o0 + 2 * S5_OPS;
 #pragma unroll
                for (int nt = 0; nt < NT; nt++) {
-                  const float v0 = o0[nt * 8 + fg] - cenB[nt], v1 = o1[nt * 8 + fg] - cenB[nt];   // column D of the tile holds 1
+                  const float v0 = o0[2 * (nt * 8 + fg)] - cenB[nt], v1 = o1[2 * (nt * 8 + fg)] - cenB[nt];   // column D of the tile holds 1
                   // the tensor core forms the 8-frame partial products in a fresh fragment; the running sums are
                   // kept on the FP32 pipe (round to nearest): its own accumulation truncates, which over the
                   // ~100 MMAs of a flush interval would bias every occupancy sum by several 1e-6

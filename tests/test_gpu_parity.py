@@ -279,8 +279,8 @@ def test_tensor_core_statistics_equal_fp32_statistics(name, monkeypatch):
     fb = _fb(fm, **kw); fb.FBFile(b); a1 = fb.GetAccs(); fb.close()
     monkeypatch.setenv("HFBGPU_STATS3", "1")
     fb = _fb(fm, **kw); fb.FBFile(b); a2 = fb.GetAccs(); fb.close()
-    e = acc_errors(a1, a2, fm)
-    assert max(e.values()) < 5e-6, e
+    e = acc_errors(a1, a2, fm)             # stats5: centre-relative TF32-split sums, product and sum of IDOutP's
+    assert max(e.values()) < 2e-5, e       # inner loop fused (FFMA2); stats3: the reference's order of operations
     e = acc_errors(a1, z["ref_acc"], fm)
     assert max(e.values()) < RTOL, e
 
