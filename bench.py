@@ -432,13 +432,13 @@ def main():
         st_flop = alpha_cells * 3 * M * 2 * 2 * fm.D            # F_acc = sum over alpha cells (N-2) M 2 2D
         if kms["stats"] > 0:
             ach = st_flop / (kms["stats"] * 1e-3) / 1e12
-            rl["stats"] = {"bound": "tensor", "kernel": "stats5_kernel (state-major, mma.sync 3xTF32 sums) + statpos_* sort",
+            rl["stats"] = {"bound": "tensor", "kernel": "stats_pre_kernel (model-major occupancies + transitions) + stats5_kernel (state-major, packed-FP32 posteriors, mma.sync 3xTF32 sums) + statpos_* sort",
                            "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": None,
-                           "ms_per_launch": kms["stats"], "launches_per_step": 4,
+                           "ms_per_launch": kms["stats"], "launches_per_step": 5,
                            "note": "SURVEY 8d classes the statistics as a tensor-pipe contraction with F_acc = alpha cells x (N-2) x M x 4D "
                                    "algorithmic FLOP; the occupancy matrix is ~2 %% dense (alpha_cells / frames ~ 1.7 models per frame), so "
-                                   "that is %.1f GFLOP per step and the kernel is bound by recomputing the component posteriors on the FP32 "
-                                   "pipe (47 %% of its instructions) and by memory latency at 16 warps/SM, not by the tensor pipe "
+                                   "that is %.1f GFLOP per step and the kernels are bound by gathering the observation rows, recomputing the "
+                                   "component posteriors (FFMA2 pairs) and memory latency at 16 warps/SM, not by the tensor pipe "
                                    "(profiles/README.md)" % (st_flop / 1e9)}
         by = beta_cells * 104.0 + n_utts * T * fm.D * 4 * 2
         ms = kms["beta"] + kms["alpha"]

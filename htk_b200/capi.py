@@ -20,7 +20,7 @@ EXPORTS = [
     "hfbgpu_accumulate", "hfbgpu_accumulate_device", "hfbgpu_acc_device_ptr", "hfbgpu_acc_count",
     "hfbgpu_get_accs", "hfbgpu_set_accs", "hfbgpu_state_loglik", "hfbgpu_get_min_durs",
     "hfbgpu_get_stats", "hfbgpu_reset_stats", "hfbgpu_set_timing", "hfbgpu_set_stream", "hfbgpu_submit", "hfbgpu_wait",
-    "hfbgpu_host_alloc", "hfbgpu_host_free", "hfbgpu_mstep",
+    "hfbgpu_host_alloc", "hfbgpu_host_free", "hfbgpu_mstep", "hfbgpu_set_qualifiers", "hfbgpu_expand_features",
 ]
 
 _lib = None
@@ -68,6 +68,8 @@ def load():
     l.hfbgpu_state_loglik.argtypes = [vp, vp, i32, vp, i32, vp, vp]
     l.hfbgpu_get_min_durs.argtypes = [vp, vp]
     l.hfbgpu_mstep.argtypes = [vp, vp, vp]
+    l.hfbgpu_set_qualifiers.argtypes = [vp, vp]
+    l.hfbgpu_expand_features.argtypes = [vp, vp, vp, i32, vp]
     l.hfbgpu_get_stats.argtypes = [vp, C.POINTER(hfb_stats)]
     l.hfbgpu_reset_stats.argtypes = [vp]
     l.hfbgpu_set_timing.argtypes = [vp, C.c_int]

@@ -1,0 +1,110 @@
+// hfb_feat.cuh -- parameter-kind qualifiers on the device: delta / acceleration / third
+// differential coefficients and per-utterance cepstral mean normalisation, so that a caller whose files hold
+// only the static coefficients (the usual HTK set-up: MFCC_0 on disk, TARGETKIND = MFCC_0_D_A[_Z] in the
+// training configuration) uploads a third of the bytes and leaves HParm's AddQualifiers to the GPU.
+//
+// Restates, for tables (whole utterances: hdValid = tlValid = 0), HTKLib/HParm.c:1618-1722 AddQualifiers ->
+// :1552-1599 AddDiffs -> HTKLib/HSigP.c:827-857 Regress and HSigP.c:803-823 FZeroMean:
+//   * order o+1 coefficients = regression over order o coefficients, all static columns (cepstra, c0 / energy):
+//       sum_{th=1..W} th * (c[min(t+th, T-1)] - c[max(t-th, 0)]) / (2 sum th^2)          (:842-852)
+//     or (c[t+W] - c[t-W]) / (2W) with SIMPLEDIFFS (:849-850); the first / last frame is replicated at the
+//     ends (:844-845).  Every operation is a separately rounded FP32 operation in the reference's order, so the
+//     result is bit-identical to HCopy / HERest's own loader;
+//   * _Z: the mean of the leading `zeroMeanCols` static columns (cepstra and c0, not the energy) over the
+//     utterance is accumulated in double, rounded to float and subtracted (:809-821), AFTER the
+//     differentials were formed (AddQualifiers' order).  The reference adds the T values sequentially; here 32
+//     lanes add strided partial sums: the double sum can differ in the last bit, the float mean only when that
+//     bit decides a rounding (never seen on the golden vectors).
+// Not covered (hfbgpu_set_qualifiers rejects what it cannot express): _N (absolute energy suppressed), _V / global
+// mean / variance files, MatTran input transforms, V1COMPAT differences, HIGHDIFF fourth order.
+#pragma once
+#include "hfb_common.h"
+
+struct FeatQual {
+   int numStatic;                   // columns of the source matrix
+   int win[3];                      // DELTAWINDOW, ACCWINDOW, THIRDWINDOW; 0 = order absent
+   int simpleDiffs;
+   int zeroMeanCols;
+   int enabled;
+};
+
+// One regression pass: dst[t][dstCol + c] = Regress(src[.][srcCol + c]), c < d.  copyStatic: also
+// dst[t][c] = src[t][c] (first pass, source = the caller's static matrix).
+__global__ void __launch_bounds__(256) feat_regress_kernel(const UttDesc *__restrict__ utt, const float *__restrict__ src,
+                                                           int srcStride, int srcCol, float *__restrict__ dst, int dstStride,
+                                                           int dstCol, int d, int win, int simple, int copyStatic)
+{
+   const UttDesc &u = utt[blockIdx.y];
+   const int T = u.T;
+   const int FR = 256 / 16;                              // frames per block pass (a 16 x 16 tile of (frame, column))
+   const float *s0 = src + (size_t)u.featOff * srcStride + srcCol;
+   float *d0 = dst + (size_t)u.featOff * dstStride;
+   float sigmaT2 = 0.f;
+   for (int th = 1; th <= win; th++) sigmaT2 = __fadd_rn(sigmaT2, (float)(th * th));
+   sigmaT2 = __fmul_rn(sigmaT2, 2.f);
+   for (int t = blockIdx.x * FR + (threadIdx.x >> 4); t < T; t += gridDim.x * FR)
+      for (int c = threadIdx.x & 15; c < d; c += 16) {
+         float sum = 0.f, fw = 0.f, bk = 0.f;
+         for (int th = 1; th <= win; th++) {
+            fw = s0[(size_t)min(t + th, T - 1) * srcStride + c];
+            bk = s0[(size_t)max(t - th, 0) * srcStride + c];
+            if (!simple) sum = __fadd_rn(sum, __fmul_rn((float)th, __fsub_rn(fw, bk)));
+         }
+         const float v = simple ? __fdiv_rn(__fsub_rn(fw, bk), (float)(2 * win)) : __fdiv_rn(sum, sigmaT2);
+         d0[(size_t)t * dstStride + dstCol + c] = v;
+         if (copyStatic) d0[(size_t)t * dstStride + c] = s0[(size_t)t * srcStride + c];
+      }
+}
+
+// plain widening copy for a qualifier set without differentials (only _Z)
+__global__ void __launch_bounds__(256) feat_copy_kernel(const UttDesc *__restrict__ utt, const float *__restrict__ src, int srcStride,
+                                                        float *__restrict__ dst, int dstStride, int d)
+{
+   const UttDesc &u = utt[blockIdx.y];
+   const float *s0 = src + (size_t)u.featOff * srcStride;
+   float *d0 = dst + (size_t)u.featOff * dstStride;
+   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < (long long)u.T * d; e += (long long)gridDim.x * 256) {
+      const int t = (int)(e / d), c = (int)(e - (long long)t * d);
+      d0[(size_t)t * dstStride + c] = s0[(size_t)t * srcStride + c];
+   }
+}
+
+// FZeroMean over the leading zCols columns of one utterance per block, one warp per column
+__global__ void __launch_bounds__(256) feat_zeromean_kernel(const UttDesc *__restrict__ utt, float *__restrict__ dst, int dstStride,
+                                                            int zCols)
+{
+   const UttDesc &u = utt[blockIdx.x];
+   const int T = u.T, lane = threadIdx.x & 31;
+   float *d0 = dst + (size_t)u.featOff * dstStride;
+   for (int c = threadIdx.x >> 5; c < zCols; c += 8) {
+      double s = 0.0;
+      for (int t = lane; t < T; t += 32) s += (double)d0[(size_t)t * dstStride + c];
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = (float)(s / (double)T);
+      for (int t = lane; t < T; t += 32) d0[(size_t)t * dstStride + c] = __fsub_rn(d0[(size_t)t * dstStride + c], mean);
+   }
+}
+
+// Enqueues the passes for nU utterances described by utt[] (device; only featOff and T are read).
+static inline int feat_expand_launch(const FeatQual &q, const UttDesc *utt, int nU, int maxT, const float *src, float *dst, int D,
+                                     cudaStream_t st, int *launches)
+{
+   if (nU <= 0) return 0;
+   const int ns = q.numStatic;
+   const dim3 grid((unsigned)std::max(1, std::min(64, (maxT + 15) / 16)), (unsigned)nU);
+   int n = 0;
+   if (q.win[0] > 0) {
+      feat_regress_kernel<<<grid, 256, 0, st>>>(utt, src, ns, 0, dst, D, ns, ns, q.win[0], q.simpleDiffs, 1);
+      n++;
+      for (int o = 1; o < 3 && q.win[o] > 0; o++) {
+         feat_regress_kernel<<<grid, 256, 0, st>>>(utt, dst, D, o * ns, dst, D, (o + 1) * ns, ns, q.win[o], q.simpleDiffs, 0);
+         n++;
+      }
+   } else {
+      feat_copy_kernel<<<grid, 256, 0, st>>>(utt, src, ns, dst, D, ns);
+      n++;
+   }
+   if (q.zeroMeanCols > 0) { feat_zeromean_kernel<<<nU, 256, 0, st>>>(utt, dst, D, q.zeroMeanCols); n++; }
+   if (launches) *launches += n;
+   return 0;
+}

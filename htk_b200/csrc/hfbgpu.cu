@@ -23,6 +23,7 @@
 #include "hfb_l2r.cuh"
 #include "hfb_stats_mma.cuh"
 #include "hfb_mstep.cuh"
+#include "hfb_feat.cuh"
 #include "gmm_tc.cuh"
 
 static thread_local std::string g_lastError;
@@ -85,12 +86,12 @@ struct WaveTables {
    std::vector<int> uttIndex;        // index in the caller's batch
    long long bFloats = 0, betaDoubles = 0, occDoubles = 0, aentDoubles = 0;
    long long totalQ = 0, totalP = 0, tiles = 0;
-   int maxQ = 0, maxS = 0, maxN = 0;
+   int maxQ = 0, maxS = 0, maxN = 0, maxT = 0;
    int lab0 = 0;                     // first label of the wave in the caller's label array
    void clear()
    {
       utt.clear(); out.clear(); posPre.clear(); tilePre.clear(); tcItems.clear(); tcItems2.clear(); tcItems4.clear(); uttIndex.clear();
-      bFloats = betaDoubles = occDoubles = aentDoubles = 0; totalQ = totalP = tiles = 0; maxQ = maxS = maxN = 0; lab0 = 0;
+      bFloats = betaDoubles = occDoubles = aentDoubles = 0; totalQ = totalP = tiles = 0; maxQ = maxS = maxN = maxT = 0; lab0 = 0;
    }
 };
 
@@ -110,6 +111,7 @@ struct hfbgpu_ctx {
    bool trace = false;
    int waveUtts = 592;                  // utterances per wave (see launch_wave: recursions co-reside with the next GMM)
    bool timing = false;
+   FeatQual qual = {};                  // hfbgpu_set_qualifiers: feat matrices hold static coefficients only
    hfb_stats stats;
    // model on device
    DevBuf<float> dMean, dIvar, dGconst, dMixLogWt, dTransLogA;
@@ -128,7 +130,8 @@ struct hfbgpu_ctx {
       cudaEvent_t evIn = nullptr, evGmm = nullptr;   // inputs uploaded / output probabilities ready
       cudaEvent_t evX = nullptr;        // timing mode: feature expansion done, tensor-core kernel starts
       bool hasX = false;
-      DevBuf<float> dFeat;              // only for host-feature calls
+      DevBuf<float> dFeat;              // only for host-feature calls and for expanded features
+      DevBuf<float> dFeatSrc;           // host static coefficients before the qualifier expansion
       DevBuf<float> dB;
       DevBuf<double> dBeta, dOcc, dAent;
       DevBuf<short> dBeams;             // 4 * frames
@@ -443,7 +446,7 @@ extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
    for (auto &sl : c->slot) {
       if (sl.stream) cudaStreamSynchronize(sl.stream);
       sl.dFeat.release(); sl.dB.release(); sl.dBeta.release(); sl.dOcc.release(); sl.dAent.release(); sl.dBeams.release();
-      sl.dTables.release(); sl.dScratch.release(); sl.dStateIdx.release(); sl.dValid.release(); sl.tcw.release();
+      sl.dTables.release(); sl.dScratch.release(); sl.dStateIdx.release(); sl.dValid.release(); sl.dFeatSrc.release(); sl.tcw.release();
       if (sl.hTables) cudaFreeHost(sl.hTables);
       if (sl.hOut) cudaFreeHost(sl.hOut);
       if (sl.hBeams) cudaFreeHost(sl.hBeams);
@@ -544,6 +547,7 @@ size_t add_utterance(const HostModel &h, WaveTables &w, int uidx, int T, const i
    if (bad) { o.status = HFB_UTT_ETEE; Q = 0; S = 0; }
    const int Pp = S - 2 * Q;
    u.T = T; u.Q = Q; u.S = S; u.P = Pp; u.J = Pp;
+   w.maxT = std::max(w.maxT, T);
    u.labOff = labOff; u.modOff = (int)w.totalQ; u.slotOff = (int)w.totalP; u.posOff = (int)w.totalP;
    u.featOff = featOff; u.frameBase = featOff;
    u.bOff = w.bFloats; u.betaOff = w.betaDoubles; u.occOff = w.occDoubles; u.aentOff = w.aentDoubles;
@@ -607,15 +611,22 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
    const int D = c->hm.D;
    S.waveFrame0 = waveFrame0; S.waveFrames = waveFrames; S.wantBeams = wantBeams;
    S.busy = true;
-   // ---- features
-   const float *dFeat;
-   if (featOnDevice) dFeat = feat + (size_t)waveFrame0 * D;
+   // ---- features (with qualifiers: the caller's matrix holds numStatic columns, expanded below into S.dFeat)
+   const FeatQual &fq = c->qual;
+   const int Dsrc = fq.enabled ? fq.numStatic : D;
+   const float *dFeat, *dFeatSrc = nullptr;
+   if (featOnDevice) dFeat = feat + (size_t)waveFrame0 * Dsrc;
    else {
-      if ((rc = S.dFeat.reserve((size_t)waveFrames * D + 4))) return rc;
-      CK(cudaMemcpyAsync(S.dFeat.p, feat + (size_t)waveFrame0 * D, (size_t)waveFrames * D * sizeof(float),
+      DevBuf<float> &stage = fq.enabled ? S.dFeatSrc : S.dFeat;
+      if ((rc = stage.reserve((size_t)waveFrames * Dsrc + 4))) return rc;
+      CK(cudaMemcpyAsync(stage.p, feat + (size_t)waveFrame0 * Dsrc, (size_t)waveFrames * Dsrc * sizeof(float),
                          cudaMemcpyHostToDevice, st));
-      c->stats.h2dBytes += (int64_t)waveFrames * D * sizeof(float);
-      dFeat = S.dFeat.p;
+      c->stats.h2dBytes += (int64_t)waveFrames * Dsrc * sizeof(float);
+      dFeat = stage.p;
+   }
+   if (fq.enabled) {
+      if ((rc = S.dFeat.reserve((size_t)waveFrames * D + 4))) return rc;
+      dFeatSrc = dFeat; dFeat = S.dFeat.p;
    }
    // ---- pack + upload the (small) host tables
    w.posPre.push_back((int)w.totalP);
@@ -654,6 +665,11 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
    W.mTmin = (int *)(sc + sl.mTmin); W.mTmax = (int *)(sc + sl.mTmax);
    W.slotState = (int *)(sc + sl.slotState); W.posSlot = (int *)(sc + sl.posSlot); W.posState = (int *)(sc + sl.posState); W.posQ = (int *)(sc + sl.posQ);
    W.feat = dFeat;
+   if (fq.enabled) {
+      int nl = 0;
+      feat_expand_launch(fq, W.utt, nU, w.maxT, dFeatSrc, S.dFeat.p, D, st, &nl);
+      c->stats.launches += nl; c->stats.launchesMisc += nl;
+   }
    W.b = S.dB.p; W.beta = S.dBeta.p; W.occ = S.dOcc.p; W.aent = S.dAent.p;
    W.qLo = S.dBeams.p; W.qHi = W.qLo + waveFrames; W.sq = W.qHi + waveFrames; W.eq = W.sq + waveFrames;
    W.acc = c->dAcc.p;
@@ -1011,6 +1027,67 @@ extern "C" int hfbgpu_mstep(hfbgpu_ctx *c, const hfb_mstep_options *opt, hfb_mst
    dInts.release(); dFl.release();
    if (e != cudaSuccess) { g_lastError = std::string("hfbgpu_mstep: ") + cudaGetErrorString(e); return HFB_ECUDA; }
    out->nFloorVar = hc[0]; out->nFloorVarMix = hc[1]; out->nCopied = hc[2]; out->nNoOcc = hc[3];
+   return HFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Parameter-kind qualifiers (hfb_feat.cuh)
+// ------------------------------------------------------------------------------------------
+extern "C" int hfbgpu_set_qualifiers(hfbgpu_ctx *c, const hfb_qualifiers *q)
+{
+   if (!c) return HFB_EINVAL;
+   { int rc = wait_impl(c); if (rc) return rc; }
+   if (!q) { c->qual = FeatQual(); return HFB_OK; }
+   const int orders = 1 + (q->delWin > 0) + (q->accWin > 0) + (q->thirdWin > 0);
+   if (q->numStatic < 1 || q->delWin < 0 || q->accWin < 0 || q->thirdWin < 0 || q->delWin > 64 || q->accWin > 64 ||
+       q->thirdWin > 64 || (q->accWin > 0 && q->delWin == 0) || (q->thirdWin > 0 && q->accWin == 0) ||
+       q->zeroMeanCols < 0 || q->zeroMeanCols > q->numStatic) {
+      g_lastError = "inconsistent qualifier description"; return HFB_EINVAL;
+   }
+   if (q->numStatic * orders != c->hm.D) {
+      g_lastError = "qualifiers do not expand to the model's vector size"; return HFB_EINVAL;
+   }
+   FeatQual f;
+   f.numStatic = q->numStatic; f.win[0] = q->delWin; f.win[1] = q->accWin; f.win[2] = q->thirdWin;
+   f.simpleDiffs = q->simpleDiffs != 0; f.zeroMeanCols = q->zeroMeanCols; f.enabled = 1;
+   c->qual = f;
+   return HFB_OK;
+}
+
+extern "C" int hfbgpu_expand_features(hfbgpu_ctx *c, const float *src, const int64_t *frameOff, int32_t numUtt, float *dst)
+{
+   if (!c || !src || !frameOff || !dst || numUtt < 0) return HFB_EINVAL;
+   if (!c->qual.enabled) { g_lastError = "hfbgpu_set_qualifiers has not been called"; return HFB_EINVAL; }
+   if (numUtt == 0) return HFB_OK;
+   CK(cudaSetDevice(c->device));
+   { int rc = wait_impl(c); if (rc) return rc; }
+   const int D = c->hm.D, ns = c->qual.numStatic;
+   std::vector<UttDesc> utt((size_t)numUtt);
+   int maxT = 0;
+   for (int u = 0; u < numUtt; u++) {
+      const long long T = frameOff[u + 1] - frameOff[u];
+      if (T < 1 || T > 0x7fffffff) return HFB_EINVAL;
+      memset(&utt[u], 0, sizeof(UttDesc));
+      utt[u].T = (int)T; utt[u].featOff = frameOff[u] - frameOff[0];
+      maxT = std::max(maxT, (int)T);
+   }
+   const size_t frames = (size_t)(frameOff[numUtt] - frameOff[0]);
+   DevBuf<float> dSrc, dDst;
+   DevBuf<UttDesc> dUtt;
+   int rc;
+   if ((rc = dSrc.reserve(frames * ns)) || (rc = dDst.reserve(frames * D)) || (rc = dUtt.reserve((size_t)numUtt))) {
+      dSrc.release(); dDst.release(); dUtt.release(); return rc;
+   }
+   cudaStream_t st = c->stream;
+   cudaError_t e = cudaMemcpyAsync(dSrc.p, src + (size_t)frameOff[0] * ns, frames * ns * sizeof(float), cudaMemcpyHostToDevice, st);
+   if (e == cudaSuccess) e = cudaMemcpyAsync(dUtt.p, utt.data(), utt.size() * sizeof(UttDesc), cudaMemcpyHostToDevice, st);
+   int nl = 0;
+   if (e == cudaSuccess) { feat_expand_launch(c->qual, dUtt.p, numUtt, maxT, dSrc.p, dDst.p, D, st, &nl); e = cudaGetLastError(); }
+   if (e == cudaSuccess) e = cudaMemcpyAsync(dst + (size_t)frameOff[0] * D, dDst.p, frames * D * sizeof(float), cudaMemcpyDeviceToHost, st);
+   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+   c->stats.launches += nl; c->stats.launchesMisc += nl;
+   dSrc.release(); dDst.release(); dUtt.release();
+   if (e != cudaSuccess) { g_lastError = cudaGetErrorString(e); cudaGetLastError(); return HFB_ECUDA; }
    return HFB_OK;
 }
 

@@ -52,6 +52,7 @@ class ForwardBackward:
         self.h = h
         self.layout = fm.layout
         self._inflight = []
+        self.qualifiers = None
 
     def close(self):
         if getattr(self, "h", None):
@@ -154,6 +155,29 @@ class ForwardBackward:
         info = dict(nFloorVar=r.nFloorVar, nFloorVarMix=r.nFloorVarMix, nCopied=r.nCopied, nNoOcc=r.nNoOcc,
                     var=var, mixWeight=w, transP=tp)
         return new, info
+
+    # -- parameter-kind qualifiers on the device (HParm.c AddQualifiers) ----------------------
+    def SetQualifiers(self, q=None):
+        """q: flat.Qualifiers or None.  Afterwards every Batch holds static coefficients only
+        (q.num_static columns); deltas / accelerations / thirds and _Z are formed on the device."""
+        cs = q.c_struct() if q is not None else None
+        rc = self.lib.hfbgpu_set_qualifiers(self.h, C.byref(cs) if cs is not None else None)
+        if rc != 0:
+            raise capi.HfbError(rc, "hfbgpu_set_qualifiers")
+        self.qualifiers = q
+
+    def ExpandFeatures(self, feats) -> list:
+        """The expansion alone (what HCopy with that TARGETKIND writes): list of [T][num_static] -> list of [T][D]."""
+        ns, D = self.qualifiers.num_static, self.fm.D
+        T = np.array([f.shape[0] for f in feats], dtype=np.int64)
+        off = np.concatenate([[0], np.cumsum(T)]).astype(np.int64)
+        src = np.ascontiguousarray(np.concatenate(feats, axis=0), dtype=np.float32)
+        assert src.shape[1] == ns
+        dst = np.zeros((int(off[-1]), D), np.float32)
+        rc = self.lib.hfbgpu_expand_features(self.h, src.ctypes.data, off.ctypes.data, len(feats), dst.ctypes.data)
+        if rc != 0:
+            raise capi.HfbError(rc, "hfbgpu_expand_features")
+        return [dst[off[i]:off[i + 1]] for i in range(len(feats))]
 
     def acc_device_ptr(self) -> int:
         return int(self.lib.hfbgpu_acc_device_ptr(self.h))

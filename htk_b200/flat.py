@@ -63,6 +63,45 @@ class hfb_mstep_result(C.Structure):
                 ("nCopied", C.c_int32), ("nNoOcc", C.c_int32)]
 
 
+class hfb_qualifiers(C.Structure):
+    _fields_ = [("numStatic", C.c_int32), ("delWin", C.c_int32), ("accWin", C.c_int32), ("thirdWin", C.c_int32),
+                ("simpleDiffs", C.c_int32), ("zeroMeanCols", C.c_int32)]
+
+
+class Qualifiers:
+    """What HParm's configuration says about the step from the files' kind to the target kind
+    (TARGETKIND, DELTAWINDOW, ACCWINDOW, THIRDWINDOW, SIMPLEDIFFS; HParm.c:838-871)."""
+
+    def __init__(self, num_static: int, del_win: int = 0, acc_win: int = 0, third_win: int = 0,
+                 simple_diffs: bool = False, zero_mean_cols: int = 0):
+        self.num_static, self.del_win, self.acc_win, self.third_win = num_static, del_win, acc_win, third_win
+        self.simple_diffs, self.zero_mean_cols = bool(simple_diffs), zero_mean_cols
+
+    @classmethod
+    def from_kinds(cls, source_kind: str, target_kind: str, num_static: int, del_win: int = 2, acc_win: int = 2,
+                   third_win: int = 2, simple_diffs: bool = False) -> "Qualifiers":
+        """source_kind: kind of the files (e.g. "MFCC_0"), target_kind: TARGETKIND (e.g. "MFCC_0_D_A_Z");
+        num_static: width of the files' vectors."""
+        sq, tq = set(source_kind.split("_")[1:]), set(target_kind.split("_")[1:])
+        if source_kind.split("_")[0] != target_kind.split("_")[0] or (sq - {"K", "C"}) - tq or sq & {"D", "A", "T", "Z"}:
+            raise ValueError("cannot go from %s to %s on the device" % (source_kind, target_kind))
+        if (tq - sq) - {"D", "A", "T", "Z"}:
+            raise ValueError("only _D _A _T _Z can be added on the device (%s -> %s)" % (source_kind, target_kind))
+        zc = 0
+        if "Z" in tq:
+            zc = num_static - (1 if "E" in tq else 0)       # cepstra and c0, not the energy (HParm.c:1709-1712)
+        return cls(num_static, del_win if "D" in tq else 0, acc_win if "A" in tq else 0,
+                   third_win if "T" in tq else 0, simple_diffs, zc)
+
+    @property
+    def vec_size(self) -> int:
+        return self.num_static * (1 + (self.del_win > 0) + (self.acc_win > 0) + (self.third_win > 0))
+
+    def c_struct(self) -> "hfb_qualifiers":
+        return hfb_qualifiers(self.num_static, self.del_win, self.acc_win, self.third_win,
+                              1 if self.simple_diffs else 0, self.zero_mean_cols)
+
+
 class hfb_batch(C.Structure):
     _fields_ = [
         ("numUtt", C.c_int32),

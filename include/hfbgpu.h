@@ -195,6 +195,29 @@ int hfbgpu_submit(hfbgpu_ctx *ctx, const hfb_batch *batch, hfb_utt_result *res,
                   const hfb_beams *beams, int featOnDevice);
 int hfbgpu_wait(hfbgpu_ctx *ctx);
 
+/* ---- parameter-kind qualifiers on the device ---------------------------
+ * Replaces, for whole utterances, HParm.c:1618-1722 AddQualifiers -> :1552-1599 AddDiffs ->
+ * HSigP.c:827-857 Regress and HSigP.c:803-823 FZeroMean: what HERest's loader does when the files
+ * hold static coefficients (say MFCC_0) and the configuration asks for TARGETKIND = MFCC_0_D_A[_Z].
+ * After hfbgpu_set_qualifiers(ctx, &q) every feature matrix passed to hfbgpu_accumulate /
+ * _device / hfbgpu_submit has numStatic columns; the library forms the differentials (bit-identical
+ * to the reference: same FP32 operations in the same order) and the cepstral mean normalisation
+ * on the device before the output probabilities.  numStatic * (1 + orders) must equal vecSize.
+ * hfbgpu_set_qualifiers(ctx, NULL) switches back to full-width matrices.
+ * Not expressible (use HParm): _N, _V, global mean / variance files, input transforms, V1COMPAT. */
+typedef struct hfb_qualifiers {
+   int32_t numStatic;      /* static columns: cepstra, then c0 (_0) and / or energy (_E)  (FindSpans, HParm.c:1430) */
+   int32_t delWin;         /* DELTAWINDOW (HParm.c:838), 0 = no _D                              */
+   int32_t accWin;         /* ACCWINDOW   (:839),        0 = no _A                              */
+   int32_t thirdWin;       /* THIRDWINDOW (:871),        0 = no _T                              */
+   int32_t simpleDiffs;    /* SIMPLEDIFFS (:840)                                                */
+   int32_t zeroMeanCols;   /* _Z: leading columns to zero-mean per utterance = cepstra (+1 with _0), HParm.c:1709-1712; 0 = no _Z */
+} hfb_qualifiers;
+int hfbgpu_set_qualifiers(hfbgpu_ctx *ctx, const hfb_qualifiers *q);
+/* The expansion alone (what HCopy with that TARGETKIND writes): src = [frames][numStatic] host
+ * floats, frameOff[numUtt + 1] as in hfb_batch, dst = [frames][vecSize] host floats.          */
+int hfbgpu_expand_features(hfbgpu_ctx *ctx, const float *src, const int64_t *frameOff, int32_t numUtt, float *dst);
+
 /* Pinned (page-locked) host memory for the feature matrix of a batch: uploads from it are
  * asynchronous DMAs that overlap the kernels of the previous batch.  Replaces nothing in the
  * reference (its observations live in HTK's ParmBuf, HParm.c); the bridge copies frames out of

@@ -1,0 +1,50 @@
+"""CPU restatement of HParm's qualifier expansion for whole utterances -- TEST INFRASTRUCTURE ONLY
+(only tests/ may import this; the product path is htk_b200/csrc/hfb_feat.cuh).
+
+Follows HTKLib/HParm.c:1618-1722 (AddQualifiers), :1552-1599 (AddDiffs, tables: hdValid = tlValid = 0,
+not V1COMPAT), HTKLib/HSigP.c:827-857 (Regress) and HSigP.c:803-823 (FZeroMean), in float32 with the reference's
+order of operations.  Pinned: bit-identical to the unmodified reference's HCopy (oracle/_ref/bin/HCopy) on
+tests/golden/qualifiers_*.npz (tests/golden/make_qualifier_golden.py; tests/test_oracle_golden.py).
+"""
+import numpy as np
+
+F = np.float32
+
+
+def regress(src: np.ndarray, win: int, simple: bool) -> np.ndarray:
+    """HSigP.c:827-857 with head = tail = 0 blocks joined: first / last row replicated."""
+    T = src.shape[0]
+    idx = np.arange(T)
+    sigma = F(0)
+    for th in range(1, win + 1):
+        sigma = F(sigma + F(th * th))                     # :835-836
+    sigma = F(sigma * F(2))                               # :837
+    acc = np.zeros_like(src, dtype=F)
+    fw = bk = src
+    for th in range(1, win + 1):
+        fw = src[np.minimum(idx + th, T - 1)]             # :844-845: the pointers stop at the ends
+        bk = src[np.maximum(idx - th, 0)]
+        if not simple:
+            acc = (acc + (F(th) * (fw - bk).astype(F)).astype(F)).astype(F)   # :846
+    if simple:
+        return ((fw - bk).astype(F) / F(2 * win)).astype(F)                   # :849
+    return (acc / sigma).astype(F)                                            # :851
+
+
+def expand(static: np.ndarray, del_win=0, acc_win=0, third_win=0, simple=False, zero_mean_cols=0) -> np.ndarray:
+    """AddQualifiers: deltas over all static columns, accelerations over the deltas, thirds over the
+    accelerations (HParm.c:1664-1697), then FZeroMean over the leading columns (:1707-1722)."""
+    x = np.ascontiguousarray(static, dtype=F)
+    cols = [x]
+    for w in (del_win, acc_win, third_win):
+        if w <= 0:
+            break
+        cols.append(regress(cols[-1], w, simple))
+    out = np.concatenate(cols, axis=1)
+    for c in range(zero_mean_cols):
+        s = 0.0
+        for v in out[:, c]:                               # HSigP.c:811-815: double sum, in order
+            s += float(v)
+        mean = F(s / float(out.shape[0]))
+        out[:, c] = (out[:, c] - mean).astype(F)
+    return out

@@ -68,3 +68,21 @@ def have_gpu():
         return capi.load().hfbgpu_device_count() > 0
     except Exception:
         return False
+
+
+QUALIFIER_CASES = ["qualifiers_0_D_A", "qualifiers_0_D_A_Z", "qualifiers_E_D_A_Z_w3", "qualifiers_0_D_A_T",
+                   "qualifiers_D_simple", "qualifiers_Z_only"]
+
+
+def load_qualifier_golden(name):
+    """-> (Qualifiers, [static per utterance], [expanded per utterance as written by the reference's HCopy])"""
+    from htk_b200.flat import Qualifiers
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    cfg = dict(l.split(" = ") for l in z["config"].tolist())
+    ns = z["static"].shape[1]
+    q = Qualifiers.from_kinds(str(z["src_kind"]), str(z["tgt_kind"]), ns, int(cfg.get("DELTAWINDOW", 2)),
+                              int(cfg.get("ACCWINDOW", 2)), int(cfg.get("THIRDWINDOW", 2)),
+                              cfg.get("SIMPLEDIFFS", "F") == "T")
+    off = np.concatenate([[0], np.cumsum(z["lengths"])])
+    n = len(z["lengths"])
+    return (q, [z["static"][off[i]:off[i + 1]] for i in range(n)], [z["expanded"][off[i]:off[i + 1]] for i in range(n)])

@@ -12,7 +12,7 @@ Tolerances (BASELINE.json north_star): log-likelihoods, occupancies and accumula
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, acc_errors, load_golden
+from conftest import GOLDEN_CASES, QUALIFIER_CASES, acc_errors, load_golden, load_qualifier_golden
 from htk_b200.flat import Batch, make_options
 
 pytestmark = pytest.mark.gpu
@@ -410,3 +410,79 @@ def test_submit_wait_equals_blocking_call():
     assert max(e.values()) < 1e-5, e
     assert tickets[1].beams.qHi.max() > 0
     fb.close()
+
+
+# ---- parameter-kind qualifiers on the device ---------------------------------------------------
+
+def _model_of_width(D, M=2):
+    from htk_b200 import synth
+    from htk_b200.flat import flatten
+    return flatten(synth.make_monophone_set(n_phones=6, M=M, D=D, seed=5, spread=0.3))
+
+
+@pytest.mark.parametrize("name", QUALIFIER_CASES)
+def test_qualifier_expansion_bit_identical_to_hcopy(name):
+    """feat_regress_kernel / feat_zeromean_kernel against the files the unmodified reference's HCopy wrote
+    (tests/golden/make_qualifier_golden.py): every float identical, utterances of 1..333 frames."""
+    q, static, expanded = load_qualifier_golden(name)
+    fb = _fb(_model_of_width(q.vec_size))
+    fb.SetQualifiers(q)
+    out = fb.ExpandFeatures(static)
+    fb.close()
+    for o, y in zip(out, expanded):
+        assert o.shape == y.shape
+        assert np.array_equal(o.view(np.uint32), y.view(np.uint32))
+
+
+def test_qualifier_description_is_checked():
+    from htk_b200 import capi
+    from htk_b200.flat import Qualifiers
+    fb = _fb(_model_of_width(39))
+    for bad in (Qualifiers(13, 2, 0, 0), Qualifiers(13, 0, 2, 0), Qualifiers(13, 2, 2, 0, zero_mean_cols=14),
+                Qualifiers(12, 2, 2, 0)):
+        with pytest.raises(capi.HfbError):
+            fb.SetQualifiers(bad)
+    fb.SetQualifiers(Qualifiers(13, 2, 2, 0, zero_mean_cols=13))
+    fb.SetQualifiers(None)
+    fb.close()
+
+
+@pytest.mark.parametrize("device_feat", [False, True])
+def test_estep_on_static_features_equals_estep_on_expanded_features(device_feat):
+    """With hfbgpu_set_qualifiers the batch holds 13 static columns; accumulators, log-likelihoods and beams must
+    equal those of the same utterances expanded beforehand (oracle/hparm_oracle.py, pinned to HCopy), through the
+    host-feature and the device-feature entry, and agree with the C oracle on the expanded features."""
+    import torch
+    from htk_b200 import synth
+    from htk_b200.flat import Qualifiers, flatten
+    from oracle import hparm_oracle as H
+    hs = synth.make_tied_triphone_set(n_states=40, M=4, n_phys=30, n_logical=30, n_centre=5, D=39, seed=12, spread=0.25)
+    fm = flatten(hs)
+    feats, labs = synth.sample_corpus(fm, n_utts=7, T=180, Q=14, seed=21, T_jitter=30)
+    q = Qualifiers.from_kinds("MFCC_0", "MFCC_0_D_A_Z", 13)
+    static = [np.ascontiguousarray(f[:, :13]) for f in feats]
+    full = [H.expand(x, q.del_win, q.acc_win, q.third_win, q.simple_diffs, q.zero_mean_cols) for x in static]
+    kw = dict(prune=None)
+    b_full, b_static = Batch(full, labs, 39), Batch(static, labs, 13)
+    fb = _fb(fm, **kw)
+    res0, beams0 = fb.FBFile(b_full, want_beams=True); a0 = fb.GetAccs()
+    fb.ZeroAccs(); fb.SetQualifiers(q)
+    if device_feat:
+        d = torch.from_numpy(b_static.feat).cuda()
+        res1, beams1 = fb.FBFile(b_static, want_beams=True, device_feat_ptr=d.data_ptr())
+    else:
+        res1, beams1 = fb.FBFile(b_static, want_beams=True)
+    a1 = fb.GetAccs()
+    st = fb.stats()
+    fb.close()
+    assert [r.status for r in res0] == [r.status for r in res1] and any(r.status == 0 for r in res0)
+    for x, y in zip(res0, res1):
+        if x.status == 0:
+            assert abs(x.pr - y.pr) <= 1e-9 * abs(x.pr)
+    for k in ("qLo", "qHi", "sq", "eq"):
+        assert np.array_equal(getattr(beams0, k), getattr(beams1, k)), k
+    e = acc_errors(a1, a0, fm)                 # identical features; atomic / FP32 fragment order only
+    assert max(e.values()) < 1e-5, e
+    ao = _oracle(fm, b_full, kw)[0]
+    e = acc_errors(a1, ao, fm)
+    assert max(e.values()) < RTOL, e

@@ -204,3 +204,47 @@ def test_device_mstep_matches_stock_herest(tmp_path, opts):
     fb = ForwardBackward(fmS); r0, _ = fb.FBFile(b); fb.close()
     fb = ForwardBackward(new); r1, _ = fb.FBFile(b); fb.close()
     assert sum(r.pr for r in r1) >= sum(r.pr for r in r0) - 1e-6 * abs(sum(r.pr for r in r0))
+
+
+def test_device_qualifiers_match_stock_herest_loader(tmp_path):
+    """files hold MFCC_0 (13 static coefficients), the configuration asks for
+    TARGETKIND = MFCC_0_D_A_Z.  The stock HERest expands in its loader (HParm.c AddQualifiers); the library gets
+    the 13-column matrices plus hfbgpu_set_qualifiers and expands on the device.  `-p 1` accumulators within 1e-4."""
+    if not os.path.exists(HEREST):
+        pytest.skip("reference binaries not built")
+    from htk_b200.estep import ForwardBackward
+    from htk_b200.flat import Batch, Qualifiers
+    tmp = str(tmp_path)
+    hs = synth.make_tied_triphone_set(n_states=40, M=3, n_phys=24, n_logical=30, n_centre=5, seed=43, spread=0.25,
+                                      parm_kind="MFCC_0_D_A_Z")
+    hs2, fm = _setup(tmp, hs, n_utts=8, T=240, Q=20, seed=11)
+    # overwrite the feature files with their 13 static columns, kind MFCC_0
+    scp = open(os.path.join(tmp, "scp")).read().split()
+    static = []
+    for f in scp:
+        x = htkio.read_htk_features(f)[0][:, :13].copy()
+        htkio.write_htk_features(f, x, "MFCC_0")
+        static.append(x)
+    open(os.path.join(tmp, "cfg"), "w").write("TARGETKIND = MFCC_0_D_A_Z\nDELTAWINDOW = 2\nACCWINDOW = 2\n")
+    os.makedirs(os.path.join(tmp, "accA"))
+    _run([HEREST, "-C", "cfg", "-T", "1", "-u", "tmvw", "-p", "1", "-H", "mmf", "-I", "labs.mlf", "-S", "scp",
+          "-M", "accA", "list"], tmp)
+    a, prA, tA = htkio.read_acc_dump(os.path.join(tmp, "accA", "HER1.acc"), hs2, fm)
+    import re
+    mlf = open(os.path.join(tmp, "labs.mlf")).read()
+    labs = []
+    for f in scp:
+        u = os.path.basename(f)[:-4]
+        block = re.search(r'"\*/%s\.lab"\n(.*?)\n\.\n' % u, mlf, re.S).group(1).split("\n")
+        labs.append(np.array([fm.hmm_index[l] for l in block], dtype=np.int32))
+    fb = ForwardBackward(fm)
+    fb.SetQualifiers(Qualifiers.from_kinds("MFCC_0", "MFCC_0_D_A_Z", 13))
+    res, _ = fb.FBFile(Batch(static, labs, 13))
+    b = fb.GetAccs()
+    fb.close()
+    assert all(r.status == 0 for r in res)
+    L = fm.layout
+    assert b[L.totalT] == tA and abs(b[L.totalPr] - prA) <= 1e-4 * abs(prA)
+    e = acc_errors(b, a, fm)
+    e.pop("totalPr"); e.pop("totalT")
+    assert max(e.values()) < 1e-4, e

@@ -4,7 +4,7 @@ with the same float/double choices, so the bar is bit-exact, beams included."""
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, acc_errors, load_golden
+from conftest import GOLDEN_CASES, QUALIFIER_CASES, acc_errors, load_golden, load_qualifier_golden
 from htk_b200.flat import make_options
 from oracle import oracle_lib as O
 
@@ -67,3 +67,15 @@ def test_min_durs():
     tee = fm.hmmTrans[names.index("sp")]
     assert md[tee] == 0
     assert all(md[i] >= 1 for i in range(fm.numTrans) if i != tee)
+
+
+@pytest.mark.parametrize("name", QUALIFIER_CASES)
+def test_qualifier_oracle_bit_identical_to_hcopy(name):
+    """oracle/hparm_oracle.py (HParm.c AddQualifiers / HSigP.c Regress, FZeroMean restated) against what the
+    unmodified reference's HCopy wrote for the target kind, utterances of 1..333 frames."""
+    from oracle import hparm_oracle as H
+    q, static, expanded = load_qualifier_golden(name)
+    for x, y in zip(static, expanded):
+        o = H.expand(x, q.del_win, q.acc_win, q.third_win, q.simple_diffs, q.zero_mean_cols)
+        assert o.shape == y.shape == (x.shape[0], q.vec_size)
+        assert np.array_equal(o.view(np.uint32), y.view(np.uint32))
