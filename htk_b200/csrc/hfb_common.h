@@ -80,6 +80,7 @@ struct Wave {                       // everything the kernels of one wave need
    int *posState;                   // tied state of each emitting position
    int *posQ;                       // model (label) index of each emitting position
    const float *feat;               // [frames][D]
+   const float *feat2;              // single-pass retraining (HERest -r): second parameterisation, or NULL
    float *b;
    double *beta;
    double *occ;

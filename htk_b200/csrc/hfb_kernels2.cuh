@@ -341,6 +341,8 @@ stats3_kernel(DevModel M, Wave W)
    const short *sqA = W.sq + u.frameBase, *eqA = W.eq + u.frameBase;
    const short *qLo = W.qLo + u.frameBase, *qHi = W.qHi + u.frameBase;
    const float *feat = W.feat + (size_t)u.featOff * D;
+   // HERest -r (HFB.c:1603-1611, :1731): posteriors from `feat`, mean / variance sums from the second data stream
+   const float *feat2 = W.feat2 ? W.feat2 + (size_t)u.featOff * D : nullptr;
    const double pr = W.out[ui].pr, minF = W.minFrwdP;
    const int uf = W.uFlags;
    const bool upM = (uf & HFB_UPMEANS) != 0, upV = (uf & HFB_UPVARS) != 0, upW = (uf & HFB_UPMIXES) != 0;
@@ -427,7 +429,12 @@ stats3_kernel(DevModel M, Wave W)
             float am0 = 0.f, am1 = 0.f, av0 = 0.f, av1 = 0.f, aocc = 0.f;
             for (int ti = 0; ti < nT; ti++) {
                const float Lr = lrs[mi * 33 + ti];
-               const float d0 = (k0 < D) ? os[ti * ostr + k0] - mu0 : 0.f, d1 = (k1 < D) ? os[ti * ostr + k1] - mu1 : 0.f;
+               float o0, o1;
+               if (feat2) {
+                  const float *r2 = feat2 + (size_t)ts[ti] * D;
+                  o0 = (k0 < D) ? r2[k0] : 0.f; o1 = (k1 < D) ? r2[k1] : 0.f;
+               } else { o0 = os[ti * ostr + k0]; o1 = os[ti * ostr + k1]; }
+               const float d0 = (k0 < D) ? o0 - mu0 : 0.f, d1 = (k1 < D) ? o1 - mu1 : 0.f;
                const float z0 = d0 * Lr, z1 = d1 * Lr;                       // zmeanlr, :1675
                aocc += Lr; am0 += z0; am1 += z1;
                av0 = fmaf(z0, d0, av0); av1 = fmaf(z1, d1, av1);

@@ -132,6 +132,7 @@ struct hfbgpu_ctx {
       bool hasX = false;
       DevBuf<float> dFeat;              // only for host-feature calls and for expanded features
       DevBuf<float> dFeatSrc;           // host static coefficients before the qualifier expansion
+      DevBuf<float> dFeat2;             // host second data stream (single-pass retraining)
       DevBuf<float> dB;
       DevBuf<double> dBeta, dOcc, dAent;
       DevBuf<short> dBeams;             // 4 * frames
@@ -446,7 +447,7 @@ extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
    for (auto &sl : c->slot) {
       if (sl.stream) cudaStreamSynchronize(sl.stream);
       sl.dFeat.release(); sl.dB.release(); sl.dBeta.release(); sl.dOcc.release(); sl.dAent.release(); sl.dBeams.release();
-      sl.dTables.release(); sl.dScratch.release(); sl.dStateIdx.release(); sl.dValid.release(); sl.dFeatSrc.release(); sl.tcw.release();
+      sl.dTables.release(); sl.dScratch.release(); sl.dStateIdx.release(); sl.dValid.release(); sl.dFeatSrc.release(); sl.dFeat2.release(); sl.tcw.release();
       if (sl.hTables) cudaFreeHost(sl.hTables);
       if (sl.hOut) cudaFreeHost(sl.hOut);
       if (sl.hBeams) cudaFreeHost(sl.hBeams);
@@ -601,7 +602,7 @@ struct ScratchLayout {
 // ------------------------------------------------------------------------------------------
 // one wave: launch (asynchronous) and finish (synchronise + hand results to the caller)
 // ------------------------------------------------------------------------------------------
-static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBase, const float *feat, bool featOnDevice,
+static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBase, const float *feat, const float *feat2, bool featOnDevice,
                        long long waveFrame0, long long waveFrames, bool wantBeams)
 {
    WaveTables &w = *S.w;
@@ -627,6 +628,17 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
    if (fq.enabled) {
       if ((rc = S.dFeat.reserve((size_t)waveFrames * D + 4))) return rc;
       dFeatSrc = dFeat; dFeat = S.dFeat.p;
+   }
+   const float *dFeat2 = nullptr;                     // second data stream: always full width
+   if (feat2) {
+      if (featOnDevice) dFeat2 = feat2 + (size_t)waveFrame0 * D;
+      else {
+         if ((rc = S.dFeat2.reserve((size_t)waveFrames * D + 4))) return rc;
+         CK(cudaMemcpyAsync(S.dFeat2.p, feat2 + (size_t)waveFrame0 * D, (size_t)waveFrames * D * sizeof(float),
+                            cudaMemcpyHostToDevice, st));
+         c->stats.h2dBytes += (int64_t)waveFrames * D * sizeof(float);
+         dFeat2 = S.dFeat2.p;
+      }
    }
    // ---- pack + upload the (small) host tables
    w.posPre.push_back((int)w.totalP);
@@ -664,7 +676,7 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
    W.mTrAcc = (long long *)(sc + sl.mTrAcc); W.mTrOcc = (long long *)(sc + sl.mTrOcc);
    W.mTmin = (int *)(sc + sl.mTmin); W.mTmax = (int *)(sc + sl.mTmax);
    W.slotState = (int *)(sc + sl.slotState); W.posSlot = (int *)(sc + sl.posSlot); W.posState = (int *)(sc + sl.posState); W.posQ = (int *)(sc + sl.posQ);
-   W.feat = dFeat;
+   W.feat = dFeat; W.feat2 = dFeat2;
    if (fq.enabled) {
       int nl = 0;
       feat_expand_launch(fq, W.utt, nU, w.maxT, dFeatSrc, S.dFeat.p, D, st, &nl);
@@ -765,7 +777,7 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
       if (w.totalP > 0 && c->opt.uFlags != 0) {
          const int Dd = c->dm.D;
          // mixture sets: occupancy-weighted sums on the tensor cores (mma.sync 3xTF32); else the FP32 kernel
-         if (c->hm.maxM >= 4 && Dd + 1 <= 40 && !getenv("HFBGPU_STATS3")) {
+         if (c->hm.maxM >= 4 && Dd + 1 <= 40 && !W.feat2 && !getenv("HFBGPU_STATS3")) {
             // positions bucketed by tied state (counting sort), then S5_CAP sorted positions per warp
             const int Jm = c->hm.J;
             const size_t nIdx = ((size_t)3 * (Jm + 2) + 3) & ~(size_t)3;
@@ -881,7 +893,7 @@ static int finish_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S)
 // waves to aim at (the blocking call splits a batch over the streams; the asynchronous one keeps
 // a batch in one wave so that consecutive calls overlap instead).
 static int submit_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, const hfb_beams *beams,
-                       bool featOnDevice, int splitWaves)
+                       bool featOnDevice, int splitWaves, const float *feat2 = nullptr)
 {
    if (!c || !b || !res) return HFB_EINVAL;
    if (b->numUtt < 0 || (b->numUtt > 0 && (!b->frameOff || !b->feat || !b->labOff || !b->lab))) return HFB_EINVAL;
@@ -927,7 +939,7 @@ static int submit_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, c
       const long long waveFrames = b->frameOff[u1] - waveFrame0;
       S.res = res;
       if (wantBeams) S.beams = *beams; else memset(&S.beams, 0, sizeof(S.beams));
-      rc = launch_wave(c, S, b->lab + w.lab0, b->feat, featOnDevice, waveFrame0, waveFrames, wantBeams);
+      rc = launch_wave(c, S, b->lab + w.lab0, b->feat, feat2, featOnDevice, waveFrame0, waveFrames, wantBeams);
       if (rc) { rcAll = rc; break; }
       u0 = u1; c->nextSlot++;
       if (c->timing) { rc = finish_wave(c, S); if (rc) { rcAll = rc; break; } }
@@ -957,6 +969,16 @@ extern "C" int hfbgpu_accumulate(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_resu
 extern "C" int hfbgpu_accumulate_device(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, const hfb_beams *beams)
 {
    int rc = submit_impl(c, b, res, beams, true, hfbgpu_ctx::NSLOT);
+   int rc2 = wait_impl(c);
+   return rc ? rc : rc2;
+}
+
+// HERest -r: state / component occupancies from batch->feat, mean and variance statistics from feat2
+extern "C" int hfbgpu_accumulate_retrain(hfbgpu_ctx *c, const hfb_batch *b, const float *feat2, hfb_utt_result *res,
+                                         const hfb_beams *beams, int featOnDevice)
+{
+   if (!feat2) return HFB_EINVAL;
+   int rc = submit_impl(c, b, res, beams, featOnDevice != 0, hfbgpu_ctx::NSLOT, feat2);
    int rc2 = wait_impl(c);
    return rc ? rc : rc2;
 }

@@ -80,6 +80,21 @@ class ForwardBackward:
             raise capi.HfbError(rc, "hfbgpu_accumulate")
         return [UttResult((r.status, r.retries, r.pr, r.pruneThresh)) for r in res[:batch.numUtt]], beams
 
+    def FBFileRetrain(self, batch: Batch, feat2: np.ndarray, want_beams: bool = False):
+        """HERest -r (single-pass retraining): alignment on batch.feat, mean / variance statistics on feat2
+        ([totalT][D], the second parameterisation of the same frames)."""
+        feat2 = np.ascontiguousarray(feat2, dtype=np.float32)
+        assert feat2.shape == (batch.totalT, self.fm.D)
+        res = (hfb_utt_result * max(1, batch.numUtt))()
+        beams = Beams(batch.totalT) if want_beams else None
+        bs = beams.c_struct() if beams is not None else None
+        b = batch.c_struct()
+        rc = self.lib.hfbgpu_accumulate_retrain(self.h, C.byref(b), feat2.ctypes.data, res,
+                                                C.byref(bs) if bs is not None else None, 0)
+        if rc != 0:
+            raise capi.HfbError(rc, "hfbgpu_accumulate_retrain")
+        return [UttResult((r.status, r.retries, r.pr, r.pruneThresh)) for r in res[:batch.numUtt]], beams
+
     # -- asynchronous form: consecutive batches overlap on the library's two streams --------
     def Submit(self, batch: Batch, device_feat_ptr: Optional[int] = None, want_beams: bool = False):
         """Enqueue a batch; returns a ticket whose .results() is valid after Wait()."""

@@ -195,6 +195,15 @@ int hfbgpu_submit(hfbgpu_ctx *ctx, const hfb_batch *batch, hfb_utt_result *res,
                   const hfb_beams *beams, int featOnDevice);
 int hfbgpu_wait(hfbgpu_ctx *ctx);
 
+/* Single-pass retraining, HERest -r (HERest.c:369, :505-511; HFB.c:1603-1611, :1731): every utterance comes as
+ * two parameterisations of the same frames.  Alignment (output probabilities, alpha / beta, beams, state and
+ * component occupancies, transition and weight counts) uses batch->feat exactly as hfbgpu_accumulate does; the mean
+ * and variance sums take their observations from feat2 = [totalT][vecSize], same frame offsets, centred on the
+ * current means as the reference does.  feat2 lives where feat lives (featOnDevice); with qualifiers set, feat is
+ * static-only and feat2 is still full width.                                                                      */
+int hfbgpu_accumulate_retrain(hfbgpu_ctx *ctx, const hfb_batch *batch, const float *feat2, hfb_utt_result *res,
+                              const hfb_beams *beams, int featOnDevice);
+
 /* ---- parameter-kind qualifiers on the device ---------------------------
  * Replaces, for whole utterances, HParm.c:1618-1722 AddQualifiers -> :1552-1599 AddDiffs ->
  * HSigP.c:827-857 Regress and HSigP.c:803-823 FZeroMean: what HERest's loader does when the files

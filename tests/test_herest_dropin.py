@@ -248,3 +248,53 @@ def test_device_qualifiers_match_stock_herest_loader(tmp_path):
     e = acc_errors(b, a, fm)
     e.pop("totalPr"); e.pop("totalT")
     assert max(e.values()) < 1e-4, e
+
+
+def test_single_pass_retraining_matches_stock_herest(tmp_path):
+    """SURVEY 8(f).4, HERest -r: paired training files.  Alignment on the first file of each pair, mean / variance
+    sums from the second (HFB.c:1603-1611); hfbgpu_accumulate_retrain against the stock tool's `-p 1` dump."""
+    if not os.path.exists(HEREST):
+        pytest.skip("reference binaries not built")
+    from htk_b200.estep import ForwardBackward
+    from htk_b200.flat import Batch
+    tmp = str(tmp_path)
+    hs = synth.make_tied_triphone_set(n_states=40, M=3, n_phys=24, n_logical=30, n_centre=5, seed=47, spread=0.25)
+    hs2, fm = _setup(tmp, hs, n_utts=8, T=220, Q=18, seed=13)
+    scp = open(os.path.join(tmp, "scp")).read().split()
+    rng = np.random.default_rng(5)
+    feats, feats2, pairs = [], [], []
+    for f in scp:
+        x = htkio.read_htk_features(f)[0]
+        y = (x * 1.5 + 0.3 + 0.1 * rng.standard_normal(x.shape)).astype(np.float32)    # "new parameterisation"
+        f2 = f[:-4] + "_b.mfc"
+        htkio.write_htk_features(f2, y, hs.parm_kind)
+        feats.append(x); feats2.append(y); pairs.append(f + " " + f2)
+    open(os.path.join(tmp, "scp2"), "w").write("\n".join(pairs) + "\n")
+    os.makedirs(os.path.join(tmp, "accA"))
+    _run([HEREST, "-r", "-T", "1", "-u", "tmvw", "-p", "1", "-H", "mmf", "-I", "labs.mlf", "-S", "scp2",
+          "-M", "accA", "list"], tmp)
+    a, prA, tA = htkio.read_acc_dump(os.path.join(tmp, "accA", "HER1.acc"), hs2, fm)
+    import re
+    mlf = open(os.path.join(tmp, "labs.mlf")).read()
+    labs = []
+    for f in scp:
+        u = os.path.basename(f)[:-4]
+        block = re.search(r'"\*/%s\.lab"\n(.*?)\n\.\n' % u, mlf, re.S).group(1).split("\n")
+        labs.append(np.array([fm.hmm_index[l] for l in block], dtype=np.int32))
+    fb = ForwardBackward(fm)
+    res, _ = fb.FBFileRetrain(Batch(feats, labs, fm.D), np.concatenate(feats2))
+    b = fb.GetAccs()
+    # and the plain pass on the first files alone differs in the mean / variance sums only
+    fb.ZeroAccs()
+    fb.FBFile(Batch(feats, labs, fm.D))
+    c = fb.GetAccs()
+    fb.close()
+    assert all(r.status == 0 for r in res)
+    L = fm.layout
+    assert b[L.totalT] == tA and abs(b[L.totalPr] - prA) <= 1e-4 * abs(prA)
+    e = acc_errors(b, a, fm)
+    e.pop("totalPr"); e.pop("totalT")
+    assert max(e.values()) < 1e-4, e
+    e = acc_errors(c, b, fm)
+    assert max(e[k] for k in ("tran", "tranOcc", "wtC", "wtOcc", "muOcc", "vaOcc")) < 1e-5, e
+    assert e["muSum"] > 1e-2 and e["vaSum"] > 1e-2, e
