@@ -399,6 +399,7 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
             const int nT8 = (nT + 7) & ~7;
             for (int e = lane; e < 16 * S4_LSTR; e += 32) lrs[e] = 0.f;
             __syncwarp();
+            // (4-byte cp.async straight into the tile, all rows in flight, no register staging: measured 4 % SLOWER)
             for (int tb = 0; tb < nT8; tb += 8) {                  // observation rows, 8 at a time (16 loads in flight per
                float v0[8], v1[8];                                 // lane); rows nT..nT8-1 are zero padding
 #pragma unroll
