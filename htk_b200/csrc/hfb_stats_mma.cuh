@@ -102,9 +102,22 @@ __global__ void __launch_bounds__(128) statpos_scatter_kernel(Wave W, const int 
    if (W.out[blockIdx.x].status != 0) return;
    const int *posState = W.posState + u.posOff, *posQ = W.posQ + u.posOff;
    const int *tmin = W.mTmin + u.modOff, *tmax = W.mTmax + u.modOff;
-   for (int pp = threadIdx.x; pp < u.P; pp += blockDim.x) {
-      const int q = posQ[pp], gq = u.modOff + q;
-      if (tmin[q] <= tmax[q]) {
+   const int lane = threadIdx.x & 31;
+   for (int base = 0; base < u.P; base += blockDim.x) {
+      const int pp = base + threadIdx.x;
+      const bool in = pp < u.P;
+      const int q = in ? posQ[pp] : 0, gq = u.modOff + q;
+      const bool on = in && tmin[q] <= tmax[q];
+      // room for one list entry per frame of the model's alpha-beam span: one atomic per warp on the cursor
+      // (one per position serialised 300 k atomics on a single address: 0.2 ms)
+      const long long span = on ? (long long)tmax[q] - tmin[q] + 1 : 0;
+      long long incl = span;
+      for (int o = 1; o < 32; o <<= 1) { const long long v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      const long long tot = __shfl_sync(0xffffffffu, incl, 31);
+      long long wbase = 0;
+      if (lane == 0 && tot > 0 && vCap > 0) wbase = (long long)atomicAdd(vCursor, (unsigned long long)tot);
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (on) {
          const int s = posState[pp];
          PosRec r;
          r.s = s; r.q = q; r.j = pp - W.mPoff[gq]; r.tmin = tmin[q]; r.tmax = tmax[q];
@@ -113,18 +126,15 @@ __global__ void __launch_bounds__(128) statpos_scatter_kernel(Wave W, const int 
          r.alphaOff = u.occOff + pp; r.aentOff = u.aentOff + q; r.betaOff = u.betaOff; r.bOff = u.bOff;
          r.frameBase = u.frameBase; r.featOff = u.featOff; r.trAcc = W.mTrAcc[gq]; r.trOcc = W.mTrOcc[gq];
          r.pr = W.out[blockIdx.x].pr;
-         {  // room for one entry per frame of the model's alpha-beam span; positions that do not fit keep the inline path
-            const long long span = (long long)r.tmax - r.tmin + 1;
-            const long long o = vCap > 0 ? (long long)atomicAdd(vCursor, (unsigned long long)span) : vCap;
-            r.vOff = (o + span <= vCap) ? o : -1;
-         }
+         const long long o = wbase + incl - span;
+         r.vOff = (vCap > 0 && o + span <= vCap) ? o : -1;    // positions that do not fit keep the inline front
          const int *ps = W.posSlot + u.posOff + W.mPoff[gq];
 #pragma unroll
          for (int i = 0; i < HFB_MAXN; i++) r.ps[i] = (i < r.N - 2) ? ps[i] : 0;
          const int at = off[s] + atomicAdd(&fill[s], 1);
          list[at] = r;
          posIdx[u.posOff + pp] = at;
-      } else
+      } else if (in)
          posIdx[u.posOff + pp] = -1;
    }
 }
