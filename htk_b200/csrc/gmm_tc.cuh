@@ -728,17 +728,13 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                constexpr int G = (MP < 32) ? MP : 32;   // columns of one state inside this chunk
 #pragma unroll
                for (int s0 = 0; s0 < 32; s0 += G) {
-                  // short dependency chains (two warps per scheduler cannot hide 16-deep ones): tree maximum,
-                  // four partial sums
-                  float m4[4] = {v[s0], v[s0 + 1], v[s0 + 2], v[s0 + 3]};
+                  float mx = v[s0];
 #pragma unroll
-                  for (int i = 4; i < G; i++) m4[i & 3] = fmaxf(m4[i & 3], v[s0 + i]);
-                  float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                  for (int i = 1; i < G; i++) mx = fmaxf(mx, v[s0 + i]);
+                  float sum = 0.f;
                   const float mb = mx * LOG2E;
-                  float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                  for (int i = 0; i < G; i++) s4[i & 3] += tc_ex2(fmaf(v[s0 + i], LOG2E, -mb));
-                  float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                  for (int i = 0; i < G; i++) sum += tc_ex2(fmaf(v[s0 + i], LOG2E, -mb));
                   if (MP > 32) {                        // merge into the carry
                      float nm = fmaxf(cmx, mx);
                      csum = csum * tc_ex2((cmx - nm) * LOG2E) + sum * tc_ex2((mx - nm) * LOG2E);
