@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(64 * 8)
 gmm_tc_expand_f16_kernel(const float *__restrict__ feat, const float *__restrict__ off, const float *__restrict__ scale,
                          int D, long long nFrames, __half *__restrict__ Ahi, __half *__restrict__ Alo)
 {
-   const int d = threadIdx.x;
-   const long long f = (long long)blockIdx.x * 8 + threadIdx.y;
+   const int d = threadIdx.x;                           // blockDim.x = D rounded up to 8 (few idle lanes), blockDim.y rows
+   const long long f = (long long)blockIdx.x * blockDim.y + threadIdx.y;
    if (d >= D || f >= nFrames) return;
    const float x = (feat[f * D + d] - off[d]) * scale[d];
    // outliers beyond 255 sigma saturate instead of becoming inf
@@ -1023,7 +1023,10 @@ static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm
          gmm_tc_init_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dm.D, (long long)wk.aCapFrames, ahi, alo);
          wk.f16Init = true;
       }
-      gmm_tc_expand_f16_kernel<<<(unsigned)((waveFrames + 7) / 8), dim3(64, 8), 0, st>>>(W.feat, t.dOffset, t.dScale, dm.D, waveFrames, ahi, alo);
+      {
+         const int bx = (dm.D + 7) & ~7, by = std::max(1, 512 / bx);
+         gmm_tc_expand_f16_kernel<<<(unsigned)((waveFrames + by - 1) / by), dim3(bx, by), 0, st>>>(W.feat, t.dOffset, t.dScale, dm.D, waveFrames, ahi, alo);
+      }
       if (afterExpand) cudaEventRecord(afterExpand, st);
       p.items = dItems4; p.nItems = nItems4;            // work items of 4 x 128 frames: two blocks per CTA
       p.C0 = t.C0H - t.C1H;                              // the epilogue subtracts C0 and adds the common constant C1 back
