@@ -203,20 +203,40 @@ gmm_tc_init_f16_kernel(int D, long long nRows, __half *__restrict__ Ahi, __half 
    Alo[idx] = __float2half_rn(0.f);
 }
 
-__global__ void __launch_bounds__(64 * 8)
+// 32 frames per block: coalesced feature reads, the split rows assembled in shared memory, then 16-byte stores of
+// the used part of every row ([1 | x'^2 | x' | 1 | 0..] hi and lo; the columns past it stay as gmm_tc_init_f16_kernel
+// left them)
+#define TC_XF_FR 32
+__global__ void __launch_bounds__(256)
 gmm_tc_expand_f16_kernel(const float *__restrict__ feat, const float *__restrict__ off, const float *__restrict__ scale,
                          int D, long long nFrames, __half *__restrict__ Ahi, __half *__restrict__ Alo)
 {
-   const int d = threadIdx.x;                           // blockDim.x = D rounded up to 8 (few idle lanes), blockDim.y rows
-   const long long f = (long long)blockIdx.x * blockDim.y + threadIdx.y;
-   if (d >= D || f >= nFrames) return;
-   const float x = (feat[f * D + d] - off[d]) * scale[d];
-   // outliers beyond 255 sigma saturate instead of becoming inf
-   const float v1 = fminf(fmaxf(x, -65000.f), 65000.f), v2 = fminf(x * x, 65000.f);
-   const __half h1 = __float2half_rn(v1), h2 = __float2half_rn(v2);
-   __half *hi = Ahi + f * TC_KH, *lo = Alo + f * TC_KH;
-   hi[1 + d] = h2;     lo[1 + d] = __float2half_rn(v2 - __half2float(h2));
-   hi[1 + D + d] = h1; lo[1 + D + d] = __float2half_rn(v1 - __half2float(h1));
+   __shared__ __align__(16) __half sh[2][TC_XF_FR][TC_KH];
+   const long long f0 = (long long)blockIdx.x * TC_XF_FR;
+   const int nf = (int)((nFrames - f0 < TC_XF_FR) ? nFrames - f0 : TC_XF_FR);
+   const int nk8 = (2 * D + 2 + 7) >> 3, kUsed = nk8 * 8, nConst = kUsed - 2 * D;   // k = 0 and k = 2D+1 .. kUsed-1
+   for (int e = threadIdx.x; e < nf * nConst; e += 256) {
+      const int fr = e / nConst, c = e - fr * nConst, k = (c == 0) ? 0 : 2 * D + c;
+      sh[0][fr][k] = __float2half_rn((k == 0 || k == 2 * D + 1) ? 1.f : 0.f);
+      sh[1][fr][k] = __float2half_rn(0.f);
+   }
+   const float *src = feat + f0 * D;
+   for (int e = threadIdx.x; e < nf * D; e += 256) {
+      const int fr = e / D, d = e - fr * D;
+      const float x = (src[e] - off[d]) * scale[d];
+      // outliers beyond 255 sigma saturate instead of becoming inf
+      const float v1 = fminf(fmaxf(x, -65000.f), 65000.f), v2 = fminf(x * x, 65000.f);
+      const __half h1 = __float2half_rn(v1), h2 = __float2half_rn(v2);
+      sh[0][fr][1 + d] = h2;     sh[1][fr][1 + d] = __float2half_rn(v2 - __half2float(h2));
+      sh[0][fr][1 + D + d] = h1; sh[1][fr][1 + D + d] = __float2half_rn(v1 - __half2float(h1));
+   }
+   __syncthreads();
+   const int per = nf * nk8;
+   for (int e = threadIdx.x; e < 2 * per; e += 256) {
+      const int arr = e >= per, r = e - arr * per, fr = r / nk8, c = r - fr * nk8;
+      __half *dst = (arr ? Alo : Ahi) + (f0 + fr) * TC_KH + c * 8;
+      *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(&sh[arr][fr][c * 8]);
+   }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1023,10 +1043,7 @@ static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm
          gmm_tc_init_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dm.D, (long long)wk.aCapFrames, ahi, alo);
          wk.f16Init = true;
       }
-      {
-         const int bx = (dm.D + 7) & ~7, by = std::max(1, 512 / bx);
-         gmm_tc_expand_f16_kernel<<<(unsigned)((waveFrames + by - 1) / by), dim3(bx, by), 0, st>>>(W.feat, t.dOffset, t.dScale, dm.D, waveFrames, ahi, alo);
-      }
+      gmm_tc_expand_f16_kernel<<<(unsigned)((waveFrames + TC_XF_FR - 1) / TC_XF_FR), 256, 0, st>>>(W.feat, t.dOffset, t.dScale, dm.D, waveFrames, ahi, alo);
       if (afterExpand) cudaEventRecord(afterExpand, st);
       p.items = dItems4; p.nItems = nItems4;            // work items of 4 x 128 frames: two blocks per CTA
       p.C0 = t.C0H - t.C1H;                              // the epilogue subtracts C0 and adds the common constant C1 back
