@@ -43,6 +43,30 @@ __device__ __forceinline__ float lg2_approx(float x)
    return r;
 }
 
+// Conversions between FP64 and FP32 execute on the XU pipe, next to ex2 / lg2 and at a quarter of their rate, and
+// that pipe is what bounds the recursion kernels (ncu on beta_l2r_kernel: sm__inst_executed_pipe_xu 150 % of its
+// sustained peak with 4 conversions + 2 MUFU per log-add).  The two conversions of a log-add are therefore done with
+// integer operations on the ALU pipe: both are exact replacements of cvt.rn for the values that occur here.
+//   f2d_alu:      float -> double for zero and normal floats (log values, the bounded correction; no denormal, inf
+//                 or NaN reaches it): re-bias the exponent, shift the mantissa.
+//   neg_abs_d2f:  -|v| as a float, round to nearest even; |v| below 2^-126 gives -0 (the ex2 that follows flushes
+//                 denormals anyway), |v| is far below 2^128 (log zero is -1e10).
+__device__ __forceinline__ double f2d_alu(float f)
+{
+   const unsigned b = __float_as_uint(f), mag = b & 0x7fffffffu;
+   const unsigned hi = (b & 0x80000000u) | (mag ? (mag >> 3) + 0x38000000u : 0u);
+   return __hiloint2double((int)hi, (int)(b << 29));
+}
+__device__ __forceinline__ float neg_abs_d2f(double v)
+{
+   const unsigned hi = (unsigned)__double2hiint(v) & 0x7fffffffu, lo = (unsigned)__double2loint(v);
+   unsigned r = ((hi - 0x38000000u) << 3) | (lo >> 29);
+   const unsigned rem = lo & 0x1fffffffu;
+   r += (rem > 0x10000000u || (rem == 0x10000000u && (r & 1u))) ? 1u : 0u;
+   r = (hi < 0x38100000u) ? 0u : r;
+   return __uint_as_float(r | 0x80000000u);
+}
+
 template <bool EXACT>
 __device__ __forceinline__ double ladd(double x, double y)
 {
@@ -53,15 +77,27 @@ __device__ __forceinline__ double ladd(double x, double y)
       return x + log(1.0 + exp(d));
    }
    const double hi = (x > y) ? x : y;
-   const float d = -fabsf((float)(x - y));
+   const float d = neg_abs_d2f(x - y);
    float c = lg2_approx(1.0f + ex2_approx(d * 1.4426950408889634f)) * 0.6931471805599453f;
    c = (d < (float)MINLOGEXP) ? 0.f : c;
-   return (hi < LSMALL_D) ? LZERO_D : hi + (double)c;
+   return (hi < LSMALL_D) ? LZERO_D : hi + f2d_alu(c);
 }
 
 // The same for callers that have already checked one operand against LSMALL (every guarded
 // `if (term > LSMALL) x = LAdd(x, term)` of HFB.c): the result cannot be log zero.
 __device__ __forceinline__ double ladd_nz(double x, double y)
+{
+   const double hi = (x > y) ? x : y;
+   const float d = neg_abs_d2f(x - y);
+   float c = lg2_approx(1.0f + ex2_approx(d * 1.4426950408889634f)) * 0.6931471805599453f;
+   c = (d < (float)MINLOGEXP) ? 0.f : c;
+   return hi + f2d_alu(c);
+}
+
+// beta kernels (64 registers, one thread per model): the integer conversions cost more issue slots and registers
+// there than the XU conversions they save (measured: 1.81 -> 1.90 ms with both on the ALU, 1.95 ms with only the
+// float -> double one), so they keep cvt
+__device__ __forceinline__ double ladd_nz_b(double x, double y)
 {
    const double hi = (x > y) ? x : y;
    const float d = -fabsf((float)(x - y));

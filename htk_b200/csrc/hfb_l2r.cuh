@@ -121,9 +121,9 @@ __global__ void __launch_bounds__(MAXT, 1024 / MAXT) beta_l2r_kernel(DevModel M,
          double lMax = LZERO_D, un0 = LZERO_D, un1 = LZERO_D, un2 = LZERO_D;
          if (active) {
             const double ex = (q + 1 >= lo1 && q + 1 <= hi1) ? prev[q + 1] : LZERO_D;      // :1225
-            const double n2 = ladd_nz(r.a2x + ex, r.a22 + u2);                             // :1228-1236
-            const double n1 = ladd_nz(r.a11 + u1, r.a12 + u2);
-            const double n0 = ladd_nz(r.a00 + u0, r.a01 + u1);
+            const double n2 = ladd_nz_b(r.a2x + ex, r.a22 + u2);                             // :1228-1236
+            const double n1 = ladd_nz_b(r.a11 + u1, r.a12 + u2);
+            const double n0 = ladd_nz_b(r.a00 + u0, r.a01 + u1);
             un0 = (double)c0 + n0; un1 = (double)c1 + n1; un2 = (double)c2 + n2;
             const double x = r.aE + un0;                                                   // :1242-1250
             bg[0] = x; bg[1] = n0; bg[2] = n1; bg[3] = n2; bg[4] = ex;
@@ -262,9 +262,9 @@ __global__ void __launch_bounds__(256, 4) beta_l2r_slide_kernel(DevModel M, Wave
          double lMax = LZERO_D, un0 = LZERO_D, un1 = LZERO_D, un2 = LZERO_D;
          if (active) {
             const double ex = (q + 1 >= lo1 && q + 1 <= hi1) ? prev[q + 1] : LZERO_D;      // :1225
-            const double n2 = ladd_nz(r.a2x + ex, r.a22 + u2);                             // :1228-1236
-            const double n1 = ladd_nz(r.a11 + u1, r.a12 + u2);
-            const double n0 = ladd_nz(r.a00 + u0, r.a01 + u1);
+            const double n2 = ladd_nz_b(r.a2x + ex, r.a22 + u2);                             // :1228-1236
+            const double n1 = ladd_nz_b(r.a11 + u1, r.a12 + u2);
+            const double n0 = ladd_nz_b(r.a00 + u0, r.a01 + u1);
             un0 = (double)c0 + n0; un1 = (double)c1 + n1; un2 = (double)c2 + n2;
             const double x = r.aE + un0;                                                   // :1242-1250
             double *bg = bgRow + 5 * q;
@@ -420,9 +420,9 @@ __global__ void __launch_bounds__(32) alpha_l2r_kernel(DevModel M, Wave W, int f
          // ---- alpha column, HFB.c:729-771
          if (have && myq >= nsq && myq <= neq) {
             a1 = (myq > 0 && ok1) ? ax1 : LZERO_D;
-            n0 = ladd_nz(r.aE + a1, e0 + r.a00) + (double)b0;
-            n1 = ladd_nz(e0 + r.a01, e1 + r.a11) + (double)b1;
-            n2 = ladd_nz(e1 + r.a12, e2 + r.a22) + (double)b2;
+            n0 = ladd_nz(r.aE + a1, e0 + r.a00) + f2d_alu(b0);
+            n1 = ladd_nz(e0 + r.a01, e1 + r.a11) + f2d_alu(b1);
+            n2 = ladd_nz(e1 + r.a12, e2 + r.a22) + f2d_alu(b2);
             nEx = (n2 > LSMALL_D) ? n2 + r.a2x : LZERO_D;
          }
       }
