@@ -42,7 +42,7 @@ __device__ __forceinline__ double dmax(double a, double b) { return (a > b) ? a 
 // K2 (standard topology): one CTA per utterance, one thread per model
 // ------------------------------------------------------------------------------------------
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT, 1024 / MAXT) beta_l2r_kernel(DevModel M, Wave W, int onlyRedo)
+__global__ void __launch_bounds__(MAXT, MAXT == 128 ? 7 : 1024 / MAXT) beta_l2r_kernel(DevModel M, Wave W, int onlyRedo)
 {
    extern __shared__ __align__(16) unsigned char smraw[];
    const UttDesc &u = W.utt[blockIdx.x];
