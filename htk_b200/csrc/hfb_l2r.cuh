@@ -177,6 +177,160 @@ __global__ void __launch_bounds__(MAXT, MAXT == 128 ? 7 : 1024 / MAXT) beta_l2r_
    }
 }
 
+// ------------------------------------------------------------------------------------------
+// K2, transcriptions of up to 128 labels: ONE WARP per utterance, four models per lane
+// ------------------------------------------------------------------------------------------
+// The one-thread-per-model kernel above spends its time waiting, not issuing: a barrier per frame (22 % of the stall
+// samples), and per thread one short dependent chain with nothing to overlap it (issue slots 40 % used).  Here lane L
+// owns the models q = L + 32 k, k = 0..3: their twelve log-adds per frame are independent (instruction-level
+// parallelism instead of warps), the neighbour's entry beta comes by shuffle (model q + 1 sits in lane L + 1, for
+// lane 31 in lane 0 one row up), the beam reductions are shuffles / redux -- no shared memory, no barrier -- and the
+// uniform beam-taper arithmetic is done once per four models.  Same arithmetic, same order, same results as
+// beta_l2r_kernel (tests: HFBGPU_NO_BETA_WARP).
+#define BW_NM 4
+__global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
+{
+   const UttDesc &u = W.utt[blockIdx.x];
+   UttOut *out = &W.out[blockIdx.x];
+   const int lane = threadIdx.x;
+   if (out->status != 0) {
+      if (lane == 0 && out->status == HFB_UTT_SKIPPED) atomicAdd(&W.acc[M.L.numSkipped], 1.0);
+      return;
+   }
+   __syncwarp();
+   const int T = u.T, Q = u.Q, J = u.J;
+   const size_t S = (size_t)5 * Q;
+   L2RRegs r[BW_NM];
+   bool mine[BW_NM];
+#pragma unroll
+   for (int k = 0; k < BW_NM; k++) {
+      const int q = lane + 32 * k;
+      mine[k] = q < Q;
+      if (mine[k]) load_l2r(r[k], M, W, u, q);
+      else { r[k].aE = r[k].a00 = r[k].a01 = r[k].a11 = r[k].a12 = r[k].a22 = r[k].a2x = LZERO_D; r[k].s0 = r[k].s1 = r[k].s2 = 0; }
+   }
+   const float *bU = W.b + u.bOff;
+   double *betaL = W.beta + u.betaOff + 5 * lane;      // model q = lane + 32 k: + 160 k
+   short *qLo = W.qLo + u.frameBase, *qHi = W.qHi + u.frameBase;
+
+   double thresh = W.pruneInit, pr = LZERO_D;
+   int retries = 0, status = 0;
+
+   for (;;) {
+      const bool noPrune = thresh >= 0.5 * HFB_NOPRUNE;
+      double u0[BW_NM], u1[BW_NM], u2[BW_NM], xPrev[BW_NM];   // b_j(o_{t+1}) + beta_j(t+1); entry beta at t+1
+      float bA0[BW_NM], bA1[BW_NM], bA2[BW_NM], bB0[BW_NM], bB1[BW_NM], bB2[BW_NM];
+      // ---- t = T-1, HFB.c:1176-1198
+      int lo1 = Q - 1, hi1 = Q - 1, lastq = lo1;
+      if (lane == 0) { qHi[T - 1] = (short)(Q - 1); qLo[T - 1] = (short)(Q - 1); }
+#pragma unroll
+      for (int k = 0; k < BW_NM; k++) {
+         const int q = lane + 32 * k;
+         u0[k] = u1[k] = u2[k] = xPrev[k] = LZERO_D;
+         bA0[k] = bA1[k] = bA2[k] = bB0[k] = bB1[k] = bB2[k] = 0.f;
+         if (mine[k] && q >= lo1) {
+            const float *bt = bU + (size_t)(T - 1) * J;
+            const double bExit = (q == Q - 1) ? 0.0 : LZERO_D;
+            const double n0 = LZERO_D + bExit, n1 = LZERO_D + bExit, n2 = r[k].a2x + bExit;
+            u0[k] = (double)bt[r[k].s0] + n0; u1[k] = (double)bt[r[k].s1] + n1; u2[k] = (double)bt[r[k].s2] + n2;
+            const double x = (n0 > LSMALL_D) ? r[k].aE + u0[k] : LZERO_D;
+            double *bg = betaL + (size_t)(T - 1) * S + 160 * k;
+            bg[0] = x; bg[1] = n0; bg[2] = n1; bg[3] = n2; bg[4] = bExit;
+            xPrev[k] = x;
+         }
+         // output probabilities travel two frames ahead of their use, in registers
+         if (mine[k]) {
+            if (T >= 2) { const float *b2 = bU + (size_t)(T - 2) * J; bA0[k] = b2[r[k].s0]; bA1[k] = b2[r[k].s1]; bA2[k] = b2[r[k].s2]; }
+            if (T >= 3) { const float *b2 = bU + (size_t)(T - 3) * J; bB0[k] = b2[r[k].s0]; bB1[k] = b2[r[k].s1]; bB2[k] = b2[r[k].s2]; }
+         }
+      }
+
+      // ---- t = T-2 .. 0, HFB.c:1205-1277
+      bool fail = false;
+      double *bgT = betaL + (size_t)(T - 1) * S;       // lane's beta column pointer at t
+      const float *bp = bU + (size_t)(T - 3) * J;      // the output-probability row of frame t-2
+      int hiC = (T - 1) / 3, hiR = (T - 1) % 3, loC = 0, loR = 0;      // closed-form taper, see beta_l2r_kernel
+      for (int t = T - 2; t >= 0; t--) {
+         bgT -= S; bp -= J;
+         if (hiR == 0) { hiR = 2; hiC--; } else hiR--;
+         if (loR == 2) { loR = 0; loC++; } else loR++;
+         const int tapLo = max(0, Q - 1 - loC), tapHi = min(Q - 1, hiC);
+         const int startq = hi1;
+         const int endq = (lo1 == 0) ? 0 : ((tapLo >= lo1) ? tapLo : lo1 - 1);
+         lastq = endq;
+         double un0[BW_NM], un1[BW_NM], un2[BW_NM], xNew[BW_NM], lMax[BW_NM];
+         bool active[BW_NM];
+#pragma unroll
+         for (int k = 0; k < BW_NM; k++) {
+            const int q = lane + 32 * k;
+            // entry beta of model q + 1 at t + 1: lane + 1 same row, lane 31 -> lane 0 one row up
+            const double y = (lane == 0) ? ((k + 1 < BW_NM) ? xPrev[k + 1] : LZERO_D) : xPrev[k];
+            const double exN = __shfl_sync(0xffffffffu, y, (lane + 1) & 31);
+            active[k] = mine[k] && q >= endq && q <= startq;
+            const float c0 = bA0[k], c1 = bA1[k], c2 = bA2[k];
+            bA0[k] = bB0[k]; bA1[k] = bB1[k]; bA2[k] = bB2[k];
+            if (t >= 2 && mine[k] && q >= endq - 2 && q <= startq) { bB0[k] = bp[r[k].s0]; bB1[k] = bp[r[k].s1]; bB2[k] = bp[r[k].s2]; }
+            lMax[k] = LZERO_D; un0[k] = un1[k] = un2[k] = xNew[k] = LZERO_D;
+            if (active[k]) {
+               const double ex = (q + 1 >= lo1 && q + 1 <= hi1) ? exN : LZERO_D;            // :1225
+               const double n2 = ladd_nz_b(r[k].a2x + ex, r[k].a22 + u2[k]);               // :1228-1236
+               const double n1 = ladd_nz_b(r[k].a11 + u1[k], r[k].a12 + u2[k]);
+               const double n0 = ladd_nz_b(r[k].a00 + u0[k], r[k].a01 + u1[k]);
+               un0[k] = (double)c0 + n0; un1[k] = (double)c1 + n1; un2[k] = (double)c2 + n2;
+               const double x = r[k].aE + un0[k];                                          // :1242-1250
+               double *bg = bgT + 160 * k;
+               bg[0] = x; bg[1] = n0; bg[2] = n1; bg[3] = n2; bg[4] = ex;
+               xNew[k] = x;
+               lMax[k] = dmax(dmax(n0, n1), n2);
+            }
+         }
+         int nhi, nlo;
+         if (noPrune) { nhi = startq; nlo = endq; }
+         else {
+            double gMax = dmax(dmax(lMax[0], lMax[1]), dmax(lMax[2], lMax[3]));
+            gMax = warp_max(gMax);
+            // ---- pruning (:1254-1272)
+            int myHi = -1, myLo = 0x7fffffff;
+#pragma unroll
+            for (int k = 0; k < BW_NM; k++) {
+               const bool keep = active[k] && !(gMax - lMax[k] > thresh);
+               if (keep) { myHi = max(myHi, lane + 32 * k); myLo = min(myLo, lane + 32 * k); }
+            }
+            nhi = __reduce_max_sync(0xffffffffu, myHi);
+            nlo = __reduce_min_sync(0xffffffffu, myLo);
+         }
+         if (nhi < 0) { fail = true; status = HFB_UTT_EBETA; break; }
+         if (nhi > tapHi) nhi = tapHi;
+         if (nlo > nhi) { fail = true; break; }
+         if (lane == 0) { qHi[t] = (short)nhi; qLo[t] = (short)nlo; }
+         hi1 = nhi; lo1 = nlo;
+#pragma unroll
+         for (int k = 0; k < BW_NM; k++) {
+            const int q = lane + 32 * k;
+            const bool inNew = active[k] && q >= nlo && q <= nhi;
+            u0[k] = inNew ? un0[k] : LZERO_D; u1[k] = inNew ? un1[k] : LZERO_D; u2[k] = inNew ? un2[k] : LZERO_D;
+            xPrev[k] = xNew[k];
+         }
+      }
+      if (status != 0) break;
+      if (!fail) {
+         // utt->pr = bqt[1] (:1280): entry beta of model lastq at the last frame processed
+         const int kq = lastq >> 5;
+         const double v = (kq == 0) ? xPrev[0] : (kq == 1) ? xPrev[1] : (kq == 2) ? xPrev[2] : xPrev[3];
+         pr = __shfl_sync(0xffffffffu, v, lastq & 31);
+         if (pr > LSMALL_D) break;
+      }
+      thresh += W.pruneInc;                            // StepBack retry (:1349-1361)
+      if (thresh > W.pruneLim || W.pruneInc == 0.0) { status = HFB_UTT_SKIPPED; break; }
+      retries++;
+   }
+   if (lane == 0) {
+      out->status = status; out->retries = retries; out->pr = (status == 0) ? pr : LZERO_D;
+      out->thresh = thresh;
+      if (status == HFB_UTT_SKIPPED) atomicAdd(&W.acc[M.L.numSkipped], 1.0);
+   }
+}
+
 // Long transcriptions with beam pruning (config #5: 667 labels, beam ~40 models): the same recursion with a SLIDING
 // window of blockDim models instead of one thread per label -- thread i owns the model q = i (mod blockDim) nearest
 // below the beam's upper end and moves blockDim models down when its model leaves the beam for good (the beta beam

@@ -738,7 +738,8 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
       if (l2r && w.maxQ <= 1024) {
          const size_t fsm = beta_fast_smem_bytes(w.maxQ);
          const bool pruning = c->opt.pruneInit < 0.5 * HFB_NOPRUNE;
-         if (w.maxQ <= 128) beta_l2r_kernel<128><<<nU, nt, fsm, st>>>(c->dm, W, 0);       // 72 registers, 7 CTAs/SM
+         if (w.maxQ <= 32 * BW_NM && !getenv("HFBGPU_NO_BETA_WARP")) beta_l2r_warp_kernel<<<nU, 32, 0, st>>>(c->dm, W);
+         else if (w.maxQ <= 128) beta_l2r_kernel<128><<<nU, nt, fsm, st>>>(c->dm, W, 0);  // 72 registers, 7 CTAs/SM
          else if (w.maxQ <= 256) beta_l2r_kernel<256><<<nU, nt, fsm, st>>>(c->dm, W, 0);
          else if (pruning && !getenv("HFBGPU_NO_SLIDE")) {
             // long transcriptions under a beam: 256-model sliding window, the one-thread-per-label kernel redoes overflows

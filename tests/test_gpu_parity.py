@@ -271,6 +271,44 @@ def test_generic_kernels_and_redo_path(name, hook, monkeypatch):
     assert max(e.values()) < RTOL, e
 
 
+@pytest.mark.parametrize("prune", [None, (2.0, 6.0, 200.0), (60.0, 30.0, 300.0)])
+def test_beta_warp_kernel_equals_block_kernel(prune, monkeypatch):
+    """beta_l2r_warp_kernel (one warp per utterance, four models per lane, no barriers) against beta_l2r_kernel
+    (one thread per model, HFBGPU_NO_BETA_WARP) and the oracle: transcriptions of 1..128 labels, with and without
+    pruning (tight beam: StepBack retries), identical beams, thresholds and log-likelihoods."""
+    from htk_b200 import synth
+    from htk_b200.flat import flatten
+    hs = synth.make_tied_triphone_set(n_states=60, M=4, n_phys=40, n_logical=40, n_centre=6, seed=5, spread=0.3)
+    fm = flatten(hs)
+    feats, labs = [], []
+    for i, Q in enumerate([1, 2, 5, 31, 32, 33, 63, 64, 65, 97, 127, 128]):
+        f, l = synth.sample_corpus(fm, n_utts=1, T=max(12, 4 * Q + 7 * (i % 3)), Q=Q, seed=100 + i)
+        feats += f; labs += l
+    b = Batch(feats, labs, fm.D)
+    kw = dict(prune=prune)
+    fb = _fb(fm, **kw); r1, b1 = fb.FBFile(b, want_beams=True); a1 = fb.GetAccs(); fb.close()
+    monkeypatch.setenv("HFBGPU_NO_BETA_WARP", "1")
+    fb = _fb(fm, **kw); r2, b2 = fb.FBFile(b, want_beams=True); a2 = fb.GetAccs(); fb.close()
+    assert any(r.status == 0 for r in r1)
+    if prune and prune[0] < 30:
+        assert any(r.retries > 0 for r in r1), [r.retries for r in r1]
+    for x, y in zip(r1, r2):
+        assert (x.status, x.retries, x.pruneThresh) == (y.status, y.retries, y.pruneThresh)
+        if x.status == 0:
+            assert x.pr == y.pr
+    for k in ("qLo", "qHi", "sq", "eq"):
+        assert np.array_equal(getattr(b1, k), getattr(b2, k)), k
+    e = acc_errors(a1, a2, fm)
+    assert max(e.values()) < 1e-5, e
+    oacc, ores, obeams = _oracle(fm, b, kw)
+    for x, y in zip(r1, ores):
+        assert x.status == y[0] and (y[0] != 0 or x.pruneThresh == y[3])
+    for k in ("qLo", "qHi", "sq", "eq"):
+        assert np.array_equal(getattr(b1, k), getattr(obeams, k)), k
+    e = acc_errors(a1, oacc, fm)
+    assert max(e.values()) < RTOL, e
+
+
 @pytest.mark.parametrize("name", ["synth_tied_m4", "synth_long_m3", "synth_tee_m2"])
 def test_tensor_core_statistics_equal_fp32_statistics(name, monkeypatch):
     """stats4_kernel (occupancy-weighted sums as 3xTF32 mma products about the state centre) against
