@@ -444,7 +444,7 @@ def main():
         ms = kms["beta"] + kms["alpha"]
         if ms > 0:
             ach = by / (ms * 1e-3) / 1e9
-            rl["recursions"] = {"bound": "hbm", "kernel": "beta_l2r_kernel + alpha_l2r_kernel", "achieved": ach, "peak": peaks["hbm"],
+            rl["recursions"] = {"bound": "hbm", "kernel": "beta_l2r_warp_kernel + alpha_l2r_kernel", "achieved": ach, "peak": peaks["hbm"],
                                 "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None, "ms_per_launch": ms, "launches_per_step": 2,
                                 "note": "algorithmic bytes = 104 B per beta cell + features both passes (SURVEY 8d); peak = %s copy "
                                         "bandwidth; latency-bound by the T-step chain (stall breakdown in profiles/README.md)" % peaks["src"]}
