@@ -250,7 +250,7 @@ __host__ __device__ inline size_t stats5_warp_bytes(int D)
 
 // NT = 8-column tiles of the right-hand side: columns 0..D-1 the dimensions, column D the ones column (D + 1 <= 8 NT)
 template <int NT>
-__global__ void __launch_bounds__(32 * S4_WARPS, 4)
+__global__ void __launch_bounds__(32 * S4_WARPS, 3)
 stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec *__restrict__ list,
               const int *__restrict__ listEnd, const ValidFrame *__restrict__ vbuf, const int *__restrict__ vcnt)
 {

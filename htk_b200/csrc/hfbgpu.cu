@@ -126,6 +126,7 @@ struct hfbgpu_ctx {
    // kernels of one wave overlap the throughput-bound GMM / statistics kernels of the other.
    struct Slot {
       cudaStream_t stream = nullptr;
+      cudaStream_t recStream = nullptr;   // HFBGPU_REC_STREAM experiment
       cudaEvent_t ev[6] = {};
       cudaEvent_t evIn = nullptr, evGmm = nullptr;   // inputs uploaded / output probabilities ready
       cudaEvent_t evX = nullptr;        // timing mode: feature expansion done, tensor-core kernel starts
@@ -301,13 +302,12 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
    c->maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
    CK(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
    c->stream = c->ownStream;
-   {
-      int prLo = 0, prHi = 0;
-      CK(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
-      CK(cudaStreamCreateWithPriority(&c->gmmStream, cudaStreamNonBlocking, prHi));
-   }
+   int prLo = 0, prHi = 0;
+   CK(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+   CK(cudaStreamCreateWithPriority(&c->gmmStream, cudaStreamNonBlocking, prHi));
    for (auto &sl : c->slot) {
       CK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithPriority(&sl.recStream, cudaStreamNonBlocking, prHi));
       for (auto &e : sl.ev) CK(cudaEventCreate(&e));
       CK(cudaEventCreateWithFlags(&sl.evIn, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&sl.evGmm, cudaEventDisableTiming));
@@ -456,6 +456,7 @@ extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
       if (sl.evGmm) cudaEventDestroy(sl.evGmm);
       if (sl.evX) cudaEventDestroy(sl.evX);
       if (sl.stream) cudaStreamDestroy(sl.stream);
+      if (sl.recStream) cudaStreamDestroy(sl.recStream);
       delete sl.w;
    }
    c->dHmmN.release(); c->dHmmStateOff.release(); c->dHmmState.release(); c->dHmmTrans.release();
@@ -723,6 +724,11 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
    if (tr) cudaEventRecord(S.ev[1], st);
    // ---- K2 / K3
    if (w.maxQ > 0) {
+      // experiment (HFBGPU_REC_STREAM=1): the latency-bound recursions of every wave on a high-priority stream of their
+      // own, so that their CTAs are placed first and the throughput kernels of the other waves fill in around them.
+      // Measured on B200, cfg3: 153.4 -> 155.4 M frames/s from device features, no change end to end; left off.
+      cudaStream_t sr = (!tm && S.recStream && getenv("HFBGPU_REC_STREAM")) ? S.recStream : st;
+      if (sr != st) { CK(cudaEventRecord(S.evIn, st)); CK(cudaStreamWaitEvent(sr, S.evIn, 0)); }
       int nt = std::min(256, std::max(32, (w.maxQ + 31) & ~31));
       const int ntGeneric = std::min(1024, std::max(32, (w.maxQ + 31) & ~31));   // long transcriptions: still 1 model/thread
       size_t rsm = rec_smem_bytes(w.maxS, w.maxQ), asm_ = alpha_warp_smem_bytes(w.maxS, w.maxQ);
@@ -738,41 +744,42 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
       if (l2r && w.maxQ <= 1024) {
          const size_t fsm = beta_fast_smem_bytes(w.maxQ);
          const bool pruning = c->opt.pruneInit < 0.5 * HFB_NOPRUNE;
-         if (w.maxQ <= 32 * BW_NM && !getenv("HFBGPU_NO_BETA_WARP")) beta_l2r_warp_kernel<<<nU, 32, 0, st>>>(c->dm, W);
-         else if (w.maxQ <= 128) beta_l2r_kernel<128><<<nU, nt, fsm, st>>>(c->dm, W, 0);  // 72 registers, 7 CTAs/SM
-         else if (w.maxQ <= 256) beta_l2r_kernel<256><<<nU, nt, fsm, st>>>(c->dm, W, 0);
+         if (w.maxQ <= 32 * BW_NM && !getenv("HFBGPU_NO_BETA_WARP")) beta_l2r_warp_kernel<<<nU, 32, 0, sr>>>(c->dm, W);
+         else if (w.maxQ <= 128) beta_l2r_kernel<128><<<nU, nt, fsm, sr>>>(c->dm, W, 0);  // 72 registers, 7 CTAs/SM
+         else if (w.maxQ <= 256) beta_l2r_kernel<256><<<nU, nt, fsm, sr>>>(c->dm, W, 0);
          else if (pruning && !getenv("HFBGPU_NO_SLIDE")) {
             // long transcriptions under a beam: 256-model sliding window, the one-thread-per-label kernel redoes overflows
-            beta_l2r_slide_kernel<<<nU, 256, fsm, st>>>(c->dm, W);
-            beta_l2r_kernel<1024><<<nU, ntGeneric, fsm, st>>>(c->dm, W, 1);
+            beta_l2r_slide_kernel<<<nU, 256, fsm, sr>>>(c->dm, W);
+            beta_l2r_kernel<1024><<<nU, ntGeneric, fsm, sr>>>(c->dm, W, 1);
             c->stats.launches++; c->stats.launchesBeta++;
-         } else beta_l2r_kernel<1024><<<nU, ntGeneric, fsm, st>>>(c->dm, W, 0);
+         } else beta_l2r_kernel<1024><<<nU, ntGeneric, fsm, sr>>>(c->dm, W, 0);
          c->stats.launchesL2R++;
       } else if (betaFastOk) {
          const size_t fsm = beta_fast_smem_bytes(w.maxQ);
          if (w.maxN <= 5) {
-            if (exact) beta_fast_kernel<true, 3><<<nU, nt, fsm, st>>>(c->dm, W);
-            else beta_fast_kernel<false, 3><<<nU, nt, fsm, st>>>(c->dm, W);
+            if (exact) beta_fast_kernel<true, 3><<<nU, nt, fsm, sr>>>(c->dm, W);
+            else beta_fast_kernel<false, 3><<<nU, nt, fsm, sr>>>(c->dm, W);
          } else {
-            if (exact) beta_fast_kernel<true, 6><<<nU, nt, fsm, st>>>(c->dm, W);
-            else beta_fast_kernel<false, 6><<<nU, nt, fsm, st>>>(c->dm, W);
+            if (exact) beta_fast_kernel<true, 6><<<nU, nt, fsm, sr>>>(c->dm, W);
+            else beta_fast_kernel<false, 6><<<nU, nt, fsm, sr>>>(c->dm, W);
          }
-      } else if (exact) beta_kernel<true><<<nU, ntGeneric, rsm, st>>>(c->dm, W);
-      else beta_kernel<false><<<nU, ntGeneric, rsm, st>>>(c->dm, W);
+      } else if (exact) beta_kernel<true><<<nU, ntGeneric, rsm, sr>>>(c->dm, W);
+      else beta_kernel<false><<<nU, ntGeneric, rsm, sr>>>(c->dm, W);
       if (tr) cudaEventRecord(S.ev[2], st);
       if (fastOk) {                                    // register/shuffle kernel; generic one redoes overflows
-         if (l2r) { alpha_l2r_kernel<<<nU, 32, 0, st>>>(c->dm, W, forceRedo); c->stats.launchesL2R++; }
+         if (l2r) { alpha_l2r_kernel<<<nU, 32, 0, sr>>>(c->dm, W, forceRedo); c->stats.launchesL2R++; }
          else if (w.maxN <= 5) {
-            if (exact) alpha_fast_kernel<true, 3><<<nU, 32, 0, st>>>(c->dm, W, forceRedo);
-            else alpha_fast_kernel<false, 3><<<nU, 32, 0, st>>>(c->dm, W, forceRedo);
+            if (exact) alpha_fast_kernel<true, 3><<<nU, 32, 0, sr>>>(c->dm, W, forceRedo);
+            else alpha_fast_kernel<false, 3><<<nU, 32, 0, sr>>>(c->dm, W, forceRedo);
          } else {
-            if (exact) alpha_fast_kernel<true, 6><<<nU, 32, 0, st>>>(c->dm, W, forceRedo);
-            else alpha_fast_kernel<false, 6><<<nU, 32, 0, st>>>(c->dm, W, forceRedo);
+            if (exact) alpha_fast_kernel<true, 6><<<nU, 32, 0, sr>>>(c->dm, W, forceRedo);
+            else alpha_fast_kernel<false, 6><<<nU, 32, 0, sr>>>(c->dm, W, forceRedo);
          }
          c->stats.launches++; c->stats.launchesAlpha++;
       }
-      if (exact) alpha_warp_kernel<true><<<nU, 32, asm_, st>>>(c->dm, W, fastOk ? 1 : 0);
-      else alpha_warp_kernel<false><<<nU, 32, asm_, st>>>(c->dm, W, fastOk ? 1 : 0);
+      if (exact) alpha_warp_kernel<true><<<nU, 32, asm_, sr>>>(c->dm, W, fastOk ? 1 : 0);
+      else alpha_warp_kernel<false><<<nU, 32, asm_, sr>>>(c->dm, W, fastOk ? 1 : 0);
+      if (sr != st) { CK(cudaEventRecord(S.evGmm, sr)); CK(cudaStreamWaitEvent(st, S.evGmm, 0)); }
       if (tr) cudaEventRecord(S.ev[3], st);
       c->stats.launches += 2; c->stats.launchesBeta++; c->stats.launchesAlpha++;
       // ---- K4
