@@ -491,6 +491,9 @@ __global__ void __launch_bounds__(256, 4) beta_l2r_slide_kernel(DevModel M, Wave
 // sliding window that starts at the alpha beam's lower end.  Without tee models StepAlpha can
 // reach [sq(t-1), eq(t-1)+1] only.  Writes alpha, the beams and first/last active frame per
 // model; gives up (out->redo) if a beam ever needs more than 32 models.
+// (Tried: two utterances per warp in lock step, for the instruction-level parallelism that pays in
+// beta_l2r_warp_kernel.  1.21 ms instead of 0.78: the per-utterance branches (window, beam, slide) keep the two chains
+// in separate basic blocks, so they run one after the other; it would need fully predicated code.)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) alpha_l2r_kernel(DevModel M, Wave W, int forceRedo)
 {
