@@ -307,7 +307,7 @@ gmm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant_
          const int half = lane / SPT, bi = lane % SPT;          // lanes [0,SPT): hi boxes, [SPT,2SPT): lo boxes
          for (int n = 0; n < nTiles; n++) {
             const int slot = n * SPT + bi;
-            const int row = (lane < 2 * SPT && slot < u.J) ? (1 + ss[slot]) * MP : 0;   // rows [0,MP) = dummy state
+            const int row = (lane < 2 * SPT && slot < u.Jt) ? (1 + ss[slot]) * MP : 0;   // rows [0,MP) = dummy state
             for (int k = 0; k < nChunks; k++) {
                if (lane == 0) { tc_mbar_wait(&emptyB[stage], phB ^ 1); tc_mbar_expect_tx(&fullB[stage], (p.dbg & 16) ? 0 : TC_B_STAGE_BYTES); }
                __syncwarp();
@@ -575,7 +575,7 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
          auto box_row = [&](int n) {
             int row = 0;                                        // rows [0,MP) = dummy state
             if (lane < 2 * HB && n < nTiles) {
-               if (SPT >= 2) { const int slot = n * SPT + (int)rank * HB + bi; if (slot < u.J) row = (1 + ss[slot]) * MP; }
+               if (SPT >= 2) { const int slot = n * SPT + (int)rank * HB + bi; if (slot < u.Jt) row = (1 + ss[slot]) * MP; }
                else row = (1 + ss[n]) * MP + (int)rank * 64;    // MP = 128: each CTA takes 64 rows of the state
             }
             return row;
@@ -733,6 +733,11 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             const uint32_t taddr = tmem + as * (2 * TC_BN) + blk * TC_BN + ((uint32_t)(quad * 32) << 16);
             const float C0 = p.C0;
             float cmx = -INFINITY, csum = 0.f;          // carry for states wider than one 32-column chunk
+            // states of at most 32 components: the warp's columns are NOUT consecutive slots of this frame's row, stored
+            // with 16-byte (8-byte) stores -- one store per lane and state cost 32 sector writes per instruction
+            constexpr int NOUT = (MP <= 32) ? CPW * 32 / MP : 0;
+            float outv[NOUT > 0 ? NOUT : 1];
+            int no = 0;
 #pragma unroll
             for (int cc = 0; cc < CPW; cc++) {
                if (p.dbg & 2) break;
@@ -764,10 +769,21 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                   if (colEnd % MP == 0) {
                      const int slot = n * SPT + colEnd / MP - 1;
                      float val = (mx < p.deadBelow) ? (float)HFB_LZERO : fmaf(tc_lg2(sum), LN2, mx - C0);
-                     if (t < u.T && slot < u.J) brow[slot] = val;
+                     if (NOUT > 0) outv[no++] = val;
+                     else if (t < u.T && slot < u.J) brow[slot] = val;
                      cmx = -INFINITY; csum = 0.f;
                   }
                }
+            }
+            if (NOUT > 0 && !(p.dbg & 2) && t < u.T) {
+               const int slot0 = n * SPT + c0 * 32 / MP;
+               if (NOUT >= 4) {
+#pragma unroll
+                  for (int g = 0; g < NOUT / 4; g++)
+                     if (slot0 + 4 * g < u.J)
+                        *reinterpret_cast<float4 *>(brow + slot0 + 4 * g) = make_float4(outv[4 * g], outv[4 * g + 1], outv[4 * g + 2], outv[4 * g + 3]);
+               } else if (slot0 < u.J)
+                  *reinterpret_cast<float2 *>(brow + slot0) = make_float2(outv[0], outv[NOUT > 1 ? 1 : 0]);
             }
             }
             tc_fence_before();

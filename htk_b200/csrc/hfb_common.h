@@ -33,11 +33,13 @@ struct UttDesc {
    int T, Q;
    int S;                           // sum of N_q: doubles per beta column
    int P;                           // sum of (N_q - 2): emitting positions
-   int J;                           // distinct tied states (output-probability slots); set by prep_kernel
+   int J;                           // row stride of b[t][slot] = distinct tied states rounded up to a multiple of 4
+                                    // (16-byte output stores of the tensor-core kernel); set by prep_kernel
    int labOff;                      // offset of the transcription in the wave's label array
    int modOff;                      // offset of model 0 in the per-model arrays
    int slotOff;                     // offset into slotState[]
    int posOff;                      // offset into posSlot[] / posState[]
+   int Jt;                          // distinct tied states (output-probability slots in use); set by prep_kernel
    long long featOff;               // first frame in the feature matrix
    long long bOff;                  // floats : [T][J] state log-likelihoods
    long long betaOff;               // doubles: [T][S]

@@ -161,7 +161,7 @@ gmm_fp32_kernel(DevModel M, Wave W)
       const int lt = (int)blockIdx.x - W.tilePre[tl.utt], nSl = (u.P + GT_SL - 1) / GT_SL;
       tl.t0 = (lt / nSl) * GT_FR; tl.s0 = (lt % nSl) * GT_SL;
    }
-   if (W.out[tl.utt].status != 0 || tl.s0 >= u.J) return;
+   if (W.out[tl.utt].status != 0 || tl.s0 >= u.Jt) return;
    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
    const int D = M.D, Dp = M.Dp;
    const float *feat = W.feat + (size_t)u.featOff * D;
@@ -174,7 +174,7 @@ gmm_fp32_kernel(DevModel M, Wave W)
 
    for (int sl = wid; sl < GT_SL; sl += 4) {
       int slot = tl.s0 + sl;
-      if (slot >= u.J) break;
+      if (slot >= u.Jt) break;
       int s = W.slotState[u.slotOff + slot];
       int mo = M.stateMixOff[s], Mn = M.stateMixOff[s + 1] - mo;
       float mx0 = -INFINITY, mx1 = -INFINITY, sm0 = 0.f, sm1 = 0.f;
@@ -206,7 +206,7 @@ gmm_fp32_kernel(DevModel M, Wave W)
    float *b = W.b + u.bOff;
    for (int idx = tid; idx < GT_FR * GT_SL; idx += 128) {
       int f = idx >> 5, sl = idx & 31, t = tl.t0 + f, slot = tl.s0 + sl;
-      if (t < u.T && slot < u.J) b[(size_t)t * u.J + slot] = outT[f * (GT_SL + 1) + sl];
+      if (t < u.T && slot < u.Jt) b[(size_t)t * u.J + slot] = outT[f * (GT_SL + 1) + sl];
    }
 }
 
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(128) prep_kernel(DevModel M, Wave W)
          if (f == pp) { slotState[J] = posState[pp]; posSlot[pp] = J++; }
          else posSlot[pp] = posSlot[f];
       }
-      u->J = J; out->J = J;
+      u->Jt = J; u->J = (J + 3) & ~3; out->J = J;
    }
 }
 

@@ -548,7 +548,7 @@ size_t add_utterance(const HostModel &h, WaveTables &w, int uidx, int T, const i
    }
    if (bad) { o.status = HFB_UTT_ETEE; Q = 0; S = 0; }
    const int Pp = S - 2 * Q;
-   u.T = T; u.Q = Q; u.S = S; u.P = Pp; u.J = Pp;
+   u.T = T; u.Q = Q; u.S = S; u.P = Pp; u.J = (Pp + 3) & ~3; u.Jt = Pp;       // J, Jt: bounds, prep_kernel sets them
    w.maxT = std::max(w.maxT, T);
    u.labOff = labOff; u.modOff = (int)w.totalQ; u.slotOff = (int)w.totalP; u.posOff = (int)w.totalP;
    u.featOff = featOff; u.frameBase = featOff;
@@ -557,7 +557,7 @@ size_t add_utterance(const HostModel &h, WaveTables &w, int uidx, int T, const i
    w.tilePre.push_back((int)w.tiles);
    size_t bytes = 0;
    if (!bad) {
-      w.bFloats += (long long)T * Pp; w.betaDoubles += (long long)T * S; w.occDoubles += (long long)T * Pp;
+      w.bFloats += (long long)T * ((Pp + 3) & ~3); w.betaDoubles += (long long)T * S; w.occDoubles += (long long)T * Pp;
       w.aentDoubles += (long long)T * Q;
       bytes = (size_t)T * ((size_t)Pp * 12 + (size_t)S * 8 + (size_t)Q * 8);
       w.totalQ += Q; w.totalP += Pp;
@@ -1145,7 +1145,8 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
    for (int i = 0; i < n; i++) if (states[i] < 0 || states[i] >= h.J) return HFB_EINVAL;
    UttDesc u;
    memset(&u, 0, sizeof(u));
-   u.T = T; u.J = n; u.P = n;
+   const int nPad = (n + 3) & ~3;                       // row stride of the output-probability matrix
+   u.T = T; u.J = nPad; u.Jt = n; u.P = n;
    UttOut o;
    memset(&o, 0, sizeof(o));
    std::vector<int2> items, items2, items4;
@@ -1159,7 +1160,7 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
           oTp = blob_put(blob, tilePre, 2), oIt = blob_put(blob, items), oIt2 = blob_put(blob, items2), oIt4 = blob_put(blob, items4);
    int rc;
    if ((rc = S0.dTables.reserve(blob.size())) || (rc = S0.dFeat.reserve((size_t)T * h.D + 4)) ||
-       (rc = S0.dB.reserve((size_t)T * n + 1)))
+       (rc = S0.dB.reserve((size_t)T * nPad + 1)))
       return rc;
    CK(cudaMemcpyAsync(S0.dTables.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, st0));
    CK(cudaMemcpyAsync(S0.dFeat.p, feat, (size_t)T * h.D * sizeof(float), cudaMemcpyHostToDevice, st0));
@@ -1182,7 +1183,8 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
       c->stats.launches++; c->stats.launchesGmm++;
    }
    CK(cudaGetLastError());
-   CK(cudaMemcpyAsync(out, S0.dB.p, (size_t)T * n * sizeof(float), cudaMemcpyDeviceToHost, st0));
+   CK(cudaMemcpy2DAsync(out, (size_t)n * sizeof(float), S0.dB.p, (size_t)nPad * sizeof(float), (size_t)n * sizeof(float), (size_t)T,
+                        cudaMemcpyDeviceToHost, st0));
    CK(cudaStreamSynchronize(st0));
    return HFB_OK;
 }
