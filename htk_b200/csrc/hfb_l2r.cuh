@@ -186,7 +186,9 @@ __global__ void __launch_bounds__(MAXT, MAXT == 128 ? 7 : 1024 / MAXT) beta_l2r_
 // parallelism instead of warps), the neighbour's entry beta comes by shuffle (model q + 1 sits in lane L + 1, for
 // lane 31 in lane 0 one row up), the beam reductions are shuffles / redux -- no shared memory, no barrier -- and the
 // uniform beam-taper arithmetic is done once per four models.  Same arithmetic, same order, same results as
-// beta_l2r_kernel (tests: HFBGPU_NO_BETA_WARP).
+// beta_l2r_kernel (tests: HFBGPU_NO_BETA_WARP).  (The 8-byte stores of the five betas of a model touch 32 sectors per
+// instruction and cost 0.26 of the 1.19 ms; staging them through shared memory for 256-byte contiguous stores cost more
+// than it saved: 1.69 ms.)
 #define BW_NM 4
 __global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
 {
