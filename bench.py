@@ -63,7 +63,7 @@ def read_peaks():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE gmm_tc2_kernel launch (1024 utterances) from the
 # `ncu --set full` capture of the same command, profiles/r1k_gmm_tc2_raw.txt: 1.121 GB + 1.256 GB
-GMM_TRAFFIC_BYTES = {"cfg3": 2.393e9}
+GMM_TRAFFIC_BYTES = {"cfg3": 2.188e9}
 
 
 def measure_tf32(dev):
