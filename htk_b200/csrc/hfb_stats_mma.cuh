@@ -452,8 +452,9 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
                         const float *mu = gmu + mi * S5_GSTR, *iv = giv + mi * S5_GSTR;
                         const float *o = os + th * S5_OPS;
                         f32x2_t sum = f2_pack(ggc[mi], ggc[mi]);
-                        int k = 0;
-                        for (; k + 4 <= D; k += 4) {
+                        // up to Dp = D rounded up to 4: the padding of the parameter rows is zero (inverse variance 0: the
+                        // ones column and the zero columns of the tile contribute exactly nothing)
+                        for (int k = 0; k < Dp; k += 4) {
                            const float4 m4 = *reinterpret_cast<const float4 *>(mu + k);
                            const float4 v4 = *reinterpret_cast<const float4 *>(iv + k);
                            const ulonglong2 oa = *reinterpret_cast<const ulonglong2 *>(o + 2 * k);
@@ -463,8 +464,6 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
                            sum = f2_step(sum, ob.x, m4.z, v4.z);
                            sum = f2_step(sum, ob.y, m4.w, v4.w);
                         }
-                        for (; k < D; k++)
-                           sum = f2_step(sum, *reinterpret_cast<const f32x2_t *>(o + 2 * k), mu[k], iv[k]);
                         float sa, sb;
                         f2_unpack(sum, sa, sb);
                         xa = (xa + (double)wt) + (double)(-0.5f * sa);          // :1581-1599
