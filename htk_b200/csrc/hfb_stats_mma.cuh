@@ -410,16 +410,18 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
             for (int e = lane; e < 16 * S4_LSTR; e += 32) lrs[e] = 0.f;
             __syncwarp();
             // (4-byte cp.async straight into the tile, all rows in flight, no register staging: measured 4 % SLOWER)
+            // rows nT..nT8-1 are padding: their occupancies stay zero, so they may hold any finite row (frame ts[0])
+            if (lane >= nT && lane < nT8) ts[lane] = ts[0];
+            __syncwarp();
+            const bool col0 = lane < D, col1 = lane + 32 < D;
+            const float pad0 = (lane == D) ? 1.f : 0.f, pad1 = (lane + 32 == D) ? 1.f : 0.f;   // the ones column: sum Lr in phase 2
             for (int tb = 0; tb < nT8; tb += 8) {                  // observation rows, 8 at a time (16 loads in flight per
-               float v0[8], v1[8];                                 // lane); rows nT..nT8-1 are zero padding
+               float v0[8], v1[8];                                 // lane)
 #pragma unroll
                for (int r = 0; r < 8; r++) {
-                  const bool on = tb + r < nT;
-                  const float *src = feat + (size_t)ts[on ? tb + r : 0] * D;
-                  v0[r] = (on && lane < D) ? src[lane] : 0.f;
-                  v1[r] = (on && lane + 32 < D) ? src[lane + 32] : 0.f;
-                  if (on && lane == D) v0[r] = 1.f;                // the ones column: sum Lr in phase 2
-                  if (on && lane + 32 == D) v1[r] = 1.f;
+                  const float *src = feat + (size_t)ts[tb + r] * D;
+                  v0[r] = col0 ? src[lane] : pad0;
+                  v1[r] = col1 ? src[lane + 32] : pad1;
                }
 #pragma unroll
                for (int r = 0; r < 8; r++) {
