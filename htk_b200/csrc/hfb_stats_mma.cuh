@@ -438,22 +438,23 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
             //      3.7x fewer instructions for this phase, but the kernel got 9-14 % SLOWER on B200 -- the legacy
             //      HMMA path cannot keep up; the tcgen05 version needs frames gathered per state, see DESIGN.md.)
             unsigned anyLr = 0;
-            // lane <-> (component, frame pair): the two frames share the component's parameters and go through the
-            // packed FP32 pipe together; row nT of an odd chunk is zero padding and its result is dropped
-            const int nTh = (nT + 1) >> 1;
-            const float rnT = 1.0f / (float)nTh;                 // (pi + 0.5) / nTh is never within 1/32 of an integer
-            for (int pi = lane; pi < ((Mc * nTh + 31) & ~31); pi += 32) {
-               float Lr0 = 0.f, Lr1 = 0.f;
-               const int mi = (int)(((float)pi + 0.5f) * rnT), th = pi - mi * nTh, ti = 2 * th;
+            // lane <-> (component, four frames): the frames share the component's parameter loads and go through the
+            // packed FP32 pipe as two independent pairs; rows past nT hold finite data whose results are dropped
+            const int nTq = (nT + 3) >> 2;
+            const float rnT = 1.0f / (float)nTq;                 // (pi + 0.5) / nTq is never within 1/16 of an integer
+            for (int pi = lane; pi < ((Mc * nTq + 31) & ~31); pi += 32) {
+               float Lr[4] = {0.f, 0.f, 0.f, 0.f};
+               const int mi = (int)(((float)pi + 0.5f) * rnT), tq = pi - mi * nTq, ti = 4 * tq;
                if (mi < Mc) {
                   const float wt = gwt[mi];
-                  const bool two = ti + 1 < nT;
                   if (wt > LMINMIX_F) {                                         // HFB.c:1573
-                     double xa = x0s[ti], xb = two ? x0s[ti + 1] : 0.0;
+                     double x[4];
+#pragma unroll
+                     for (int j = 0; j < 4; j++) x[j] = (ti + j < nT) ? x0s[ti + j] : 0.0;
                      if (Mn > 1) {
                         const float *mu = gmu + mi * S5_GSTR, *iv = giv + mi * S5_GSTR;
-                        const float *o = os + th * S5_OPS;
-                        f32x2_t sum = f2_pack(ggc[mi], ggc[mi]);
+                        const float *o = os + 2 * tq * S5_OPS;
+                        f32x2_t sA = f2_pack(ggc[mi], ggc[mi]), sB = sA;
                         // up to Dp = D rounded up to 4: the padding of the parameter rows is zero (inverse variance 0: the
                         // ones column and the zero columns of the tile contribute exactly nothing)
                         for (int k = 0; k < Dp; k += 4) {
@@ -461,23 +462,27 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
                            const float4 v4 = *reinterpret_cast<const float4 *>(iv + k);
                            const ulonglong2 oa = *reinterpret_cast<const ulonglong2 *>(o + 2 * k);
                            const ulonglong2 ob = *reinterpret_cast<const ulonglong2 *>(o + 2 * k + 4);
-                           sum = f2_step(sum, oa.x, m4.x, v4.x);
-                           sum = f2_step(sum, oa.y, m4.y, v4.y);
-                           sum = f2_step(sum, ob.x, m4.z, v4.z);
-                           sum = f2_step(sum, ob.y, m4.w, v4.w);
+                           const ulonglong2 oc = *reinterpret_cast<const ulonglong2 *>(o + S5_OPS + 2 * k);
+                           const ulonglong2 od = *reinterpret_cast<const ulonglong2 *>(o + S5_OPS + 2 * k + 4);
+                           sA = f2_step(sA, oa.x, m4.x, v4.x); sB = f2_step(sB, oc.x, m4.x, v4.x);
+                           sA = f2_step(sA, oa.y, m4.y, v4.y); sB = f2_step(sB, oc.y, m4.y, v4.y);
+                           sA = f2_step(sA, ob.x, m4.z, v4.z); sB = f2_step(sB, od.x, m4.z, v4.z);
+                           sA = f2_step(sA, ob.y, m4.w, v4.w); sB = f2_step(sB, od.y, m4.w, v4.w);
                         }
-                        float sa, sb;
-                        f2_unpack(sum, sa, sb);
-                        xa = (xa + (double)wt) + (double)(-0.5f * sa);          // :1581-1599
-                        xb = (xb + (double)wt) + (double)(-0.5f * sb);
+                        float sv[4];
+                        f2_unpack(sA, sv[0], sv[1]); f2_unpack(sB, sv[2], sv[3]);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) x[j] = (x[j] + (double)wt) + (double)(-0.5f * sv[j]);   // :1581-1599
                      }
-                     if (-xa < minF) Lr0 = expf((float)xa);                     // :1606, :1612
-                     if (two && -xb < minF) Lr1 = expf((float)xb);
+#pragma unroll
+                     for (int j = 0; j < 4; j++)
+                        if (ti + j < nT && -x[j] < minF) Lr[j] = expf((float)x[j]);   // :1606, :1612
                   }
-                  lrs[mi * S4_LSTR + ti] = Lr0;
-                  if (two) lrs[mi * S4_LSTR + ti + 1] = Lr1;
+#pragma unroll
+                  for (int j = 0; j < 4; j++)
+                     if (ti + j < nT) lrs[mi * S4_LSTR + ti + j] = Lr[j];
                }
-               anyLr |= __ballot_sync(0xffffffffu, Lr0 > 0.f || Lr1 > 0.f);
+               anyLr |= __ballot_sync(0xffffffffu, Lr[0] > 0.f || Lr[1] > 0.f || Lr[2] > 0.f || Lr[3] > 0.f);
             }
             __syncwarp();
             if (!anyLr) continue;
