@@ -323,9 +323,22 @@ stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec
          __syncwarp();
       };
 
+      // software prefetch pipeline along the sorted list (long-scoreboard stalls were the largest share): record
+      // fields of position it + 3 -> frame numbers of it + 2 -> observation rows of it + 1 into L2
+      int tB = -1, cntA = 0;
+      long long fB = 0, offA = -1, featA = 0;
       for (int it = i0; it < i1; it++) {
          const PosRec &R = list[it];
          if (it + 1 < i1) prefetch_l1(&list[it + 1]);
+         if (tB >= 0) {
+            const float *row = W.feat + (size_t)(fB + tB) * D;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 32));
+         }
+         tB = (offA >= 0 && lane < cntA) ? vbuf[offA + lane].t : -1;
+         fB = featA;
+         offA = -1;
+         if (it + 3 < i1) { offA = list[it + 3].vOff; cntA = min(32, vcnt[it + 3]); featA = list[it + 3].featOff; }
          const int s = R.s;
          if (s != curS) {
             if (any) flush();
