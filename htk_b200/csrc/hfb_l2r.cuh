@@ -568,20 +568,22 @@ __global__ void __launch_bounds__(32) alpha_l2r_kernel(DevModel M, Wave W, int f
          const bool ok1 = (q1 == myq - 1);
          const double mp = dmax(ok1 ? ex1 : LZERO_D, mpS);                  // MaxModelProb(q, t-1), :655-682
          const bool keep = inWin && !(pr - mp > minF);
+         // the alpha column (HFB.c:729-771) does not depend on the beam decisions: its log-adds are issued first and
+         // run under the latency of the two warp reductions; the beam only decides whether the values are kept
+         const double a1s = (myq > 0 && ok1) ? ax1 : LZERO_D;
+         const double s0 = ladd_nz(r.aE + a1s, e0 + r.a00) + f2d_alu(b0);
+         const double s1 = ladd_nz(e0 + r.a01, e1 + r.a11) + f2d_alu(b1);
+         const double s2 = ladd_nz(e1 + r.a12, e2 + r.a22) + f2d_alu(b2);
+         const int eq0 = (hiP < Q - 1) ? hiP + 1 : hiP;
          nsq = __reduce_min_sync(FULL, (keep && myq >= loP) ? myq : 0x7fffffff);
+         neq = __reduce_max_sync(FULL, (keep && myq <= eq0) ? myq : -1);
          if (nsq > hiT) { if (lane == 0) out->status = HFB_UTT_EALPHA; return; }        // HError 7390
          if (nsq < loT) nsq = loT;
-         const int eq0 = (hiP < Q - 1) ? hiP + 1 : hiP;
-         neq = __reduce_max_sync(FULL, (keep && myq <= eq0) ? myq : -1);
          if (neq < nsq) { if (lane == 0) out->status = HFB_UTT_EALPHA; return; }
          if (neq > hiT) neq = hiT;
          if (neq + 1 - nsq >= 32) { if (lane == 0) out->redo = 1; return; }
-         // ---- alpha column, HFB.c:729-771
          if (have && myq >= nsq && myq <= neq) {
-            a1 = (myq > 0 && ok1) ? ax1 : LZERO_D;
-            n0 = ladd_nz(r.aE + a1, e0 + r.a00) + f2d_alu(b0);
-            n1 = ladd_nz(e0 + r.a01, e1 + r.a11) + f2d_alu(b1);
-            n2 = ladd_nz(e1 + r.a12, e2 + r.a22) + f2d_alu(b2);
+            a1 = a1s; n0 = s0; n1 = s1; n2 = s2;
             nEx = (n2 > LSMALL_D) ? n2 + r.a2x : LZERO_D;
          }
       }
