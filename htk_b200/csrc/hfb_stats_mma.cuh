@@ -49,7 +49,7 @@ __device__ __forceinline__ void s4_mma(float (&d)[4], const uint32_t (&a)[4], ui
 }
 
 
-#define S5_CAP 16                     // sorted positions per warp
+#define S5_CAP 16                     // sorted positions per warp: minimum; the host raises it to 32 / 64 for large waves
 
 // ---- counting sort of the wave's positions by tied state ------------------------------------------
 // cnt[J] must be zero on entry.  Only positions whose model was ever inside the alpha beam are listed.
@@ -252,12 +252,12 @@ __host__ __device__ inline size_t stats5_warp_bytes(int D)
 template <int NT>
 __global__ void __launch_bounds__(32 * S4_WARPS, 3)
 stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec *__restrict__ list,
-              const int *__restrict__ listEnd, const ValidFrame *__restrict__ vbuf, const int *__restrict__ vcnt)
+              const int *__restrict__ listEnd, const ValidFrame *__restrict__ vbuf, const int *__restrict__ vcnt, int cap)
 {
    extern __shared__ __align__(16) unsigned char smraw[];
    const int wInB = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const int nSorted = *listEnd;
-   const int i0 = (blockIdx.x * S4_WARPS + wInB) * S5_CAP, i1 = min(nSorted, i0 + S5_CAP);
+   const int i0 = (blockIdx.x * S4_WARPS + wInB) * cap, i1 = min(nSorted, i0 + cap);
    if (i0 >= i1) return;
    const int D = M.D, Dp = M.Dp;
    unsigned char *mine = smraw + stats5_warp_bytes<NT>(D) * wInB;

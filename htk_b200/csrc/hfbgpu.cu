@@ -815,10 +815,14 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
                stats_pre_kernel<<<dim3(nU, gy), 32 * SPRE_WARPS, 0, st>>>(c->dm, W, list, posIdx, S.dValid.p, vcnt);
                c->stats.launches++; c->stats.launchesStats++;
             }
-            const unsigned nWarps = (unsigned)((w.totalP + S5_CAP - 1) / S5_CAP);
+            // positions per warp: more of them = longer runs of one state per warp (fewer flushes, the prefetch pipeline
+            // stays primed: 16 -> 64 is 1.75 -> 1.67 ms on config #3), as long as two waves of CTAs remain
+            int cap = S5_CAP;
+            while (cap < 64 && w.totalP >= (long long)2 * cap * S4_WARPS * 3 * c->smCount * 2) cap *= 2;
+            const unsigned nWarps = (unsigned)((w.totalP + cap - 1) / cap);
             const unsigned grid = (nWarps + S4_WARPS - 1) / S4_WARPS;
-            if (Dd + 1 <= 32) stats5_kernel<4><<<grid, 32 * S4_WARPS, S4_WARPS * stats5_warp_bytes<4>(Dd), st>>>(c->dm, W, c->dCentre.p, list, off + Jm, S.dValid.p, vcnt);
-            else stats5_kernel<5><<<grid, 32 * S4_WARPS, S4_WARPS * stats5_warp_bytes<5>(Dd), st>>>(c->dm, W, c->dCentre.p, list, off + Jm, S.dValid.p, vcnt);
+            if (Dd + 1 <= 32) stats5_kernel<4><<<grid, 32 * S4_WARPS, S4_WARPS * stats5_warp_bytes<4>(Dd), st>>>(c->dm, W, c->dCentre.p, list, off + Jm, S.dValid.p, vcnt, cap);
+            else stats5_kernel<5><<<grid, 32 * S4_WARPS, S4_WARPS * stats5_warp_bytes<5>(Dd), st>>>(c->dm, W, c->dCentre.p, list, off + Jm, S.dValid.p, vcnt, cap);
             c->stats.launches += 3; c->stats.launchesStats += 3;
          } else
             stats3_kernel<<<(unsigned)((w.totalP + ST_WARPS - 1) / ST_WARPS), 32 * ST_WARPS, stats_smem_bytes(c->dm.D), st>>>(c->dm, W);
