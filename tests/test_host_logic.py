@@ -118,3 +118,40 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".c")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_lib" not in txt and "hfb_oracle" not in txt and "libhfboracle" not in txt, f
+
+
+def test_qualifier_description_from_kinds():
+    """Qualifiers.from_kinds mirrors what HParm derives from SOURCEKIND / TARGETKIND (FindSpans, HParm.c:1430-1455;
+    AddQualifiers :1707-1712): static width, which orders to add, which leading columns _Z zero-means."""
+    from htk_b200.flat import Qualifiers
+    q = Qualifiers.from_kinds("MFCC_0", "MFCC_0_D_A_Z", 13)
+    assert (q.num_static, q.del_win, q.acc_win, q.third_win, q.zero_mean_cols, q.vec_size) == (13, 2, 2, 0, 13, 39)
+    q = Qualifiers.from_kinds("MFCC_E", "MFCC_E_D_A_Z", 13, del_win=3, acc_win=1)
+    assert (q.del_win, q.acc_win, q.zero_mean_cols, q.vec_size) == (3, 1, 12, 39)      # the energy is not zero-meaned
+    q = Qualifiers.from_kinds("MFCC", "MFCC_D", 12, simple_diffs=True)
+    assert (q.vec_size, q.simple_diffs, q.zero_mean_cols) == (24, True, 0)
+    q = Qualifiers.from_kinds("MFCC_0_K", "MFCC_0_D_A_T", 13)                          # _K (CRC) is a file property
+    assert q.vec_size == 52
+    for src, tgt in (("MFCC_0", "PLP_0_D"), ("MFCC_0_D", "MFCC_0_D_A"), ("MFCC_0", "MFCC_0_D_N"), ("MFCC_E", "MFCC_0_D")):
+        with pytest.raises(ValueError):
+            Qualifiers.from_kinds(src, tgt, 13)
+    c = Qualifiers(13, 2, 2, 0, True, 13).c_struct()
+    assert (c.numStatic, c.delWin, c.accWin, c.thirdWin, c.simpleDiffs, c.zeroMeanCols) == (13, 2, 2, 0, 1, 13)
+
+
+def test_qualifier_oracle_properties():
+    """Size-independent properties of the regression restatement (oracle/hparm_oracle.py): a constant signal has zero
+    differentials, a ramp has slope-1 deltas away from the ends and clamped ones at the ends (first / last frame
+    replicated, HSigP.c:844-845), zero-meaning removes the column mean."""
+    from oracle import hparm_oracle as H
+    T = 50
+    const = np.full((T, 3), 2.5, np.float32)
+    out = H.expand(const, 2, 2)
+    assert np.all(out[:, 3:] == 0)
+    ramp = np.arange(T, dtype=np.float32)[:, None].repeat(2, 1)
+    d = H.regress(ramp, 2, False)
+    assert np.allclose(d[2:-2], 1.0) and np.allclose(d[0], (1 * 1 + 2 * 2) / 10.0) and np.allclose(d[-1], d[0])
+    assert np.allclose(H.regress(ramp, 2, True)[2:-2], 1.0)
+    x = np.random.default_rng(0).standard_normal((T, 4)).astype(np.float32) + 7
+    z = H.expand(x, 0, 0, 0, False, 3)
+    assert np.all(np.abs(z[:, :3].mean(0)) < 1e-6) and np.array_equal(z[:, 3], x[:, 3])
