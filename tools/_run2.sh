@@ -1,3 +1,5 @@
-timeout 900 python bench.py > gpurun_out/bench_r1_final.json 2> gpurun_out/bench_r1_final.err
-python -c "import json; d=json.loads(open('gpurun_out/bench_r1_final.json').read().strip().splitlines()[-1]); print(d['value']/1e6, d['e2e']['value']/1e6, d['roofline']['frac'], d['roofline']['frac_of_peak_over_3'], d['cpu_baseline']['value'], d['clocks'], d['gpu_launches'], d['kernels_ms_per_step'], d['rooflines']['recursions']['frac'])"
-for w in cfg4; do timeout 600 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$w', d['value']/1e6, d['e2e']['value']/1e6, d['kernels_ms_per_step'])"; done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/r1z_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/r1z_launch_bench.log 2>&1
+for k in gmm_tc2 stats5 stats_pre beta_l2r_warp alpha_l2r; do
+timeout 200 ncu --set full --import-source on --clock-control none -k regex:${k}_kernel -s 3 -c 1 -o gpurun_out/r1z_$k -f python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/r1z_ncu_$k.log 2>&1
+done
+ls gpurun_out/r1z_* | wc -l
