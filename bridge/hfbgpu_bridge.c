@@ -65,6 +65,7 @@ static struct {
    int nHmm, nSte, nMp, nMean, nVar, nTr;
    /* totals */
    long nOk, nSkipped;
+   int twoData;                          /* HERest -r */
 } B;
 
 /* Two pending batches: while the library works on one (hfbgpu_submit is asynchronous), HERest's own
@@ -72,6 +73,7 @@ static struct {
    memory (hfbgpu_host_alloc) so that the upload is an asynchronous DMA. */
 typedef struct {
    float *feat; long featCap, nFrames;
+   float *feat2; long feat2Cap;          /* single-pass retraining (-r): the second parameterisation, HFB.c:445 */
    int64_t *frameOff; int32_t *labOff, *lab; int nUtt, labCap, nLab;
    char **names;
    hfb_utt_result *res;
@@ -281,6 +283,16 @@ static void Flush(void)
    p->frameOff[p->nUtt] = p->nFrames; p->labOff[p->nUtt] = p->nLab;
    b.numUtt = p->nUtt; b.frameOff = p->frameOff; b.feat = p->feat; b.labOff = p->labOff; b.lab = p->lab;
    p->res = (hfb_utt_result *)calloc(p->nUtt, sizeof(hfb_utt_result));
+   if (B.twoData) {
+      /* -r: alignment on the first file of each pair, mean / variance sums from the second (HFB.c:1603-1611);
+         the library's entry for it is blocking, so the batch is completed and reported right away */
+      rc = hfbgpu_accumulate_retrain(B.ctx, &b, p->feat2, p->res, NULL, 0);
+      if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_accumulate_retrain failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
+      p->inflight = 1;
+      cur ^= 1;
+      Drain();
+      return;
+   }
    rc = hfbgpu_submit(B.ctx, &b, p->res, NULL, 0);
    if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_submit failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
    p->inflight = 1;
@@ -296,7 +308,7 @@ Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
    LLink lab;
    Pending *p = &P[cur];
    int q, t, k, T = utt->T, Q = utt->Q, D = B.D;
-   if (utt->twoDataFiles) HError(7399, "hfbgpu bridge: single-pass retraining is not accelerated");
+   B.twoData = utt->twoDataFiles ? 1 : 0;
    if (!p->frameOff) {
       p->frameOff = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (B.batchUtts + 2));
       p->labOff = (int32_t *)xrealloc(NULL, sizeof(int32_t) * (B.batchUtts + 2));
@@ -308,6 +320,13 @@ Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
       if (!nf) HError(7399, "hfbgpu bridge: out of pinned host memory");
       if (p->feat) { memcpy(nf, p->feat, sizeof(float) * (size_t)p->nFrames * D); hfbgpu_host_free(p->feat); }
       p->feat = nf; p->featCap = ncap;
+   }
+   if (B.twoData && p->nFrames + T > p->feat2Cap) {
+      long ncap = (p->nFrames + T) * 2 + 1024;
+      float *nf = (float *)hfbgpu_host_alloc(sizeof(float) * (size_t)ncap * D);
+      if (!nf) HError(7399, "hfbgpu bridge: out of pinned host memory");
+      if (p->feat2) { memcpy(nf, p->feat2, sizeof(float) * (size_t)p->nFrames * D); hfbgpu_host_free(p->feat2); }
+      p->feat2 = nf; p->feat2Cap = ncap;
    }
    if (p->nLab + Q > p->labCap) {
       p->labCap = (p->nLab + Q) * 2 + 1024;
@@ -327,6 +346,10 @@ Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
    for (t = 0; t < T; t++) {
       ReadAsTable(utt->pbuf, t, &utt->ot);
       for (k = 1; k <= D; k++) p->feat[(size_t)(p->nFrames + t) * D + k - 1] = utt->ot.fv[1][k];
+      if (B.twoData) {                                      /* HFB.c:445 */
+         ReadAsTable(utt->pbuf2, t, &utt->ot2);
+         for (k = 1; k <= D; k++) p->feat2[(size_t)(p->nFrames + t) * D + k - 1] = utt->ot2.fv[1][k];
+      }
    }
    p->names[p->nUtt] = strdup(datafn);
    p->nFrames += T; p->nLab += Q; p->nUtt++;

@@ -274,6 +274,18 @@ def test_single_pass_retraining_matches_stock_herest(tmp_path):
     _run([HEREST, "-r", "-T", "1", "-u", "tmvw", "-p", "1", "-H", "mmf", "-I", "labs.mlf", "-S", "scp2",
           "-M", "accA", "list"], tmp)
     a, prA, tA = htkio.read_acc_dump(os.path.join(tmp, "accA", "HER1.acc"), hs2, fm)
+    if os.path.exists(HEREST_GPU):
+        # the same command line through the bridge (`HERest_gpu -r`: both files of every pair buffered, batches of 3)
+        os.makedirs(os.path.join(tmp, "accB"))
+        env = dict(os.environ, HFBGPU_BATCH_UTTS="3")
+        pr = subprocess.run([HEREST_GPU, "-r", "-T", "1", "-u", "tmvw", "-p", "1", "-H", "mmf", "-I", "labs.mlf", "-S", "scp2",
+                             "-M", "accB", "list"], cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert pr.returncode == 0, pr.stdout[-3000:]
+        g, prG, tG = htkio.read_acc_dump(os.path.join(tmp, "accB", "HER1.acc"), hs2, fm)
+        assert tG == tA and abs(prG - prA) <= 1e-6 * abs(prA)
+        eg = acc_errors(g, a, fm)
+        eg.pop("totalPr"); eg.pop("totalT")
+        assert max(eg.values()) < 1e-4, eg
     import re
     mlf = open(os.path.join(tmp, "labs.mlf")).read()
     labs = []

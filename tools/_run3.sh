@@ -1,2 +1,1 @@
-timeout 600 python -m pytest tests/test_multi_gpu.py -m gpu -q 2>&1 | tail -2
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('2gpu', d['value']/1e6, d['e2e']['value']/1e6, d['ms_per_step'])"
+timeout 200 python -m pytest tests/test_herest_dropin.py -m gpu -q 2>&1 | tail -12
