@@ -61,9 +61,54 @@ def read_peaks():
     return dict(hbm=6650.0, tensor=1400.0, tensor_burst=1590.0, src="fallback")
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE gmm_tc2_kernel launch (1024 utterances) from the
-# `ncu --set full` capture of the same command, profiles/r1k_gmm_tc2_raw.txt: 1.121 GB + 1.256 GB
-GMM_TRAFFIC_BYTES = {"cfg3": 2.188e9}
+def gmm_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the tensor-core GMM kernel (cfg3, 1024 utterances)
+    from the newest `ncu --set full` summary committed under profiles/ (tools/export_profiles.sh writes them);
+    returns (bytes, file name) or (None, None)."""
+    import glob
+    import re
+    best = None
+    for f in glob.glob(os.path.join(ROOT, "profiles", "*_gmm_tc*_raw.txt")):
+        m = re.match(r"r(\d+)([a-z]*)_", os.path.basename(f))
+        key = (int(m.group(1)), m.group(2)) if m else (0, "")
+        if best is None or key > best[0]:
+            best = (key, f)
+    if best is None:
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for line in open(best[1]):
+        c = line.split()
+        if len(c) >= 3 and c[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and c[2] in unit:
+            tot += float(c[1]) * unit[c[2]]
+    return (tot or None), os.path.basename(best[1])
+
+
+def distinct_states_in_beam(fm, lab, Q, T, qLo, qHi):
+    """sum over frames of E_beta(t) = the number of DISTINCT tied states among the models inside the final
+    beta beam qLo[t]..qHi[t] (1-based, as the library returns them) -- the (frame, state) pairs the reference's
+    Setotprob / ShStrP evaluates once each (HFB.c:1014-1016, :910-912).  lab[n][Q] physical HMM per label (standard
+    3-emitting-state sets), beams flattened over the n utterances of T frames."""
+    n = lab.shape[0]
+    states = fm.hmmState.reshape(fm.P, 3)[lab].reshape(n, 3 * Q)
+    total = 0
+    ar = np.arange(3 * Q)
+    for u in range(n):
+        st = states[u]
+        # prev[i] = previous position with the same tied state, or -1: position i counts in a window [a, b) iff prev[i] < a
+        order = np.argsort(st, kind="stable")
+        prev = np.full(3 * Q, -1, np.int64)
+        same = st[order][1:] == st[order][:-1]
+        prev[order[1:][same]] = order[:-1][same]
+        lo = 3 * (qLo[u * T:(u + 1) * T].astype(np.int64) - 1)
+        hi = 3 * qHi[u * T:(u + 1) * T].astype(np.int64)
+        ok = hi > lo
+        # count of i in [lo, hi) with prev[i] < lo, per frame: group frames by lo (few distinct values per utterance)
+        for a in np.unique(lo[ok]):
+            sel = ok & (lo == a)
+            c = np.concatenate([[0], np.cumsum((prev < a) & (ar >= a))])
+            total += int(c[hi[sel]].sum())
+    return total
 
 
 def measure_tf32(dev):
@@ -259,6 +304,185 @@ def cpu_port(fm, cfg, prune, cores, budget_s=20.0):
 
 # ------------------------------------------------------------------------------------ main
 
+def run_workload(name, args, rank, world, local_rank, dev, K, full):
+    """Times one workload on this rank's GPU (all ranks call it together).  `full`: also the per-kernel breakdown, the
+    rooflines and the work counts (the headline workload); otherwise only value / e2e (the sub-records of the other
+    BASELINE configs).  Returns the record on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    from htk_b200.estep import ForwardBackward
+    cfg = dict(WORKLOADS[name])
+    if args.prune == "off":
+        prune = None
+    elif args.prune:
+        prune = tuple(float(x) for x in args.prune.split(","))
+    else:
+        prune = cfg.get("prune")
+    T, Q = cfg["T"], cfg["Q"]
+    n_utts = args.utts or (1024 if T <= 1000 else 64)
+    fm = make_model(cfg)
+    fb = ForwardBackward(fm, prune=prune, device=local_rank, gmm_kernel=args.gmm_kernel)
+    stream = torch.cuda.current_stream()
+    fb.set_stream(stream.cuda_stream)
+    batch, dfeat = make_batch(fm, cfg, n_utts, seed=1000 + rank, device=dev)
+    acc_t = fb.acc_tensor() if world > 1 else None
+    acc_host = np.zeros(fm.layout.count, np.float64)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def submit_device():
+        return fb.Submit(batch, device_feat_ptr=dfeat.data_ptr())
+
+    def submit_host():
+        return fb.Submit(batch)
+
+    def timed(submit, K, download):
+        """K steps through the asynchronous form of the public call (hfbgpu_submit / hfbgpu_wait): batch i+1 is enqueued
+        while batch i runs, every step's per-utterance results are read back inside the timed region, and the pass ends
+        with the accumulator all-reduce (N > 1) and -- `download`, the end-to-end leg -- the copy of the accumulators to
+        the host ("upload + kernels + allreduce + download of accumulators")."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fb.ZeroAccs()
+        e0.record(stream)
+        tickets = [submit() for _ in range(K)]
+        fb.Wait()
+        ok = sum(T for tk in tickets for r in tk.results() if r.status == 0)
+        if world > 1:
+            dist.all_reduce(acc_t)            # the per-pass exchange (replaces the `-p 0` file merge)
+        if download:
+            fb.lib.hfbgpu_get_accs(fb.h, acc_host.ctypes.data)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, float(ok)], dtype=torch.float64, device=dev)
+        if world > 1:
+            tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            return float(tm[0]), float(ts[1])
+        return float(t[0]), float(t[1])
+
+    # warm-up through the same (asynchronous) paths that are timed; at least four submits of each kind so that every
+    # one of the library's four wave slots has grown its workspace AND its host-feature staging buffer (a first-use
+    # cudaMalloc inside the timed region serialises the whole device)
+    for _ in range(max(4, args.warmup)):
+        submit_device()
+    fb.Wait()
+    for _ in range(max(4, args.warmup)):
+        submit_host()
+    fb.Wait()
+    if world > 1:                                 # ... including the collective (NCCL sets its channels up on first use)
+        for _ in range(2):
+            dist.all_reduce(acc_t)
+        torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if (rank == 0 and full) else None
+    fb.reset_stats()
+    ms_dev, frames_dev = timed(submit_device, K, download=False)
+    st = fb.stats()
+    launches = int(st.launches)
+    ms_host, frames_host = timed(submit_host, K, download=True)
+    clocks = sampler.stop() if sampler else None
+    value = frames_dev / (ms_dev * 1e-3)
+    e2e = frames_host / (ms_host * 1e-3)
+    acc_bytes = int(fm.layout.count * 8)
+    rec = {"workload": "%s: %s; %d utterances x %d frames x %d labels per step per GPU; pruning %s; minFrwdP 10; -u tmvw"
+                       % (name, cfg["desc"], n_utts, T, Q, ("-t %g %g %g" % prune) if prune else "off (HERest default)"),
+           "value": value, "unit": "frames/s", "ms_per_step": ms_dev / K, "steps": K,
+           "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(n_utts * T * fm.D * 4),
+                   "d2h_bytes_per_step": int(n_utts * 24 + acc_bytes / K), "ms_per_step": ms_host / K,
+                   "accumulator_download_bytes_per_pass": acc_bytes},
+           "gpu_launches": launches, "allreduce_bytes_per_pass": acc_bytes if world > 1 else 0}
+    if not full:
+        # per-kernel times of the sub-record (one serialised pass)
+        fb.set_timing(True)
+        fb.FBFile(batch, device_feat_ptr=dfeat.data_ptr())
+        fb.reset_stats()
+        fb.FBFile(batch, device_feat_ptr=dfeat.data_ptr())
+        sk = fb.stats(); fb.set_timing(False)
+        rec["kernels_ms_per_step"] = {"gmm": sk.msGmm, "beta": sk.msBeta, "alpha": sk.msAlpha, "stats": sk.msStats}
+        fb.close()
+        del dfeat, batch
+        torch.cuda.empty_cache()
+        return rec if rank == 0 else None
+
+    # kernel breakdown + roofline of the dominant kernel (CUDA events on the launching stream)
+    fb.set_timing(True)
+    fb.FBFile(batch, device_feat_ptr=dfeat.data_ptr())   # timing mode serialises: let its buffers grow untimed
+    fb.reset_stats()
+    for _ in range(K):
+        fb.FBFile(batch, device_feat_ptr=dfeat.data_ptr())
+    sk = fb.stats(); fb.set_timing(False)
+    res, beams = fb.FBFile(batch, want_beams=True, device_feat_ptr=dfeat.data_ptr())
+    beta_cells = int(np.sum(beams.qHi.astype(np.int64) - beams.qLo + 1))
+    alpha_cells = int(np.sum((beams.eq.astype(np.int64) - beams.sq + 1)[beams.sq > 0]))
+    out = None
+    if rank == 0:
+        peaks = read_peaks()
+        tf32 = measure_tf32(dev) if world == 1 else None
+        kms = {"gmm": sk.msGmm / K, "beta": sk.msBeta / K, "alpha": sk.msAlpha / K, "stats": sk.msStats / K}
+        ms_expand = sk.msExpand / K                               # feature expansion, part of "gmm"
+        ms_gemm = kms["gmm"] - ms_expand                          # the tensor-core kernel alone
+        M = cfg["M"]
+        lab = np.asarray(batch.lab).reshape(n_utts, Q)
+        # SURVEY 8d: algorithmic pairs = distinct tied states among the BETA CELLS of each frame (what the reference's
+        # Setotprob evaluates), not every frame x every state of the utterance
+        pairs = float(distinct_states_in_beam(fm, lab, Q, T, beams.qLo, beams.qHi))
+        pairs_computed = sk.gmmPairs / K                         # what the kernel evaluated (tiles issued)
+        gmm_flop = pairs * M * ALG_FLOP_PER_GAUSS_FRAME(fm.D)
+        dom = max(kms, key=kms.get)
+        traffic, traffic_src = gmm_traffic_bytes()
+        # ---- one roofline per kernel family (SURVEY.md 8d says which resource bounds which); `roofline` = the dominant one
+        rl = {}
+        if ms_gemm > 0:
+            ach = gmm_flop / (ms_gemm * 1e-3) / 1e12
+            rl["gmm"] = {"bound": "tensor", "kernel": "gmm_tc2_kernel (tcgen05 cta_group::2, 3xFP16 split, FP32 accumulate in TMEM)",
+                         "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"],
+                         "traffic": traffic if (name == "cfg3" and n_utts == 1024) else None, "traffic_source": traffic_src,
+                         "ms_per_launch": ms_gemm, "launches_per_step": 1,
+                         "frac_of_peak_over_3": ach / (peaks["tensor"] / 3.0),
+                         "frac_of_burst_peak": ach / peaks["tensor_burst"],
+                         "tf32_tflops_measured": tf32,
+                         "pairs_algorithmic": pairs, "pairs_computed": pairs_computed,
+                         "note": "algorithmic FLOP = sum over frames of the DISTINCT tied states among the beta cells x M x 2(2D+1) "
+                                 "(SURVEY 8d; counted on the host from the returned beams), one launch per step; pairs_computed = "
+                                 "what the kernel evaluated; peak = bf16 %s (%s); every product costs 3 FP16 MMAs (hi*hi + hi*lo "
+                                 "+ lo*hi), so the ceiling of this kernel is peak / 3 -- frac_of_peak_over_3" % ("sustained", peaks["src"])}
+        st_flop = alpha_cells * 3 * M * 2 * 2 * fm.D            # SURVEY 8d: F_acc = sum over alpha cells (N-2) M 2 2D
+        if kms["stats"] > 0:
+            ach = st_flop / (kms["stats"] * 1e-3) / 1e12
+            rl["stats"] = {"bound": "tensor", "kernel": "stats_pre_kernel + stats5_kernel + statpos_* sort",
+                           "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": None,
+                           "ms_per_launch": kms["stats"], "launches_per_step": 5,
+                           "note": "SURVEY 8d: F_acc = alpha cells x (N-2) x M x 4D algorithmic FLOP = %.1f GFLOP per step (the "
+                                   "occupancy matrix is ~2 %% dense); bound by the gather of observation rows and memory latency, "
+                                   "not by the tensor pipe (profiles/README.md)" % (st_flop / 1e9)}
+        by = beta_cells * 104.0 + n_utts * T * fm.D * 4 * 2
+        ms = kms["beta"] + kms["alpha"]
+        if ms > 0:
+            ach = by / (ms * 1e-3) / 1e9
+            rl["recursions"] = {"bound": "hbm", "kernel": "beta_l2r_warp_kernel + alpha_l2r_kernel", "achieved": ach, "peak": peaks["hbm"],
+                                "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None, "ms_per_launch": ms, "launches_per_step": 2,
+                                "note": "algorithmic bytes = 104 B per beta cell + features both passes (SURVEY 8d); peak = %s copy "
+                                        "bandwidth; latency-bound by the T-step chain (stall breakdown in profiles/README.md)" % peaks["src"]}
+        key = {"gmm": "gmm", "stats": "stats", "beta": "recursions", "alpha": "recursions"}[dom]
+        roof = dict(rl.get(key) or next(iter(rl.values())))
+        roof["dominant_of"] = {k: round(v, 3) for k, v in kms.items()}
+        out = dict(rec)
+        out.update({"clocks": clocks, "roofline": roof, "rooflines": rl,
+                    "kernels_ms_per_step": dict(kms, gmm_expand=ms_expand),
+                    "work_per_step": {"frames": n_utts * T, "gmm_state_frame_pairs": pairs,
+                                      "gmm_state_frame_pairs_computed": pairs_computed, "beta_cells": beta_cells,
+                                      "alpha_cells": alpha_cells, "gmm_algorithmic_gflop": gmm_flop / 1e9},
+                    "_fm": fm, "_cfg": cfg, "_prune": prune})
+    fb.close()
+    del dfeat, batch
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -266,6 +490,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--also", default="cfg2,cfg4,cfg5",
+                    help="other BASELINE configs measured after the headline one, few steps each, as sub-records under "
+                         "`workloads` ('' = none)")
+    ap.add_argument("--also-steps", type=int, default=5)
     ap.add_argument("--utts", type=int, default=0, help="utterances per step per GPU (0 = workload default)")
     ap.add_argument("--prune", default="", help="'off' or 'init,inc,lim' (default: workload's; HERest default is off)")
     ap.add_argument("--gmm-kernel", type=int, default=0)
@@ -297,10 +525,13 @@ def main():
         K = max(1, args.steps)
         vals, secs = [], []
         base = None
+        # every step is a fresh bounded sample; together they give each process ~3 minutes of work (BASELINE.md asks for
+        # long per-process runs; the default driver call must still end within a few minutes)
+        budget = max(8.0, 170.0 / (K + 1))
         for i in range(args.warmup + K):
             if i < args.warmup and i > 0:
                 continue                      # one warm-up sample is enough to page the binary in
-            r = cpu_reference(fm, cfg, prune, cores, budget_s=max(6.0, 90.0 / (K + 1)), want_merge=(i == args.warmup + K - 1))
+            r = cpu_reference(fm, cfg, prune, cores, budget_s=budget, want_merge=(i == args.warmup + K - 1))
             base = r
             if i >= args.warmup:
                 vals.append(r["value"]); secs.append(r.get("sample_s") or 0.0)
@@ -311,7 +542,8 @@ def main():
                "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic", "config": config,
                "cpu_baseline": {"value": v, "unit": "frames/s", "cores": base["cores"], "kind": base["kind"],
-                                "sample": base["sample"]},
+                                "sample": base["sample"] + "; %d such samples, %.0f s of work per process in total, "
+                                          "min / max sample rate %.0f / %.0f frames/s" % (len(vals), float(np.sum(secs)), min(vals), max(vals))},
                "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(out))
         return
@@ -322,153 +554,37 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    from htk_b200.estep import ForwardBackward
-
-    fm = make_model(cfg)
-    fb = ForwardBackward(fm, prune=prune, device=local_rank, gmm_kernel=args.gmm_kernel)
-    stream = torch.cuda.current_stream()
-    fb.set_stream(stream.cuda_stream)
-    batch, dfeat = make_batch(fm, cfg, n_utts, seed=1000 + rank, device=dev)
-    acc_t = fb.acc_tensor() if world > 1 else None
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def submit_device():
-        return fb.Submit(batch, device_feat_ptr=dfeat.data_ptr())
-
-    def submit_host():
-        return fb.Submit(batch)
-
-    def timed(submit, K):
-        """K steps through the asynchronous form of the public call (hfbgpu_submit / hfbgpu_wait):
-        batch i+1 is enqueued while batch i runs, every step's per-utterance results are read back
-        inside the timed region, and the pass ends with the accumulator all-reduce."""
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        fb.ZeroAccs()
-        e0.record(stream)
-        tickets = [submit() for _ in range(K)]
-        fb.Wait()
-        ok = sum(T for tk in tickets for r in tk.results() if r.status == 0)
-        if world > 1:
-            dist.all_reduce(acc_t)            # the per-pass exchange (replaces the `-p 0` file merge)
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms, float(ok)], dtype=torch.float64, device=dev)
-        if world > 1:
-            tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-            return float(tm[0]), float(ts[1])
-        return float(t[0]), float(t[1])
-
-    # warm-up through the same (asynchronous) paths that are timed; at least four submits of each kind so that every
-    # one of the library's four wave slots has grown its workspace AND its host-feature staging buffer (a first-use
-    # cudaMalloc inside the timed region serialises the whole device)
-    for _ in range(max(4, args.warmup)):
-        submit_device()
-    fb.Wait()
-    for _ in range(max(4, args.warmup)):
-        submit_host()
-    fb.Wait()
-    if world > 1:                                 # ... including the collective (NCCL sets its channels up on first use)
-        for _ in range(2):
-            dist.all_reduce(acc_t)
-        torch.cuda.synchronize()
     K = max(1, args.steps)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    fb.reset_stats()
-    ms_dev, frames_dev = timed(submit_device, K)
-    st = fb.stats()
-    launches = int(st.launches)
-    ms_host, frames_host = timed(submit_host, K)
-    clocks = sampler.stop() if sampler else None
-
-    # kernel breakdown + roofline of the dominant kernel (CUDA events on the launching stream)
-    fb.set_timing(True)
-    fb.FBFile(batch, device_feat_ptr=dfeat.data_ptr())   # timing mode serialises: let its buffers grow untimed
-    fb.reset_stats()
-    for _ in range(K):
-        fb.FBFile(batch, device_feat_ptr=dfeat.data_ptr())
-    sk = fb.stats(); fb.set_timing(False)
-    res, beams = fb.FBFile(batch, want_beams=True, device_feat_ptr=dfeat.data_ptr())
-    beta_cells = int(np.sum(beams.qHi.astype(np.int64) - beams.qLo + 1))
-    alpha_cells = int(np.sum((beams.eq.astype(np.int64) - beams.sq + 1)[beams.sq > 0]))
+    main_rec = run_workload(args.workload, args, rank, world, local_rank, dev, K, full=True)
+    also = {}
+    if not args.utts and not args.prune:
+        for name in [w for w in args.also.split(",") if w and w != args.workload]:
+            r = run_workload(name, args, rank, world, local_rank, dev, max(1, args.also_steps), full=False)
+            if rank == 0:
+                also[name] = r
+    # the exchange itself against the reference's multi-process merge (untimed)
+    from htk_b200.dist import merge_parity
+    try:
+        mp = merge_parity(local_rank, rank, world)
+    except Exception as e:                                    # never let the check kill the bench line
+        mp = {"ok": False, "error": repr(e)}
 
     if rank == 0:
-        peaks = read_peaks()
-        tf32 = measure_tf32(dev) if world == 1 else None
-        kms = {"gmm": sk.msGmm / K, "beta": sk.msBeta / K, "alpha": sk.msAlpha / K, "stats": sk.msStats / K}
-        ms_expand = sk.msExpand / K                               # feature expansion, part of "gmm"
-        ms_gemm = kms["gmm"] - ms_expand                          # the tensor-core kernel alone
-        M = cfg["M"]
-        pairs = sk.gmmPairs / K                                  # (frame, distinct tied state) pairs per step
-        gmm_flop = pairs * M * ALG_FLOP_PER_GAUSS_FRAME(fm.D)
-        dom = max(kms, key=kms.get)
-        # ---- one roofline per kernel family (SURVEY.md 8d says which resource bounds which); `roofline` = the dominant one
-        rl = {}
-        if ms_gemm > 0 and M > 1:
-            ach = gmm_flop / (ms_gemm * 1e-3) / 1e12
-            rl["gmm"] = {"bound": "tensor", "kernel": "gmm_tc2_kernel (tcgen05 cta_group::2, 3xFP16 split, FP32 accumulate in TMEM)",
-                         "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"],
-                         "traffic": GMM_TRAFFIC_BYTES.get(args.workload) if n_utts == 1024 else None,
-                         "ms_per_launch": ms_gemm, "launches_per_step": 1,
-                         "frac_of_peak_over_3": ach / (peaks["tensor"] / 3.0),
-                         "tf32_tflops_measured": tf32,
-                         "note": "algorithmic FLOP = (frame, distinct state) pairs x M x 2(2D+1) (SURVEY 8d), one launch per step; "
-                                 "peak = bf16 %s (%s); every product costs 3 FP16 MMAs (hi*hi + hi*lo + lo*hi), so the ceiling of "
-                                 "this kernel is peak / 3 -- frac_of_peak_over_3.  ncu: 59 %% tensor-pipe active, 67 %% XU (ex2 of "
-                                 "the fused log-sum-exp), SM clock 1.62 GHz under this load" % ("sustained", peaks["src"])}
-        elif kms["gmm"] > 0:
-            ach = gmm_flop / (kms["gmm"] * 1e-3) / 1e12
-            rl["gmm"] = {"bound": "tensor", "kernel": "gmm_fp32_kernel (single-Gaussian set: FP32 pipe, no tensor-core path)",
-                         "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": None,
-                         "ms_per_launch": kms["gmm"], "launches_per_step": 1,
-                         "note": "SURVEY 8d classes the output probabilities as tensor-pipe work; with one Gaussian per state there "
-                                 "is no mixture contraction worth a tcgen05 tile and the direct FP32 kernel is used"}
-        st_flop = alpha_cells * 3 * M * 2 * 2 * fm.D            # SURVEY 8d: F_acc = sum over alpha cells (N-2) M 2 2D
-        if kms["stats"] > 0:
-            ach = st_flop / (kms["stats"] * 1e-3) / 1e12
-            rl["stats"] = {"bound": "tensor", "kernel": "stats_pre_kernel (model-major occupancies + transitions) + stats5_kernel (state-major, packed-FP32 posteriors, mma.sync 3xTF32 sums) + statpos_* sort",
-                           "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": None,
-                           "ms_per_launch": kms["stats"], "launches_per_step": 5,
-                           "note": "SURVEY 8d classes the statistics as a tensor-pipe contraction with F_acc = alpha cells x (N-2) x M x 4D "
-                                   "algorithmic FLOP; the occupancy matrix is ~2 %% dense (alpha_cells / frames ~ 1.7 models per frame), so "
-                                   "that is %.1f GFLOP per step and the kernels are bound by gathering the observation rows, recomputing the "
-                                   "component posteriors (FFMA2 pairs) and memory latency at 16 warps/SM, not by the tensor pipe "
-                                   "(profiles/README.md)" % (st_flop / 1e9)}
-        by = beta_cells * 104.0 + n_utts * T * fm.D * 4 * 2
-        ms = kms["beta"] + kms["alpha"]
-        if ms > 0:
-            ach = by / (ms * 1e-3) / 1e9
-            rl["recursions"] = {"bound": "hbm", "kernel": "beta_l2r_warp_kernel + alpha_l2r_kernel", "achieved": ach, "peak": peaks["hbm"],
-                                "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None, "ms_per_launch": ms, "launches_per_step": 2,
-                                "note": "algorithmic bytes = 104 B per beta cell + features both passes (SURVEY 8d); peak = %s copy "
-                                        "bandwidth; latency-bound by the T-step chain (stall breakdown in profiles/README.md)" % peaks["src"]}
-        key = {"gmm": "gmm", "stats": "stats", "beta": "recursions", "alpha": "recursions"}[dom]
-        roof = dict(rl.get(key) or next(iter(rl.values())))
-        roof["dominant_of"] = {k: round(v, 3) for k, v in kms.items()}
+        fm, cfg2, prune2 = main_rec.pop("_fm"), main_rec.pop("_cfg"), main_rec.pop("_prune")
         cpu = None
         if world == 1 and not args.no_cpu:
             try:
-                cpu = cpu_reference(fm, cfg, prune, cores, budget_s=args.cpu_budget)
+                cpu = cpu_reference(fm, cfg2, prune2, cores, budget_s=args.cpu_budget)
             except Exception as e:                                # never let the baseline leg kill the GPU line
                 cpu = {"value": None, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": "failed: %r" % (e,)}
-        value = frames_dev / (ms_dev * 1e-3)
-        e2e = frames_host / (ms_host * 1e-3)
-        out = {"metric": "HERest E-step frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
-               "warmup": max(3, args.warmup), "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
+        out = {"metric": "HERest E-step frames/sec", "value": main_rec["value"], "unit": "frames/s", "n_gpus": world, "steps": K,
+               "warmup": max(4, args.warmup), "ms_per_step": main_rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f16x3 split GMM with f32 accumulate / f64 recursions+accumulators", "data": "synthetic",
-               "config": config, "clocks": clocks,
-               "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(n_utts * T * fm.D * 4),
-                       "d2h_bytes_per_step": int(n_utts * 24), "ms_per_step": ms_host / K},
-               "gpu_launches": launches, "roofline": roof, "rooflines": rl, "cpu_baseline": cpu,
-               "kernels_ms_per_step": dict(kms, gmm_expand=ms_expand),
-               "work_per_step": {"frames": n_utts * T, "gmm_state_frame_pairs": pairs, "beta_cells": beta_cells,
-                                 "alpha_cells": alpha_cells, "gmm_algorithmic_gflop": gmm_flop / 1e9}}
+               "config": config, "clocks": main_rec["clocks"], "e2e": main_rec["e2e"],
+               "gpu_launches": main_rec["gpu_launches"], "roofline": main_rec["roofline"], "rooflines": main_rec["rooflines"],
+               "cpu_baseline": cpu, "kernels_ms_per_step": main_rec["kernels_ms_per_step"],
+               "work_per_step": main_rec["work_per_step"], "allreduce_bytes_per_pass": main_rec["allreduce_bytes_per_pass"],
+               "allreduce_parity": mp, "workloads": also}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

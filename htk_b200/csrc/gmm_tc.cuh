@@ -66,13 +66,15 @@ struct GmmTcModel {
 
 struct GmmTcWork {             // per-stream expanded feature operand (floats: TF32 split; halfs: FP16 split)
    float *dAhi = nullptr, *dAlo = nullptr;
+   unsigned char *dFlag = nullptr;   // [frames] 1 = this frame's row of b is recomputed in FP32 (gmm_fixup_kernel)
    size_t aCapFrames = 0;
    bool f16Init = false;       // constant / padding columns of the FP16 layout are in place
    void release()
    {
       if (dAhi) cudaFree(dAhi);
       if (dAlo) cudaFree(dAlo);
-      dAhi = dAlo = nullptr; aCapFrames = 0; f16Init = false;
+      if (dFlag) cudaFree(dFlag);
+      dAhi = dAlo = nullptr; dFlag = nullptr; aCapFrames = 0; f16Init = false;
    }
 };
 #define TC_KH 128           // expanded K of the FP16 operands: 2 swizzle atoms of 64 halfs
@@ -207,11 +209,17 @@ gmm_tc_init_f16_kernel(int D, long long nRows, __half *__restrict__ Ahi, __half 
 // the used part of every row ([1 | x'^2 | x' | 1 | 0..] hi and lo; the columns past it stay as gmm_tc_init_f16_kernel
 // left them)
 #define TC_XF_FR 32
+#define TC_FAR 64.f         // scaled |x - o| beyond which a frame goes to the FP32 fix-up
+#define TC_DEAD_BELOW (-30000.f)   // FP16 path: a state whose best component is below this goes to the FP32 fix-up
 __global__ void __launch_bounds__(256)
 gmm_tc_expand_f16_kernel(const float *__restrict__ feat, const float *__restrict__ off, const float *__restrict__ scale,
-                         int D, long long nFrames, __half *__restrict__ Ahi, __half *__restrict__ Alo)
+                         int D, long long nFrames, __half *__restrict__ Ahi, __half *__restrict__ Alo,
+                         unsigned char *__restrict__ flag)
 {
    __shared__ __align__(16) __half sh[2][TC_XF_FR][TC_KH];
+   __shared__ int far[TC_XF_FR];
+   if (threadIdx.x < TC_XF_FR) far[threadIdx.x] = 0;
+   __syncthreads();
    const long long f0 = (long long)blockIdx.x * TC_XF_FR;
    const int nf = (int)((nFrames - f0 < TC_XF_FR) ? nFrames - f0 : TC_XF_FR);
    const int nk8 = (2 * D + 2 + 7) >> 3, kUsed = nk8 * 8, nConst = kUsed - 2 * D;   // k = 0 and k = 2D+1 .. kUsed-1
@@ -224,13 +232,18 @@ gmm_tc_expand_f16_kernel(const float *__restrict__ feat, const float *__restrict
    for (int e = threadIdx.x; e < nf * D; e += 256) {
       const int fr = e / D, d = e - fr * D;
       const float x = (src[e] - off[d]) * scale[d];
-      // outliers beyond 255 sigma saturate instead of becoming inf
+      // A frame with a coordinate beyond TC_FAR typical standard deviations from the global mean (or a non-finite one)
+      // leaves the range where the FP16 split is as accurate as the reference's float: its whole row of b is
+      // recomputed by gmm_fixup_kernel in FP32, as IDOutP does (HModel.c:5420-5431).  The clamp only keeps inf / NaN
+      // out of the tensor core; what it produces for such a frame is overwritten.
+      if (!(fabsf(x) <= TC_FAR)) far[fr] = 1;
       const float v1 = fminf(fmaxf(x, -65000.f), 65000.f), v2 = fminf(x * x, 65000.f);
       const __half h1 = __float2half_rn(v1), h2 = __float2half_rn(v2);
       sh[0][fr][1 + d] = h2;     sh[1][fr][1 + d] = __float2half_rn(v2 - __half2float(h2));
       sh[0][fr][1 + D + d] = h1; sh[1][fr][1 + D + d] = __float2half_rn(v1 - __half2float(h1));
    }
    __syncthreads();
+   if (threadIdx.x < nf) flag[f0 + threadIdx.x] = (unsigned char)far[threadIdx.x];
    const int per = nf * nk8;
    for (int e = threadIdx.x; e < 2 * per; e += 256) {
       const int arr = e >= per, r = e - arr * per, fr = r / nk8, c = r - fr * nk8;
@@ -254,6 +267,7 @@ struct TcParams {
    float deadBelow;            // a column maximum below this means "no live component": output log zero
    int dbg;                    // timing experiments only (HFBGPU_TC_DEBUG): 1 = no A_lo x B_hi, 2 = no epilogue math
    long long *trace;           // HFBGPU_TC_TRACE: clock64() timeline of the first pair (tools/tc_trace.py); else null
+   unsigned char *flag;        // FP16 path: per-frame "recompute in FP32" flags (see gmm_fixup_kernel); else null
 };
 #define TC_TRACE_TILES 512
 #define TC_TR(role, tile, slot) do { if (p.trace && pair == 0 && (tile) < TC_TRACE_TILES) \
@@ -769,6 +783,10 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                   if (colEnd % MP == 0) {
                      const int slot = n * SPT + colEnd / MP - 1;
                      float val = (mx < p.deadBelow) ? (float)HFB_LZERO : fmaf(tc_lg2(sum), LN2, mx - C0);
+                     // FP16 operands: "no live component" and "every live component far away" look alike here (dead rows
+                     // carry -60000); the FP32 fix-up decides, so that a far-away state gets its true value like the
+                     // reference's (HModel.c:5420-5431) instead of log zero
+                     if (p.flag && mx < p.deadBelow && t < u.T && slot < u.Jt) p.flag[u.frameBase + t] = 1;
                      if (NOUT > 0) outv[no++] = val;
                      else if (t < u.T && slot < u.J) brow[slot] = val;
                      cmx = -INFINITY; csum = 0.f;
@@ -798,6 +816,60 @@ gmm_tc2_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
    if (warp == 1) {
       tc_fence_after();
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+   }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// FP32 fix-up of the FP16 tensor-core path.  Rows of b flagged by gmm_tc_expand_f16_kernel (a coordinate further
+// than TC_FAR typical standard deviations from the global mean, or not finite) or by the epilogue (a state whose
+// best component came out below TC_DEAD_BELOW) are recomputed the way the reference does: IDOutP per component
+// (HModel.c:5420-5431), log-add over the components with weight > LMINMIX (ShStrP, HFB.c:949-960), log zero
+// only when no component is live.  One CTA per (utterance, 128 frames); it leaves at once when no frame of
+// its block is flagged -- on clean data the kernel costs one byte read per frame.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+gmm_fixup_kernel(DevModel M, Wave W, const int2 *__restrict__ items, const unsigned char *__restrict__ flag)
+{
+   __shared__ float xs[64];
+   __shared__ int list[128];
+   __shared__ int nList;
+   const int2 item = items[blockIdx.x];
+   const UttDesc u = W.utt[item.x];
+   const int t = item.y + (int)threadIdx.x;
+   const int mine = (t < u.T) ? (int)flag[u.frameBase + t] : 0;
+   if (threadIdx.x == 0) nList = 0;
+   if (!__syncthreads_or(mine)) return;
+   if (mine) list[atomicAdd(&nList, 1)] = t;
+   __syncthreads();
+   const int D = M.D, Dp = M.Dp, n = nList;
+   const int *ss = W.slotState + u.slotOff;
+   for (int i = 0; i < n; i++) {
+      const int tt = list[i];
+      if ((int)threadIdx.x < D) xs[threadIdx.x] = W.feat[((size_t)u.featOff + tt) * D + threadIdx.x];
+      __syncthreads();
+      float *brow = W.b + u.bOff + (size_t)tt * u.J;
+      for (int slot = threadIdx.x; slot < u.Jt; slot += 128) {
+         const int st = ss[slot];
+         const int mo = M.stateMixOff[st], Mn = M.stateMixOff[st + 1] - mo;
+         float mx = -INFINITY, sm = 0.f;
+         bool any = false;
+         for (int m = 0; m < Mn; m++) {
+            const float wt = M.mixLogWt[mo + m];
+            if (Mn > 1 && !(wt > LMINMIX_F)) continue;
+            any = true;
+            const int g = M.mixGauss[mo + m];
+            const float *mu = M.mean + (size_t)g * Dp, *iv = M.ivar + (size_t)g * Dp;
+            float a = M.gconst[g];
+            for (int k = 0; k < D; k++) { const float d = xs[k] - __ldg(mu + k); a = fmaf(d * d, __ldg(iv + k), a); }
+            float v = -0.5f * a;
+            if (Mn == 1) { mx = v; sm = 1.f; break; }
+            v += wt;
+            if (v > mx) { sm = sm * expf(mx - v) + 1.f; mx = v; } else sm += expf(v - mx);
+         }
+         brow[slot] = any ? mx + logf(sm) : (float)HFB_LZERO;
+      }
+      __syncthreads();
    }
 }
 
@@ -977,7 +1049,10 @@ static inline int gmm_tc_prepare(GmmTcModel &t, const hfb_model *m, cudaStream_t
       c1 = nLive ? c1 / nLive : 0.0;
       t.C1H = (float)c1;
       std::vector<__half> hh((size_t)t.rows * TC_KH, __float2half_rn(0.f)), hl((size_t)t.rows * TC_KH, __float2half_rn(0.f));
+      bool inRange = true;             // a model whose scaled parameters leave the FP16 range keeps the 3xTF32 kernel
       auto putH = [&](long long r, int k, double v) {
+         if (!(fabs(v) < 30000.0) && k != 2 * D + 1) inRange = false;
+         if (k == 2 * D + 1 && live[r] && !(fabs(v) < 20000.0)) inRange = false;
          float f = (float)v;
          __half h = __float2half_rn(f);
          hh[(size_t)r * TC_KH + k] = h;
@@ -1004,7 +1079,8 @@ static inline int gmm_tc_prepare(GmmTcModel &t, const hfb_model *m, cudaStream_t
          for (long long r = 0; r < t.rows; r++) { hh[(size_t)r * TC_KH] = __float2half_rn(t.C0H); hl[(size_t)r * TC_KH] = __float2half_rn(0.f); }
       }
       size_t hb = hh.size() * sizeof(__half);
-      if (cudaMalloc(&t.dBhiH, hb) == cudaSuccess && cudaMalloc(&t.dBloH, hb) == cudaSuccess &&
+      if (!inRange) { /* stay on the 3xTF32 operands */ }
+      else if (cudaMalloc(&t.dBhiH, hb) == cudaSuccess && cudaMalloc(&t.dBloH, hb) == cudaSuccess &&
           cudaMalloc(&t.dScale, D * sizeof(float)) == cudaSuccess) {
          cudaMemcpyAsync(t.dBhiH, hh.data(), hb, cudaMemcpyHostToDevice, st);
          cudaMemcpyAsync(t.dBloH, hl.data(), hb, cudaMemcpyHostToDevice, st);
@@ -1030,7 +1106,8 @@ static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm
       wk.release();
       size_t cap = need + need / 8;
       if (cudaMalloc(&wk.dAhi, cap * TC_KE * sizeof(float)) != cudaSuccess ||
-          cudaMalloc(&wk.dAlo, cap * TC_KE * sizeof(float)) != cudaSuccess) { cudaGetLastError(); wk.release(); return HFB_ENOMEM; }
+          cudaMalloc(&wk.dAlo, cap * TC_KE * sizeof(float)) != cudaSuccess ||
+          cudaMalloc(&wk.dFlag, cap) != cudaSuccess) { cudaGetLastError(); wk.release(); return HFB_ENOMEM; }
       wk.aCapFrames = cap;
    }
    TcParams p;
@@ -1038,7 +1115,7 @@ static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm
    p.kSteps = (2 * dm.D + 2 + 7) / 8;
    p.deadBelow = -1.0e29f;
    { const char *e = getenv("HFBGPU_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; if (p.dbg & 4) p.kSteps = 12; }
-   p.trace = nullptr;
+   p.trace = nullptr; p.flag = nullptr;
    const char *traceFile = getenv("HFBGPU_TC_TRACE");
    const size_t traceN = (size_t)6 * TC_TRACE_TILES * 16;
    if (traceFile) { cudaMalloc(&p.trace, traceN * sizeof(long long)); cudaMemsetAsync(p.trace, 0, traceN * sizeof(long long), st); }
@@ -1059,12 +1136,13 @@ static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm
          gmm_tc_init_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dm.D, (long long)wk.aCapFrames, ahi, alo);
          wk.f16Init = true;
       }
-      gmm_tc_expand_f16_kernel<<<(unsigned)((waveFrames + TC_XF_FR - 1) / TC_XF_FR), 256, 0, st>>>(W.feat, t.dOffset, t.dScale, dm.D, waveFrames, ahi, alo);
+      gmm_tc_expand_f16_kernel<<<(unsigned)((waveFrames + TC_XF_FR - 1) / TC_XF_FR), 256, 0, st>>>(W.feat, t.dOffset, t.dScale, dm.D, waveFrames, ahi, alo, wk.dFlag);
+      p.flag = wk.dFlag;
       if (afterExpand) cudaEventRecord(afterExpand, st);
       p.items = dItems4; p.nItems = nItems4;            // work items of 4 x 128 frames: two blocks per CTA
       p.C0 = t.C0H - t.C1H;                              // the epilogue subtracts C0 and adds the common constant C1 back
       p.kSteps = (2 * dm.D + 2 + 15) / 16;               // 16 halfs per MMA
-      p.deadBelow = -50000.f;
+      p.deadBelow = TC_DEAD_BELOW;
       const int grid2 = 2 * std::min(nItems4, smCount / 2);
       switch (t.MP) {
       case 8: gmm_tc2_kernel<8, true><<<grid2, TC2_THREADS, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
@@ -1072,6 +1150,10 @@ static inline int gmm_tc_launch(GmmTcModel &t, GmmTcWork &wk, const DevModel &dm
       case 32: gmm_tc2_kernel<32, true><<<grid2, TC2_THREADS, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
       case 64: gmm_tc2_kernel<64, true><<<grid2, TC2_THREADS, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
       default: gmm_tc2_kernel<128, true><<<grid2, TC2_THREADS, TC2_SMEM_BYTES, st>>>(mapAhi, mapAlo, t.mapBhiH, t.mapBloH, p); break;
+      }
+      if (!getenv("HFBGPU_NO_FIXUP")) {
+         gmm_fixup_kernel<<<nItems, 128, 0, st>>>(dm, W, dItems, wk.dFlag);
+         if (launches) *launches = 3;
       }
       if (traceFile) {                                  // diagnostics only: synchronous dump of the timeline
          std::vector<long long> h(traceN);

@@ -508,6 +508,7 @@ extern "C" int hfbgpu_set_accs(hfbgpu_ctx *c, const double *hostIn)
 {
    if (!c || !hostIn) return HFB_EINVAL;
    CK(cudaSetDevice(c->device));
+   { int rc = wait_impl(c); if (rc) return rc; }        // never under an in-flight wave
    CK(cudaStreamSynchronize(c->stream));
    CK(cudaMemcpy(c->dAcc.p, hostIn, (size_t)c->L.count * sizeof(double), cudaMemcpyHostToDevice));
    return HFB_OK;
@@ -603,8 +604,8 @@ struct ScratchLayout {
 // ------------------------------------------------------------------------------------------
 // one wave: launch (asynchronous) and finish (synchronise + hand results to the caller)
 // ------------------------------------------------------------------------------------------
-static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBase, const float *feat, const float *feat2, bool featOnDevice,
-                       long long waveFrame0, long long waveFrames, bool wantBeams)
+static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBase, const float *feat, const float *feat2, bool featOnDevice,
+                            long long waveFrame0, long long waveFrames, bool wantBeams)
 {
    WaveTables &w = *S.w;
    const int nU = (int)w.utt.size();
@@ -854,10 +855,26 @@ static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBas
    return HFB_OK;
 }
 
+// A wave that failed part-way (out of memory, unsupported shape, launch error) must not stay "in flight": whatever it
+// enqueued is drained and the slot is released, so that a later wait / finish never reads results that were not produced.
+static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBase, const float *feat, const float *feat2, bool featOnDevice,
+                       long long waveFrame0, long long waveFrames, bool wantBeams)
+{
+   const int rc = launch_wave_impl(c, S, labBase, feat, feat2, featOnDevice, waveFrame0, waveFrames, wantBeams);
+   if (rc) {
+      cudaStreamSynchronize(S.stream);
+      cudaGetLastError();
+      S.busy = false; S.res = nullptr; S.hasX = false;
+      memset(&S.beams, 0, sizeof(S.beams));
+   }
+   return rc;
+}
+
 static int finish_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S)
 {
    if (!S.busy) return HFB_OK;
    S.busy = false;
+   if (!S.res || !S.hOut || !S.w || S.w->utt.size() > S.hOutCap) { g_lastError = "internal: wave slot without results"; return HFB_ECUDA; }
    hfb_utt_result *res = S.res;
    const hfb_beams *beams = &S.beams;
    WaveTables &w = *S.w;
@@ -913,6 +930,16 @@ static int submit_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, c
    CK(cudaSetDevice(c->device));
    CK(cudaStreamSynchronize(c->stream));               // accumulator zeroing / model uploads are done
    const HostModel &h = c->hm;
+   // validated for the WHOLE batch before anything is launched: a rejected batch leaves the accumulators untouched
+   for (int u = 0; u < b->numUtt; u++) {
+      const long long T = b->frameOff[u + 1] - b->frameOff[u];
+      const long long Q = (long long)b->labOff[u + 1] - b->labOff[u];
+      if (T < 0 || Q < 0) return HFB_EINVAL;
+      if (T > HFB_MAX_FRAMES || Q > HFB_MAX_LABELS) {
+         g_lastError = "utterance beyond the int16 beam range (more than 32767 frames or 32766 labels): hand it to the reference's FBFile";
+         return HFB_EUNSUPPORTED;
+      }
+   }
    const bool wantBeams = beams && (beams->qLo || beams->qHi || beams->sq || beams->eq);
    // timing mode serialises the waves so that the per-kernel events do not overlap
    const int ns = c->timing ? 1 : c->numSlots;
@@ -936,7 +963,6 @@ static int submit_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, c
       while (u1 < b->numUtt) {
          long long f0 = b->frameOff[u1], f1 = b->frameOff[u1 + 1];
          int T = (int)(f1 - f0), Q = b->labOff[u1 + 1] - b->labOff[u1];
-         if (T > 32767 || Q > 32766) { g_lastError = "utterance beyond int16 beam range"; rcAll = HFB_EUNSUPPORTED; break; }
          size_t perFrame = 0;
          for (int q = 0; q < Q; q++) {
             int p = b->lab[b->labOff[u1] + q];
@@ -1143,6 +1169,7 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
    if (!c || !feat || !states || !out || T < 1 || n < 1) return HFB_EINVAL;
    if (mixOut) { g_lastError = "per-mixture output is not exported by the GPU path"; return HFB_EUNSUPPORTED; }
    CK(cudaSetDevice(c->device));
+   { int rc = wait_impl(c); if (rc) return rc; }        // borrows slot 0's buffers: never under an in-flight wave
    const HostModel &h = c->hm;
    hfbgpu_ctx::Slot &S0 = c->slot[0];
    cudaStream_t st0 = S0.stream;

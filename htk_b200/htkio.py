@@ -522,6 +522,74 @@ def read_acc_dump(path: str, hs: HMMSetDef, flat, uflags: int = 15):
     return acc, total_pr, total_t
 
 
+def read_acc_dump_flat(path: str, flat, uflags: int = 15):
+    """Decode a binary HER$.acc (HTrain.c:1454-1505 DumpAccs + HERest.c:544-549 trailer) straight into a
+    flat float64 array in ``flat.layout`` order, for a FlatModel without an HMMSetDef behind it (the
+    BASELINE-size synthetic sets of synth.make_flat_*: no Python object per Gaussian).  The physical order
+    is the one of the file (names are in the records); sharing follows DumpAccs' seen flags: a tied state,
+    a mean vector, a variance vector and a transition matrix appear once, inside the first HMM that uses
+    them.  Returns (acc, totalPr, totalT)."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    L = flat.layout
+    D = flat.D
+    acc = np.zeros(L.count, dtype=np.float64)
+    index = {n: i for i, n in enumerate(flat.names)}
+    seen_state = np.zeros(flat.J, bool); seen_tr = np.zeros(flat.numTrans, bool)
+    seen_mu = np.zeros(flat.numMeanAcc, bool); seen_va = np.zeros(flat.numVarAcc, bool)
+    seen_g = np.zeros(flat.G, bool)
+    pos = 0
+    n_hmm = 0
+    while n_hmm < flat.P:
+        nl = raw.index(b"\n", pos)
+        name = raw[pos:nl].decode("latin-1")
+        if name.startswith('"') and name.endswith('"'):
+            name = name[1:-1]
+        p_ = index[name.replace("\\", "")]
+        pos = nl + 1
+        acc[L.numEgs + p_] = struct.unpack(">i", raw[pos:pos + 4])[0]
+        pos += 4
+        for s in flat.hmmState[flat.hmmStateOff[p_]:flat.hmmStateOff[p_ + 1]]:
+            s = int(s)
+            if seen_state[s]:
+                continue
+            seen_state[s] = True
+            o, e = int(flat.stateMixOff[s]), int(flat.stateMixOff[s + 1])
+            M = e - o
+            v = np.frombuffer(raw, dtype=">f4", count=M + 1, offset=pos); pos += 4 * (M + 1)
+            acc[L.wtC + o:L.wtC + e] = v[:M]; acc[L.wtOcc + s] = v[M]
+            for g in flat.mixGauss[o:e]:
+                g = int(g)
+                if seen_g[g]:
+                    continue
+                seen_g[g] = True
+                i = int(flat.meanId[g])
+                if (uflags & UPMEANS) and not seen_mu[i]:
+                    seen_mu[i] = True
+                    v = np.frombuffer(raw, dtype=">f4", count=D + 1, offset=pos); pos += 4 * (D + 1)
+                    acc[L.muSum + i * D:L.muSum + (i + 1) * D] = v[:D]; acc[L.muOcc + i] = v[D]
+                i = int(flat.varId[g])
+                if (uflags & UPVARS) and not seen_va[i]:
+                    seen_va[i] = True
+                    v = np.frombuffer(raw, dtype=">f4", count=D + 1, offset=pos); pos += 4 * (D + 1)
+                    acc[L.vaSum + i * D:L.vaSum + (i + 1) * D] = v[:D]; acc[L.vaOcc + i] = v[D]
+        t = int(flat.hmmTrans[p_])
+        if not seen_tr[t]:
+            seen_tr[t] = True
+            N = int(flat.transN[t])
+            v = np.frombuffer(raw, dtype=">f4", count=N * N + N, offset=pos); pos += 4 * (N * N + N)
+            oa = L.tran + int(flat.tranAccOff[t]); ob = L.tranOcc + int(flat.tranOccOff[t])
+            acc[oa:oa + N * N] = v[:N * N]; acc[ob:ob + N] = v[N * N:]
+        mark = struct.unpack(">i", raw[pos:pos + 4])[0]; pos += 4
+        if mark != 123456:
+            raise ValueError("acc dump: bad marker %d after %s" % (mark, name))
+        n_hmm += 1
+    total_pr = float(np.frombuffer(raw, dtype=">f4", count=1, offset=pos)[0]); pos += 4
+    total_t = struct.unpack(">i", raw[pos:pos + 4])[0]
+    acc[L.totalPr] = total_pr; acc[L.totalT] = total_t
+    return acc, total_pr, total_t
+
+
 def write_acc_dump(path: str, hs: HMMSetDef, flat, acc: np.ndarray, uflags: int = 15,
                    order: Optional[Sequence[str]] = None) -> None:
     """Write flat FP64 accumulators as a binary HER$.acc that stock ``HERest -p 0`` loads

@@ -40,6 +40,12 @@ extern "C" {
 #define HFB_LMINMIX (-11.5129254649702)
 #define HFB_NOPRUNE 1.0E20          /* HTKLib/HFB.h:31 */
 
+/* Limits of one utterance (the per-frame beams are int16 like the reference's `short *qHi, *qLo`,
+ * HFB.h:88-89).  A batch holding a longer utterance is rejected as a whole with HFB_EUNSUPPORTED
+ * BEFORE anything is accumulated; the caller hands such an utterance to the reference's FBFile. */
+#define HFB_MAX_FRAMES 32767
+#define HFB_MAX_LABELS 32766
+
 /* update flags, HTKLib/HTrain.h:44 (UPMEANS|UPVARS|UPTRANS|UPMIXES) */
 enum { HFB_UPMEANS = 1, HFB_UPVARS = 2, HFB_UPTRANS = 4, HFB_UPMIXES = 8 };
 

@@ -29,37 +29,7 @@ def load_golden(name):
     return z, fm, b, dict(prune=prune, min_frwd_p=float(z["minFrwdP"]), uflags=uf)
 
 
-def acc_errors(acc, ref, fm):
-    """Normalised deviations per accumulator block.
-
-    Occupancy-like blocks: |a-b| / max(|b|, 1e-2).  Centred first/second-order sums are
-    near-cancelling (SURVEY.md 8a "do not compare the centred mean sums element-wise"): they
-    are compared as the re-estimation formulae use them, mu/occ and var/occ in units of sigma
-    (sigma ~ 1 on all fixtures), with the occupancy floored at one frame -- below that the
-    reference's own float rounding of log b_j(o_t) (~1e-5 absolute) exceeds the tolerance."""
-    L = fm.layout
-    D = fm.D
-    out = {}
-
-    def rel(a, b, floor=1e-2):
-        a = np.asarray(a); b = np.asarray(b)
-        return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
-
-    out["tran"] = rel(acc[L.tran:L.tranOcc], ref[L.tran:L.tranOcc])
-    out["tranOcc"] = rel(acc[L.tranOcc:L.wtC], ref[L.tranOcc:L.wtC])
-    out["wtC"] = rel(acc[L.wtC:L.wtOcc], ref[L.wtC:L.wtOcc])
-    out["wtOcc"] = rel(acc[L.wtOcc:L.muSum], ref[L.wtOcc:L.muSum])
-    out["muOcc"] = rel(acc[L.muOcc:L.vaSum], ref[L.muOcc:L.vaSum])
-    out["vaOcc"] = rel(acc[L.vaOcc:L.numEgs], ref[L.vaOcc:L.numEgs])
-    mocc = np.repeat(np.maximum(ref[L.muOcc:L.vaSum], 1.0), D)
-    vocc = np.repeat(np.maximum(ref[L.vaOcc:L.numEgs], 1.0), D)
-    out["muSum"] = float(np.max(np.abs(acc[L.muSum:L.muOcc] - ref[L.muSum:L.muOcc]) / mocc)) if mocc.size else 0.0
-    out["vaSum"] = float(np.max(np.abs(acc[L.vaSum:L.vaOcc] - ref[L.vaSum:L.vaOcc]) /
-                                np.maximum(vocc, np.abs(ref[L.vaSum:L.vaOcc])))) if vocc.size else 0.0
-    out["numEgs"] = float(np.max(np.abs(acc[L.numEgs:L.totalT] - ref[L.numEgs:L.totalT]))) if fm.P else 0.0
-    out["totalT"] = abs(acc[L.totalT] - ref[L.totalT])
-    out["totalPr"] = abs(acc[L.totalPr] - ref[L.totalPr]) / max(abs(ref[L.totalPr]), 1.0)
-    return out
+from htk_b200.compare import acc_errors  # noqa: E402,F401  (re-exported: the tests import it from here)
 
 
 def have_gpu():

@@ -1,0 +1,129 @@
+"""Parity at the BASELINE.json configuration sizes (missing #1).
+
+The bench models themselves -- config #2 single-Gaussian monophones, #3 5 000 x 16, #4 10 000 x 32 and #5
+8 000 x 16 with T = 6000 / Q = 667 utterances under `-t 250 150 1000` -- are written as a text MMF, a handful of
+utterances go through the STOCK reference `HERest -T 1 -p 1` (oracle/_ref/bin/HERest, built from the unmodified
+sources; it travels to the GPU box) and through libhfbgpu, and are compared the way north_star asks:
+
+  * per-utterance log-likelihood per frame (the reference prints 7 digits) within 1e-4 relative,
+  * every accumulator block of the `-p 1` dump within 1e-4 (conftest.acc_errors),
+  * beams and retry thresholds against the C oracle (pinned bit-exact to the reference on tests/golden).
+
+Everything that needs the reference binary is skipped when it is absent; nothing reads /root/reference.
+"""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, acc_errors
+from htk_b200 import htkio, synth
+from htk_b200.flat import Batch, make_options
+
+HEREST = os.path.join(ROOT, "oracle", "_ref", "bin", "HERest")
+
+# name -> (bench workload key, utterances)
+CASES = {"cfg2": 8, "cfg3": 8, "cfg4": 4, "cfg5": 2}
+
+
+def _bench():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("hfb_bench", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def make_case(name, n_utts, seed=77):
+    """(FlatModel, Batch, prune) of a bench workload, with the bench's own model and corpus generators."""
+    bench = _bench()
+    cfg = bench.WORKLOADS[name]
+    fm = bench.make_model(cfg)
+    T, Q = cfg["T"], cfg["Q"]
+    lab, gauss = synth.corpus_plan(fm, n_utts, T, Q, seed)
+    rng = np.random.default_rng(seed + 1)
+    x = (fm.mean[gauss] + rng.standard_normal((len(gauss), fm.D)).astype(np.float32) / np.sqrt(fm.ivar[gauss])).astype(np.float32)
+    b = Batch.from_arrays(x, np.arange(n_utts + 1, dtype=np.int64) * T, lab.reshape(-1),
+                          np.arange(n_utts + 1, dtype=np.int32) * Q)
+    return fm, b, cfg.get("prune"), lab, x, T
+
+
+def run_stock_herest(tmp, fm, lab, x, T, prune):
+    """Stock `HERest -T 1 -u tmvw [-t ...] -p 1` on the utterances -> (acc in flat layout, per-utterance pr / T)."""
+    synth.write_flat_as_mmf(os.path.join(tmp, "mmf"), os.path.join(tmp, "list"), fm)
+    mlf, scp = {}, []
+    for u in range(len(lab)):
+        fn = os.path.join(tmp, "u%d.mfc" % u)
+        htkio.write_htk_features(fn, x[u * T:(u + 1) * T])
+        mlf["u%d" % u] = [fm.names[j] for j in lab[u]]
+        scp.append(fn)
+    htkio.write_mlf(os.path.join(tmp, "labs.mlf"), mlf)
+    open(os.path.join(tmp, "scp"), "w").write("\n".join(scp) + "\n")
+    os.makedirs(os.path.join(tmp, "acc"))
+    targs = [] if prune is None else ["-t"] + ["%.1f" % v for v in prune]
+    p = subprocess.run([HEREST, "-T", "1", "-u", "tmvw"] + targs + ["-p", "1", "-H", "mmf", "-I", "labs.mlf", "-S", "scp",
+                        "-M", "acc", "list"], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert p.returncode == 0, p.stdout[-2000:]
+    ppf = [float(v) for v in re.findall(r"Utterance prob per frame = (\S+)", p.stdout)]
+    acc, pr, tt = htkio.read_acc_dump_flat(os.path.join(tmp, "acc", "HER1.acc"), fm)
+    return acc, ppf, tt
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_bench_config_matches_stock_herest(name, tmp_path):
+    if not os.path.exists(HEREST):
+        pytest.skip("reference HERest not built (oracle/Makefile ref)")
+    from htk_b200.estep import ForwardBackward
+    from oracle import oracle_lib as O
+    fm, b, prune, lab, x, T = make_case(name, CASES[name])
+    ref, ppf, tt = run_stock_herest(str(tmp_path), fm, lab, x, T, prune)
+    assert len(ppf) == b.numUtt and tt == b.totalT          # nothing skipped by the reference
+    fb = ForwardBackward(fm, prune=prune)
+    res, beams = fb.FBFile(b, want_beams=True)
+    acc = fb.GetAccs()
+    st = fb.stats()
+    fb.close()
+    for r, want in zip(res, ppf):
+        assert r.status == 0
+        assert abs(r.pr / T - want) <= 1e-4 * abs(want) + 1e-6      # 7 printed digits
+    L = fm.layout
+    assert acc[L.totalT] == tt
+    e = acc_errors(acc, ref, fm)
+    assert max(e.values()) < 1e-4, e
+    # the beams, retry counts and thresholds of the reference's pruning: against the C oracle
+    oacc, ores, obeams = O.accumulate(fm, make_options(prune=prune), b, acc_double=True, threads=os.cpu_count() or 1)
+    for r, o in zip(res, ores):
+        assert (r.status, r.retries, r.pruneThresh) == (o[0], o[1], o[3])
+        assert abs(r.pr - o[2]) <= 1e-6 * abs(o[2])
+    total = 4 * b.totalT
+    ties = sum(int(np.sum(getattr(beams, k) != getattr(obeams, k))) for k in ("qLo", "qHi", "sq", "eq"))
+    assert ties <= max(1, total // 2000), "beam mismatches: %d of %d" % (ties, total)
+    e2 = acc_errors(acc, oacc, fm)
+    assert max(e2.values()) < 1e-4, e2
+    if name != "cfg2":
+        assert st.launchesGmm > 0 and st.launchesL2R > 0             # the flagship kernels ran, not a generic path
+
+
+def test_flat_dump_reader_against_object_reader(tmp_path):
+    """htkio.read_acc_dump_flat (no HMMSetDef) decodes a stock dump exactly like htkio.read_acc_dump."""
+    if not os.path.exists(HEREST):
+        pytest.skip("reference HERest not built")
+    fm = synth.make_flat_tied(n_states=60, M=4, n_phys=40, n_centre=6, seed=3)
+    lab, gauss = synth.corpus_plan(fm, 3, 200, 20, seed=5)
+    rng = np.random.default_rng(1)
+    x = (fm.mean[gauss] + rng.standard_normal((len(gauss), fm.D)).astype(np.float32) / np.sqrt(fm.ivar[gauss])).astype(np.float32)
+    ref, ppf, tt = run_stock_herest(str(tmp_path), fm, lab, x, 200, None)
+    from htk_b200.flat import flatten
+    names = open(os.path.join(str(tmp_path), "list")).read().split()
+    hs = htkio.read_mmf([os.path.join(str(tmp_path), "mmf")], hmm_list=names)
+    fm2 = flatten(hs, order=names)
+    acc2, pr2, tt2 = htkio.read_acc_dump(os.path.join(str(tmp_path), "acc", "HER1.acc"), hs, fm2)
+    L = fm.layout
+    assert tt == tt2 == 600 and len(ppf) == 3
+    # same physical order (the flat set's names), same tying -> same numbering of states / Gaussians
+    for a, z in ((L.wtOcc, L.muSum), (L.muOcc, L.vaSum), (L.vaOcc, L.numEgs), (L.numEgs, L.totalT), (L.tranOcc, L.wtC)):
+        assert np.allclose(np.sort(ref[a:z]), np.sort(acc2[a:z]), rtol=0, atol=0)
+    assert abs(ref[L.muSum:L.muOcc].sum() - acc2[L.muSum:L.muOcc].sum()) < 1e-6

@@ -524,3 +524,41 @@ def test_estep_on_static_features_equals_estep_on_expanded_features(device_feat)
     ao = _oracle(fm, b_full, kw)[0]
     e = acc_errors(a1, ao, fm)
     assert max(e.values()) < RTOL, e
+
+
+def test_outlier_frames_get_the_references_values():
+    """the FP16 operands of the tensor-core kernel have a finite range.  Frames far outside it
+    (a coordinate 300 sigma off, a frame of zeros, a frame 80 sigma off in EVERY dimension so that every component of
+    every state is below -50 000) must come out as the reference computes them (IDOutP in float, HModel.c:5420-5431):
+    the true, hugely negative, value -- never a clamped one, never log zero -- and the utterance is still processed."""
+    from oracle import oracle_lib as O
+    z, fm, b, kw = load_golden("synth_tied_m4")
+    feat = np.array(z["feat"], dtype=np.float32)
+    f0 = int(z["frameOff"][1])                       # corrupt utterance 1
+    sd = np.sqrt(1.0 / fm.ivar.astype(np.float64)).mean(0).astype(np.float32)
+    feat[f0 + 10, 3] += 300.0 * sd[3]
+    feat[f0 + 11, :] = 0.0
+    feat[f0 + 12, :] += 80.0 * sd
+    feat[f0 + 13, 7] -= 3000.0 * sd[7]               # beyond the FP16 range even after scaling
+    bad = [f0 + 10, f0 + 11, f0 + 12, f0 + 13]
+    rows = np.r_[f0:f0 + 40]
+    states = np.arange(fm.J, dtype=np.int32)
+    want = O.state_loglik(fm, feat[rows], states)
+    assert want[12].max() < -50000.0                 # the case the old epilogue turned into log zero
+    for gk in (2, 1):
+        fb = _fb(fm, gmm_kernel=gk, **kw)
+        got = fb.OutP(feat[rows], states)
+        assert np.all(got > -1e9)
+        assert np.max(np.abs(got - want) / np.abs(want)) < 1e-5, np.max(np.abs(got - want) / np.abs(want))
+        b2 = Batch.from_arrays(feat, z["frameOff"], z["lab"], z["labOff"])
+        res, beams = fb.FBFile(b2, want_beams=True)
+        acc = fb.GetAccs()
+        oacc, ores, obeams = _oracle(fm, b2, kw)
+        for r, o in zip(res, ores):
+            assert r.status == o[0] == 0
+            assert abs(r.pr - o[2]) <= 1e-6 * abs(o[2])
+        assert res[1].pr < ores[0][2] - 1e4          # the corrupt frames are in the likelihood
+        e = acc_errors(acc, oacc, fm)
+        assert max(e.values()) < RTOL, e
+        assert np.array_equal(beams.sq, obeams.sq) and np.array_equal(beams.qLo, obeams.qLo)
+        fb.close()

@@ -39,7 +39,11 @@ def main():
             assert acc[L.totalT] == z["ref_acc"][L.totalT], (acc[L.totalT], z["ref_acc"][L.totalT])
             print("%s: world=%d max normalised accumulator error %.2e" % (name, world, max(e.values())))
         fb.close()
+    from htk_b200.dist import merge_parity
+    mp = merge_parity(lr, rank, world)                 # vs the stock -p 1..4 + -p 0 merge
     if rank == 0:
+        print("merge parity:", mp)
+        assert mp["ok"], mp
         assert worst < 1e-4, worst
         print("MGPU_PARITY_OK")
     dist.destroy_process_group()
