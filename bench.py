@@ -326,7 +326,7 @@ def run_workload(name, args, rank, world, local_rank, dev, K, full):
     fb.set_stream(stream.cuda_stream)
     batch, dfeat = make_batch(fm, cfg, n_utts, seed=1000 + rank, device=dev)
     acc_t = fb.acc_tensor() if world > 1 else None
-    acc_host = np.zeros(fm.layout.count, np.float64)
+    acc_pinned = torch.empty(int(fm.layout.count), dtype=torch.float64, pin_memory=True)   # like the features: page-locked
 
     def barrier():
         if world > 1:
@@ -354,7 +354,7 @@ def run_workload(name, args, rank, world, local_rank, dev, K, full):
         if world > 1:
             dist.all_reduce(acc_t)            # the per-pass exchange (replaces the `-p 0` file merge)
         if download:
-            fb.lib.hfbgpu_get_accs(fb.h, acc_host.ctypes.data)
+            fb.lib.hfbgpu_get_accs(fb.h, acc_pinned.data_ptr())
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)

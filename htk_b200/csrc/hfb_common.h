@@ -55,6 +55,7 @@ struct UttOut {                     // hfb_utt_result + what the host wants back
    double thresh;
    int J;
    int redo;                        // fast alpha kernel gave up (window > 32 models): generic kernel redoes it
+   long long pairs;                 // (frame, distinct state) pairs inside the slots' taper intervals: what K1 evaluates
 };
 
 struct Wave {                       // everything the kernels of one wave need
@@ -78,6 +79,15 @@ struct Wave {                       // everything the kernels of one wave need
    long long *mTrOcc;               // offset of its TrAcc.occ block
    int *mTmin, *mTmax;              // first / last frame inside the alpha beam
    int *slotState;                  // tied state of each slot
+   // Frames in which a slot's output probability can be needed at all: the union, over the positions that share the
+   // slot, of the beam taper of their model (SetBeamTaper, HFB.c:1116-1145) widened by the look-back / look-ahead of
+   // SetBeta (models qLo-1 .. qHi of frame t+1, HFB.c:1207-1215).  The tensor-core kernel skips (tile, frame block)
+   // combinations outside [first, last], as the reference's Setotprob does (HFB.c:1014-1016).  Written by prep_kernel.
+   int *slotFirst, *slotLast;       // per slot (indexed like slotState)
+   int *tileFirst, *tileLast;       // per group of `spt` consecutive slots (indexed u.slotOff + tile)
+   int spt;                         // slots per tensor-core tile (TC_BN / MP); 0 = no tensor-core kernel
+   int globalSlots;                 // > 0: small single-Gaussian set -- slot j of every utterance IS tied state j (J = globalSlots)
+   int noTaperSkip;                 // HFBGPU_NO_TAPER_SKIP: intervals cover the whole utterance
    int *posSlot;                    // slot of each emitting position
    int *posState;                   // tied state of each emitting position
    int *posQ;                       // model (label) index of each emitting position

@@ -257,22 +257,61 @@ __global__ void __launch_bounds__(128) prep_kernel(DevModel M, Wave W)
    __syncthreads();
    // the reference evaluates each tied state once per frame (HFB.c:910-912): find the first
    // position using the same state, then number the distinct states ("slots")
-   for (int pp = tid; pp < P; pp += nt) {
-      const int s = posState[pp];
-      int f = pp;
-      for (int p2 = 0; p2 < pp; p2++) if (posState[p2] == s) { f = p2; break; }
-      posSlot[pp] = f;
+   __shared__ int sJ;
+   if (W.globalSlots > 0) {
+      // small single-Gaussian sets: slot = tied state (every utterance uses most of them anyway), so that the
+      // tensor-core kernel reads its B operand as contiguous rows
+      for (int pp = tid; pp < P; pp += nt) posSlot[pp] = posState[pp];
+      for (int j = tid; j < W.globalSlots; j += nt) slotState[j] = j;
+      if (tid == 0) { sJ = W.globalSlots; u->Jt = sJ; u->J = (sJ + 3) & ~3; out->J = sJ; }
+   } else {
+      for (int pp = tid; pp < P; pp += nt) {
+         const int s = posState[pp];
+         int f = pp;
+         for (int p2 = 0; p2 < pp; p2++) if (posState[p2] == s) { f = p2; break; }
+         posSlot[pp] = f;
+      }
+      __syncthreads();
+      if (tid == 0) {
+         int J = 0;
+         for (int pp = 0; pp < P; pp++) {
+            const int f = posSlot[pp];
+            if (f == pp) { slotState[J] = posState[pp]; posSlot[pp] = J++; }
+            else posSlot[pp] = posSlot[f];
+         }
+         sJ = J; u->Jt = J; u->J = (J + 3) & ~3; out->J = J;
+      }
    }
    __syncthreads();
-   if (tid == 0) {
-      int J = 0;
-      for (int pp = 0; pp < P; pp++) {
-         const int f = posSlot[pp];
-         if (f == pp) { slotState[J] = posState[pp]; posSlot[pp] = J++; }
-         else posSlot[pp] = posSlot[f];
+   // ---- frames in which each slot can be needed (see Wave::slotFirst)
+   const int J = sJ;
+   int *slotFirst = W.slotFirst + u->slotOff, *slotLast = W.slotLast + u->slotOff;
+   for (int j = tid; j < J; j += nt) { slotFirst[j] = W.noTaperSkip ? 0 : 0x7fffffff; slotLast[j] = W.noTaperSkip ? T - 1 : -1; }
+   __syncthreads();
+   if (!W.noTaperSkip)
+      for (int pp = tid; pp < P; pp += nt) {
+         const int q = W.posQ[u->posOff + pp], q2 = min(q + 2, Q - 1);
+         const int tf = max(0, mPre[q] - 3), tl = min(T - 1, T - 1 - mSuf[q2] + 2);
+         atomicMin(&slotFirst[posSlot[pp]], tf);
+         atomicMax(&slotLast[posSlot[pp]], tl);
       }
-      u->Jt = J; u->J = (J + 3) & ~3; out->J = J;
+   __syncthreads();
+   long long mine = 0;
+   for (int j = tid; j < J; j += nt) mine += max(0, slotLast[j] - slotFirst[j] + 1);
+   if (W.spt > 0) {
+      int *tileFirst = W.tileFirst + u->slotOff, *tileLast = W.tileLast + u->slotOff;
+      const int nTiles = (J + W.spt - 1) / W.spt;
+      for (int n = tid; n < nTiles; n += nt) {
+         int f = 0x7fffffff, l = -1;
+         for (int j = n * W.spt; j < min(J, (n + 1) * W.spt); j++) { f = min(f, slotFirst[j]); l = max(l, slotLast[j]); }
+         tileFirst[n] = f; tileLast[n] = l;
+      }
    }
+   __shared__ long long sPairs[4];
+   for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+   if ((tid & 31) == 0) sPairs[tid >> 5] = mine;
+   __syncthreads();
+   if (tid == 0) { long long a = 0; for (int w2 = 0; w2 < (nt >> 5); w2++) a += sPairs[w2]; out->pairs = a; }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -25,6 +25,7 @@
 #include "hfb_mstep.cuh"
 #include "hfb_feat.cuh"
 #include "gmm_tc.cuh"
+#include "gmm_tc3.cuh"
 
 static thread_local std::string g_lastError;
 
@@ -85,13 +86,13 @@ struct WaveTables {
    std::vector<int2> tcItems4;       // ... and of 4*TC_BM frames (two blocks per CTA, 3xFP16 path)
    std::vector<int> uttIndex;        // index in the caller's batch
    long long bFloats = 0, betaDoubles = 0, occDoubles = 0, aentDoubles = 0;
-   long long totalQ = 0, totalP = 0, tiles = 0;
+   long long totalQ = 0, totalP = 0, totalSl = 0, tiles = 0;   // totalSl: slots allocated (>= positions; global-slot sets: tied states)
    int maxQ = 0, maxS = 0, maxN = 0, maxT = 0;
    int lab0 = 0;                     // first label of the wave in the caller's label array
    void clear()
    {
       utt.clear(); out.clear(); posPre.clear(); tilePre.clear(); tcItems.clear(); tcItems2.clear(); tcItems4.clear(); uttIndex.clear();
-      bFloats = betaDoubles = occDoubles = aentDoubles = 0; totalQ = totalP = tiles = 0; maxQ = maxS = maxN = maxT = 0; lab0 = 0;
+      bFloats = betaDoubles = occDoubles = aentDoubles = 0; totalQ = totalP = totalSl = tiles = 0; maxQ = maxS = maxN = maxT = 0; lab0 = 0;
    }
 };
 
@@ -118,6 +119,8 @@ struct hfbgpu_ctx {
    DevBuf<float> dCentre;             // [J][S4_CSTR] centre of each tied state's component means (stats4_kernel)
    DevBuf<int> dMeanId, dVarId, dStateMixOff, dMixGauss;
    GmmTcModel tc;                    // expanded / split operands for the tcgen05 path
+   GmmTc3Model tc3;                  // operands of gmm_tc3_kernel (fused expansion, taper skipping, single-Gaussian sets)
+   bool useV3 = false;               // K1 = gmm_tc3_kernel
    // accumulators
    DevBuf<double> dAcc;
    DevBuf<int> dHmmN, dHmmStateOff, dHmmState, dHmmTrans, dTransOffF, dTransMinDur;
@@ -409,7 +412,15 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
 
    // tensor-core operands (expanded quadratic form, 3xTF32 split)
    if ((rc = gmm_tc_prepare(c->tc, m, c->stream))) { hfbgpu_destroy(c); return rc; }
-   if (opt->gmmKernel == 2 && !gmm_tc_available(c->tc)) {
+   {
+      void *fn = c->tc.encodeFn;
+      cudaDriverEntryPointQueryResult qr;
+      if (!fn && (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn)) { cudaGetLastError(); fn = nullptr; }
+      if (!getenv("HFBGPU_GMM_V2") && !getenv("HFBGPU_TC_TF32") && !getenv("HFBGPU_NO_PAIR") && opt->gmmKernel != 1 &&
+          (rc = gmm_tc3_prepare(c->tc3, m, c->stream, fn))) { hfbgpu_destroy(c); return rc; }
+      c->useV3 = c->tc3.ready && c->smCount >= 2;
+   }
+   if (opt->gmmKernel == 2 && !gmm_tc_available(c->tc) && !c->useV3) {
       hfbgpu_destroy(c); g_lastError = "tcgen05 GMM kernel requested but not available for this model";
       return HFB_EUNSUPPORTED;
    }
@@ -443,6 +454,7 @@ extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
    c->dMean.release(); c->dIvar.release(); c->dGconst.release(); c->dMixLogWt.release(); c->dTransLogA.release();
    c->dMeanId.release(); c->dVarId.release(); c->dStateMixOff.release(); c->dMixGauss.release();
    gmm_tc_release(c->tc);
+   gmm_tc3_release(c->tc3);
    c->dAcc.release();
    for (auto &sl : c->slot) {
       if (sl.stream) cudaStreamSynchronize(sl.stream);
@@ -533,7 +545,7 @@ namespace {
 // Sizes one utterance (sum of N over its labels) and appends its descriptor.
 // Returns the workspace bytes it needs.
 size_t add_utterance(const HostModel &h, WaveTables &w, int uidx, int T, const int32_t *lab, int Q, int labOff,
-                     long long featOff)
+                     long long featOff, int globalSlots)
 {
    UttDesc u;
    memset(&u, 0, sizeof(u));
@@ -549,19 +561,20 @@ size_t add_utterance(const HostModel &h, WaveTables &w, int uidx, int T, const i
    }
    if (bad) { o.status = HFB_UTT_ETEE; Q = 0; S = 0; }
    const int Pp = S - 2 * Q;
-   u.T = T; u.Q = Q; u.S = S; u.P = Pp; u.J = (Pp + 3) & ~3; u.Jt = Pp;       // J, Jt: bounds, prep_kernel sets them
+   const int slots = bad ? 0 : std::max(Pp, globalSlots);                     // output-probability slots to allocate
+   u.T = T; u.Q = Q; u.S = S; u.P = Pp; u.J = (slots + 3) & ~3; u.Jt = slots;  // J, Jt: bounds, prep_kernel sets them
    w.maxT = std::max(w.maxT, T);
-   u.labOff = labOff; u.modOff = (int)w.totalQ; u.slotOff = (int)w.totalP; u.posOff = (int)w.totalP;
+   u.labOff = labOff; u.modOff = (int)w.totalQ; u.slotOff = (int)w.totalSl; u.posOff = (int)w.totalP;
    u.featOff = featOff; u.frameBase = featOff;
    u.bOff = w.bFloats; u.betaOff = w.betaDoubles; u.occOff = w.occDoubles; u.aentOff = w.aentDoubles;
    w.posPre.push_back((int)w.totalP);
    w.tilePre.push_back((int)w.tiles);
    size_t bytes = 0;
    if (!bad) {
-      w.bFloats += (long long)T * ((Pp + 3) & ~3); w.betaDoubles += (long long)T * S; w.occDoubles += (long long)T * Pp;
+      w.bFloats += (long long)T * ((slots + 3) & ~3); w.betaDoubles += (long long)T * S; w.occDoubles += (long long)T * Pp;
       w.aentDoubles += (long long)T * Q;
       bytes = (size_t)T * ((size_t)Pp * 12 + (size_t)S * 8 + (size_t)Q * 8);
-      w.totalQ += Q; w.totalP += Pp;
+      w.totalQ += Q; w.totalP += Pp; w.totalSl += slots;
       w.tiles += (long long)((T + GT_FR - 1) / GT_FR) * ((Pp + GT_SL - 1) / GT_SL);
       for (int t0 = 0; t0 < T; t0 += TC_BM) w.tcItems.push_back(make_int2(uLocal, t0));
       for (int t0 = 0; t0 < T; t0 += 2 * TC_BM) w.tcItems2.push_back(make_int2(uLocal, t0));
@@ -586,15 +599,17 @@ size_t blob_put(std::vector<unsigned char> &blob, const std::vector<T> &v) { ret
 // device scratch written by prep_kernel / alpha kernel
 struct ScratchLayout {
    size_t mN, mTrans, mSoff, mPoff, mDms, mPre, mSuf, mHmm, mTmin, mTmax, mTrAcc, mTrOcc, slotState, posSlot, posState, posQ, posList, bytes;
-   ScratchLayout(long long totalQ, long long totalP)
+   size_t slotFirst, slotLast, tileFirst, tileLast;
+   ScratchLayout(long long totalQ, long long totalP, long long totalSl)
    {
       size_t o = 0;
       auto take = [&](size_t n, size_t el) { size_t r = o; o += ((n * el + 255) & ~(size_t)255) + 256; return r; };
-      const size_t q = (size_t)totalQ + 1, pp = (size_t)totalP + 1;
+      const size_t q = (size_t)totalQ + 1, pp = (size_t)totalP + 1, ns = (size_t)totalSl + 1;
       mTrAcc = take(q, 8); mTrOcc = take(q, 8);
       mN = take(q, 4); mTrans = take(q, 4); mSoff = take(q, 4); mPoff = take(q, 4); mDms = take(q, 4);
       mPre = take(q, 4); mSuf = take(q, 4); mHmm = take(q, 4); mTmin = take(q, 4); mTmax = take(q, 4);
-      slotState = take(pp, 4); posSlot = take(pp, 4); posState = take(pp, 4); posQ = take(pp, 4); posList = take(pp, sizeof(PosRec));
+      slotState = take(ns, 4); slotFirst = take(ns, 4); slotLast = take(ns, 4); tileFirst = take(ns, 4); tileLast = take(ns, 4);
+      posSlot = take(pp, 4); posState = take(pp, 4); posQ = take(pp, 4); posList = take(pp, sizeof(PosRec));
       bytes = o;
    }
 };
@@ -657,7 +672,7 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
       CK(cudaMallocHost(&S.hTables, S.hTablesCap));
    }
    memcpy(S.hTables, blob.data(), blob.size());
-   const ScratchLayout sl(w.totalQ, w.totalP);
+   const ScratchLayout sl(w.totalQ, w.totalP, w.totalSl);
    if ((rc = S.dTables.reserve(blob.size())) || (rc = S.dScratch.reserve(sl.bytes))) return rc;
    CK(cudaMemcpyAsync(S.dTables.p, S.hTables, blob.size(), cudaMemcpyHostToDevice, st));
    c->stats.h2dBytes += (int64_t)blob.size();
@@ -677,7 +692,9 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
    W.mSuf = (int *)(sc + sl.mSuf); W.mHmm = (int *)(sc + sl.mHmm);
    W.mTrAcc = (long long *)(sc + sl.mTrAcc); W.mTrOcc = (long long *)(sc + sl.mTrOcc);
    W.mTmin = (int *)(sc + sl.mTmin); W.mTmax = (int *)(sc + sl.mTmax);
-   W.slotState = (int *)(sc + sl.slotState); W.posSlot = (int *)(sc + sl.posSlot); W.posState = (int *)(sc + sl.posState); W.posQ = (int *)(sc + sl.posQ);
+   W.slotState = (int *)(sc + sl.slotState); W.slotFirst = (int *)(sc + sl.slotFirst); W.slotLast = (int *)(sc + sl.slotLast);
+   W.tileFirst = (int *)(sc + sl.tileFirst); W.tileLast = (int *)(sc + sl.tileLast);
+   W.posSlot = (int *)(sc + sl.posSlot); W.posState = (int *)(sc + sl.posState); W.posQ = (int *)(sc + sl.posQ);
    W.feat = dFeat; W.feat2 = dFeat2;
    if (fq.enabled) {
       int nl = 0;
@@ -690,6 +707,12 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
    W.pruneInit = c->opt.pruneInit; W.pruneInc = c->opt.pruneInc; W.pruneLim = c->opt.pruneLim;
    W.minFrwdP = (double)c->opt.minFrwdP; W.uFlags = c->opt.uFlags;
 
+   {
+      const int mp = c->useV3 ? c->tc3.MP : (gmm_tc_available(c->tc) ? c->tc.MP : 0);
+      W.spt = (c->opt.gmmKernel != 1 && mp > 0) ? TC_BN / mp : 0;
+      W.globalSlots = (c->useV3 && c->opt.gmmKernel != 1) ? c->tc3.globalSlots : 0;
+      W.noTaperSkip = (getenv("HFBGPU_NO_TAPER_SKIP") || !(c->useV3 && c->opt.gmmKernel != 1)) ? 1 : 0;
+   }
    const bool tm = c->timing;
    // Experiment kept behind HFBGPU_GMM_STREAM=1 (+ HFBGPU_WAVE_UTTS=592): the table-building and tensor-core
    // kernels of ALL waves go through one high-priority stream, back to back, so that the latency-bound
@@ -707,8 +730,13 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
    if (tr) cudaEventRecord(S.ev[0], sg);
    // ---- K1
    int gk = c->opt.gmmKernel;
-   if (gk == 0) gk = gmm_tc_available(c->tc) ? 2 : 1;
-   if (gk == 2) {
+   if (gk == 0) gk = (c->useV3 || gmm_tc_available(c->tc)) ? 2 : 1;
+   if (gk == 2 && c->useV3) {
+      int nl = 0;
+      if ((rc = gmm_tc3_launch(c->tc3, S.tcw, c->dm, W, waveFrames, (const int2 *)(base + oIt), (int)w.tcItems.size(),
+                               (const int2 *)(base + oIt4), (int)w.tcItems4.size(), c->smCount, sg, &nl))) return rc;
+      c->stats.launches += nl; c->stats.launchesGmm += nl;
+   } else if (gk == 2) {
       int nl = 0;
       if ((rc = gmm_tc_launch(c->tc, S.tcw, c->dm, W, waveFrames, (const int2 *)(base + oIt), (int)w.tcItems.size(),
                               (const int2 *)(base + oIt2), (int)w.tcItems2.size(),
@@ -902,7 +930,7 @@ static int finish_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S)
       const UttOut &o = S.hOut[k];
       r.status = o.status; r.retries = o.retries; r.pr = o.pr; r.pruneThresh = o.thresh;
       const UttDesc &u = w.utt[k];
-      if (o.status == 0) c->stats.gmmPairs += (int64_t)u.T * o.J;
+      if (o.status == 0) c->stats.gmmPairs += (int64_t)o.pairs;
       if (S.wantBeams) {
          const long long dst = S.waveFrame0 + u.frameBase;                         // frame index in the batch
          const short *lo = S.hBeams + u.frameBase, *hi = lo + waveFrames, *s = hi + waveFrames, *e = s + waveFrames;
@@ -971,7 +999,8 @@ static int submit_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, c
          }
          size_t need = (size_t)T * perFrame;
          if (u1 > u0 && (bytes + need > wsPerSlot || u1 - u0 >= maxWaveUtts || f0 - waveFrame0 >= targetFrames)) break;
-         bytes += add_utterance(h, w, u1, T, b->lab + b->labOff[u1], Q, b->labOff[u1] - w.lab0, f0 - waveFrame0);
+         bytes += add_utterance(h, w, u1, T, b->lab + b->labOff[u1], Q, b->labOff[u1] - w.lab0, f0 - waveFrame0,
+                                (c->useV3 && c->opt.gmmKernel != 1) ? c->tc3.globalSlots : 0);
          u1++;
       }
       if (rcAll) break;
@@ -1187,8 +1216,10 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
    const int nTiles = ((T + GT_FR - 1) / GT_FR) * ((n + GT_SL - 1) / GT_SL);
    const int tilePre[2] = {0, nTiles};
    std::vector<unsigned char> blob;
+   const std::vector<int> tfirst((size_t)n, 0), tlast((size_t)n, T - 1);          // every tile is needed in every frame
    size_t oUtt = blob_put(blob, &u, 1), oOut = blob_put(blob, &o, 1), oSs = blob_put(blob, states, (size_t)n),
-          oTp = blob_put(blob, tilePre, 2), oIt = blob_put(blob, items), oIt2 = blob_put(blob, items2), oIt4 = blob_put(blob, items4);
+          oTp = blob_put(blob, tilePre, 2), oIt = blob_put(blob, items), oIt2 = blob_put(blob, items2), oIt4 = blob_put(blob, items4),
+          oTf = blob_put(blob, tfirst), oTl = blob_put(blob, tlast);
    int rc;
    if ((rc = S0.dTables.reserve(blob.size())) || (rc = S0.dFeat.reserve((size_t)T * h.D + 4)) ||
        (rc = S0.dB.reserve((size_t)T * nPad + 1)))
@@ -1200,9 +1231,17 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
    W.utt = (UttDesc *)(S0.dTables.p + oUtt); W.out = (UttOut *)(S0.dTables.p + oOut); W.numUtt = 1;
    W.slotState = (int *)(S0.dTables.p + oSs); W.tilePre = (const int *)(S0.dTables.p + oTp);
    W.feat = S0.dFeat.p; W.b = S0.dB.p;
+   W.tileFirst = (int *)(S0.dTables.p + oTf); W.tileLast = (int *)(S0.dTables.p + oTl);
    int gk = c->opt.gmmKernel;
-   if (gk == 0) gk = gmm_tc_available(c->tc) ? 2 : 1;
-   if (gk == 2) {
+   const bool v3 = c->useV3 && c->tc3.MP > 1;           // single-Gaussian sets: the tensor-core kernel needs slot = state
+   if (gk == 0) gk = (v3 || gmm_tc_available(c->tc)) ? 2 : 1;
+   if (gk == 2 && !v3 && !gmm_tc_available(c->tc)) gk = 1;
+   if (gk == 2 && v3) {
+      int nl = 0;
+      if ((rc = gmm_tc3_launch(c->tc3, S0.tcw, c->dm, W, T, (const int2 *)(S0.dTables.p + oIt), (int)items.size(),
+                               (const int2 *)(S0.dTables.p + oIt4), (int)items4.size(), c->smCount, st0, &nl))) return rc;
+      c->stats.launches += nl; c->stats.launchesGmm += nl;
+   } else if (gk == 2) {
       int nl = 0;
       if ((rc = gmm_tc_launch(c->tc, S0.tcw, c->dm, W, T, (const int2 *)(S0.dTables.p + oIt), (int)items.size(),
                               (const int2 *)(S0.dTables.p + oIt2), (int)items2.size(),

@@ -91,8 +91,6 @@ def test_bench_config_matches_stock_herest(name, tmp_path):
         assert abs(r.pr / T - want) <= 1e-4 * abs(want) + 1e-6      # 7 printed digits
     L = fm.layout
     assert acc[L.totalT] == tt
-    e = acc_errors(acc, ref, fm)
-    assert max(e.values()) < 1e-4, e
     # the beams, retry counts and thresholds of the reference's pruning: against the C oracle
     oacc, ores, obeams = O.accumulate(fm, make_options(prune=prune), b, acc_double=True, threads=os.cpu_count() or 1)
     for r, o in zip(res, ores):
@@ -101,8 +99,22 @@ def test_bench_config_matches_stock_herest(name, tmp_path):
     total = 4 * b.totalT
     ties = sum(int(np.sum(getattr(beams, k) != getattr(obeams, k))) for k in ("qLo", "qHi", "sq", "eq"))
     assert ties <= max(1, total // 2000), "beam mismatches: %d of %d" % (ties, total)
-    e2 = acc_errors(acc, oacc, fm)
-    assert max(e2.values()) < 1e-4, e2
+    # Accumulators, three ways.  At these sizes a handful of utterances leaves most of the 80 000+ Gaussians with a
+    # fraction of a frame of occupancy, where the stock tool's own FLOAT accumulators and float log b_j(o_t) sit
+    # 2e-5 .. 5e-5 (normalised) away from the exact-arithmetic evaluation of the same algorithm (e_ref below: stock dump
+    # vs the C oracle with FP64 accumulators, which is pinned bit-exact to the stock tool in float mode).  So:
+    #   library vs exact arithmetic            < 1e-4   (the bar, on every block)
+    #   library vs stock dump                  < 1e-4 on every occupancy-like block and on the totals,
+    #                                          < 1e-4 + the stock tool's own distance e_ref on the centred sums
+    e_gpu = acc_errors(acc, oacc, fm)
+    e_ref = acc_errors(ref, oacc, fm)
+    e = acc_errors(acc, ref, fm)
+    print("%s: library vs oracle(FP64) %.2e, stock vs oracle(FP64) %.2e, library vs stock %.2e"
+          % (name, max(e_gpu.values()), max(e_ref.values()), max(e.values())))
+    assert max(e_gpu.values()) < 1e-4, e_gpu
+    for k, v in e.items():
+        slack = e_ref[k] if k in ("muSum", "vaSum") else 0.0
+        assert v < 1e-4 + slack, (k, v, e_ref[k], e_gpu[k])
     if name != "cfg2":
         assert st.launchesGmm > 0 and st.launchesL2R > 0             # the flagship kernels ran, not a generic path
 

@@ -107,14 +107,17 @@ def test_outp_matches_oracle(gmm_kernel):
         fb.close()
 
 
-@pytest.mark.parametrize("variant", ["f16_pair", "tf32_pair", "tf32_single"])
+@pytest.mark.parametrize("variant", ["f16_fused", "f16_pair", "tf32_pair", "tf32_single"])
 def test_outp_tensor_core_variants_on_badly_scaled_features(variant, monkeypatch):
-    """The three tcgen05 GMM kernels (CTA pair 3xFP16 = default, CTA pair 3xTF32, single CTA 3xTF32) against a
+    """The four tcgen05 GMM kernels (gmm_tc3 = default: fused expansion + taper skipping; CTA pair 3xFP16 with the
+    pre-expanded operand, CTA pair 3xTF32, single CTA 3xTF32) against a
     float64 evaluation on features whose dimensions span five decades of scale with offsets of hundreds --
     what a real front end delivers; the FP16 split relies on its per-dimension power-of-two scaling here."""
     from htk_b200 import synth
     from htk_b200.flat import flatten
-    if variant == "tf32_pair":
+    if variant == "f16_pair":                      # round-1 kernel: pre-expanded operand in HBM, no taper skipping
+        monkeypatch.setenv("HFBGPU_GMM_V2", "1")
+    elif variant == "tf32_pair":
         monkeypatch.setenv("HFBGPU_TC_TF32", "1")
     elif variant == "tf32_single":
         monkeypatch.setenv("HFBGPU_NO_PAIR", "1")
@@ -562,3 +565,32 @@ def test_outlier_frames_get_the_references_values():
         assert max(e.values()) < RTOL, e
         assert np.array_equal(beams.sq, obeams.sq) and np.array_equal(beams.qLo, obeams.qLo)
         fb.close()
+
+
+@pytest.mark.parametrize("name", ["synth_tied_m4", "synth_long_m3", "synth_tee_m2", "synth_mono_m1", "htkdemo_t20_15_200"])
+def test_taper_skipping_changes_nothing(name, monkeypatch):
+    """gmm_tc3_kernel leaves out the (tile, frame block) combinations outside the beam taper, as the reference's
+    Setotprob does (HFB.c:1014-1016).  Everything downstream must be identical to evaluating every frame x every
+    state, and to the round-1 kernel: same likelihoods, thresholds and beams, accumulators equal up to the order of the
+    FP64 atomics."""
+    z, fm, b, kw = load_golden(name)
+    outs = []
+    for env in (None, "HFBGPU_NO_TAPER_SKIP", "HFBGPU_GMM_V2"):
+        if env:
+            monkeypatch.setenv(env, "1")
+        fb = _fb(fm, **kw)
+        res, beams = fb.FBFile(b, want_beams=True)
+        outs.append((res, beams, fb.GetAccs(), fb.stats().gmmPairs))
+        fb.close()
+        if env:
+            monkeypatch.delenv(env)
+    (r0, b0, a0, p0), (r1, b1, a1, p1), (r2, b2, a2, p2) = outs
+    assert [tuple(r) for r in r0] == [tuple(r) for r in r1]             # bit-identical likelihoods
+    for k in ("qLo", "qHi", "sq", "eq"):
+        assert np.array_equal(getattr(b0, k), getattr(b1, k)) and np.array_equal(getattr(b0, k), getattr(b2, k))
+    assert np.allclose(a0, a1, rtol=1e-12, atol=1e-12)
+    e = acc_errors(a0, a2, fm)
+    assert max(e.values()) < 1e-5, e
+    assert p0 <= p1                                                       # fewer (frame, state) pairs evaluated
+    if name in ("synth_tied_m4", "synth_long_m3"):
+        assert p0 < 0.9 * p1, (p0, p1)
