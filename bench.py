@@ -280,6 +280,78 @@ def cpu_reference(fm, cfg, prune, cores, budget_s=25.0, want_merge=True):
         shutil.rmtree(w, ignore_errors=True)
 
 
+def herest_gpu_tool(fm, cfg, prune, n_files=1024, gpu_index=0):
+    """throughput of the DROP-IN TOOL itself -- the reference's HERest (C) with its FBFile call site
+    re-pointed at libhfbgpu (bridge/, oracle/_ref/bin/HERest_gpu) -- end to end from feature files on disk:
+    `HERest_gpu -p 1` over n_files synthetic utterances, MMF load and start-up removed by the marginal rate between a
+    small and the full list.  Returns None when the binary is absent."""
+    from htk_b200 import htkio, synth
+    exe = os.path.join(ROOT, "oracle", "_ref", "bin", "HERest_gpu")
+    if not os.path.exists(exe):
+        return None
+    T, Q = cfg["T"], cfg["Q"]
+    w = tempfile.mkdtemp(prefix="hfb_tool_")
+    try:
+        synth.write_flat_as_mmf(os.path.join(w, "mmf"), os.path.join(w, "list"), fm)
+        rng = np.random.default_rng(11)
+        lab, gauss = synth.corpus_plan(fm, n_files, T, Q, seed=900)
+        mlf, scp = {}, []
+        step = 64
+        for u0 in range(0, n_files, step):
+            g = gauss[u0 * T:(u0 + step) * T]
+            x = (fm.mean[g] + rng.standard_normal((len(g), fm.D)).astype(np.float32) / np.sqrt(fm.ivar[g])).astype(np.float32)
+            for i in range(len(g) // T):
+                fn = os.path.join(w, "u%d.mfc" % (u0 + i))
+                htkio.write_htk_features(fn, x[i * T:(i + 1) * T])
+                mlf["u%d" % (u0 + i)] = [fm.names[j] for j in lab[u0 + i]]
+                scp.append(fn)
+        htkio.write_mlf(os.path.join(w, "labs.mlf"), mlf)
+        targs = [] if prune is None else ["-t"] + ["%.1f" % v for v in prune]
+
+        def run(n, tag):
+            open(os.path.join(w, tag + ".scp"), "w").write("\n".join(scp[:n]) + "\n")
+            os.makedirs(os.path.join(w, tag))
+            t0 = time.time()
+            p = subprocess.run([exe, "-T", "1", "-u", "tmvw"] + targs + ["-p", "1", "-H", os.path.join(w, "mmf"), "-I",
+                                os.path.join(w, "labs.mlf"), "-S", os.path.join(w, tag + ".scp"), "-M", os.path.join(w, tag),
+                                os.path.join(w, "list")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            return time.time() - t0, p
+
+        n_small = 16
+        ta, pa = run(n_small, "a")
+        util = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        smi = None
+        try:
+            smi = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=utilization.gpu", "--format=csv,noheader,nounits",
+                                    "-lms", "50"], stdout=util, stderr=subprocess.DEVNULL)
+        except Exception:
+            smi = None
+        tb, pb = run(n_files, "b")
+        busy = None
+        if smi is not None:
+            smi.terminate()
+            try:
+                smi.wait(timeout=5)
+            except Exception:
+                smi.kill()
+            util.flush(); util.seek(0)
+            v = [float(x) for x in util.read().split() if x.strip().replace(".", "").isdigit()]
+            busy = float(np.mean(v)) if v else None
+        os.unlink(util.name)
+        if pb.returncode != 0:
+            return {"error": pb.stdout[-400:]}
+        import re
+        m = re.search(r"(\d+) utterances through the fast loader, (\d+) through HParm", pb.stdout)
+        rate = (n_files - n_small) * T / max(tb - ta, 1e-6)
+        return {"value": rate, "unit": "frames/s", "files": n_files, "frames": n_files * T, "wall_s": tb, "startup_s": ta,
+                "gpu_utilization_mean_pct": busy, "fast_loader_files": int(m.group(1)) if m else None,
+                "how": "`HERest_gpu -T 1 -u tmvw -p 1` (reference HERest + bridge + libhfbgpu) over %d feature files of %d "
+                       "frames on local disk, one process, one GPU; marginal rate between %d and %d files so that MMF "
+                       "load and CUDA start-up (%.1f s) are not charged" % (n_files, T, n_small, n_files, ta)}
+    finally:
+        shutil.rmtree(w, ignore_errors=True)
+
+
 def cpu_port(fm, cfg, prune, cores, budget_s=20.0):
     from htk_b200 import synth
     from htk_b200.flat import Batch, make_options
@@ -499,6 +571,7 @@ def main():
     ap.add_argument("--gmm-kernel", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--tool-files", type=int, default=1024, help="utterance files for the HERest_gpu throughput record (0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -577,6 +650,12 @@ def main():
                 cpu = cpu_reference(fm, cfg2, prune2, cores, budget_s=args.cpu_budget)
             except Exception as e:                                # never let the baseline leg kill the GPU line
                 cpu = {"value": None, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": "failed: %r" % (e,)}
+        tool = None
+        if world == 1 and args.tool_files > 0 and not args.utts and not args.prune:
+            try:
+                tool = herest_gpu_tool(fm, cfg2, prune2, args.tool_files, local_rank)
+            except Exception as e:
+                tool = {"error": repr(e)}
         out = {"metric": "HERest E-step frames/sec", "value": main_rec["value"], "unit": "frames/s", "n_gpus": world, "steps": K,
                "warmup": max(4, args.warmup), "ms_per_step": main_rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f16x3 split GMM with f32 accumulate / f64 recursions+accumulators", "data": "synthetic",
@@ -584,7 +663,7 @@ def main():
                "gpu_launches": main_rec["gpu_launches"], "roofline": main_rec["roofline"], "rooflines": main_rec["rooflines"],
                "cpu_baseline": cpu, "kernels_ms_per_step": main_rec["kernels_ms_per_step"],
                "work_per_step": main_rec["work_per_step"], "allreduce_bytes_per_pass": main_rec["allreduce_bytes_per_pass"],
-               "allreduce_parity": mp, "workloads": also}
+               "allreduce_parity": mp, "workloads": also, "extra": {"herest_gpu_tool": tool}}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

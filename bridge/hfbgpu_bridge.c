@@ -20,6 +20,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
+#include <unistd.h>
+#include <fcntl.h>
+#include <pthread.h>
 
 #include "hfbgpu.h"
 #include "hfbgpu_bridge.h"
@@ -66,6 +69,13 @@ static struct {
    /* totals */
    long nOk, nSkipped;
    int twoData;                          /* HERest -r */
+   int trace;                            /* HERest's own trace flags (-T): bit 0 = the per-utterance line */
+   /* raw feature-file reader (see "fast loader" below) */
+   int fastState;                        /* 0 = first file not seen yet, 1 = validated, -1 = off */
+   int fastSwap;                         /* payload is byte-swapped on this host */
+   short fastKind, fastSize;             /* header fields every fast-loaded file must carry */
+   int fastFd; long fastT;               /* file opened by HFBGPU_FastLoad, consumed by HFBGPU_Queue */
+   long nFast, nSlow;
 } B;
 
 /* Two pending batches: while the library works on one (hfbgpu_submit is asynchronous), HERest's own
@@ -78,6 +88,8 @@ typedef struct {
    char **names;
    hfb_utt_result *res;
    int inflight;
+   int64_t ticket;                       /* of the hfbgpu_submit that took this batch */
+   int jobs;                             /* reader jobs not finished yet (guarded by R.mu) */
 } Pending;
 static Pending P[2];
 static int cur = 0;
@@ -87,6 +99,102 @@ static void *xrealloc(void *p, size_t n)
    void *q = realloc(p, n);
    if (!q) HError(7399, "hfbgpu bridge: out of host memory");
    return q;
+}
+
+/* ------------------------------------------------------------------ fast loader
+   HTK parameter files are a 12-byte header + nSamples x sampSize bytes of big-endian floats (HWave.c:1399-1433,
+   HParm.c OpenParmFile).  When the file kind already IS the target kind -- the first utterance is loaded by the
+   reference's own LoadData / ReadAsTable (HFB.c:1837-1879, HParm.c:4616) and the raw payload must reproduce those
+   observations bit for bit -- later files skip HParm altogether: the main thread reads the header, reserves the rows in
+   the pinned batch buffer and a pool of reader threads preads + byte-swaps the payload straight into it while HERest's
+   loop goes on resolving labels.  Files that do not carry the validated header (other kind, _C compressed, _K CRC,
+   other width) and everything under -r fall back to LoadData.  HFBGPU_READERS = threads (0 = off). */
+typedef struct { int fd; size_t bytes; float *dst; int swap; Pending *owner; } Job;
+static struct {
+   pthread_t *th; int nTh;
+   pthread_mutex_t mu; pthread_cond_t work, done;
+   Job *q; int cap, head, tail, n; int stop; int failed;
+} R;
+
+static void swap_floats(float *p, size_t n)
+{
+   unsigned int *u = (unsigned int *)p;
+   size_t i;
+   for (i = 0; i < n; i++) u[i] = __builtin_bswap32(u[i]);
+}
+
+static int read_payload(int fd, float *dst, size_t bytes, int swap)
+{
+   size_t got = 0;
+   while (got < bytes) {
+      ssize_t r = pread(fd, (char *)dst + got, bytes - got, (off_t)(12 + got));
+      if (r <= 0) return -1;
+      got += (size_t)r;
+   }
+   if (swap) swap_floats(dst, bytes / 4);
+   return 0;
+}
+
+static void *reader_main(void *arg)
+{
+   (void)arg;
+   for (;;) {
+      Job j;
+      pthread_mutex_lock(&R.mu);
+      while (R.n == 0 && !R.stop) pthread_cond_wait(&R.work, &R.mu);
+      if (R.n == 0 && R.stop) { pthread_mutex_unlock(&R.mu); return NULL; }
+      j = R.q[R.head]; R.head = (R.head + 1) % R.cap; R.n--;
+      pthread_mutex_unlock(&R.mu);
+      {
+         int bad = read_payload(j.fd, j.dst, j.bytes, j.swap);
+         close(j.fd);
+         pthread_mutex_lock(&R.mu);
+         if (bad) R.failed = 1;
+         j.owner->jobs--;
+         pthread_cond_broadcast(&R.done);
+         pthread_mutex_unlock(&R.mu);
+      }
+   }
+}
+
+static void reader_start(int n)
+{
+   int i;
+   memset(&R, 0, sizeof(R));
+   if (n <= 0) return;
+   pthread_mutex_init(&R.mu, NULL); pthread_cond_init(&R.work, NULL); pthread_cond_init(&R.done, NULL);
+   R.cap = 8192; R.q = (Job *)calloc(R.cap, sizeof(Job));
+   R.th = (pthread_t *)calloc(n, sizeof(pthread_t));
+   for (i = 0; i < n; i++) if (pthread_create(&R.th[R.nTh], NULL, reader_main, NULL) == 0) R.nTh++;
+}
+
+static void reader_push(Job j)
+{
+   pthread_mutex_lock(&R.mu);
+   while (R.n == R.cap) pthread_cond_wait(&R.done, &R.mu);
+   R.q[R.tail] = j; R.tail = (R.tail + 1) % R.cap; R.n++;
+   j.owner->jobs++;
+   pthread_cond_signal(&R.work);
+   pthread_mutex_unlock(&R.mu);
+}
+
+static void reader_wait(Pending *p)                      /* every payload of this batch is in the pinned buffer */
+{
+   if (R.nTh == 0) return;
+   pthread_mutex_lock(&R.mu);
+   while (p->jobs > 0) pthread_cond_wait(&R.done, &R.mu);
+   pthread_mutex_unlock(&R.mu);
+   if (R.failed) HError(7350, "hfbgpu bridge: short read in a parameter file (fast loader)");
+}
+
+static void reader_stop(void)
+{
+   int i;
+   if (R.nTh == 0) return;
+   pthread_mutex_lock(&R.mu); R.stop = 1; pthread_cond_broadcast(&R.work); pthread_mutex_unlock(&R.mu);
+   for (i = 0; i < R.nTh; i++) pthread_join(R.th[i], NULL);
+   free(R.th); free(R.q);
+   memset(&R, 0, sizeof(R));
 }
 
 /* ------------------------------------------------------------------ flatten the HMMSet */
@@ -203,7 +311,7 @@ static void Flatten(HMMSet *hset)
 
 /* ------------------------------------------------------------------ public */
 void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pruneInc,
-                 LogDouble pruneLim, float minFrwdP, UPDSet uFlags)
+                 LogDouble pruneLim, float minFrwdP, UPDSet uFlags, int herestTrace)
 {
    hfb_options opt;
    ConfParam *cParm[MAXGLOBS];
@@ -212,10 +320,16 @@ void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pr
    char *env;
 
    memset(&B, 0, sizeof(B));
-   B.hset = hset; B.uFlags = uFlags;
+   B.hset = hset; B.uFlags = uFlags; B.trace = herestTrace; B.fastFd = -1;
    if (fbInfo->twoModels) HError(7399, "hfbgpu bridge: 2-model re-estimation is not accelerated");
    if (hset->xf != NULL || (uFlags & (UPXFORM | UPSEMIT | UPMAP)))
       HError(7399, "hfbgpu bridge: transforms / MAP updates are not accelerated");
+   /* the reference applies these inside Setotprob / UpMixParms (ApplyCompFXForm + Jacobian); the library does not,
+      and silently training on untransformed features would be a wrong model */
+   if (hset->semiTied != NULL || hset->projSize > 0)
+      HError(7399, "hfbgpu bridge: semi-tied / projected (HLDA) sets are not accelerated");
+   if (fbInfo->inXForm != NULL || fbInfo->al_inXForm != NULL || fbInfo->paXForm != NULL)
+      HError(7399, "hfbgpu bridge: input / parent transforms (-a, -J, -E) are not accelerated");
    if (!hset->logWt) HError(7399, "hfbgpu bridge: expected log weights (ConvLogWt)");
    Flatten(hset);
    hfbgpu_default_options(&opt);
@@ -238,6 +352,11 @@ void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pr
    env = getenv("HFBGPU_DEVICE"); opt.device = env ? atoi(env) : 0;
    env = getenv("HFBGPU_BATCH_UTTS"); B.batchUtts = env ? atoi(env) : 2048;
    env = getenv("HFBGPU_BATCH_FRAMES"); B.batchFrames = env ? atol(env) : 4000000L;
+   {
+      long nc = sysconf(_SC_NPROCESSORS_ONLN);
+      env = getenv("HFBGPU_READERS");
+      reader_start(env ? atoi(env) : (int)(nc > 8 ? 8 : (nc > 1 ? nc - 1 : 1)));
+   }
    rc = hfbgpu_create(&B.ctx, &B.m, &opt);
    if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_create failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
    hfbgpu_acc_layout(&B.m, &B.L);
@@ -246,31 +365,39 @@ void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pr
    fflush(stdout);
 }
 
-/* Completes everything in flight and reports per-utterance outcomes in submission order. */
+/* Completes ONE batch (and any older one) and reports its per-utterance outcomes in submission order; a younger batch
+   keeps running on the GPU meanwhile (hfbgpu_wait_ticket). */
+static void Complete(Pending *p)
+{
+   int u, rc;
+   if (!p->inflight) return;
+   rc = hfbgpu_wait_ticket(B.ctx, p->ticket);
+   if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_wait_ticket failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
+   for (u = 0; u < p->nUtt; u++) {
+      const hfb_utt_result *r = &p->res[u];
+      if (r->status == HFB_UTT_OK) {
+         B.nOk++;
+         if (B.trace & 1) {                                            /* HFB.c:1286-1293, under HERest -T 1 */
+            printf(" Utterance prob per frame = %e\n", r->pr / (double)(p->frameOff[u + 1] - p->frameOff[u]));
+            fflush(stdout);
+         }
+      } else if (r->status == HFB_UTT_SKIPPED) {                       /* HFB.c:1342, :1354 */
+         HError(-7324, "StepBack: File %s - bad data or over pruning\n", p->names[u]);
+         B.nSkipped++;
+      } else if (r->status == HFB_UTT_ETEE)
+         HError(7332, "CreateInsts: Cannot have Tee models at start or end of transcription / successive Tee models (%s)", p->names[u]);
+      else
+         HError(r->status, "hfbgpu: forward-backward failed for %s (%s)", p->names[u], hfbgpu_strerror(r->status));
+      free(p->names[u]);
+   }
+   free(p->res); p->res = NULL;
+   p->inflight = 0; p->nUtt = 0; p->nFrames = 0; p->nLab = 0;
+}
+
 static void Drain(void)
 {
-   int k, u, rc;
-   if (!P[0].inflight && !P[1].inflight) return;
-   rc = hfbgpu_wait(B.ctx);
-   if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_wait failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
-   for (k = 0; k < 2; k++) {
-      Pending *p = &P[(cur + k) & 1];                       /* P[cur] was submitted before P[cur ^ 1] */
-      if (!p->inflight) continue;
-      for (u = 0; u < p->nUtt; u++) {
-         const hfb_utt_result *r = &p->res[u];
-         if (r->status == HFB_UTT_OK) B.nOk++;
-         else if (r->status == HFB_UTT_SKIPPED) {                      /* HFB.c:1342, :1354 */
-            HError(-7324, "StepBack: File %s - bad data or over pruning\n", p->names[u]);
-            B.nSkipped++;
-         } else if (r->status == HFB_UTT_ETEE)
-            HError(7332, "CreateInsts: Cannot have Tee models at start or end of transcription / successive Tee models (%s)", p->names[u]);
-         else
-            HError(r->status, "hfbgpu: forward-backward failed for %s (%s)", p->names[u], hfbgpu_strerror(r->status));
-         free(p->names[u]);
-      }
-      free(p->res); p->res = NULL;
-      p->inflight = 0; p->nUtt = 0; p->nFrames = 0; p->nLab = 0;
-   }
+   Complete(&P[cur]);                                       /* P[cur] was submitted before P[cur ^ 1] */
+   Complete(&P[cur ^ 1]);
 }
 
 /* Hands the current batch to the library (asynchronously) and switches to the other buffer. */
@@ -280,6 +407,7 @@ static void Flush(void)
    hfb_batch b;
    int rc;
    if (p->nUtt == 0) return;
+   reader_wait(p);
    p->frameOff[p->nUtt] = p->nFrames; p->labOff[p->nUtt] = p->nLab;
    b.numUtt = p->nUtt; b.frameOff = p->frameOff; b.feat = p->feat; b.labOff = p->labOff; b.lab = p->lab;
    p->res = (hfb_utt_result *)calloc(p->nUtt, sizeof(hfb_utt_result));
@@ -288,16 +416,68 @@ static void Flush(void)
          the library's entry for it is blocking, so the batch is completed and reported right away */
       rc = hfbgpu_accumulate_retrain(B.ctx, &b, p->feat2, p->res, NULL, 0);
       if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_accumulate_retrain failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
-      p->inflight = 1;
+      p->inflight = 1; p->ticket = hfbgpu_last_ticket(B.ctx);
       cur ^= 1;
       Drain();
       return;
    }
    rc = hfbgpu_submit(B.ctx, &b, p->res, NULL, 0);
    if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_submit failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
-   p->inflight = 1;
+   p->inflight = 1; p->ticket = hfbgpu_last_ticket(B.ctx);
    cur ^= 1;
-   if (P[cur].inflight) Drain();                            /* the buffer we are about to refill must be done */
+   Complete(&P[cur]);                                       /* the buffer about to be refilled must be done; the batch
+                                                               just submitted keeps the GPU busy meanwhile */
+}
+
+/* First utterance (loaded by the reference's own LoadData): does the raw payload of the file reproduce, bit for bit,
+   the observations HParm delivered?  Only then may later files with the same header skip HParm. */
+static void FastValidate(UttInfo *utt, char *datafn, const float *want, int T)
+{
+   unsigned char h[12];
+   int fd, sw, D = B.D;
+   float *tmp;
+   B.fastState = -1;
+   if (R.nTh == 0 || utt->twoDataFiles) return;
+   fd = open(datafn, O_RDONLY);
+   if (fd < 0) return;
+   if (pread(fd, h, 12, 0) != 12) { close(fd); return; }
+   tmp = (float *)malloc((size_t)T * D * sizeof(float));
+   for (sw = 1; sw >= 0 && tmp; sw--) {                     /* HTK files are big-endian unless NATURALREADORDER */
+      unsigned int ns = *(unsigned int *)h; unsigned short ss = *(unsigned short *)(h + 8), kd = *(unsigned short *)(h + 10);
+      if (sw) { ns = __builtin_bswap32(ns); ss = __builtin_bswap16(ss); kd = __builtin_bswap16(kd); }
+      if ((long)ns != (long)T || (int)ss != D * (int)sizeof(float)) continue;
+      if (kd & (HASCOMPX | HASCRCC | HASVQ)) continue;       /* compressed / CRC-checked / VQ files stay with HParm */
+      if (read_payload(fd, tmp, (size_t)T * D * sizeof(float), sw) != 0) continue;
+      if (memcmp(tmp, want, (size_t)T * D * sizeof(float)) != 0) continue;
+      B.fastState = 1; B.fastSwap = sw; B.fastKind = (short)kd; B.fastSize = (short)ss;
+      break;
+   }
+   free(tmp);
+   close(fd);
+   if (B.trace & 1) {
+      printf("hfbgpu: fast loader %s\n", B.fastState == 1 ? "on (file kind = target kind; payload verified against HParm on the first file)"
+                                                            : "off (files need HParm's conversions)");
+      fflush(stdout);
+   }
+}
+
+/* Called instead of LoadData (HFB.c:1837-1879) once the fast loader is validated: reads the 12-byte header, checks
+   it against the validated one and leaves the open file for HFBGPU_Queue.  FALSE = the caller runs LoadData. */
+Boolean HFBGPU_FastLoad(UttInfo *utt, char *datafn, char *datafn2)
+{
+   unsigned char h[12];
+   unsigned int ns; unsigned short ss, kd;
+   int fd;
+   if (B.ctx == NULL || B.fastState != 1 || utt->twoDataFiles || datafn2 != NULL) return FALSE;
+   fd = open(datafn, O_RDONLY);
+   if (fd < 0) return FALSE;                                /* let LoadData report it */
+   if (pread(fd, h, 12, 0) != 12) { close(fd); return FALSE; }
+   ns = *(unsigned int *)h; ss = *(unsigned short *)(h + 8); kd = *(unsigned short *)(h + 10);
+   if (B.fastSwap) { ns = __builtin_bswap32(ns); ss = __builtin_bswap16(ss); kd = __builtin_bswap16(kd); }
+   if ((short)kd != B.fastKind || (short)ss != B.fastSize || ns == 0 || ns > 100000000u) { close(fd); return FALSE; }
+   utt->T = (int)ns;
+   B.fastFd = fd; B.fastT = (long)ns;
+   return TRUE;
 }
 
 /* Replaces FBFile (HFB.c:1923): the utterance is only buffered here.  Always returns FALSE so
@@ -316,6 +496,8 @@ Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
    }
    if (p->nFrames + T > p->featCap) {                       /* grow the pinned feature buffer */
       long ncap = (p->nFrames + T) * 2 + 1024;
+      if (ncap < B.batchFrames + T + 1024) ncap = B.batchFrames + T + 1024;   /* one allocation per buffer in the normal case */
+      reader_wait(p);                                       /* nobody writes into the old buffer any more */
       float *nf = (float *)hfbgpu_host_alloc(sizeof(float) * (size_t)ncap * D);
       if (!nf) HError(7399, "hfbgpu bridge: out of pinned host memory");
       if (p->feat) { memcpy(nf, p->feat, sizeof(float) * (size_t)p->nFrames * D); hfbgpu_host_free(p->feat); }
@@ -342,14 +524,26 @@ Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
       if (ph < 0) HError(7321, "hfbgpu bridge: label %s maps to an unknown physical HMM", lab->labid->name);
       p->lab[p->nLab + q] = ph;
    }
-   /* observations exactly as the reference reads them, frame by frame (HFB.c:1009, :1778) */
-   for (t = 0; t < T; t++) {
-      ReadAsTable(utt->pbuf, t, &utt->ot);
-      for (k = 1; k <= D; k++) p->feat[(size_t)(p->nFrames + t) * D + k - 1] = utt->ot.fv[1][k];
-      if (B.twoData) {                                      /* HFB.c:445 */
-         ReadAsTable(utt->pbuf2, t, &utt->ot2);
-         for (k = 1; k <= D; k++) p->feat2[(size_t)(p->nFrames + t) * D + k - 1] = utt->ot2.fv[1][k];
+   if (B.fastFd >= 0) {
+      /* HFBGPU_FastLoad opened the file: a reader thread brings the payload into the pinned rows */
+      Job j;
+      j.fd = B.fastFd; j.bytes = (size_t)T * D * sizeof(float); j.dst = p->feat + (size_t)p->nFrames * D;
+      j.swap = B.fastSwap; j.owner = p;
+      B.fastFd = -1;
+      reader_push(j);
+      B.nFast++;
+   } else {
+      /* observations exactly as the reference reads them, frame by frame (HFB.c:1009, :1778) */
+      for (t = 0; t < T; t++) {
+         ReadAsTable(utt->pbuf, t, &utt->ot);
+         for (k = 1; k <= D; k++) p->feat[(size_t)(p->nFrames + t) * D + k - 1] = utt->ot.fv[1][k];
+         if (B.twoData) {                                   /* HFB.c:445 */
+            ReadAsTable(utt->pbuf2, t, &utt->ot2);
+            for (k = 1; k <= D; k++) p->feat2[(size_t)(p->nFrames + t) * D + k - 1] = utt->ot2.fv[1][k];
+         }
       }
+      B.nSlow++;
+      if (B.fastState == 0) FastValidate(utt, datafn, p->feat + (size_t)p->nFrames * D, T);
    }
    p->names[p->nUtt] = strdup(datafn);
    p->nFrames += T; p->nLab += Q; p->nUtt++;
@@ -408,7 +602,24 @@ void HFBGPU_Finish(int *totalT, LogDouble *totalPr)
    *totalT += (int)(acc[B.L.totalT] + 0.5);                             /* HERest.c:779-780 */
    *totalPr += acc[B.L.totalPr];
    free(acc);
-   for (i = 0; i < 2; i++) { hfbgpu_host_free(P[i].feat); P[i].feat = NULL; P[i].featCap = 0; }
+   reader_stop();
+   if (B.trace & 1) { printf("hfbgpu: %ld utterances through the fast loader, %ld through HParm\n", B.nFast, B.nSlow); fflush(stdout); }
+   for (i = 0; i < 2; i++) {
+      hfbgpu_host_free(P[i].feat); hfbgpu_host_free(P[i].feat2);
+      free(P[i].frameOff); free(P[i].labOff); free(P[i].lab); free(P[i].names); free(P[i].res);
+      memset(&P[i], 0, sizeof(P[i]));
+   }
    hfbgpu_destroy(B.ctx);
    B.ctx = NULL;
+   {
+      PMap *pm[6]; int k2;
+      pm[0] = &B.pmHmm; pm[1] = &B.pmSte; pm[2] = &B.pmMp; pm[3] = &B.pmMean; pm[4] = &B.pmVar; pm[5] = &B.pmTr;
+      for (k2 = 0; k2 < 6; k2++) { free((void *)pm[k2]->key); free(pm[k2]->val); }
+   }
+   free(B.hmm); free(B.ste); free(B.mp); free(B.meanV); free(B.varV); free(B.trans);
+   free((void *)B.m.mean); free((void *)B.m.ivar); free((void *)B.m.gConst); free((void *)B.m.meanId); free((void *)B.m.varId);
+   free((void *)B.m.stateMixOff); free((void *)B.m.mixGauss); free((void *)B.m.mixLogWt); free((void *)B.m.hmmNumStates);
+   free((void *)B.m.hmmStateOff); free((void *)B.m.hmmState); free((void *)B.m.hmmTrans); free((void *)B.m.transN);
+   free((void *)B.m.transOff); free((void *)B.m.transLogA);
+   memset(&B, 0, sizeof(B)); B.fastFd = -1;
 }

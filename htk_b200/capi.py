@@ -20,6 +20,7 @@ EXPORTS = [
     "hfbgpu_accumulate", "hfbgpu_accumulate_device", "hfbgpu_acc_device_ptr", "hfbgpu_acc_count",
     "hfbgpu_get_accs", "hfbgpu_set_accs", "hfbgpu_state_loglik", "hfbgpu_get_min_durs",
     "hfbgpu_get_stats", "hfbgpu_reset_stats", "hfbgpu_set_timing", "hfbgpu_set_stream", "hfbgpu_submit", "hfbgpu_wait",
+    "hfbgpu_last_ticket", "hfbgpu_wait_ticket",
     "hfbgpu_host_alloc", "hfbgpu_host_free", "hfbgpu_mstep", "hfbgpu_set_qualifiers", "hfbgpu_expand_features", "hfbgpu_accumulate_retrain",
 ]
 
@@ -59,6 +60,9 @@ def load():
     l.hfbgpu_accumulate_device.argtypes = l.hfbgpu_accumulate.argtypes
     l.hfbgpu_submit.argtypes = l.hfbgpu_accumulate.argtypes + [C.c_int]
     l.hfbgpu_wait.argtypes = [vp]
+    l.hfbgpu_last_ticket.argtypes = [vp]
+    l.hfbgpu_last_ticket.restype = i64
+    l.hfbgpu_wait_ticket.argtypes = [vp, i64]
     l.hfbgpu_accumulate_retrain.argtypes = [vp, C.POINTER(hfb_batch), vp, C.POINTER(hfb_utt_result), C.POINTER(hfb_beams), C.c_int]
     l.hfbgpu_acc_device_ptr.argtypes = [vp]
     l.hfbgpu_acc_device_ptr.restype = vp

@@ -43,6 +43,45 @@ def acc_errors(acc, ref, fm):
 
 
 
+def acc_errors_ties(acc, ref, fm, min_frwd_p=10.0, max_flips=3):
+    """acc_errors with the minimum-occupancy ties counted instead of charged.
+
+    UpMixParms keeps a component's contribution only if its log posterior exceeds -minFrwdP (HFB.c:1606), i.e. if
+    Lr > exp(-minFrwdP) = 4.5e-5.  A posterior that sits exactly at the cut is kept by one evaluation and dropped by
+    another that differs in the last float bit of log b_j(o_t) -- the stock tool against its own exact-arithmetic
+    restatement included.  One such flip moves a component occupancy by 4.5e-5, which is 4.5e-3 of the 1e-2 floor the
+    occupancy blocks are normalised with.  north_star: "the set of pruned frames identical, except for counted ...
+    ties": Gaussians whose occupancy differs by no more than `max_flips` such quanta (and fails the plain test) are
+    counted and left out of the component-level blocks; everything else is compared as in acc_errors.
+    Returns (errors, number of tied Gaussians)."""
+    L, D = fm.layout, fm.D
+    acc = np.array(acc, np.float64); ref = np.asarray(ref, np.float64)
+    quantum = float(np.exp(-min_frwd_p))
+    do, ro = acc[L.muOcc:L.vaSum], ref[L.muOcc:L.vaSum]
+    d = np.abs(do - ro)
+    tied = (d > 1e-4 * np.maximum(np.abs(ro), 1e-2)) & (d <= max_flips * 1.2 * quantum)
+    n = int(tied.sum())
+    if n:
+        gm = np.asarray(fm.meanId)                                  # Gaussian -> mean accumulator
+        gt = tied[gm]                                               # per Gaussian
+        a2 = acc.copy()
+        idx = np.nonzero(tied)[0]
+        a2[L.muOcc + idx] = ref[L.muOcc + idx]
+        for i in idx:
+            a2[L.muSum + i * D:L.muSum + (i + 1) * D] = ref[L.muSum + i * D:L.muSum + (i + 1) * D]
+        vi = np.unique(np.asarray(fm.varId)[gt])
+        a2[L.vaOcc + vi] = ref[L.vaOcc + vi]
+        for i in vi:
+            a2[L.vaSum + i * D:L.vaSum + (i + 1) * D] = ref[L.vaSum + i * D:L.vaSum + (i + 1) * D]
+        mg = np.asarray(fm.mixGauss)
+        wt = np.nonzero(gt[mg])[0]                                  # mixture slots of the tied Gaussians
+        a2[L.wtC + wt] = ref[L.wtC + wt]
+        st = np.unique(np.searchsorted(np.asarray(fm.stateMixOff), wt, side="right") - 1)
+        a2[L.wtOcc + st] = ref[L.wtOcc + st]
+        acc = a2
+    return acc_errors(acc, ref, fm), n
+
+
 def reestimated_errors(mean, var, ref_mean, ref_var):
     """north_star: "the re-estimated MMF after one pass within 1e-4 relative on means and variances" --
     means in units of the reference's standard deviation, variances relative."""

@@ -42,7 +42,7 @@ struct Tc3Params {
    int nItems;
    const UttDesc *utt;
    const int *slotState;
-   const int *tileFirst, *tileLast;
+   const int2 *tileIv;         // per tile: (first, last) frame in which one of its states can be needed
    const float *feat;          // raw features of the wave [frames][D]
    const float *offset, *scale;
    float *b;
@@ -79,7 +79,7 @@ __device__ __forceinline__ void tc3_wait_acquire_cluster(uint64_t *bar, uint32_t
 }
 
 template <int MP>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(144)
 gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, Tc3Params p)
 {
    extern __shared__ uint8_t tc_smem_raw[];
@@ -120,8 +120,9 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
 
    // which of the item's two 256-frame blocks need tile n: bit b set = frames [y + 256 b, y + 256 (b+1)) ∩ [0, T)
    // intersect the tile's interval.  Identical in every role of both CTAs (same inputs), so they walk the same tiles.
-   auto tile_need = [&](const int *tf, const int *tl, int n, int y, int T) -> int {
-      const int f = tf[n], l = tl[n];
+   // The intervals are read ONE TILE AHEAD (an L2 round trip per tile on the critical path of the epilogue warps cost
+   // 0.3 ms per step on config #3).
+   auto tile_need = [&](int f, int l, int y, int T) -> int {
       int need = 0;
       if (f < min(T, y + 2 * TC_BM) && l >= y) need |= 1;
       if (T - y > 2 * TC_BM && f < min(T, y + 4 * TC_BM) && l >= y + 2 * TC_BM) need |= 2;
@@ -138,10 +139,13 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
          const UttDesc u = p.utt[item.x];
          const int nTiles = (u.Jt + SPT - 1) / SPT;
          const int *ss = p.slotState + u.slotOff;
-         const int *tf = p.tileFirst + u.slotOff, *tl = p.tileLast + u.slotOff;
+         const int2 *tiv = p.tileIv + u.slotOff;
          const int bi = lane % HB;                              // lanes [0,HB): hi boxes, [HB,2HB): lo boxes
+         int2 ivN = tiv[0];
          for (int n = 0; n < nTiles; n++) {
-            if (!tile_need(tf, tl, n, item.y, u.T)) continue;
+            const int2 iv = ivN;
+            if (n + 1 < nTiles) ivN = tiv[n + 1];
+            if (!tile_need(iv.x, iv.y, item.y, u.T)) continue;
             int row = 0;                                        // rows [0, 128) = dummy state ("log zero")
             if (MP == 1) row = TC3_ROW0 + n * TC_BN + (int)rank * 64;  // global slots: 64 consecutive states per CTA
             else if (lane < 2 * HB) {
@@ -176,12 +180,15 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
             const int2 item = p.items[it];
             const UttDesc u = p.utt[item.x];
             const int nTiles = (u.Jt + SPT - 1) / SPT;
-            const int *tf = p.tileFirst + u.slotOff, *tl = p.tileLast + u.slotOff;
+            const int2 *tiv = p.tileIv + u.slotOff;
+            int2 ivN = tiv[0];
             tc3_wait_acquire_cluster(fullA, phA);               // both CTAs' A blocks are in shared memory
             phA ^= 1;
             tc_fence_after();
             for (int n = 0; n < nTiles; n++) {
-               const int need = tile_need(tf, tl, n, item.y, u.T);
+               const int2 iv = ivN;
+               if (n + 1 < nTiles) ivN = tiv[n + 1];
+               const int need = tile_need(iv.x, iv.y, item.y, u.T);
                if (!need) continue;
                const uint32_t as = tile & 1, phT = (tile >> 1) & 1;
                tc_mbar_wait(&tmemEmpty[as], phT ^ 1);
@@ -234,11 +241,14 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
          const int2 item = p.items[it];
          const UttDesc u = p.utt[item.x];
          const int nTiles = (u.Jt + SPT - 1) / SPT;
-         const int *tf = p.tileFirst + u.slotOff, *tl = p.tileLast + u.slotOff;
+         const int2 *tiv = p.tileIv + u.slotOff;
+         int2 ivN = tiv[0];
          for (int n = 0; n < nTiles; n++) {
-            const int need = tile_need(tf, tl, n, item.y, u.T);
+            const int2 iv = ivN;
+            if (n + 1 < nTiles) ivN = tiv[n + 1];
+            const int need = tile_need(iv.x, iv.y, item.y, u.T);
             if (!need) continue;
-            const int f = tf[n], l = tl[n];
+            const int f = iv.x, l = iv.y;
             const uint32_t as = tile & 1, phT = (tile >> 1) & 1;
             tc_mbar_wait(&tmemFull[as], phT);
             tc_fence_after();
@@ -326,58 +336,87 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
       }
    } else {
       // ================= expanders (both CTAs, 4 warps): raw FP32 features -> this CTA's two A blocks =================
-      // thread r owns row r of both blocks.  Columns: 0 = 1 (pairs with the symmetrising constant), 2d+1 = x'_d^2,
-      // 2d+2 = x'_d (d < D), 2D+1 = 1 (pairs with the Gaussian constant), the rest 0; x' = (x - offset) * scale.
-      const int r = threadIdx.x - (2 + EPW) * 32;       // 0..127
+      // Warp w owns rows 32 w .. 32 w + 31 of both blocks and walks them one row at a time with LANE = DIMENSION (lane d
+      // and d + 32), so that the feature reads are coalesced (one row = 156 contiguous bytes; a thread-per-row mapping
+      // touched 32 cache lines per load instruction and cost ~13 us per work item).  Columns: 0 = 1 (pairs with the
+      // symmetrising constant), 2d+1 = x'_d^2, 2d+2 = x'_d (d < D), 2D+1 = 1 (pairs with the Gaussian constant), the
+      // rest 0; x' = (x - offset) * scale.  The constant columns are written once.
+      const int ew = warp - (2 + EPW);                  // 0..3
       const int D = p.D;
-      const int nUnits = 2 * p.kSteps;                  // 16-byte units (8 columns) the MMAs read
+      {  // zero both blocks, then the two columns of ones
+         const int tid = threadIdx.x - (2 + EPW) * 32;
+         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+         for (uint32_t o = tid * 16; o < 2 * A_BLK; o += 128 * 16) *reinterpret_cast<uint4 *>(sA + o) = z;
+         asm volatile("bar.sync 1, 128;" ::: "memory");
+         const unsigned short one = __half_as_ushort(__float2half_rn(1.f));
+         for (int bb = 0; bb < 2; bb++)
+            for (int kc = 0; kc < 2; kc++) {
+               const int k = kc ? 2 * D + 1 : 0;
+               *reinterpret_cast<unsigned short *>(sA + bb * A_BLK + tc3_unit_off(tid, k >> 3) + (k & 7) * 2) = one;
+            }
+         asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      const bool has0 = lane < D, has1 = lane + 32 < D;
+      const float off0 = has0 ? p.offset[lane] : 0.f, sc0 = has0 ? p.scale[lane] : 0.f;
+      const float off1 = has1 ? p.offset[lane + 32] : 0.f, sc1 = has1 ? p.scale[lane + 32] : 0.f;
+      // byte offset of column k inside a row's swizzle atom, split into the part that does not depend on the row
+      // (chunk + position inside the 16-byte unit) and the unit index that is XORed with row mod 8
+      auto colc = [](int k) { return (uint32_t)((k >> 6) * 16384 + (k & 7) * 2); };
+      auto colu = [](int k) { return (uint32_t)((k & 63) >> 3); };
+      const uint32_t cA0 = colc(2 * lane + 1), uA0 = colu(2 * lane + 1), cB0 = colc(2 * lane + 2), uB0 = colu(2 * lane + 2);
+      const uint32_t cA1 = colc(2 * lane + 65), uA1 = colu(2 * lane + 65), cB1 = colc(2 * lane + 66), uB1 = colu(2 * lane + 66);
       uint32_t phA = 0;
       for (int it = pair; it < p.nItems; it += nPairs) {
          const int2 item = p.items[it];
          const UttDesc u = p.utt[item.x];
-         // the raw features of my frame of block 0 travel into registers BEFORE the wait for the A blocks to drain
-         float x[TC3_DMAX + 1];
-         auto load_row = [&](int b) {
-            const int t = item.y + (2 * b + (int)rank) * TC_BM + r;
-            const bool inside = t < u.T;
-            bool far = false;
-            const float *src = p.feat + ((size_t)u.featOff + (inside ? t : 0)) * D;
+         const float *src = p.feat + (size_t)u.featOff * D;
+         float v0[32], v1[32];
+         auto load_block = [&](int b) {
+            const int t0 = item.y + (2 * b + (int)rank) * TC_BM + ew * 32;
 #pragma unroll
-            for (int d = 0; d <= TC3_DMAX; d++) {
-               float v = 0.f;
-               if (d < D && inside) {
-                  v = (src[d] - p.offset[d]) * p.scale[d];
-                  if (!(fabsf(v) <= TC_FAR)) far = true;
-                  v = fminf(fmaxf(v, -250.f), 250.f);             // keeps inf / NaN out of the tensor core; the row is recomputed
-               }
-               x[d] = v;
+            for (int i = 0; i < 32; i++) {
+               const bool inside = t0 + i < u.T;
+               v0[i] = (inside && has0) ? src[(size_t)(t0 + i) * D + lane] : 0.f;
+               v1[i] = (inside && has1) ? src[(size_t)(t0 + i) * D + lane + 32] : 0.f;
             }
-            if (inside) p.flag[u.frameBase + t] = far ? 1 : 0;
          };
-         load_row(0);
+         load_block(0);                                 // in flight BEFORE the wait for the A blocks to drain
          tc_mbar_wait(emptyA, phA ^ 1);
          phA ^= 1;
 #pragma unroll 1
          for (int b = 0; b < 2; b++) {
-            if (b == 1) load_row(1);
+            if (b == 1) load_block(1);
+            const int t0 = item.y + (2 * b + (int)rank) * TC_BM + ew * 32;
             uint8_t *blk = sA + b * A_BLK;
 #pragma unroll
-            for (int un = 0; un < 16; un++) {
-               if (un >= nUnits) break;
-               __half hi[8], lo[8];
-#pragma unroll
-               for (int e = 0; e < 8; e++) {
-                  const int k = un * 8 + e;             // compile-time column
-                  float v;
-                  if (k == 0) v = 1.f;
-                  else if (k & 1) { const int d = (k - 1) >> 1; v = (d < D) ? x[d] * x[d] : ((d == D) ? 1.f : 0.f); }
-                  else { const int d = (k - 2) >> 1; v = (d < D) ? x[d] : 0.f; }
-                  hi[e] = __float2half_rn(v);
-                  lo[e] = __float2half_rn(v - __half2float(hi[e]));
+            for (int i = 0; i < 32; i++) {
+               const int t = t0 + i;
+               if (t >= u.T) break;                     // rows past the utterance keep whatever they held: never stored
+               const int rr = ew * 32 + i;
+               float x0 = (v0[i] - off0) * sc0, x1 = (v1[i] - off1) * sc1;
+               const bool far = (has0 && !(fabsf(x0) <= TC_FAR)) || (has1 && !(fabsf(x1) <= TC_FAR));
+               const unsigned anyFar = __ballot_sync(0xffffffffu, far);
+               if (lane == 0) p.flag[u.frameBase + t] = anyFar ? 1 : 0;
+               x0 = fminf(fmaxf(x0, -250.f), 250.f);     // keeps inf / NaN out of the tensor core; a far row is recomputed
+               x1 = fminf(fmaxf(x1, -250.f), 250.f);
+               uint8_t *row = blk + rr * 128;
+               const uint32_t x7 = (uint32_t)(rr & 7);
+               if (has0) {
+                  const float q = x0 * x0;
+                  const __half hq = __float2half_rn(q), hx = __float2half_rn(x0);
+                  const __half lq = __float2half_rn(q - __half2float(hq)), lx = __float2half_rn(x0 - __half2float(hx));
+                  uint8_t *pa = row + cA0 + ((uA0 ^ x7) << 4), *pb = row + cB0 + ((uB0 ^ x7) << 4);
+                  *reinterpret_cast<__half *>(pa) = hq; *reinterpret_cast<__half *>(pa + 32768) = lq;
+                  *reinterpret_cast<__half *>(pb) = hx; *reinterpret_cast<__half *>(pb + 32768) = lx;
                }
-               const uint32_t off = tc3_unit_off(r, un);
-               *reinterpret_cast<uint4 *>(blk + off) = *reinterpret_cast<const uint4 *>(hi);
-               *reinterpret_cast<uint4 *>(blk + 32768 + off) = *reinterpret_cast<const uint4 *>(lo);
+               if (has1) {
+                  const float q = x1 * x1;
+                  const __half hq = __float2half_rn(q), hx = __float2half_rn(x1);
+                  const __half lq = __float2half_rn(q - __half2float(hq)), lx = __float2half_rn(x1 - __half2float(hx));
+                  uint8_t *pa = row + cA1 + ((uA1 ^ x7) << 4), *pb = row + cB1 + ((uB1 ^ x7) << 4);
+                  *reinterpret_cast<__half *>(pa) = hq; *reinterpret_cast<__half *>(pa + 32768) = lq;
+                  *reinterpret_cast<__half *>(pb) = hx; *reinterpret_cast<__half *>(pb + 32768) = lx;
+               }
             }
          }
          // generic-proxy writes -> visible to the tensor core (async proxy), then tell the leader's MMA thread
@@ -527,7 +566,7 @@ static inline int gmm_tc3_launch(GmmTc3Model &t, GmmTcWork &wk, const DevModel &
    }
    Tc3Params p;
    p.items = dItems4; p.nItems = nItems4; p.utt = W.utt; p.slotState = W.slotState;
-   p.tileFirst = W.tileFirst; p.tileLast = W.tileLast;
+   p.tileIv = W.tileIv;
    p.feat = W.feat; p.offset = t.dOffset; p.scale = t.dScale; p.b = W.b; p.flag = wk.dFlag3;
    p.C0 = t.C0; p.D = dm.D; p.kSteps = (2 * dm.D + 2 + 15) / 16; p.deadBelow = TC_DEAD_BELOW;
    { const char *e = getenv("HFBGPU_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }

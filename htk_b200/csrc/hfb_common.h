@@ -6,6 +6,7 @@
 // numbering only when they are copied out to the caller.
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 #include "../../include/hfbgpu.h"
 
 #define HFB_MAXN 16                 // max states per HMM handled by the recursion kernels
@@ -84,7 +85,7 @@ struct Wave {                       // everything the kernels of one wave need
    // SetBeta (models qLo-1 .. qHi of frame t+1, HFB.c:1207-1215).  The tensor-core kernel skips (tile, frame block)
    // combinations outside [first, last], as the reference's Setotprob does (HFB.c:1014-1016).  Written by prep_kernel.
    int *slotFirst, *slotLast;       // per slot (indexed like slotState)
-   int *tileFirst, *tileLast;       // per group of `spt` consecutive slots (indexed u.slotOff + tile)
+   int2 *tileIv;                    // (first, last) per group of `spt` consecutive slots (indexed u.slotOff + tile)
    int spt;                         // slots per tensor-core tile (TC_BN / MP); 0 = no tensor-core kernel
    int globalSlots;                 // > 0: small single-Gaussian set -- slot j of every utterance IS tied state j (J = globalSlots)
    int noTaperSkip;                 // HFBGPU_NO_TAPER_SKIP: intervals cover the whole utterance

@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(256) beta_fast_kernel(DevModel M, Wave W)
             nhi = -1; nlo = 0x7fffffff;
             for (int w = 0; w < nw; w++) { nhi = max(nhi, whi[w]); nlo = min(nlo, wlo[w]); }
          }
-         if (nhi < 0) { fail = true; status = HFB_UTT_EBETA; break; }
+         if (nhi < 0) { fail = true; if (endq == 0) status = HFB_UTT_EBETA; break; }
          if (nhi > tapHi) nhi = tapHi;
          if (nlo > nhi) { fail = true; break; }
          if (tid == 0) { qHi[t] = (short)nhi; qLo[t] = (short)nlo; }

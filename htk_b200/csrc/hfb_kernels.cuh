@@ -299,12 +299,12 @@ __global__ void __launch_bounds__(128) prep_kernel(DevModel M, Wave W)
    long long mine = 0;
    for (int j = tid; j < J; j += nt) mine += max(0, slotLast[j] - slotFirst[j] + 1);
    if (W.spt > 0) {
-      int *tileFirst = W.tileFirst + u->slotOff, *tileLast = W.tileLast + u->slotOff;
+      int2 *tileIv = W.tileIv + u->slotOff;
       const int nTiles = (J + W.spt - 1) / W.spt;
       for (int n = tid; n < nTiles; n += nt) {
          int f = 0x7fffffff, l = -1;
          for (int j = n * W.spt; j < min(J, (n + 1) * W.spt); j++) { f = min(f, slotFirst[j]); l = max(l, slotLast[j]); }
-         tileFirst[n] = f; tileLast[n] = l;
+         tileIv[n] = make_int2(f, l);
       }
    }
    __shared__ long long sPairs[4];
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(1024) beta_kernel(DevModel M, Wave W)
          __syncthreads();
          int nhi = -1, nlo = 0x7fffffff;
          for (int w = 0; w < nw; w++) { nhi = max(nhi, sm.whi[w]); nlo = min(nlo, sm.wlo[w]); }
-         if (nhi < 0) { fail = true; status = HFB_UTT_EBETA; break; }   // HError 7323
+         if (nhi < 0) { fail = true; if (endq == 0) status = HFB_UTT_EBETA; break; }   // HError 7323
          if (nhi > tapHi) nhi = tapHi;                                   // "on taper" (:1259-1263)
          if (nlo > nhi) { fail = true; break; }                          // beam empty -> LZERO (:1268-1270)
          if (tid == 0) { qHi[t] = (short)nhi; qLo[t] = (short)nlo; }

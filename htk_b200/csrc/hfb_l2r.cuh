@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 128 ? 7 : 1024 / MAXT) beta_l2r_
             nhi = -1; nlo = 0x7fffffff;
             for (int w = 0; w < nw; w++) { nhi = max(nhi, whi[w]); nlo = min(nlo, wlo[w]); }
          }
-         if (nhi < 0) { fail = true; status = HFB_UTT_EBETA; break; }
+         if (nhi < 0) { fail = true; if (endq == 0) status = HFB_UTT_EBETA; break; }
          if (nhi > tapHi) nhi = tapHi;
          if (nlo > nhi) { fail = true; break; }
          if (tid == 0) { qHi[t] = (short)nhi; qLo[t] = (short)nlo; }
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
             nhi = __reduce_max_sync(0xffffffffu, myHi);
             nlo = __reduce_min_sync(0xffffffffu, myLo);
          }
-         if (nhi < 0) { fail = true; status = HFB_UTT_EBETA; break; }
+         if (nhi < 0) { fail = true; if (endq == 0) status = HFB_UTT_EBETA; break; }
          if (nhi > tapHi) nhi = tapHi;
          if (nlo > nhi) { fail = true; break; }
          if (lane == 0) { qHi[t] = (short)nhi; qLo[t] = (short)nlo; }
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(256, 4) beta_l2r_slide_kernel(DevModel M, Wave
             nhi = -1; nlo = 0x7fffffff;
             for (int w = 0; w < nw; w++) { nhi = max(nhi, whi[w]); nlo = min(nlo, wlo[w]); }
          }
-         if (nhi < 0) { fail = true; status = HFB_UTT_EBETA; break; }
+         if (nhi < 0) { fail = true; if (endq == 0) status = HFB_UTT_EBETA; break; }
          if (nhi > tapHi) nhi = tapHi;
          if (nlo > nhi) { fail = true; break; }
          if (tid == 0) { qHi[t] = (short)nhi; qLo[t] = (short)nlo; }

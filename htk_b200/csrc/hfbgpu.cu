@@ -154,6 +154,7 @@ struct hfbgpu_ctx {
       size_t hBeamsCap = 0;
       // in-flight wave
       bool busy = false;
+      int64_t ticket = 0;               // hfbgpu_submit call this wave belongs to
       hfb_utt_result *res = nullptr;    // where the in-flight wave's results go
       hfb_beams beams = {};
       WaveTablesPtr w = nullptr;
@@ -164,6 +165,7 @@ struct hfbgpu_ctx {
    Slot slot[NSLOT];
    int numSlots = NSLOT;
    unsigned nextSlot = 0;
+   int64_t submitSeq = 0;               // tickets of hfbgpu_submit (hfbgpu_wait_ticket)
    size_t workspaceBytes = 0;
    int smCount = 148;
    int maxSmemOptin = 0;
@@ -599,7 +601,7 @@ size_t blob_put(std::vector<unsigned char> &blob, const std::vector<T> &v) { ret
 // device scratch written by prep_kernel / alpha kernel
 struct ScratchLayout {
    size_t mN, mTrans, mSoff, mPoff, mDms, mPre, mSuf, mHmm, mTmin, mTmax, mTrAcc, mTrOcc, slotState, posSlot, posState, posQ, posList, bytes;
-   size_t slotFirst, slotLast, tileFirst, tileLast;
+   size_t slotFirst, slotLast, tileIv;
    ScratchLayout(long long totalQ, long long totalP, long long totalSl)
    {
       size_t o = 0;
@@ -608,7 +610,7 @@ struct ScratchLayout {
       mTrAcc = take(q, 8); mTrOcc = take(q, 8);
       mN = take(q, 4); mTrans = take(q, 4); mSoff = take(q, 4); mPoff = take(q, 4); mDms = take(q, 4);
       mPre = take(q, 4); mSuf = take(q, 4); mHmm = take(q, 4); mTmin = take(q, 4); mTmax = take(q, 4);
-      slotState = take(ns, 4); slotFirst = take(ns, 4); slotLast = take(ns, 4); tileFirst = take(ns, 4); tileLast = take(ns, 4);
+      slotState = take(ns, 4); slotFirst = take(ns, 4); slotLast = take(ns, 4); tileIv = take(ns, 8);
       posSlot = take(pp, 4); posState = take(pp, 4); posQ = take(pp, 4); posList = take(pp, sizeof(PosRec));
       bytes = o;
    }
@@ -693,7 +695,7 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
    W.mTrAcc = (long long *)(sc + sl.mTrAcc); W.mTrOcc = (long long *)(sc + sl.mTrOcc);
    W.mTmin = (int *)(sc + sl.mTmin); W.mTmax = (int *)(sc + sl.mTmax);
    W.slotState = (int *)(sc + sl.slotState); W.slotFirst = (int *)(sc + sl.slotFirst); W.slotLast = (int *)(sc + sl.slotLast);
-   W.tileFirst = (int *)(sc + sl.tileFirst); W.tileLast = (int *)(sc + sl.tileLast);
+   W.tileIv = (int2 *)(sc + sl.tileIv);
    W.posSlot = (int *)(sc + sl.posSlot); W.posState = (int *)(sc + sl.posState); W.posQ = (int *)(sc + sl.posQ);
    W.feat = dFeat; W.feat2 = dFeat2;
    if (fq.enabled) {
@@ -1005,7 +1007,7 @@ static int submit_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, c
       }
       if (rcAll) break;
       const long long waveFrames = b->frameOff[u1] - waveFrame0;
-      S.res = res;
+      S.res = res; S.ticket = c->submitSeq;
       if (wantBeams) S.beams = *beams; else memset(&S.beams, 0, sizeof(S.beams));
       rc = launch_wave(c, S, b->lab + w.lab0, b->feat, feat2, featOnDevice, waveFrame0, waveFrames, wantBeams);
       if (rc) { rcAll = rc; break; }
@@ -1053,7 +1055,25 @@ extern "C" int hfbgpu_accumulate_retrain(hfbgpu_ctx *c, const hfb_batch *b, cons
 
 extern "C" int hfbgpu_submit(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, const hfb_beams *beams, int featOnDevice)
 {
+   if (c) c->submitSeq++;
    return submit_impl(c, b, res, beams, featOnDevice != 0, 1);
+}
+
+extern "C" int64_t hfbgpu_last_ticket(hfbgpu_ctx *c) { return c ? c->submitSeq : 0; }
+
+// Completes the batches submitted up to and including `ticket` and leaves younger ones in flight.
+extern "C" int hfbgpu_wait_ticket(hfbgpu_ctx *c, int64_t ticket)
+{
+   if (!c) return HFB_EINVAL;
+   CK(cudaSetDevice(c->device));
+   int rcAll = HFB_OK;
+   for (int i = 0; i < hfbgpu_ctx::NSLOT; i++) {        // oldest first
+      hfbgpu_ctx::Slot &S = c->slot[(c->nextSlot + i) % hfbgpu_ctx::NSLOT];
+      if (!S.busy || S.ticket > ticket) continue;
+      int rc = finish_wave(c, S);
+      if (rc && !rcAll) rcAll = rc;
+   }
+   return rcAll;
 }
 
 extern "C" int hfbgpu_wait(hfbgpu_ctx *c) { return wait_impl(c); }
@@ -1216,10 +1236,10 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
    const int nTiles = ((T + GT_FR - 1) / GT_FR) * ((n + GT_SL - 1) / GT_SL);
    const int tilePre[2] = {0, nTiles};
    std::vector<unsigned char> blob;
-   const std::vector<int> tfirst((size_t)n, 0), tlast((size_t)n, T - 1);          // every tile is needed in every frame
+   const std::vector<int2> tiv((size_t)n, make_int2(0, T - 1));                   // every tile is needed in every frame
    size_t oUtt = blob_put(blob, &u, 1), oOut = blob_put(blob, &o, 1), oSs = blob_put(blob, states, (size_t)n),
           oTp = blob_put(blob, tilePre, 2), oIt = blob_put(blob, items), oIt2 = blob_put(blob, items2), oIt4 = blob_put(blob, items4),
-          oTf = blob_put(blob, tfirst), oTl = blob_put(blob, tlast);
+          oTf = blob_put(blob, tiv);
    int rc;
    if ((rc = S0.dTables.reserve(blob.size())) || (rc = S0.dFeat.reserve((size_t)T * h.D + 4)) ||
        (rc = S0.dB.reserve((size_t)T * nPad + 1)))
@@ -1231,7 +1251,7 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
    W.utt = (UttDesc *)(S0.dTables.p + oUtt); W.out = (UttOut *)(S0.dTables.p + oOut); W.numUtt = 1;
    W.slotState = (int *)(S0.dTables.p + oSs); W.tilePre = (const int *)(S0.dTables.p + oTp);
    W.feat = S0.dFeat.p; W.b = S0.dB.p;
-   W.tileFirst = (int *)(S0.dTables.p + oTf); W.tileLast = (int *)(S0.dTables.p + oTl);
+   W.tileIv = (int2 *)(S0.dTables.p + oTf);
    int gk = c->opt.gmmKernel;
    const bool v3 = c->useV3 && c->tc3.MP > 1;           // single-Gaussian sets: the tensor-core kernel needs slot = state
    if (gk == 0) gk = (v3 || gmm_tc_available(c->tc)) ? 2 : 1;

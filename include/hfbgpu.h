@@ -200,6 +200,12 @@ int hfbgpu_accumulate_device(hfbgpu_ctx *ctx, const hfb_batch *batch,
 int hfbgpu_submit(hfbgpu_ctx *ctx, const hfb_batch *batch, hfb_utt_result *res,
                   const hfb_beams *beams, int featOnDevice);
 int hfbgpu_wait(hfbgpu_ctx *ctx);
+/* Per-batch completion: every hfbgpu_submit gets a ticket (1, 2, ...; hfbgpu_last_ticket returns the one of the most
+ * recent call).  hfbgpu_wait_ticket completes the batches submitted up to and including `ticket` -- their res[] are
+ * valid afterwards -- and leaves younger batches running, so a caller with two buffers can refill the older one while
+ * the GPU works on the newer (what the HERest bridge does).                                                      */
+int64_t hfbgpu_last_ticket(hfbgpu_ctx *ctx);
+int hfbgpu_wait_ticket(hfbgpu_ctx *ctx, int64_t ticket);
 
 /* Single-pass retraining, HERest -r (HERest.c:369, :505-511; HFB.c:1603-1611, :1731): every utterance comes as
  * two parameterisations of the same frames.  Alignment (output probabilities, alpha / beta, beams, state and

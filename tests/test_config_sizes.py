@@ -102,15 +102,22 @@ def test_bench_config_matches_stock_herest(name, tmp_path):
     # Accumulators, three ways.  At these sizes a handful of utterances leaves most of the 80 000+ Gaussians with a
     # fraction of a frame of occupancy, where the stock tool's own FLOAT accumulators and float log b_j(o_t) sit
     # 2e-5 .. 5e-5 (normalised) away from the exact-arithmetic evaluation of the same algorithm (e_ref below: stock dump
-    # vs the C oracle with FP64 accumulators, which is pinned bit-exact to the stock tool in float mode).  So:
+    # vs the C oracle with FP64 accumulators, which is pinned bit-exact to the stock tool in float mode), and where a
+    # component posterior exactly at the exp(-minFrwdP) cut (HFB.c:1606) flips between two evaluations -- counted as
+    # ties like the beam boundaries (compare.acc_errors_ties).  So:
     #   library vs exact arithmetic            < 1e-4   (the bar, on every block)
     #   library vs stock dump                  < 1e-4 on every occupancy-like block and on the totals,
     #                                          < 1e-4 + the stock tool's own distance e_ref on the centred sums
-    e_gpu = acc_errors(acc, oacc, fm)
-    e_ref = acc_errors(ref, oacc, fm)
-    e = acc_errors(acc, ref, fm)
-    print("%s: library vs oracle(FP64) %.2e, stock vs oracle(FP64) %.2e, library vs stock %.2e"
-          % (name, max(e_gpu.values()), max(e_ref.values()), max(e.values())))
+    from htk_b200.compare import acc_errors_ties
+    e_gpu, t_gpu = acc_errors_ties(acc, oacc, fm)
+    e_ref, t_ref = acc_errors_ties(ref, oacc, fm)
+    e, t_st = acc_errors_ties(acc, ref, fm)
+    n_occ = int(np.count_nonzero(oacc[L.muOcc:L.vaSum]))
+    print("%s: library vs oracle(FP64) %.2e (%d ties), stock vs oracle(FP64) %.2e (%d ties), library vs stock %.2e (%d ties); "
+          "%d Gaussians with occupancy" % (name, max(e_gpu.values()), t_gpu, max(e_ref.values()), t_ref, max(e.values()), t_st, n_occ))
+    print("   library vs oracle per block:", {k: "%.1e" % v for k, v in e_gpu.items()})
+    print("   library vs stock  per block:", {k: "%.1e" % v for k, v in e.items()})
+    assert max(t_gpu, t_st) <= max(2, n_occ // 2000), (t_gpu, t_st, n_occ)
     assert max(e_gpu.values()) < 1e-4, e_gpu
     for k, v in e.items():
         slack = e_ref[k] if k in ("muSum", "vaSum") else 0.0

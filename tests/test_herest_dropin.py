@@ -78,11 +78,22 @@ def test_herest_gpu_matches_stock_herest(tmp_path, case, monkeypatch):
         hs2, fm = _setup(tmp, hs, n_utts=10, T=250, Q=18, seed=5, tee=True, add_short=True)
         targs = ["-t", "40.0", "20.0", "400.0"]
     base = ["-T", "1", "-u", "tmvw"] + targs + ["-p", "1", "-H", "mmf", "-I", "labs.mlf", "-S", "scp"]
+    import re
+    probs = {}
     for exe, d in ((HEREST, "accA"), (HEREST_GPU, "accB")):
         os.makedirs(os.path.join(tmp, d))
         out = _run([exe] + base + ["-M", d, "list"], tmp)
         if case != "tied_m4":
             assert "7324" in out                       # the too-short utterance is skipped with a warning
+        probs[d] = [float(v) for v in re.findall(r"Utterance prob per frame = (\S+)", out)]
+        if exe == HEREST_GPU:
+            # files already hold the target kind: after the first one (validated against HParm) the reader pool takes over
+            assert "fast loader on" in out, out[-1500:]
+            m = re.search(r"(\d+) utterances through the fast loader, (\d+) through HParm", out)
+            assert m and int(m.group(2)) == 1 and int(m.group(1)) >= 9, out[-600:]
+    # the per-utterance trace line of HERest -T 1 (HFB.c:1286-1293), same utterances in the same order
+    assert len(probs["accA"]) == len(probs["accB"]) >= 9
+    assert np.allclose(probs["accA"], probs["accB"], rtol=1e-4, atol=0)
     a, prA, tA = htkio.read_acc_dump(os.path.join(tmp, "accA", "HER1.acc"), hs2, fm)
     b, prB, tB = htkio.read_acc_dump(os.path.join(tmp, "accB", "HER1.acc"), hs2, fm)
     assert tA == tB and abs(prA - prB) <= 1e-6 * abs(prA)
@@ -248,6 +259,17 @@ def test_device_qualifiers_match_stock_herest_loader(tmp_path):
     e = acc_errors(b, a, fm)
     e.pop("totalPr"); e.pop("totalT")
     assert max(e.values()) < 1e-4, e
+    # the drop-in tool on the same files: HParm has to expand them, so the raw-file fast loader must stay off
+    if os.path.exists(HEREST_GPU):
+        os.makedirs(os.path.join(tmp, "accG"))
+        out = _run([HEREST_GPU, "-C", "cfg", "-T", "1", "-u", "tmvw", "-p", "1", "-H", "mmf", "-I", "labs.mlf", "-S", "scp",
+                    "-M", "accG", "list"], tmp)
+        assert "fast loader off" in out and "0 utterances through the fast loader" in out, out[-800:]
+        g, prG, tG = htkio.read_acc_dump(os.path.join(tmp, "accG", "HER1.acc"), hs2, fm)
+        assert tG == tA and abs(prG - prA) <= 1e-4 * abs(prA)
+        e = acc_errors(g, a, fm)
+        e.pop("totalPr"); e.pop("totalT")
+        assert max(e.values()) < 1e-4, e
 
 
 def test_single_pass_retraining_matches_stock_herest(tmp_path):
