@@ -380,9 +380,11 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
                v1[i] = (inside && has1) ? src[(size_t)(t0 + i) * D + lane + 32] : 0.f;
             }
          };
-         load_block(0);                                 // in flight BEFORE the wait for the A blocks to drain
+         const bool skipX = (p.dbg & 32) && it != pair;  // timing experiment: reuse the first item's A blocks
+         if (!skipX) load_block(0);                     // in flight BEFORE the wait for the A blocks to drain
          tc_mbar_wait(emptyA, phA ^ 1);
          phA ^= 1;
+         if (skipX) { __syncwarp(); if (lane == 0) tc3_arrive_leader_release(fullA); continue; }
 #pragma unroll 1
          for (int b = 0; b < 2; b++) {
             if (b == 1) load_block(1);
