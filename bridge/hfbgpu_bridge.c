@@ -357,11 +357,22 @@ void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pr
       env = getenv("HFBGPU_READERS");
       reader_start(env ? atoi(env) : (int)(nc > 8 ? 8 : (nc > 1 ? nc - 1 : 1)));
    }
-   rc = hfbgpu_create(&B.ctx, &B.m, &opt);
+   /* HFBGPU_DEVICES = "0,1,2,3" or "all": one HERest process drives every listed GPU (hfbgpu_create_multi) -- what
+      the reference does with N `-p k` processes and a `-p 0` merge */
+   env = getenv("HFBGPU_DEVICES");
+   if (env != NULL && *env != '\0') {
+      int32_t devs[16];
+      int nd = 0;
+      if (strcmp(env, "all") == 0) { int n = hfbgpu_device_count(); for (nd = 0; nd < n && nd < 16; nd++) devs[nd] = nd; }
+      else { char *e = env; while (*e && nd < 16) { devs[nd++] = (int32_t)strtol(e, &e, 10); while (*e == ',' || *e == ' ') e++; } }
+      if (nd < 1) HError(7399, "hfbgpu bridge: HFBGPU_DEVICES lists no device");
+      rc = hfbgpu_create_multi(&B.ctx, &B.m, &opt, devs, nd);
+   } else
+      rc = hfbgpu_create(&B.ctx, &B.m, &opt);
    if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_create failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
    hfbgpu_acc_layout(&B.m, &B.L);
-   printf("hfbgpu: %d physical HMMs, %d tied states, %d Gaussians, %d transition matrices on device %d\n",
-          B.nHmm, B.nSte, B.nMp, B.nTr, opt.device);
+   printf("hfbgpu: %d physical HMMs, %d tied states, %d Gaussians, %d transition matrices on %d GPU(s)\n",
+          B.nHmm, B.nSte, B.nMp, B.nTr, hfbgpu_num_devices(B.ctx));
    fflush(stdout);
 }
 

@@ -20,7 +20,7 @@ EXPORTS = [
     "hfbgpu_accumulate", "hfbgpu_accumulate_device", "hfbgpu_acc_device_ptr", "hfbgpu_acc_count",
     "hfbgpu_get_accs", "hfbgpu_set_accs", "hfbgpu_state_loglik", "hfbgpu_get_min_durs",
     "hfbgpu_get_stats", "hfbgpu_reset_stats", "hfbgpu_set_timing", "hfbgpu_set_stream", "hfbgpu_submit", "hfbgpu_wait",
-    "hfbgpu_last_ticket", "hfbgpu_wait_ticket",
+    "hfbgpu_last_ticket", "hfbgpu_wait_ticket", "hfbgpu_create_multi", "hfbgpu_num_devices", "hfbgpu_reduce_accs",
     "hfbgpu_host_alloc", "hfbgpu_host_free", "hfbgpu_mstep", "hfbgpu_set_qualifiers", "hfbgpu_expand_features", "hfbgpu_accumulate_retrain",
 ]
 
@@ -55,6 +55,9 @@ def load():
     l.hfbgpu_device_count.restype = C.c_int
     l.hfbgpu_create.argtypes = [C.POINTER(vp), C.POINTER(hfb_model), C.POINTER(hfb_options)]
     l.hfbgpu_destroy.argtypes = [vp]
+    l.hfbgpu_create_multi.argtypes = [C.POINTER(vp), C.POINTER(hfb_model), C.POINTER(hfb_options), C.POINTER(i32), i32]
+    l.hfbgpu_num_devices.argtypes = [vp]
+    l.hfbgpu_reduce_accs.argtypes = [vp]
     l.hfbgpu_zero_accs.argtypes = [vp]
     l.hfbgpu_accumulate.argtypes = [vp, C.POINTER(hfb_batch), C.POINTER(hfb_utt_result), C.POINTER(hfb_beams)]
     l.hfbgpu_accumulate_device.argtypes = l.hfbgpu_accumulate.argtypes

@@ -79,7 +79,7 @@ __device__ __forceinline__ void tc3_wait_acquire_cluster(uint64_t *bar, uint32_t
 }
 
 template <int MP>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(144)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
 gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, Tc3Params p)
 {
    extern __shared__ uint8_t tc_smem_raw[];

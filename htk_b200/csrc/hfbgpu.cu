@@ -166,6 +166,10 @@ struct hfbgpu_ctx {
    int numSlots = NSLOT;
    unsigned nextSlot = 0;
    int64_t submitSeq = 0;               // tickets of hfbgpu_submit (hfbgpu_wait_ticket)
+   // ---- device group (hfbgpu_create_multi): this context owns no device memory, it drives one child per GPU
+   std::vector<hfbgpu_ctx *> kids;
+   std::vector<std::vector<int64_t>> kidTickets;   // [group ticket % 64][kid]
+   bool reduced = true;                 // children 1.. hold nothing that is not already in child 0
    size_t workspaceBytes = 0;
    int smCount = 148;
    int maxSmemOptin = 0;
@@ -450,6 +454,11 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
 extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
 {
    if (!c) return HFB_EINVAL;
+   if (!c->kids.empty()) {
+      for (auto *k : c->kids) hfbgpu_destroy(k);
+      delete c;
+      return HFB_OK;
+   }
    cudaSetDevice(c->device);
    if (c->stream) cudaStreamSynchronize(c->stream);
    c->dCentre.release();
@@ -484,6 +493,7 @@ extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
 extern "C" int hfbgpu_set_stream(hfbgpu_ctx *c, void *st)
 {
    if (!c) return HFB_EINVAL;
+   if (!c->kids.empty()) { g_lastError = "a device group runs on the library's own streams"; return HFB_EUNSUPPORTED; }
    CK(cudaSetDevice(c->device));
    CK(cudaStreamSynchronize(c->stream));
    c->stream = st ? (cudaStream_t)st : c->ownStream;
@@ -491,10 +501,18 @@ extern "C" int hfbgpu_set_stream(hfbgpu_ctx *c, void *st)
 }
 
 static int wait_impl(hfbgpu_ctx *c);
+static bool is_group(const hfbgpu_ctx *c);
+static int group_reduce(hfbgpu_ctx *g);
 
 extern "C" int hfbgpu_zero_accs(hfbgpu_ctx *c)
 {
    if (!c) return HFB_EINVAL;
+   if (is_group(c)) {
+      int rcAll = HFB_OK;
+      for (auto *k : c->kids) { int rc = hfbgpu_zero_accs(k); if (rc && !rcAll) rcAll = rc; }
+      c->reduced = true;
+      return rcAll;
+   }
    CK(cudaSetDevice(c->device));
    { int rc = wait_impl(c); if (rc) return rc; }
    CK(cudaMemsetAsync(c->dAcc.p, 0, (size_t)c->L.count * sizeof(double), c->stream));
@@ -502,7 +520,7 @@ extern "C" int hfbgpu_zero_accs(hfbgpu_ctx *c)
    return HFB_OK;
 }
 
-extern "C" double *hfbgpu_acc_device_ptr(hfbgpu_ctx *c) { return c ? c->dAcc.p : nullptr; }
+extern "C" double *hfbgpu_acc_device_ptr(hfbgpu_ctx *c) { return !c ? nullptr : (is_group(c) ? c->kids[0]->dAcc.p : c->dAcc.p); }
 extern "C" int64_t hfbgpu_acc_count(hfbgpu_ctx *c) { return c ? c->L.count : 0; }
 
 static int wait_impl(hfbgpu_ctx *c);
@@ -510,6 +528,7 @@ static int wait_impl(hfbgpu_ctx *c);
 extern "C" int hfbgpu_get_accs(hfbgpu_ctx *c, double *hostOut)
 {
    if (!c || !hostOut) return HFB_EINVAL;
+   if (is_group(c)) { int rc = group_reduce(c); return rc ? rc : hfbgpu_get_accs(c->kids[0], hostOut); }
    CK(cudaSetDevice(c->device));
    { int rc = wait_impl(c); if (rc) return rc; }
    CK(cudaStreamSynchronize(c->stream));
@@ -521,6 +540,10 @@ extern "C" int hfbgpu_get_accs(hfbgpu_ctx *c, double *hostOut)
 extern "C" int hfbgpu_set_accs(hfbgpu_ctx *c, const double *hostIn)
 {
    if (!c || !hostIn) return HFB_EINVAL;
+   if (is_group(c)) {
+      int rc = hfbgpu_zero_accs(c);
+      return rc ? rc : hfbgpu_set_accs(c->kids[0], hostIn);
+   }
    CK(cudaSetDevice(c->device));
    { int rc = wait_impl(c); if (rc) return rc; }        // never under an in-flight wave
    CK(cudaStreamSynchronize(c->stream));
@@ -531,13 +554,40 @@ extern "C" int hfbgpu_set_accs(hfbgpu_ctx *c, const double *hostIn)
 extern "C" int hfbgpu_get_min_durs(hfbgpu_ctx *c, int32_t *out)
 {
    if (!c || !out) return HFB_EINVAL;
+   if (is_group(c)) return hfbgpu_get_min_durs(c->kids[0], out);
    for (int i = 0; i < c->hm.numTrans; i++) out[i] = c->hm.minDur[i];
    return HFB_OK;
 }
 
-extern "C" int hfbgpu_get_stats(hfbgpu_ctx *c, hfb_stats *o) { if (!c || !o) return HFB_EINVAL; *o = c->stats; return HFB_OK; }
-extern "C" int hfbgpu_reset_stats(hfbgpu_ctx *c) { if (!c) return HFB_EINVAL; memset(&c->stats, 0, sizeof(c->stats)); return HFB_OK; }
-extern "C" int hfbgpu_set_timing(hfbgpu_ctx *c, int on) { if (!c) return HFB_EINVAL; c->timing = on != 0; return HFB_OK; }
+extern "C" int hfbgpu_get_stats(hfbgpu_ctx *c, hfb_stats *o)
+{
+   if (!c || !o) return HFB_EINVAL;
+   if (!is_group(c)) { *o = c->stats; return HFB_OK; }
+   memset(o, 0, sizeof(*o));                           // counters: sums over the devices; times: the slowest device
+   for (auto *k : c->kids) {
+      const hfb_stats &s = k->stats;
+      o->launches += s.launches; o->launchesGmm += s.launchesGmm; o->launchesBeta += s.launchesBeta; o->launchesAlpha += s.launchesAlpha;
+      o->launchesStats += s.launchesStats; o->launchesMisc += s.launchesMisc; o->launchesL2R += s.launchesL2R;
+      o->betaCells += s.betaCells; o->alphaCells += s.alphaCells; o->gmmPairs += s.gmmPairs; o->h2dBytes += s.h2dBytes; o->d2hBytes += s.d2hBytes;
+      o->msGmm = std::max(o->msGmm, s.msGmm); o->msBeta = std::max(o->msBeta, s.msBeta); o->msAlpha = std::max(o->msAlpha, s.msAlpha);
+      o->msStats = std::max(o->msStats, s.msStats); o->msExpand = std::max(o->msExpand, s.msExpand);
+   }
+   return HFB_OK;
+}
+extern "C" int hfbgpu_reset_stats(hfbgpu_ctx *c)
+{
+   if (!c) return HFB_EINVAL;
+   for (auto *k : c->kids) hfbgpu_reset_stats(k);
+   memset(&c->stats, 0, sizeof(c->stats));
+   return HFB_OK;
+}
+extern "C" int hfbgpu_set_timing(hfbgpu_ctx *c, int on)
+{
+   if (!c) return HFB_EINVAL;
+   for (auto *k : c->kids) hfbgpu_set_timing(k, on);
+   c->timing = on != 0;
+   return HFB_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 // wave construction: the host only sizes things; the tables are built by prep_kernel
@@ -1029,8 +1079,157 @@ static int wait_impl(hfbgpu_ctx *c)
    return rcAll;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Device groups: one host thread, one context, N GPUs (SURVEY 8b "device list", 8e).
+// hfbgpu_create_multi builds one child context per device; every batch is cut into N contiguous utterance ranges of
+// equal sum(T * Q) and submitted to the children back to back (their kernels run concurrently, each on its own GPU);
+// the per-GPU FP64 accumulators are combined ON THE DEVICE by a kernel on child 0 that reads the peers' buffers over
+// NVLink (peer access; a staged cudaMemcpyPeer where that is unavailable) -- the in-library equivalent of the one
+// all-reduce per pass, and of what `HERest -p 0` does with the per-process dumps (HTrain.c:1626-1687).
+// ------------------------------------------------------------------------------------------
+#define HFB_MAX_GROUP 16
+struct PeerPtrs { const double *p[HFB_MAX_GROUP]; };
+
+__global__ void acc_sum_peers_kernel(double *__restrict__ dst, PeerPtrs src, int n, long long count)
+{
+   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+      double a = dst[i];
+      for (int k = 0; k < n; k++) a += src.p[k][i];
+      dst[i] = a;
+   }
+}
+
+static bool is_group(const hfbgpu_ctx *c) { return c && !c->kids.empty(); }
+
+static int group_reduce(hfbgpu_ctx *g)
+{
+   int rcAll = HFB_OK;
+   for (auto *k : g->kids) { int rc = wait_impl(k); if (rc && !rcAll) rcAll = rc; }
+   if (rcAll) return rcAll;
+   if (g->reduced || g->kids.size() < 2) { g->reduced = true; return HFB_OK; }
+   hfbgpu_ctx *k0 = g->kids[0];
+   const long long count = k0->L.count;
+   for (auto *k : g->kids) { CK(cudaSetDevice(k->device)); CK(cudaStreamSynchronize(k->stream)); }
+   CK(cudaSetDevice(k0->device));
+   PeerPtrs pp;
+   int n = 0;
+   std::vector<double *> staged;
+   for (size_t i = 1; i < g->kids.size(); i++) {
+      hfbgpu_ctx *k = g->kids[i];
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, k0->device, k->device);
+      if (can) {
+         cudaError_t e = cudaDeviceEnablePeerAccess(k->device, 0);
+         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+         cudaGetLastError();
+      }
+      if (can) pp.p[n++] = k->dAcc.p;
+      else {                                            // no NVLink / PCIe peer path: stage a copy on device 0
+         double *tmp = nullptr;
+         if (cudaMalloc(&tmp, (size_t)count * sizeof(double)) != cudaSuccess) { cudaGetLastError(); for (auto *t : staged) cudaFree(t); return HFB_ENOMEM; }
+         staged.push_back(tmp);
+         CK(cudaMemcpyPeerAsync(tmp, k0->device, k->dAcc.p, k->device, (size_t)count * sizeof(double), k0->stream));
+         pp.p[n++] = tmp;
+      }
+   }
+   const int grid = std::max(1, std::min(k0->smCount * 8, (int)((count + 255) / 256)));
+   acc_sum_peers_kernel<<<grid, 256, 0, k0->stream>>>(k0->dAcc.p, pp, n, count);
+   k0->stats.launches++; k0->stats.launchesMisc++;
+   CK(cudaGetLastError());
+   CK(cudaStreamSynchronize(k0->stream));
+   for (auto *t : staged) cudaFree(t);
+   for (size_t i = 1; i < g->kids.size(); i++) {        // their content now lives in child 0
+      hfbgpu_ctx *k = g->kids[i];
+      CK(cudaSetDevice(k->device));
+      CK(cudaMemsetAsync(k->dAcc.p, 0, (size_t)count * sizeof(double), k->stream));
+      CK(cudaStreamSynchronize(k->stream));
+   }
+   g->reduced = true;
+   return HFB_OK;
+}
+
+// contiguous utterance ranges of (nearly) equal sum(T * Q)
+static void group_split(const hfb_batch *b, int n, std::vector<int> &cut)
+{
+   cut.assign(n + 1, 0);
+   std::vector<double> pre((size_t)b->numUtt + 1, 0.0);
+   for (int u = 0; u < b->numUtt; u++)
+      pre[u + 1] = pre[u] + (double)(b->frameOff[u + 1] - b->frameOff[u]) * (double)std::max(1, b->labOff[u + 1] - b->labOff[u]);
+   int u = 0;
+   for (int k = 1; k < n; k++) {
+      const double want = pre[b->numUtt] * k / n;
+      while (u < b->numUtt && pre[u + 1] <= want) u++;
+      cut[k] = u;
+   }
+   cut[n] = b->numUtt;
+}
+
+static int group_submit(hfbgpu_ctx *g, const hfb_batch *b, const float *feat2, hfb_utt_result *res, const hfb_beams *beams, int mode)
+{
+   // mode 0 = hfbgpu_submit (asynchronous), 1 = hfbgpu_accumulate (blocking), 2 = hfbgpu_accumulate_retrain
+   if (!b || !res) return HFB_EINVAL;
+   if (b->numUtt < 0 || (b->numUtt > 0 && (!b->frameOff || !b->feat || !b->labOff || !b->lab))) return HFB_EINVAL;
+   const int n = (int)g->kids.size();
+   std::vector<int> cut;
+   group_split(b, n, cut);
+   g->submitSeq++;
+   g->reduced = false;
+   std::vector<int64_t> tk((size_t)n, 0);
+   int rcAll = HFB_OK;
+   for (int k = 0; k < n; k++) {
+      hfbgpu_ctx *kid = g->kids[k];
+      tk[k] = kid->submitSeq;
+      if (cut[k + 1] == cut[k]) continue;
+      hfb_batch sub = *b;                               // offsets stay absolute: the children index feat / lab with them
+      sub.numUtt = cut[k + 1] - cut[k]; sub.frameOff = b->frameOff + cut[k]; sub.labOff = b->labOff + cut[k];
+      kid->submitSeq++;
+      int rc = submit_impl(kid, &sub, res + cut[k], beams, false, mode == 0 ? 1 : (int)hfbgpu_ctx::NSLOT, feat2);
+      tk[k] = kid->submitSeq;
+      if (rc && !rcAll) rcAll = rc;
+   }
+   if (g->kidTickets.size() < 64) g->kidTickets.resize(64);
+   g->kidTickets[(size_t)(g->submitSeq % 64)] = tk;
+   if (mode != 0)
+      for (auto *kid : g->kids) { int rc = wait_impl(kid); if (rc && !rcAll) rcAll = rc; }
+   return rcAll;
+}
+
+extern "C" int hfbgpu_create_multi(hfbgpu_ctx **out, const hfb_model *m, const hfb_options *opt, const int32_t *devices, int32_t numDevices)
+{
+   if (!out || !m || !opt || !devices || numDevices < 1 || numDevices > HFB_MAX_GROUP) return HFB_EINVAL;
+   *out = nullptr;
+   for (int i = 0; i < numDevices; i++)
+      for (int j = 0; j < i; j++) if (devices[i] == devices[j]) { g_lastError = "device listed twice"; return HFB_EINVAL; }
+   hfbgpu_ctx *g = new hfbgpu_ctx();
+   g->opt = *opt;
+   memset(&g->stats, 0, sizeof(g->stats));
+   for (int i = 0; i < numDevices; i++) {
+      hfb_options o = *opt;
+      o.device = devices[i];
+      hfbgpu_ctx *kid = nullptr;
+      int rc = hfbgpu_create(&kid, m, &o);
+      if (rc) { for (auto *k : g->kids) hfbgpu_destroy(k); delete g; return rc; }
+      g->kids.push_back(kid);
+   }
+   g->device = devices[0];
+   g->L = g->kids[0]->L;
+   *out = g;
+   return HFB_OK;
+}
+
+extern "C" int hfbgpu_num_devices(hfbgpu_ctx *c) { return !c ? 0 : (is_group(c) ? (int)c->kids.size() : 1); }
+
+// Sums the per-device accumulators into the first device's buffer (no-op for a single-device context).
+extern "C" int hfbgpu_reduce_accs(hfbgpu_ctx *c)
+{
+   if (!c) return HFB_EINVAL;
+   return is_group(c) ? group_reduce(c) : wait_impl(c);
+}
+
 extern "C" int hfbgpu_accumulate(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, const hfb_beams *beams)
 {
+   if (is_group(c)) return group_submit(c, b, nullptr, res, beams, 1);
    int rc = submit_impl(c, b, res, beams, false, hfbgpu_ctx::NSLOT);
    int rc2 = wait_impl(c);
    return rc ? rc : rc2;
@@ -1038,6 +1237,7 @@ extern "C" int hfbgpu_accumulate(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_resu
 
 extern "C" int hfbgpu_accumulate_device(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, const hfb_beams *beams)
 {
+   if (is_group(c)) { g_lastError = "device-resident features belong to one GPU: use host features with a device group"; return HFB_EUNSUPPORTED; }
    int rc = submit_impl(c, b, res, beams, true, hfbgpu_ctx::NSLOT);
    int rc2 = wait_impl(c);
    return rc ? rc : rc2;
@@ -1048,6 +1248,7 @@ extern "C" int hfbgpu_accumulate_retrain(hfbgpu_ctx *c, const hfb_batch *b, cons
                                          const hfb_beams *beams, int featOnDevice)
 {
    if (!feat2) return HFB_EINVAL;
+   if (is_group(c)) return featOnDevice ? HFB_EUNSUPPORTED : group_submit(c, b, feat2, res, beams, 2);
    int rc = submit_impl(c, b, res, beams, featOnDevice != 0, hfbgpu_ctx::NSLOT, feat2);
    int rc2 = wait_impl(c);
    return rc ? rc : rc2;
@@ -1055,6 +1256,7 @@ extern "C" int hfbgpu_accumulate_retrain(hfbgpu_ctx *c, const hfb_batch *b, cons
 
 extern "C" int hfbgpu_submit(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, const hfb_beams *beams, int featOnDevice)
 {
+   if (is_group(c)) return featOnDevice ? HFB_EUNSUPPORTED : group_submit(c, b, nullptr, res, beams, 0);
    if (c) c->submitSeq++;
    return submit_impl(c, b, res, beams, featOnDevice != 0, 1);
 }
@@ -1065,6 +1267,13 @@ extern "C" int64_t hfbgpu_last_ticket(hfbgpu_ctx *c) { return c ? c->submitSeq :
 extern "C" int hfbgpu_wait_ticket(hfbgpu_ctx *c, int64_t ticket)
 {
    if (!c) return HFB_EINVAL;
+   if (is_group(c)) {
+      if (ticket <= c->submitSeq - 64 || ticket > c->submitSeq) return hfbgpu_wait(c);
+      const std::vector<int64_t> &tk = c->kidTickets[(size_t)(ticket % 64)];
+      int rcAll = HFB_OK;
+      for (size_t k = 0; k < c->kids.size(); k++) { int rc = hfbgpu_wait_ticket(c->kids[k], tk[k]); if (rc && !rcAll) rcAll = rc; }
+      return rcAll;
+   }
    CK(cudaSetDevice(c->device));
    int rcAll = HFB_OK;
    for (int i = 0; i < hfbgpu_ctx::NSLOT; i++) {        // oldest first
@@ -1076,7 +1285,15 @@ extern "C" int hfbgpu_wait_ticket(hfbgpu_ctx *c, int64_t ticket)
    return rcAll;
 }
 
-extern "C" int hfbgpu_wait(hfbgpu_ctx *c) { return wait_impl(c); }
+extern "C" int hfbgpu_wait(hfbgpu_ctx *c)
+{
+   if (is_group(c)) {
+      int rcAll = HFB_OK;
+      for (auto *k : c->kids) { int rc = wait_impl(k); if (rc && !rcAll) rcAll = rc; }
+      return rcAll;
+   }
+   return wait_impl(c);
+}
 
 // ------------------------------------------------------------------------------------------
 // M-step on the device
@@ -1085,6 +1302,7 @@ extern "C" int hfbgpu_mstep(hfbgpu_ctx *c, const hfb_mstep_options *opt, hfb_mst
 {
    if (!c || !opt || !out || !out->mean || !out->var || !out->gConst || !out->mixWeight || !out->transP || !opt->varFloor)
       return HFB_EINVAL;
+   if (is_group(c)) { int rc = group_reduce(c); return rc ? rc : hfbgpu_mstep(c->kids[0], opt, out); }
    CK(cudaSetDevice(c->device));
    { int rc = wait_impl(c); if (rc) return rc; }
    const HostModel &h = c->hm;
@@ -1146,6 +1364,11 @@ extern "C" int hfbgpu_mstep(hfbgpu_ctx *c, const hfb_mstep_options *opt, hfb_mst
 extern "C" int hfbgpu_set_qualifiers(hfbgpu_ctx *c, const hfb_qualifiers *q)
 {
    if (!c) return HFB_EINVAL;
+   if (is_group(c)) {
+      int rcAll = HFB_OK;
+      for (auto *k : c->kids) { int rc = hfbgpu_set_qualifiers(k, q); if (rc && !rcAll) rcAll = rc; }
+      return rcAll;
+   }
    { int rc = wait_impl(c); if (rc) return rc; }
    if (!q) { c->qual = FeatQual(); return HFB_OK; }
    const int orders = 1 + (q->delWin > 0) + (q->accWin > 0) + (q->thirdWin > 0);
@@ -1167,6 +1390,7 @@ extern "C" int hfbgpu_set_qualifiers(hfbgpu_ctx *c, const hfb_qualifiers *q)
 extern "C" int hfbgpu_expand_features(hfbgpu_ctx *c, const float *src, const int64_t *frameOff, int32_t numUtt, float *dst)
 {
    if (!c || !src || !frameOff || !dst || numUtt < 0) return HFB_EINVAL;
+   if (is_group(c)) return hfbgpu_expand_features(c->kids[0], src, frameOff, numUtt, dst);
    if (!c->qual.enabled) { g_lastError = "hfbgpu_set_qualifiers has not been called"; return HFB_EINVAL; }
    if (numUtt == 0) return HFB_OK;
    CK(cudaSetDevice(c->device));
@@ -1216,6 +1440,7 @@ extern "C" int hfbgpu_state_loglik(hfbgpu_ctx *c, const float *feat, int32_t T, 
                                    float *out, float *mixOut)
 {
    if (!c || !feat || !states || !out || T < 1 || n < 1) return HFB_EINVAL;
+   if (is_group(c)) return hfbgpu_state_loglik(c->kids[0], feat, T, states, n, out, mixOut);
    if (mixOut) { g_lastError = "per-mixture output is not exported by the GPU path"; return HFB_EUNSUPPORTED; }
    CK(cudaSetDevice(c->device));
    { int rc = wait_impl(c); if (rc) return rc; }        // borrows slot 0's buffers: never under an in-flight wave

@@ -40,13 +40,18 @@ class _Ticket:
 
 class ForwardBackward:
     def __init__(self, fm: FlatModel, prune=None, min_frwd_p: float = 10.0, uflags: int = 15,
-                 device: int = 0, gmm_kernel: int = 0, workspace_bytes: int = 0):
+                 device: int = 0, gmm_kernel: int = 0, workspace_bytes: int = 0, devices=None):
+        """`devices`: list of CUDA ordinals -> one context driving all of them (hfbgpu_create_multi)."""
         self.lib = capi.load()
         self.fm = fm
-        self.opt = make_options(prune, min_frwd_p, uflags, device, gmm_kernel, workspace_bytes)
+        self.opt = make_options(prune, min_frwd_p, uflags, device if not devices else devices[0], gmm_kernel, workspace_bytes)
         self._m = fm.c_struct()
         h = C.c_void_p()
-        rc = self.lib.hfbgpu_create(C.byref(h), C.byref(self._m), C.byref(self.opt))
+        if devices:
+            arr = (C.c_int32 * len(devices))(*devices)
+            rc = self.lib.hfbgpu_create_multi(C.byref(h), C.byref(self._m), C.byref(self.opt), arr, len(devices))
+        else:
+            rc = self.lib.hfbgpu_create(C.byref(h), C.byref(self._m), C.byref(self.opt))
         if rc != 0:
             raise capi.HfbError(rc, "hfbgpu_create")
         self.h = h

@@ -171,6 +171,18 @@ int  hfbgpu_device_count(void);
 int hfbgpu_create(hfbgpu_ctx **ctx, const hfb_model *m, const hfb_options *opt);
 int hfbgpu_destroy(hfbgpu_ctx *ctx);
 
+/* The same on a LIST of devices (SURVEY.md 8b "device list", 8e): one context, one host thread, N GPUs.  Replaces the
+ * reference's only parallelism -- N `HERest -p k` processes + the `-p 0` merge of their dumps (HERest.c:514-521,
+ * HTrain.c:1626-1687).  Every batch passed to hfbgpu_accumulate / hfbgpu_submit / hfbgpu_accumulate_retrain (HOST
+ * features) is cut into numDevices contiguous utterance ranges of equal sum(T * Q), one per GPU; hfbgpu_get_accs,
+ * hfbgpu_mstep and hfbgpu_reduce_accs first sum the per-GPU FP64 accumulators into the first device's buffer with a
+ * kernel that reads the peers' buffers over NVLink (peer access), so the caller sees ONE set of accumulators.
+ * opt->device is ignored; hfbgpu_set_stream and device-resident features are single-device only.                    */
+int hfbgpu_create_multi(hfbgpu_ctx **ctx, const hfb_model *m, const hfb_options *opt,
+                        const int32_t *devices, int32_t numDevices);
+int hfbgpu_num_devices(hfbgpu_ctx *ctx);
+int hfbgpu_reduce_accs(hfbgpu_ctx *ctx);
+
 /* Run on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream) instead
  * of the library's own, so the caller's events bracket the kernels.  NULL restores it. */
 int hfbgpu_set_stream(hfbgpu_ctx *ctx, void *cudaStream);
