@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 128 ? 7 : 1024 / MAXT) beta_l2r_
 // instruction and cost 0.26 of the 1.19 ms; staging them through shared memory for 256-byte contiguous stores cost more
 // than it saved: 1.69 ms.)
 #define BW_NM 4
+template <bool ALUCVT>
 __global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
 {
    const UttDesc &u = W.utt[blockIdx.x];
@@ -275,9 +276,9 @@ __global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
             lMax[k] = LZERO_D; un0[k] = un1[k] = un2[k] = xNew[k] = LZERO_D;
             if (active[k]) {
                const double ex = (q + 1 >= lo1 && q + 1 <= hi1) ? exN : LZERO_D;            // :1225
-               const double n2 = ladd_nz_b(r[k].a2x + ex, r[k].a22 + u2[k]);               // :1228-1236
-               const double n1 = ladd_nz_b(r[k].a11 + u1[k], r[k].a12 + u2[k]);
-               const double n0 = ladd_nz_b(r[k].a00 + u0[k], r[k].a01 + u1[k]);
+               const double n2 = (ALUCVT ? ladd_nz : ladd_nz_b)(r[k].a2x + ex, r[k].a22 + u2[k]);               // :1228-1236
+               const double n1 = (ALUCVT ? ladd_nz : ladd_nz_b)(r[k].a11 + u1[k], r[k].a12 + u2[k]);
+               const double n0 = (ALUCVT ? ladd_nz : ladd_nz_b)(r[k].a00 + u0[k], r[k].a01 + u1[k]);
                un0[k] = (double)c0 + n0; un1[k] = (double)c1 + n1; un2[k] = (double)c2 + n2;
                const double x = r[k].aE + un0[k];                                          // :1242-1250
                double *bg = bgT + 160 * k;

@@ -825,7 +825,11 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
       if (l2r && w.maxQ <= 1024) {
          const size_t fsm = beta_fast_smem_bytes(w.maxQ);
          const bool pruning = c->opt.pruneInit < 0.5 * HFB_NOPRUNE;
-         if (w.maxQ <= 32 * BW_NM && !getenv("HFBGPU_NO_BETA_WARP")) beta_l2r_warp_kernel<<<nU, 32, 0, sr>>>(c->dm, W);
+         if (w.maxQ <= 32 * BW_NM && !getenv("HFBGPU_NO_BETA_WARP")) {
+            // HFBGPU_BETA_ALU: the FP64 <-> FP32 conversions of the log-add as integer operations (experiment)
+            if (getenv("HFBGPU_BETA_ALU")) beta_l2r_warp_kernel<true><<<nU, 32, 0, sr>>>(c->dm, W);
+            else beta_l2r_warp_kernel<false><<<nU, 32, 0, sr>>>(c->dm, W);
+         }
          else if (w.maxQ <= 128) beta_l2r_kernel<128><<<nU, nt, fsm, sr>>>(c->dm, W, 0);  // 72 registers, 7 CTAs/SM
          else if (w.maxQ <= 256) beta_l2r_kernel<256><<<nU, nt, fsm, sr>>>(c->dm, W, 0);
          else if (pruning && !getenv("HFBGPU_NO_SLIDE")) {
