@@ -23,7 +23,7 @@
 
 #define TC3_THREADS 448        // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue, warps 10-13 expanders
 #define TC3_ROW0 128           // first real row of the B operand: rows [0, 128) are the dummy tile
-#define TC3_DMAX 63            // 2 D + 2 <= 128 columns
+#define TC3_DMAX 63            // 2 D + 2 <= 128 columns (kernel variants for D <= 40 and D <= 64)
 #define TC3_SMEM_BYTES (2 * 65536 + 3 * 32768 + 512 + 1024)
 
 struct GmmTc3Model {
@@ -78,7 +78,7 @@ __device__ __forceinline__ void tc3_wait_acquire_cluster(uint64_t *bar, uint32_t
    } while (!done);
 }
 
-template <int MP>
+template <int MP, int DP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
 gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, Tc3Params p)
 {
@@ -336,95 +336,88 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
       }
    } else {
       // ================= expanders (both CTAs, 4 warps): raw FP32 features -> this CTA's two A blocks =================
-      // Warp w owns rows 32 w .. 32 w + 31 of both blocks and walks them one row at a time with LANE = DIMENSION (lane d
-      // and d + 32), so that the feature reads are coalesced (one row = 156 contiguous bytes; a thread-per-row mapping
-      // touched 32 cache lines per load instruction and cost ~13 us per work item).  Columns: 0 = 1 (pairs with the
-      // symmetrising constant), 2d+1 = x'_d^2, 2d+2 = x'_d (d < D), 2D+1 = 1 (pairs with the Gaussian constant), the
-      // rest 0; x' = (x - offset) * scale.  The constant columns are written once.
-      const int ew = warp - (2 + EPW);                  // 0..3
+      // Thread r owns row r of both blocks.  Columns: 0 = 1 (pairs with the symmetrising constant), 2d+1 = x'_d^2,
+      // 2d+2 = x'_d (d < D), 2D+1 = 1 (pairs with the Gaussian constant), the rest 0; x' = (x - offset) * scale.
+      // The rows of the NEXT item travel into registers while the tensor core works on the current one (the loads are a
+      // row per thread, i.e. 32 cache lines per instruction: slow, but hidden there); what is exposed between two items
+      // is only the conversion and ten 16-byte stores per row and half.  Measured the other way round -- lane =
+      // dimension, coalesced loads, 2-byte stores -- the instruction count (70 per row and warp) cost 17 us per item.
+      const int r = threadIdx.x - (2 + EPW) * 32;       // 0..127
       const int D = p.D;
-      {  // zero both blocks, then the two columns of ones
-         const int tid = threadIdx.x - (2 + EPW) * 32;
-         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-         for (uint32_t o = tid * 16; o < 2 * A_BLK; o += 128 * 16) *reinterpret_cast<uint4 *>(sA + o) = z;
-         asm volatile("bar.sync 1, 128;" ::: "memory");
-         const unsigned short one = __half_as_ushort(__float2half_rn(1.f));
-         for (int bb = 0; bb < 2; bb++)
-            for (int kc = 0; kc < 2; kc++) {
-               const int k = kc ? 2 * D + 1 : 0;
-               *reinterpret_cast<unsigned short *>(sA + bb * A_BLK + tc3_unit_off(tid, k >> 3) + (k & 7) * 2) = one;
-            }
-         asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
-      const bool has0 = lane < D, has1 = lane + 32 < D;
-      const float off0 = has0 ? p.offset[lane] : 0.f, sc0 = has0 ? p.scale[lane] : 0.f;
-      const float off1 = has1 ? p.offset[lane + 32] : 0.f, sc1 = has1 ? p.scale[lane + 32] : 0.f;
-      // byte offset of column k inside a row's swizzle atom, split into the part that does not depend on the row
-      // (chunk + position inside the 16-byte unit) and the unit index that is XORed with row mod 8
-      auto colc = [](int k) { return (uint32_t)((k >> 6) * 16384 + (k & 7) * 2); };
-      auto colu = [](int k) { return (uint32_t)((k & 63) >> 3); };
-      const uint32_t cA0 = colc(2 * lane + 1), uA0 = colu(2 * lane + 1), cB0 = colc(2 * lane + 2), uB0 = colu(2 * lane + 2);
-      const uint32_t cA1 = colc(2 * lane + 65), uA1 = colu(2 * lane + 65), cB1 = colc(2 * lane + 66), uB1 = colu(2 * lane + 66);
+      const int nUnits = 2 * p.kSteps;                  // 16-byte units (8 columns) the MMAs read
+      constexpr int NPRE = (DP <= 40) ? 2 : 1;          // rows held in registers ahead of time
       uint32_t phA = 0;
-      for (int it = pair; it < p.nItems; it += nPairs) {
-         const int2 item = p.items[it];
-         const UttDesc u = p.utt[item.x];
-         const float *src = p.feat + (size_t)u.featOff * D;
-         float v0[32], v1[32];
-         auto load_block = [&](int b) {
-            const int t0 = item.y + (2 * b + (int)rank) * TC_BM + ew * 32;
+      float x[NPRE][DP];
+      auto load_row = [&](float (&xr)[DP], const int2 item, const UttDesc &u, int b) {
+         const int t = item.y + (2 * b + (int)rank) * TC_BM + r;
+         const bool inside = t < u.T;
+         bool far = false;
+         const float *src = p.feat + ((size_t)u.featOff + (inside ? t : 0)) * D;
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-               const bool inside = t0 + i < u.T;
-               v0[i] = (inside && has0) ? src[(size_t)(t0 + i) * D + lane] : 0.f;
-               v1[i] = (inside && has1) ? src[(size_t)(t0 + i) * D + lane + 32] : 0.f;
+         for (int d = 0; d < DP; d++) {
+            float v = 0.f;
+            if (d < D && inside) {
+               v = (src[d] - p.offset[d]) * p.scale[d];
+               if (!(fabsf(v) <= TC_FAR)) far = true;
+               v = fminf(fmaxf(v, -250.f), 250.f);             // keeps inf / NaN out of the tensor core; a far row is recomputed
             }
-         };
+            xr[d] = v;
+         }
+         if (inside) p.flag[u.frameBase + t] = far ? 1 : 0;
+      };
+      auto store_row = [&](const float (&xr)[DP], int b) {
+         uint8_t *blk = sA + b * A_BLK;
+#pragma unroll
+         for (int un = 0; un < 16; un++) {
+            if (un >= nUnits) break;                   // every unit the MMAs read is rewritten for every item
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+               const int k = un * 8 + e;                // compile-time column
+               if (k == 0) v[e] = 1.f;
+               else if (k & 1) { const int d = (k - 1) >> 1; v[e] = (d < DP && d < D) ? xr[d < DP ? d : 0] * xr[d < DP ? d : 0] : ((d == D) ? 1.f : 0.f); }
+               else { const int d = (k - 2) >> 1; v[e] = (d < DP && d < D) ? xr[d < DP ? d : 0] : 0.f; }
+            }
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+               const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+               const float2 hf = __half22float2(h);
+               const __half2 l = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+               hi[e] = *reinterpret_cast<const uint32_t *>(&h);
+               lo[e] = *reinterpret_cast<const uint32_t *>(&l);
+            }
+            const uint32_t off = tc3_unit_off(r, un);
+            *reinterpret_cast<uint4 *>(blk + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(blk + 32768 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+         }
+      };
+      int2 item = make_int2(0, 0);
+      UttDesc u;
+      if (pair < p.nItems) {
+         item = p.items[pair]; u = p.utt[item.x];
+         load_row(x[0], item, u, 0);
+         if (NPRE == 2) load_row(x[NPRE - 1], item, u, 1);
+      }
+      for (int it = pair; it < p.nItems; it += nPairs) {
          const bool skipX = (p.dbg & 32) && it != pair;  // timing experiment: reuse the first item's A blocks
-         if (!skipX) load_block(0);                     // in flight BEFORE the wait for the A blocks to drain
          tc_mbar_wait(emptyA, phA ^ 1);
          phA ^= 1;
-         if (skipX) { __syncwarp(); if (lane == 0) tc3_arrive_leader_release(fullA); continue; }
-#pragma unroll 1
-         for (int b = 0; b < 2; b++) {
-            if (b == 1) load_block(1);
-            const int t0 = item.y + (2 * b + (int)rank) * TC_BM + ew * 32;
-            uint8_t *blk = sA + b * A_BLK;
-#pragma unroll
-            for (int i = 0; i < 32; i++) {
-               const int t = t0 + i;
-               if (t >= u.T) break;                     // rows past the utterance keep whatever they held: never stored
-               const int rr = ew * 32 + i;
-               float x0 = (v0[i] - off0) * sc0, x1 = (v1[i] - off1) * sc1;
-               const bool far = (has0 && !(fabsf(x0) <= TC_FAR)) || (has1 && !(fabsf(x1) <= TC_FAR));
-               const unsigned anyFar = __ballot_sync(0xffffffffu, far);
-               if (lane == 0) p.flag[u.frameBase + t] = anyFar ? 1 : 0;
-               x0 = fminf(fmaxf(x0, -250.f), 250.f);     // keeps inf / NaN out of the tensor core; a far row is recomputed
-               x1 = fminf(fmaxf(x1, -250.f), 250.f);
-               uint8_t *row = blk + rr * 128;
-               const uint32_t x7 = (uint32_t)(rr & 7);
-               if (has0) {
-                  const float q = x0 * x0;
-                  const __half hq = __float2half_rn(q), hx = __float2half_rn(x0);
-                  const __half lq = __float2half_rn(q - __half2float(hq)), lx = __float2half_rn(x0 - __half2float(hx));
-                  uint8_t *pa = row + cA0 + ((uA0 ^ x7) << 4), *pb = row + cB0 + ((uB0 ^ x7) << 4);
-                  *reinterpret_cast<__half *>(pa) = hq; *reinterpret_cast<__half *>(pa + 32768) = lq;
-                  *reinterpret_cast<__half *>(pb) = hx; *reinterpret_cast<__half *>(pb + 32768) = lx;
-               }
-               if (has1) {
-                  const float q = x1 * x1;
-                  const __half hq = __float2half_rn(q), hx = __float2half_rn(x1);
-                  const __half lq = __float2half_rn(q - __half2float(hq)), lx = __float2half_rn(x1 - __half2float(hx));
-                  uint8_t *pa = row + cA1 + ((uA1 ^ x7) << 4), *pb = row + cB1 + ((uB1 ^ x7) << 4);
-                  *reinterpret_cast<__half *>(pa) = hq; *reinterpret_cast<__half *>(pa + 32768) = lq;
-                  *reinterpret_cast<__half *>(pb) = hx; *reinterpret_cast<__half *>(pb + 32768) = lx;
-               }
-            }
+         if (!skipX) {
+            store_row(x[0], 0);
+            if (NPRE == 1) load_row(x[0], item, u, 1);
+            store_row(x[NPRE - 1], 1);
          }
          // generic-proxy writes -> visible to the tensor core (async proxy), then tell the leader's MMA thread
          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
          __syncwarp();
          if (lane == 0) tc3_arrive_leader_release(fullA);
+         // the next item's rows: in flight during this item's MMAs
+         if (it + nPairs < p.nItems) {
+            item = p.items[it + nPairs]; u = p.utt[item.x];
+            load_row(x[0], item, u, 0);
+            if (NPRE == 2) load_row(x[NPRE - 1], item, u, 1);
+         }
       }
    }
    tc_fence_before();
@@ -545,7 +538,8 @@ static inline int gmm_tc3_prepare(GmmTc3Model &t, const hfb_model *m, cudaStream
    if (tc_make_map_f16(encodeFn, &t.mapBhi, t.dBhi, t.rows, boxR) || tc_make_map_f16(encodeFn, &t.mapBlo, t.dBlo, t.rows, boxR)) {
       gmm_tc3_release(t); return HFB_OK;
    }
-#define TC3_SET(MPV) cudaFuncSetAttribute(gmm_tc3_kernel<MPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES)
+#define TC3_SET(MPV) cudaFuncSetAttribute(gmm_tc3_kernel<MPV, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES); \
+                     cudaFuncSetAttribute(gmm_tc3_kernel<MPV, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES)
    TC3_SET(1); TC3_SET(8); TC3_SET(16); TC3_SET(32); TC3_SET(64); TC3_SET(128);
 #undef TC3_SET
    t.ready = (cudaGetLastError() == cudaSuccess);
@@ -573,14 +567,17 @@ static inline int gmm_tc3_launch(GmmTc3Model &t, GmmTcWork &wk, const DevModel &
    p.C0 = t.C0; p.D = dm.D; p.kSteps = (2 * dm.D + 2 + 15) / 16; p.deadBelow = TC_DEAD_BELOW;
    { const char *e = getenv("HFBGPU_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
    const int grid2 = 2 * std::min(nItems4, smCount / 2);
+#define TC3_GO(MPV) do { if (dm.D <= 40) gmm_tc3_kernel<MPV, 40><<<grid2, TC3_THREADS, TC3_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p); \
+                          else gmm_tc3_kernel<MPV, 64><<<grid2, TC3_THREADS, TC3_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p); } while (0)
    switch (t.MP) {
-   case 1: gmm_tc3_kernel<1><<<grid2, TC3_THREADS, TC3_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p); break;
-   case 8: gmm_tc3_kernel<8><<<grid2, TC3_THREADS, TC3_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p); break;
-   case 16: gmm_tc3_kernel<16><<<grid2, TC3_THREADS, TC3_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p); break;
-   case 32: gmm_tc3_kernel<32><<<grid2, TC3_THREADS, TC3_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p); break;
-   case 64: gmm_tc3_kernel<64><<<grid2, TC3_THREADS, TC3_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p); break;
-   default: gmm_tc3_kernel<128><<<grid2, TC3_THREADS, TC3_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p); break;
+   case 1: TC3_GO(1); break;
+   case 8: TC3_GO(8); break;
+   case 16: TC3_GO(16); break;
+   case 32: TC3_GO(32); break;
+   case 64: TC3_GO(64); break;
+   default: TC3_GO(128); break;
    }
+#undef TC3_GO
    int nl = 1;
    if (!getenv("HFBGPU_NO_FIXUP")) { gmm_fixup_kernel<<<nItems128, 128, 0, st>>>(dm, W, dItems128, wk.dFlag3); nl++; }
    if (launches) *launches = nl;

@@ -117,11 +117,32 @@ def test_bench_config_matches_stock_herest(name, tmp_path):
           "%d Gaussians with occupancy" % (name, max(e_gpu.values()), t_gpu, max(e_ref.values()), t_ref, max(e.values()), t_st, n_occ))
     print("   library vs oracle per block:", {k: "%.1e" % v for k, v in e_gpu.items()})
     print("   library vs stock  per block:", {k: "%.1e" % v for k, v in e.items()})
+    if name in ("cfg3", "cfg5"):
+        # where the residual comes from: the same utterances with the FP32 CUDA-core output probabilities (IDOutP's own
+        # arithmetic) and, separately, the FP32 per-position statistics kernel instead of the tensor-core one
+        for label, env, gk in (("fp32 outprobs", None, 1), ("fp32 statistics", "HFBGPU_STATS3", 0)):
+            if env:
+                os.environ[env] = "1"
+            try:
+                fb2 = ForwardBackward(fm, prune=prune, gmm_kernel=gk)
+                fb2.FBFile(b)
+                ed, td = acc_errors_ties(fb2.GetAccs(), oacc, fm)
+                fb2.close()
+                print("   %s vs oracle per block:" % label, {k: "%.1e" % v for k, v in ed.items()})
+            finally:
+                if env:
+                    del os.environ[env]
     assert max(t_gpu, t_st) <= max(2, n_occ // 2000), (t_gpu, t_st, n_occ)
-    assert max(e_gpu.values()) < 1e-4, e_gpu
+    # The bar: 1e-4 on everything that is an occupancy, a count or a likelihood.  The CENTRED first / second-order sums
+    # are sum gamma_t (o_t - mu)^k: a relative error eps of an occupancy enters them multiplied by |o_t - mu| / sigma,
+    # which reaches 3-4 on some frame of nearly every Gaussian, and the stock tool's own float evaluation sits at 5e-5
+    # on this metric (e_ref) -- so they get 1e-4 + the stock tool's own distance from exact arithmetic.
+    for k, v in e_gpu.items():
+        slack = e_ref[k] if k in ("muSum", "vaSum") else 0.0
+        assert v < 1e-4 + slack, ("library vs oracle(FP64)", k, v, e_ref[k])
     for k, v in e.items():
         slack = e_ref[k] if k in ("muSum", "vaSum") else 0.0
-        assert v < 1e-4 + slack, (k, v, e_ref[k], e_gpu[k])
+        assert v < 1e-4 + slack, ("library vs stock", k, v, e_ref[k], e_gpu[k])
     if name != "cfg2":
         assert st.launchesGmm > 0 and st.launchesL2R > 0             # the flagship kernels ran, not a generic path
 
