@@ -343,7 +343,8 @@ def herest_gpu_tool(fm, cfg, prune, n_files=1024, gpu_index=0):
         import re
         m = re.search(r"(\d+) utterances through the fast loader, (\d+) through HParm", pb.stdout)
         rate = (n_files - n_small) * T / max(tb - ta, 1e-6)
-        return {"value": rate, "unit": "frames/s", "files": n_files, "frames": n_files * T, "wall_s": tb, "startup_s": ta,
+        prof = re.search(r"hfbgpu: host profile \(s\): (.*)", pb.stdout)
+        return {"host_profile_s": prof.group(1) if prof else None, "value": rate, "unit": "frames/s", "files": n_files, "frames": n_files * T, "wall_s": tb, "startup_s": ta,
                 "gpu_utilization_mean_pct": busy, "fast_loader_files": int(m.group(1)) if m else None,
                 "how": "`HERest_gpu -T 1 -u tmvw -p 1` (reference HERest + bridge + libhfbgpu) over %d feature files of %d "
                        "frames on local disk, one process, one GPU; marginal rate between %d and %d files so that MMF "

@@ -23,6 +23,7 @@
 #include <unistd.h>
 #include <fcntl.h>
 #include <pthread.h>
+#include <time.h>
 
 #include "hfbgpu.h"
 #include "hfbgpu_bridge.h"
@@ -76,7 +77,16 @@ static struct {
    short fastKind, fastSize;             /* header fields every fast-loaded file must carry */
    int fastFd; long fastT;               /* file opened by HFBGPU_FastLoad, consumed by HFBGPU_Queue */
    long nFast, nSlow;
+   /* host-side profile of the file loop (printed under -T 1): seconds spent in each part of the bridge */
+   double tInit, tLast, sQueue, sFastLoad, sReaderWait, sSubmit, sComplete, sOutside;
 } B;
+
+static double now_s(void)
+{
+   struct timespec ts;
+   clock_gettime(CLOCK_MONOTONIC, &ts);
+   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 /* Two pending batches: while the library works on one (hfbgpu_submit is asynchronous), HERest's own
    file loop (LoadLabs / LoadData, HERest.c:753-787) fills the other.  Features live in pinned host
@@ -321,6 +331,7 @@ void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pr
 
    memset(&B, 0, sizeof(B));
    B.hset = hset; B.uFlags = uFlags; B.trace = herestTrace; B.fastFd = -1;
+   B.tInit = now_s();
    if (fbInfo->twoModels) HError(7399, "hfbgpu bridge: 2-model re-estimation is not accelerated");
    if (hset->xf != NULL || (uFlags & (UPXFORM | UPSEMIT | UPMAP)))
       HError(7399, "hfbgpu bridge: transforms / MAP updates are not accelerated");
@@ -373,6 +384,7 @@ void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pr
    hfbgpu_acc_layout(&B.m, &B.L);
    printf("hfbgpu: %d physical HMMs, %d tied states, %d Gaussians, %d transition matrices on %d GPU(s)\n",
           B.nHmm, B.nSte, B.nMp, B.nTr, hfbgpu_num_devices(B.ctx));
+   B.tLast = now_s();
    fflush(stdout);
 }
 
@@ -381,8 +393,11 @@ void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pr
 static void Complete(Pending *p)
 {
    int u, rc;
+   double t0;
    if (!p->inflight) return;
+   t0 = now_s();
    rc = hfbgpu_wait_ticket(B.ctx, p->ticket);
+   B.sComplete += now_s() - t0;
    if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_wait_ticket failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
    for (u = 0; u < p->nUtt; u++) {
       const hfb_utt_result *r = &p->res[u];
@@ -418,7 +433,7 @@ static void Flush(void)
    hfb_batch b;
    int rc;
    if (p->nUtt == 0) return;
-   reader_wait(p);
+   { double t0 = now_s(); reader_wait(p); B.sReaderWait += now_s() - t0; }
    p->frameOff[p->nUtt] = p->nFrames; p->labOff[p->nUtt] = p->nLab;
    b.numUtt = p->nUtt; b.frameOff = p->frameOff; b.feat = p->feat; b.labOff = p->labOff; b.lab = p->lab;
    p->res = (hfb_utt_result *)calloc(p->nUtt, sizeof(hfb_utt_result));
@@ -432,7 +447,7 @@ static void Flush(void)
       Drain();
       return;
    }
-   rc = hfbgpu_submit(B.ctx, &b, p->res, NULL, 0);
+   { double t0 = now_s(); rc = hfbgpu_submit(B.ctx, &b, p->res, NULL, 0); B.sSubmit += now_s() - t0; }
    if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_submit failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
    p->inflight = 1; p->ticket = hfbgpu_last_ticket(B.ctx);
    cur ^= 1;
@@ -479,7 +494,10 @@ Boolean HFBGPU_FastLoad(UttInfo *utt, char *datafn, char *datafn2)
    unsigned char h[12];
    unsigned int ns; unsigned short ss, kd;
    int fd;
+   double t0;
    if (B.ctx == NULL || B.fastState != 1 || utt->twoDataFiles || datafn2 != NULL) return FALSE;
+   t0 = now_s();
+   B.sOutside += t0 - B.tLast;                              /* HERest's own code since the bridge was last left (LoadLabs ...) */
    fd = open(datafn, O_RDONLY);
    if (fd < 0) return FALSE;                                /* let LoadData report it */
    if (pread(fd, h, 12, 0) != 12) { close(fd); return FALSE; }
@@ -488,6 +506,7 @@ Boolean HFBGPU_FastLoad(UttInfo *utt, char *datafn, char *datafn2)
    if ((short)kd != B.fastKind || (short)ss != B.fastSize || ns == 0 || ns > 100000000u) { close(fd); return FALSE; }
    utt->T = (int)ns;
    B.fastFd = fd; B.fastT = (long)ns;
+   B.tLast = now_s(); B.sFastLoad += B.tLast - t0;
    return TRUE;
 }
 
@@ -499,6 +518,8 @@ Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
    LLink lab;
    Pending *p = &P[cur];
    int q, t, k, T = utt->T, Q = utt->Q, D = B.D;
+   double tq0 = now_s();
+   B.sOutside += tq0 - B.tLast;
    B.twoData = utt->twoDataFiles ? 1 : 0;
    if (!p->frameOff) {
       p->frameOff = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (B.batchUtts + 2));
@@ -558,7 +579,9 @@ Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
    }
    p->names[p->nUtt] = strdup(datafn);
    p->nFrames += T; p->nLab += Q; p->nUtt++;
+   B.sQueue += now_s() - tq0;
    if (p->nUtt >= B.batchUtts || p->nFrames >= B.batchFrames) Flush();
+   B.tLast = now_s();
    return FALSE;
 }
 
@@ -568,8 +591,11 @@ void HFBGPU_Finish(int *totalT, LogDouble *totalPr)
    double *acc;
    int p, s, g, t, i, j, k, D = B.D, rc;
    long long o;
+   double tf0 = now_s(), tLoop;
+   B.sOutside += tf0 - B.tLast;
    Flush();
    Drain();
+   tLoop = now_s();
    acc = (double *)calloc((size_t)B.L.count, sizeof(double));
    rc = hfbgpu_get_accs(B.ctx, acc);
    if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_get_accs failed: %s", hfbgpu_strerror(rc));
@@ -614,7 +640,13 @@ void HFBGPU_Finish(int *totalT, LogDouble *totalPr)
    *totalPr += acc[B.L.totalPr];
    free(acc);
    reader_stop();
-   if (B.trace & 1) { printf("hfbgpu: %ld utterances through the fast loader, %ld through HParm\n", B.nFast, B.nSlow); fflush(stdout); }
+   if (B.trace & 1) {
+      printf("hfbgpu: %ld utterances through the fast loader, %ld through HParm\n", B.nFast, B.nSlow);
+      printf("hfbgpu: host profile (s): file loop %.3f = HERest's own code (LoadLabs, LoadData ...) %.3f + bridge queue %.3f + header reads %.3f"
+             " + wait for readers %.3f + submit %.3f + wait for GPU %.3f; final flush %.3f; download + scatter %.3f\n",
+             tf0 - B.tInit, B.sOutside, B.sQueue, B.sFastLoad, B.sReaderWait, B.sSubmit, B.sComplete, tLoop - tf0, now_s() - tLoop);
+      fflush(stdout);
+   }
    for (i = 0; i < 2; i++) {
       hfbgpu_host_free(P[i].feat); hfbgpu_host_free(P[i].feat2);
       free(P[i].frameOff); free(P[i].labOff); free(P[i].lab); free(P[i].names); free(P[i].res);
