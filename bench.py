@@ -40,7 +40,7 @@ WORKLOADS = {
     "cfg4": dict(desc="tied-state triphones 10k states x 32 mix", kind="tied", n_states=10000, M=32, n_phys=16000,
                  T=1000, Q=100),
     "cfg5": dict(desc="long utterances, 8k states x 16 mix, beam on", kind="tied", n_states=8000, M=16,
-                 n_phys=12000, T=6000, Q=667, prune=(250.0, 150.0, 1000.0)),
+                 n_phys=12000, T=6000, Q=667, prune=(250.0, 150.0, 1000.0), utts=96, workspace_gb=136),
 }
 ALG_FLOP_PER_GAUSS_FRAME = lambda D: 2 * (2 * D + 1)      # 158 for D = 39
 
@@ -392,9 +392,12 @@ def run_workload(name, args, rank, world, local_rank, dev, K, full):
     else:
         prune = cfg.get("prune")
     T, Q = cfg["T"], cfg["Q"]
-    n_utts = args.utts or (1024 if T <= 1000 else 64)
+    n_utts = args.utts or cfg.get("utts") or (1024 if T <= 1000 else 64)
     fm = make_model(cfg)
-    fb = ForwardBackward(fm, prune=prune, device=local_rank, gmm_kernel=args.gmm_kernel)
+    # long utterances: 0.33 GB of workspace each -- a wave should hold the whole step, so that the T-step chains of the
+    # recursions run once per step and not once per fragment of it
+    fb = ForwardBackward(fm, prune=prune, device=local_rank, gmm_kernel=args.gmm_kernel,
+                         workspace_bytes=int(cfg.get("workspace_gb", 0)) << 30)
     stream = torch.cuda.current_stream()
     fb.set_stream(stream.cuda_stream)
     batch, dfeat = make_batch(fm, cfg, n_utts, seed=1000 + rank, device=dev)
@@ -585,7 +588,7 @@ def main():
     else:
         prune = cfg.get("prune")
     T, Q = cfg["T"], cfg["Q"]
-    n_utts = args.utts or (1024 if T <= 1000 else 64)
+    n_utts = args.utts or cfg.get("utts") or (1024 if T <= 1000 else 64)
     cores = os.cpu_count() or 1
     config = {"workload": "%s: %s; %d utterances x %d frames x %d labels per step per GPU; pruning %s; minFrwdP 10; -u tmvw"
                           % (args.workload, cfg["desc"], n_utts, T, Q, ("-t %g %g %g" % prune) if prune else "off (HERest default)"),

@@ -66,6 +66,7 @@ static struct {
    /* HTK objects in flat order */
    HLink *hmm; StreamElem **ste; MixPDF **mp; SVector *meanV, *varV; SMatrix *trans;
    PMap pmHmm, pmSte, pmMp, pmMean, pmVar, pmTr;
+   PMap pmLab; int *labPhys; int labCap;   /* label id (LabId) -> physical HMM index, filled on first use */
    int nHmm, nSte, nMp, nMean, nVar, nTr;
    /* totals */
    long nOk, nSkipped;
@@ -78,7 +79,7 @@ static struct {
    int fastFd; long fastT;               /* file opened by HFBGPU_FastLoad, consumed by HFBGPU_Queue */
    long nFast, nSlow;
    /* host-side profile of the file loop (printed under -T 1): seconds spent in each part of the bridge */
-   double tInit, tLast, sQueue, sFastLoad, sReaderWait, sSubmit, sComplete, sOutside;
+   double tInit, tLoop0, tLast, sQueue, sFastLoad, sReaderWait, sSubmit, sComplete, sOutside;
 } B;
 
 static double now_s(void)
@@ -221,6 +222,7 @@ static void Flatten(HMMSet *hset)
    pm_init(&B.pmHmm, hset->numPhyHMM); pm_init(&B.pmSte, hset->numStates + 16);
    pm_init(&B.pmMp, hset->numMix + 16); pm_init(&B.pmMean, hset->numMix + 16);
    pm_init(&B.pmVar, hset->numMix + 16); pm_init(&B.pmTr, hset->numPhyHMM);
+   pm_init(&B.pmLab, hset->numLogHMM + 1024);
    B.hmm = (HLink *)calloc(hset->numPhyHMM + 1, sizeof(HLink));
 
    /* pass 1: number physical HMMs (HMMScan order = dump order), states, pdfs, vectors, matrices */
@@ -384,8 +386,16 @@ void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pr
    hfbgpu_acc_layout(&B.m, &B.L);
    printf("hfbgpu: %d physical HMMs, %d tied states, %d Gaussians, %d transition matrices on %d GPU(s)\n",
           B.nHmm, B.nSte, B.nMp, B.nTr, hfbgpu_num_devices(B.ctx));
-   B.tLast = now_s();
    fflush(stdout);
+   {  /* the two pinned batch buffers, once (cudaMallocHost of ~0.6 GB takes a few tenths of a second) */
+      int i2;
+      const long ncap = B.batchFrames + 40000;
+      for (i2 = 0; i2 < 2; i2++) {
+         P[i2].feat = (float *)hfbgpu_host_alloc(sizeof(float) * (size_t)ncap * B.D);
+         P[i2].featCap = P[i2].feat ? ncap : 0;
+      }
+   }
+   B.tLoop0 = B.tLast = now_s();
 }
 
 /* Completes ONE batch (and any older one) and reports its per-utterance outcomes in submission order; a younger batch
@@ -549,11 +559,18 @@ Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
    p->frameOff[p->nUtt] = p->nFrames; p->labOff[p->nUtt] = p->nLab;
    /* labels -> physical HMM indices (CreateInsts, HFB.c:538-542) */
    for (lab = utt->tr->head->head->succ, q = 0; lab->succ != NULL; lab = lab->succ, q++) {
-      MLink ml = FindMacroName(B.hset, 'l', lab->labid);
-      int ph;
-      if (ml == NULL) HError(7321, "CreateInsts: Unknown label %s", lab->labid->name);
-      ph = pm_get(&B.pmHmm, ml->structure);
-      if (ph < 0) HError(7321, "hfbgpu bridge: label %s maps to an unknown physical HMM", lab->labid->name);
+      int li = pm_get(&B.pmLab, lab->labid), ph;
+      if (li < 0) {                                         /* first time this label is seen: the reference's lookup */
+         MLink ml = FindMacroName(B.hset, 'l', lab->labid);
+         if (ml == NULL) HError(7321, "CreateInsts: Unknown label %s", lab->labid->name);
+         ph = pm_get(&B.pmHmm, ml->structure);
+         if (ph < 0) HError(7321, "hfbgpu bridge: label %s maps to an unknown physical HMM", lab->labid->name);
+         if (B.pmLab.n * 2 + 2 < B.pmLab.cap) {
+            li = pm_add(&B.pmLab, lab->labid);
+            if (li >= B.labCap) { B.labCap = li * 2 + 1024; B.labPhys = (int *)xrealloc(B.labPhys, sizeof(int) * (size_t)B.labCap); }
+            B.labPhys[li] = ph;
+         }
+      } else ph = B.labPhys[li];
       p->lab[p->nLab + q] = ph;
    }
    if (B.fastFd >= 0) {
@@ -642,9 +659,9 @@ void HFBGPU_Finish(int *totalT, LogDouble *totalPr)
    reader_stop();
    if (B.trace & 1) {
       printf("hfbgpu: %ld utterances through the fast loader, %ld through HParm\n", B.nFast, B.nSlow);
-      printf("hfbgpu: host profile (s): file loop %.3f = HERest's own code (LoadLabs, LoadData ...) %.3f + bridge queue %.3f + header reads %.3f"
+      printf("hfbgpu: host profile (s): set-up (flatten, CUDA context, model upload, pinned buffers) %.3f; file loop %.3f = HERest's own code (LoadLabs, LoadData ...) %.3f + bridge queue %.3f + header reads %.3f"
              " + wait for readers %.3f + submit %.3f + wait for GPU %.3f; final flush %.3f; download + scatter %.3f\n",
-             tf0 - B.tInit, B.sOutside, B.sQueue, B.sFastLoad, B.sReaderWait, B.sSubmit, B.sComplete, tLoop - tf0, now_s() - tLoop);
+             B.tLoop0 - B.tInit, tf0 - B.tLoop0, B.sOutside, B.sQueue, B.sFastLoad, B.sReaderWait, B.sSubmit, B.sComplete, tLoop - tf0, now_s() - tLoop);
       fflush(stdout);
    }
    for (i = 0; i < 2; i++) {
@@ -655,11 +672,11 @@ void HFBGPU_Finish(int *totalT, LogDouble *totalPr)
    hfbgpu_destroy(B.ctx);
    B.ctx = NULL;
    {
-      PMap *pm[6]; int k2;
-      pm[0] = &B.pmHmm; pm[1] = &B.pmSte; pm[2] = &B.pmMp; pm[3] = &B.pmMean; pm[4] = &B.pmVar; pm[5] = &B.pmTr;
-      for (k2 = 0; k2 < 6; k2++) { free((void *)pm[k2]->key); free(pm[k2]->val); }
+      PMap *pm[7]; int k2;
+      pm[0] = &B.pmHmm; pm[1] = &B.pmSte; pm[2] = &B.pmMp; pm[3] = &B.pmMean; pm[4] = &B.pmVar; pm[5] = &B.pmTr; pm[6] = &B.pmLab;
+      for (k2 = 0; k2 < 7; k2++) { free((void *)pm[k2]->key); free(pm[k2]->val); }
    }
-   free(B.hmm); free(B.ste); free(B.mp); free(B.meanV); free(B.varV); free(B.trans);
+   free(B.labPhys); free(B.hmm); free(B.ste); free(B.mp); free(B.meanV); free(B.varV); free(B.trans);
    free((void *)B.m.mean); free((void *)B.m.ivar); free((void *)B.m.gConst); free((void *)B.m.meanId); free((void *)B.m.varId);
    free((void *)B.m.stateMixOff); free((void *)B.m.mixGauss); free((void *)B.m.mixLogWt); free((void *)B.m.hmmNumStates);
    free((void *)B.m.hmmStateOff); free((void *)B.m.hmmState); free((void *)B.m.hmmTrans); free((void *)B.m.transN);

@@ -190,7 +190,12 @@ __global__ void __launch_bounds__(MAXT, MAXT == 128 ? 7 : 1024 / MAXT) beta_l2r_
 // instruction and cost 0.26 of the 1.19 ms; staging them through shared memory for 256-byte contiguous stores cost more
 // than it saved: 1.69 ms.)
 #define BW_NM 4
-template <bool ALUCVT>
+// RING: transcriptions of any length under a beam (config #5: 667 labels, beam ~40 models).  The 128 (lane, slot) pairs
+// form a ring: pair (L, k) holds the model q = L + 32 k (mod 128) nearest below the beam's upper end and takes the one
+// 128 below when its model has left the beam for good (the beta beam only ever moves towards the start of the
+// transcription).  No shared memory, no barrier -- the 256-thread sliding block kernel (beta_l2r_slide_kernel) needs two
+// barriers per frame.  A beam wider than 124 models flags the utterance HFB_UTT_BETAWIDE and beta_l2r_kernel<1024> redoes it.
+template <bool ALUCVT, bool RING>
 __global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
 {
    const UttDesc &u = W.utt[blockIdx.x];
@@ -205,15 +210,20 @@ __global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
    const size_t S = (size_t)5 * Q;
    L2RRegs r[BW_NM];
    bool mine[BW_NM];
+   int qk[BW_NM];                                      // model held by slot k (RING: changes as the window slides)
+   auto place = [&]() {                                // window at the top of the transcription
 #pragma unroll
-   for (int k = 0; k < BW_NM; k++) {
-      const int q = lane + 32 * k;
-      mine[k] = q < Q;
-      if (mine[k]) load_l2r(r[k], M, W, u, q);
-      else { r[k].aE = r[k].a00 = r[k].a01 = r[k].a11 = r[k].a12 = r[k].a22 = r[k].a2x = LZERO_D; r[k].s0 = r[k].s1 = r[k].s2 = 0; }
-   }
+      for (int k = 0; k < BW_NM; k++) {
+         const int res = lane + 32 * k;
+         qk[k] = RING ? ((res <= Q - 1) ? res + 128 * ((Q - 1 - res) / 128) : -1) : res;
+         mine[k] = qk[k] >= 0 && qk[k] < Q;
+         if (mine[k]) load_l2r(r[k], M, W, u, qk[k]);
+         else { r[k].aE = r[k].a00 = r[k].a01 = r[k].a11 = r[k].a12 = r[k].a22 = r[k].a2x = LZERO_D; r[k].s0 = r[k].s1 = r[k].s2 = 0; }
+      }
+   };
+   if (!RING) place();
    const float *bU = W.b + u.bOff;
-   double *betaL = W.beta + u.betaOff + 5 * lane;      // model q = lane + 32 k: + 160 k
+   double *betaL = W.beta + u.betaOff;
    short *qLo = W.qLo + u.frameBase, *qHi = W.qHi + u.frameBase;
 
    double thresh = W.pruneInit, pr = LZERO_D;
@@ -221,6 +231,7 @@ __global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
 
    for (;;) {
       const bool noPrune = thresh >= 0.5 * HFB_NOPRUNE;
+      if (RING) place();                               // every retry starts again at the top
       double u0[BW_NM], u1[BW_NM], u2[BW_NM], xPrev[BW_NM];   // b_j(o_{t+1}) + beta_j(t+1); entry beta at t+1
       float bA0[BW_NM], bA1[BW_NM], bA2[BW_NM], bB0[BW_NM], bB1[BW_NM], bB2[BW_NM];
       // ---- t = T-1, HFB.c:1176-1198
@@ -228,7 +239,7 @@ __global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
       if (lane == 0) { qHi[T - 1] = (short)(Q - 1); qLo[T - 1] = (short)(Q - 1); }
 #pragma unroll
       for (int k = 0; k < BW_NM; k++) {
-         const int q = lane + 32 * k;
+         const int q = qk[k];
          u0[k] = u1[k] = u2[k] = xPrev[k] = LZERO_D;
          bA0[k] = bA1[k] = bA2[k] = bB0[k] = bB1[k] = bB2[k] = 0.f;
          if (mine[k] && q >= lo1) {
@@ -237,7 +248,7 @@ __global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
             const double n0 = LZERO_D + bExit, n1 = LZERO_D + bExit, n2 = r[k].a2x + bExit;
             u0[k] = (double)bt[r[k].s0] + n0; u1[k] = (double)bt[r[k].s1] + n1; u2[k] = (double)bt[r[k].s2] + n2;
             const double x = (n0 > LSMALL_D) ? r[k].aE + u0[k] : LZERO_D;
-            double *bg = betaL + (size_t)(T - 1) * S + 160 * k;
+            double *bg = betaL + (size_t)(T - 1) * S + 5 * q;
             bg[0] = x; bg[1] = n0; bg[2] = n1; bg[3] = n2; bg[4] = bExit;
             xPrev[k] = x;
          }
@@ -250,7 +261,7 @@ __global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
 
       // ---- t = T-2 .. 0, HFB.c:1205-1277
       bool fail = false;
-      double *bgT = betaL + (size_t)(T - 1) * S;       // lane's beta column pointer at t
+      double *bgT = betaL + (size_t)(T - 1) * S;       // beta column block of frame t
       const float *bp = bU + (size_t)(T - 3) * J;      // the output-probability row of frame t-2
       int hiC = (T - 1) / 3, hiR = (T - 1) % 3, loC = 0, loR = 0;      // closed-form taper, see beta_l2r_kernel
       for (int t = T - 2; t >= 0; t--) {
@@ -265,9 +276,9 @@ __global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
          bool active[BW_NM];
 #pragma unroll
          for (int k = 0; k < BW_NM; k++) {
-            const int q = lane + 32 * k;
-            // entry beta of model q + 1 at t + 1: lane + 1 same row, lane 31 -> lane 0 one row up
-            const double y = (lane == 0) ? ((k + 1 < BW_NM) ? xPrev[k + 1] : LZERO_D) : xPrev[k];
+            const int q = qk[k];
+            // entry beta of model q + 1 at t + 1: lane + 1 same slot, lane 31 -> lane 0 one slot up (RING: the slots wrap)
+            const double y = (lane == 0) ? (RING ? xPrev[(k + 1) % BW_NM] : ((k + 1 < BW_NM) ? xPrev[k + 1] : LZERO_D)) : xPrev[k];
             const double exN = __shfl_sync(0xffffffffu, y, (lane + 1) & 31);
             active[k] = mine[k] && q >= endq && q <= startq;
             const float c0 = bA0[k], c1 = bA1[k], c2 = bA2[k];
@@ -281,7 +292,7 @@ __global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
                const double n0 = (ALUCVT ? ladd_nz : ladd_nz_b)(r[k].a00 + u0[k], r[k].a01 + u1[k]);
                un0[k] = (double)c0 + n0; un1[k] = (double)c1 + n1; un2[k] = (double)c2 + n2;
                const double x = r[k].aE + un0[k];                                          // :1242-1250
-               double *bg = bgT + 160 * k;
+               double *bg = bgT + 5 * q;
                bg[0] = x; bg[1] = n0; bg[2] = n1; bg[3] = n2; bg[4] = ex;
                xNew[k] = x;
                lMax[k] = dmax(dmax(n0, n1), n2);
@@ -297,7 +308,7 @@ __global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
 #pragma unroll
             for (int k = 0; k < BW_NM; k++) {
                const bool keep = active[k] && !(gMax - lMax[k] > thresh);
-               if (keep) { myHi = max(myHi, lane + 32 * k); myLo = min(myLo, lane + 32 * k); }
+               if (keep) { myHi = max(myHi, qk[k]); myLo = min(myLo, qk[k]); }
             }
             nhi = __reduce_max_sync(0xffffffffu, myHi);
             nlo = __reduce_min_sync(0xffffffffu, myLo);
@@ -309,16 +320,33 @@ __global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
          hi1 = nhi; lo1 = nlo;
 #pragma unroll
          for (int k = 0; k < BW_NM; k++) {
-            const int q = lane + 32 * k;
+            const int q = qk[k];
             const bool inNew = active[k] && q >= nlo && q <= nhi;
             u0[k] = inNew ? un0[k] : LZERO_D; u1[k] = inNew ? un1[k] : LZERO_D; u2[k] = inNew ? un2[k] : LZERO_D;
             xPrev[k] = xNew[k];
+         }
+         if (RING) {
+            // everything the next frame can touch is [lo1 - 3, hi1] (beam, one model of growth, two of look-ahead)
+            if (hi1 - lo1 + 4 > 32 * BW_NM) { fail = true; status = HFB_UTT_BETAWIDE; break; }
+#pragma unroll
+            for (int k = 0; k < BW_NM; k++)
+               if (mine[k] && qk[k] > hi1) {           // my model has left the beam for good: take the one 128 below
+                  do qk[k] -= 32 * BW_NM; while (qk[k] > hi1);
+                  mine[k] = qk[k] >= 0;
+                  u0[k] = u1[k] = u2[k] = xPrev[k] = LZERO_D;
+                  bA0[k] = bA1[k] = bA2[k] = bB0[k] = bB1[k] = bB2[k] = 0.f;
+                  if (mine[k]) {
+                     load_l2r(r[k], M, W, u, qk[k]);
+                     if (t >= 1) { const float *b1 = bp + J; bA0[k] = b1[r[k].s0]; bA1[k] = b1[r[k].s1]; bA2[k] = b1[r[k].s2]; }
+                     if (t >= 2) { bB0[k] = bp[r[k].s0]; bB1[k] = bp[r[k].s1]; bB2[k] = bp[r[k].s2]; }
+                  }
+               }
          }
       }
       if (status != 0) break;
       if (!fail) {
          // utt->pr = bqt[1] (:1280): entry beta of model lastq at the last frame processed
-         const int kq = lastq >> 5;
+         const int kq = (lastq >> 5) % BW_NM;
          const double v = (kq == 0) ? xPrev[0] : (kq == 1) ? xPrev[1] : (kq == 2) ? xPrev[2] : xPrev[3];
          pr = __shfl_sync(0xffffffffu, v, lastq & 31);
          if (pr > LSMALL_D) break;

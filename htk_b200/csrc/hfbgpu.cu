@@ -434,7 +434,7 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
    size_t freeB = 0, totalB = 0;
    CK(cudaMemGetInfo(&freeB, &totalB));
    size_t ws = opt->workspaceBytes ? opt->workspaceBytes : ((size_t)48 << 30);
-   if (ws > freeB * 6 / 10) ws = freeB * 6 / 10;
+   if (ws > freeB / 10 * 8) ws = freeB / 10 * 8;
    c->workspaceBytes = ws;
 
    int maxOpt = c->maxSmemOptin;
@@ -827,8 +827,15 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
          const bool pruning = c->opt.pruneInit < 0.5 * HFB_NOPRUNE;
          if (w.maxQ <= 32 * BW_NM && !getenv("HFBGPU_NO_BETA_WARP")) {
             // HFBGPU_BETA_ALU: the FP64 <-> FP32 conversions of the log-add as integer operations (experiment)
-            if (getenv("HFBGPU_BETA_ALU")) beta_l2r_warp_kernel<true><<<nU, 32, 0, sr>>>(c->dm, W);
-            else beta_l2r_warp_kernel<false><<<nU, 32, 0, sr>>>(c->dm, W);
+            if (getenv("HFBGPU_BETA_ALU")) beta_l2r_warp_kernel<true, false><<<nU, 32, 0, sr>>>(c->dm, W);
+            else beta_l2r_warp_kernel<false, false><<<nU, 32, 0, sr>>>(c->dm, W);
+         }
+         else if (pruning && !getenv("HFBGPU_NO_RING")) {
+            // long transcriptions under a beam: one warp per utterance, 128-model ring window that slides down with the
+            // beam; the one-thread-per-label kernel redoes the utterances whose beam outgrew it
+            beta_l2r_warp_kernel<false, true><<<nU, 32, 0, sr>>>(c->dm, W);
+            beta_l2r_kernel<1024><<<nU, ntGeneric, fsm, sr>>>(c->dm, W, 1);
+            c->stats.launches++; c->stats.launchesBeta++;
          }
          else if (w.maxQ <= 128) beta_l2r_kernel<128><<<nU, nt, fsm, sr>>>(c->dm, W, 0);  // 72 registers, 7 CTAs/SM
          else if (w.maxQ <= 256) beta_l2r_kernel<256><<<nU, nt, fsm, sr>>>(c->dm, W, 0);

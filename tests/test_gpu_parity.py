@@ -597,3 +597,42 @@ def test_taper_skipping_changes_nothing(name, monkeypatch):
     assert p0 <= p1                                                       # fewer (frame, state) pairs evaluated
     if name in ("synth_tied_m4", "synth_long_m3"):
         assert p0 < 0.9 * p1, (p0, p1)
+
+
+def test_ring_window_beta_equals_sliding_block_kernel(monkeypatch):
+    """Transcriptions of more than 128 labels under a beam: the warp kernel with a 128-model ring window (default)
+    against the 256-thread sliding block kernel (HFBGPU_NO_RING) and the one-thread-per-label kernel (HFBGPU_NO_SLIDE):
+    same recursion, same order of operations -- identical likelihoods, thresholds and beams."""
+    z, fm, b, kw = load_golden("synth_long_m3")                      # Q = 160, -t 250 150 1000
+    outs = []
+    for env in (None, "HFBGPU_NO_RING", "HFBGPU_NO_SLIDE"):
+        if env:
+            monkeypatch.setenv("HFBGPU_NO_RING", "1")
+            monkeypatch.setenv(env, "1")
+        fb = _fb(fm, **kw)
+        res, beams = fb.FBFile(b, want_beams=True)
+        outs.append((res, beams, fb.GetAccs()))
+        fb.close()
+    for res, beams, acc in outs[1:]:
+        assert [tuple(r) for r in res] == [tuple(r) for r in outs[0][0]]
+        for k in ("qLo", "qHi", "sq", "eq"):
+            assert np.array_equal(getattr(beams, k), getattr(outs[0][1], k))
+        e = acc_errors(acc, outs[0][2], fm)
+        assert max(e.values()) < 1e-5, e
+    # a tight beam on the same data: retries (the window is placed at the top again), narrower windows
+    kw2 = dict(kw); kw2["prune"] = (60.0, 40.0, 400.0)
+    outs = []
+    for env in (None, "HFBGPU_NO_RING"):
+        if env:
+            monkeypatch.setenv(env, "1")
+        else:
+            monkeypatch.delenv("HFBGPU_NO_RING", raising=False); monkeypatch.delenv("HFBGPU_NO_SLIDE", raising=False)
+        fb = _fb(fm, **kw2)
+        res, beams = fb.FBFile(b, want_beams=True)
+        outs.append((res, beams))
+        fb.close()
+    assert [tuple(r) for r in outs[0][0]] == [tuple(r) for r in outs[1][0]]
+    assert np.array_equal(outs[0][1].qLo, outs[1][1].qLo) and np.array_equal(outs[0][1].qHi, outs[1][1].qHi)
+    oacc, ores, obeams = _oracle(fm, b, kw2)
+    assert [(r.status, r.retries, r.pruneThresh) for r in outs[0][0]] == [(o[0], o[1], o[3]) for o in ores]
+    assert np.array_equal(outs[0][1].qLo, obeams.qLo) and np.array_equal(outs[0][1].qHi, obeams.qHi)
