@@ -344,7 +344,17 @@ def herest_gpu_tool(fm, cfg, prune, n_files=1024, gpu_index=0):
         m = re.search(r"(\d+) utterances through the fast loader, (\d+) through HParm", pb.stdout)
         rate = (n_files - n_small) * T / max(tb - ta, 1e-6)
         prof = re.search(r"hfbgpu: host profile \(s\): (.*)", pb.stdout)
-        return {"host_profile_s": prof.group(1) if prof else None, "value": rate, "unit": "frames/s", "files": n_files, "frames": n_files * T, "wall_s": tb, "startup_s": ta,
+        loop_rate = None
+        if prof:
+            m2 = re.search(r"file loop ([0-9.]+) .*final flush ([0-9.]+); download \+ scatter ([0-9.]+)", prof.group(1))
+            if m2:
+                loop_rate = n_files * T / max(sum(float(x) for x in m2.groups()), 1e-6)
+        return {"host_profile_s": prof.group(1) if prof else None, "file_loop_frames_per_s": loop_rate,
+                "note": "value = marginal end-to-end rate of the whole tool, which at this corpus size is dominated by HTK's own MLF "
+                        "pre-scan (HLabel.c LoadMasterFile, ~12 us per label line, paid before the first utterance); "
+                        "file_loop_frames_per_s = frames / (file loop + final flush + accumulator download and scatter), i.e. "
+                        "what HERest's loop + the bridge + the library sustain once the MLF is indexed",
+                "value": rate, "unit": "frames/s", "files": n_files, "frames": n_files * T, "wall_s": tb, "startup_s": ta,
                 "gpu_utilization_mean_pct": busy, "fast_loader_files": int(m.group(1)) if m else None,
                 "how": "`HERest_gpu -T 1 -u tmvw -p 1` (reference HERest + bridge + libhfbgpu) over %d feature files of %d "
                        "frames on local disk, one process, one GPU; marginal rate between %d and %d files so that MMF "
