@@ -96,7 +96,7 @@ struct __align__(16) PosRec {
 
 __global__ void __launch_bounds__(128) statpos_scatter_kernel(Wave W, const int *__restrict__ off, int *__restrict__ fill,
                                                               PosRec *__restrict__ list, unsigned long long *vCursor,
-                                                              long long vCap, int *__restrict__ posIdx)
+                                                              long long vCap, int *__restrict__ posIdx, int *__restrict__ overflow)
 {
    const UttDesc &u = W.utt[blockIdx.x];
    if (W.out[blockIdx.x].status != 0) return;
@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(128) statpos_scatter_kernel(Wave W, const int 
          r.pr = W.out[blockIdx.x].pr;
          const long long o = wbase + incl - span;
          r.vOff = (vCap > 0 && o + span <= vCap) ? o : -1;    // positions that do not fit keep the inline front
+         if (r.vOff < 0) *overflow = 1;                       // ... of stats5_kernel: the tcgen05 kernel then leaves the wave to it
          const int *ps = W.posSlot + u.posOff + W.mPoff[gq];
 #pragma unroll
          for (int i = 0; i < HFB_MAXN; i++) r.ps[i] = (i < r.N - 2) ? ps[i] : 0;
@@ -252,9 +253,11 @@ __host__ __device__ inline size_t stats5_warp_bytes(int D)
 template <int NT>
 __global__ void __launch_bounds__(32 * S4_WARPS, 3)
 stats5_kernel(DevModel M, Wave W, const float *__restrict__ centre, const PosRec *__restrict__ list,
-              const int *__restrict__ listEnd, const ValidFrame *__restrict__ vbuf, const int *__restrict__ vcnt, int cap)
+              const int *__restrict__ listEnd, const ValidFrame *__restrict__ vbuf, const int *__restrict__ vcnt, int cap,
+              const int *__restrict__ onlyIfOverflow)
 {
    extern __shared__ __align__(16) unsigned char smraw[];
+   if (onlyIfOverflow != nullptr && *onlyIfOverflow == 0) return;   // stats_tc_kernel has done the wave
    const int wInB = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const int nSorted = *listEnd;
    const int i0 = (blockIdx.x * S4_WARPS + wInB) * cap, i1 = min(nSorted, i0 + cap);

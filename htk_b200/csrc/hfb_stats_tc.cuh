@@ -1,0 +1,366 @@
+// hfb_stats_tc.cuh -- K4 on the 5th-generation tensor cores.
+//
+// UpMixParms (HTKLib/HFB.c:1426-1744) as the two contractions north_star asks for, per tied state, over the frames of
+// the whole wave in which one of the state's positions survives the alpha beam (stats_pre_kernel's dense lists):
+//
+//   (1) component log-likelihoods   V[frames x components] = A[frames x (1 | x'^2, x' | 1)] x B_state^T
+//       -- the very product gmm_tc3_kernel forms for the state log-likelihood (same operands, same 3xFP16 split, same
+//       MMA order, so the same numbers), for 128 gathered frames at a time: tcgen05.mma M = 128, N = 16 / 32, K = 80;
+//   (2) occupancy-weighted sums     S[(1 | x'^2, x') x components] = A^T[columns x frames] x Lr[frames x components]
+//       with Lr = exp(initx + log weight + log N) under the minimum-occupancy rule (HFB.c:1581-1612).  A^T is the SAME
+//       shared-memory tile read as an MN-major operand (a 128-byte-swizzled K-major tile of [frames][64 columns] IS the
+//       canonical MN-major tile with MN = 64, K = frames), Lr is written by the epilogue of (1) as the K-major B
+//       operand, hi / lo FP16 halves: M = 128 (operand columns), N = components, K = 128 frames.
+//
+// The accumulators of (2) live in TMEM for one tile only (24 truncating tensor-core accumulations, ~1e-6 relative); the
+// running sums of a state stay in FP32 registers of the thread that owns the operand column and are moved once per
+// state -- to HTK's centred form about each component mean (HFB.c:1673-1678) -- into the FP64 accumulators:
+//     sum Lr (o - mu)   = S1 / s - d S0,      sum Lr (o - mu)^2 = S2 / s^2 - 2 d S1 / s + d^2 S0,   d = mu - offset,
+// with s the per-dimension power-of-two scale of the operands.  Replaces stats5_kernel (mma.sync 3xTF32 sums behind an
+// FP32 recomputation of the posteriors: 25 % of its instructions, 12 warps / SM); stats_pre_kernel and the position sort
+// are unchanged.  Frames outside the FP16 operand range (gmm_tc3's flags) get their posteriors from an FP32 evaluation.
+//
+// One CTA = 4 worker warps (thread = tile row: gather + expansion, epilogue of (1), TMEM lane of (2)) + 1 MMA / TMA
+// warp; it owns ST_CAP consecutive entries of the state-sorted position list.  The phases of a tile are sequential
+// inside a CTA; two CTAs per SM overlap them.
+#pragma once
+#include "gmm_tc3.cuh"
+#include "hfb_stats_mma.cuh"
+
+#define ST_CAP 128                   // sorted positions per CTA
+#define ST_THREADS 160
+#define ST_LR_SCALE 4096.f           // Lr in (4.5e-5, 1] -> FP16 normal range; removed again at the flush
+
+struct StatsTcParams {
+   const PosRec *list;
+   const int *listEnd;               // number of sorted positions
+   const ValidFrame *vbuf;
+   const int *vcnt;
+   const unsigned char *flag;        // per frame of the wave: FP16 operands out of range (gmm_tc3)
+   const int *overflow;              // != 0: some position did not fit the frame lists -> stats5_kernel does the wave
+   const float *offset, *scale;
+   float C0;
+   int kSteps, N, MP;
+};
+
+__device__ __forceinline__ void st_mma_f16(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
+{
+   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                ::"r"(tmemD), "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate) : "memory");
+}
+// MN-major, 128-byte swizzle: LBO = stride between 64-element groups along MN, SBO = stride between 8-element groups along K
+__device__ __forceinline__ uint64_t st_desc_mn(uint32_t smemAddr, uint32_t lboBytes, uint32_t sboBytes)
+{
+   return (uint64_t)((smemAddr >> 4) & 0x3FFF) | ((uint64_t)((lboBytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sboBytes >> 4) & 0x3FFF) << 32) |
+          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+template <int NC>
+__device__ __forceinline__ void st_tmem_ld(uint32_t taddr, float *v)
+{
+   uint32_t *r = reinterpret_cast<uint32_t *>(v);
+   if (NC == 16)
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                     "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                   : "r"(taddr));
+   else {
+      tc_tmem_ld32(taddr, v);
+      return;
+   }
+   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int N, int DP>
+__global__ void __launch_bounds__(ST_THREADS, 2)
+stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, DevModel M, Wave W, StatsTcParams p)
+{
+   extern __shared__ uint8_t st_smem_raw[];
+   if (*p.overflow) return;
+   const int nSorted = *p.listEnd;
+   const int i0 = blockIdx.x * ST_CAP, i1 = min(nSorted, i0 + ST_CAP);
+   if (i0 >= i1) return;
+   uint8_t *base = (uint8_t *)(((uintptr_t)st_smem_raw + 1023) & ~(uintptr_t)1023);
+   uint8_t *sA = base;                                  // [hi c0 | hi c1 | lo c0 | lo c1] x 16 KB: 128 rows x 128 columns
+   uint8_t *sB1 = sA + 65536;                           // the state's Gaussians: [hi c0 | hi c1 | lo c0 | lo c1] x N x 128 B
+   uint8_t *sB2 = sB1 + 4 * N * 128;                    // Lr: [hi f0-63 | hi f64-127 | lo .. | lo ..] x N x 128 B
+   float *stage = (float *)sB2;                         // [128][N] flush staging: Lr is dead when a state is flushed
+   int *pre = (int *)(sB2 + 4 * N * 128);               // [ST_CAP + 1] prefix sums of the positions' frame counts
+   int *stt = pre + ST_CAP + 1;                         // [ST_CAP] tied state of each position
+   uint64_t *bars = (uint64_t *)(((uintptr_t)(stt + ST_CAP) + 15) & ~(uintptr_t)15);
+   uint64_t *barB = bars, *bar1 = bars + 1, *bar2 = bars + 2;
+   uint32_t *tmemSlot = (uint32_t *)(bars + 3);
+   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+   const bool worker = warp < 4;
+   const int D = M.D, Dp = M.Dp;
+   constexpr uint32_t TCOLS = (2 * N <= 32) ? 32 : 64;
+
+   if (tid == 0) {
+      tc_mbar_init(barB, 1); tc_mbar_init(bar1, 1); tc_mbar_init(bar2, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   if (warp == 4) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmemSlot)), "r"(TCOLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+   }
+   // frame counts / states of my slice; the A tile starts out finite (stale rows are multiplied by Lr = 0 in (2))
+   for (int k = tid; k < ST_CAP; k += ST_THREADS) {
+      const int it = i0 + k;
+      pre[k + 1] = (it < i1 && p.list[it].vOff >= 0) ? p.vcnt[it] : 0;
+      stt[k] = (it < i1) ? p.list[it].s : -1;
+   }
+   for (uint32_t o = tid * 16; o < 65536; o += ST_THREADS * 16) *reinterpret_cast<uint4 *>(sA + o) = make_uint4(0u, 0u, 0u, 0u);
+   tc_fence_before();
+   __syncthreads();
+   tc_fence_after();
+   if (tid == 0) { pre[0] = 0; for (int k = 0; k < ST_CAP; k++) pre[k + 1] += pre[k]; }
+   __syncthreads();
+   const uint32_t tmem = *tmemSlot;
+   const uint32_t tD1 = tmem, tD2 = tmem + N;
+   const int nPos = i1 - i0;
+   const int uf = W.uFlags;
+   const bool upM = (uf & HFB_UPMEANS) != 0, upV = (uf & HFB_UPVARS) != 0, upW = (uf & HFB_UPMIXES) != 0;
+   const double minF = W.minFrwdP;
+   const uint32_t idesc1 = tc_idesc(TC_BM, N, 0u);                     // K-major A and B
+   const uint32_t idesc2 = tc_idesc(TC_BM, N, 0u) | (1u << 15);        // A MN-major (the transposed tile), B K-major
+   uint32_t phB = 0, ph1 = 0, ph2 = 0;
+   float run[N];                                        // running sums of operand column `tid` of the current state
+
+   for (int a = 0; a < nPos;) {
+      const int s = stt[a];
+      int b = a + 1;
+      while (b < nPos && stt[b] == s) b++;
+      const int g0 = pre[a], g1 = pre[b];
+      if (g1 > g0) {
+         const int mo = M.stateMixOff[s], Mn = M.stateMixOff[s + 1] - mo;
+         // ---- the state's Gaussians: rows TC3_ROW0 + s MP .. + N of the tensor-core B operand
+         if (warp == 4 && lane == 0) {
+            tc_mbar_expect_tx(barB, 4 * N * 128);
+            constexpr int BOXR = (N < 64) ? ((N == 16) ? 16 : 32) : 64;
+            const int boxR = (p.MP < BOXR) ? p.MP : BOXR;            // rows per TMA box as the maps were built
+            for (int c = 0; c < 2; c++)
+               for (int r0 = 0; r0 < N; r0 += boxR) {
+                  tc_tma_load_2d(sB1 + c * (N * 128) + r0 * 128, &mapBhi, barB, c * 64, TC3_ROW0 + s * p.MP + r0);
+                  tc_tma_load_2d(sB1 + (2 + c) * (N * 128) + r0 * 128, &mapBlo, barB, c * 64, TC3_ROW0 + s * p.MP + r0);
+               }
+         }
+#pragma unroll
+         for (int m = 0; m < N; m++) run[m] = 0.f;
+         bool newState = true;
+         for (int t0 = g0; t0 < g1; t0 += TC_BM) {
+            // ================= phase A: gather + expand 128 frames (thread = row) =================
+            double x0 = 0.0;
+            bool valid = false, far = false;
+            const float *frow = nullptr;
+            if (worker) {
+               const int g = t0 + tid;
+               valid = g < g1;
+               float x[DP];
+#pragma unroll
+               for (int d = 0; d < DP; d++) x[d] = 0.f;
+               if (valid) {
+                  int lo = a, hi = b;                   // position with pre[it] <= g < pre[it + 1]
+                  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= g) lo = mid; else hi = mid; }
+                  const PosRec &R = p.list[i0 + lo];
+                  const ValidFrame vf = p.vbuf[R.vOff + (g - pre[lo])];
+                  x0 = vf.x0;
+                  frow = W.feat + ((size_t)R.featOff + vf.t) * D;
+                  far = p.flag != nullptr && p.flag[R.frameBase + vf.t] != 0;
+#pragma unroll
+                  for (int d = 0; d < DP; d++)
+                     if (d < D) x[d] = fminf(fmaxf((frow[d] - p.offset[d]) * p.scale[d], -250.f), 250.f);
+               }
+#pragma unroll
+               for (int un = 0; un < 16; un++) {
+                  if (un >= 2 * p.kSteps) break;
+                  float v[8];
+#pragma unroll
+                  for (int e = 0; e < 8; e++) {
+                     const int k = un * 8 + e;
+                     if (k == 0) v[e] = valid ? 1.f : 0.f;
+                     else if (k & 1) { const int d = (k - 1) >> 1; v[e] = (d < DP && d < D) ? x[d < DP ? d : 0] * x[d < DP ? d : 0] : ((d == D && valid) ? 1.f : 0.f); }
+                     else { const int d = (k - 2) >> 1; v[e] = (d < DP && d < D) ? x[d < DP ? d : 0] : 0.f; }
+                  }
+                  uint32_t h4[4], l4[4];
+#pragma unroll
+                  for (int e = 0; e < 4; e++) {
+                     const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                     const float2 hf = __half22float2(h);
+                     const __half2 l = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+                     h4[e] = *reinterpret_cast<const uint32_t *>(&h);
+                     l4[e] = *reinterpret_cast<const uint32_t *>(&l);
+                  }
+                  const uint32_t off = tc3_unit_off(tid, un);
+                  *reinterpret_cast<uint4 *>(sA + off) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+                  *reinterpret_cast<uint4 *>(sA + 32768 + off) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+               }
+               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            // ================= (1): V = A x B_state^T =================
+            if (warp == 4) {
+               if (newState) { tc_mbar_wait(barB, phB); phB ^= 1; tc_fence_after(); }
+               if (lane == 0) {
+                  const uint32_t aB = tc_smem_u32(sA), bB = tc_smem_u32(sB1);
+                  for (int ks = 0; ks < p.kSteps; ks++) {              // corrections first (see gmm_tc3_kernel)
+                     const uint32_t oa = (ks >> 2) * 16384 + (ks & 3) * 32, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
+                     st_mma_f16(tD1, tc_smem_desc(aB + oa), tc_smem_desc(bB + 2 * N * 128 + ob), idesc1, ks ? 1u : 0u);
+                     st_mma_f16(tD1, tc_smem_desc(aB + 32768 + oa), tc_smem_desc(bB + ob), idesc1, 1u);
+                  }
+                  for (int ks = 0; ks < p.kSteps; ks++) {
+                     const uint32_t oa = (ks >> 2) * 16384 + (ks & 3) * 32, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
+                     st_mma_f16(tD1, tc_smem_desc(aB + oa), tc_smem_desc(bB + ob), idesc1, 1u);
+                  }
+                  tc_commit(bar1);
+               }
+               __syncwarp();
+            }
+            newState = false;
+            // ================= epilogue of (1): Lr -> B operand of (2) =================
+            if (worker) {
+               tc_mbar_wait(bar1, ph1);
+               tc_fence_after();
+               float v[N];
+               st_tmem_ld<N>(tD1 + ((uint32_t)(warp * 32) << 16), v);
+               if (valid && far && Mn > 1) {
+                  // operands out of the FP16 range: the component log-likelihoods as IDOutP computes them (HModel.c:5420-5431)
+#pragma unroll
+                  for (int m = 0; m < N; m++) {
+                     float val = -1.0e30f;
+                     if (m < Mn) {
+                        const float wt = M.mixLogWt[mo + m];
+                        if (wt > LMINMIX_F) {
+                           const int g = M.mixGauss[mo + m];
+                           const float *mu = M.mean + (size_t)g * Dp, *iv = M.ivar + (size_t)g * Dp;
+                           float acc = M.gconst[g];
+                           for (int k = 0; k < D; k++) { const float dd = frow[k] - mu[k]; acc = fmaf(dd * dd, iv[k], acc); }
+                           val = -0.5f * acc + wt + p.C0;
+                        }
+                     }
+                     v[m] = val;
+                  }
+               }
+#pragma unroll
+               for (int m = 0; m < N; m++) {
+                  float Lr = 0.f;
+                  if (valid && m < Mn) {
+                     // x = initx + log weight + log N_m (:1581-1599); single-Gaussian states: x = log occupancy (:1575-1576)
+                     const double x = (Mn > 1) ? x0 + (double)(v[m] - p.C0) : x0;
+                     if (-x < minF && (Mn > 1 || m == 0)) Lr = expf((float)x) * ST_LR_SCALE;      // :1606, :1612
+                  }
+                  const __half h = __float2half_rn(Lr), l = __float2half_rn(Lr - __half2float(h));
+                  const uint32_t off = (uint32_t)((tid >> 6) * (N * 128) + m * 128 + ((((tid & 63) >> 3) ^ (m & 7)) << 4) + (tid & 7) * 2);
+                  *reinterpret_cast<__half *>(sB2 + off) = h;
+                  *reinterpret_cast<__half *>(sB2 + 2 * N * 128 + off) = l;
+               }
+               ph1 ^= 1;
+               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            // ================= (2): S = A^T x Lr =================
+            if (warp == 4) {
+               if (lane == 0) {
+                  const uint32_t aB = tc_smem_u32(sA), bB = tc_smem_u32(sB2);
+                  for (int ks = 0; ks < 8; ks++) {                    // 16 frames per step
+                     const uint32_t oa = ks * 2048, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
+                     st_mma_f16(tD2, st_desc_mn(aB + oa, 16384, 1024), tc_smem_desc(bB + 2 * N * 128 + ob), idesc2, ks ? 1u : 0u);
+                     st_mma_f16(tD2, st_desc_mn(aB + 32768 + oa, 16384, 1024), tc_smem_desc(bB + ob), idesc2, 1u);
+                  }
+                  for (int ks = 0; ks < 8; ks++) {
+                     const uint32_t oa = ks * 2048, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
+                     st_mma_f16(tD2, st_desc_mn(aB + oa, 16384, 1024), tc_smem_desc(bB + ob), idesc2, 1u);
+                  }
+                  tc_commit(bar2);
+               }
+               __syncwarp();
+            }
+            if (worker) {
+               tc_mbar_wait(bar2, ph2);
+               ph2 ^= 1;
+               tc_fence_after();
+               float v[N];
+               st_tmem_ld<N>(tD2 + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+               for (int m = 0; m < N; m++) run[m] += v[m];
+            }
+            tc_fence_before();
+            __syncthreads();                            // the tile, Lr and both accumulators may be overwritten
+            tc_fence_after();
+         }
+         // ================= flush: the state's sums -> FP64 accumulators, centred on the component means =================
+         if (worker) {
+#pragma unroll
+            for (int m = 0; m < N; m++) stage[tid * N + m] = run[m];
+         }
+         __syncthreads();
+         if (worker) {
+            const double inv = 1.0 / (double)ST_LR_SCALE;
+            double wsum = 0.0;
+            for (int e = tid; e < Mn * (D + 1); e += 128) {
+               const int m = e / (D + 1), k = e - m * (D + 1);
+               const double S0 = (double)stage[0 * N + m] * inv;
+               if (!(S0 > 0.0)) continue;               // component never passed the minimum-occupancy rule
+               const int g = M.mixGauss[mo + m];
+               if (k == D) {
+                  if (upM) atomicAdd(&W.acc[M.L.muOcc + M.meanId[g]], S0);
+                  if (upV) atomicAdd(&W.acc[M.L.vaOcc + M.varId[g]], S0);
+                  if (upW) atomicAdd(&W.acc[M.L.wtC + mo + m], S0);
+               } else {
+                  const double sk = (double)p.scale[k], d = ((double)M.mean[(size_t)g * Dp + k] - (double)p.offset[k]) * sk;
+                  const double S2 = (double)stage[(2 * k + 1) * N + m] * inv, S1 = (double)stage[(2 * k + 2) * N + m] * inv;
+                  if (upM) atomicAdd(&W.acc[M.L.muSum + (size_t)M.meanId[g] * D + k], (S1 - d * S0) / sk);
+                  if (upV) atomicAdd(&W.acc[M.L.vaSum + (size_t)M.varId[g] * D + k], (S2 - 2.0 * d * S1 + d * d * S0) / (sk * sk));
+               }
+            }
+            if (tid < Mn) wsum = (double)stage[tid] * inv;
+            for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+            if (tid == 0 && wsum > 0.0) atomicAdd(&W.acc[M.L.wtOcc + s], wsum);
+         }
+         __syncthreads();
+      }
+      a = b;
+   }
+   tc_fence_before();
+   __syncthreads();
+   if (warp == 4) {
+      tc_fence_after();
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TCOLS) : "memory");
+   }
+}
+
+template <int N>
+static inline size_t stats_tc_smem_bytes() { return 1024 + 65536 + 8 * N * 128 + sizeof(int) * (2 * ST_CAP + 1) + 128; }
+
+// Launch: returns false when the model is outside what the kernel covers (the caller keeps stats5_kernel).
+static inline bool stats_tc_supported(const GmmTc3Model &t, int D) { return t.ready && (t.MP == 8 || t.MP == 16 || t.MP == 32) && D <= 63; }
+
+static inline void stats_tc_set_attributes()
+{
+   cudaFuncSetAttribute(stats_tc_kernel<16, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_tc_smem_bytes<16>());
+   cudaFuncSetAttribute(stats_tc_kernel<16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_tc_smem_bytes<16>());
+   cudaFuncSetAttribute(stats_tc_kernel<32, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_tc_smem_bytes<32>());
+   cudaFuncSetAttribute(stats_tc_kernel<32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_tc_smem_bytes<32>());
+}
+
+static inline void stats_tc_launch(const GmmTc3Model &t, const DevModel &dm, const Wave &W, const PosRec *list, const int *listEnd,
+                                   const ValidFrame *vbuf, const int *vcnt, const unsigned char *flag, const int *overflow,
+                                   long long totalP, cudaStream_t st)
+{
+   StatsTcParams p;
+   p.list = list; p.listEnd = listEnd; p.vbuf = vbuf; p.vcnt = vcnt; p.flag = flag; p.overflow = overflow;
+   p.offset = t.dOffset; p.scale = t.dScale; p.C0 = t.C0; p.kSteps = (2 * dm.D + 2 + 15) / 16; p.MP = t.MP;
+   p.N = (t.MP <= 16) ? 16 : 32;
+   const unsigned grid = (unsigned)((totalP + ST_CAP - 1) / ST_CAP);
+   if (grid == 0) return;
+   if (p.N == 16) {
+      if (dm.D <= 40) stats_tc_kernel<16, 40><<<grid, ST_THREADS, stats_tc_smem_bytes<16>(), st>>>(t.mapBhi, t.mapBlo, dm, W, p);
+      else stats_tc_kernel<16, 64><<<grid, ST_THREADS, stats_tc_smem_bytes<16>(), st>>>(t.mapBhi, t.mapBlo, dm, W, p);
+   } else {
+      if (dm.D <= 40) stats_tc_kernel<32, 40><<<grid, ST_THREADS, stats_tc_smem_bytes<32>(), st>>>(t.mapBhi, t.mapBlo, dm, W, p);
+      else stats_tc_kernel<32, 64><<<grid, ST_THREADS, stats_tc_smem_bytes<32>(), st>>>(t.mapBhi, t.mapBlo, dm, W, p);
+   }
+}

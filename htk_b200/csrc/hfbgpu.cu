@@ -26,6 +26,7 @@
 #include "hfb_feat.cuh"
 #include "gmm_tc.cuh"
 #include "gmm_tc3.cuh"
+#include "hfb_stats_tc.cuh"
 
 static thread_local std::string g_lastError;
 
@@ -446,6 +447,7 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
    cudaFuncSetAttribute(beta_l2r_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(stats5_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(stats5_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
+   stats_tc_set_attributes();
    CK(cudaStreamSynchronize(c->stream));
    *out = c;
    return HFB_OK;
@@ -901,7 +903,8 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
             CK(cudaMemsetAsync(cnt, 0, (nIdx + 4) * sizeof(int), st));
             statpos_count_kernel<<<nU, 128, 0, st>>>(W, cnt);
             statpos_scan_kernel<<<1, 1024, 0, st>>>(cnt, off, fill, Jm);
-            statpos_scatter_kernel<<<nU, 128, 0, st>>>(W, off, fill, list, vCursor, vCap, posIdx);
+            int *overflow = cnt + nIdx + 2;             // zeroed with the counters above
+            statpos_scatter_kernel<<<nU, 128, 0, st>>>(W, off, fill, list, vCursor, vCap, posIdx, overflow);
             if (pre) {
                const int gy = std::max(1, std::min(16, (w.maxQ + SPRE_WARPS - 1) / SPRE_WARPS));
                stats_pre_kernel<<<dim3(nU, gy), 32 * SPRE_WARPS, 0, st>>>(c->dm, W, list, posIdx, S.dValid.p, vcnt);
@@ -913,8 +916,16 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
             while (cap < 64 && w.totalP >= (long long)2 * cap * S4_WARPS * 3 * c->smCount * 2) cap *= 2;
             const unsigned nWarps = (unsigned)((w.totalP + cap - 1) / cap);
             const unsigned grid = (nWarps + S4_WARPS - 1) / S4_WARPS;
-            if (Dd + 1 <= 32) stats5_kernel<4><<<grid, 32 * S4_WARPS, S4_WARPS * stats5_warp_bytes<4>(Dd), st>>>(c->dm, W, c->dCentre.p, list, off + Jm, S.dValid.p, vcnt, cap);
-            else stats5_kernel<5><<<grid, 32 * S4_WARPS, S4_WARPS * stats5_warp_bytes<5>(Dd), st>>>(c->dm, W, c->dCentre.p, list, off + Jm, S.dValid.p, vcnt, cap);
+            // the sums on tcgen05 (hfb_stats_tc.cuh); stats5_kernel then only runs for a wave whose frame lists overflowed
+            const int *only = nullptr;
+            if (pre && c->useV3 && stats_tc_supported(c->tc3, Dd) && !getenv("HFBGPU_STATS5")) {
+               const bool v3ran = c->opt.gmmKernel != 1;
+               stats_tc_launch(c->tc3, c->dm, W, list, off + Jm, S.dValid.p, vcnt, v3ran ? S.tcw.dFlag3 : nullptr, overflow, w.totalP, st);
+               c->stats.launches++; c->stats.launchesStats++;
+               only = overflow;
+            }
+            if (Dd + 1 <= 32) stats5_kernel<4><<<grid, 32 * S4_WARPS, S4_WARPS * stats5_warp_bytes<4>(Dd), st>>>(c->dm, W, c->dCentre.p, list, off + Jm, S.dValid.p, vcnt, cap, only);
+            else stats5_kernel<5><<<grid, 32 * S4_WARPS, S4_WARPS * stats5_warp_bytes<5>(Dd), st>>>(c->dm, W, c->dCentre.p, list, off + Jm, S.dValid.p, vcnt, cap, only);
             c->stats.launches += 3; c->stats.launchesStats += 3;
          } else
             stats3_kernel<<<(unsigned)((w.totalP + ST_WARPS - 1) / ST_WARPS), 32 * ST_WARPS, stats_smem_bytes(c->dm.D), st>>>(c->dm, W);

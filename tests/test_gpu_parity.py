@@ -636,3 +636,27 @@ def test_ring_window_beta_equals_sliding_block_kernel(monkeypatch):
     oacc, ores, obeams = _oracle(fm, b, kw2)
     assert [(r.status, r.retries, r.pruneThresh) for r in outs[0][0]] == [(o[0], o[1], o[3]) for o in ores]
     assert np.array_equal(outs[0][1].qLo, obeams.qLo) and np.array_equal(outs[0][1].qHi, obeams.qHi)
+
+
+@pytest.mark.parametrize("name", ["synth_tied_m4", "synth_long_m3", "synth_tee_m2"])
+def test_tcgen05_statistics_equal_mma_sync_statistics(name, monkeypatch):
+    """K4 on tcgen05 (hfb_stats_tc.cuh: component posteriors and occupancy-weighted sums as two UMMA contractions per
+    tied state, the default) against stats5_kernel (FP32 posteriors + mma.sync sums, HFBGPU_STATS5) and the per-position
+    FP32 kernel (HFBGPU_STATS3); all three against the oracle elsewhere."""
+    z, fm, b, kw = load_golden(name)
+    outs = []
+    for env in (None, "HFBGPU_STATS5", "HFBGPU_STATS3"):
+        if env:
+            monkeypatch.setenv(env, "1")
+        fb = _fb(fm, **kw)
+        fb.FBFile(b)
+        outs.append(fb.GetAccs())
+        fb.close()
+        if env:
+            monkeypatch.delenv(env)
+    for other in outs[1:]:
+        e = acc_errors(outs[0], other, fm)
+        assert max(e.values()) < 2e-5, e
+    oacc, _, _ = _oracle(fm, b, kw)
+    e = acc_errors(outs[0], oacc, fm)
+    assert max(e.values()) < RTOL, e
