@@ -126,13 +126,54 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
    uint32_t phB = 0, ph1 = 0, ph2 = 0;
    float run[N];                                        // running sums of operand column `tid` of the current state
 
-   for (int a = 0; a < nPos;) {
-      const int s = stt[a];
-      int b = a + 1;
-      while (b < nPos && stt[b] == s) b++;
-      const int g0 = pre[a], g1 = pre[b];
-      if (g1 > g0) {
-         const int mo = M.stateMixOff[s], Mn = M.stateMixOff[s + 1] - mo;
+   // ---- the tiles of my slice: consecutive blocks of 128 frames of one state segment [a, b) of the position list.
+   //      The rows of the NEXT tile are fetched (list entry -> frame record -> feature row: three dependent global
+   //      loads) while the tensor core and the epilogue work on the current one.
+   struct TileAt { int a, b, t0, g1, s; bool have; };
+   auto next_tile = [&](TileAt c) -> TileAt {
+      if (c.have && c.t0 + TC_BM < c.g1) { c.t0 += TC_BM; return c; }
+      int na = c.have ? c.b : 0;
+      for (;;) {
+         if (na >= nPos) { c.have = false; return c; }
+         int nb = na + 1;
+         const int st = stt[na];
+         while (nb < nPos && stt[nb] == st) nb++;
+         if (pre[nb] > pre[na]) { c.a = na; c.b = nb; c.t0 = pre[na]; c.g1 = pre[nb]; c.s = st; c.have = true; return c; }
+         na = nb;
+      }
+   };
+   float x[DP];                                         // my row of the tile in flight: scaled, clamped features
+   float px0 = 0.f;
+   bool pvalid = false, pfar = false;
+   const float *pfrow = nullptr;
+   auto fetch = [&](const TileAt &c) {
+      pvalid = false; pfar = false; pfrow = nullptr; px0 = 0.f;
+      if (!worker || !c.have) return;
+      const int g = c.t0 + tid;
+      pvalid = g < c.g1;
+#pragma unroll
+      for (int d = 0; d < DP; d++) x[d] = 0.f;
+      if (pvalid) {
+         int lo = c.a, hi = c.b;                        // position with pre[it] <= g < pre[it + 1]
+         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= g) lo = mid; else hi = mid; }
+         const PosRec &R = p.list[i0 + lo];
+         const ValidFrame vf = p.vbuf[R.vOff + (g - pre[lo])];
+         px0 = (float)vf.x0;
+         pfrow = W.feat + ((size_t)R.featOff + vf.t) * D;
+         pfar = p.flag != nullptr && p.flag[R.frameBase + vf.t] != 0;
+#pragma unroll
+         for (int d = 0; d < DP; d++)
+            if (d < D) x[d] = fminf(fmaxf((pfrow[d] - p.offset[d]) * p.scale[d], -250.f), 250.f);
+      }
+   };
+   TileAt cur; cur.a = cur.b = cur.t0 = cur.g1 = 0; cur.s = -1; cur.have = false;
+   cur = next_tile(cur);
+   fetch(cur);
+   const float minFf = (float)minF;
+   while (cur.have) {
+      const int s = cur.s, mo = M.stateMixOff[s], Mn = M.stateMixOff[s + 1] - mo;
+      const bool first = cur.t0 == pre[cur.a], last = cur.t0 + TC_BM >= cur.g1;
+      if (first) {
          // ---- the state's Gaussians: rows TC3_ROW0 + s MP .. + N of the tensor-core B operand
          if (warp == 4 && lane == 0) {
             tc_mbar_expect_tx(barB, 4 * N * 128);
@@ -146,151 +187,135 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
          }
 #pragma unroll
          for (int m = 0; m < N; m++) run[m] = 0.f;
-         bool newState = true;
-         for (int t0 = g0; t0 < g1; t0 += TC_BM) {
-            // ================= phase A: gather + expand 128 frames (thread = row) =================
-            double x0 = 0.0;
-            bool valid = false, far = false;
-            const float *frow = nullptr;
-            if (worker) {
-               const int g = t0 + tid;
-               valid = g < g1;
-               float x[DP];
+      }
+      // ================= phase A: my row of the tile -> shared memory (thread = row) =================
+      const bool valid = pvalid, far = pfar;
+      const float x0 = px0;
+      const float *frow = pfrow;
+      if (worker) {
 #pragma unroll
-               for (int d = 0; d < DP; d++) x[d] = 0.f;
-               if (valid) {
-                  int lo = a, hi = b;                   // position with pre[it] <= g < pre[it + 1]
-                  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= g) lo = mid; else hi = mid; }
-                  const PosRec &R = p.list[i0 + lo];
-                  const ValidFrame vf = p.vbuf[R.vOff + (g - pre[lo])];
-                  x0 = vf.x0;
-                  frow = W.feat + ((size_t)R.featOff + vf.t) * D;
-                  far = p.flag != nullptr && p.flag[R.frameBase + vf.t] != 0;
+         for (int un = 0; un < 16; un++) {
+            if (un >= 2 * p.kSteps) break;
+            float v[8];
 #pragma unroll
-                  for (int d = 0; d < DP; d++)
-                     if (d < D) x[d] = fminf(fmaxf((frow[d] - p.offset[d]) * p.scale[d], -250.f), 250.f);
-               }
-#pragma unroll
-               for (int un = 0; un < 16; un++) {
-                  if (un >= 2 * p.kSteps) break;
-                  float v[8];
-#pragma unroll
-                  for (int e = 0; e < 8; e++) {
-                     const int k = un * 8 + e;
-                     if (k == 0) v[e] = valid ? 1.f : 0.f;
-                     else if (k & 1) { const int d = (k - 1) >> 1; v[e] = (d < DP && d < D) ? x[d < DP ? d : 0] * x[d < DP ? d : 0] : ((d == D && valid) ? 1.f : 0.f); }
-                     else { const int d = (k - 2) >> 1; v[e] = (d < DP && d < D) ? x[d < DP ? d : 0] : 0.f; }
-                  }
-                  uint32_t h4[4], l4[4];
-#pragma unroll
-                  for (int e = 0; e < 4; e++) {
-                     const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-                     const float2 hf = __half22float2(h);
-                     const __half2 l = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
-                     h4[e] = *reinterpret_cast<const uint32_t *>(&h);
-                     l4[e] = *reinterpret_cast<const uint32_t *>(&l);
-                  }
-                  const uint32_t off = tc3_unit_off(tid, un);
-                  *reinterpret_cast<uint4 *>(sA + off) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
-                  *reinterpret_cast<uint4 *>(sA + 32768 + off) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
-               }
-               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int e = 0; e < 8; e++) {
+               const int k = un * 8 + e;
+               if (k == 0) v[e] = valid ? 1.f : 0.f;
+               else if (k & 1) { const int d = (k - 1) >> 1; v[e] = (d < DP && d < D) ? x[d < DP ? d : 0] * x[d < DP ? d : 0] : ((d == D && valid) ? 1.f : 0.f); }
+               else { const int d = (k - 2) >> 1; v[e] = (d < DP && d < D) ? x[d < DP ? d : 0] : 0.f; }
             }
-            tc_fence_before();
-            __syncthreads();
-            tc_fence_after();
-            // ================= (1): V = A x B_state^T =================
-            if (warp == 4) {
-               if (newState) { tc_mbar_wait(barB, phB); phB ^= 1; tc_fence_after(); }
-               if (lane == 0) {
-                  const uint32_t aB = tc_smem_u32(sA), bB = tc_smem_u32(sB1);
-                  for (int ks = 0; ks < p.kSteps; ks++) {              // corrections first (see gmm_tc3_kernel)
-                     const uint32_t oa = (ks >> 2) * 16384 + (ks & 3) * 32, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
-                     st_mma_f16(tD1, tc_smem_desc(aB + oa), tc_smem_desc(bB + 2 * N * 128 + ob), idesc1, ks ? 1u : 0u);
-                     st_mma_f16(tD1, tc_smem_desc(aB + 32768 + oa), tc_smem_desc(bB + ob), idesc1, 1u);
-                  }
-                  for (int ks = 0; ks < p.kSteps; ks++) {
-                     const uint32_t oa = (ks >> 2) * 16384 + (ks & 3) * 32, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
-                     st_mma_f16(tD1, tc_smem_desc(aB + oa), tc_smem_desc(bB + ob), idesc1, 1u);
-                  }
-                  tc_commit(bar1);
-               }
-               __syncwarp();
-            }
-            newState = false;
-            // ================= epilogue of (1): Lr -> B operand of (2) =================
-            if (worker) {
-               tc_mbar_wait(bar1, ph1);
-               tc_fence_after();
-               float v[N];
-               st_tmem_ld<N>(tD1 + ((uint32_t)(warp * 32) << 16), v);
-               if (valid && far && Mn > 1) {
-                  // operands out of the FP16 range: the component log-likelihoods as IDOutP computes them (HModel.c:5420-5431)
+            uint32_t h4[4], l4[4];
 #pragma unroll
-                  for (int m = 0; m < N; m++) {
-                     float val = -1.0e30f;
-                     if (m < Mn) {
-                        const float wt = M.mixLogWt[mo + m];
-                        if (wt > LMINMIX_F) {
-                           const int g = M.mixGauss[mo + m];
-                           const float *mu = M.mean + (size_t)g * Dp, *iv = M.ivar + (size_t)g * Dp;
-                           float acc = M.gconst[g];
-                           for (int k = 0; k < D; k++) { const float dd = frow[k] - mu[k]; acc = fmaf(dd * dd, iv[k], acc); }
-                           val = -0.5f * acc + wt + p.C0;
-                        }
-                     }
-                     v[m] = val;
-                  }
-               }
-#pragma unroll
-               for (int m = 0; m < N; m++) {
-                  float Lr = 0.f;
-                  if (valid && m < Mn) {
-                     // x = initx + log weight + log N_m (:1581-1599); single-Gaussian states: x = log occupancy (:1575-1576)
-                     const double x = (Mn > 1) ? x0 + (double)(v[m] - p.C0) : x0;
-                     if (-x < minF && (Mn > 1 || m == 0)) Lr = expf((float)x) * ST_LR_SCALE;      // :1606, :1612
-                  }
-                  const __half h = __float2half_rn(Lr), l = __float2half_rn(Lr - __half2float(h));
-                  const uint32_t off = (uint32_t)((tid >> 6) * (N * 128) + m * 128 + ((((tid & 63) >> 3) ^ (m & 7)) << 4) + (tid & 7) * 2);
-                  *reinterpret_cast<__half *>(sB2 + off) = h;
-                  *reinterpret_cast<__half *>(sB2 + 2 * N * 128 + off) = l;
-               }
-               ph1 ^= 1;
-               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int e = 0; e < 4; e++) {
+               const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+               const float2 hf = __half22float2(h);
+               const __half2 l = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+               h4[e] = *reinterpret_cast<const uint32_t *>(&h);
+               l4[e] = *reinterpret_cast<const uint32_t *>(&l);
             }
-            tc_fence_before();
-            __syncthreads();
-            tc_fence_after();
-            // ================= (2): S = A^T x Lr =================
-            if (warp == 4) {
-               if (lane == 0) {
-                  const uint32_t aB = tc_smem_u32(sA), bB = tc_smem_u32(sB2);
-                  for (int ks = 0; ks < 8; ks++) {                    // 16 frames per step
-                     const uint32_t oa = ks * 2048, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
-                     st_mma_f16(tD2, st_desc_mn(aB + oa, 16384, 1024), tc_smem_desc(bB + 2 * N * 128 + ob), idesc2, ks ? 1u : 0u);
-                     st_mma_f16(tD2, st_desc_mn(aB + 32768 + oa, 16384, 1024), tc_smem_desc(bB + ob), idesc2, 1u);
-                  }
-                  for (int ks = 0; ks < 8; ks++) {
-                     const uint32_t oa = ks * 2048, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
-                     st_mma_f16(tD2, st_desc_mn(aB + oa, 16384, 1024), tc_smem_desc(bB + ob), idesc2, 1u);
-                  }
-                  tc_commit(bar2);
-               }
-               __syncwarp();
-            }
-            if (worker) {
-               tc_mbar_wait(bar2, ph2);
-               ph2 ^= 1;
-               tc_fence_after();
-               float v[N];
-               st_tmem_ld<N>(tD2 + ((uint32_t)(warp * 32) << 16), v);
-#pragma unroll
-               for (int m = 0; m < N; m++) run[m] += v[m];
-            }
-            tc_fence_before();
-            __syncthreads();                            // the tile, Lr and both accumulators may be overwritten
-            tc_fence_after();
+            const uint32_t off = tc3_unit_off(tid, un);
+            *reinterpret_cast<uint4 *>(sA + off) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+            *reinterpret_cast<uint4 *>(sA + 32768 + off) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
          }
+         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+      const TileAt nxt = next_tile(cur);
+      fetch(nxt);                                       // in flight during (1), its epilogue and (2)
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      // ================= (1): V = A x B_state^T =================
+      if (warp == 4) {
+         if (first) { tc_mbar_wait(barB, phB); phB ^= 1; tc_fence_after(); }
+         if (lane == 0) {
+            const uint32_t aB = tc_smem_u32(sA), bB = tc_smem_u32(sB1);
+            for (int ks = 0; ks < p.kSteps; ks++) {              // corrections first (see gmm_tc3_kernel)
+               const uint32_t oa = (ks >> 2) * 16384 + (ks & 3) * 32, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
+               st_mma_f16(tD1, tc_smem_desc(aB + oa), tc_smem_desc(bB + 2 * N * 128 + ob), idesc1, ks ? 1u : 0u);
+               st_mma_f16(tD1, tc_smem_desc(aB + 32768 + oa), tc_smem_desc(bB + ob), idesc1, 1u);
+            }
+            for (int ks = 0; ks < p.kSteps; ks++) {
+               const uint32_t oa = (ks >> 2) * 16384 + (ks & 3) * 32, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
+               st_mma_f16(tD1, tc_smem_desc(aB + oa), tc_smem_desc(bB + ob), idesc1, 1u);
+            }
+            tc_commit(bar1);
+         }
+         __syncwarp();
+      }
+      // ================= epilogue of (1): Lr -> B operand of (2) =================
+      if (worker) {
+         tc_mbar_wait(bar1, ph1);
+         tc_fence_after();
+         float v[N];
+         st_tmem_ld<N>(tD1 + ((uint32_t)(warp * 32) << 16), v);
+         if (valid && far && Mn > 1) {
+            // operands out of the FP16 range: the component log-likelihoods as IDOutP computes them (HModel.c:5420-5431)
+#pragma unroll
+            for (int m = 0; m < N; m++) {
+               float val = -1.0e30f;
+               if (m < Mn) {
+                  const float wt = M.mixLogWt[mo + m];
+                  if (wt > LMINMIX_F) {
+                     const int g = M.mixGauss[mo + m];
+                     const float *mu = M.mean + (size_t)g * Dp, *iv = M.ivar + (size_t)g * Dp;
+                     float acc = M.gconst[g];
+                     for (int k = 0; k < D; k++) { const float dd = frow[k] - mu[k]; acc = fmaf(dd * dd, iv[k], acc); }
+                     val = -0.5f * acc + wt + p.C0;
+                  }
+               }
+               v[m] = val;
+            }
+         }
+         const uint32_t offT = (uint32_t)((tid >> 6) * (N * 128) + (tid & 7) * 2), unit = (uint32_t)((tid & 63) >> 3);
+#pragma unroll
+         for (int m = 0; m < N; m++) {
+            float Lr = 0.f;
+            if (valid && m < Mn) {
+               // x = initx + log weight + log N_m (:1581-1599); single-Gaussian states: x = log occupancy (:1575-1576)
+               const float xx = (Mn > 1) ? x0 + (v[m] - p.C0) : x0;
+               if (-xx < minFf && (Mn > 1 || m == 0)) Lr = tc_ex2(xx * 1.4426950408889634f) * ST_LR_SCALE;   // :1606, :1612
+            }
+            const __half h = __float2half_rn(Lr), l = __float2half_rn(Lr - __half2float(h));
+            const uint32_t off = offT + (uint32_t)(m * 128) + ((unit ^ (uint32_t)(m & 7)) << 4);
+            *reinterpret_cast<__half *>(sB2 + off) = h;
+            *reinterpret_cast<__half *>(sB2 + 2 * N * 128 + off) = l;
+         }
+         ph1 ^= 1;
+         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      // ================= (2): S = A^T x Lr =================
+      if (warp == 4) {
+         if (lane == 0) {
+            const uint32_t aB = tc_smem_u32(sA), bB = tc_smem_u32(sB2);
+            for (int ks = 0; ks < 8; ks++) {                    // 16 frames per step
+               const uint32_t oa = ks * 2048, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
+               st_mma_f16(tD2, st_desc_mn(aB + oa, 16384, 1024), tc_smem_desc(bB + 2 * N * 128 + ob), idesc2, ks ? 1u : 0u);
+               st_mma_f16(tD2, st_desc_mn(aB + 32768 + oa, 16384, 1024), tc_smem_desc(bB + ob), idesc2, 1u);
+            }
+            for (int ks = 0; ks < 8; ks++) {
+               const uint32_t oa = ks * 2048, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
+               st_mma_f16(tD2, st_desc_mn(aB + oa, 16384, 1024), tc_smem_desc(bB + ob), idesc2, 1u);
+            }
+            tc_commit(bar2);
+         }
+         __syncwarp();
+      }
+      if (worker) {
+         tc_mbar_wait(bar2, ph2);
+         ph2 ^= 1;
+         tc_fence_after();
+         float v[N];
+         st_tmem_ld<N>(tD2 + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+         for (int m = 0; m < N; m++) run[m] += v[m];
+      }
+      tc_fence_before();
+      __syncthreads();                                  // the tile, Lr and both accumulators may be overwritten
+      tc_fence_after();
+      if (last) {
          // ================= flush: the state's sums -> FP64 accumulators, centred on the component means =================
          if (worker) {
 #pragma unroll
@@ -322,7 +347,7 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
          }
          __syncthreads();
       }
-      a = b;
+      cur = nxt;
    }
    tc_fence_before();
    __syncthreads();

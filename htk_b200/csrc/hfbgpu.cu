@@ -434,7 +434,9 @@ extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_opt
 
    size_t freeB = 0, totalB = 0;
    CK(cudaMemGetInfo(&freeB, &totalB));
-   size_t ws = opt->workspaceBytes ? opt->workspaceBytes : ((size_t)48 << 30);
+   // default: 70 % of what is free now (the per-wave buffers grow on demand up to this; models, accumulators and the
+   // caller's own feature buffers live in the rest)
+   size_t ws = opt->workspaceBytes ? opt->workspaceBytes : freeB / 10 * 7;
    if (ws > freeB / 10 * 8) ws = freeB / 10 * 8;
    c->workspaceBytes = ws;
 

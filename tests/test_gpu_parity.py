@@ -320,8 +320,8 @@ def test_tensor_core_statistics_equal_fp32_statistics(name, monkeypatch):
     fb = _fb(fm, **kw); fb.FBFile(b); a1 = fb.GetAccs(); fb.close()
     monkeypatch.setenv("HFBGPU_STATS3", "1")
     fb = _fb(fm, **kw); fb.FBFile(b); a2 = fb.GetAccs(); fb.close()
-    e = acc_errors(a1, a2, fm)             # stats5: centre-relative TF32-split sums, product and sum of IDOutP's
-    assert max(e.values()) < 2e-5, e       # inner loop fused (FFMA2); stats3: the reference's order of operations
+    e = acc_errors(a1, a2, fm)             # tcgen05 statistics: posteriors from the 3xFP16-split product (~4e-6 on log N,
+    assert max(e.values()) < 5e-5, e       # times |o - mu| / sigma ~ 3 in the centred sums); stats3: the reference's order of operations
     e = acc_errors(a1, z["ref_acc"], fm)
     assert max(e.values()) < RTOL, e
 
@@ -656,7 +656,7 @@ def test_tcgen05_statistics_equal_mma_sync_statistics(name, monkeypatch):
             monkeypatch.delenv(env)
     for other in outs[1:]:
         e = acc_errors(outs[0], other, fm)
-        assert max(e.values()) < 2e-5, e
+        assert max(e.values()) < 5e-5, e
     oacc, _, _ = _oracle(fm, b, kw)
     e = acc_errors(outs[0], oacc, fm)
     assert max(e.values()) < RTOL, e
