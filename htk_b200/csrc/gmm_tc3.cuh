@@ -78,6 +78,19 @@ __device__ __forceinline__ void tc3_wait_acquire_cluster(uint64_t *bar, uint32_t
    } while (!done);
 }
 
+__device__ __forceinline__ void tc3_tmem_ld32_nowait(uint32_t taddr, float *v)
+{
+   uint32_t *r = reinterpret_cast<uint32_t *>(v);
+   asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+}
+
 template <int MP, int DP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
 gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, Tc3Params p)
@@ -91,8 +104,10 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
    uint8_t *sB = base + 2 * A_BLK;
    uint64_t *bars = (uint64_t *)(sB + NST * ST_BYTES);
    uint64_t *fullA = bars, *emptyA = bars + 1, *fullB = bars + 2, *emptyB = bars + 2 + NST;
-   uint64_t *tmemFull = bars + 2 + 2 * NST, *tmemEmpty = tmemFull + 2;
-   uint32_t *tmemSlot = (uint32_t *)(tmemEmpty + 2);
+   // accumulator hand-over per (buffer, 128-frame block): the epilogue of block 0 runs while the tensor core still
+   // works on block 1 of the same tile
+   uint64_t *tmemFull = bars + 2 + 2 * NST, *tmemEmpty = tmemFull + 4;
+   uint32_t *tmemSlot = (uint32_t *)(tmemEmpty + 4);
    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const uint32_t rank = tc_cluster_ctarank();          // 0 = leader (issues the MMAs)
    const int pair = blockIdx.x >> 1, nPairs = gridDim.x >> 1;
@@ -105,7 +120,7 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
       // fullA: both CTAs' expanders (4 warps each) arrive on the LEADER's barrier; emptyA: one commit, multicast
       tc_mbar_init(fullA, 8); tc_mbar_init(emptyA, 1);
       for (int s = 0; s < NST; s++) { tc_mbar_init(&fullB[s], 1); tc_mbar_init(&emptyB[s], 1); }
-      for (int s = 0; s < 2; s++) { tc_mbar_init(&tmemFull[s], 1); tc_mbar_init(&tmemEmpty[s], 2 * EPW); }
+      for (int s = 0; s < 4; s++) { tc_mbar_init(&tmemFull[s], 1); tc_mbar_init(&tmemEmpty[s], 2 * EPW); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    if (warp == 1) {
@@ -175,7 +190,7 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
          asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
          const uint32_t idesc = tc_idesc(2 * TC_BM, TC_BN, 0u);
          const uint32_t aBase = tc_smem_u32(sA), bBase = tc_smem_u32(sB);
-         uint32_t stage = 0, phB = 0, phA = 0, tile = 0;
+         uint32_t stage = 0, phB = 0, phA = 0, tile = 0, phAcc = 0;    // phAcc: one phase bit per (buffer, block)
          for (int it = pair; it < p.nItems; it += nPairs) {
             const int2 item = p.items[it];
             const UttDesc u = p.utt[item.x];
@@ -190,15 +205,16 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
                if (n + 1 < nTiles) ivN = tiv[n + 1];
                const int need = tile_need(iv.x, iv.y, item.y, u.T);
                if (!need) continue;
-               const uint32_t as = tile & 1, phT = (tile >> 1) & 1;
-               tc_mbar_wait(&tmemEmpty[as], phT ^ 1);
-               tc_fence_after();
+               const uint32_t as = tile & 1;
                const uint32_t dMain = tmem + as * (2 * TC_BN);
                tc_mbar_wait(&fullB[stage], phB);
                tc_fence_after();
                const uint32_t bSt = bBase + stage * ST_BYTES;
                for (int b = 0; b < 2; b++) {
                   if (!(need & (1 << b))) continue;
+                  const uint32_t ai = as * 2 + b;
+                  tc_mbar_wait(&tmemEmpty[ai], ((phAcc >> ai) & 1u) ^ 1u);
+                  tc_fence_after();
                   const uint32_t aB = aBase + b * A_BLK, dAcc = dMain + b * TC_BN;
 #pragma unroll
                   for (int ks = 0; ks < 8; ks++) {
@@ -218,12 +234,13 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
                      const uint64_t dAhi = tc_smem_desc(aB + o), dBhi = tc_smem_desc(bSt + o);
                      if (elected) tc_mma_pair<true>(dAcc, dAhi, dBhi, idesc, 1u);
                   }
+                  if (elected) tc_commit_pair(&tmemFull[ai]);      // this block's accumulator: ready for both CTAs' epilogues
+                  __syncwarp();
+                  phAcc ^= 1u << ai;
                }
                if (elected) tc_commit_pair(&emptyB[stage]);
                __syncwarp();
                if (++stage == NST) { stage = 0; phB ^= 1; }
-               if (elected) tc_commit_pair(&tmemFull[as]);
-               __syncwarp();
                tile++;
             }
             if (elected) tc_commit_pair(emptyA);                 // A blocks reusable (arrives in both CTAs)
@@ -236,7 +253,7 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
       constexpr int CPW = 2;                            // 32-column chunks per warp (8 warps: two per quadrant)
       const int c0 = ((warp - 2) >> 2) * CPW;
       const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-      uint32_t tile = 0;
+      uint32_t tile = 0, phAcc = 0;
       for (int it = pair; it < p.nItems; it += nPairs) {
          const int2 item = p.items[it];
          const UttDesc u = p.utt[item.x];
@@ -249,13 +266,18 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
             const int need = tile_need(iv.x, iv.y, item.y, u.T);
             if (!need) continue;
             const int f = iv.x, l = iv.y;
-            const uint32_t as = tile & 1, phT = (tile >> 1) & 1;
-            tc_mbar_wait(&tmemFull[as], phT);
-            tc_fence_after();
+            const uint32_t as = tile & 1;
             for (int blk = 0; blk < 2; blk++) {
+               if (!(need & (1 << blk))) continue;
+               const uint32_t ai = as * 2 + blk;
+               tc_mbar_wait(&tmemFull[ai], (phAcc >> ai) & 1u);
+               tc_fence_after();
+               phAcc ^= 1u << ai;
+               // hands the block's accumulator back (also when this warp had nothing to read from it)
+               auto release = [&]() { tc_fence_before(); __syncwarp(); if (lane == 0) tc_mbar_arrive_leader(&tmemEmpty[ai]); };
                const int w0 = item.y + (2 * blk + (int)rank) * TC_BM + quad * 32;      // first frame of this warp
                // nothing of this warp's 32 frames lies inside the tile's interval (or inside the utterance)
-               if (!(need & (1 << blk)) || w0 >= u.T || f >= w0 + 32 || l < w0 || (p.dbg & 2)) continue;
+               if (w0 >= u.T || f >= w0 + 32 || l < w0 || (p.dbg & 2)) { release(); continue; }
                const int t = w0 + lane;
                float *brow = p.b + u.bOff + (size_t)t * u.J;
                const uint32_t taddr = tmem + as * (2 * TC_BN) + blk * TC_BN + ((uint32_t)(quad * 32) << 16);
@@ -279,17 +301,24 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
                               *reinterpret_cast<float4 *>(brow + slot0 + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
                      }
                   }
+                  release();
                   continue;
                }
                float cmx = -INFINITY, csum = 0.f;       // carry for states wider than one 32-column chunk
                constexpr int NOUT = (MP <= 32) ? CPW * 32 / MP : 0;
                float outv[NOUT > 0 ? NOUT : 1];
                int no = 0;
+               // both chunks of this warp go to registers first and the accumulator is handed back BEFORE the log-sum-exp:
+               // the tensor core refills it while the special-function unit works through the 64 exponentials per lane
+               float vv[CPW][32];
+               tc3_tmem_ld32_nowait(taddr + c0 * 32, vv[0]);
+               tc3_tmem_ld32_nowait(taddr + (c0 + 1) * 32, vv[1]);
+               asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+               release();
 #pragma unroll
                for (int cc = 0; cc < CPW; cc++) {
                   const int c = c0 + cc;
-                  float v[32];
-                  tc_tmem_ld32(taddr + c * 32, v);
+                  float (&v)[32] = vv[cc];
                   constexpr int G = (MP < 32) ? MP : 32;   // columns of one state inside this chunk
 #pragma unroll
                   for (int s0 = 0; s0 < 32; s0 += G) {
@@ -328,9 +357,6 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
                      *reinterpret_cast<float2 *>(brow + slot0) = make_float2(outv[0], outv[NOUT > 1 ? 1 : 0]);
                }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc_mbar_arrive_leader(&tmemEmpty[as]);
             tile++;
          }
       }
@@ -457,7 +483,7 @@ static inline int gmm_tc3_prepare(GmmTc3Model &t, const hfb_model *m, cudaStream
    } else {
       MP = 8;
       while (MP < maxM) MP *= 2;
-      if (MP > TC_BN) return HFB_OK;
+      if (MP > 64) return HFB_OK;                         // eight epilogue warps = two 32-column chunks each: a state spans at most one warp's share
    }
    int dev = 0, major = 0;
    cudaGetDevice(&dev);

@@ -87,7 +87,10 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
    float *stage = (float *)sB2;                         // [128][N] flush staging: Lr is dead when a state is flushed
    int *pre = (int *)(sB2 + 4 * N * 128);               // [ST_CAP + 1] prefix sums of the positions' frame counts
    int *stt = pre + ST_CAP + 1;                         // [ST_CAP] tied state of each position
-   uint64_t *bars = (uint64_t *)(((uintptr_t)(stt + ST_CAP) + 15) & ~(uintptr_t)15);
+   float *sOff = (float *)(stt + ST_CAP), *sScl = sOff + 64;   // per-dimension offset / scale of the operands
+   long long *pV = (long long *)(((uintptr_t)(sScl + 64) + 15) & ~(uintptr_t)15);   // per position: first entry of its frame list,
+   long long *pF = pV + ST_CAP, *pB = pF + ST_CAP;      // first frame of its utterance in the feature matrix / in the flag array
+   uint64_t *bars = (uint64_t *)(pB + ST_CAP);
    uint64_t *barB = bars, *bar1 = bars + 1, *bar2 = bars + 2;
    uint32_t *tmemSlot = (uint32_t *)(bars + 3);
    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -108,7 +111,9 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
       const int it = i0 + k;
       pre[k + 1] = (it < i1 && p.list[it].vOff >= 0) ? p.vcnt[it] : 0;
       stt[k] = (it < i1) ? p.list[it].s : -1;
+      if (it < i1) { pV[k] = p.list[it].vOff; pF[k] = p.list[it].featOff; pB[k] = p.list[it].frameBase; }
    }
+   if (tid < 64) { sOff[tid] = (tid < D) ? p.offset[tid] : 0.f; sScl[tid] = (tid < D) ? p.scale[tid] : 0.f; }
    for (uint32_t o = tid * 16; o < 65536; o += ST_THREADS * 16) *reinterpret_cast<uint4 *>(sA + o) = make_uint4(0u, 0u, 0u, 0u);
    tc_fence_before();
    __syncthreads();
@@ -142,12 +147,12 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
          na = nb;
       }
    };
-   float x[DP];                                         // my row of the tile in flight: scaled, clamped features
-   float px0 = 0.f;
+   float x[DP];                                         // my row of the tile in flight: RAW features (transformed when stored)
+   float px0 = 0.f, px0l = 0.f;                         // initx / log occupancy as hi + lo floats (it can be ~1e6 on outlier frames)
    bool pvalid = false, pfar = false;
    const float *pfrow = nullptr;
    auto fetch = [&](const TileAt &c) {
-      pvalid = false; pfar = false; pfrow = nullptr; px0 = 0.f;
+      pvalid = false; pfar = false; pfrow = nullptr; px0 = 0.f; px0l = 0.f;
       if (!worker || !c.have) return;
       const int g = c.t0 + tid;
       pvalid = g < c.g1;
@@ -156,14 +161,13 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
       if (pvalid) {
          int lo = c.a, hi = c.b;                        // position with pre[it] <= g < pre[it + 1]
          while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= g) lo = mid; else hi = mid; }
-         const PosRec &R = p.list[i0 + lo];
-         const ValidFrame vf = p.vbuf[R.vOff + (g - pre[lo])];
-         px0 = (float)vf.x0;
-         pfrow = W.feat + ((size_t)R.featOff + vf.t) * D;
-         pfar = p.flag != nullptr && p.flag[R.frameBase + vf.t] != 0;
+         const ValidFrame vf = p.vbuf[pV[lo] + (g - pre[lo])];
+         px0 = (float)vf.x0; px0l = (float)(vf.x0 - (double)px0);
+         pfrow = W.feat + ((size_t)pF[lo] + vf.t) * D;
+         pfar = p.flag != nullptr && p.flag[pB[lo] + vf.t] != 0;
 #pragma unroll
          for (int d = 0; d < DP; d++)
-            if (d < D) x[d] = fminf(fmaxf((pfrow[d] - p.offset[d]) * p.scale[d], -250.f), 250.f);
+            if (d < D) x[d] = pfrow[d];                 // no arithmetic here: the loads stay in flight behind the MMAs
       }
    };
    TileAt cur; cur.a = cur.b = cur.t0 = cur.g1 = 0; cur.s = -1; cur.have = false;
@@ -190,9 +194,12 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
       }
       // ================= phase A: my row of the tile -> shared memory (thread = row) =================
       const bool valid = pvalid, far = pfar;
-      const float x0 = px0;
+      const float x0 = px0, x0l = px0l;
       const float *frow = pfrow;
       if (worker) {
+#pragma unroll
+         for (int d = 0; d < DP; d++)
+            if (d < D) x[d] = valid ? fminf(fmaxf((x[d] - sOff[d]) * sScl[d], -250.f), 250.f) : 0.f;
 #pragma unroll
          for (int un = 0; un < 16; un++) {
             if (un >= 2 * p.kSteps) break;
@@ -248,6 +255,8 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
          tc_fence_after();
          float v[N];
          st_tmem_ld<N>(tD1 + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+         for (int m = 0; m < N; m++) v[m] -= p.C0;      // log weight + log N_m
          if (valid && far && Mn > 1) {
             // operands out of the FP16 range: the component log-likelihoods as IDOutP computes them (HModel.c:5420-5431)
 #pragma unroll
@@ -260,7 +269,7 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
                      const float *mu = M.mean + (size_t)g * Dp, *iv = M.ivar + (size_t)g * Dp;
                      float acc = M.gconst[g];
                      for (int k = 0; k < D; k++) { const float dd = frow[k] - mu[k]; acc = fmaf(dd * dd, iv[k], acc); }
-                     val = -0.5f * acc + wt + p.C0;
+                     val = -0.5f * acc + wt;
                   }
                }
                v[m] = val;
@@ -272,7 +281,9 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
             float Lr = 0.f;
             if (valid && m < Mn) {
                // x = initx + log weight + log N_m (:1581-1599); single-Gaussian states: x = log occupancy (:1575-1576)
-               const float xx = (Mn > 1) ? x0 + (v[m] - p.C0) : x0;
+               // (on an outlier frame initx and log N_m are both ~1e6 with opposite signs: their float sum is exact, the
+               // low part of initx restores what its own rounding to float lost)
+               const float xx = (Mn > 1) ? (x0 + v[m]) + x0l : x0 + x0l;
                if (-xx < minFf && (Mn > 1 || m == 0)) Lr = tc_ex2(xx * 1.4426950408889634f) * ST_LR_SCALE;   // :1606, :1612
             }
             const __half h = __float2half_rn(Lr), l = __float2half_rn(Lr - __half2float(h));
@@ -358,7 +369,7 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
 }
 
 template <int N>
-static inline size_t stats_tc_smem_bytes() { return 1024 + 65536 + 8 * N * 128 + sizeof(int) * (2 * ST_CAP + 1) + 128; }
+static inline size_t stats_tc_smem_bytes() { return 1024 + 65536 + 8 * N * 128 + sizeof(int) * (2 * ST_CAP + 1) + 512 + 16 + 3 * 8 * ST_CAP + 128; }
 
 // Launch: returns false when the model is outside what the kernel covers (the caller keeps stats5_kernel).
 static inline bool stats_tc_supported(const GmmTc3Model &t, int D) { return t.ready && (t.MP == 8 || t.MP == 16 || t.MP == 32) && D <= 63; }

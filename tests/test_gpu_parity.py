@@ -333,6 +333,7 @@ def test_statistics_front_kernel_equals_inline_front(name, cap, monkeypatch):
     stats5_kernel (HFBGPU_NO_STATS_PRE); with a list too small for the wave (HFBGPU_STATS_PRE_CAP) some positions
     take one front and some the other inside the same launch."""
     z, fm, b, kw = load_golden(name)
+    monkeypatch.setenv("HFBGPU_STATS5", "1")           # same back end (mma.sync sums) behind both fronts
     if cap:
         monkeypatch.setenv("HFBGPU_STATS_PRE_CAP", cap)
     fb = _fb(fm, **kw); fb.FBFile(b); a1 = fb.GetAccs(); fb.close()
@@ -659,4 +660,18 @@ def test_tcgen05_statistics_equal_mma_sync_statistics(name, monkeypatch):
         assert max(e.values()) < 5e-5, e
     oacc, _, _ = _oracle(fm, b, kw)
     e = acc_errors(outs[0], oacc, fm)
+    assert max(e.values()) < RTOL, e
+
+
+def test_tcgen05_statistics_leave_overflowing_waves_to_stats5(monkeypatch):
+    """When the frame lists of stats_pre_kernel overflow (HFBGPU_STATS_PRE_CAP), the tcgen05 statistics kernel steps
+    aside for the whole wave and stats5_kernel (with its inline front for the positions without a list) does it."""
+    z, fm, b, kw = load_golden("synth_tied_m4")
+    fb = _fb(fm, **kw); fb.FBFile(b); a1 = fb.GetAccs(); fb.close()
+    monkeypatch.setenv("HFBGPU_STATS_PRE_CAP", "700")
+    fb = _fb(fm, **kw); fb.FBFile(b); a2 = fb.GetAccs(); fb.close()
+    e = acc_errors(a1, a2, fm)
+    assert max(e.values()) < 5e-5, e
+    oacc, _, _ = _oracle(fm, b, kw)
+    e = acc_errors(a2, oacc, fm)
     assert max(e.values()) < RTOL, e
