@@ -61,6 +61,18 @@ __device__ __forceinline__ uint32_t tc3_unit_off(int r, int unit)       // unit 
    return (uint32_t)((unit >> 3) * 16384 + r * 128 + (((unit & 7) ^ (r & 7)) << 4));
 }
 
+// a wait that may sleep: the expander warps wait for most of an item's duration and must not take issue slots from the
+// epilogue warps that share their schedulers (the spin loops were 12 % of the kernel's instructions)
+__device__ __forceinline__ void tc3_mbar_wait_relaxed(uint64_t *bar, uint32_t parity)
+{
+   uint32_t done, addr = tc_smem_u32(bar);
+   do {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                   "selp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(addr), "r"(parity), "r"(2000u) : "memory");
+   } while (!done);
+}
+
 // cluster-scope release / acquire around the hand-written A blocks: the expanders of BOTH CTAs arrive on the leader's
 // barrier after their generic-proxy stores (made visible to the tensor core by fence.proxy.async), the leader's MMA
 // thread acquires at cluster scope before issuing MMAs that read both CTAs' shared memory
@@ -104,8 +116,9 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
    uint8_t *sB = base + 2 * A_BLK;
    uint64_t *bars = (uint64_t *)(sB + NST * ST_BYTES);
    uint64_t *fullA = bars, *emptyA = bars + 1, *fullB = bars + 2, *emptyB = bars + 2 + NST;
-   // accumulator hand-over per (buffer, 128-frame block): the epilogue of block 0 runs while the tensor core still
-   // works on block 1 of the same tile
+   // accumulators: "full" per buffer (one commit per tile -- a commit per block cost the MMA thread 0.2 ms per step),
+   // "empty" per (buffer, 128-frame block): every epilogue warp hands a block back as soon as its two chunks are in
+   // registers, before the log-sum-exp, so the tensor core refills it while the special-function unit works
    uint64_t *tmemFull = bars + 2 + 2 * NST, *tmemEmpty = tmemFull + 4;
    uint32_t *tmemSlot = (uint32_t *)(tmemEmpty + 4);
    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -120,7 +133,7 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
       // fullA: both CTAs' expanders (4 warps each) arrive on the LEADER's barrier; emptyA: one commit, multicast
       tc_mbar_init(fullA, 8); tc_mbar_init(emptyA, 1);
       for (int s = 0; s < NST; s++) { tc_mbar_init(&fullB[s], 1); tc_mbar_init(&emptyB[s], 1); }
-      for (int s = 0; s < 4; s++) { tc_mbar_init(&tmemFull[s], 1); tc_mbar_init(&tmemEmpty[s], 2 * EPW); }
+      for (int s = 0; s < 4; s++) { tc_mbar_init(&tmemFull[s], 1); tc_mbar_init(&tmemEmpty[s], 2 * EPW); }   // tmemFull: [0], [1] used
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    if (warp == 1) {
@@ -234,13 +247,13 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
                      const uint64_t dAhi = tc_smem_desc(aB + o), dBhi = tc_smem_desc(bSt + o);
                      if (elected) tc_mma_pair<true>(dAcc, dAhi, dBhi, idesc, 1u);
                   }
-                  if (elected) tc_commit_pair(&tmemFull[ai]);      // this block's accumulator: ready for both CTAs' epilogues
-                  __syncwarp();
                   phAcc ^= 1u << ai;
                }
                if (elected) tc_commit_pair(&emptyB[stage]);
                __syncwarp();
                if (++stage == NST) { stage = 0; phB ^= 1; }
+               if (elected) tc_commit_pair(&tmemFull[as]);         // accumulators ready for both CTAs' epilogues
+               __syncwarp();
                tile++;
             }
             if (elected) tc_commit_pair(emptyA);                 // A blocks reusable (arrives in both CTAs)
@@ -253,7 +266,7 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
       constexpr int CPW = 2;                            // 32-column chunks per warp (8 warps: two per quadrant)
       const int c0 = ((warp - 2) >> 2) * CPW;
       const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-      uint32_t tile = 0, phAcc = 0;
+      uint32_t tile = 0;
       for (int it = pair; it < p.nItems; it += nPairs) {
          const int2 item = p.items[it];
          const UttDesc u = p.utt[item.x];
@@ -267,12 +280,11 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
             if (!need) continue;
             const int f = iv.x, l = iv.y;
             const uint32_t as = tile & 1;
+            tc_mbar_wait(&tmemFull[as], (tile >> 1) & 1u);
+            tc_fence_after();
             for (int blk = 0; blk < 2; blk++) {
                if (!(need & (1 << blk))) continue;
                const uint32_t ai = as * 2 + blk;
-               tc_mbar_wait(&tmemFull[ai], (phAcc >> ai) & 1u);
-               tc_fence_after();
-               phAcc ^= 1u << ai;
                // hands the block's accumulator back (also when this warp had nothing to read from it)
                auto release = [&]() { tc_fence_before(); __syncwarp(); if (lane == 0) tc_mbar_arrive_leader(&tmemEmpty[ai]); };
                const int w0 = item.y + (2 * blk + (int)rank) * TC_BM + quad * 32;      // first frame of this warp
@@ -427,7 +439,7 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
       }
       for (int it = pair; it < p.nItems; it += nPairs) {
          const bool skipX = (p.dbg & 32) && it != pair;  // timing experiment: reuse the first item's A blocks
-         tc_mbar_wait(emptyA, phA ^ 1);
+         tc3_mbar_wait_relaxed(emptyA, phA ^ 1);
          phA ^= 1;
          if (!skipX) {
             store_row(x[0], 0);

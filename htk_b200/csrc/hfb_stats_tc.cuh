@@ -87,8 +87,10 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
    float *stage = (float *)sB2;                         // [128][N] flush staging: Lr is dead when a state is flushed
    int *pre = (int *)(sB2 + 4 * N * 128);               // [ST_CAP + 1] prefix sums of the positions' frame counts
    int *stt = pre + ST_CAP + 1;                         // [ST_CAP] tied state of each position
-   float *sOff = (float *)(stt + ST_CAP), *sScl = sOff + 64;   // per-dimension offset / scale of the operands
-   long long *pV = (long long *)(((uintptr_t)(sScl + 64) + 15) & ~(uintptr_t)15);   // per position: first entry of its frame list,
+   float2 *sXf = (float2 *)(((uintptr_t)(stt + ST_CAP) + 7) & ~(uintptr_t)7);   // per dimension: (scale, -offset * scale): x' = fma(x, s, c)
+   float *sScl = (float *)(sXf + 64);                   // (padding kept for the layout below)
+   int *segEnd = (int *)sScl;                           // [ST_CAP] end of the run of equal states that starts at a position
+   long long *pV = (long long *)(((uintptr_t)(segEnd + ST_CAP) + 15) & ~(uintptr_t)15);   // per position: first entry of its frame list,
    long long *pF = pV + ST_CAP, *pB = pF + ST_CAP;      // first frame of its utterance in the feature matrix / in the flag array
    uint64_t *bars = (uint64_t *)(pB + ST_CAP);
    uint64_t *barB = bars, *bar1 = bars + 1, *bar2 = bars + 2;
@@ -113,12 +115,17 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
       stt[k] = (it < i1) ? p.list[it].s : -1;
       if (it < i1) { pV[k] = p.list[it].vOff; pF[k] = p.list[it].featOff; pB[k] = p.list[it].frameBase; }
    }
-   if (tid < 64) { sOff[tid] = (tid < D) ? p.offset[tid] : 0.f; sScl[tid] = (tid < D) ? p.scale[tid] : 0.f; }
+   if (tid < 64) sXf[tid] = (tid < D) ? make_float2(p.scale[tid], -p.offset[tid] * p.scale[tid]) : make_float2(0.f, 0.f);
    for (uint32_t o = tid * 16; o < 65536; o += ST_THREADS * 16) *reinterpret_cast<uint4 *>(sA + o) = make_uint4(0u, 0u, 0u, 0u);
    tc_fence_before();
    __syncthreads();
    tc_fence_after();
    if (tid == 0) { pre[0] = 0; for (int k = 0; k < ST_CAP; k++) pre[k + 1] += pre[k]; }
+   if (tid == 32) {
+      const int np = i1 - i0;
+      int e = np;
+      for (int k = np - 1; k >= 0; k--) { if (k + 1 < np && stt[k + 1] != stt[k]) e = k + 1; segEnd[k] = e; }
+   }
    __syncthreads();
    const uint32_t tmem = *tmemSlot;
    const uint32_t tD1 = tmem, tD2 = tmem + N;
@@ -140,10 +147,8 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
       int na = c.have ? c.b : 0;
       for (;;) {
          if (na >= nPos) { c.have = false; return c; }
-         int nb = na + 1;
-         const int st = stt[na];
-         while (nb < nPos && stt[nb] == st) nb++;
-         if (pre[nb] > pre[na]) { c.a = na; c.b = nb; c.t0 = pre[na]; c.g1 = pre[nb]; c.s = st; c.have = true; return c; }
+         const int nb = segEnd[na];                     // first position of the slice with another state
+         if (pre[nb] > pre[na]) { c.a = na; c.b = nb; c.t0 = pre[na]; c.g1 = pre[nb]; c.s = stt[na]; c.have = true; return c; }
          na = nb;
       }
    };
@@ -199,7 +204,15 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
       if (worker) {
 #pragma unroll
          for (int d = 0; d < DP; d++)
-            if (d < D) x[d] = valid ? fminf(fmaxf((x[d] - sOff[d]) * sScl[d], -250.f), 250.f) : 0.f;
+            if (d < D) {
+               // rows of frames outside the FP16 range are zeroed (they are accumulated apart, see the epilogue); every
+               // other row is within TC_FAR of the centre by construction of the flags -- without flags (FP32 output
+               // probabilities were requested) the clamp keeps the operands finite
+               const float2 sc = sXf[d];
+               float xv = fmaf(x[d], sc.x, sc.y);
+               if (p.flag == nullptr) xv = fminf(fmaxf(xv, -250.f), 250.f);
+               x[d] = (valid && !far) ? xv : 0.f;
+            }
 #pragma unroll
          for (int un = 0; un < 16; un++) {
             if (un >= 2 * p.kSteps) break;
@@ -285,6 +298,22 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
                // low part of initx restores what its own rounding to float lost)
                const float xx = (Mn > 1) ? (x0 + v[m]) + x0l : x0 + x0l;
                if (-xx < minFf && (Mn > 1 || m == 0)) Lr = tc_ex2(xx * 1.4426950408889634f) * ST_LR_SCALE;   // :1606, :1612
+               if (far && Lr > 0.f) {
+                  // a frame outside the FP16 operand range: its row of the tile holds clamped values, so it is kept out of
+                  // the tensor-core sums (Lr = 0 below) and accumulated directly as the reference does (HFB.c:1665-1678, :1724-1736)
+                  const double L = (double)Lr / (double)ST_LR_SCALE;
+                  const int g = M.mixGauss[mo + m], mId = M.meanId[g], vId = M.varId[g];
+                  for (int k = 0; k < D; k++) {
+                     const double z = (double)frow[k] - (double)M.mean[(size_t)g * Dp + k];
+                     if (upM) atomicAdd(&W.acc[M.L.muSum + (size_t)mId * D + k], z * L);
+                     if (upV) atomicAdd(&W.acc[M.L.vaSum + (size_t)vId * D + k], z * z * L);
+                  }
+                  if (upM) atomicAdd(&W.acc[M.L.muOcc + mId], L);
+                  if (upV) atomicAdd(&W.acc[M.L.vaOcc + vId], L);
+                  if (upW) atomicAdd(&W.acc[M.L.wtC + mo + m], L);
+                  atomicAdd(&W.acc[M.L.wtOcc + s], L);
+                  Lr = 0.f;
+               }
             }
             const __half h = __float2half_rn(Lr), l = __float2half_rn(Lr - __half2float(h));
             const uint32_t off = offT + (uint32_t)(m * 128) + ((unit ^ (uint32_t)(m & 7)) << 4);
@@ -369,7 +398,7 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
 }
 
 template <int N>
-static inline size_t stats_tc_smem_bytes() { return 1024 + 65536 + 8 * N * 128 + sizeof(int) * (2 * ST_CAP + 1) + 512 + 16 + 3 * 8 * ST_CAP + 128; }
+static inline size_t stats_tc_smem_bytes() { return 1024 + 65536 + 8 * N * 128 + sizeof(int) * (3 * ST_CAP + 1) + 8 + 512 + 16 + 3 * 8 * ST_CAP + 128; }
 
 // Launch: returns false when the model is outside what the kernel covers (the caller keeps stats5_kernel).
 static inline bool stats_tc_supported(const GmmTc3Model &t, int D) { return t.ready && (t.MP == 8 || t.MP == 16 || t.MP == 32) && D <= 63; }
