@@ -61,18 +61,6 @@ __device__ __forceinline__ uint32_t tc3_unit_off(int r, int unit)       // unit 
    return (uint32_t)((unit >> 3) * 16384 + r * 128 + (((unit & 7) ^ (r & 7)) << 4));
 }
 
-// a wait that may sleep: the expander warps wait for most of an item's duration and must not take issue slots from the
-// epilogue warps that share their schedulers (the spin loops were 12 % of the kernel's instructions)
-__device__ __forceinline__ void tc3_mbar_wait_relaxed(uint64_t *bar, uint32_t parity)
-{
-   uint32_t done, addr = tc_smem_u32(bar);
-   do {
-      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-                   "selp.u32 %0, 1, 0, p;\n\t}"
-                   : "=r"(done) : "r"(addr), "r"(parity), "r"(2000u) : "memory");
-   } while (!done);
-}
-
 // cluster-scope release / acquire around the hand-written A blocks: the expanders of BOTH CTAs arrive on the leader's
 // barrier after their generic-proxy stores (made visible to the tensor core by fence.proxy.async), the leader's MMA
 // thread acquires at cluster scope before issuing MMAs that read both CTAs' shared memory
@@ -90,19 +78,6 @@ __device__ __forceinline__ void tc3_wait_acquire_cluster(uint64_t *bar, uint32_t
    } while (!done);
 }
 
-__device__ __forceinline__ void tc3_tmem_ld32_nowait(uint32_t taddr, float *v)
-{
-   uint32_t *r = reinterpret_cast<uint32_t *>(v);
-   asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-}
-
 template <int MP, int DP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
 gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, Tc3Params p)
@@ -116,11 +91,8 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
    uint8_t *sB = base + 2 * A_BLK;
    uint64_t *bars = (uint64_t *)(sB + NST * ST_BYTES);
    uint64_t *fullA = bars, *emptyA = bars + 1, *fullB = bars + 2, *emptyB = bars + 2 + NST;
-   // accumulators: "full" per buffer (one commit per tile -- a commit per block cost the MMA thread 0.2 ms per step),
-   // "empty" per (buffer, 128-frame block): every epilogue warp hands a block back as soon as its two chunks are in
-   // registers, before the log-sum-exp, so the tensor core refills it while the special-function unit works
-   uint64_t *tmemFull = bars + 2 + 2 * NST, *tmemEmpty = tmemFull + 4;
-   uint32_t *tmemSlot = (uint32_t *)(tmemEmpty + 4);
+   uint64_t *tmemFull = bars + 2 + 2 * NST, *tmemEmpty = tmemFull + 2;
+   uint32_t *tmemSlot = (uint32_t *)(tmemEmpty + 2);
    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const uint32_t rank = tc_cluster_ctarank();          // 0 = leader (issues the MMAs)
    const int pair = blockIdx.x >> 1, nPairs = gridDim.x >> 1;
@@ -133,7 +105,7 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
       // fullA: both CTAs' expanders (4 warps each) arrive on the LEADER's barrier; emptyA: one commit, multicast
       tc_mbar_init(fullA, 8); tc_mbar_init(emptyA, 1);
       for (int s = 0; s < NST; s++) { tc_mbar_init(&fullB[s], 1); tc_mbar_init(&emptyB[s], 1); }
-      for (int s = 0; s < 4; s++) { tc_mbar_init(&tmemFull[s], 1); tc_mbar_init(&tmemEmpty[s], 2 * EPW); }   // tmemFull: [0], [1] used
+      for (int s = 0; s < 2; s++) { tc_mbar_init(&tmemFull[s], 1); tc_mbar_init(&tmemEmpty[s], 2 * EPW); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    if (warp == 1) {
@@ -203,7 +175,7 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
          asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elected));
          const uint32_t idesc = tc_idesc(2 * TC_BM, TC_BN, 0u);
          const uint32_t aBase = tc_smem_u32(sA), bBase = tc_smem_u32(sB);
-         uint32_t stage = 0, phB = 0, phA = 0, tile = 0, phAcc = 0;    // phAcc: one phase bit per (buffer, block)
+         uint32_t stage = 0, phB = 0, phA = 0, tile = 0;
          for (int it = pair; it < p.nItems; it += nPairs) {
             const int2 item = p.items[it];
             const UttDesc u = p.utt[item.x];
@@ -218,16 +190,15 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
                if (n + 1 < nTiles) ivN = tiv[n + 1];
                const int need = tile_need(iv.x, iv.y, item.y, u.T);
                if (!need) continue;
-               const uint32_t as = tile & 1;
+               const uint32_t as = tile & 1, phT = (tile >> 1) & 1;
+               tc_mbar_wait(&tmemEmpty[as], phT ^ 1);
+               tc_fence_after();
                const uint32_t dMain = tmem + as * (2 * TC_BN);
                tc_mbar_wait(&fullB[stage], phB);
                tc_fence_after();
                const uint32_t bSt = bBase + stage * ST_BYTES;
                for (int b = 0; b < 2; b++) {
                   if (!(need & (1 << b))) continue;
-                  const uint32_t ai = as * 2 + b;
-                  tc_mbar_wait(&tmemEmpty[ai], ((phAcc >> ai) & 1u) ^ 1u);
-                  tc_fence_after();
                   const uint32_t aB = aBase + b * A_BLK, dAcc = dMain + b * TC_BN;
 #pragma unroll
                   for (int ks = 0; ks < 8; ks++) {
@@ -247,12 +218,11 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
                      const uint64_t dAhi = tc_smem_desc(aB + o), dBhi = tc_smem_desc(bSt + o);
                      if (elected) tc_mma_pair<true>(dAcc, dAhi, dBhi, idesc, 1u);
                   }
-                  phAcc ^= 1u << ai;
                }
                if (elected) tc_commit_pair(&emptyB[stage]);
                __syncwarp();
                if (++stage == NST) { stage = 0; phB ^= 1; }
-               if (elected) tc_commit_pair(&tmemFull[as]);         // accumulators ready for both CTAs' epilogues
+               if (elected) tc_commit_pair(&tmemFull[as]);
                __syncwarp();
                tile++;
             }
@@ -262,6 +232,11 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
       }
    } else if (warp < 2 + EPW) {
       // ================= epilogue (both CTAs): own frames x 128 components per block =================
+      // (Measured and dropped, round 2: accumulator hand-over per 128-frame block -- "full" and "empty" barriers per
+      // (buffer, block), so that block 0's epilogue overlaps block 1's MMAs -- and handing a block back as soon as its two
+      // chunks are in registers, before the log-sum-exp.  Both made the kernel SLOWER, 1.86 -> 2.03 / 2.00 ms on config #3,
+      // and the no-epilogue-math run went 1.41 -> 1.57: the second commit / second cluster-wide wait per tile costs the
+      // MMA-issuing thread more than the finer hand-over gains.)
       const int quad = warp & 3;                        // TMEM lane quadrant this warp may read
       constexpr int CPW = 2;                            // 32-column chunks per warp (8 warps: two per quadrant)
       const int c0 = ((warp - 2) >> 2) * CPW;
@@ -279,17 +254,13 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
             const int need = tile_need(iv.x, iv.y, item.y, u.T);
             if (!need) continue;
             const int f = iv.x, l = iv.y;
-            const uint32_t as = tile & 1;
-            tc_mbar_wait(&tmemFull[as], (tile >> 1) & 1u);
+            const uint32_t as = tile & 1, phT = (tile >> 1) & 1;
+            tc_mbar_wait(&tmemFull[as], phT);
             tc_fence_after();
             for (int blk = 0; blk < 2; blk++) {
-               if (!(need & (1 << blk))) continue;
-               const uint32_t ai = as * 2 + blk;
-               // hands the block's accumulator back (also when this warp had nothing to read from it)
-               auto release = [&]() { tc_fence_before(); __syncwarp(); if (lane == 0) tc_mbar_arrive_leader(&tmemEmpty[ai]); };
                const int w0 = item.y + (2 * blk + (int)rank) * TC_BM + quad * 32;      // first frame of this warp
                // nothing of this warp's 32 frames lies inside the tile's interval (or inside the utterance)
-               if (w0 >= u.T || f >= w0 + 32 || l < w0 || (p.dbg & 2)) { release(); continue; }
+               if (!(need & (1 << blk)) || w0 >= u.T || f >= w0 + 32 || l < w0 || (p.dbg & 2)) continue;
                const int t = w0 + lane;
                float *brow = p.b + u.bOff + (size_t)t * u.J;
                const uint32_t taddr = tmem + as * (2 * TC_BN) + blk * TC_BN + ((uint32_t)(quad * 32) << 16);
@@ -313,24 +284,17 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
                               *reinterpret_cast<float4 *>(brow + slot0 + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
                      }
                   }
-                  release();
                   continue;
                }
                float cmx = -INFINITY, csum = 0.f;       // carry for states wider than one 32-column chunk
                constexpr int NOUT = (MP <= 32) ? CPW * 32 / MP : 0;
                float outv[NOUT > 0 ? NOUT : 1];
                int no = 0;
-               // both chunks of this warp go to registers first and the accumulator is handed back BEFORE the log-sum-exp:
-               // the tensor core refills it while the special-function unit works through the 64 exponentials per lane
-               float vv[CPW][32];
-               tc3_tmem_ld32_nowait(taddr + c0 * 32, vv[0]);
-               tc3_tmem_ld32_nowait(taddr + (c0 + 1) * 32, vv[1]);
-               asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-               release();
 #pragma unroll
                for (int cc = 0; cc < CPW; cc++) {
                   const int c = c0 + cc;
-                  float (&v)[32] = vv[cc];
+                  float v[32];
+                  tc_tmem_ld32(taddr + c * 32, v);
                   constexpr int G = (MP < 32) ? MP : 32;   // columns of one state inside this chunk
 #pragma unroll
                   for (int s0 = 0; s0 < 32; s0 += G) {
@@ -369,6 +333,9 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
                      *reinterpret_cast<float2 *>(brow + slot0) = make_float2(outv[0], outv[NOUT > 1 ? 1 : 0]);
                }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive_leader(&tmemEmpty[as]);
             tile++;
          }
       }
@@ -439,7 +406,7 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
       }
       for (int it = pair; it < p.nItems; it += nPairs) {
          const bool skipX = (p.dbg & 32) && it != pair;  // timing experiment: reuse the first item's A blocks
-         tc3_mbar_wait_relaxed(emptyA, phA ^ 1);
+         tc_mbar_wait(emptyA, phA ^ 1);
          phA ^= 1;
          if (!skipX) {
             store_row(x[0], 0);

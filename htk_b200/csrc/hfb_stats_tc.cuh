@@ -270,50 +270,45 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
          st_tmem_ld<N>(tD1 + ((uint32_t)(warp * 32) << 16), v);
 #pragma unroll
          for (int m = 0; m < N; m++) v[m] -= p.C0;      // log weight + log N_m
-         if (valid && far && Mn > 1) {
-            // operands out of the FP16 range: the component log-likelihoods as IDOutP computes them (HModel.c:5420-5431)
-#pragma unroll
-            for (int m = 0; m < N; m++) {
-               float val = -1.0e30f;
-               if (m < Mn) {
-                  const float wt = M.mixLogWt[mo + m];
-                  if (wt > LMINMIX_F) {
-                     const int g = M.mixGauss[mo + m];
-                     const float *mu = M.mean + (size_t)g * Dp, *iv = M.ivar + (size_t)g * Dp;
-                     float acc = M.gconst[g];
-                     for (int k = 0; k < D; k++) { const float dd = frow[k] - mu[k]; acc = fmaf(dd * dd, iv[k], acc); }
-                     val = -0.5f * acc + wt;
-                  }
+         if (valid && far) {
+            // A frame outside the FP16 operand range: its row of the tile is zero and its Lr below is zero, i.e. the tensor
+            // core never sees it.  Its component log-likelihoods are evaluated as IDOutP does (HModel.c:5420-5431) and its
+            // contribution goes straight to the accumulators as in the reference (HFB.c:1581-1612, :1665-1678, :1724-1736).
+#pragma unroll 1
+            for (int m = 0; m < Mn; m++) {
+               const float wt = M.mixLogWt[mo + m];
+               if (Mn > 1 && !(wt > LMINMIX_F)) continue;
+               const int g = M.mixGauss[mo + m], mId = M.meanId[g], vId = M.varId[g];
+               const float *mu = M.mean + (size_t)g * Dp, *iv = M.ivar + (size_t)g * Dp;
+               float xx = x0 + x0l;                            // single-Gaussian state: x = log occupancy (:1575-1576)
+               if (Mn > 1) {
+                  float acc = M.gconst[g];
+                  for (int k = 0; k < D; k++) { const float dd = frow[k] - mu[k]; acc = fmaf(dd * dd, iv[k], acc); }
+                  xx = (x0 + (-0.5f * acc + wt)) + x0l;        // both ~1e6 with opposite signs on such a frame: exact
                }
-               v[m] = val;
+               if (!(-xx < minFf)) continue;                   // :1606
+               const double L = (double)expf(xx);
+               for (int k = 0; k < D; k++) {
+                  const double z = (double)frow[k] - (double)mu[k];
+                  if (upM) atomicAdd(&W.acc[M.L.muSum + (size_t)mId * D + k], z * L);
+                  if (upV) atomicAdd(&W.acc[M.L.vaSum + (size_t)vId * D + k], z * z * L);
+               }
+               if (upM) atomicAdd(&W.acc[M.L.muOcc + mId], L);
+               if (upV) atomicAdd(&W.acc[M.L.vaOcc + vId], L);
+               if (upW) atomicAdd(&W.acc[M.L.wtC + mo + m], L);
+               atomicAdd(&W.acc[M.L.wtOcc + s], L);
             }
          }
          const uint32_t offT = (uint32_t)((tid >> 6) * (N * 128) + (tid & 7) * 2), unit = (uint32_t)((tid & 63) >> 3);
 #pragma unroll
          for (int m = 0; m < N; m++) {
             float Lr = 0.f;
-            if (valid && m < Mn) {
+            if (valid && !far && m < Mn) {
                // x = initx + log weight + log N_m (:1581-1599); single-Gaussian states: x = log occupancy (:1575-1576)
                // (on an outlier frame initx and log N_m are both ~1e6 with opposite signs: their float sum is exact, the
                // low part of initx restores what its own rounding to float lost)
                const float xx = (Mn > 1) ? (x0 + v[m]) + x0l : x0 + x0l;
                if (-xx < minFf && (Mn > 1 || m == 0)) Lr = tc_ex2(xx * 1.4426950408889634f) * ST_LR_SCALE;   // :1606, :1612
-               if (far && Lr > 0.f) {
-                  // a frame outside the FP16 operand range: its row of the tile holds clamped values, so it is kept out of
-                  // the tensor-core sums (Lr = 0 below) and accumulated directly as the reference does (HFB.c:1665-1678, :1724-1736)
-                  const double L = (double)Lr / (double)ST_LR_SCALE;
-                  const int g = M.mixGauss[mo + m], mId = M.meanId[g], vId = M.varId[g];
-                  for (int k = 0; k < D; k++) {
-                     const double z = (double)frow[k] - (double)M.mean[(size_t)g * Dp + k];
-                     if (upM) atomicAdd(&W.acc[M.L.muSum + (size_t)mId * D + k], z * L);
-                     if (upV) atomicAdd(&W.acc[M.L.vaSum + (size_t)vId * D + k], z * z * L);
-                  }
-                  if (upM) atomicAdd(&W.acc[M.L.muOcc + mId], L);
-                  if (upV) atomicAdd(&W.acc[M.L.vaOcc + vId], L);
-                  if (upW) atomicAdd(&W.acc[M.L.wtC + mo + m], L);
-                  atomicAdd(&W.acc[M.L.wtOcc + s], L);
-                  Lr = 0.f;
-               }
             }
             const __half h = __float2half_rn(Lr), l = __float2half_rn(Lr - __half2float(h));
             const uint32_t off = offT + (uint32_t)(m * 128) + ((unit ^ (uint32_t)(m & 7)) << 4);

@@ -920,9 +920,9 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
             const unsigned grid = (nWarps + S4_WARPS - 1) / S4_WARPS;
             // the sums on tcgen05 (hfb_stats_tc.cuh); stats5_kernel then only runs for a wave whose frame lists overflowed
             const int *only = nullptr;
-            if (pre && c->useV3 && stats_tc_supported(c->tc3, Dd) && !getenv("HFBGPU_STATS5")) {
-               const bool v3ran = c->opt.gmmKernel != 1;
-               stats_tc_launch(c->tc3, c->dm, W, list, off + Jm, S.dValid.p, vcnt, v3ran ? S.tcw.dFlag3 : nullptr, overflow, w.totalP, st);
+            // (only behind gmm_tc3_kernel: its per-frame flags say which frames are outside the FP16 operand range)
+            if (pre && c->useV3 && c->opt.gmmKernel != 1 && stats_tc_supported(c->tc3, Dd) && !getenv("HFBGPU_STATS5")) {
+               stats_tc_launch(c->tc3, c->dm, W, list, off + Jm, S.dValid.p, vcnt, S.tcw.dFlag3, overflow, w.totalP, st);
                c->stats.launches++; c->stats.launchesStats++;
                only = overflow;
             }
