@@ -182,9 +182,11 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
    while (cur.have) {
       const int s = cur.s, mo = M.stateMixOff[s], Mn = M.stateMixOff[s + 1] - mo;
       const bool first = cur.t0 == pre[cur.a], last = cur.t0 + TC_BM >= cur.g1;
+      // single-Gaussian sets (MP = 1): Lr is the state occupancy itself, contraction (1) is not needed at all
+      const bool needV = p.MP > 1;
       if (first) {
          // ---- the state's Gaussians: rows TC3_ROW0 + s MP .. + N of the tensor-core B operand
-         if (warp == 4 && lane == 0) {
+         if (needV && warp == 4 && lane == 0) {
             tc_mbar_expect_tx(barB, 4 * N * 128);
             constexpr int BOXR = (N < 64) ? ((N == 16) ? 16 : 32) : 64;
             const int boxR = (p.MP < BOXR) ? p.MP : BOXR;            // rows per TMA box as the maps were built
@@ -245,7 +247,7 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
       __syncthreads();
       tc_fence_after();
       // ================= (1): V = A x B_state^T =================
-      if (warp == 4) {
+      if (warp == 4 && needV) {
          if (first) { tc_mbar_wait(barB, phB); phB ^= 1; tc_fence_after(); }
          if (lane == 0) {
             const uint32_t aB = tc_smem_u32(sA), bB = tc_smem_u32(sB1);
@@ -264,10 +266,16 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
       }
       // ================= epilogue of (1): Lr -> B operand of (2) =================
       if (worker) {
-         tc_mbar_wait(bar1, ph1);
-         tc_fence_after();
          float v[N];
-         st_tmem_ld<N>(tD1 + ((uint32_t)(warp * 32) << 16), v);
+         if (needV) {
+            tc_mbar_wait(bar1, ph1);
+            tc_fence_after();
+            st_tmem_ld<N>(tD1 + ((uint32_t)(warp * 32) << 16), v);
+            ph1 ^= 1;
+         } else {
+#pragma unroll
+            for (int m = 0; m < N; m++) v[m] = 0.f;
+         }
 #pragma unroll
          for (int m = 0; m < N; m++) v[m] -= p.C0;      // log weight + log N_m
          if (valid && far) {
@@ -315,7 +323,6 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
             *reinterpret_cast<__half *>(sB2 + off) = h;
             *reinterpret_cast<__half *>(sB2 + 2 * N * 128 + off) = l;
          }
-         ph1 ^= 1;
          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
       tc_fence_before();
@@ -396,7 +403,7 @@ template <int N>
 static inline size_t stats_tc_smem_bytes() { return 1024 + 65536 + 8 * N * 128 + sizeof(int) * (3 * ST_CAP + 1) + 8 + 512 + 16 + 3 * 8 * ST_CAP + 128; }
 
 // Launch: returns false when the model is outside what the kernel covers (the caller keeps stats5_kernel).
-static inline bool stats_tc_supported(const GmmTc3Model &t, int D) { return t.ready && (t.MP == 8 || t.MP == 16 || t.MP == 32) && D <= 63; }
+static inline bool stats_tc_supported(const GmmTc3Model &t, int D) { return t.ready && (t.MP == 1 || t.MP == 8 || t.MP == 16 || t.MP == 32) && D <= 63; }
 
 static inline void stats_tc_set_attributes()
 {

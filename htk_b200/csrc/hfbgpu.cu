@@ -882,7 +882,10 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
       if (w.totalP > 0 && c->opt.uFlags != 0) {
          const int Dd = c->dm.D;
          // mixture sets: occupancy-weighted sums on the tensor cores (mma.sync 3xTF32); else the FP32 kernel
-         if (c->hm.maxM >= 4 && Dd + 1 <= 40 && !W.feat2 && !getenv("HFBGPU_STATS3")) {
+         // (single-Gaussian sets: only with the tcgen05 kernel, where the sums are one contraction per tile)
+         const bool tcStats = c->useV3 && c->opt.gmmKernel != 1 && stats_tc_supported(c->tc3, Dd) && !getenv("HFBGPU_STATS5") &&
+                              !getenv("HFBGPU_NO_STATS_PRE");
+         if ((c->hm.maxM >= 4 || tcStats) && Dd + 1 <= 40 && !W.feat2 && !getenv("HFBGPU_STATS3")) {
             // positions bucketed by tied state (counting sort), then S5_CAP sorted positions per warp
             const int Jm = c->hm.J;
             const size_t nIdx = ((size_t)3 * (Jm + 2) + 3) & ~(size_t)3;
@@ -921,7 +924,7 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
             // the sums on tcgen05 (hfb_stats_tc.cuh); stats5_kernel then only runs for a wave whose frame lists overflowed
             const int *only = nullptr;
             // (only behind gmm_tc3_kernel: its per-frame flags say which frames are outside the FP16 operand range)
-            if (pre && c->useV3 && c->opt.gmmKernel != 1 && stats_tc_supported(c->tc3, Dd) && !getenv("HFBGPU_STATS5")) {
+            if (pre && tcStats) {
                stats_tc_launch(c->tc3, c->dm, W, list, off + Jm, S.dValid.p, vcnt, S.tcw.dFlag3, overflow, w.totalP, st);
                c->stats.launches++; c->stats.launchesStats++;
                only = overflow;
