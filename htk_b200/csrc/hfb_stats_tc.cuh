@@ -156,7 +156,6 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
    float px0 = 0.f, px0l = 0.f;                         // initx / log occupancy as hi + lo floats (it can be ~1e6 on outlier frames)
    bool pvalid = false, pfar = false;
    const float *pfrow = nullptr;
-   int ppos = 0, pt = 0;                                // position (in my slice) and frame of my row: far rows look b up again
    auto fetch = [&](const TileAt &c) {
       pvalid = false; pfar = false; pfrow = nullptr; px0 = 0.f; px0l = 0.f;
       if (!worker || !c.have) return;
@@ -170,7 +169,6 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
          const ValidFrame vf = p.vbuf[pV[lo] + (g - pre[lo])];
          px0 = (float)vf.x0; px0l = (float)(vf.x0 - (double)px0);
          pfrow = W.feat + ((size_t)pF[lo] + vf.t) * D;
-         ppos = lo; pt = vf.t;
          pfar = p.flag != nullptr && p.flag[pB[lo] + vf.t] != 0;
 #pragma unroll
          for (int d = 0; d < DP; d++)
@@ -205,7 +203,6 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
       const bool valid = pvalid, far = pfar;
       const float x0 = px0, x0l = px0l;
       const float *frow = pfrow;
-      const int rpos = ppos, rt = pt;
       if (worker) {
 #pragma unroll
          for (int d = 0; d < DP; d++)
@@ -283,40 +280,23 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
          for (int m = 0; m < N; m++) v[m] -= p.C0;      // log weight + log N_m
          if (valid && far) {
             // A frame outside the FP16 operand range: its row of the tile is zero and its Lr below is zero, i.e. the tensor
-            // core never sees it.  Its component log-likelihoods are evaluated as IDOutP does (HModel.c:5420-5431), the
-            // posteriors are normalised with THEIR OWN log-sum (at |log N| ~ 1e6 one float ulp is 0.5: nothing may depend on
-            // two evaluations agreeing bit for bit), and the contribution goes straight to the accumulators as in the
-            // reference (HFB.c:1581-1612, :1665-1678, :1724-1736).
-            const PosRec &R = p.list[i0 + rpos];
-            const double bjt = (double)W.b[R.bOff + (size_t)rt * R.J + R.ps[R.j]];
-            const double lg = (Mn > 1) ? ((double)x0 + (double)x0l) + bjt : (double)x0 + (double)x0l;   // log occupancy of the state
-            double lse = 0.0;
-            if (Mn > 1) {
-               double mx = -1.0e300, sm = 0.0;
-#pragma unroll 1
-               for (int m = 0; m < Mn; m++) {
-                  const float wt = M.mixLogWt[mo + m];
-                  if (!(wt > LMINMIX_F)) continue;
-                  const int g = M.mixGauss[mo + m];
-                  const float *mu = M.mean + (size_t)g * Dp, *iv = M.ivar + (size_t)g * Dp;
-                  float acc = M.gconst[g];
-                  for (int k = 0; k < D; k++) { const float dd = frow[k] - mu[k]; acc = fmaf(dd * dd, iv[k], acc); }
-                  const double val = (double)(-0.5f * acc + wt);
-                  if (val > mx) { sm = sm * exp(mx - val) + 1.0; mx = val; } else sm += exp(val - mx);
-               }
-               lse = mx + log(sm);
-            }
+            // core never sees it.  It goes straight to the accumulators the way the reference forms them: x = initx + log
+            // weight + log N_m summed in DOUBLE from the float log N_m of IDOutP (HFB.c:1581-1599, HModel.c:5420-5431).  On
+            // such a frame |log N_m| ~ 1e6, where the float log-sum b_j(o_t) that went into alpha is a fraction of an ulp
+            // (0.5) off the exact log-sum of the components: the reference's component occupancies then do not add up to
+            // the state occupancy, and neither may ours (parity is with the reference, not with the arithmetic identity).
+            const double xi = (double)x0 + (double)x0l;        // initx (log occupancy for a single-Gaussian state)
 #pragma unroll 1
             for (int m = 0; m < Mn; m++) {
                const float wt = M.mixLogWt[mo + m];
-               if (Mn > 1 && !(wt > LMINMIX_F)) continue;
+               if (Mn > 1 && !(wt > LMINMIX_F)) continue;      // :1573
                const int g = M.mixGauss[mo + m], mId = M.meanId[g], vId = M.varId[g];
                const float *mu = M.mean + (size_t)g * Dp, *iv = M.ivar + (size_t)g * Dp;
-               double xx = lg;                                 // single-Gaussian state: x = log occupancy (:1575-1576)
+               double xx = xi;                                 // :1575-1576
                if (Mn > 1) {
                   float acc = M.gconst[g];
                   for (int k = 0; k < D; k++) { const float dd = frow[k] - mu[k]; acc = fmaf(dd * dd, iv[k], acc); }
-                  xx = lg + ((double)(-0.5f * acc + wt) - lse);
+                  xx = (xi + (double)wt) + (double)(-0.5f * acc);
                }
                if (!(-xx < minF)) continue;                    // :1606
                const double L = exp(xx);
