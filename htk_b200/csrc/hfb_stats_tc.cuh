@@ -156,17 +156,30 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
    float px0 = 0.f, px0l = 0.f;                         // initx / log occupancy as hi + lo floats (it can be ~1e6 on outlier frames)
    bool pvalid = false, pfar = false;
    const float *pfrow = nullptr;
-   auto fetch = [&](const TileAt &c) {
-      pvalid = false; pfar = false; pfrow = nullptr; px0 = 0.f; px0l = 0.f;
+   // two steps, so that neither of the two dependent global loads (frame record, then feature row) is waited for:
+   // fetch_index issues the record load BEFORE the current tile's rows are converted and stored, fetch_row uses it after
+   ValidFrame nvf; nvf.x0 = 0.0; nvf.t = 0; nvf.pad = 0;
+   int nlo = 0;
+   bool nvalid = false;
+   auto fetch_index = [&](const TileAt &c) {
+      nvalid = false;
       if (!worker || !c.have) return;
       const int g = c.t0 + tid;
-      pvalid = g < c.g1;
+      nvalid = g < c.g1;
+      if (nvalid) {
+         int lo = c.a, hi = c.b;                        // position with pre[it] <= g < pre[it + 1]
+         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= g) lo = mid; else hi = mid; }
+         nvf = p.vbuf[pV[lo] + (g - pre[lo])];
+         nlo = lo;
+      }
+   };
+   auto fetch_row = [&]() {
+      pvalid = nvalid; pfar = false; pfrow = nullptr; px0 = 0.f; px0l = 0.f;
 #pragma unroll
       for (int d = 0; d < DP; d++) x[d] = 0.f;
       if (pvalid) {
-         int lo = c.a, hi = c.b;                        // position with pre[it] <= g < pre[it + 1]
-         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= g) lo = mid; else hi = mid; }
-         const ValidFrame vf = p.vbuf[pV[lo] + (g - pre[lo])];
+         const ValidFrame vf = nvf;
+         const int lo = nlo;
          px0 = (float)vf.x0; px0l = (float)(vf.x0 - (double)px0);
          pfrow = W.feat + ((size_t)pF[lo] + vf.t) * D;
          pfar = p.flag != nullptr && p.flag[pB[lo] + vf.t] != 0;
@@ -177,7 +190,8 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
    };
    TileAt cur; cur.a = cur.b = cur.t0 = cur.g1 = 0; cur.s = -1; cur.have = false;
    cur = next_tile(cur);
-   fetch(cur);
+   fetch_index(cur);
+   fetch_row();
    const float minFf = (float)minF;
    while (cur.have) {
       const int s = cur.s, mo = M.stateMixOff[s], Mn = M.stateMixOff[s + 1] - mo;
@@ -203,6 +217,8 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
       const bool valid = pvalid, far = pfar;
       const float x0 = px0, x0l = px0l;
       const float *frow = pfrow;
+      const TileAt nxt = next_tile(cur);
+      fetch_index(nxt);                                 // frame records of the next tile: in flight during phase A
       if (worker) {
 #pragma unroll
          for (int d = 0; d < DP; d++)
@@ -241,8 +257,7 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
          }
          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
-      const TileAt nxt = next_tile(cur);
-      fetch(nxt);                                       // in flight during (1), its epilogue and (2)
+      fetch_row();                                      // feature rows of the next tile: in flight during (1), its epilogue and (2)
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
