@@ -342,7 +342,7 @@ def herest_gpu_tool(fm, cfg, prune, n_files=1024, gpu_index=0):
             return {"error": pb.stdout[-400:]}
         import re
         m = re.search(r"(\d+) utterances through the fast loader, (\d+) through HParm", pb.stdout)
-        rate = (n_files - n_small) * T / max(tb - ta, 1e-6)
+        rate = (n_files - n_small) * T / (tb - ta) if tb - ta > 0.2 else None      # start-up noise exceeds the loop at this size
         prof = re.search(r"hfbgpu: host profile \(s\): (.*)", pb.stdout)
         loop_rate = None
         if prof:
@@ -350,11 +350,12 @@ def herest_gpu_tool(fm, cfg, prune, n_files=1024, gpu_index=0):
             if m2:
                 loop_rate = n_files * T / max(sum(float(x) for x in m2.groups()), 1e-6)
         return {"host_profile_s": prof.group(1) if prof else None, "file_loop_frames_per_s": loop_rate,
-                "note": "value = marginal end-to-end rate of the whole tool, which at this corpus size is dominated by HTK's own MLF "
-                        "pre-scan (HLabel.c LoadMasterFile, ~12 us per label line, paid before the first utterance); "
-                        "file_loop_frames_per_s = frames / (file loop + final flush + accumulator download and scatter), i.e. "
-                        "what HERest's loop + the bridge + the library sustain once the MLF is indexed",
-                "value": rate, "unit": "frames/s", "files": n_files, "frames": n_files * T, "wall_s": tb, "startup_s": ta,
+                "note": "value = file_loop_frames_per_s = frames / (file loop + final flush + accumulator download and scatter), i.e. "
+                        "what HERest's own loop (LoadLabs) + the bridge + the library sustain once the MLF is indexed and the CUDA "
+                        "context is up; marginal_frames_per_s = (frames of the long run - frames of the short run) / difference of "
+                        "the two wall times, which at this corpus size is dominated by HTK's own start-up (MLF pre-scan, HLabel.c "
+                        "LoadMasterFile) and is null when start-up noise exceeds the loop time",
+                "marginal_frames_per_s": rate, "value": loop_rate if loop_rate else rate, "unit": "frames/s", "files": n_files, "frames": n_files * T, "wall_s": tb, "startup_s": ta,
                 "gpu_utilization_mean_pct": busy, "fast_loader_files": int(m.group(1)) if m else None,
                 "how": "`HERest_gpu -T 1 -u tmvw -p 1` (reference HERest + bridge + libhfbgpu) over %d feature files of %d "
                        "frames on local disk, one process, one GPU; marginal rate between %d and %d files so that MMF "

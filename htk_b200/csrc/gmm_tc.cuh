@@ -69,6 +69,8 @@ struct GmmTcWork {             // per-stream expanded feature operand (floats: T
    unsigned char *dFlag = nullptr;   // [frames] 1 = this frame's row of b is recomputed in FP32 (gmm_fixup_kernel)
    unsigned char *dFlag3 = nullptr;  // the same for gmm_tc3_kernel (which needs no expanded operand)
    size_t flagCap = 0;
+   float *dPad = nullptr;            // gmm_tc3_pad_kernel: scaled features with padded rows (single-Gaussian sets)
+   size_t padCap = 0;
    size_t aCapFrames = 0;
    bool f16Init = false;       // constant / padding columns of the FP16 layout are in place
    void release()
@@ -77,7 +79,8 @@ struct GmmTcWork {             // per-stream expanded feature operand (floats: T
       if (dAlo) cudaFree(dAlo);
       if (dFlag) cudaFree(dFlag);
       if (dFlag3) cudaFree(dFlag3);
-      dAhi = dAlo = nullptr; dFlag = dFlag3 = nullptr; aCapFrames = 0; flagCap = 0; f16Init = false;
+      if (dPad) cudaFree(dPad);
+      dAhi = dAlo = nullptr; dFlag = dFlag3 = nullptr; dPad = nullptr; aCapFrames = 0; flagCap = 0; padCap = 0; f16Init = false;
    }
 };
 #define TC_KH 128           // expanded K of the FP16 operands: 2 swizzle atoms of 64 halfs

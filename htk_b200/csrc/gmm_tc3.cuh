@@ -44,6 +44,7 @@ struct Tc3Params {
    const int *slotState;
    const int2 *tileIv;         // per tile: (first, last) frame in which one of its states can be needed
    const float *feat;          // raw features of the wave [frames][D]
+   const float *featPad;       // or (single-Gaussian sets): scaled features [frames][DP], 16-byte aligned rows, see gmm_tc3_pad_kernel
    const float *offset, *scale;
    float *b;
    unsigned char *flag;
@@ -357,6 +358,18 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
          const int t = item.y + (2 * b + (int)rank) * TC_BM + r;
          const bool inside = t < u.T;
          bool far = false;
+         if (p.featPad != nullptr) {
+            // pre-scaled rows of DP floats: ten 16-byte loads per row instead of 39 scalar ones (with one tile per item --
+            // single-Gaussian sets -- the row loads are NOT hidden behind the previous item's MMAs and were what the
+            // kernel waited for: 32 cache lines per load instruction)
+            const float4 *s4 = reinterpret_cast<const float4 *>(p.featPad + ((size_t)u.featOff + (inside ? t : 0)) * DP);
+#pragma unroll
+            for (int i = 0; i < DP / 4; i++) {
+               const float4 q = inside ? s4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+               xr[4 * i] = q.x; xr[4 * i + 1] = q.y; xr[4 * i + 2] = q.z; xr[4 * i + 3] = q.w;
+            }
+            return;
+         }
          const float *src = p.feat + ((size_t)u.featOff + (inside ? t : 0)) * D;
 #pragma unroll
          for (int d = 0; d < DP; d++) {
@@ -431,6 +444,29 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
       tc_fence_after();
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
    }
+}
+
+// Scaled, clamped copy of the wave's features with rows padded to DP floats (16-byte aligned) + the per-frame flags;
+// only for sets with one K1 tile per work item (single-Gaussian sets), see load_row above.
+__global__ void __launch_bounds__(256)
+gmm_tc3_pad_kernel(const float *__restrict__ feat, const float *__restrict__ offset, const float *__restrict__ scale,
+                   int D, int DPad, long long nFrames, float *__restrict__ out, unsigned char *__restrict__ flag)
+{
+   const int lane = threadIdx.x & 31;
+   const long long f = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);     // one warp per frame
+   if (f >= nFrames) return;
+   bool far = false;
+   for (int d = lane; d < DPad; d += 32) {
+      float v = 0.f;
+      if (d < D) {
+         v = (feat[f * D + d] - offset[d]) * scale[d];
+         if (!(fabsf(v) <= TC_FAR)) far = true;
+         v = fminf(fmaxf(v, -250.f), 250.f);
+      }
+      out[f * DPad + d] = v;
+   }
+   far = __any_sync(0xffffffffu, far);
+   if (lane == 0) flag[f] = far ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -568,7 +604,21 @@ static inline int gmm_tc3_launch(GmmTc3Model &t, GmmTcWork &wk, const DevModel &
    Tc3Params p;
    p.items = dItems4; p.nItems = nItems4; p.utt = W.utt; p.slotState = W.slotState;
    p.tileIv = W.tileIv;
-   p.feat = W.feat; p.offset = t.dOffset; p.scale = t.dScale; p.b = W.b; p.flag = wk.dFlag3;
+   p.feat = W.feat; p.featPad = nullptr; p.offset = t.dOffset; p.scale = t.dScale; p.b = W.b; p.flag = wk.dFlag3;
+   int nl = 0;
+   if (t.MP == 1 && !getenv("HFBGPU_NO_PAD")) {
+      const int DPad = (dm.D <= 40) ? 40 : 64;
+      const size_t needPad = ((size_t)waveFrames + TC_BM) * DPad;
+      if (needPad > wk.padCap) {
+         if (wk.dPad) cudaFree(wk.dPad);
+         wk.dPad = nullptr; wk.padCap = 0;
+         if (cudaMalloc(&wk.dPad, (needPad + needPad / 8) * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return HFB_ENOMEM; }
+         wk.padCap = needPad + needPad / 8;
+      }
+      gmm_tc3_pad_kernel<<<(unsigned)((waveFrames + 7) / 8), 256, 0, st>>>(W.feat, t.dOffset, t.dScale, dm.D, DPad, waveFrames, wk.dPad, wk.dFlag3);
+      p.featPad = wk.dPad;
+      nl++;
+   }
    p.C0 = t.C0; p.D = dm.D; p.kSteps = (2 * dm.D + 2 + 15) / 16; p.deadBelow = TC_DEAD_BELOW;
    { const char *e = getenv("HFBGPU_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
    const int grid2 = 2 * std::min(nItems4, smCount / 2);
@@ -583,7 +633,7 @@ static inline int gmm_tc3_launch(GmmTc3Model &t, GmmTcWork &wk, const DevModel &
    default: TC3_GO(128); break;
    }
 #undef TC3_GO
-   int nl = 1;
+   nl += 1;
    if (!getenv("HFBGPU_NO_FIXUP")) { gmm_fixup_kernel<<<nItems128, 128, 0, st>>>(dm, W, dItems128, wk.dFlag3); nl++; }
    if (launches) *launches = nl;
    return HFB_OK;
