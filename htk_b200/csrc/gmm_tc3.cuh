@@ -606,7 +606,9 @@ static inline int gmm_tc3_launch(GmmTc3Model &t, GmmTcWork &wk, const DevModel &
    p.tileIv = W.tileIv;
    p.feat = W.feat; p.featPad = nullptr; p.offset = t.dOffset; p.scale = t.dScale; p.b = W.b; p.flag = wk.dFlag3;
    int nl = 0;
-   if (t.MP == 1 && !getenv("HFBGPU_NO_PAD")) {
+   // (experiment, off: measured on config #2 the pre-pass costs what the wider loads save -- 0.47 against 0.42 ms;
+   // what that kernel waits for with one tile per item is the load / store queue, `lg_throttle` in profiles/r2_gmm_tc3_cfg2_raw.txt)
+   if (t.MP == 1 && getenv("HFBGPU_PAD")) {
       const int DPad = (dm.D <= 40) ? 40 : 64;
       const size_t needPad = ((size_t)waveFrames + TC_BM) * DPad;
       if (needPad > wk.padCap) {
