@@ -55,19 +55,24 @@ static int pm_add(PMap *m, const void *p)          /* returns index, new or exis
 }
 
 /* ------------------------------------------------------------------ state */
-static struct {
-   HMMSet *hset;
-   hfbgpu_ctx *ctx;
+/* One HMM set flattened for the library, with the HTK objects behind every flat index */
+typedef struct {
    hfb_model m;
+   HLink *hmm; StreamElem **ste; MixPDF **mp; SVector *meanV, *varV; SMatrix *trans;
+   PMap pmHmm, pmSte, pmMp, pmMean, pmVar, pmTr;
+   int nHmm, nSte, nMp, nMean, nVar, nTr;
+} FlatSet;
+
+static struct {
+   HMMSet *hset;                         /* the set whose accumulators are filled (up_hset) */
+   HMMSet *alHset;                       /* 2-model re-estimation: the set that aligns (fbInfo->al_hset), else NULL */
+   hfbgpu_ctx *ctx;
+   FlatSet u, a;                         /* update set; alignment set (2-model re-estimation only) */
    hfb_acc_layout L;
    int D, batchUtts;
    long batchFrames;
    UPDSet uFlags;
-   /* HTK objects in flat order */
-   HLink *hmm; StreamElem **ste; MixPDF **mp; SVector *meanV, *varV; SMatrix *trans;
-   PMap pmHmm, pmSte, pmMp, pmMean, pmVar, pmTr;
-   PMap pmLab; int *labPhys; int labCap;   /* label id (LabId) -> physical HMM index, filled on first use */
-   int nHmm, nSte, nMp, nMean, nVar, nTr;
+   PMap pmLab; int *labPhys, *labPhysAl; int labCap;   /* label id (LabId) -> physical HMM index in each set, filled on first use */
    /* totals */
    long nOk, nSkipped;
    int twoData;                          /* HERest -r */
@@ -95,7 +100,7 @@ static double now_s(void)
 typedef struct {
    float *feat; long featCap, nFrames;
    float *feat2; long feat2Cap;          /* single-pass retraining (-r): the second parameterisation, HFB.c:445 */
-   int64_t *frameOff; int32_t *labOff, *lab; int nUtt, labCap, nLab;
+   int64_t *frameOff; int32_t *labOff, *lab, *labAl; int nUtt, labCap, nLab;
    char **names;
    hfb_utt_result *res;
    int inflight;
@@ -209,7 +214,7 @@ static void reader_stop(void)
 }
 
 /* ------------------------------------------------------------------ flatten the HMMSet */
-static void Flatten(HMMSet *hset)
+static void Flatten(HMMSet *hset, FlatSet *F)
 {
    HMMScanState hss;
    int p, j, m, k, D = hset->vecSize, sumM = 0, sumE = 0, sumNN = 0;
@@ -219,28 +224,27 @@ static void Flatten(HMMSet *hset)
    if (hset->swidth[0] != 1) HError(7399, "hfbgpu bridge: only single-stream sets are accelerated");
    if (hset->hsKind != PLAINHS && hset->hsKind != SHAREDHS)
       HError(7399, "hfbgpu bridge: only PLAINHS/SHAREDHS sets are accelerated");
-   pm_init(&B.pmHmm, hset->numPhyHMM); pm_init(&B.pmSte, hset->numStates + 16);
-   pm_init(&B.pmMp, hset->numMix + 16); pm_init(&B.pmMean, hset->numMix + 16);
-   pm_init(&B.pmVar, hset->numMix + 16); pm_init(&B.pmTr, hset->numPhyHMM);
-   pm_init(&B.pmLab, hset->numLogHMM + 1024);
-   B.hmm = (HLink *)calloc(hset->numPhyHMM + 1, sizeof(HLink));
+   pm_init(&F->pmHmm, hset->numPhyHMM); pm_init(&F->pmSte, hset->numStates + 16);
+   pm_init(&F->pmMp, hset->numMix + 16); pm_init(&F->pmMean, hset->numMix + 16);
+   pm_init(&F->pmVar, hset->numMix + 16); pm_init(&F->pmTr, hset->numPhyHMM);
+   F->hmm = (HLink *)calloc(hset->numPhyHMM + 1, sizeof(HLink));
 
    /* pass 1: number physical HMMs (HMMScan order = dump order), states, pdfs, vectors, matrices */
    NewHMMScan(hset, &hss);
    do {
       HLink hmm = hss.hmm;
-      p = pm_add(&B.pmHmm, hmm); B.hmm[p] = hmm;
-      pm_add(&B.pmTr, hmm->transP);
+      p = pm_add(&F->pmHmm, hmm); F->hmm[p] = hmm;
+      pm_add(&F->pmTr, hmm->transP);
       for (j = 2; j < hmm->numStates; j++) {
          StreamElem *ste = hmm->svec[j].info->pdf + 1;
          int M = ste->nMix < 0 ? -ste->nMix : ste->nMix;
-         if (pm_get(&B.pmSte, ste) < 0) {
-            pm_add(&B.pmSte, ste);
+         if (pm_get(&F->pmSte, ste) < 0) {
+            pm_add(&F->pmSte, ste);
             for (m = 1; m <= M; m++) {
                MixPDF *mp = ste->spdf.cpdf[m].mpdf;
                if (mp->ckind != INVDIAGC && mp->ckind != DIAGC)
                   HError(7399, "hfbgpu bridge: only diagonal covariances are accelerated");
-               pm_add(&B.pmMp, mp); pm_add(&B.pmMean, mp->mean); pm_add(&B.pmVar, mp->cov.var);
+               pm_add(&F->pmMp, mp); pm_add(&F->pmMean, mp->mean); pm_add(&F->pmVar, mp->cov.var);
             }
             sumM += M;
          }
@@ -248,47 +252,47 @@ static void Flatten(HMMSet *hset)
       }
    } while (GoNextHMM(&hss));
    EndHMMScan(&hss);
-   B.nHmm = B.pmHmm.n; B.nSte = B.pmSte.n; B.nMp = B.pmMp.n; B.nMean = B.pmMean.n; B.nVar = B.pmVar.n; B.nTr = B.pmTr.n;
+   F->nHmm = F->pmHmm.n; F->nSte = F->pmSte.n; F->nMp = F->pmMp.n; F->nMean = F->pmMean.n; F->nVar = F->pmVar.n; F->nTr = F->pmTr.n;
 
-   B.ste = (StreamElem **)calloc(B.nSte + 1, sizeof(void *)); B.mp = (MixPDF **)calloc(B.nMp + 1, sizeof(void *));
-   B.meanV = (SVector *)calloc(B.nMean + 1, sizeof(SVector)); B.varV = (SVector *)calloc(B.nVar + 1, sizeof(SVector));
-   B.trans = (SMatrix *)calloc(B.nTr + 1, sizeof(SMatrix));
-   stateMixOff = (int32_t *)calloc(B.nSte + 1, sizeof(int32_t));
+   F->ste = (StreamElem **)calloc(F->nSte + 1, sizeof(void *)); F->mp = (MixPDF **)calloc(F->nMp + 1, sizeof(void *));
+   F->meanV = (SVector *)calloc(F->nMean + 1, sizeof(SVector)); F->varV = (SVector *)calloc(F->nVar + 1, sizeof(SVector));
+   F->trans = (SMatrix *)calloc(F->nTr + 1, sizeof(SMatrix));
+   stateMixOff = (int32_t *)calloc(F->nSte + 1, sizeof(int32_t));
    mixGauss = (int32_t *)calloc(sumM + 1, sizeof(int32_t)); mixLogWt = (float *)calloc(sumM + 1, sizeof(float));
-   mean = (float *)calloc((size_t)B.nMp * D + 1, sizeof(float)); ivar = (float *)calloc((size_t)B.nMp * D + 1, sizeof(float));
-   gConst = (float *)calloc(B.nMp + 1, sizeof(float));
-   meanId = (int32_t *)calloc(B.nMp + 1, sizeof(int32_t)); varId = (int32_t *)calloc(B.nMp + 1, sizeof(int32_t));
-   hmmN = (int32_t *)calloc(B.nHmm + 1, sizeof(int32_t)); hmmStateOff = (int32_t *)calloc(B.nHmm + 2, sizeof(int32_t));
-   hmmState = (int32_t *)calloc(sumE + 1, sizeof(int32_t)); hmmTrans = (int32_t *)calloc(B.nHmm + 1, sizeof(int32_t));
-   transN = (int32_t *)calloc(B.nTr + 1, sizeof(int32_t)); transOff = (int32_t *)calloc(B.nTr + 2, sizeof(int32_t));
+   mean = (float *)calloc((size_t)F->nMp * D + 1, sizeof(float)); ivar = (float *)calloc((size_t)F->nMp * D + 1, sizeof(float));
+   gConst = (float *)calloc(F->nMp + 1, sizeof(float));
+   meanId = (int32_t *)calloc(F->nMp + 1, sizeof(int32_t)); varId = (int32_t *)calloc(F->nMp + 1, sizeof(int32_t));
+   hmmN = (int32_t *)calloc(F->nHmm + 1, sizeof(int32_t)); hmmStateOff = (int32_t *)calloc(F->nHmm + 2, sizeof(int32_t));
+   hmmState = (int32_t *)calloc(sumE + 1, sizeof(int32_t)); hmmTrans = (int32_t *)calloc(F->nHmm + 1, sizeof(int32_t));
+   transN = (int32_t *)calloc(F->nTr + 1, sizeof(int32_t)); transOff = (int32_t *)calloc(F->nTr + 2, sizeof(int32_t));
 
    /* pass 2: fill (state / pdf numbering follows first-use order of pass 1, so offsets are
       assigned by walking the states in index order) */
    {
-      int *mOfState = (int *)calloc(B.nSte + 1, sizeof(int));
-      for (p = 0; p < B.nHmm; p++) {
-         HLink hmm = B.hmm[p];
+      int *mOfState = (int *)calloc(F->nSte + 1, sizeof(int));
+      for (p = 0; p < F->nHmm; p++) {
+         HLink hmm = F->hmm[p];
          for (j = 2; j < hmm->numStates; j++) {
             StreamElem *ste = hmm->svec[j].info->pdf + 1;
-            int s = pm_get(&B.pmSte, ste);
-            B.ste[s] = ste; mOfState[s] = ste->nMix < 0 ? -ste->nMix : ste->nMix;
+            int s = pm_get(&F->pmSte, ste);
+            F->ste[s] = ste; mOfState[s] = ste->nMix < 0 ? -ste->nMix : ste->nMix;
          }
       }
-      for (j = 0; j < B.nSte; j++) stateMixOff[j + 1] = stateMixOff[j] + mOfState[j];
+      for (j = 0; j < F->nSte; j++) stateMixOff[j + 1] = stateMixOff[j] + mOfState[j];
       free(mOfState);
    }
-   for (j = 0; j < B.nSte; j++) {
-      StreamElem *ste = B.ste[j];
+   for (j = 0; j < F->nSte; j++) {
+      StreamElem *ste = F->ste[j];
       int M = stateMixOff[j + 1] - stateMixOff[j];
       for (m = 1; m <= M; m++) {
          MixPDF *mp = ste->spdf.cpdf[m].mpdf;
-         int g = pm_get(&B.pmMp, mp), o = stateMixOff[j] + m - 1;
+         int g = pm_get(&F->pmMp, mp), o = stateMixOff[j] + m - 1;
          mixGauss[o] = g;
          mixLogWt[o] = MixLogWeight(hset, ste->spdf.cpdf[m].weight);     /* log weight (ConvLogWt done) */
-         if (!B.mp[g]) {
-            B.mp[g] = mp;
-            meanId[g] = pm_get(&B.pmMean, mp->mean); varId[g] = pm_get(&B.pmVar, mp->cov.var);
-            B.meanV[meanId[g]] = mp->mean; B.varV[varId[g]] = mp->cov.var;
+         if (!F->mp[g]) {
+            F->mp[g] = mp;
+            meanId[g] = pm_get(&F->pmMean, mp->mean); varId[g] = pm_get(&F->pmVar, mp->cov.var);
+            F->meanV[meanId[g]] = mp->mean; F->varV[varId[g]] = mp->cov.var;
             gConst[g] = mp->gConst;                                      /* as stored, never recomputed */
             for (k = 1; k <= D; k++) {
                mean[(size_t)g * D + k - 1] = mp->mean[k];
@@ -297,28 +301,40 @@ static void Flatten(HMMSet *hset)
          }
       }
    }
-   for (p = 0; p < B.nHmm; p++) {
-      HLink hmm = B.hmm[p];
-      int t = pm_get(&B.pmTr, hmm->transP);
+   for (p = 0; p < F->nHmm; p++) {
+      HLink hmm = F->hmm[p];
+      int t = pm_get(&F->pmTr, hmm->transP);
       hmmN[p] = hmm->numStates; hmmTrans[p] = t;
       hmmStateOff[p + 1] = hmmStateOff[p] + hmm->numStates - 2;
-      for (j = 2; j < hmm->numStates; j++) hmmState[hmmStateOff[p] + j - 2] = pm_get(&B.pmSte, hmm->svec[j].info->pdf + 1);
-      if (!B.trans[t]) { B.trans[t] = hmm->transP; transN[t] = hmm->numStates; }
+      for (j = 2; j < hmm->numStates; j++) hmmState[hmmStateOff[p] + j - 2] = pm_get(&F->pmSte, hmm->svec[j].info->pdf + 1);
+      if (!F->trans[t]) { F->trans[t] = hmm->transP; transN[t] = hmm->numStates; }
    }
-   for (j = 0; j < B.nTr; j++) { transOff[j + 1] = transOff[j] + transN[j] * transN[j]; }
-   sumNN = transOff[B.nTr];
+   for (j = 0; j < F->nTr; j++) { transOff[j + 1] = transOff[j] + transN[j] * transN[j]; }
+   sumNN = transOff[F->nTr];
    transLogA = (float *)calloc(sumNN + 1, sizeof(float));
-   for (j = 0; j < B.nTr; j++) {
+   for (j = 0; j < F->nTr; j++) {
       int N = transN[j], a, b2;
-      for (a = 1; a <= N; a++) for (b2 = 1; b2 <= N; b2++) transLogA[transOff[j] + (a - 1) * N + b2 - 1] = B.trans[j][a][b2];
+      for (a = 1; a <= N; a++) for (b2 = 1; b2 <= N; b2++) transLogA[transOff[j] + (a - 1) * N + b2 - 1] = F->trans[j][a][b2];
    }
-   memset(&B.m, 0, sizeof(B.m));
-   B.m.vecSize = D; B.m.numGauss = B.nMp; B.m.mean = mean; B.m.ivar = ivar; B.m.gConst = gConst;
-   B.m.meanId = meanId; B.m.varId = varId; B.m.numMeanAcc = B.nMean; B.m.numVarAcc = B.nVar;
-   B.m.numStates = B.nSte; B.m.stateMixOff = stateMixOff; B.m.mixGauss = mixGauss; B.m.mixLogWt = mixLogWt;
-   B.m.numHmm = B.nHmm; B.m.hmmNumStates = hmmN; B.m.hmmStateOff = hmmStateOff; B.m.hmmState = hmmState;
-   B.m.hmmTrans = hmmTrans; B.m.numTrans = B.nTr; B.m.transN = transN; B.m.transOff = transOff; B.m.transLogA = transLogA;
-   B.D = D;
+   memset(&F->m, 0, sizeof(F->m));
+   F->m.vecSize = D; F->m.numGauss = F->nMp; F->m.mean = mean; F->m.ivar = ivar; F->m.gConst = gConst;
+   F->m.meanId = meanId; F->m.varId = varId; F->m.numMeanAcc = F->nMean; F->m.numVarAcc = F->nVar;
+   F->m.numStates = F->nSte; F->m.stateMixOff = stateMixOff; F->m.mixGauss = mixGauss; F->m.mixLogWt = mixLogWt;
+   F->m.numHmm = F->nHmm; F->m.hmmNumStates = hmmN; F->m.hmmStateOff = hmmStateOff; F->m.hmmState = hmmState;
+   F->m.hmmTrans = hmmTrans; F->m.numTrans = F->nTr; F->m.transN = transN; F->m.transOff = transOff; F->m.transLogA = transLogA;
+}
+
+static void FreeFlat(FlatSet *F)
+{
+   PMap *pm[6]; int k;
+   pm[0] = &F->pmHmm; pm[1] = &F->pmSte; pm[2] = &F->pmMp; pm[3] = &F->pmMean; pm[4] = &F->pmVar; pm[5] = &F->pmTr;
+   for (k = 0; k < 6; k++) { free((void *)pm[k]->key); free(pm[k]->val); }
+   free(F->hmm); free(F->ste); free(F->mp); free(F->meanV); free(F->varV); free(F->trans);
+   free((void *)F->m.mean); free((void *)F->m.ivar); free((void *)F->m.gConst); free((void *)F->m.meanId); free((void *)F->m.varId);
+   free((void *)F->m.stateMixOff); free((void *)F->m.mixGauss); free((void *)F->m.mixLogWt); free((void *)F->m.hmmNumStates);
+   free((void *)F->m.hmmStateOff); free((void *)F->m.hmmState); free((void *)F->m.hmmTrans); free((void *)F->m.transN);
+   free((void *)F->m.transOff); free((void *)F->m.transLogA);
+   memset(F, 0, sizeof(*F));
 }
 
 /* ------------------------------------------------------------------ public */
@@ -334,7 +350,7 @@ void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pr
    memset(&B, 0, sizeof(B));
    B.hset = hset; B.uFlags = uFlags; B.trace = herestTrace; B.fastFd = -1;
    B.tInit = now_s();
-   if (fbInfo->twoModels) HError(7399, "hfbgpu bridge: 2-model re-estimation is not accelerated");
+   B.alHset = fbInfo->twoModels ? fbInfo->al_hset : NULL;
    if (hset->xf != NULL || (uFlags & (UPXFORM | UPSEMIT | UPMAP)))
       HError(7399, "hfbgpu bridge: transforms / MAP updates are not accelerated");
    /* the reference applies these inside Setotprob / UpMixParms (ApplyCompFXForm + Jacobian); the library does not,
@@ -344,8 +360,23 @@ void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pr
    if (fbInfo->inXForm != NULL || fbInfo->al_inXForm != NULL || fbInfo->paXForm != NULL)
       HError(7399, "hfbgpu bridge: input / parent transforms (-a, -J, -E) are not accelerated");
    if (!hset->logWt) HError(7399, "hfbgpu bridge: expected log weights (ConvLogWt)");
-   Flatten(hset);
+   Flatten(hset, &B.u);
+   B.D = hset->vecSize;
+   pm_init(&B.pmLab, hset->numLogHMM + (B.alHset ? B.alHset->numLogHMM : 0) + 1024);
    hfbgpu_default_options(&opt);
+   if (B.alHset != NULL) {
+      /* 2-model re-estimation (ALIGNMODELMMF ..., HERest.c:647-684; UseAlignHMMSet, HFB.c:296-333): the library aligns
+         with this set and collects the statistics of `hset` */
+      Boolean bv;
+      if (B.alHset->xf != NULL || B.alHset->semiTied != NULL || B.alHset->projSize > 0)
+         HError(7399, "hfbgpu bridge: transforms on the alignment set are not accelerated");
+      if (!B.alHset->logWt) HError(7399, "hfbgpu bridge: expected log weights in the alignment set (ConvLogWt)");
+      nParm = GetConfig("HFB", TRUE, cParm, MAXGLOBS);
+      if (nParm > 0 && GetConfBool(cParm, nParm, "ALIGNCOMPLEVEL", &bv) && bv)
+         HError(7399, "hfbgpu bridge: ALIGNCOMPLEVEL (HFB.c:1521-1530) is not accelerated");
+      Flatten(B.alHset, &B.a);
+      opt.alignModel = &B.a.m;
+   }
    /* same precedence as InitFB + InitialiseForBack (HFB.c:221-233, :270-276): config file first,
       command line overrides */
    nParm = GetConfig("HFB", TRUE, cParm, MAXGLOBS);
@@ -379,13 +410,13 @@ void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pr
       if (strcmp(env, "all") == 0) { int n = hfbgpu_device_count(); for (nd = 0; nd < n && nd < 16; nd++) devs[nd] = nd; }
       else { char *e = env; while (*e && nd < 16) { devs[nd++] = (int32_t)strtol(e, &e, 10); while (*e == ',' || *e == ' ') e++; } }
       if (nd < 1) HError(7399, "hfbgpu bridge: HFBGPU_DEVICES lists no device");
-      rc = hfbgpu_create_multi(&B.ctx, &B.m, &opt, devs, nd);
+      rc = hfbgpu_create_multi(&B.ctx, &B.u.m, &opt, devs, nd);
    } else
-      rc = hfbgpu_create(&B.ctx, &B.m, &opt);
+      rc = hfbgpu_create(&B.ctx, &B.u.m, &opt);
    if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_create failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
-   hfbgpu_acc_layout(&B.m, &B.L);
+   hfbgpu_acc_layout(&B.u.m, &B.L);
    printf("hfbgpu: %d physical HMMs, %d tied states, %d Gaussians, %d transition matrices on %d GPU(s)\n",
-          B.nHmm, B.nSte, B.nMp, B.nTr, hfbgpu_num_devices(B.ctx));
+          B.u.nHmm, B.u.nSte, B.u.nMp, B.u.nTr, hfbgpu_num_devices(B.ctx));
    fflush(stdout);
    {  /* the two pinned batch buffers, once (cudaMallocHost of ~0.6 GB takes a few tenths of a second) */
       int i2;
@@ -446,6 +477,7 @@ static void Flush(void)
    { double t0 = now_s(); reader_wait(p); B.sReaderWait += now_s() - t0; }
    p->frameOff[p->nUtt] = p->nFrames; p->labOff[p->nUtt] = p->nLab;
    b.numUtt = p->nUtt; b.frameOff = p->frameOff; b.feat = p->feat; b.labOff = p->labOff; b.lab = p->lab;
+   b.labAlign = (B.alHset != NULL) ? p->labAl : NULL;
    p->res = (hfb_utt_result *)calloc(p->nUtt, sizeof(hfb_utt_result));
    if (B.twoData) {
       /* -r: alignment on the first file of each pair, mean / variance sums from the second (HFB.c:1603-1611);
@@ -552,26 +584,48 @@ Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
       if (p->feat2) { memcpy(nf, p->feat2, sizeof(float) * (size_t)p->nFrames * D); hfbgpu_host_free(p->feat2); }
       p->feat2 = nf; p->feat2Cap = ncap;
    }
+   if (B.alHset != NULL && B.twoData)
+      HError(7399, "hfbgpu bridge: 2-model re-estimation with two data files (-r) is not accelerated");
    if (p->nLab + Q > p->labCap) {
       p->labCap = (p->nLab + Q) * 2 + 1024;
       p->lab = (int32_t *)xrealloc(p->lab, sizeof(int32_t) * (size_t)p->labCap);
+      if (B.alHset != NULL) p->labAl = (int32_t *)xrealloc(p->labAl, sizeof(int32_t) * (size_t)p->labCap);
    }
    p->frameOff[p->nUtt] = p->nFrames; p->labOff[p->nUtt] = p->nLab;
-   /* labels -> physical HMM indices (CreateInsts, HFB.c:538-542) */
+   /* labels -> physical HMM indices (CreateInsts, HFB.c:538-552; with two sets: al_qList and up_qList) */
    for (lab = utt->tr->head->head->succ, q = 0; lab->succ != NULL; lab = lab->succ, q++) {
-      int li = pm_get(&B.pmLab, lab->labid), ph;
+      int li = pm_get(&B.pmLab, lab->labid), ph, pa = -1;
       if (li < 0) {                                         /* first time this label is seen: the reference's lookup */
-         MLink ml = FindMacroName(B.hset, 'l', lab->labid);
-         if (ml == NULL) HError(7321, "CreateInsts: Unknown label %s", lab->labid->name);
-         ph = pm_get(&B.pmHmm, ml->structure);
+         MLink ml;
+         if (B.alHset != NULL) {
+            HLink ah;
+            ml = FindMacroName(B.alHset, 'l', lab->labid);
+            if (ml == NULL) HError(7321, "CreateInsts: Unknown label %s", lab->labid->name);
+            ah = (HLink)ml->structure;
+            pa = pm_get(&B.a.pmHmm, ah);
+            if (pa < 0) HError(7321, "hfbgpu bridge: label %s maps to an unknown physical HMM of the alignment set", lab->labid->name);
+            ml = FindMacroName(B.hset, 'l', lab->labid);
+            if (ml == NULL) HError(2321, "CreateInsts: Unknown update label %s", lab->labid->name);
+            if (ah->numStates != ((HLink)ml->structure)->numStates)
+               HError(999, "Num states differ in align and update models (%d %d)", ah->numStates, ((HLink)ml->structure)->numStates);
+         } else {
+            ml = FindMacroName(B.hset, 'l', lab->labid);
+            if (ml == NULL) HError(7321, "CreateInsts: Unknown label %s", lab->labid->name);
+         }
+         ph = pm_get(&B.u.pmHmm, ml->structure);
          if (ph < 0) HError(7321, "hfbgpu bridge: label %s maps to an unknown physical HMM", lab->labid->name);
          if (B.pmLab.n * 2 + 2 < B.pmLab.cap) {
             li = pm_add(&B.pmLab, lab->labid);
-            if (li >= B.labCap) { B.labCap = li * 2 + 1024; B.labPhys = (int *)xrealloc(B.labPhys, sizeof(int) * (size_t)B.labCap); }
-            B.labPhys[li] = ph;
+            if (li >= B.labCap) {
+               B.labCap = li * 2 + 1024;
+               B.labPhys = (int *)xrealloc(B.labPhys, sizeof(int) * (size_t)B.labCap);
+               B.labPhysAl = (int *)xrealloc(B.labPhysAl, sizeof(int) * (size_t)B.labCap);
+            }
+            B.labPhys[li] = ph; B.labPhysAl[li] = pa;
          }
-      } else ph = B.labPhys[li];
+      } else { ph = B.labPhys[li]; pa = B.labPhysAl[li]; }
       p->lab[p->nLab + q] = ph;
+      if (B.alHset != NULL) p->labAl[p->nLab + q] = pa;
    }
    if (B.fastFd >= 0) {
       /* HFBGPU_FastLoad opened the file: a reader thread brings the payload into the pinned rows */
@@ -616,39 +670,39 @@ void HFBGPU_Finish(int *totalT, LogDouble *totalPr)
    acc = (double *)calloc((size_t)B.L.count, sizeof(double));
    rc = hfbgpu_get_accs(B.ctx, acc);
    if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_get_accs failed: %s", hfbgpu_strerror(rc));
-   for (p = 0; p < B.nHmm; p++) {
-      long n = (long)B.hmm[p]->hook + (long)(acc[B.L.numEgs + p] + 0.5);
-      B.hmm[p]->hook = (void *)n;                                       /* HFB.c:1768-1772 */
+   for (p = 0; p < B.u.nHmm; p++) {
+      long n = (long)B.u.hmm[p]->hook + (long)(acc[B.L.numEgs + p] + 0.5);
+      B.u.hmm[p]->hook = (void *)n;                                       /* HFB.c:1768-1772 */
    }
-   for (t = 0, o = 0; t < B.nTr; t++) {
-      TrAcc *ta = (TrAcc *)GetHook(B.trans[t]);
-      int N = B.m.transN[t];
+   for (t = 0, o = 0; t < B.u.nTr; t++) {
+      TrAcc *ta = (TrAcc *)GetHook(B.u.trans[t]);
+      int N = B.u.m.transN[t];
       if (ta != NULL && (B.uFlags & UPTRANS))
          for (i = 1; i <= N; i++)
             for (j = 1; j <= N; j++) ta->tran[i][j] += (float)acc[B.L.tran + o + (i - 1) * N + j - 1];
       o += (long long)N * N;
    }
-   for (t = 0, o = 0; t < B.nTr; t++) {
-      TrAcc *ta = (TrAcc *)GetHook(B.trans[t]);
-      int N = B.m.transN[t];
+   for (t = 0, o = 0; t < B.u.nTr; t++) {
+      TrAcc *ta = (TrAcc *)GetHook(B.u.trans[t]);
+      int N = B.u.m.transN[t];
       if (ta != NULL && (B.uFlags & UPTRANS)) for (i = 1; i <= N; i++) ta->occ[i] += (float)acc[B.L.tranOcc + o + i - 1];
       o += N;
    }
-   for (s = 0; s < B.nSte; s++) {
-      WtAcc *wa = (WtAcc *)B.ste[s]->hook;
-      int M = B.m.stateMixOff[s + 1] - B.m.stateMixOff[s];
+   for (s = 0; s < B.u.nSte; s++) {
+      WtAcc *wa = (WtAcc *)B.u.ste[s]->hook;
+      int M = B.u.m.stateMixOff[s + 1] - B.u.m.stateMixOff[s];
       if (wa == NULL) continue;
-      for (k = 1; k <= M; k++) wa->c[k] += (float)acc[B.L.wtC + B.m.stateMixOff[s] + k - 1];
+      for (k = 1; k <= M; k++) wa->c[k] += (float)acc[B.L.wtC + B.u.m.stateMixOff[s] + k - 1];
       wa->occ += (float)acc[B.L.wtOcc + s];
    }
-   for (g = 0; g < B.nMean; g++) {
-      MuAcc *ma = (MuAcc *)GetHook(B.meanV[g]);
+   for (g = 0; g < B.u.nMean; g++) {
+      MuAcc *ma = (MuAcc *)GetHook(B.u.meanV[g]);
       if (ma == NULL) continue;
       for (k = 1; k <= D; k++) ma->mu[k] += (float)acc[B.L.muSum + (long long)g * D + k - 1];
       ma->occ += (float)acc[B.L.muOcc + g];
    }
-   for (g = 0; g < B.nVar; g++) {
-      VaAcc *va = (VaAcc *)GetHook(B.varV[g]);
+   for (g = 0; g < B.u.nVar; g++) {
+      VaAcc *va = (VaAcc *)GetHook(B.u.varV[g]);
       if (va == NULL) continue;
       for (k = 1; k <= D; k++) va->cov.var[k] += (float)acc[B.L.vaSum + (long long)g * D + k - 1];
       va->occ += (float)acc[B.L.vaOcc + g];
@@ -666,20 +720,14 @@ void HFBGPU_Finish(int *totalT, LogDouble *totalPr)
    }
    for (i = 0; i < 2; i++) {
       hfbgpu_host_free(P[i].feat); hfbgpu_host_free(P[i].feat2);
-      free(P[i].frameOff); free(P[i].labOff); free(P[i].lab); free(P[i].names); free(P[i].res);
+      free(P[i].frameOff); free(P[i].labOff); free(P[i].lab); free(P[i].labAl); free(P[i].names); free(P[i].res);
       memset(&P[i], 0, sizeof(P[i]));
    }
    hfbgpu_destroy(B.ctx);
    B.ctx = NULL;
-   {
-      PMap *pm[7]; int k2;
-      pm[0] = &B.pmHmm; pm[1] = &B.pmSte; pm[2] = &B.pmMp; pm[3] = &B.pmMean; pm[4] = &B.pmVar; pm[5] = &B.pmTr; pm[6] = &B.pmLab;
-      for (k2 = 0; k2 < 7; k2++) { free((void *)pm[k2]->key); free(pm[k2]->val); }
-   }
-   free(B.labPhys); free(B.hmm); free(B.ste); free(B.mp); free(B.meanV); free(B.varV); free(B.trans);
-   free((void *)B.m.mean); free((void *)B.m.ivar); free((void *)B.m.gConst); free((void *)B.m.meanId); free((void *)B.m.varId);
-   free((void *)B.m.stateMixOff); free((void *)B.m.mixGauss); free((void *)B.m.mixLogWt); free((void *)B.m.hmmNumStates);
-   free((void *)B.m.hmmStateOff); free((void *)B.m.hmmState); free((void *)B.m.hmmTrans); free((void *)B.m.transN);
-   free((void *)B.m.transOff); free((void *)B.m.transLogA);
+   free((void *)B.pmLab.key); free(B.pmLab.val);
+   free(B.labPhys); free(B.labPhysAl);
+   FreeFlat(&B.u);
+   if (B.alHset != NULL) FreeFlat(&B.a);
    memset(&B, 0, sizeof(B)); B.fastFd = -1;
 }

@@ -459,3 +459,165 @@ stats3_kernel(DevModel M, Wave W)
    }
    if (lane == 0 && wsum > 0.0) atomicAdd(&W.acc[M.L.wtOcc + s], wsum);     // :1736
 }
+
+// ------------------------------------------------------------------------------------------
+// Two-model re-estimation (UseAlignHMMSet, HFB.c:296-333; HERest ALIGNMODELMMF): the wave was aligned with set A
+// (output probabilities, beams, alpha, beta, pr -- every kernel above ran on it); the statistics belong to set U.
+// One warp per emitting position (utterance, label q, state j), like stats3_kernel.  Per frame inside the alpha beam
+// (HFB.c:1518-1547, :1573-1578):
+//    comp_prob[m] = wght_m + log N(o_t; U's component m)            float, all M components of U's state
+//    norm         = LAdd over m of comp_prob[m]                      rounded to float after every LAdd
+//    x            = comp_prob[m] + alpha_j(t) + beta_j(t) - pr - norm   (M = 1: alpha_j + beta_j - pr)
+//    kept if wght_m > LMINMIX and -x < minFrwdP; Lr = exp(x) goes into U's accumulators, sums centred on U's means.
+// Transition statistics do not exist in this mode (HFB.c:313-316); numEgs counts U's physical HMMs (:1768-1772).
+// Not a bench path: FP32 CUDA cores, the reference's own evaluation order.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t stats_two_smem_bytes(int D)
+{
+   return ST_WARPS * (sizeof(double) * 64 + sizeof(float) * ((size_t)32 * stats_ostride(D) + 32 * 33 + 32) + sizeof(int) * 32);
+}
+
+__global__ void __launch_bounds__(32 * ST_WARPS)
+stats_two_kernel(DevModel A, DevModel U, Wave W, const int *__restrict__ labUp)
+{
+   extern __shared__ __align__(16) unsigned char smraw[];
+   const int wInB = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const int wg = blockIdx.x * ST_WARPS + wInB;
+   if (wg >= W.totalPos) return;
+   const int ui = upper_index(W.posPre, W.numUtt, wg);
+   if (W.out[ui].status != 0) return;
+   const UttDesc u = W.utt[ui];
+   const int lp = wg - W.posPre[ui];
+   if (lp == 0)                                                               // up_hmm->hook, HFB.c:1768-1772
+      for (int q2 = lane; q2 < u.Q; q2 += 32) atomicAdd(&W.acc[U.L.numEgs + labUp[u.labOff + q2]], 1.0);
+   const int q = upper_index(W.mPoff + u.modOff, u.Q, lp);
+   const int gq = u.modOff + q;
+   const int j = lp - W.mPoff[gq];                     // emitting index 0..N-3
+   const int tmin = W.mTmin[gq], tmax = W.mTmax[gq];
+   const int uf = W.uFlags;
+   const bool upM = (uf & HFB_UPMEANS) != 0, upV = (uf & HFB_UPVARS) != 0, upW = (uf & HFB_UPMIXES) != 0;
+   if (tmin > tmax || !(upM || upV || upW)) return;
+   const int D = U.D, Dp = U.Dp, P = u.P, S = u.S, ostr = stats_ostride(D);
+   const size_t perWarp = sizeof(double) * 64 + sizeof(float) * ((size_t)32 * ostr + 32 * 33 + 32) + sizeof(int) * 32;
+   unsigned char *mine = smraw + perWarp * wInB;
+   double *ajs = (double *)mine, *bjs = ajs + 32;      // [32] alpha_j(t), beta_j(t) of the chunk's frames
+   float *os = (float *)(bjs + 32);                    // [32][ostr] observation rows
+   float *lrs = os + 32 * ostr;                        // [32 components][33] comp_prob, then Lr
+   float *nrm = lrs + 32 * 33;                         // [32] norm per frame
+   int *ts = (int *)(nrm + 32);                        // [32] frame numbers
+
+   const int so = W.mSoff[gq];
+   const int pU = labUp[u.labOff + q];
+   const int s = U.hmmState[U.hmmStateOff[pU] + j];    // the update set's tied state at this position
+   const int mo = U.stateMixOff[s], Mn = U.stateMixOff[s + 1] - mo;
+   const double *alphaJ = W.occ + u.occOff + lp;
+   const double *betaU = W.beta + u.betaOff;
+   const short *sqA = W.sq + u.frameBase, *eqA = W.eq + u.frameBase;
+   const float *feat = W.feat + (size_t)u.featOff * D;
+   const double pr = W.out[ui].pr, minF = W.minFrwdP;
+   const int k0 = lane, k1 = lane + 32;                // D <= 64 (checked at create)
+   double wsum = 0.0;
+
+   auto comp_prob = [&](int m, const float *o) -> float {          // wght + MOutP, HFB.c:1544-1545 (IDOutP: HModel.c:5420-5431)
+      const int g = U.mixGauss[mo + m];
+      const float *mu = U.mean + (size_t)g * Dp, *iv = U.ivar + (size_t)g * Dp;
+      float sum = U.gconst[g];
+      for (int k = 0; k < D; k++) {
+         const float d = __fsub_rn(o[k], mu[k]);
+         sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), iv[k]));
+      }
+      return __fadd_rn(U.mixLogWt[mo + m], -0.5f * sum);
+   };
+
+   for (int t0 = tmin; t0 <= tmax; t0 += 32) {
+      const int t = t0 + lane;
+      const bool inb = (t <= tmax) && q >= sqA[t] && q <= eqA[t];
+      double aj = 0.0, bj = 0.0;
+      bool valid = false;
+      if (inb) {
+         aj = alphaJ[(size_t)t * P];
+         bj = betaU[(size_t)t * S + so + 1 + j];
+         valid = !((aj + bj) - pr < -(minF + 0.25));                         // posteriors are <= 1: nothing can pass :1606
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, valid);
+      const int nT = __popc(mask);
+      if (nT == 0) continue;
+      if (valid) { int idx = __popc(mask & ((1u << lane) - 1)); ts[idx] = t; ajs[idx] = aj; bjs[idx] = bj; }
+      __syncwarp();
+      for (int e = lane; e < nT * D; e += 32) {
+         const int ti = e / D, k = e - ti * D;
+         os[ti * ostr + k] = feat[(size_t)ts[ti] * D + k];
+      }
+      __syncwarp();
+      // ---- norm of every frame: components in order, float after every LAdd
+      float norm = (float)LZERO_D;
+      if (Mn > 1)
+         for (int mb = 0; mb < Mn; mb += 32) {
+            const int Mc = min(32, Mn - mb);
+            for (int pi = lane; pi < Mc * nT; pi += 32) {
+               const int mi = pi / nT, ti = pi - mi * nT;
+               lrs[mi * 33 + ti] = comp_prob(mb + mi, os + ti * ostr);
+            }
+            __syncwarp();
+            if (lane < nT)
+               for (int mi = 0; mi < Mc; mi++) norm = (float)ladd<true>((double)norm, (double)lrs[mi * 33 + lane]);
+            __syncwarp();
+         }
+      nrm[lane] = norm;
+      __syncwarp();
+      for (int mb = 0; mb < Mn; mb += 32) {
+         const int Mc = min(32, Mn - mb);
+         // ---- phase 1: lanes <-> (component, frame) pairs
+         unsigned act = 0;
+         for (int pi = lane; pi < ((Mc * nT + 31) & ~31); pi += 32) {
+            float Lr = 0.f;
+            const int mi = pi / nT, ti = pi - mi * nT;
+            if (mi < Mc) {
+               const float wt = U.mixLogWt[mo + mb + mi];
+               if (wt > LMINMIX_F) {                                         // HFB.c:1573
+                  double x;
+                  if (Mn == 1) x = (ajs[ti] + bjs[ti]) - pr;                 // :1575-1576
+                  else {
+                     const float cp = (Mn <= 32) ? lrs[mi * 33 + ti] : comp_prob(mb + mi, os + ti * ostr);
+                     x = ((((double)cp + ajs[ti]) + bjs[ti]) - pr) - (double)nrm[ti];   // :1578
+                  }
+                  if (-x < minF) Lr = (float)exp(x);                         // :1606, :1612
+               }
+            }
+            if (mi < Mc) lrs[mi * 33 + ti] = Lr;                             // the lane that read this comp_prob overwrites it
+            act |= __reduce_or_sync(0xffffffffu, (Lr > 0.f) ? (1u << mi) : 0u);
+         }
+         __syncwarp();
+         // ---- phase 2: lanes <-> feature dimensions, sums centred on the UPDATE set's means
+         for (unsigned b = act; b; b &= b - 1) {
+            const int mi = __ffs(b) - 1;
+            const int g = U.mixGauss[mo + mb + mi];
+            const float mu0 = (k0 < D) ? U.mean[(size_t)g * Dp + k0] : 0.f, mu1 = (k1 < D) ? U.mean[(size_t)g * Dp + k1] : 0.f;
+            float am0 = 0.f, am1 = 0.f, av0 = 0.f, av1 = 0.f, aocc = 0.f;
+            for (int ti = 0; ti < nT; ti++) {
+               const float Lr = lrs[mi * 33 + ti];
+               const float d0 = (k0 < D) ? os[ti * ostr + k0] - mu0 : 0.f, d1 = (k1 < D) ? os[ti * ostr + k1] - mu1 : 0.f;
+               const float z0 = d0 * Lr, z1 = d1 * Lr;                       // zmeanlr, :1675
+               aocc += Lr; am0 += z0; am1 += z1;
+               av0 = fmaf(z0, d0, av0); av1 = fmaf(z1, d1, av1);
+            }
+            if (upM) {
+               double *mu = W.acc + U.L.muSum + (size_t)U.meanId[g] * D;
+               if (k0 < D) atomicAdd(&mu[k0], (double)am0);
+               if (k1 < D) atomicAdd(&mu[k1], (double)am1);
+               if (lane == 0) atomicAdd(&W.acc[U.L.muOcc + U.meanId[g]], (double)aocc);
+            }
+            if (upV) {
+               double *va = W.acc + U.L.vaSum + (size_t)U.varId[g] * D;
+               if (k0 < D) atomicAdd(&va[k0], (double)av0);
+               if (k1 < D) atomicAdd(&va[k1], (double)av1);
+               if (lane == 0) atomicAdd(&W.acc[U.L.vaOcc + U.varId[g]], (double)aocc);
+            }
+            if (upW && lane == 0) atomicAdd(&W.acc[U.L.wtC + mo + mb + mi], (double)aocc);
+            wsum += (double)aocc;
+         }
+         __syncwarp();
+      }
+   }
+   if (lane == 0 && wsum > 0.0) atomicAdd(&W.acc[U.L.wtOcc + s], wsum);     // :1736
+}

@@ -122,6 +122,11 @@ struct hfbgpu_ctx {
    GmmTcModel tc;                    // expanded / split operands for the tcgen05 path
    GmmTc3Model tc3;                  // operands of gmm_tc3_kernel (fused expansion, taper skipping, single-Gaussian sets)
    bool useV3 = false;               // K1 = gmm_tc3_kernel
+   // Two-model re-estimation (hfb_options.alignModel): THIS context holds the alignment set and runs every kernel up to
+   // alpha on it; `upd` is a complete context of the update set that owns the accumulators (its layout, plus a tail of
+   // P_align doubles where the alignment kernels' numEgs increments land and are ignored), the M-step and the model
+   // tables stats_two_kernel reads.
+   hfbgpu_ctx *upd = nullptr;
    // accumulators
    DevBuf<double> dAcc;
    DevBuf<int> dHmmN, dHmmStateOff, dHmmState, dHmmTrans, dTransOffF, dTransMinDur;
@@ -290,10 +295,45 @@ static int upload(DevBuf<T> &b, const T *src, size_t n, cudaStream_t st)
    return HFB_OK;
 }
 
+static int create_one(hfbgpu_ctx **out, const hfb_model *m, const hfb_options *opt);
+
+static double *accp(hfbgpu_ctx *c) { return c->upd ? c->upd->dAcc.p : c->dAcc.p; }
+
 extern "C" int hfbgpu_create(hfbgpu_ctx **out, const hfb_model *m, const hfb_options *opt)
 {
    if (!out || !m || !opt) return HFB_EINVAL;
    *out = nullptr;
+   if (!opt->alignModel) return create_one(out, m, opt);
+   // ---- two-model re-estimation: UseAlignHMMSet, HFB.c:296-333
+   const hfb_model *al = opt->alignModel;
+   if (al->vecSize != m->vecSize) { g_lastError = "alignment and update sets differ in vector size (HError 7392)"; return HFB_EINVAL; }
+   hfb_options o = *opt;
+   o.alignModel = nullptr;
+   hfbgpu_ctx *u = nullptr, *a = nullptr;
+   hfb_options ou = o;
+   ou.gmmKernel = 1;                                    // the update set evaluates nothing on the tensor cores
+   int rc = create_one(&u, m, &ou);
+   if (rc) return rc;
+   o.uFlags &= ~HFB_UPTRANS;                            // "Don't update transitions on a 2-model alignment", HFB.c:313-316
+   if ((rc = create_one(&a, al, &o))) { hfbgpu_destroy(u); return rc; }
+   // the accumulators are the update set's; the alignment kernels index totalT / totalPr / numOk / numSkipped through
+   // their DevModel's layout, and numEgs by alignment HMM: that one goes to a tail nobody reads
+   a->dAcc.release();
+   a->L = u->L;
+   a->dm.L = u->L;
+   a->dm.L.numEgs = u->L.count;
+   if ((rc = u->dAcc.reserve((size_t)u->L.count + (size_t)al->numHmm + 1))) { hfbgpu_destroy(u); hfbgpu_destroy(a); return rc; }
+   if (cudaMemset(u->dAcc.p, 0, ((size_t)u->L.count + (size_t)al->numHmm + 1) * sizeof(double)) != cudaSuccess) {
+      cudaGetLastError(); hfbgpu_destroy(u); hfbgpu_destroy(a); return HFB_ECUDA;
+   }
+   a->upd = u;
+   cudaFuncSetAttribute(stats_two_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a->maxSmemOptin);
+   *out = a;
+   return HFB_OK;
+}
+
+static int create_one(hfbgpu_ctx **out, const hfb_model *m, const hfb_options *opt)
+{
    if (m->vecSize < 1 || m->numGauss < 1 || m->numStates < 1 || m->numHmm < 1 || m->numTrans < 1) return HFB_EINVAL;
    if (m->vecSize > 64) { g_lastError = "vecSize > 64 is outside the accelerated path"; return HFB_EUNSUPPORTED; }
    int ndev = hfbgpu_device_count();
@@ -465,6 +505,7 @@ extern "C" int hfbgpu_destroy(hfbgpu_ctx *c)
    }
    cudaSetDevice(c->device);
    if (c->stream) cudaStreamSynchronize(c->stream);
+   if (c->upd) { hfbgpu_destroy(c->upd); c->upd = nullptr; }
    c->dCentre.release();
    c->dMean.release(); c->dIvar.release(); c->dGconst.release(); c->dMixLogWt.release(); c->dTransLogA.release();
    c->dMeanId.release(); c->dVarId.release(); c->dStateMixOff.release(); c->dMixGauss.release();
@@ -519,12 +560,12 @@ extern "C" int hfbgpu_zero_accs(hfbgpu_ctx *c)
    }
    CK(cudaSetDevice(c->device));
    { int rc = wait_impl(c); if (rc) return rc; }
-   CK(cudaMemsetAsync(c->dAcc.p, 0, (size_t)c->L.count * sizeof(double), c->stream));
+   CK(cudaMemsetAsync(accp(c), 0, ((size_t)c->L.count + (c->upd ? (size_t)c->hm.P + 1 : 0)) * sizeof(double), c->stream));
    CK(cudaStreamSynchronize(c->stream));
    return HFB_OK;
 }
 
-extern "C" double *hfbgpu_acc_device_ptr(hfbgpu_ctx *c) { return !c ? nullptr : (is_group(c) ? c->kids[0]->dAcc.p : c->dAcc.p); }
+extern "C" double *hfbgpu_acc_device_ptr(hfbgpu_ctx *c) { return !c ? nullptr : (is_group(c) ? accp(c->kids[0]) : accp(c)); }
 extern "C" int64_t hfbgpu_acc_count(hfbgpu_ctx *c) { return c ? c->L.count : 0; }
 
 static int wait_impl(hfbgpu_ctx *c);
@@ -536,7 +577,7 @@ extern "C" int hfbgpu_get_accs(hfbgpu_ctx *c, double *hostOut)
    CK(cudaSetDevice(c->device));
    { int rc = wait_impl(c); if (rc) return rc; }
    CK(cudaStreamSynchronize(c->stream));
-   CK(cudaMemcpy(hostOut, c->dAcc.p, (size_t)c->L.count * sizeof(double), cudaMemcpyDeviceToHost));
+   CK(cudaMemcpy(hostOut, accp(c), (size_t)c->L.count * sizeof(double), cudaMemcpyDeviceToHost));
    c->stats.d2hBytes += c->L.count * (int64_t)sizeof(double);
    return HFB_OK;
 }
@@ -551,7 +592,7 @@ extern "C" int hfbgpu_set_accs(hfbgpu_ctx *c, const double *hostIn)
    CK(cudaSetDevice(c->device));
    { int rc = wait_impl(c); if (rc) return rc; }        // never under an in-flight wave
    CK(cudaStreamSynchronize(c->stream));
-   CK(cudaMemcpy(c->dAcc.p, hostIn, (size_t)c->L.count * sizeof(double), cudaMemcpyHostToDevice));
+   CK(cudaMemcpy(accp(c), hostIn, (size_t)c->L.count * sizeof(double), cudaMemcpyHostToDevice));
    return HFB_OK;
 }
 
@@ -675,8 +716,8 @@ struct ScratchLayout {
 // ------------------------------------------------------------------------------------------
 // one wave: launch (asynchronous) and finish (synchronise + hand results to the caller)
 // ------------------------------------------------------------------------------------------
-static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBase, const float *feat, const float *feat2, bool featOnDevice,
-                            long long waveFrame0, long long waveFrames, bool wantBeams)
+static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBase, const int32_t *labUpBase, const float *feat, const float *feat2,
+                            bool featOnDevice, long long waveFrame0, long long waveFrames, bool wantBeams)
 {
    WaveTables &w = *S.w;
    const int nU = (int)w.utt.size();
@@ -722,6 +763,7 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
           oTp = blob_put(blob, w.tilePre), oIt = blob_put(blob, w.tcItems), oIt2 = blob_put(blob, w.tcItems2), oIt4 = blob_put(blob, w.tcItems4);
    const size_t nLab = (size_t)w.utt.back().labOff + (size_t)w.utt.back().Q;
    size_t oLab = blob_put(blob, labBase, nLab);
+   const size_t oLabUp = labUpBase ? blob_put(blob, labUpBase, nLab) : 0;     // two-model re-estimation: up_qList
    if (blob.size() > S.hTablesCap) {
       if (S.hTables) cudaFreeHost(S.hTables);
       S.hTablesCap = blob.size() * 2;
@@ -759,7 +801,7 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
    }
    W.b = S.dB.p; W.beta = S.dBeta.p; W.occ = S.dOcc.p; W.aent = S.dAent.p;
    W.qLo = S.dBeams.p; W.qHi = W.qLo + waveFrames; W.sq = W.qHi + waveFrames; W.eq = W.sq + waveFrames;
-   W.acc = c->dAcc.p;
+   W.acc = accp(c);
    W.pruneInit = c->opt.pruneInit; W.pruneInc = c->opt.pruneInc; W.pruneLim = c->opt.pruneLim;
    W.minFrwdP = (double)c->opt.minFrwdP; W.uFlags = c->opt.uFlags;
 
@@ -879,7 +921,14 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
       if (tr) cudaEventRecord(S.ev[3], st);
       c->stats.launches += 2; c->stats.launchesBeta++; c->stats.launchesAlpha++;
       // ---- K4
-      if (w.totalP > 0 && c->opt.uFlags != 0) {
+      if (c->upd) {
+         // two-model re-estimation: statistics of the update set from this set's alignment (hfb_kernels2.cuh)
+         if (w.totalP > 0) {
+            stats_two_kernel<<<(unsigned)((w.totalP + ST_WARPS - 1) / ST_WARPS), 32 * ST_WARPS, stats_two_smem_bytes(c->dm.D), st>>>(
+               c->dm, c->upd->dm, W, (const int *)(base + oLabUp));
+            c->stats.launches++; c->stats.launchesStats++;
+         }
+      } else if (w.totalP > 0 && c->opt.uFlags != 0) {
          const int Dd = c->dm.D;
          // mixture sets: occupancy-weighted sums on the tensor cores (mma.sync 3xTF32); else the FP32 kernel
          // (single-Gaussian sets: only with the tcgen05 kernel, where the sums are one contraction per tile)
@@ -964,10 +1013,10 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
 
 // A wave that failed part-way (out of memory, unsupported shape, launch error) must not stay "in flight": whatever it
 // enqueued is drained and the slot is released, so that a later wait / finish never reads results that were not produced.
-static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBase, const float *feat, const float *feat2, bool featOnDevice,
-                       long long waveFrame0, long long waveFrames, bool wantBeams)
+static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBase, const int32_t *labUpBase, const float *feat, const float *feat2,
+                       bool featOnDevice, long long waveFrame0, long long waveFrames, bool wantBeams)
 {
-   const int rc = launch_wave_impl(c, S, labBase, feat, feat2, featOnDevice, waveFrame0, waveFrames, wantBeams);
+   const int rc = launch_wave_impl(c, S, labBase, labUpBase, feat, feat2, featOnDevice, waveFrame0, waveFrames, wantBeams);
    if (rc) {
       cudaStreamSynchronize(S.stream);
       cudaGetLastError();
@@ -1037,6 +1086,20 @@ static int submit_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, c
    CK(cudaSetDevice(c->device));
    CK(cudaStreamSynchronize(c->stream));               // accumulator zeroing / model uploads are done
    const HostModel &h = c->hm;
+   // two-model re-estimation: `lab` indexes the update set, `labAlign` this context's (alignment) set
+   if (c->upd && b->numUtt > 0 && !b->labAlign) { g_lastError = "two-model re-estimation: hfb_batch.labAlign is missing"; return HFB_EINVAL; }
+   if (c->upd && feat2) { g_lastError = "two-model re-estimation with two data files is outside the accelerated path"; return HFB_EUNSUPPORTED; }
+   const int32_t *labA = c->upd ? b->labAlign : b->lab;
+   if (c->upd && b->numUtt > 0) {
+      const HostModel &hu = c->upd->hm;
+      for (int i = b->labOff[0]; i < b->labOff[b->numUtt]; i++) {
+         const int pa = labA[i], pu = b->lab[i];
+         if (pu < 0 || pu >= hu.P) { g_lastError = "two-model re-estimation: update-set label out of range (HError 2321)"; return HFB_EINVAL; }
+         if (pa >= 0 && pa < h.P && h.hmmN[pa] != hu.hmmN[pu]) {
+            g_lastError = "Num states differ in align and update models (HError 999, HFB.c:549-551)"; return HFB_EINVAL;
+         }
+      }
+   }
    // validated for the WHOLE batch before anything is launched: a rejected batch leaves the accumulators untouched
    for (int u = 0; u < b->numUtt; u++) {
       const long long T = b->frameOff[u + 1] - b->frameOff[u];
@@ -1072,13 +1135,13 @@ static int submit_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, c
          int T = (int)(f1 - f0), Q = b->labOff[u1 + 1] - b->labOff[u1];
          size_t perFrame = 0;
          for (int q = 0; q < Q; q++) {
-            int p = b->lab[b->labOff[u1] + q];
+            int p = labA[b->labOff[u1] + q];
             int N = (p >= 0 && p < h.P) ? h.hmmN[p] : 2;
             perFrame += (size_t)N * 8 + (size_t)(N - 2) * 12 + 8;
          }
          size_t need = (size_t)T * perFrame;
          if (u1 > u0 && (bytes + need > wsPerSlot || u1 - u0 >= maxWaveUtts || f0 - waveFrame0 >= targetFrames)) break;
-         bytes += add_utterance(h, w, u1, T, b->lab + b->labOff[u1], Q, b->labOff[u1] - w.lab0, f0 - waveFrame0,
+         bytes += add_utterance(h, w, u1, T, labA + b->labOff[u1], Q, b->labOff[u1] - w.lab0, f0 - waveFrame0,
                                 (c->useV3 && c->opt.gmmKernel != 1) ? c->tc3.globalSlots : 0);
          u1++;
       }
@@ -1086,7 +1149,7 @@ static int submit_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, c
       const long long waveFrames = b->frameOff[u1] - waveFrame0;
       S.res = res; S.ticket = c->submitSeq;
       if (wantBeams) S.beams = *beams; else memset(&S.beams, 0, sizeof(S.beams));
-      rc = launch_wave(c, S, b->lab + w.lab0, b->feat, feat2, featOnDevice, waveFrame0, waveFrames, wantBeams);
+      rc = launch_wave(c, S, labA + w.lab0, c->upd ? b->lab + w.lab0 : nullptr, b->feat, feat2, featOnDevice, waveFrame0, waveFrames, wantBeams);
       if (rc) { rcAll = rc; break; }
       u0 = u1; c->nextSlot++;
       if (c->timing) { rc = finish_wave(c, S); if (rc) { rcAll = rc; break; } }
@@ -1151,17 +1214,17 @@ static int group_reduce(hfbgpu_ctx *g)
          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
          cudaGetLastError();
       }
-      if (can) pp.p[n++] = k->dAcc.p;
+      if (can) pp.p[n++] = accp(k);
       else {                                            // no NVLink / PCIe peer path: stage a copy on device 0
          double *tmp = nullptr;
          if (cudaMalloc(&tmp, (size_t)count * sizeof(double)) != cudaSuccess) { cudaGetLastError(); for (auto *t : staged) cudaFree(t); return HFB_ENOMEM; }
          staged.push_back(tmp);
-         CK(cudaMemcpyPeerAsync(tmp, k0->device, k->dAcc.p, k->device, (size_t)count * sizeof(double), k0->stream));
+         CK(cudaMemcpyPeerAsync(tmp, k0->device, accp(k), k->device, (size_t)count * sizeof(double), k0->stream));
          pp.p[n++] = tmp;
       }
    }
    const int grid = std::max(1, std::min(k0->smCount * 8, (int)((count + 255) / 256)));
-   acc_sum_peers_kernel<<<grid, 256, 0, k0->stream>>>(k0->dAcc.p, pp, n, count);
+   acc_sum_peers_kernel<<<grid, 256, 0, k0->stream>>>(accp(k0), pp, n, count);
    k0->stats.launches++; k0->stats.launchesMisc++;
    CK(cudaGetLastError());
    CK(cudaStreamSynchronize(k0->stream));
@@ -1169,7 +1232,7 @@ static int group_reduce(hfbgpu_ctx *g)
    for (size_t i = 1; i < g->kids.size(); i++) {        // their content now lives in child 0
       hfbgpu_ctx *k = g->kids[i];
       CK(cudaSetDevice(k->device));
-      CK(cudaMemsetAsync(k->dAcc.p, 0, (size_t)count * sizeof(double), k->stream));
+      CK(cudaMemsetAsync(accp(k), 0, (size_t)count * sizeof(double), k->stream));
       CK(cudaStreamSynchronize(k->stream));
    }
    g->reduced = true;
@@ -1332,6 +1395,7 @@ extern "C" int hfbgpu_mstep(hfbgpu_ctx *c, const hfb_mstep_options *opt, hfb_mst
    if (is_group(c)) { int rc = group_reduce(c); return rc ? rc : hfbgpu_mstep(c->kids[0], opt, out); }
    CK(cudaSetDevice(c->device));
    { int rc = wait_impl(c); if (rc) return rc; }
+   if (c->upd) return hfbgpu_mstep(c->upd, opt, out);   // two-model re-estimation: the update set is what gets re-estimated
    const HostModel &h = c->hm;
    const int D = h.D, G = h.G, J = h.J, nT = h.numTrans, nM = h.numMeanAcc, nV = h.numVarAcc;
    const int sumM = h.stateMixOff[J];

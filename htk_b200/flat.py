@@ -50,6 +50,7 @@ class hfb_options(C.Structure):
         ("pruneInit", C.c_double), ("pruneInc", C.c_double), ("pruneLim", C.c_double),
         ("minFrwdP", C.c_float), ("uFlags", C.c_int32), ("device", C.c_int32),
         ("gmmKernel", C.c_int32), ("reserved0", C.c_int32), ("workspaceBytes", C.c_size_t),
+        ("alignModel", C.c_void_p),
     ]
 
 
@@ -106,7 +107,7 @@ class hfb_batch(C.Structure):
     _fields_ = [
         ("numUtt", C.c_int32),
         ("frameOff", C.c_void_p), ("feat", C.c_void_p),
-        ("labOff", C.c_void_p), ("lab", C.c_void_p),
+        ("labOff", C.c_void_p), ("lab", C.c_void_p), ("labAlign", C.c_void_p),
     ]
 
 
@@ -137,9 +138,14 @@ NOPRUNE = 1.0e20
 
 
 def make_options(prune=None, min_frwd_p: float = 10.0, uflags: int = 15, device: int = 0,
-                 gmm_kernel: int = 0, workspace_bytes: int = 0) -> hfb_options:
-    """``prune`` = None (off, HFB.c:83) or (init, inc, lim) as HERest -t takes them."""
+                 gmm_kernel: int = 0, workspace_bytes: int = 0, align_model=None) -> hfb_options:
+    """``prune`` = None (off, HFB.c:83) or (init, inc, lim) as HERest -t takes them.  ``align_model`` = a FlatModel:
+    two-model re-estimation (HFB.c:296-333), the model the options are used with is then the update set."""
     o = hfb_options()
+    if align_model is not None:
+        o._align_model = align_model                    # keeps the arrays and the struct alive with the options
+        o._align_keep = align_model.c_struct()
+        o.alignModel = C.addressof(o._align_keep)
     if prune is None:
         o.pruneInit, o.pruneInc, o.pruneLim = NOPRUNE, 0.0, NOPRUNE
     else:
@@ -352,6 +358,12 @@ class Batch:
         b.totalT = int(b.frameOff[-1])
         return b
 
+    def with_align_labels(self, lab_align) -> "Batch":
+        """Two-model re-estimation: ``lab`` indexes the update set, ``lab_align`` the alignment set (same length)."""
+        self.labAlign = np.ascontiguousarray(lab_align, dtype=np.int32)
+        assert self.labAlign.shape == self.lab.shape
+        return self
+
     def c_struct(self, feat_ptr: Optional[int] = None) -> hfb_batch:
         b = hfb_batch()
         b.numUtt = self.numUtt
@@ -359,6 +371,8 @@ class Batch:
         b.feat = feat_ptr if feat_ptr is not None else self.feat.ctypes.data
         b.labOff = self.labOff.ctypes.data
         b.lab = self.lab.ctypes.data
+        la = getattr(self, "labAlign", None)
+        b.labAlign = la.ctypes.data if la is not None else None
         return b
 
 

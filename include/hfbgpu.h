@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HFBGPU_ABI_VERSION 1
+#define HFBGPU_ABI_VERSION 2
 
 /* log-arithmetic constants, HTKLib/HMath.h:42-45 and HTKLib/HModel.h:52-53 */
 #define HFB_LZERO   (-1.0E10)
@@ -112,6 +112,14 @@ typedef struct hfb_options {
    int32_t gmmKernel;            /* 0 = auto, 1 = FP32 CUDA-core, 2 = tcgen05 3xTF32 */
    int32_t reserved0;
    size_t  workspaceBytes;       /* 0 = default; cap for per-wave beta/outprob pool  */
+   /* Two-model re-estimation (UseAlignHMMSet, HFB.c:296-333; HERest ALIGNMODELMMF / ALIGNHMMLIST,
+    * HERest.c:163-181, :647-684).  NULL = one set does both jobs.  Otherwise this set ALIGNS -- output
+    * probabilities, beams, alpha, beta, utt->pr come from it -- and the model handed to hfbgpu_create is the UPDATE
+    * set: component posteriors (HFB.c:1518-1547, :1577-1578), centred sums, numEgs and the accumulator layout are
+    * its own.  Both sets must have the same vecSize, and the two HMMs a label resolves to the same number of states
+    * (HFB.c:549-551).  HFB_UPTRANS is dropped from uFlags as the reference does (HRError 7392, HFB.c:313-316): the
+    * transition accumulators stay zero.  Only read during hfbgpu_create / hfbgpu_create_multi.                     */
+   const struct hfb_model *alignModel;
 } hfb_options;
 
 /* ---- one batch of loaded utterances ------------------------------------------- */
@@ -121,6 +129,9 @@ typedef struct hfb_batch {
    const float   *feat;          /* [totalT][D] row-major, what ReadAsTable yields   */
    const int32_t *labOff;        /* [numUtt+1] offsets into lab                      */
    const int32_t *lab;           /* physical-HMM index per label (utt->tr resolved)  */
+   const int32_t *labAlign;      /* two-model re-estimation only (hfb_options.alignModel): the same labels resolved
+                                    in the ALIGNMENT set (al_qList, HFB.c:540-542); `lab` is then up_qList (:545-547).
+                                    NULL otherwise                                     */
 } hfb_batch;
 
 typedef struct hfb_utt_result {

@@ -107,7 +107,9 @@ int hfbo_min_durs(const hfb_model *m, int32_t *out)
 /* ------------------------------------------------------------------ context */
 
 typedef struct {
-   const hfb_model *m;
+   const hfb_model *m;       /* the set that aligns (al_hset); the only set unless two-model re-estimation is on */
+   const hfb_model *up;      /* the set whose statistics are collected (up_hset, HFB.c:253, :331)               */
+   int twoModels;            /* UseAlignHMMSet, HFB.c:296-333                                                     */
    hfb_options opt;
    hfb_acc_layout L;
    int accDouble;
@@ -137,8 +139,13 @@ static int ctx_init(Ctx *c, const hfb_model *m, const hfb_options *opt, void *ac
    int j, i;
    int64_t o;
    memset(c, 0, sizeof(*c));
-   c->m = m; c->opt = *opt; c->acc = acc; c->accDouble = accDouble;
-   layout_of(m, &c->L);
+   c->up = m; c->opt = *opt; c->acc = acc; c->accDouble = accDouble;
+   layout_of(m, &c->L);                                   /* accumulators belong to the update set */
+   if (opt->alignModel) {
+      m = opt->alignModel; c->twoModels = 1;
+      c->opt.uFlags &= ~HFB_UPTRANS;                      /* HFB.c:313-316 */
+   }
+   c->m = m;
    c->maxM = 0;
    for (j = 0; j < m->numStates; j++) {
       int M = m->stateMixOff[j + 1] - m->stateMixOff[j];
@@ -253,7 +260,8 @@ int hfbo_state_loglik(const hfb_model *m, const float *feat, int32_t T,
 typedef struct {
    int T, Q;
    const float *feat;
-   const int32_t *lab;
+   const int32_t *lab;     /* al_qList: physical HMMs of the aligning set */
+   const int32_t *labUp;   /* up_qList (HFB.c:521-531): the same array unless two-model re-estimation is on */
    int *N;            /* [Q+2] states per model */
    const float **A;   /* [Q+2] transition logs (row-major N*N, 0-based) */
    int *dms;          /* [Q+2] minimum durations (qDms) */
@@ -476,8 +484,8 @@ static int step_alpha(Ctx *c, Utt *u, int t, int *start, int *end, double pr)
  * and UpTranParms (:1371-1423) for model q at time t.                            */
 static void accumulate_model(Ctx *c, Utt *u, int t, int q, double pr)
 {
-   const hfb_model *m = c->m;
-   int N = u->N[q], i, j, k, mx, D = m->vecSize, p = u->lab[q - 1];
+   const hfb_model *m = c->up;                           /* UpMixParms / UpTranParms get up_hmm, HFB.c:1802-1805 */
+   int N = u->N[q], i, j, k, mx, D = m->vecSize, p = u->labUp[q - 1];
    int hasB = in_beam(u, t, q);                          /* always true inside the alpha beam */
    int hasB1 = (t < u->T) && in_beam(u, t + 1, q);       /* bqt1 != NULL */
    int hasBq1 = (q < u->Q) && in_beam(u, t, q + 1);      /* bq1t != NULL */
@@ -503,9 +511,9 @@ static void accumulate_model(Ctx *c, Utt *u, int t, int q, double pr)
       for (j = 2; j < N; j++) {
          int s = m->hmmState[m->hmmStateOff[p] + (j - 2)];
          int mo = m->stateMixOff[s], M = m->stateMixOff[s + 1] - mo;
-         const float *ov = outp(c, s, u->feat, t);
+         const float *ov = c->twoModels ? NULL : outp(c, s, u->feat, t);
          double initx = LZERO, steSumLr = 0.0, Lr;
-         float a;
+         float a, norm = 0.0f, comp_prob[256];
          if (c->maxM > 1) {                                       /* :1480-1489 */
             initx = TR(u, q, 1, j) + AL(u, q, 1);
             if (t > 1)
@@ -515,11 +523,20 @@ static void accumulate_model(Ctx *c, Utt *u, int t, int q, double pr)
                }
             initx += BETA(u, t, q, j) - pr;
          }
+         if (c->twoModels) {                                      /* component probs of the update hmm, :1518-1547 */
+            if (M > 255) M = 255;
+            norm = (float)LZERO;
+            for (mx = 1; mx <= M; mx++) {
+               comp_prob[mx] = m->mixLogWt[mo + mx - 1] + gauss_logp(m, m->mixGauss[mo + mx - 1], o);
+               norm = (float)ladd((double)norm, (double)comp_prob[mx]);
+            }
+         }
          for (mx = 1; mx <= M; mx++) {
             float wght = m->mixLogWt[mo + mx - 1];
             int g = m->mixGauss[mo + mx - 1];
             if (!(wght > HFB_LMINMIX)) continue;                  /* :1573 */
             if (M == 1) x = AL(u, q, j) + BETA(u, t, q, j) - pr; /* :1575-1576 */
+            else if (c->twoModels) x = comp_prob[mx] + AL(u, q, j) + BETA(u, t, q, j) - pr - norm;   /* :1577-1578 */
             else { x = initx + wght; x += ov[mx]; }              /* :1581-1599 */
             if (-x < c->opt.minFrwdP) {                           /* :1606 */
                const float *mean = m->mean + (size_t)g * D;
@@ -580,7 +597,7 @@ static void accumulate_model(Ctx *c, Utt *u, int t, int q, double pr)
 }
 
 /* FBFile = StepBack (HFB.c:1321-1366) + StepForward (:1752-1810) */
-static void fb_utt(Ctx *c, const float *feat, int T, const int32_t *lab, int Q,
+static void fb_utt(Ctx *c, const float *feat, int T, const int32_t *lab, const int32_t *labUp, int Q,
                    hfb_utt_result *r, int16_t *bLo, int16_t *bHi, int16_t *aLo, int16_t *aHi)
 {
    const hfb_model *m = c->m;
@@ -590,7 +607,7 @@ static void fb_utt(Ctx *c, const float *feat, int T, const int32_t *lab, int Q,
 
    memset(&u, 0, sizeof(u));
    r->status = HFB_UTT_OK; r->retries = 0; r->pr = LZERO; r->pruneThresh = c->opt.pruneInit;
-   u.T = T; u.Q = Q; u.feat = feat; u.lab = lab;
+   u.T = T; u.Q = Q; u.feat = feat; u.lab = lab; u.labUp = labUp ? labUp : lab;
    u.N = (int *)calloc((size_t)(Q + 2) * 4, sizeof(int));
    u.dms = u.N + (Q + 2); u.off = u.dms + (Q + 2); u.poff = u.off + (Q + 2);
    u.A = (const float **)calloc(Q + 2, sizeof(float *));
@@ -605,6 +622,7 @@ static void fb_utt(Ctx *c, const float *feat, int T, const int32_t *lab, int Q,
       if (u.N[q] > maxN) maxN = u.N[q];
       qt += u.dms[q];
       if (q > 1 && u.dms[q] == 0 && u.dms[q - 1] == 0) err = HFB_UTT_ETEE;
+      if (c->twoModels && c->up->hmmNumStates[u.labUp[q - 1]] != u.N[q]) err = HFB_EINVAL;   /* HError 999, :549-551 */
    }
    u.S = S; u.P = P;
    if (Q < 1 || u.dms[1] == 0 || u.dms[Q] == 0) err = HFB_UTT_ETEE;
@@ -633,7 +651,7 @@ static void fb_utt(Ctx *c, const float *feat, int T, const int32_t *lab, int Q,
 
    /* StepForward */
    init_alpha(c, &u, &start, &end);
-   for (q = 1; q <= Q; q++) acc_add(c, c->L.numEgs + lab[q - 1], 1.0);  /* :1768-1772 */
+   for (q = 1; q <= Q; q++) acc_add(c, c->L.numEgs + u.labUp[q - 1], 1.0);  /* up_hmm->hook, :1768-1772 */
    for (t = 1; t <= T; t++) {
       if (t > 1) {
          err = step_alpha(c, &u, t, &start, &end, lbeta);
@@ -677,7 +695,8 @@ static void *worker(void *p)
       {
          int64_t f0 = b->frameOff[u];
          int T = (int)(b->frameOff[u + 1] - f0), Q = b->labOff[u + 1] - b->labOff[u];
-         fb_utt(&c, b->feat + (size_t)f0 * D, T, b->lab + b->labOff[u], Q, &w->res[u],
+         fb_utt(&c, b->feat + (size_t)f0 * D, T, (b->labAlign ? b->labAlign : b->lab) + b->labOff[u],
+                b->lab + b->labOff[u], Q, &w->res[u],
                 beams && beams->qLo ? beams->qLo + f0 : NULL, beams && beams->qHi ? beams->qHi + f0 : NULL,
                 beams && beams->sq ? beams->sq + f0 : NULL, beams && beams->eq ? beams->eq + f0 : NULL);
       }
@@ -700,7 +719,8 @@ int hfbo_accumulate(const hfb_model *m, const hfb_options *opt, const hfb_batch 
       for (u = 0; u < b->numUtt; u++) {
          int64_t f0 = b->frameOff[u];
          int T = (int)(b->frameOff[u + 1] - f0), Q = b->labOff[u + 1] - b->labOff[u];
-         fb_utt(&c, b->feat + (size_t)f0 * D, T, b->lab + b->labOff[u], Q, &res[u],
+         fb_utt(&c, b->feat + (size_t)f0 * D, T, (b->labAlign ? b->labAlign : b->lab) + b->labOff[u],
+                b->lab + b->labOff[u], Q, &res[u],
                 beams && beams->qLo ? beams->qLo + f0 : NULL, beams && beams->qHi ? beams->qHi + f0 : NULL,
                 beams && beams->sq ? beams->sq + f0 : NULL, beams && beams->eq ? beams->eq + f0 : NULL);
       }
@@ -748,7 +768,7 @@ int hfbo_utt_occupancy(const hfb_model *m, const hfb_options *opt,
    for (q = 0; q < Q; q++) P += m->hmmNumStates[lab[q]] - 2;
    memset(occ, 0, sizeof(float) * (size_t)T * P);
    c.occOut = occ;
-   fb_utt(&c, feat, T, lab, Q, res, NULL, NULL, NULL, NULL);
+   fb_utt(&c, feat, T, lab, NULL, Q, res, NULL, NULL, NULL, NULL);
    ctx_free(&c);
    free(acc);
    return HFB_OK;

@@ -29,6 +29,22 @@ def load_golden(name):
     return z, fm, b, dict(prune=prune, min_frwd_p=float(z["minFrwdP"]), uflags=uf)
 
 
+TWO_MODEL_CASES = ["two_model_tied", "two_model_mono"]
+
+
+def load_two_model_golden(name):
+    """-> (npz, update FlatModel, alignment FlatModel, Batch with both label arrays, options kwargs)
+    Fixtures of tests/golden/make_two_model_golden.py: the stock HERest run with ALIGNMODELMMF."""
+    from htk_b200.flat import Batch, flat_from_arrays
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    fu = flat_from_arrays(D=int(z["D"]), names=list(z["names_up"]), **{k[2:]: z[k] for k in z.files if k.startswith("m_")})
+    fa = flat_from_arrays(D=int(z["D"]), names=list(z["names_al"]), **{k[2:]: z[k] for k in z.files if k.startswith("a_")})
+    b = Batch.from_arrays(z["feat"], z["frameOff"], z["lab"], z["labOff"]).with_align_labels(z["labAlign"])
+    pr = z["prune"]
+    prune = None if pr[0] >= 1e19 else tuple(float(x) for x in pr)
+    return z, fu, fa, b, dict(prune=prune, min_frwd_p=float(z["minFrwdP"]), uflags=int(z["uflags"]), align_model=fa)
+
+
 from htk_b200.compare import acc_errors  # noqa: E402,F401  (re-exported: the tests import it from here)
 
 

@@ -676,3 +676,60 @@ def test_tcgen05_statistics_leave_overflowing_waves_to_stats5(monkeypatch):
     oacc, _, _ = _oracle(fm, b, kw)
     e = acc_errors(a2, oacc, fm)
     assert max(e.values()) < RTOL, e
+
+
+# ------------------------------------------------------------------------------------------
+# two-model re-estimation (UseAlignHMMSet, HFB.c:296-333; UpMixParms :1518-1547)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("gmm_kernel", [1, 2])
+@pytest.mark.parametrize("name", ["two_model_tied", "two_model_mono"])
+def test_two_model_reestimation_matches_stock_herest(name, gmm_kernel):
+    """hfb_options.alignModel: aligned with one set, statistics of another -- against the dump the stock HERest wrote
+    with ALIGNMODELMMF / ALIGNHMMLIST (tests/golden/make_two_model_golden.py) and against the oracle."""
+    from conftest import load_two_model_golden
+    z, fu, fa, b, kw = load_two_model_golden(name)
+    fb = _fb(fu, gmm_kernel=gmm_kernel, **kw)
+    res, beams = fb.FBFile(b, want_beams=True)
+    acc = fb.GetAccs()
+    L = fu.layout
+    for r, t, rpf in zip(res, np.diff(z["frameOff"]), z["ref_pr_per_frame"]):
+        assert r.status == 0
+        assert abs(r.pr / t - rpf) <= RTOL * abs(rpf) + 1e-6
+    ref = z["ref_acc"]
+    assert np.all(acc[L.tran:L.wtC] == 0)                         # HFB.c:313-316: UPTRANS dropped
+    assert np.array_equal(acc[L.numEgs:L.totalT], ref[L.numEgs:L.totalT])      # up_hmm->hook
+    assert acc[L.totalT] == ref[L.totalT] and acc[L.numOk] == b.numUtt
+    e = acc_errors(acc, ref, fu)
+    assert max(e.values()) < RTOL, e
+    oacc, ores, obeams = _oracle(fu, b, kw)
+    e = acc_errors(acc, oacc, fu)
+    assert max(e.values()) < RTOL, e
+    for k in ("qLo", "qHi", "sq", "eq"):
+        assert np.array_equal(getattr(beams, k), getattr(obeams, k)), k
+    # twice the batch = twice the accumulators; zeroing clears them (and the numEgs tail of the alignment kernels)
+    fb.FBFile(b)
+    acc2 = fb.GetAccs()
+    assert np.allclose(acc2, 2 * acc, rtol=1e-9, atol=1e-9)
+    fb.ZeroAccs()
+    assert not fb.GetAccs().any()
+    # M-step = the update set re-estimated (the device M-step against the oracle-fed one)
+    fb.FBFile(b)
+    new, info = fb.MStep(min_egs=1)
+    fb.close()
+    assert new.mean.shape == fu.mean.shape and np.isfinite(new.mean).all()
+    occ = acc[L.muOcc:L.vaSum]
+    g = int(np.argmax(occ[fu.meanId]))
+    want = fu.mean[g] + acc[L.muSum + fu.meanId[g] * fu.D: L.muSum + (fu.meanId[g] + 1) * fu.D] / occ[fu.meanId[g]]
+    assert np.allclose(new.mean[g], want, rtol=1e-5, atol=1e-5)             # HERest.c:974-1012
+
+
+def test_two_model_rejects_bad_input():
+    from conftest import load_two_model_golden
+    from htk_b200 import capi
+    z, fu, fa, b, kw = load_two_model_golden("two_model_mono")
+    fb = _fb(fu, **kw)
+    plain = Batch.from_arrays(z["feat"], z["frameOff"], z["lab"], z["labOff"])          # no alignment labels
+    with pytest.raises(capi.HfbError):
+        fb.FBFile(plain)
+    assert not fb.GetAccs().any()
+    fb.close()

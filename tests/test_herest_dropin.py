@@ -334,3 +334,63 @@ def test_single_pass_retraining_matches_stock_herest(tmp_path):
     # 3xFP16-split product differ by ~4e-6 on log N)
     assert max(e[k] for k in ("tran", "tranOcc", "wtC", "wtOcc", "muOcc", "vaOcc")) < 5e-5, e
     assert e["muSum"] > 1e-2 and e["vaSum"] > 1e-2, e
+
+
+def test_herest_gpu_two_model_reestimation(tmp_path):
+    """2-model re-estimation through the drop-in tool (config ALIGNMODELMMF / ALIGNHMMLIST; HERest.c:647-684,
+    UseAlignHMMSet HFB.c:296-333): HERest_gpu and the stock HERest on the same two MMFs, lists, MLF and features ->
+    HER1.acc of the UPDATE set within 1e-4, the MMF the stock `-p 0` re-estimates from either dump within 1e-4."""
+    if not (os.path.exists(HEREST) and os.path.exists(HEREST_GPU)):
+        pytest.skip("reference binaries not built (bridge/make_herest_gpu.sh needs /root/reference)")
+    import re
+    tmp = str(tmp_path)
+    al = synth.make_tied_triphone_set(n_states=60, M=2, n_phys=40, n_logical=60, n_centre=8, seed=13, spread=0.2)
+    up = synth.make_tied_triphone_set(n_states=50, M=[4, 1, 3], n_phys=40, n_logical=60, n_centre=8, seed=31, spread=0.2)
+    sets = {}
+    for tag, hs in (("al", al), ("up", up)):
+        htkio.write_mmf(os.path.join(tmp, tag + ".mmf"), hs)
+        htkio.write_hmm_list(os.path.join(tmp, tag + ".list"), hs)
+        names = open(os.path.join(tmp, tag + ".list")).read().splitlines()
+        h2 = htkio.read_mmf([os.path.join(tmp, tag + ".mmf")], hmm_list=names)
+        sets[tag] = (h2, flatten(h2), names)
+    fa, fu = sets["al"][1], sets["up"][1]
+    common = [n for n in fa.hmm_index if n in fu.hmm_index]
+    rng = np.random.default_rng(3)
+    os.makedirs(os.path.join(tmp, "feat"))
+    mlf, scp = {}, []
+    for i in range(9):
+        names = [common[int(k)] for k in rng.integers(0, len(common), size=26)]
+        la = np.array([fa.hmm_index[n] for n in names], dtype=np.int32)
+        f = synth.sample_utterance(fa, la, 250 + int(rng.integers(-20, 21)), rng)
+        fn = os.path.join(tmp, "feat", "u%03d.mfc" % i)
+        htkio.write_htk_features(fn, f, up.parm_kind)
+        mlf["u%03d" % i] = names; scp.append(fn)
+    htkio.write_mlf(os.path.join(tmp, "labs.mlf"), mlf)
+    open(os.path.join(tmp, "scp"), "w").write("\n".join(scp) + "\n")
+    open(os.path.join(tmp, "two.cfg"), "w").write("ALIGNMODELMMF = al.mmf\nALIGNHMMLIST = al.list\n")
+    base = ["-C", "two.cfg", "-T", "1", "-u", "mvw", "-p", "1", "-H", "up.mmf", "-I", "labs.mlf", "-S", "scp"]
+    probs = {}
+    for exe, d in ((HEREST, "accA"), (HEREST_GPU, "accB")):
+        os.makedirs(os.path.join(tmp, d))
+        out = _run([exe] + base + ["-M", d, "up.list"], tmp)
+        assert "2-model re-estimation enabled" in out
+        probs[d] = [float(v) for v in re.findall(r"Utterance prob per frame = (\S+)", out)]
+    assert len(probs["accA"]) == len(probs["accB"]) == 9
+    assert np.allclose(probs["accA"], probs["accB"], rtol=1e-4, atol=0)
+    hsU, fmU, namesU = sets["up"]
+    a, prA, tA = htkio.read_acc_dump(os.path.join(tmp, "accA", "HER1.acc"), hsU, fmU, 11)
+    b, prB, tB = htkio.read_acc_dump(os.path.join(tmp, "accB", "HER1.acc"), hsU, fmU, 11)
+    assert tA == tB and abs(prA - prB) <= 1e-6 * abs(prA)
+    e = acc_errors(b, a, fmU)
+    e.pop("totalPr"); e.pop("totalT")
+    assert max(e.values()) < 1e-4, e
+    L = fmU.layout
+    assert a[L.muOcc:L.vaSum].sum() > 0.9 * tA
+    for d, o in (("accA", "outA"), ("accB", "outB")):
+        os.makedirs(os.path.join(tmp, o))
+        _run([HEREST, "-u", "mvw", "-p", "0", "-H", "up.mmf", "-M", o, "up.list", os.path.join(d, "HER1.acc")], tmp)
+    mA, vA, tA_, wA = _mmf_params(os.path.join(tmp, "outA", "up.mmf"), namesU)
+    mB, vB, tB_, wB = _mmf_params(os.path.join(tmp, "outB", "up.mmf"), namesU)
+    assert np.max(np.abs(mA - mB) / np.sqrt(vA)) < 1e-4 + 2e-6
+    assert np.max(np.abs(vA - vB) / vA) < 1e-4 + 2e-6
+    assert np.max(np.abs(np.exp(wA) - np.exp(wB))) < 1e-4

@@ -4,7 +4,8 @@ with the same float/double choices, so the bar is bit-exact, beams included."""
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, QUALIFIER_CASES, acc_errors, load_golden, load_qualifier_golden
+from conftest import (GOLDEN_CASES, QUALIFIER_CASES, TWO_MODEL_CASES, acc_errors, load_golden, load_qualifier_golden,
+                      load_two_model_golden)
 from htk_b200.flat import make_options
 from oracle import oracle_lib as O
 
@@ -33,6 +34,26 @@ def test_oracle_matches_reference_bit_exact(name):
             r = z["ref_" + k]
             m = r > 0
             assert np.array_equal(a[m], r[m]), k
+
+
+@pytest.mark.parametrize("name", TWO_MODEL_CASES)
+def test_oracle_two_model_matches_reference_bit_exact(name):
+    """Two-model re-estimation (HFB.c:296-333, :1518-1547): the stock HERest with ALIGNMODELMMF / ALIGNHMMLIST aligned with
+    one set and dumped the accumulators of another; the oracle, given both, reproduces the dump bit for bit."""
+    z, fu, fa, b, kw = load_two_model_golden(name)
+    acc, res, _ = O.accumulate(fu, make_options(**kw), b)
+    ref = z["ref_acc"]
+    L = fu.layout
+    assert np.all(ref[L.tran:L.wtC] == 0)              # HFB.c:313-316: no transition statistics on a 2-model alignment
+    assert np.array_equal(acc[:L.totalT].astype(np.float32), ref[:L.totalT].astype(np.float32))
+    assert acc[L.totalT] == ref[L.totalT]
+    assert np.float32(acc[L.totalPr]) == np.float32(ref[L.totalPr])
+    for (st, retries, pr, thr), t, rpf in zip(res, np.diff(z["frameOff"]), z["ref_pr_per_frame"]):
+        assert st == 0 and float("%e" % (pr / t)) == rpf
+    # and it is not the one-model answer: the update set alone gives other occupancies
+    kw1 = dict(kw); kw1.pop("align_model")
+    one, _, _ = O.accumulate(fu, make_options(**kw1), b)
+    assert not np.allclose(one[L.muOcc:L.vaSum], acc[L.muOcc:L.vaSum], rtol=1e-3, atol=1e-3)
 
 
 def test_oracle_double_accumulators_close_to_float():
