@@ -345,7 +345,7 @@ def test_herest_gpu_two_model_reestimation(tmp_path):
     import re
     tmp = str(tmp_path)
     al = synth.make_tied_triphone_set(n_states=60, M=2, n_phys=40, n_logical=60, n_centre=8, seed=13, spread=0.2)
-    up = synth.make_tied_triphone_set(n_states=50, M=[4, 1, 3], n_phys=40, n_logical=60, n_centre=8, seed=31, spread=0.2)
+    up = synth.make_tied_triphone_set(n_states=50, M=3, n_phys=40, n_logical=60, n_centre=8, seed=31, spread=0.2)
     sets = {}
     for tag, hs in (("al", al), ("up", up)):
         htkio.write_mmf(os.path.join(tmp, tag + ".mmf"), hs)
