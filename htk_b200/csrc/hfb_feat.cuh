@@ -15,8 +15,10 @@
 //     differentials were formed (AddQualifiers' order).  The reference adds the T values sequentially; here 32
 //     lanes add strided partial sums: the double sum can differ in the last bit, the float mean only when that
 //     bit decides a rounding (never seen on the golden vectors).
-// Not covered (hfbgpu_set_qualifiers rejects what it cannot express): _N (absolute energy suppressed), _V / global
-// mean / variance files, MatTran input transforms, V1COMPAT differences, HIGHDIFF fourth order.
+//   * _N (absolute energy suppressed, HParm.c:2882, :4655-4656): the last static column (energy or c0) feeds the
+//     differentials like any other but is not part of the observation; every later column moves one to the left.
+// Not covered (hfbgpu_set_qualifiers rejects what it cannot express): _V / global mean / variance files, MatTran
+// input transforms, V1COMPAT differences, HIGHDIFF fourth order.
 #pragma once
 #include "hfb_common.h"
 
@@ -25,6 +27,7 @@ struct FeatQual {
    int win[3];                      // DELTAWINDOW, ACCWINDOW, THIRDWINDOW; 0 = order absent
    int simpleDiffs;
    int zeroMeanCols;
+   int suppressEnergy;              // _N: static column numStatic-1 is not written
    int enabled;
 };
 
@@ -34,6 +37,7 @@ __global__ void __launch_bounds__(256) feat_regress_kernel(const UttDesc *__rest
                                                            int srcStride, int srcCol, float *__restrict__ dst, int dstStride,
                                                            int dstCol, int d, int win, int simple, int copyStatic)
 {
+   // copyStatic = how many leading static columns go to dst as they are (0 = none; numStatic - 1 with _N)
    const UttDesc &u = utt[blockIdx.y];
    const int T = u.T;
    const int FR = 256 / 16;                              // frames per block pass (a 16 x 16 tile of (frame, column))
@@ -52,7 +56,7 @@ __global__ void __launch_bounds__(256) feat_regress_kernel(const UttDesc *__rest
          }
          const float v = simple ? __fdiv_rn(__fsub_rn(fw, bk), (float)(2 * win)) : __fdiv_rn(sum, sigmaT2);
          d0[(size_t)t * dstStride + dstCol + c] = v;
-         if (copyStatic) d0[(size_t)t * dstStride + c] = s0[(size_t)t * srcStride + c];
+         if (c < copyStatic) d0[(size_t)t * dstStride + c] = s0[(size_t)t * srcStride + c];
       }
 }
 
@@ -90,14 +94,14 @@ static inline int feat_expand_launch(const FeatQual &q, const UttDesc *utt, int 
                                      cudaStream_t st, int *launches)
 {
    if (nU <= 0) return 0;
-   const int ns = q.numStatic;
+   const int ns = q.numStatic, sh = q.suppressEnergy ? 1 : 0;   // columns after the statics sit `sh` to the left
    const dim3 grid((unsigned)std::max(1, std::min(64, (maxT + 15) / 16)), (unsigned)nU);
    int n = 0;
    if (q.win[0] > 0) {
-      feat_regress_kernel<<<grid, 256, 0, st>>>(utt, src, ns, 0, dst, D, ns, ns, q.win[0], q.simpleDiffs, 1);
+      feat_regress_kernel<<<grid, 256, 0, st>>>(utt, src, ns, 0, dst, D, ns - sh, ns, q.win[0], q.simpleDiffs, ns - sh);
       n++;
       for (int o = 1; o < 3 && q.win[o] > 0; o++) {
-         feat_regress_kernel<<<grid, 256, 0, st>>>(utt, dst, D, o * ns, dst, D, (o + 1) * ns, ns, q.win[o], q.simpleDiffs, 0);
+         feat_regress_kernel<<<grid, 256, 0, st>>>(utt, dst, D, o * ns - sh, dst, D, (o + 1) * ns - sh, ns, q.win[o], q.simpleDiffs, 0);
          n++;
       }
    } else {

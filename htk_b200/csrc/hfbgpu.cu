@@ -1465,15 +1465,16 @@ extern "C" int hfbgpu_set_qualifiers(hfbgpu_ctx *c, const hfb_qualifiers *q)
    const int orders = 1 + (q->delWin > 0) + (q->accWin > 0) + (q->thirdWin > 0);
    if (q->numStatic < 1 || q->delWin < 0 || q->accWin < 0 || q->thirdWin < 0 || q->delWin > 64 || q->accWin > 64 ||
        q->thirdWin > 64 || (q->accWin > 0 && q->delWin == 0) || (q->thirdWin > 0 && q->accWin == 0) ||
-       q->zeroMeanCols < 0 || q->zeroMeanCols > q->numStatic) {
+       q->zeroMeanCols < 0 || q->zeroMeanCols > q->numStatic || (q->suppressEnergy && (q->delWin == 0 || q->numStatic < 2)) ||
+       (q->suppressEnergy && q->zeroMeanCols > q->numStatic - 1)) {
       g_lastError = "inconsistent qualifier description"; return HFB_EINVAL;
    }
-   if (q->numStatic * orders != c->hm.D) {
+   if (q->numStatic * orders - (q->suppressEnergy ? 1 : 0) != c->hm.D) {
       g_lastError = "qualifiers do not expand to the model's vector size"; return HFB_EINVAL;
    }
    FeatQual f;
    f.numStatic = q->numStatic; f.win[0] = q->delWin; f.win[1] = q->accWin; f.win[2] = q->thirdWin;
-   f.simpleDiffs = q->simpleDiffs != 0; f.zeroMeanCols = q->zeroMeanCols; f.enabled = 1;
+   f.simpleDiffs = q->simpleDiffs != 0; f.zeroMeanCols = q->zeroMeanCols; f.suppressEnergy = q->suppressEnergy != 0; f.enabled = 1;
    c->qual = f;
    return HFB_OK;
 }

@@ -66,7 +66,7 @@ class hfb_mstep_result(C.Structure):
 
 class hfb_qualifiers(C.Structure):
     _fields_ = [("numStatic", C.c_int32), ("delWin", C.c_int32), ("accWin", C.c_int32), ("thirdWin", C.c_int32),
-                ("simpleDiffs", C.c_int32), ("zeroMeanCols", C.c_int32)]
+                ("simpleDiffs", C.c_int32), ("zeroMeanCols", C.c_int32), ("suppressEnergy", C.c_int32)]
 
 
 class Qualifiers:
@@ -74,9 +74,10 @@ class Qualifiers:
     (TARGETKIND, DELTAWINDOW, ACCWINDOW, THIRDWINDOW, SIMPLEDIFFS; HParm.c:838-871)."""
 
     def __init__(self, num_static: int, del_win: int = 0, acc_win: int = 0, third_win: int = 0,
-                 simple_diffs: bool = False, zero_mean_cols: int = 0):
+                 simple_diffs: bool = False, zero_mean_cols: int = 0, suppress_energy: bool = False):
         self.num_static, self.del_win, self.acc_win, self.third_win = num_static, del_win, acc_win, third_win
         self.simple_diffs, self.zero_mean_cols = bool(simple_diffs), zero_mean_cols
+        self.suppress_energy = bool(suppress_energy)     # _N: last static column (energy / c0) left out of the observation
 
     @classmethod
     def from_kinds(cls, source_kind: str, target_kind: str, num_static: int, del_win: int = 2, acc_win: int = 2,
@@ -86,21 +87,25 @@ class Qualifiers:
         sq, tq = set(source_kind.split("_")[1:]), set(target_kind.split("_")[1:])
         if source_kind.split("_")[0] != target_kind.split("_")[0] or (sq - {"K", "C"}) - tq or sq & {"D", "A", "T", "Z"}:
             raise ValueError("cannot go from %s to %s on the device" % (source_kind, target_kind))
-        if (tq - sq) - {"D", "A", "T", "Z"}:
-            raise ValueError("only _D _A _T _Z can be added on the device (%s -> %s)" % (source_kind, target_kind))
+        if (tq - sq) - {"D", "A", "T", "Z", "N"}:
+            raise ValueError("only _D _A _T _Z _N can be added on the device (%s -> %s)" % (source_kind, target_kind))
+        if "N" in tq and ("D" not in tq or not (tq & {"E", "0"}) or {"E", "0"} <= tq):
+            raise ValueError("_N needs _D and exactly one of _E / _0 (HParm.c:1415-1420)")
         zc = 0
         if "Z" in tq:
             zc = num_static - (1 if "E" in tq else 0)       # cepstra and c0, not the energy (HParm.c:1709-1712)
+            if "N" in tq:
+                zc = min(zc, num_static - 1)                # the suppressed column is never delivered
         return cls(num_static, del_win if "D" in tq else 0, acc_win if "A" in tq else 0,
-                   third_win if "T" in tq else 0, simple_diffs, zc)
+                   third_win if "T" in tq else 0, simple_diffs, zc, "N" in tq)
 
     @property
     def vec_size(self) -> int:
-        return self.num_static * (1 + (self.del_win > 0) + (self.acc_win > 0) + (self.third_win > 0))
+        return self.num_static * (1 + (self.del_win > 0) + (self.acc_win > 0) + (self.third_win > 0)) - (1 if self.suppress_energy else 0)
 
     def c_struct(self) -> "hfb_qualifiers":
         return hfb_qualifiers(self.num_static, self.del_win, self.acc_win, self.third_win,
-                              1 if self.simple_diffs else 0, self.zero_mean_cols)
+                              1 if self.simple_diffs else 0, self.zero_mean_cols, 1 if self.suppress_energy else 0)
 
 
 class hfb_batch(C.Structure):

@@ -256,6 +256,8 @@ typedef struct hfb_qualifiers {
    int32_t thirdWin;       /* THIRDWINDOW (:871),        0 = no _T                              */
    int32_t simpleDiffs;    /* SIMPLEDIFFS (:840)                                                */
    int32_t zeroMeanCols;   /* _Z: leading columns to zero-mean per utterance = cepstra (+1 with _0), HParm.c:1709-1712; 0 = no _Z */
+   int32_t suppressEnergy; /* _N: the absolute energy / c0 -- the LAST static column -- enters the differentials but is left
+                              out of the observation (HParm.c:2882 skipE, :4655-4656): vecSize = numStatic * orders - 1 */
 } hfb_qualifiers;
 int hfbgpu_set_qualifiers(hfbgpu_ctx *ctx, const hfb_qualifiers *q);
 /* The expansion alone (what HCopy with that TARGETKIND writes): src = [frames][numStatic] host

@@ -31,9 +31,11 @@ def regress(src: np.ndarray, win: int, simple: bool) -> np.ndarray:
     return (acc / sigma).astype(F)                                            # :851
 
 
-def expand(static: np.ndarray, del_win=0, acc_win=0, third_win=0, simple=False, zero_mean_cols=0) -> np.ndarray:
+def expand(static: np.ndarray, del_win=0, acc_win=0, third_win=0, simple=False, zero_mean_cols=0,
+           suppress_energy=False) -> np.ndarray:
     """AddQualifiers: deltas over all static columns, accelerations over the deltas, thirds over the
-    accelerations (HParm.c:1664-1697), then FZeroMean over the leading columns (:1707-1722)."""
+    accelerations (HParm.c:1664-1697), then FZeroMean over the leading columns (:1707-1722); with _N the last static
+    column (energy / c0) is left out of the observation that is delivered (HParm.c:2882, :4655-4656)."""
     x = np.ascontiguousarray(static, dtype=F)
     cols = [x]
     for w in (del_win, acc_win, third_win):
@@ -47,4 +49,6 @@ def expand(static: np.ndarray, del_win=0, acc_win=0, third_win=0, simple=False, 
             s += float(v)
         mean = F(s / float(out.shape[0]))
         out[:, c] = (out[:, c] - mean).astype(F)
+    if suppress_energy:
+        out = np.delete(out, x.shape[1] - 1, axis=1)
     return out

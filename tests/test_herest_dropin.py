@@ -217,26 +217,30 @@ def test_device_mstep_matches_stock_herest(tmp_path, opts):
     assert sum(r.pr for r in r1) >= sum(r.pr for r in r0) - 1e-6 * abs(sum(r.pr for r in r0))
 
 
-def test_device_qualifiers_match_stock_herest_loader(tmp_path):
+@pytest.mark.parametrize("src_kind,tgt_kind", [("MFCC_0", "MFCC_0_D_A_Z"), ("MFCC_E", "MFCC_E_D_A_N"), ("MFCC_0", "MFCC_0_D_N_Z")])
+def test_device_qualifiers_match_stock_herest_loader(tmp_path, src_kind, tgt_kind):
     """files hold MFCC_0 (13 static coefficients), the configuration asks for
     TARGETKIND = MFCC_0_D_A_Z.  The stock HERest expands in its loader (HParm.c AddQualifiers); the library gets
-    the 13-column matrices plus hfbgpu_set_qualifiers and expands on the device.  `-p 1` accumulators within 1e-4."""
+    the 13-column matrices plus hfbgpu_set_qualifiers and expands on the device.  `-p 1` accumulators within 1e-4.
+    The _N targets (absolute energy / c0 suppressed: 38 and 25 columns) cannot be written by HCopy (it refuses them as a
+    coding target), so the stock HERest loader is the reference for them; the CPU restatement is checked alongside."""
     if not os.path.exists(HEREST):
         pytest.skip("reference binaries not built")
     from htk_b200.estep import ForwardBackward
     from htk_b200.flat import Batch, Qualifiers
     tmp = str(tmp_path)
+    q = Qualifiers.from_kinds(src_kind, tgt_kind, 13)
     hs = synth.make_tied_triphone_set(n_states=40, M=3, n_phys=24, n_logical=30, n_centre=5, seed=43, spread=0.25,
-                                      parm_kind="MFCC_0_D_A_Z")
+                                      parm_kind=tgt_kind, D=q.vec_size)
     hs2, fm = _setup(tmp, hs, n_utts=8, T=240, Q=20, seed=11)
     # overwrite the feature files with their 13 static columns, kind MFCC_0
     scp = open(os.path.join(tmp, "scp")).read().split()
     static = []
     for f in scp:
         x = htkio.read_htk_features(f)[0][:, :13].copy()
-        htkio.write_htk_features(f, x, "MFCC_0")
+        htkio.write_htk_features(f, x, src_kind)
         static.append(x)
-    open(os.path.join(tmp, "cfg"), "w").write("TARGETKIND = MFCC_0_D_A_Z\nDELTAWINDOW = 2\nACCWINDOW = 2\n")
+    open(os.path.join(tmp, "cfg"), "w").write("TARGETKIND = %s\nDELTAWINDOW = 2\nACCWINDOW = 2\n" % tgt_kind)
     os.makedirs(os.path.join(tmp, "accA"))
     _run([HEREST, "-C", "cfg", "-T", "1", "-u", "tmvw", "-p", "1", "-H", "mmf", "-I", "labs.mlf", "-S", "scp",
           "-M", "accA", "list"], tmp)
@@ -249,9 +253,14 @@ def test_device_qualifiers_match_stock_herest_loader(tmp_path):
         block = re.search(r'"\*/%s\.lab"\n(.*?)\n\.\n' % u, mlf, re.S).group(1).split("\n")
         labs.append(np.array([fm.hmm_index[l] for l in block], dtype=np.int32))
     fb = ForwardBackward(fm)
-    fb.SetQualifiers(Qualifiers.from_kinds("MFCC_0", "MFCC_0_D_A_Z", 13))
+    fb.SetQualifiers(q)
     res, _ = fb.FBFile(Batch(static, labs, 13))
     b = fb.GetAccs()
+    # the expansion alone against the CPU restatement of HParm.c (bit-identical)
+    from oracle import hparm_oracle as H
+    for x, y in zip(static[:3], fb.ExpandFeatures(static[:3])):
+        want = H.expand(x, q.del_win, q.acc_win, q.third_win, q.simple_diffs, q.zero_mean_cols, q.suppress_energy)
+        assert y.shape == want.shape == (x.shape[0], q.vec_size) and np.array_equal(y, want)
     fb.close()
     assert all(r.status == 0 for r in res)
     L = fm.layout

@@ -132,7 +132,13 @@ def test_qualifier_description_from_kinds():
     assert (q.vec_size, q.simple_diffs, q.zero_mean_cols) == (24, True, 0)
     q = Qualifiers.from_kinds("MFCC_0_K", "MFCC_0_D_A_T", 13)                          # _K (CRC) is a file property
     assert q.vec_size == 52
-    for src, tgt in (("MFCC_0", "PLP_0_D"), ("MFCC_0_D", "MFCC_0_D_A"), ("MFCC_0", "MFCC_0_D_N"), ("MFCC_E", "MFCC_0_D")):
+    q = Qualifiers.from_kinds("MFCC_E", "MFCC_E_D_A_N", 13)                            # _N: energy out of the observation
+    assert (q.suppress_energy, q.vec_size, q.c_struct().suppressEnergy) == (True, 38, 1)
+    q = Qualifiers.from_kinds("MFCC_0", "MFCC_0_D_N_Z", 13)
+    assert (q.vec_size, q.zero_mean_cols) == (25, 12)
+    # _N needs _D and exactly one of _E / _0 (ValidConversion, HParm.c:1415-1420)
+    for src, tgt in (("MFCC_0", "PLP_0_D"), ("MFCC_0_D", "MFCC_0_D_A"), ("MFCC_0", "MFCC_0_N"), ("MFCC", "MFCC_D_N"),
+                     ("MFCC_E", "MFCC_0_D")):
         with pytest.raises(ValueError):
             Qualifiers.from_kinds(src, tgt, 13)
     c = Qualifiers(13, 2, 2, 0, True, 13).c_struct()
