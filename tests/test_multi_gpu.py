@@ -77,3 +77,27 @@ def test_herest_gpu_on_two_devices_equals_stock(tmp_path, monkeypatch):
     e = acc_errors(b, a, fm)
     e.pop("totalPr"); e.pop("totalT")
     assert max(e.values()) < 1e-4, e
+
+
+def test_two_model_reestimation_on_a_device_group():
+    """hfb_options.alignModel through hfbgpu_create_multi: every child context aligns with one set and accumulates the other;
+    the summed buffers equal the single-device result and the stock HERest dump (ALIGNMODELMMF fixture)."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from conftest import acc_errors, load_two_model_golden
+    from htk_b200.estep import ForwardBackward
+    z, fu, fa, b, kw = load_two_model_golden("two_model_tied")
+    one = ForwardBackward(fu, **kw); r1, _ = one.FBFile(b); a1 = one.GetAccs(); one.close()
+    grp = ForwardBackward(fu, devices=[0, 1], **kw)
+    r2, _ = grp.FBFile(b)
+    a2 = grp.GetAccs()
+    grp.close()
+    assert [tuple(r) for r in r1] == [tuple(r) for r in r2]
+    e = acc_errors(a2, a1, fu)
+    assert max(e.values()) < 1e-5, e
+    e = acc_errors(a2, z["ref_acc"], fu)
+    assert max(e.values()) < 1e-4, e
+    L = fu.layout
+    assert np.array_equal(a2[L.numEgs:L.totalT], z["ref_acc"][L.numEgs:L.totalT])
