@@ -71,6 +71,8 @@ struct GmmTcWork {             // per-stream expanded feature operand (floats: T
    size_t flagCap = 0;
    float *dPad = nullptr;            // gmm_tc3_pad_kernel: scaled features with padded rows (single-Gaussian sets)
    size_t padCap = 0;
+   uint4 *dExpA = nullptr;           // gmm_tc3_kernel's optional output: every frame's expanded operand row (hfb_stats_tc.cuh)
+   size_t expCap = 0;                // in 16-byte units
    size_t aCapFrames = 0;
    bool f16Init = false;       // constant / padding columns of the FP16 layout are in place
    void release()
@@ -80,6 +82,8 @@ struct GmmTcWork {             // per-stream expanded feature operand (floats: T
       if (dFlag) cudaFree(dFlag);
       if (dFlag3) cudaFree(dFlag3);
       if (dPad) cudaFree(dPad);
+      if (dExpA) cudaFree(dExpA);
+      dExpA = nullptr; expCap = 0;
       dAhi = dAlo = nullptr; dFlag = dFlag3 = nullptr; dPad = nullptr; aCapFrames = 0; flagCap = 0; padCap = 0; f16Init = false;
    }
 };

@@ -48,6 +48,9 @@ struct Tc3Params {
    const float *offset, *scale;
    float *b;
    unsigned char *flag;
+   uint4 *expA;                // optional output: every frame's expanded operand row, [frames][hi units | lo units] of 16 bytes
+                               // (2 * 2 * kSteps per row) -- the tensor-core statistics kernel gathers them instead of
+                               // expanding the rows a second time (hfb_stats_tc.cuh)
    float C0;
    int D;
    int kSteps;                 // 16-half K steps that hold data: ceil((2D+2)/16)
@@ -383,7 +386,7 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
          }
          if (inside) p.flag[u.frameBase + t] = far ? 1 : 0;
       };
-      auto store_row = [&](const float (&xr)[DP], int b) {
+      auto store_row = [&](const float (&xr)[DP], int b, uint4 *grow, const bool toSmem) {
          uint8_t *blk = sA + b * A_BLK;
 #pragma unroll
          for (int un = 0; un < 16; un++) {
@@ -405,10 +408,21 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
                hi[e] = *reinterpret_cast<const uint32_t *>(&h);
                lo[e] = *reinterpret_cast<const uint32_t *>(&l);
             }
-            const uint32_t off = tc3_unit_off(r, un);
-            *reinterpret_cast<uint4 *>(blk + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4 *>(blk + 32768 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            if (toSmem) {
+               const uint32_t off = tc3_unit_off(r, un);
+               *reinterpret_cast<uint4 *>(blk + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+               *reinterpret_cast<uint4 *>(blk + 32768 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            if (grow != nullptr) {
+               grow[un] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+               grow[nUnits + un] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
          }
+      };
+      // where block b's row of this thread goes in the expanded-operand output (nullptr: not wanted / past the utterance)
+      auto exp_row = [&](const int2 item, const UttDesc &u, int b) -> uint4 * {
+         const int t = item.y + (2 * b + (int)rank) * TC_BM + r;
+         return (p.expA != nullptr && t < u.T) ? p.expA + (size_t)(u.frameBase + t) * (size_t)(2 * nUnits) : nullptr;
       };
       int2 item = make_int2(0, 0);
       UttDesc u;
@@ -422,14 +436,20 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
          tc_mbar_wait(emptyA, phA ^ 1);
          phA ^= 1;
          if (!skipX) {
-            store_row(x[0], 0);
+            // (the copy of the rows to global memory waits until the MMA thread has been told, below: with both rows in
+            // registers the conversion is simply done a second time, outside the window the tensor core idles in)
+            store_row(x[0], 0, NPRE == 1 ? exp_row(item, u, 0) : nullptr, true);
             if (NPRE == 1) load_row(x[0], item, u, 1);
-            store_row(x[NPRE - 1], 1);
+            store_row(x[NPRE - 1], 1, NPRE == 1 ? exp_row(item, u, 1) : nullptr, true);
          }
          // generic-proxy writes -> visible to the tensor core (async proxy), then tell the leader's MMA thread
          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
          __syncwarp();
          if (lane == 0) tc3_arrive_leader_release(fullA);
+         if (NPRE == 2 && p.expA != nullptr && !skipX) {
+            store_row(x[0], 0, exp_row(item, u, 0), false);
+            store_row(x[NPRE - 1], 1, exp_row(item, u, 1), false);
+         }
          // the next item's rows: in flight during this item's MMAs
          if (it + nPairs < p.nItems) {
             item = p.items[it + nPairs]; u = p.utt[item.x];
@@ -590,7 +610,7 @@ static inline int gmm_tc3_prepare(GmmTc3Model &t, const hfb_model *m, cudaStream
 
 static inline int gmm_tc3_launch(GmmTc3Model &t, GmmTcWork &wk, const DevModel &dm, const Wave &W, long long waveFrames,
                                  const int2 *dItems128, int nItems128, const int2 *dItems4, int nItems4, int smCount,
-                                 cudaStream_t st, int *launches)
+                                 cudaStream_t st, int *launches, bool wantExp = false)
 {
    if (!t.ready) return HFB_EUNSUPPORTED;
    if (nItems4 == 0) return HFB_OK;
@@ -605,10 +625,24 @@ static inline int gmm_tc3_launch(GmmTc3Model &t, GmmTcWork &wk, const DevModel &
    p.items = dItems4; p.nItems = nItems4; p.utt = W.utt; p.slotState = W.slotState;
    p.tileIv = W.tileIv;
    p.feat = W.feat; p.featPad = nullptr; p.offset = t.dOffset; p.scale = t.dScale; p.b = W.b; p.flag = wk.dFlag3;
+   p.expA = nullptr;
+   if (wantExp) {
+      const size_t units = (size_t)4 * ((2 * dm.D + 2 + 15) / 16);          // 16-byte units per row: hi + lo
+      const size_t needU = ((size_t)waveFrames + TC_BM) * units;
+      if (needU > wk.expCap) {
+         if (wk.dExpA) cudaFree(wk.dExpA);
+         wk.dExpA = nullptr; wk.expCap = 0;
+         if (cudaMalloc(&wk.dExpA, (needU + needU / 8) * sizeof(uint4)) != cudaSuccess) { cudaGetLastError(); return HFB_ENOMEM; }
+         wk.expCap = needU + needU / 8;
+      }
+      p.expA = wk.dExpA;
+   }
    int nl = 0;
-   // (experiment, off: measured on config #2 the pre-pass costs what the wider loads save -- 0.47 against 0.42 ms;
-   // what that kernel waits for with one tile per item is the load / store queue, `lg_throttle` in profiles/r2_gmm_tc3_cfg2_raw.txt)
-   if (t.MP == 1 && getenv("HFBGPU_PAD")) {
+   // Single-Gaussian sets: one tile per work item, so the row loads of the expanders are NOT hidden behind MMAs and the
+   // kernel waits for its load / store queue (`lg_throttle`, profiles/r2_gmm_tc3_cfg2_raw.txt).  A pre-pass that scales the
+   // features into 16-byte-aligned rows turns 39 scalar loads per row into ten vector loads: config #2, A/B on one box,
+   // 0.70 ms without it, 0.47-0.48 ms with it (pre-pass included).  HFBGPU_NO_PAD switches it off.
+   if (t.MP == 1 && !getenv("HFBGPU_NO_PAD")) {
       const int DPad = (dm.D <= 40) ? 40 : 64;
       const size_t needPad = ((size_t)waveFrames + TC_BM) * DPad;
       if (needPad > wk.padCap) {

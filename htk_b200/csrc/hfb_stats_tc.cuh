@@ -39,9 +39,15 @@ struct StatsTcParams {
    const unsigned char *flag;        // per frame of the wave: FP16 operands out of range (gmm_tc3)
    const int *overflow;              // != 0: some position did not fit the frame lists -> stats5_kernel does the wave
    const float *offset, *scale;
+   const uint4 *expA;                // PRE: the expanded operand rows gmm_tc3_kernel wrote, [frame of the wave][hi units | lo units]
    float C0;
    int kSteps, N, MP;
 };
+
+__device__ __forceinline__ void st_cp_async16(void *smemDst, const void *gsrc)
+{
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc_smem_u32(smemDst)), "l"(gsrc) : "memory");
+}
 
 __device__ __forceinline__ void st_mma_f16(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
 {
@@ -71,7 +77,11 @@ __device__ __forceinline__ void st_tmem_ld(uint32_t taddr, float *v)
    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int N, int DP>
+// PRE = the rows of a tile are COPIED (cp.async, 16 bytes at a time, straight into the swizzled tile) from the expanded
+// operand gmm_tc3_kernel left in global memory -- bit-identical to what the expansion below produces -- instead of being
+// gathered as raw features and expanded again: the expansion was 35 % of this kernel's instructions and sat at the head
+// of every tile's phase chain.  The copy of the NEXT tile is issued as soon as contraction (2) has released the tile.
+template <int N, int DP, bool PRE>
 __global__ void __launch_bounds__(ST_THREADS, 2)
 stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, DevModel M, Wave W, StatsTcParams p)
 {
@@ -152,7 +162,7 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
          na = nb;
       }
    };
-   float x[DP];                                         // my row of the tile in flight: RAW features (transformed when stored)
+   float x[PRE ? 1 : DP];                               // my row of the tile in flight: RAW features (transformed when stored)
    float px0 = 0.f, px0l = 0.f;                         // initx / log occupancy as hi + lo floats (it can be ~1e6 on outlier frames)
    bool pvalid = false, pfar = false;
    const float *pfrow = nullptr;
@@ -175,18 +185,35 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
    };
    auto fetch_row = [&]() {
       pvalid = nvalid; pfar = false; pfrow = nullptr; px0 = 0.f; px0l = 0.f;
+      if (!PRE) {
 #pragma unroll
-      for (int d = 0; d < DP; d++) x[d] = 0.f;
+         for (int d = 0; d < (PRE ? 1 : DP); d++) x[d] = 0.f;
+      }
       if (pvalid) {
          const ValidFrame vf = nvf;
          const int lo = nlo;
          px0 = (float)vf.x0; px0l = (float)(vf.x0 - (double)px0);
          pfrow = W.feat + ((size_t)pF[lo] + vf.t) * D;
          pfar = p.flag != nullptr && p.flag[pB[lo] + vf.t] != 0;
+         if (PRE) {
+            // rows of invalid tile positions keep whatever finite halfs they held: their Lr is zero in (2), their row of V
+            // is never read; the same holds for a frame outside the FP16 range (its expanded row is clamped, finite)
+            const int nUn = 2 * p.kSteps;
+            const uint4 *src = p.expA + (size_t)(pB[lo] + vf.t) * (size_t)(2 * nUn);
 #pragma unroll
-         for (int d = 0; d < DP; d++)
-            if (d < D) x[d] = pfrow[d];                 // no arithmetic here: the loads stay in flight behind the MMAs
+            for (int un = 0; un < 16; un++) {
+               if (un >= nUn) break;
+               const uint32_t off = tc3_unit_off(tid, un);
+               st_cp_async16(sA + off, src + un);
+               st_cp_async16(sA + 32768 + off, src + nUn + un);
+            }
+         } else {
+#pragma unroll
+            for (int d = 0; d < (PRE ? 1 : DP); d++)
+               if (d < D) x[d] = pfrow[d];              // no arithmetic here: the loads stay in flight behind the MMAs
+         }
       }
+      if (PRE) asm volatile("cp.async.commit_group;" ::: "memory");
    };
    TileAt cur; cur.a = cur.b = cur.t0 = cur.g1 = 0; cur.s = -1; cur.have = false;
    cur = next_tile(cur);
@@ -219,9 +246,14 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
       const float *frow = pfrow;
       const TileAt nxt = next_tile(cur);
       fetch_index(nxt);                                 // frame records of the next tile: in flight during phase A
-      if (worker) {
+      if (PRE) {
+         if (worker) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+         }
+      } else if (worker) {
 #pragma unroll
-         for (int d = 0; d < DP; d++)
+         for (int d = 0; d < (PRE ? 1 : DP); d++)
             if (d < D) {
                // rows of frames outside the FP16 range are zeroed (they are accumulated apart, see the epilogue); every
                // other row is within TC_FAR of the centre by construction of the flags -- without flags (FP32 output
@@ -239,8 +271,8 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
             for (int e = 0; e < 8; e++) {
                const int k = un * 8 + e;
                if (k == 0) v[e] = valid ? 1.f : 0.f;
-               else if (k & 1) { const int d = (k - 1) >> 1; v[e] = (d < DP && d < D) ? x[d < DP ? d : 0] * x[d < DP ? d : 0] : ((d == D && valid) ? 1.f : 0.f); }
-               else { const int d = (k - 2) >> 1; v[e] = (d < DP && d < D) ? x[d < DP ? d : 0] : 0.f; }
+               else if (k & 1) { const int d = (k - 1) >> 1; v[e] = (!PRE && d < DP && d < D) ? x[(!PRE && d < DP) ? d : 0] * x[(!PRE && d < DP) ? d : 0] : ((d == D && valid) ? 1.f : 0.f); }
+               else { const int d = (k - 2) >> 1; v[e] = (!PRE && d < DP && d < D) ? x[(!PRE && d < DP) ? d : 0] : 0.f; }
             }
             uint32_t h4[4], l4[4];
 #pragma unroll
@@ -257,7 +289,7 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
          }
          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
-      fetch_row();                                      // feature rows of the next tile: in flight during (1), its epilogue and (2)
+      if (!PRE) fetch_row();                            // feature rows of the next tile: in flight during (1), its epilogue and (2)
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
@@ -368,6 +400,7 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
          tc_mbar_wait(bar2, ph2);
          ph2 ^= 1;
          tc_fence_after();
+         if (PRE) fetch_row();                          // (2) has read the tile: the next tile's rows start to arrive
          float v[N];
          st_tmem_ld<N>(tD2 + ((uint32_t)(warp * 32) << 16), v);
 #pragma unroll
@@ -426,27 +459,28 @@ static inline bool stats_tc_supported(const GmmTc3Model &t, int D) { return t.re
 
 static inline void stats_tc_set_attributes()
 {
-   cudaFuncSetAttribute(stats_tc_kernel<16, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_tc_smem_bytes<16>());
-   cudaFuncSetAttribute(stats_tc_kernel<16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_tc_smem_bytes<16>());
-   cudaFuncSetAttribute(stats_tc_kernel<32, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_tc_smem_bytes<32>());
-   cudaFuncSetAttribute(stats_tc_kernel<32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_tc_smem_bytes<32>());
+#define ST_SET(NV, DPV) \
+   cudaFuncSetAttribute(stats_tc_kernel<NV, DPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_tc_smem_bytes<NV>()); \
+   cudaFuncSetAttribute(stats_tc_kernel<NV, DPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_tc_smem_bytes<NV>())
+   ST_SET(16, 40); ST_SET(16, 64); ST_SET(32, 40); ST_SET(32, 64);
+#undef ST_SET
 }
 
+// expA: the expanded operand rows of the wave (gmm_tc3_launch with wantExp), or nullptr = gather raw features and expand
 static inline void stats_tc_launch(const GmmTc3Model &t, const DevModel &dm, const Wave &W, const PosRec *list, const int *listEnd,
                                    const ValidFrame *vbuf, const int *vcnt, const unsigned char *flag, const int *overflow,
-                                   long long totalP, cudaStream_t st)
+                                   long long totalP, cudaStream_t st, const uint4 *expA = nullptr)
 {
    StatsTcParams p;
    p.list = list; p.listEnd = listEnd; p.vbuf = vbuf; p.vcnt = vcnt; p.flag = flag; p.overflow = overflow;
    p.offset = t.dOffset; p.scale = t.dScale; p.C0 = t.C0; p.kSteps = (2 * dm.D + 2 + 15) / 16; p.MP = t.MP;
    p.N = (t.MP <= 16) ? 16 : 32;
+   p.expA = expA;
    const unsigned grid = (unsigned)((totalP + ST_CAP - 1) / ST_CAP);
    if (grid == 0) return;
-   if (p.N == 16) {
-      if (dm.D <= 40) stats_tc_kernel<16, 40><<<grid, ST_THREADS, stats_tc_smem_bytes<16>(), st>>>(t.mapBhi, t.mapBlo, dm, W, p);
-      else stats_tc_kernel<16, 64><<<grid, ST_THREADS, stats_tc_smem_bytes<16>(), st>>>(t.mapBhi, t.mapBlo, dm, W, p);
-   } else {
-      if (dm.D <= 40) stats_tc_kernel<32, 40><<<grid, ST_THREADS, stats_tc_smem_bytes<32>(), st>>>(t.mapBhi, t.mapBlo, dm, W, p);
-      else stats_tc_kernel<32, 64><<<grid, ST_THREADS, stats_tc_smem_bytes<32>(), st>>>(t.mapBhi, t.mapBlo, dm, W, p);
-   }
+#define ST_GO(NV, DPV) do { if (expA) stats_tc_kernel<NV, DPV, true><<<grid, ST_THREADS, stats_tc_smem_bytes<NV>(), st>>>(t.mapBhi, t.mapBlo, dm, W, p); \
+                            else stats_tc_kernel<NV, DPV, false><<<grid, ST_THREADS, stats_tc_smem_bytes<NV>(), st>>>(t.mapBhi, t.mapBlo, dm, W, p); } while (0)
+   if (p.N == 16) { if (dm.D <= 40) ST_GO(16, 40); else ST_GO(16, 64); }
+   else { if (dm.D <= 40) ST_GO(32, 40); else ST_GO(32, 64); }
+#undef ST_GO
 }

@@ -829,10 +829,16 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
    // ---- K1
    int gk = c->opt.gmmKernel;
    if (gk == 0) gk = (c->useV3 || gmm_tc_available(c->tc)) ? 2 : 1;
+   // K4 on the tensor cores (decided here: K1 then also leaves every frame's expanded operand row for it)
+   const bool tcStats = !c->upd && c->useV3 && c->opt.gmmKernel != 1 && stats_tc_supported(c->tc3, c->dm.D) && !getenv("HFBGPU_STATS5") &&
+                        !getenv("HFBGPU_NO_STATS_PRE") && c->dm.D + 1 <= 40 && !feat2 && !getenv("HFBGPU_STATS3") && c->opt.uFlags != 0;
+   // (not for single-Gaussian sets: their K1 is bound by its load / store queue and the extra row stores cost it 0.3 ms
+   // on config #2, more than the statistics kernel gains)
+   const bool expRows = tcStats && c->tc3.MP > 1 && !getenv("HFBGPU_NO_EXPA");
    if (gk == 2 && c->useV3) {
       int nl = 0;
       if ((rc = gmm_tc3_launch(c->tc3, S.tcw, c->dm, W, waveFrames, (const int2 *)(base + oIt), (int)w.tcItems.size(),
-                               (const int2 *)(base + oIt4), (int)w.tcItems4.size(), c->smCount, sg, &nl))) return rc;
+                               (const int2 *)(base + oIt4), (int)w.tcItems4.size(), c->smCount, sg, &nl, expRows))) return rc;
       c->stats.launches += nl; c->stats.launchesGmm += nl;
    } else if (gk == 2) {
       int nl = 0;
@@ -932,8 +938,6 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
          const int Dd = c->dm.D;
          // mixture sets: occupancy-weighted sums on the tensor cores (mma.sync 3xTF32); else the FP32 kernel
          // (single-Gaussian sets: only with the tcgen05 kernel, where the sums are one contraction per tile)
-         const bool tcStats = c->useV3 && c->opt.gmmKernel != 1 && stats_tc_supported(c->tc3, Dd) && !getenv("HFBGPU_STATS5") &&
-                              !getenv("HFBGPU_NO_STATS_PRE");
          if ((c->hm.maxM >= 4 || tcStats) && Dd + 1 <= 40 && !W.feat2 && !getenv("HFBGPU_STATS3")) {
             // positions bucketed by tied state (counting sort), then S5_CAP sorted positions per warp
             const int Jm = c->hm.J;
@@ -974,7 +978,8 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
             const int *only = nullptr;
             // (only behind gmm_tc3_kernel: its per-frame flags say which frames are outside the FP16 operand range)
             if (pre && tcStats) {
-               stats_tc_launch(c->tc3, c->dm, W, list, off + Jm, S.dValid.p, vcnt, S.tcw.dFlag3, overflow, w.totalP, st);
+               stats_tc_launch(c->tc3, c->dm, W, list, off + Jm, S.dValid.p, vcnt, S.tcw.dFlag3, overflow, w.totalP, st,
+                               expRows ? S.tcw.dExpA : nullptr);
                c->stats.launches++; c->stats.launchesStats++;
                only = overflow;
             }
