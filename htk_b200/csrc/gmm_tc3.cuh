@@ -56,6 +56,7 @@ struct Tc3Params {
    int kSteps;                 // 16-half K steps that hold data: ceil((2D+2)/16)
    float deadBelow;
    int dbg;
+   long long *trace;           // HFBGPU_TC_TRACE: clock64 stamps of pair 0 (gmm_tc4_kernel), else nullptr
 };
 
 // element (row r, column k) of one 128-row, 128-column FP16 operand block [chunk 0 | chunk 1], each chunk
@@ -608,6 +609,9 @@ static inline int gmm_tc3_prepare(GmmTc3Model &t, const hfb_model *m, cudaStream
    return HFB_OK;
 }
 
+// gmm_tc4.cuh: the same work with the A operand in tensor memory (the default; HFBGPU_GMM_V3 keeps this file's kernel)
+static inline void gmm_tc4_go(const GmmTc3Model &t, const Tc3Params &p, int D, int grid2, cudaStream_t st);
+
 static inline int gmm_tc3_launch(GmmTc3Model &t, GmmTcWork &wk, const DevModel &dm, const Wave &W, long long waveFrames,
                                  const int2 *dItems128, int nItems128, const int2 *dItems4, int nItems4, int smCount,
                                  cudaStream_t st, int *launches, bool wantExp = false)
@@ -657,9 +661,19 @@ static inline int gmm_tc3_launch(GmmTc3Model &t, GmmTcWork &wk, const DevModel &
    }
    p.C0 = t.C0; p.D = dm.D; p.kSteps = (2 * dm.D + 2 + 15) / 16; p.deadBelow = TC_DEAD_BELOW;
    { const char *e = getenv("HFBGPU_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+   p.trace = nullptr;
+   static long long *dTrace = nullptr;
+   if (getenv("HFBGPU_TC_TRACE")) {
+      if (!dTrace) cudaMalloc(&dTrace, 8 * 4096 * sizeof(long long));
+      cudaMemsetAsync(dTrace, 0, 8 * 4096 * sizeof(long long), st);
+      p.trace = dTrace;
+   }
    const int grid2 = 2 * std::min(nItems4, smCount / 2);
 #define TC3_GO(MPV) do { if (dm.D <= 40) gmm_tc3_kernel<MPV, 40><<<grid2, TC3_THREADS, TC3_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p); \
                           else gmm_tc3_kernel<MPV, 64><<<grid2, TC3_THREADS, TC3_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p); } while (0)
+   static const bool ssMode = getenv("HFBGPU_GMM_V3") != nullptr;
+   if (!ssMode) gmm_tc4_go(t, p, dm.D, grid2, st);
+   else
    switch (t.MP) {
    case 1: TC3_GO(1); break;
    case 8: TC3_GO(8); break;
@@ -670,6 +684,18 @@ static inline int gmm_tc3_launch(GmmTc3Model &t, GmmTcWork &wk, const DevModel &
    }
 #undef TC3_GO
    nl += 1;
+   if (p.trace) {                                        // diagnostic: per-block stamps of the MMA thread and of one epilogue warp
+      static int printed = 0;
+      cudaStreamSynchronize(st);
+      if (printed++ == 3) {
+         std::vector<long long> h(8 * 4096);
+         cudaMemcpy(h.data(), dTrace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+         const long long t0 = h[0];
+         for (int i = 40; i < 72; i++)
+            fprintf(stderr, "[tc trace] blk %3d  mma: waitB %6lld  gotEmpty %6lld  issued %6lld | epi(cta0 w2): gotFull %6lld arrived %6lld | epi(cta1 w2): gotFull %6lld arrived %6lld\n", i,
+                    h[8 * i] - t0, h[8 * i + 1] - t0, h[8 * i + 2] - t0, h[8 * i + 3] - t0, h[8 * i + 4] - t0, h[8 * i + 5] - t0, h[8 * i + 6] - t0);
+      }
+   }
    if (!getenv("HFBGPU_NO_FIXUP")) { gmm_fixup_kernel<<<nItems128, 128, 0, st>>>(dm, W, dItems128, wk.dFlag3); nl++; }
    if (launches) *launches = nl;
    return HFB_OK;

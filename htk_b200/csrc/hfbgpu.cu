@@ -26,6 +26,7 @@
 #include "hfb_feat.cuh"
 #include "gmm_tc.cuh"
 #include "gmm_tc3.cuh"
+#include "gmm_tc4.cuh"
 #include "hfb_stats_tc.cuh"
 
 static thread_local std::string g_lastError;
@@ -490,6 +491,7 @@ static int create_one(hfbgpu_ctx **out, const hfb_model *m, const hfb_options *o
    cudaFuncSetAttribute(stats5_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(stats5_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    stats_tc_set_attributes();
+   gmm_tc4_set_attributes();
    CK(cudaStreamSynchronize(c->stream));
    *out = c;
    return HFB_OK;

@@ -21,8 +21,8 @@ __device__ __forceinline__ void mwait(uint64_t *bar, uint32_t parity)
 }
 
 // kind: 0 = tf32, 1 = bf16
-template <int PAIR>
-__global__ void __launch_bounds__(128, 1) rate_kernel(int kind, int N, int reps, int nDist, long long *out)
+template <int PAIR, int ND>
+__global__ void __launch_bounds__(128, 1) rate_kernel(int kind, int N, int reps, int nDist, long long *out, int ats)
 {
    extern __shared__ uint8_t raw[];
    uint8_t *base = (uint8_t *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
@@ -67,7 +67,12 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int kind, int N, int reps,
             for (int j = 0; j < 8; j++) {
                // 8 operand slices in rotation (kk offsets as in a real K loop), two accumulators
                const uint64_t da = sdesc(a0 + (j & 3) * 32 + (j >> 2) * 16384), db = sdesc(b0 + (j & 3) * 32 + (j >> 2) * 16384);
-               const uint32_t d = tmem + (uint32_t)((j & 1) * 256);
+               const uint32_t d = tmem + (uint32_t)(((j / ND) & 1) * (ats ? 128 : 256));   // nDist = MMAs in a row into one accumulator
+               const uint32_t ta = tmem + 384 + (uint32_t)(j * 8);      // A operand in TMEM: K = 16 halfs = 8 columns per MMA
+               if (elected && ats) {
+                  if (PAIR) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(ta), "l"(db), "r"(idesc), "r"(1u) : "memory");
+                  else asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(ta), "l"(db), "r"(idesc), "r"(1u) : "memory");
+               } else
                if (elected) {
                   if (PAIR) {
                      if (kind == 0) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"(1u) : "memory");
@@ -105,27 +110,33 @@ int main()
    long long *d, h[2];
    cudaMalloc(&d, 16);
    const int smem = 200 * 1024, reps = 2000;
-   cudaFuncSetAttribute(rate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-   cudaFuncSetAttribute(rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+   cudaFuncSetAttribute(rate_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+   cudaFuncSetAttribute(rate_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+   cudaFuncSetAttribute(rate_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+   cudaFuncSetAttribute(rate_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
    for (int grid = 148; grid <= 148; grid += 147)
       for (int pair = 0; pair < 2; pair++)
          for (int kind = 0; kind < 2; kind++)
+          for (int ats = 0; ats < 2; ats++)
+           for (int nDist = 1; nDist <= 8; nDist *= 8)
             for (int N = 64; N <= 256; N *= 2) {
-               const int nDist = 8;
+               if (ats && (kind == 0 || N > 128)) continue;
                if (pair) {
                   cudaLaunchConfig_t cfg = {};
                   cfg.gridDim = dim3(grid == 1 ? 2 : 148); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
                   cudaLaunchAttribute at[1];
                   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                   cfg.attrs = at; cfg.numAttrs = 1;
-                  cudaLaunchKernelEx(&cfg, rate_kernel<1>, kind, N, reps, nDist, d);
-               } else rate_kernel<0><<<grid, 128, smem>>>(kind, N, reps, nDist, d);
+                  if (nDist == 1) cudaLaunchKernelEx(&cfg, rate_kernel<1, 1>, kind, N, reps, nDist, d, ats);
+                  else cudaLaunchKernelEx(&cfg, rate_kernel<1, 8>, kind, N, reps, nDist, d, ats);
+               } else if (nDist == 1) rate_kernel<0, 1><<<grid, 128, smem>>>(kind, N, reps, nDist, d, ats);
+               else rate_kernel<0, 8><<<grid, 128, smem>>>(kind, N, reps, nDist, d, ats);
                cudaError_t e = cudaDeviceSynchronize();
                cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
                const int M = pair ? 256 : 128, K = kind == 0 ? 8 : 16;
                const double cyc = (double)h[1] / reps;
-               printf("grid %3d  %s  %s  M=%3d N=%3d K=%2d : issue %.1f cyc/MMA, issue+drain %.1f cyc/MMA -> %.0f MAC/clk/SM  (%s)\n",
-                      grid, pair ? "cta_group::2" : "cta_group::1", kind == 0 ? "tf32" : "bf16", M, N, K, (double)h[0] / reps, cyc,
+               printf("grid %3d  %s  %s  %s  run of %d per accumulator  M=%3d N=%3d K=%2d : issue %.1f cyc/MMA, issue+drain %.1f cyc/MMA -> %.0f MAC/clk/SM  (%s)\n",
+                      grid, pair ? "cta_group::2" : "cta_group::1", kind == 0 ? "tf32" : "bf16", ats ? "A in TMEM" : "A in smem", nDist, M, N, K, (double)h[0] / reps, cyc,
                       (double)(M / (pair ? 2 : 1)) * N * K / cyc, cudaGetErrorString(e));
             }
    return 0;
