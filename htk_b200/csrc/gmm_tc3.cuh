@@ -671,7 +671,7 @@ static inline int gmm_tc3_launch(GmmTc3Model &t, GmmTcWork &wk, const DevModel &
    const int grid2 = 2 * std::min(nItems4, smCount / 2);
 #define TC3_GO(MPV) do { if (dm.D <= 40) gmm_tc3_kernel<MPV, 40><<<grid2, TC3_THREADS, TC3_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p); \
                           else gmm_tc3_kernel<MPV, 64><<<grid2, TC3_THREADS, TC3_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p); } while (0)
-   static const bool ssMode = getenv("HFBGPU_GMM_V3") != nullptr;
+   const bool ssMode = getenv("HFBGPU_GMM_V3") != nullptr;
    if (!ssMode) gmm_tc4_go(t, p, dm.D, grid2, st);
    else
    switch (t.MP) {

@@ -107,15 +107,18 @@ def test_outp_matches_oracle(gmm_kernel):
         fb.close()
 
 
-@pytest.mark.parametrize("variant", ["f16_fused", "f16_pair", "tf32_pair", "tf32_single"])
+@pytest.mark.parametrize("variant", ["f16_tmem", "f16_fused", "f16_pair", "tf32_pair", "tf32_single"])
 def test_outp_tensor_core_variants_on_badly_scaled_features(variant, monkeypatch):
-    """The four tcgen05 GMM kernels (gmm_tc3 = default: fused expansion + taper skipping; CTA pair 3xFP16 with the
+    """The five tcgen05 GMM kernels (gmm_tc4 = default: A operand in tensor memory; gmm_tc3: the same with A in shared
+    memory, both with fused expansion + taper skipping; CTA pair 3xFP16 with the
     pre-expanded operand, CTA pair 3xTF32, single CTA 3xTF32) against a
     float64 evaluation on features whose dimensions span five decades of scale with offsets of hundreds --
     what a real front end delivers; the FP16 split relies on its per-dimension power-of-two scaling here."""
     from htk_b200 import synth
     from htk_b200.flat import flatten
-    if variant == "f16_pair":                      # round-1 kernel: pre-expanded operand in HBM, no taper skipping
+    if variant == "f16_fused":                     # gmm_tc3_kernel: operand A expanded into shared memory
+        monkeypatch.setenv("HFBGPU_GMM_V3", "1")
+    elif variant == "f16_pair":                    # round-1 kernel: pre-expanded operand in HBM, no taper skipping
         monkeypatch.setenv("HFBGPU_GMM_V2", "1")
     elif variant == "tf32_pair":
         monkeypatch.setenv("HFBGPU_TC_TF32", "1")
@@ -577,7 +580,7 @@ def test_taper_skipping_changes_nothing(name, monkeypatch):
     FP64 atomics."""
     z, fm, b, kw = load_golden(name)
     outs = []
-    for env in (None, "HFBGPU_NO_TAPER_SKIP", "HFBGPU_GMM_V2"):
+    for env in (None, "HFBGPU_NO_TAPER_SKIP", "HFBGPU_GMM_V2", "HFBGPU_GMM_V3"):
         if env:
             monkeypatch.setenv(env, "1")
         fb = _fb(fm, **kw)
@@ -586,8 +589,18 @@ def test_taper_skipping_changes_nothing(name, monkeypatch):
         fb.close()
         if env:
             monkeypatch.delenv(env)
-    (r0, b0, a0, p0), (r1, b1, a1, p1), (r2, b2, a2, p2) = outs
+    (r0, b0, a0, p0), (r1, b1, a1, p1), (r2, b2, a2, p2), (r3, b3, a3, p3) = outs
     assert [tuple(r) for r in r0] == [tuple(r) for r in r1]             # bit-identical likelihoods
+    # A in tensor memory (default) vs A in shared memory: the same operands through the same MMAs in the same order; the
+    # epilogues add the 16 exponentials of a state in another order (packed pairs), i.e. log b differs in the last bits
+    assert p0 == p3
+    for x, y in zip(r0, r3):
+        assert (x.status, x.retries, x.pruneThresh) == (y.status, y.retries, y.pruneThresh)
+        assert abs(x.pr - y.pr) <= 1e-7 * abs(y.pr)
+    for k in ("qLo", "qHi", "sq", "eq"):
+        assert np.array_equal(getattr(b0, k), getattr(b3, k))
+    e = acc_errors(a0, a3, fm)
+    assert max(e.values()) < 2e-5, e
     for k in ("qLo", "qHi", "sq", "eq"):
         assert np.array_equal(getattr(b0, k), getattr(b1, k)) and np.array_equal(getattr(b0, k), getattr(b2, k))
     # same b inside the beams -> same posteriors; the statistics kernels sum FP32 fragments in an order that depends on
