@@ -17,6 +17,6 @@ cap() {   # cap <kernel regex> <name> <bench args...>
       rm -f gpurun_out/${tag}_$n.ncu-rep
    fi
 }
-for k in gmm_tc3 stats_tc stats_pre beta_l2r_warp alpha_l2r; do cap ${k}_kernel $k; done
-cap gmm_tc3_kernel gmm_tc3_cfg2 --workload cfg2
+for k in gmm_tc4 stats_tc stats_pre beta_l2r_warp alpha_l2r; do cap ${k}_kernel $k; done
+cap gmm_tc4_kernel gmm_tc4_cfg2 --workload cfg2
 ls -la gpurun_out/
