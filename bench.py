@@ -68,7 +68,9 @@ def gmm_traffic_bytes():
     import glob
     import re
     best = None
-    for f in glob.glob(os.path.join(ROOT, "profiles", "*_gmm_tc*_raw.txt")):
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_gmm_tc*_raw.txt"))):
+        if "cfg" in os.path.basename(f):                 # captures of the other configurations
+            continue
         m = re.match(r"r(\d+)([a-z]*)_", os.path.basename(f))
         key = (int(m.group(1)), m.group(2)) if m else (0, "")
         if best is None or key > best[0]:
@@ -525,7 +527,7 @@ def run_workload(name, args, rank, world, local_rank, dev, K, full):
         rl = {}
         if ms_gemm > 0:
             ach = gmm_flop / (ms_gemm * 1e-3) / 1e12
-            rl["gmm"] = {"bound": "tensor", "kernel": "gmm_tc2_kernel (tcgen05 cta_group::2, 3xFP16 split, FP32 accumulate in TMEM)",
+            rl["gmm"] = {"bound": "tensor", "kernel": "gmm_tc4_kernel (tcgen05 cta_group::2, A operand in tensor memory, 3xFP16 split, FP32 accumulate in TMEM)",
                          "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"],
                          "traffic": traffic if (name == "cfg3" and n_utts == 1024) else None, "traffic_source": traffic_src,
                          "ms_per_launch": ms_gemm, "launches_per_step": 1,
@@ -536,11 +538,12 @@ def run_workload(name, args, rank, world, local_rank, dev, K, full):
                          "note": "algorithmic FLOP = sum over frames of the DISTINCT tied states among the beta cells x M x 2(2D+1) "
                                  "(SURVEY 8d; counted on the host from the returned beams), one launch per step; pairs_computed = "
                                  "what the kernel evaluated; peak = bf16 %s (%s); every product costs 3 FP16 MMAs (hi*hi + hi*lo "
-                                 "+ lo*hi), so the ceiling of this kernel is peak / 3 -- frac_of_peak_over_3" % ("sustained", peaks["src"])}
+                                 "+ lo*hi), so the ceiling of this kernel is peak / 3 -- frac_of_peak_over_3; the launch runs at the board's power "
+                                 "cap (tensor pipe saturated at ~1.0 GHz without the epilogue arithmetic, profiles/README.md r2b)" % ("sustained", peaks["src"])}
         st_flop = alpha_cells * 3 * M * 2 * 2 * fm.D            # F_acc = sum over alpha cells (N-2) M 2 2D
         if kms["stats"] > 0:
             ach = st_flop / (kms["stats"] * 1e-3) / 1e12
-            rl["stats"] = {"bound": "tensor", "kernel": "stats_pre_kernel + stats5_kernel + statpos_* sort",
+            rl["stats"] = {"bound": "tensor", "kernel": "stats_pre_kernel + stats_tc_kernel (tcgen05) + statpos_* sort",
                            "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"], "traffic": None,
                            "ms_per_launch": kms["stats"], "launches_per_step": 5,
                            "note": "SURVEY 8d: F_acc = alpha cells x (N-2) x M x 4D algorithmic FLOP = %.1f GFLOP per step (the "
