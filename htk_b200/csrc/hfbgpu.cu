@@ -865,7 +865,10 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
       // (Round 2, measured in timing mode: alpha_l2r_kernel on a second stream WHILE gmm_tc4_kernel runs -- what a
       // software pipeline "alpha of wave w under the GMM of wave w + 1" would do -- takes 3.99 ms for the pair against
       // 2.03 + 0.77 one after the other: next to the 448-thread GMM CTA only four alpha warps fit an SM and they share
-      // its issue slots and its power budget.  The waves stay on their own streams.)
+      // its issue slots and its power budget.  Likewise alpha of one wave next to the beta pass of another, beta capped
+      // at 6 warps per SM so that both fit: 3.05 ms for the pair against 1.08 + 0.76, with or without a common
+      // shared-memory carve-out -- two latency-bound kernels that stream 5 GB between them lengthen each other's
+      // dependent loads.  The waves stay on their own streams.)
       cudaStream_t sr = (!tm && S.recStream && getenv("HFBGPU_REC_STREAM")) ? S.recStream : st;
       if (sr != st) { CK(cudaEventRecord(S.evIn, st)); CK(cudaStreamWaitEvent(sr, S.evIn, 0)); }
       int nt = std::min(256, std::max(32, (w.maxQ + 31) & ~31));
