@@ -61,6 +61,15 @@ __device__ __forceinline__ uint64_t st_desc_mn(uint32_t smemAddr, uint32_t lboBy
    return (uint64_t)((smemAddr >> 4) & 0x3FFF) | ((uint64_t)((lboBytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sboBytes >> 4) & 0x3FFF) << 32) |
           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// operand tile WITHOUT swizzle ("interleaved" canonical layout): core matrices of 8 rows x 16 bytes stored as 128 contiguous
+// bytes; `lbo` / `sbo` = byte strides between core matrices along the two tile dimensions (which is which depends on the
+// major-ness, see the call sites); bit 46 = descriptor version, swizzle field 0
+__device__ __forceinline__ uint64_t st_desc_ns(uint32_t smemAddr, uint32_t lboBytes, uint32_t sboBytes, bool mnMajor)
+{
+   (void)mnMajor;
+   return (uint64_t)((smemAddr >> 4) & 0x3FFF) | ((uint64_t)((lboBytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sboBytes >> 4) & 0x3FFF) << 32) |
+          ((uint64_t)1 << 46);
+}
 template <int NC>
 __device__ __forceinline__ void st_tmem_ld(uint32_t taddr, float *v)
 {
@@ -81,8 +90,13 @@ __device__ __forceinline__ void st_tmem_ld(uint32_t taddr, float *v)
 // operand gmm_tc3_kernel left in global memory -- bit-identical to what the expansion below produces -- instead of being
 // gathered as raw features and expanded again: the expansion was 35 % of this kernel's instructions and sat at the head
 // of every tile's phase chain.  The copy of the NEXT tile is issued as soon as contraction (2) has released the tile.
-template <int N, int DP, bool PRE>
-__global__ void __launch_bounds__(ST_THREADS, 2)
+// NSW (with PRE) = the tile is stored WITHOUT swizzle and without the padding of the 128-byte-swizzled form: per group of 8
+// rows the 2 kSteps core matrices (8 rows x 8 columns, 128 contiguous bytes) that exist, one after the other -- 40 KB
+// instead of 64 KB for D = 39, so that THREE CTAs fit an SM (the kernel is bound by the latency of its per-tile phase chain).
+// The same bytes serve both contractions: a core matrix read K-major is 8 frames x 8 columns, read MN-major it is 8 columns
+// (MN) x 8 frames (K).
+template <int N, int DP, bool PRE, bool NSW>
+__global__ void __launch_bounds__(ST_THREADS, NSW ? 3 : 2)
 stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, DevModel M, Wave W, StatsTcParams p)
 {
    extern __shared__ uint8_t st_smem_raw[];
@@ -92,7 +106,10 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
    if (i0 >= i1) return;
    uint8_t *base = (uint8_t *)(((uintptr_t)st_smem_raw + 1023) & ~(uintptr_t)1023);
    uint8_t *sA = base;                                  // [hi c0 | hi c1 | lo c0 | lo c1] x 16 KB: 128 rows x 128 columns
-   uint8_t *sB1 = sA + 65536;                           // the state's Gaussians: [hi c0 | hi c1 | lo c0 | lo c1] x N x 128 B
+   const uint32_t GS = 2u * (uint32_t)p.kSteps * 128u;  // NSW: bytes of one group of 8 rows (2 kSteps core matrices)
+   const uint32_t HALF = NSW ? 16u * GS : 32768u;       // bytes of the hi (or lo) part of the tile
+   const uint32_t TILE = NSW ? ((2u * HALF + 1023u) & ~1023u) : 65536u;
+   uint8_t *sB1 = sA + TILE;                            // the state's Gaussians: [hi c0 | hi c1 | lo c0 | lo c1] x N x 128 B
    uint8_t *sB2 = sB1 + 4 * N * 128;                    // Lr: [hi f0-63 | hi f64-127 | lo .. | lo ..] x N x 128 B
    float *stage = (float *)sB2;                         // [128][N] flush staging: Lr is dead when a state is flushed
    int *pre = (int *)(sB2 + 4 * N * 128);               // [ST_CAP + 1] prefix sums of the positions' frame counts
@@ -126,7 +143,7 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
       if (it < i1) { pV[k] = p.list[it].vOff; pF[k] = p.list[it].featOff; pB[k] = p.list[it].frameBase; }
    }
    if (tid < 64) sXf[tid] = (tid < D) ? make_float2(p.scale[tid], -p.offset[tid] * p.scale[tid]) : make_float2(0.f, 0.f);
-   for (uint32_t o = tid * 16; o < 65536; o += ST_THREADS * 16) *reinterpret_cast<uint4 *>(sA + o) = make_uint4(0u, 0u, 0u, 0u);
+   for (uint32_t o = tid * 16; o < TILE; o += ST_THREADS * 16) *reinterpret_cast<uint4 *>(sA + o) = make_uint4(0u, 0u, 0u, 0u);
    tc_fence_before();
    __syncthreads();
    tc_fence_after();
@@ -203,9 +220,9 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
 #pragma unroll
             for (int un = 0; un < 16; un++) {
                if (un >= nUn) break;
-               const uint32_t off = tc3_unit_off(tid, un);
+               const uint32_t off = NSW ? (uint32_t)(tid >> 3) * GS + (uint32_t)un * 128u + (uint32_t)(tid & 7) * 16u : tc3_unit_off(tid, un);
                st_cp_async16(sA + off, src + un);
-               st_cp_async16(sA + 32768 + off, src + nUn + un);
+               st_cp_async16(sA + HALF + off, src + nUn + un);
             }
          } else {
 #pragma unroll
@@ -298,14 +315,20 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
          if (first) { tc_mbar_wait(barB, phB); phB ^= 1; tc_fence_after(); }
          if (lane == 0) {
             const uint32_t aB = tc_smem_u32(sA), bB = tc_smem_u32(sB1);
+            // A slice of K step ks: swizzled tile = 32 bytes further inside the 128-byte rows of chunk ks / 4; compact tile =
+            // two core matrices further (K-major, no swizzle: 128 bytes between core matrices along K, GS between row groups)
+            auto adesc1 = [&](uint32_t part, int ks) -> uint64_t {
+               if (NSW) return st_desc_ns(aB + part * HALF + ks * 256, 128, GS, false);
+               return tc_smem_desc(aB + part * 32768 + (ks >> 2) * 16384 + (ks & 3) * 32);
+            };
             for (int ks = 0; ks < p.kSteps; ks++) {              // corrections first (see gmm_tc3_kernel)
-               const uint32_t oa = (ks >> 2) * 16384 + (ks & 3) * 32, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
-               st_mma_f16(tD1, tc_smem_desc(aB + oa), tc_smem_desc(bB + 2 * N * 128 + ob), idesc1, ks ? 1u : 0u);
-               st_mma_f16(tD1, tc_smem_desc(aB + 32768 + oa), tc_smem_desc(bB + ob), idesc1, 1u);
+               const uint32_t ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
+               st_mma_f16(tD1, adesc1(0, ks), tc_smem_desc(bB + 2 * N * 128 + ob), idesc1, ks ? 1u : 0u);
+               st_mma_f16(tD1, adesc1(1, ks), tc_smem_desc(bB + ob), idesc1, 1u);
             }
             for (int ks = 0; ks < p.kSteps; ks++) {
-               const uint32_t oa = (ks >> 2) * 16384 + (ks & 3) * 32, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
-               st_mma_f16(tD1, tc_smem_desc(aB + oa), tc_smem_desc(bB + ob), idesc1, 1u);
+               const uint32_t ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
+               st_mma_f16(tD1, adesc1(0, ks), tc_smem_desc(bB + ob), idesc1, 1u);
             }
             tc_commit(bar1);
          }
@@ -383,14 +406,23 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
       if (warp == 4) {
          if (lane == 0) {
             const uint32_t aB = tc_smem_u32(sA), bB = tc_smem_u32(sB2);
+            // the transposed tile, 16 frames (K) per step: swizzled = 16 rows of 128 bytes further; compact = two row groups
+            // further (MN-major, no swizzle: the descriptor's "leading" stride is the one along K = frames here, GS, and its
+            // "stride" field the 128 bytes between core matrices along MN = operand columns -- found by trying both on the
+            // golden fixtures; operand columns past 16 kSteps read the next group's bytes -- finite halfs -- into rows of S
+            // nobody uses)
+            auto adesc2 = [&](uint32_t part, int ks) -> uint64_t {
+               if (NSW) return st_desc_ns(aB + part * HALF + ks * 2 * GS, GS, 128, true);
+               return st_desc_mn(aB + part * 32768 + ks * 2048, 16384, 1024);
+            };
             for (int ks = 0; ks < 8; ks++) {                    // 16 frames per step
-               const uint32_t oa = ks * 2048, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
-               st_mma_f16(tD2, st_desc_mn(aB + oa, 16384, 1024), tc_smem_desc(bB + 2 * N * 128 + ob), idesc2, ks ? 1u : 0u);
-               st_mma_f16(tD2, st_desc_mn(aB + 32768 + oa, 16384, 1024), tc_smem_desc(bB + ob), idesc2, 1u);
+               const uint32_t ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
+               st_mma_f16(tD2, adesc2(0, ks), tc_smem_desc(bB + 2 * N * 128 + ob), idesc2, ks ? 1u : 0u);
+               st_mma_f16(tD2, adesc2(1, ks), tc_smem_desc(bB + ob), idesc2, 1u);
             }
             for (int ks = 0; ks < 8; ks++) {
-               const uint32_t oa = ks * 2048, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
-               st_mma_f16(tD2, st_desc_mn(aB + oa, 16384, 1024), tc_smem_desc(bB + ob), idesc2, 1u);
+               const uint32_t ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
+               st_mma_f16(tD2, adesc2(0, ks), tc_smem_desc(bB + ob), idesc2, 1u);
             }
             tc_commit(bar2);
          }
@@ -452,7 +484,11 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constan
 }
 
 template <int N>
-static inline size_t stats_tc_smem_bytes() { return 1024 + 65536 + 8 * N * 128 + sizeof(int) * (3 * ST_CAP + 1) + 8 + 512 + 16 + 3 * 8 * ST_CAP + 128; }
+static inline size_t stats_tc_smem_bytes(int kSteps = 0)   // kSteps > 0: the compact (no-swizzle) tile
+{
+   const size_t tile = kSteps > 0 ? (((size_t)2 * 16 * 2 * kSteps * 128 + 1023) & ~(size_t)1023) : 65536;
+   return 1024 + tile + 8 * N * 128 + sizeof(int) * (3 * ST_CAP + 1) + 8 + 512 + 16 + 3 * 8 * ST_CAP + 128;
+}
 
 // Launch: returns false when the model is outside what the kernel covers (the caller keeps stats5_kernel).
 static inline bool stats_tc_supported(const GmmTc3Model &t, int D) { return t.ready && (t.MP == 1 || t.MP == 8 || t.MP == 16 || t.MP == 32) && D <= 63; }
@@ -460,8 +496,9 @@ static inline bool stats_tc_supported(const GmmTc3Model &t, int D) { return t.re
 static inline void stats_tc_set_attributes()
 {
 #define ST_SET(NV, DPV) \
-   cudaFuncSetAttribute(stats_tc_kernel<NV, DPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_tc_smem_bytes<NV>()); \
-   cudaFuncSetAttribute(stats_tc_kernel<NV, DPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_tc_smem_bytes<NV>())
+   cudaFuncSetAttribute(stats_tc_kernel<NV, DPV, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_tc_smem_bytes<NV>()); \
+   cudaFuncSetAttribute(stats_tc_kernel<NV, DPV, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_tc_smem_bytes<NV>()); \
+   cudaFuncSetAttribute(stats_tc_kernel<NV, DPV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stats_tc_smem_bytes<NV>())
    ST_SET(16, 40); ST_SET(16, 64); ST_SET(32, 40); ST_SET(32, 64);
 #undef ST_SET
 }
@@ -478,8 +515,13 @@ static inline void stats_tc_launch(const GmmTc3Model &t, const DevModel &dm, con
    p.expA = expA;
    const unsigned grid = (unsigned)((totalP + ST_CAP - 1) / ST_CAP);
    if (grid == 0) return;
-#define ST_GO(NV, DPV) do { if (expA) stats_tc_kernel<NV, DPV, true><<<grid, ST_THREADS, stats_tc_smem_bytes<NV>(), st>>>(t.mapBhi, t.mapBlo, dm, W, p); \
-                            else stats_tc_kernel<NV, DPV, false><<<grid, ST_THREADS, stats_tc_smem_bytes<NV>(), st>>>(t.mapBhi, t.mapBlo, dm, W, p); } while (0)
+   // the compact tile pays when it lets a third CTA onto the SM: K steps <= 6 and 16 components per tile (with 32 the two
+   // B operands take 32 KB and three CTAs miss the SM's shared memory by 1 KB: measured 2.16 against 2.03 ms on config #4)
+   const bool ns = expA != nullptr && p.kSteps <= 6 && p.N == 16 && !getenv("HFBGPU_ST_SWZ");
+#define ST_GO(NV, DPV) do { \
+      if (ns) stats_tc_kernel<NV, DPV, true, true><<<grid, ST_THREADS, stats_tc_smem_bytes<NV>(p.kSteps), st>>>(t.mapBhi, t.mapBlo, dm, W, p); \
+      else if (expA) stats_tc_kernel<NV, DPV, true, false><<<grid, ST_THREADS, stats_tc_smem_bytes<NV>(), st>>>(t.mapBhi, t.mapBlo, dm, W, p); \
+      else stats_tc_kernel<NV, DPV, false, false><<<grid, ST_THREADS, stats_tc_smem_bytes<NV>(), st>>>(t.mapBhi, t.mapBlo, dm, W, p); } while (0)
    if (p.N == 16) { if (dm.D <= 40) ST_GO(16, 40); else ST_GO(16, 64); }
    else { if (dm.D <= 40) ST_GO(32, 40); else ST_GO(32, 64); }
 #undef ST_GO

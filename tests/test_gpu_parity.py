@@ -656,11 +656,13 @@ def test_ring_window_beta_equals_sliding_block_kernel(monkeypatch):
 @pytest.mark.parametrize("name", ["synth_tied_m4", "synth_long_m3", "synth_tee_m2"])
 def test_tcgen05_statistics_equal_mma_sync_statistics(name, monkeypatch):
     """K4 on tcgen05 (hfb_stats_tc.cuh: component posteriors and occupancy-weighted sums as two UMMA contractions per
-    tied state, the default) against stats5_kernel (FP32 posteriors + mma.sync sums, HFBGPU_STATS5) and the per-position
-    FP32 kernel (HFBGPU_STATS3); all three against the oracle elsewhere."""
+    tied state, the default: rows copied from K1's expanded operand into the compact, unswizzled tile) against its
+    other forms -- 128-byte-swizzled tile (HFBGPU_ST_SWZ), rows expanded by the kernel itself (HFBGPU_NO_EXPA) --,
+    stats5_kernel (FP32 posteriors + mma.sync sums, HFBGPU_STATS5) and the per-position FP32 kernel (HFBGPU_STATS3);
+    all against the oracle elsewhere."""
     z, fm, b, kw = load_golden(name)
     outs = []
-    for env in (None, "HFBGPU_STATS5", "HFBGPU_STATS3"):
+    for env in (None, "HFBGPU_ST_SWZ", "HFBGPU_NO_EXPA", "HFBGPU_STATS5", "HFBGPU_STATS3"):
         if env:
             monkeypatch.setenv(env, "1")
         fb = _fb(fm, **kw)
