@@ -469,15 +469,20 @@ gmm_tc3_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant
 
 // Scaled, clamped copy of the wave's features with rows padded to DP floats (16-byte aligned) + the per-frame flags;
 // only for sets with one K1 tile per work item (single-Gaussian sets), see load_row above.
+// expA != nullptr: also every frame's expanded operand row ([hi units | lo units], as the expanders of the GMM kernels
+// build it) for the statistics kernel -- written here, by a streaming kernel, because the single-Gaussian GMM kernel is
+// bound by its load / store queue.
 __global__ void __launch_bounds__(256)
 gmm_tc3_pad_kernel(const float *__restrict__ feat, const float *__restrict__ offset, const float *__restrict__ scale,
-                   int D, int DPad, long long nFrames, float *__restrict__ out, unsigned char *__restrict__ flag)
+                   int D, int DPad, long long nFrames, float *__restrict__ out, unsigned char *__restrict__ flag,
+                   uint4 *__restrict__ expA, int kSteps)
 {
    const int lane = threadIdx.x & 31;
    const long long f = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);     // one warp per frame
    if (f >= nFrames) return;
    bool far = false;
-   for (int d = lane; d < DPad; d += 32) {
+   float v01[2] = {0.f, 0.f};                                              // dimensions lane and lane + 32
+   for (int d = lane, i = 0; d < DPad; d += 32, i++) {
       float v = 0.f;
       if (d < D) {
          v = (feat[f * D + d] - offset[d]) * scale[d];
@@ -485,9 +490,40 @@ gmm_tc3_pad_kernel(const float *__restrict__ feat, const float *__restrict__ off
          v = fminf(fmaxf(v, -250.f), 250.f);
       }
       out[f * DPad + d] = v;
+      v01[i] = v;
    }
    far = __any_sync(0xffffffffu, far);
    if (lane == 0) flag[f] = far ? 1 : 0;
+   if (expA != nullptr) {
+      // lane un < 2 kSteps builds unit un = operand columns 8 un .. 8 un + 7: column 0 = 1, 2d+1 = x'_d^2, 2d+2 = x'_d, 2D+1 = 1
+      const int nUn = 2 * kSteps, un = (lane < nUn) ? lane : 0;
+      float c[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+         const int k = 8 * un + e;
+         const int d = (k & 1) ? (k - 1) >> 1 : (k - 2) >> 1;
+         const int dd = (d >= 0 && d < D) ? d : 0;
+         const float a = __shfl_sync(0xffffffffu, v01[0], dd & 31), b = __shfl_sync(0xffffffffu, v01[1], dd & 31);
+         const float x = (dd >= 32) ? b : a;
+         if (k == 0) c[e] = 1.f;
+         else if (k & 1) c[e] = (d < D) ? x * x : ((d == D) ? 1.f : 0.f);
+         else c[e] = (d >= 0 && d < D) ? x : 0.f;
+      }
+      if (lane < nUn) {
+         uint32_t hi[4], lo[4];
+#pragma unroll
+         for (int e = 0; e < 4; e++) {
+            const __half2 h = __floats2half2_rn(c[2 * e], c[2 * e + 1]);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(c[2 * e] - hf.x, c[2 * e + 1] - hf.y);
+            hi[e] = *reinterpret_cast<const uint32_t *>(&h);
+            lo[e] = *reinterpret_cast<const uint32_t *>(&l);
+         }
+         uint4 *row = expA + (size_t)f * (size_t)(2 * nUn);
+         row[lane] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+         row[nUn + lane] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+   }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -655,8 +691,10 @@ static inline int gmm_tc3_launch(GmmTc3Model &t, GmmTcWork &wk, const DevModel &
          if (cudaMalloc(&wk.dPad, (needPad + needPad / 8) * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return HFB_ENOMEM; }
          wk.padCap = needPad + needPad / 8;
       }
-      gmm_tc3_pad_kernel<<<(unsigned)((waveFrames + 7) / 8), 256, 0, st>>>(W.feat, t.dOffset, t.dScale, dm.D, DPad, waveFrames, wk.dPad, wk.dFlag3);
+      gmm_tc3_pad_kernel<<<(unsigned)((waveFrames + 7) / 8), 256, 0, st>>>(W.feat, t.dOffset, t.dScale, dm.D, DPad, waveFrames, wk.dPad, wk.dFlag3,
+                                                                            p.expA, (2 * dm.D + 2 + 15) / 16);
       p.featPad = wk.dPad;
+      p.expA = nullptr;                                  // written by the pre-pass, not by the GMM kernel
       nl++;
    }
    p.C0 = t.C0; p.D = dm.D; p.kSteps = (2 * dm.D + 2 + 15) / 16; p.deadBelow = TC_DEAD_BELOW;

@@ -834,9 +834,9 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
    // K4 on the tensor cores (decided here: K1 then also leaves every frame's expanded operand row for it)
    const bool tcStats = !c->upd && c->useV3 && c->opt.gmmKernel != 1 && stats_tc_supported(c->tc3, c->dm.D) && !getenv("HFBGPU_STATS5") &&
                         !getenv("HFBGPU_NO_STATS_PRE") && c->dm.D + 1 <= 40 && !feat2 && !getenv("HFBGPU_STATS3") && c->opt.uFlags != 0;
-   // (not for single-Gaussian sets: their K1 is bound by its load / store queue and the extra row stores cost it 0.3 ms
-   // on config #2, more than the statistics kernel gains)
-   const bool expRows = tcStats && c->tc3.MP > 1 && !getenv("HFBGPU_NO_EXPA");
+   // (single-Gaussian sets: their K1 is bound by its load / store queue and the extra row stores cost it 0.3 ms on config #2,
+   // more than the statistics kernel gains -- there the padded pre-pass, a streaming kernel, writes the rows)
+   const bool expRows = tcStats && (c->tc3.MP > 1 || !getenv("HFBGPU_NO_PAD")) && !getenv("HFBGPU_NO_EXPA");
    if (gk == 2 && c->useV3) {
       int nl = 0;
       if ((rc = gmm_tc3_launch(c->tc3, S.tcw, c->dm, W, waveFrames, (const int2 *)(base + oIt), (int)w.tcItems.size(),
