@@ -109,7 +109,7 @@ typedef struct hfb_options {
    float   minFrwdP;             /* default 10.0 (HFB.c:83)                          */
    int32_t uFlags;               /* HFB_UP* mask                                     */
    int32_t device;               /* CUDA device ordinal                              */
-   int32_t gmmKernel;            /* 0 = auto, 1 = FP32 CUDA-core, 2 = tcgen05 3xTF32 */
+   int32_t gmmKernel;            /* 0 = auto, 1 = FP32 CUDA-core, 2 = tcgen05 (3xFP16) */
    int32_t reserved0;
    size_t  workspaceBytes;       /* 0 = default; cap for per-wave beta/outprob pool  */
    /* Two-model re-estimation (UseAlignHMMSet, HFB.c:296-333; HERest ALIGNMODELMMF / ALIGNHMMLIST,
