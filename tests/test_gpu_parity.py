@@ -353,6 +353,13 @@ def test_statistics_front_kernel_equals_inline_front(name, cap, monkeypatch):
     dict(D=39, M=20, parm="MFCC_0_D_A"),                    # two 16-component tiles in the statistics kernel, MP = 32
     dict(D=26, M=5, parm="MFCC_E_D"),                       # 7 of 12 K steps, 4 right-hand-side tiles
     dict(D=13, M=4, parm="MFCC_0"),                         # one K chunk
+    # MP = 64: a state spans two 32-column chunks of the K1 epilogue (carry).  2 400 Gaussians on 6 utterances: the centred
+    # first-order sums of the barely occupied ones sit at 0.8-1.0e-4 from the FP64 oracle with EVERY kernel combination
+    # (FP32 CUDA-core GMM 8.2e-5, round-1 tensor-core kernel 9.8e-5, FP32 statistics kernel 1.0e-4) -- the
+    # cancellation SURVEY 8a warns about, not a kernel's rounding -- hence the wider bound on that block alone
+    dict(D=39, M=40, parm="MFCC_0_D_A", tol_centred=2e-4),
+    dict(D=63, M=4, parm="USER"),                           # 8 K steps: the A operand fills all 256 TMEM columns left of the accumulators
+    dict(D=50, M=1, parm="USER"),                           # single-Gaussian set on the wide (DP = 64) kernel variants
 ])
 def test_model_shapes_against_oracle(shape):
     """Kernel template / tiling variants the golden fixtures do not reach, against the C oracle."""
@@ -376,7 +383,8 @@ def test_model_shapes_against_oracle(shape):
     for k in ("qLo", "qHi", "sq", "eq"):
         assert np.array_equal(getattr(beams, k), getattr(obeams, k)), k
     e = acc_errors(acc, oacc, fm)
-    assert max(e.values()) < RTOL, e
+    for k, v in e.items():
+        assert v < (shape.get("tol_centred", RTOL) if k in ("muSum", "vaSum") else RTOL), (k, v, e)
 
 
 def test_shared_variance_vectors_against_oracle():
