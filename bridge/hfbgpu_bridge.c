@@ -373,7 +373,7 @@ void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pr
       if (!B.alHset->logWt) HError(7399, "hfbgpu bridge: expected log weights in the alignment set (ConvLogWt)");
       nParm = GetConfig("HFB", TRUE, cParm, MAXGLOBS);
       if (nParm > 0 && GetConfBool(cParm, nParm, "ALIGNCOMPLEVEL", &bv) && bv)
-         HError(7399, "hfbgpu bridge: ALIGNCOMPLEVEL (HFB.c:1521-1530) is not accelerated");
+         opt.flags |= HFB_OPT_ALIGN_COMP_LEVEL;          /* HFB.c:231, :1521-1530: posteriors from the alignment set's components */
       Flatten(B.alHset, &B.a);
       opt.alignModel = &B.a.m;
    }

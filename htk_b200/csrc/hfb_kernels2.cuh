@@ -469,6 +469,8 @@ stats3_kernel(DevModel M, Wave W)
 //    norm         = LAdd over m of comp_prob[m]                      rounded to float after every LAdd
 //    x            = comp_prob[m] + alpha_j(t) + beta_j(t) - pr - norm   (M = 1: alpha_j + beta_j - pr)
 //    kept if wght_m > LMINMIX and -x < minFrwdP; Lr = exp(x) goes into U's accumulators, sums centred on U's means.
+// compLevel (HFB: ALIGNCOMPLEVEL = T, :1521-1530): comp_prob / norm are those of A's state at the position instead (same
+// number of components, checked when the batch is submitted); what is kept and where it goes stays U's.
 // Transition statistics do not exist in this mode (HFB.c:313-316); numEgs counts U's physical HMMs (:1768-1772).
 // Not a bench path: FP32 CUDA cores, the reference's own evaluation order.
 // ------------------------------------------------------------------------------------------
@@ -478,7 +480,7 @@ __host__ __device__ inline size_t stats_two_smem_bytes(int D)
 }
 
 __global__ void __launch_bounds__(32 * ST_WARPS)
-stats_two_kernel(DevModel A, DevModel U, Wave W, const int *__restrict__ labUp)
+stats_two_kernel(DevModel A, DevModel U, Wave W, const int *__restrict__ labUp, int compLevel)
 {
    extern __shared__ __align__(16) unsigned char smraw[];
    const int wInB = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -517,16 +519,20 @@ stats_two_kernel(DevModel A, DevModel U, Wave W, const int *__restrict__ labUp)
    const double pr = W.out[ui].pr, minF = W.minFrwdP;
    const int k0 = lane, k1 = lane + 32;                // D <= 64 (checked at create)
    double wsum = 0.0;
+   // the set whose components give comp_prob / norm: U's state, or (ALIGNCOMPLEVEL) A's state at this position
+   const DevModel &C = compLevel ? A : U;
+   const int cmo = compLevel ? A.stateMixOff[W.posState[u.posOff + lp]] : mo;
+   const int CDp = C.Dp;
 
    auto comp_prob = [&](int m, const float *o) -> float {          // wght + MOutP, HFB.c:1544-1545 (IDOutP: HModel.c:5420-5431)
-      const int g = U.mixGauss[mo + m];
-      const float *mu = U.mean + (size_t)g * Dp, *iv = U.ivar + (size_t)g * Dp;
-      float sum = U.gconst[g];
+      const int g = C.mixGauss[cmo + m];
+      const float *mu = C.mean + (size_t)g * CDp, *iv = C.ivar + (size_t)g * CDp;
+      float sum = C.gconst[g];
       for (int k = 0; k < D; k++) {
          const float d = __fsub_rn(o[k], mu[k]);
          sum = __fadd_rn(sum, __fmul_rn(__fmul_rn(d, d), iv[k]));
       }
-      return __fadd_rn(U.mixLogWt[mo + m], -0.5f * sum);
+      return __fadd_rn(C.mixLogWt[cmo + m], -0.5f * sum);
    };
 
    for (int t0 = tmin; t0 <= tmax; t0 += 32) {

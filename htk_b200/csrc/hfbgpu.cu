@@ -940,7 +940,7 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
          // two-model re-estimation: statistics of the update set from this set's alignment (hfb_kernels2.cuh)
          if (w.totalP > 0) {
             stats_two_kernel<<<(unsigned)((w.totalP + ST_WARPS - 1) / ST_WARPS), 32 * ST_WARPS, stats_two_smem_bytes(c->dm.D), st>>>(
-               c->dm, c->upd->dm, W, (const int *)(base + oLabUp));
+               c->dm, c->upd->dm, W, (const int *)(base + oLabUp), (c->opt.flags & HFB_OPT_ALIGN_COMP_LEVEL) ? 1 : 0);
             c->stats.launches++; c->stats.launchesStats++;
          }
       } else if (w.totalP > 0 && c->opt.uFlags != 0) {
@@ -1112,6 +1112,14 @@ static int submit_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, c
          if (pa >= 0 && pa < h.P && h.hmmN[pa] != hu.hmmN[pu]) {
             g_lastError = "Num states differ in align and update models (HError 999, HFB.c:549-551)"; return HFB_EINVAL;
          }
+         if ((c->opt.flags & HFB_OPT_ALIGN_COMP_LEVEL) && pa >= 0 && pa < h.P)
+            for (int j = 0; j < h.hmmN[pa] - 2; j++) {
+               const int sa = h.hmmState[h.hmmStateOff[pa] + j], su = hu.hmmState[hu.hmmStateOff[pu] + j];
+               if (h.stateMixOff[sa + 1] - h.stateMixOff[sa] != hu.stateMixOff[su + 1] - hu.stateMixOff[su]) {
+                  g_lastError = "Cannot align at the component level if number of components is different (HError 999, HFB.c:1523-1524)";
+                  return HFB_EINVAL;
+               }
+            }
       }
    }
    // validated for the WHOLE batch before anything is launched: a rejected batch leaves the accumulators untouched

@@ -40,14 +40,15 @@ class _Ticket:
 
 class ForwardBackward:
     def __init__(self, fm: FlatModel, prune=None, min_frwd_p: float = 10.0, uflags: int = 15,
-                 device: int = 0, gmm_kernel: int = 0, workspace_bytes: int = 0, devices=None, align_model=None):
+                 device: int = 0, gmm_kernel: int = 0, workspace_bytes: int = 0, devices=None, align_model=None,
+                 align_comp_level: bool = False):
         """`devices`: list of CUDA ordinals -> one context driving all of them (hfbgpu_create_multi).
         `align_model`: a FlatModel = two-model re-estimation (UseAlignHMMSet, HFB.c:296-333): `fm` is then the update set
         and every batch carries both label arrays (Batch.with_align_labels)."""
         self.lib = capi.load()
         self.fm = fm
         self.opt = make_options(prune, min_frwd_p, uflags, device if not devices else devices[0], gmm_kernel, workspace_bytes,
-                                align_model=align_model)
+                                align_model=align_model, align_comp_level=align_comp_level)
         self._m = fm.c_struct()
         h = C.c_void_p()
         if devices:

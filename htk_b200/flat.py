@@ -49,7 +49,7 @@ class hfb_options(C.Structure):
     _fields_ = [
         ("pruneInit", C.c_double), ("pruneInc", C.c_double), ("pruneLim", C.c_double),
         ("minFrwdP", C.c_float), ("uFlags", C.c_int32), ("device", C.c_int32),
-        ("gmmKernel", C.c_int32), ("reserved0", C.c_int32), ("workspaceBytes", C.c_size_t),
+        ("gmmKernel", C.c_int32), ("flags", C.c_int32), ("workspaceBytes", C.c_size_t),
         ("alignModel", C.c_void_p),
     ]
 
@@ -143,7 +143,7 @@ NOPRUNE = 1.0e20
 
 
 def make_options(prune=None, min_frwd_p: float = 10.0, uflags: int = 15, device: int = 0,
-                 gmm_kernel: int = 0, workspace_bytes: int = 0, align_model=None) -> hfb_options:
+                 gmm_kernel: int = 0, workspace_bytes: int = 0, align_model=None, align_comp_level: bool = False) -> hfb_options:
     """``prune`` = None (off, HFB.c:83) or (init, inc, lim) as HERest -t takes them.  ``align_model`` = a FlatModel:
     two-model re-estimation (HFB.c:296-333), the model the options are used with is then the update set."""
     o = hfb_options()
@@ -159,6 +159,7 @@ def make_options(prune=None, min_frwd_p: float = 10.0, uflags: int = 15, device:
     o.uFlags = uflags
     o.device = device
     o.gmmKernel = gmm_kernel
+    o.flags = 1 if align_comp_level else 0          # HFB_OPT_ALIGN_COMP_LEVEL (HFB: ALIGNCOMPLEVEL = T)
     o.workspaceBytes = workspace_bytes
     return o
 

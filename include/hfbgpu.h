@@ -46,6 +46,11 @@ extern "C" {
 #define HFB_MAX_FRAMES 32767
 #define HFB_MAX_LABELS 32766
 
+/* hfb_options.flags.  ALIGN_COMP_LEVEL: two-model re-estimation with the configuration variable HFB: ALIGNCOMPLEVEL = T
+ * (HFB.c:71, :231, :1521-1530) -- the component posteriors comp_prob[m] / norm are those of the ALIGNMENT set's state
+ * (same number of components required, HError 999) instead of the update set's. */
+enum { HFB_OPT_ALIGN_COMP_LEVEL = 1 };
+
 /* update flags, HTKLib/HTrain.h:44 (UPMEANS|UPVARS|UPTRANS|UPMIXES) */
 enum { HFB_UPMEANS = 1, HFB_UPVARS = 2, HFB_UPTRANS = 4, HFB_UPMIXES = 8 };
 
@@ -110,7 +115,7 @@ typedef struct hfb_options {
    int32_t uFlags;               /* HFB_UP* mask                                     */
    int32_t device;               /* CUDA device ordinal                              */
    int32_t gmmKernel;            /* 0 = auto, 1 = FP32 CUDA-core, 2 = tcgen05 (3xFP16) */
-   int32_t reserved0;
+   int32_t flags;                /* HFB_OPT_* bits                                   */
    size_t  workspaceBytes;       /* 0 = default; cap for per-wave beta/outprob pool  */
    /* Two-model re-estimation (UseAlignHMMSet, HFB.c:296-333; HERest ALIGNMODELMMF / ALIGNHMMLIST,
     * HERest.c:163-181, :647-684).  NULL = one set does both jobs.  Otherwise this set ALIGNS -- output

@@ -110,6 +110,7 @@ typedef struct {
    const hfb_model *m;       /* the set that aligns (al_hset); the only set unless two-model re-estimation is on */
    const hfb_model *up;      /* the set whose statistics are collected (up_hset, HFB.c:253, :331)               */
    int twoModels;            /* UseAlignHMMSet, HFB.c:296-333                                                     */
+   int compLevelMismatch;    /* ALIGNCOMPLEVEL with different component counts (fatal HError 999 in the reference)         */
    hfb_options opt;
    hfb_acc_layout L;
    int accDouble;
@@ -524,10 +525,18 @@ static void accumulate_model(Ctx *c, Utt *u, int t, int q, double pr)
             initx += BETA(u, t, q, j) - pr;
          }
          if (c->twoModels) {                                      /* component probs of the update hmm, :1518-1547 */
+            /* ALIGNCOMPLEVEL (:1521-1530): ... of the ALIGNMENT hmm's state j instead (same number of components) */
+            const hfb_model *cm = m;
+            int cmo = mo;
+            if (c->opt.flags & HFB_OPT_ALIGN_COMP_LEVEL) {
+               int sa = c->m->hmmState[c->m->hmmStateOff[u->lab[q - 1]] + (j - 2)];
+               cm = c->m; cmo = cm->stateMixOff[sa];
+               if (cm->stateMixOff[sa + 1] - cmo != M) { c->compLevelMismatch = 1; continue; }   /* HError 999, :1524 */
+            }
             if (M > 255) M = 255;
             norm = (float)LZERO;
             for (mx = 1; mx <= M; mx++) {
-               comp_prob[mx] = m->mixLogWt[mo + mx - 1] + gauss_logp(m, m->mixGauss[mo + mx - 1], o);
+               comp_prob[mx] = cm->mixLogWt[cmo + mx - 1] + gauss_logp(cm, cm->mixGauss[cmo + mx - 1], o);
                norm = (float)ladd((double)norm, (double)comp_prob[mx]);
             }
          }
@@ -623,6 +632,13 @@ static void fb_utt(Ctx *c, const float *feat, int T, const int32_t *lab, const i
       qt += u.dms[q];
       if (q > 1 && u.dms[q] == 0 && u.dms[q - 1] == 0) err = HFB_UTT_ETEE;
       if (c->twoModels && c->up->hmmNumStates[u.labUp[q - 1]] != u.N[q]) err = HFB_EINVAL;   /* HError 999, :549-551 */
+      else if (c->twoModels && (c->opt.flags & HFB_OPT_ALIGN_COMP_LEVEL)) {                  /* HError 999, :1523-1524 */
+         int j, pu = u.labUp[q - 1];
+         for (j = 0; j < u.N[q] - 2; j++) {
+            int sa = m->hmmState[m->hmmStateOff[p] + j], su = c->up->hmmState[c->up->hmmStateOff[pu] + j];
+            if (m->stateMixOff[sa + 1] - m->stateMixOff[sa] != c->up->stateMixOff[su + 1] - c->up->stateMixOff[su]) err = HFB_EINVAL;
+         }
+      }
    }
    u.S = S; u.P = P;
    if (Q < 1 || u.dms[1] == 0 || u.dms[Q] == 0) err = HFB_UTT_ETEE;

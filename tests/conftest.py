@@ -29,7 +29,7 @@ def load_golden(name):
     return z, fm, b, dict(prune=prune, min_frwd_p=float(z["minFrwdP"]), uflags=uf)
 
 
-TWO_MODEL_CASES = ["two_model_tied", "two_model_mono"]
+TWO_MODEL_CASES = ["two_model_tied", "two_model_mono", "two_model_complevel"]
 
 
 def load_two_model_golden(name):
@@ -42,7 +42,10 @@ def load_two_model_golden(name):
     b = Batch.from_arrays(z["feat"], z["frameOff"], z["lab"], z["labOff"]).with_align_labels(z["labAlign"])
     pr = z["prune"]
     prune = None if pr[0] >= 1e19 else tuple(float(x) for x in pr)
-    return z, fu, fa, b, dict(prune=prune, min_frwd_p=float(z["minFrwdP"]), uflags=int(z["uflags"]), align_model=fa)
+    kw = dict(prune=prune, min_frwd_p=float(z["minFrwdP"]), uflags=int(z["uflags"]), align_model=fa)
+    if "comp_level" in z.files and bool(z["comp_level"]):
+        kw["align_comp_level"] = True
+    return z, fu, fa, b, kw
 
 
 from htk_b200.compare import acc_errors  # noqa: E402,F401  (re-exported: the tests import it from here)

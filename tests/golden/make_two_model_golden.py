@@ -46,7 +46,7 @@ def load(w, tag):
     return hs, flatten(hs)
 
 
-def case(name, hs_al, hs_up, n_utts, T, Q, prune, seed, uflags="mvw", T_jitter=0):
+def case(name, hs_al, hs_up, n_utts, T, Q, prune, seed, uflags="mvw", T_jitter=0, comp_level=False):
     w = os.path.join(WORK, name)
     shutil.rmtree(w, ignore_errors=True)
     os.makedirs(os.path.join(w, "feat")); os.makedirs(os.path.join(w, "accs"))
@@ -70,7 +70,8 @@ def case(name, hs_al, hs_up, n_utts, T, Q, prune, seed, uflags="mvw", T_jitter=0
         feats.append(f); labs_al.append(la); labs_up.append(lu); mlf["u%04d" % i] = names; scp.append(fn)
     htkio.write_mlf(os.path.join(w, "labs.mlf"), mlf)
     open(os.path.join(w, "train.scp"), "w").write("\n".join(scp) + "\n")
-    open(os.path.join(w, "two.cfg"), "w").write("ALIGNMODELMMF = al.mmf\nALIGNHMMLIST = al.list\n")
+    open(os.path.join(w, "two.cfg"), "w").write("ALIGNMODELMMF = al.mmf\nALIGNHMMLIST = al.list\n" +
+                                                ("HFB: ALIGNCOMPLEVEL = T\n" if comp_level else ""))
     targs = [] if prune is None else (["-t"] + ["%.1f" % x for x in prune])
     out = run([os.path.join(BIN, "HERest"), "-C", "two.cfg", "-T", "1", "-u", uflags] + targs +
               ["-p", "1", "-H", "up.mmf", "-I", "labs.mlf", "-S", "train.scp", "-M", "accs", "up.list"], w)
@@ -79,7 +80,7 @@ def case(name, hs_al, hs_up, n_utts, T, Q, prune, seed, uflags="mvw", T_jitter=0
     uf = sum({"t": 4, "m": 1, "v": 2, "w": 8}[c] for c in uflags)
     acc, tp, tt = htkio.read_acc_dump(os.path.join(w, "accs/HER1.acc"), hs_up, fu, uf)
     Ts = np.array([f.shape[0] for f in feats], dtype=np.int64)
-    d = dict(D=fu.D, names_al=np.array(fa.names), names_up=np.array(fu.names), uflags=uf,
+    d = dict(D=fu.D, names_al=np.array(fa.names), names_up=np.array(fu.names), uflags=uf, comp_level=bool(comp_level),
              prune=np.array(prune if prune else [1e20, 0, 1e20], dtype=np.float64), minFrwdP=np.float32(10.0),
              feat=np.concatenate(feats, 0).astype(np.float32), frameOff=np.concatenate([[0], np.cumsum(Ts)]),
              lab=np.concatenate(labs_up).astype(np.int32), labAlign=np.concatenate(labs_al).astype(np.int32),
@@ -104,6 +105,10 @@ def main():
     al = synth.make_monophone_set(n_phones=10, M=1, seed=17, spread=0.2)
     up = synth.make_monophone_set(n_phones=10, M=2, seed=18, spread=0.2)
     case("two_model_mono", al, up, n_utts=4, T=240, Q=24, prune=(250.0, 150.0, 1000.0), seed=42, uflags="tmvw")
+    # HFB: ALIGNCOMPLEVEL = T (HFB.c:1521-1530): component posteriors from the ALIGNMENT set's states (same component counts)
+    al = synth.make_tied_triphone_set(n_states=60, M=3, n_phys=40, n_logical=60, n_centre=8, seed=13, spread=0.2)
+    up = synth.make_tied_triphone_set(n_states=50, M=3, n_phys=40, n_logical=60, n_centre=8, seed=31, spread=0.2)
+    case("two_model_complevel", al, up, n_utts=4, T=260, Q=26, prune=None, seed=43, T_jitter=20, comp_level=True)
 
 
 if __name__ == "__main__":

@@ -705,7 +705,7 @@ def test_tcgen05_statistics_leave_overflowing_waves_to_stats5(monkeypatch):
 # two-model re-estimation (UseAlignHMMSet, HFB.c:296-333; UpMixParms :1518-1547)
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("gmm_kernel", [1, 2])
-@pytest.mark.parametrize("name", ["two_model_tied", "two_model_mono"])
+@pytest.mark.parametrize("name", ["two_model_tied", "two_model_mono", "two_model_complevel"])
 def test_two_model_reestimation_matches_stock_herest(name, gmm_kernel):
     """hfb_options.alignModel: aligned with one set, statistics of another -- against the dump the stock HERest wrote
     with ALIGNMODELMMF / ALIGNHMMLIST (tests/golden/make_two_model_golden.py) and against the oracle."""
@@ -739,6 +739,15 @@ def test_two_model_reestimation_matches_stock_herest(name, gmm_kernel):
     fb.FBFile(b)
     new, info = fb.MStep(min_egs=1)
     fb.close()
+    if name == "two_model_complevel":
+        # HFB: ALIGNCOMPLEVEL = T needs the same number of components in both sets: refused before anything is launched
+        from htk_b200 import capi
+        z2, fu2, fa2, b2, kw2 = load_two_model_golden("two_model_tied")
+        fb2 = _fb(fu2, align_comp_level=True, **kw2)
+        with pytest.raises(capi.HfbError):
+            fb2.FBFile(b2)
+        assert not fb2.GetAccs().any()
+        fb2.close()
     assert new.mean.shape == fu.mean.shape and np.isfinite(new.mean).all()
     occ = acc[L.muOcc:L.vaSum]
     g = int(np.argmax(occ[fu.meanId]))

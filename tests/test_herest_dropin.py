@@ -345,7 +345,8 @@ def test_single_pass_retraining_matches_stock_herest(tmp_path):
     assert e["muSum"] > 1e-2 and e["vaSum"] > 1e-2, e
 
 
-def test_herest_gpu_two_model_reestimation(tmp_path):
+@pytest.mark.parametrize("comp_level", [False, True])
+def test_herest_gpu_two_model_reestimation(tmp_path, comp_level):
     """2-model re-estimation through the drop-in tool (config ALIGNMODELMMF / ALIGNHMMLIST; HERest.c:647-684,
     UseAlignHMMSet HFB.c:296-333): HERest_gpu and the stock HERest on the same two MMFs, lists, MLF and features ->
     HER1.acc of the UPDATE set within 1e-4, the MMF the stock `-p 0` re-estimates from either dump within 1e-4."""
@@ -353,7 +354,8 @@ def test_herest_gpu_two_model_reestimation(tmp_path):
         pytest.skip("reference binaries not built (bridge/make_herest_gpu.sh needs /root/reference)")
     import re
     tmp = str(tmp_path)
-    al = synth.make_tied_triphone_set(n_states=60, M=2, n_phys=40, n_logical=60, n_centre=8, seed=13, spread=0.2)
+    # comp_level: HFB: ALIGNCOMPLEVEL = T (HFB.c:1521-1530), posteriors from the alignment set's components (same counts)
+    al = synth.make_tied_triphone_set(n_states=60, M=3 if comp_level else 2, n_phys=40, n_logical=60, n_centre=8, seed=13, spread=0.2)
     up = synth.make_tied_triphone_set(n_states=50, M=3, n_phys=40, n_logical=60, n_centre=8, seed=31, spread=0.2)
     sets = {}
     for tag, hs in (("al", al), ("up", up)):
@@ -376,7 +378,8 @@ def test_herest_gpu_two_model_reestimation(tmp_path):
         mlf["u%03d" % i] = names; scp.append(fn)
     htkio.write_mlf(os.path.join(tmp, "labs.mlf"), mlf)
     open(os.path.join(tmp, "scp"), "w").write("\n".join(scp) + "\n")
-    open(os.path.join(tmp, "two.cfg"), "w").write("ALIGNMODELMMF = al.mmf\nALIGNHMMLIST = al.list\n")
+    open(os.path.join(tmp, "two.cfg"), "w").write("ALIGNMODELMMF = al.mmf\nALIGNHMMLIST = al.list\n" +
+                                                  ("HFB: ALIGNCOMPLEVEL = T\n" if comp_level else ""))
     base = ["-C", "two.cfg", "-T", "1", "-u", "mvw", "-p", "1", "-H", "up.mmf", "-I", "labs.mlf", "-S", "scp"]
     probs = {}
     for exe, d in ((HEREST, "accA"), (HEREST_GPU, "accB")):
