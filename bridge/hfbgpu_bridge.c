@@ -584,8 +584,6 @@ Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
       if (p->feat2) { memcpy(nf, p->feat2, sizeof(float) * (size_t)p->nFrames * D); hfbgpu_host_free(p->feat2); }
       p->feat2 = nf; p->feat2Cap = ncap;
    }
-   if (B.alHset != NULL && B.twoData)
-      HError(7399, "hfbgpu bridge: 2-model re-estimation with two data files (-r) is not accelerated");
    if (p->nLab + Q > p->labCap) {
       p->labCap = (p->nLab + Q) * 2 + 1024;
       p->lab = (int32_t *)xrealloc(p->lab, sizeof(int32_t) * (size_t)p->labCap);

@@ -471,6 +471,8 @@ stats3_kernel(DevModel M, Wave W)
 //    kept if wght_m > LMINMIX and -x < minFrwdP; Lr = exp(x) goes into U's accumulators, sums centred on U's means.
 // compLevel (HFB: ALIGNCOMPLEVEL = T, :1521-1530): comp_prob / norm are those of A's state at the position instead (same
 // number of components, checked when the batch is submitted); what is kept and where it goes stays U's.
+// With a second data stream (HERest -r, W.feat2): the alignment saw the first stream; comp_prob is evaluated on the SECOND
+// one (:1533-1541) -- on the first one with compLevel (:1534-1535) -- and the sums are the second stream's (:1603-1611).
 // Transition statistics do not exist in this mode (HFB.c:313-316); numEgs counts U's physical HMMs (:1768-1772).
 // Not a bench path: FP32 CUDA cores, the reference's own evaluation order.
 // ------------------------------------------------------------------------------------------
@@ -515,7 +517,11 @@ stats_two_kernel(DevModel A, DevModel U, Wave W, const int *__restrict__ labUp, 
    const double *alphaJ = W.occ + u.occOff + lp;
    const double *betaU = W.beta + u.betaOff;
    const short *sqA = W.sq + u.frameBase, *eqA = W.eq + u.frameBase;
-   const float *feat = W.feat + (size_t)u.featOff * D;
+   const float *feat1 = W.feat + (size_t)u.featOff * D;
+   const float *feat2 = W.feat2 ? W.feat2 + (size_t)u.featOff * D : nullptr;
+   const float *feat = (feat2 && !compLevel) ? feat2 : feat1;      // rows comp_prob is evaluated on (kept in shared memory)
+   const float *featS = feat2 ? feat2 : feat1;                     // rows the sums are formed from
+   const bool sameRows = featS == feat;
    const double pr = W.out[ui].pr, minF = W.minFrwdP;
    const int k0 = lane, k1 = lane + 32;                // D <= 64 (checked at create)
    double wsum = 0.0;
@@ -602,7 +608,13 @@ stats_two_kernel(DevModel A, DevModel U, Wave W, const int *__restrict__ labUp, 
             float am0 = 0.f, am1 = 0.f, av0 = 0.f, av1 = 0.f, aocc = 0.f;
             for (int ti = 0; ti < nT; ti++) {
                const float Lr = lrs[mi * 33 + ti];
-               const float d0 = (k0 < D) ? os[ti * ostr + k0] - mu0 : 0.f, d1 = (k1 < D) ? os[ti * ostr + k1] - mu1 : 0.f;
+               float o0, o1;
+               if (sameRows) { o0 = os[ti * ostr + k0]; o1 = os[ti * ostr + k1]; }
+               else {
+                  const float *r2 = featS + (size_t)ts[ti] * D;
+                  o0 = (k0 < D) ? r2[k0] : 0.f; o1 = (k1 < D) ? r2[k1] : 0.f;
+               }
+               const float d0 = (k0 < D) ? o0 - mu0 : 0.f, d1 = (k1 < D) ? o1 - mu1 : 0.f;
                const float z0 = d0 * Lr, z1 = d1 * Lr;                       // zmeanlr, :1675
                aocc += Lr; am0 += z0; am1 += z1;
                av0 = fmaf(z0, d0, av0); av1 = fmaf(z1, d1, av1);

@@ -1102,7 +1102,6 @@ static int submit_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, c
    const HostModel &h = c->hm;
    // two-model re-estimation: `lab` indexes the update set, `labAlign` this context's (alignment) set
    if (c->upd && b->numUtt > 0 && !b->labAlign) { g_lastError = "two-model re-estimation: hfb_batch.labAlign is missing"; return HFB_EINVAL; }
-   if (c->upd && feat2) { g_lastError = "two-model re-estimation with two data files is outside the accelerated path"; return HFB_EUNSUPPORTED; }
    const int32_t *labA = c->upd ? b->labAlign : b->lab;
    if (c->upd && b->numUtt > 0) {
       const HostModel &hu = c->upd->hm;

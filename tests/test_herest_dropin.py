@@ -406,3 +406,70 @@ def test_herest_gpu_two_model_reestimation(tmp_path, comp_level):
     assert np.max(np.abs(mA - mB) / np.sqrt(vA)) < 1e-4 + 2e-6
     assert np.max(np.abs(vA - vB) / vA) < 1e-4 + 2e-6
     assert np.max(np.abs(np.exp(wA) - np.exp(wB))) < 1e-4
+
+
+@pytest.mark.parametrize("comp_level", [False, True])
+def test_two_model_single_pass_retraining_matches_stock_herest(tmp_path, comp_level):
+    """2-model re-estimation combined with `-r` (paired data files): the alignment set sees the first file of a pair; the
+    update set's component posteriors are evaluated on the SECOND file (HFB.c:1533-1541; on the first one under
+    ALIGNCOMPLEVEL, :1534-1535) and its sums are the second file's (:1603-1611).  Library (hfbgpu_accumulate_retrain on a
+    context with hfb_options.alignModel) and HERest_gpu against the stock tool's `-p 1` dump."""
+    if not (os.path.exists(HEREST) and os.path.exists(HEREST_GPU)):
+        pytest.skip("reference binaries not built (bridge/make_herest_gpu.sh needs /root/reference)")
+    from htk_b200.estep import ForwardBackward
+    from htk_b200.flat import Batch
+    tmp = str(tmp_path)
+    al = synth.make_tied_triphone_set(n_states=60, M=3 if comp_level else 2, n_phys=40, n_logical=60, n_centre=8, seed=13, spread=0.2)
+    up = synth.make_tied_triphone_set(n_states=50, M=3, n_phys=40, n_logical=60, n_centre=8, seed=31, spread=0.2)
+    sets = {}
+    for tag, hs in (("al", al), ("up", up)):
+        htkio.write_mmf(os.path.join(tmp, tag + ".mmf"), hs)
+        htkio.write_hmm_list(os.path.join(tmp, tag + ".list"), hs)
+        names = open(os.path.join(tmp, tag + ".list")).read().splitlines()
+        h2 = htkio.read_mmf([os.path.join(tmp, tag + ".mmf")], hmm_list=names)
+        sets[tag] = (h2, flatten(h2), names)
+    fa, fu = sets["al"][1], sets["up"][1]
+    common = [n for n in fa.hmm_index if n in fu.hmm_index]
+    rng = np.random.default_rng(7)
+    os.makedirs(os.path.join(tmp, "feat"))
+    mlf, pairs, feats, feats2, labs_a, labs_u = {}, [], [], [], [], []
+    for i in range(7):
+        names = [common[int(k)] for k in rng.integers(0, len(common), size=22)]
+        la = np.array([fa.hmm_index[n] for n in names], dtype=np.int32)
+        lu = np.array([fu.hmm_index[n] for n in names], dtype=np.int32)
+        x = synth.sample_utterance(fa, la, 230 + int(rng.integers(-15, 16)), rng)
+        y = (x * 1.2 - 0.2 + 0.1 * rng.standard_normal(x.shape)).astype(np.float32)      # the "new parameterisation"
+        f1, f2 = os.path.join(tmp, "feat", "u%03d.mfc" % i), os.path.join(tmp, "feat", "u%03d_b.mfc" % i)
+        htkio.write_htk_features(f1, x, up.parm_kind); htkio.write_htk_features(f2, y, up.parm_kind)
+        mlf["u%03d" % i] = names; pairs.append(f1 + " " + f2)
+        feats.append(x); feats2.append(y); labs_a.append(la); labs_u.append(lu)
+    htkio.write_mlf(os.path.join(tmp, "labs.mlf"), mlf)
+    open(os.path.join(tmp, "scp2"), "w").write("\n".join(pairs) + "\n")
+    open(os.path.join(tmp, "two.cfg"), "w").write("ALIGNMODELMMF = al.mmf\nALIGNHMMLIST = al.list\n" +
+                                                  ("HFB: ALIGNCOMPLEVEL = T\n" if comp_level else ""))
+    base = ["-r", "-C", "two.cfg", "-T", "1", "-u", "mvw", "-p", "1", "-H", "up.mmf", "-I", "labs.mlf", "-S", "scp2"]
+    hsU, fmU, namesU = sets["up"]
+    dumps = {}
+    for exe, d in ((HEREST, "accA"), (HEREST_GPU, "accB")):
+        os.makedirs(os.path.join(tmp, d))
+        out = _run([exe] + base + ["-M", d, "up.list"], tmp)
+        assert "2-model re-estimation enabled" in out
+        dumps[d] = htkio.read_acc_dump(os.path.join(tmp, d, "HER1.acc"), hsU, fmU, 11)
+    (a, prA, tA), (g, prG, tG) = dumps["accA"], dumps["accB"]
+    assert tA == tG and abs(prA - prG) <= 1e-6 * abs(prA)
+    e = acc_errors(g, a, fmU)
+    e.pop("totalPr"); e.pop("totalT")
+    assert max(e.values()) < 1e-4, e
+    # the same through the library's own interface
+    b = Batch(feats, labs_u, fmU.D).with_align_labels(np.concatenate(labs_a))
+    fb = ForwardBackward(fmU, uflags=11, align_model=fa, align_comp_level=comp_level)
+    res, _ = fb.FBFileRetrain(b, np.concatenate(feats2))
+    acc = fb.GetAccs()
+    fb.ZeroAccs(); fb.FBFile(b); plain = fb.GetAccs()
+    fb.close()
+    assert all(r.status == 0 for r in res)
+    e = acc_errors(acc, a, fmU)
+    e.pop("totalPr"); e.pop("totalT")
+    assert max(e.values()) < 1e-4, e
+    L = fmU.layout
+    assert not np.allclose(plain[L.muSum:L.muOcc], acc[L.muSum:L.muOcc], rtol=1e-3, atol=1e-3)    # -r changes the sums
