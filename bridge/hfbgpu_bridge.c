@@ -80,6 +80,7 @@ static struct {
    /* raw feature-file reader (see "fast loader" below) */
    int fastState;                        /* 0 = first file not seen yet, 1 = validated, -1 = off */
    int fastSwap;                         /* payload is byte-swapped on this host */
+   int fastComp, fastCrc;                /* the validated files are `_C` compressed (16-bit integers + A / B) / carry a `_K` check sum */
    short fastKind, fastSize;             /* header fields every fast-loaded file must carry */
    int fastFd; long fastT;               /* file opened by HFBGPU_FastLoad, consumed by HFBGPU_Queue */
    long nFast, nSlow;
@@ -103,6 +104,8 @@ typedef struct {
    int64_t *frameOff; int32_t *labOff, *lab, *labAl; int nUtt, labCap, nLab;
    char **names;
    hfb_utt_result *res;
+   int comp;                             /* this batch holds the 16-bit integers of `_C` files in `feat` (hfb_compressed) */
+   float *scaleA, *scaleB; long abCap;   /* their A / B vectors, [nUtt][D] */
    int inflight;
    int64_t ticket;                       /* of the hfbgpu_submit that took this batch */
    int jobs;                             /* reader jobs not finished yet (guarded by R.mu) */
@@ -123,9 +126,14 @@ static void *xrealloc(void *p, size_t n)
    reference's own LoadData / ReadAsTable (HFB.c:1837-1879, HParm.c:4616) and the raw payload must reproduce those
    observations bit for bit -- later files skip HParm altogether: the main thread reads the header, reserves the rows in
    the pinned batch buffer and a pool of reader threads preads + byte-swaps the payload straight into it while HERest's
-   loop goes on resolving labels.  Files that do not carry the validated header (other kind, _C compressed, _K CRC,
+   loop goes on resolving labels.  `_C` compressed files (HASCOMPX; 12-byte header, vectors A and B, rows of 16-bit
+   integers, HParm.c:3680-3699) take the same route when the first one decodes -- v = ((float)s + B) / A, HParm.c:3492-3493
+   -- to exactly what HParm delivered: the readers then bring the INTEGERS into the pinned buffer, check the `_K` check
+   sum like the reference (UpdateCRCC, HParm.c:3357-3380; HError 6350), and the library decodes them on the device
+   (hfbgpu_submit_compressed): half the bytes over PCIe.  Files that do not carry the validated header (other kind,
    other width) and everything under -r fall back to LoadData.  HFBGPU_READERS = threads (0 = off). */
-typedef struct { int fd; size_t bytes; float *dst; int swap; Pending *owner; } Job;
+typedef struct { int fd; size_t bytes; float *dst; int swap; Pending *owner;
+                 int comp, crc, cols; long rows; float *A, *Bv; } Job;
 static struct {
    pthread_t *th; int nTh;
    pthread_mutex_t mu; pthread_cond_t work, done;
@@ -151,6 +159,39 @@ static int read_payload(int fd, float *dst, size_t bytes, int swap)
    return 0;
 }
 
+/* `_C` file: A, B into the batch's scale rows, the integers into the pinned rows, all in host byte order; returns 0, -1
+   (short read) or -2 (check sum of a `_K` file does not match, HParm.c:4515) */
+static int read_compressed(const Job *j)
+{
+   const size_t ab = (size_t)j->cols * sizeof(float), body = (size_t)j->rows * j->cols * sizeof(short);
+   short *sp = (short *)j->dst;
+   size_t got = 0, i;
+   unsigned int crc = 0;
+   unsigned char tail[2];
+   if (pread(j->fd, j->A, ab, 12) != (ssize_t)ab || pread(j->fd, j->Bv, ab, (off_t)(12 + ab)) != (ssize_t)ab) return -1;
+   while (got < body) {
+      ssize_t r = pread(j->fd, (char *)sp + got, body - got, (off_t)(12 + 2 * ab + got));
+      if (r <= 0) return -1;
+      got += (size_t)r;
+   }
+   if (j->swap) {
+      unsigned short *u = (unsigned short *)sp;
+      swap_floats(j->A, (size_t)j->cols); swap_floats(j->Bv, (size_t)j->cols);
+      for (i = 0; i < (size_t)j->rows * j->cols; i++) u[i] = __builtin_bswap16(u[i]);
+   }
+   if (j->crc) {
+      /* the sum runs over the 16-bit words in FILE order: most significant half of every float first */
+      const unsigned int *a = (const unsigned int *)j->A, *b = (const unsigned int *)j->Bv;
+      const unsigned short *u = (const unsigned short *)sp;
+      for (i = 0; i < (size_t)j->cols; i++) { crc = (crc * 65536 + (a[i] >> 16)) % 36897; crc = (crc * 65536 + (a[i] & 0xffff)) % 36897; }
+      for (i = 0; i < (size_t)j->cols; i++) { crc = (crc * 65536 + (b[i] >> 16)) % 36897; crc = (crc * 65536 + (b[i] & 0xffff)) % 36897; }
+      for (i = 0; i < (size_t)j->rows * j->cols; i++) crc = (crc * 65536 + u[i]) % 36897;
+      if (pread(j->fd, tail, 2, (off_t)(12 + 2 * ab + body)) != 2) return -1;
+      if (crc != (unsigned int)((tail[0] << 8) | tail[1])) return -2;
+   }
+   return 0;
+}
+
 static void *reader_main(void *arg)
 {
    (void)arg;
@@ -162,10 +203,10 @@ static void *reader_main(void *arg)
       j = R.q[R.head]; R.head = (R.head + 1) % R.cap; R.n--;
       pthread_mutex_unlock(&R.mu);
       {
-         int bad = read_payload(j.fd, j.dst, j.bytes, j.swap);
+         int bad = j.comp ? read_compressed(&j) : read_payload(j.fd, j.dst, j.bytes, j.swap);
          close(j.fd);
          pthread_mutex_lock(&R.mu);
-         if (bad) R.failed = 1;
+         if (bad == -2) R.failed = 2; else if (bad && !R.failed) R.failed = 1;
          j.owner->jobs--;
          pthread_cond_broadcast(&R.done);
          pthread_mutex_unlock(&R.mu);
@@ -200,6 +241,7 @@ static void reader_wait(Pending *p)                      /* every payload of thi
    pthread_mutex_lock(&R.mu);
    while (p->jobs > 0) pthread_cond_wait(&R.done, &R.mu);
    pthread_mutex_unlock(&R.mu);
+   if (R.failed == 2) HError(6350, "CloseBuffer: Crc error (hfbgpu bridge, fast loader)");      /* HParm.c:4515 */
    if (R.failed) HError(7350, "hfbgpu bridge: short read in a parameter file (fast loader)");
 }
 
@@ -489,7 +531,14 @@ static void Flush(void)
       Drain();
       return;
    }
-   { double t0 = now_s(); rc = hfbgpu_submit(B.ctx, &b, p->res, NULL, 0); B.sSubmit += now_s() - t0; }
+   if (p->comp) {
+      hfb_compressed cf;
+      double t0 = now_s();
+      cf.feat = (const int16_t *)p->feat; cf.scaleA = p->scaleA; cf.scaleB = p->scaleB;
+      b.feat = NULL;
+      rc = hfbgpu_submit_compressed(B.ctx, &b, &cf, p->res, NULL);
+      B.sSubmit += now_s() - t0;
+   } else { double t0 = now_s(); rc = hfbgpu_submit(B.ctx, &b, p->res, NULL, 0); B.sSubmit += now_s() - t0; }
    if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_submit failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
    p->inflight = 1; p->ticket = hfbgpu_last_ticket(B.ctx);
    cur ^= 1;
@@ -513,8 +562,28 @@ static void FastValidate(UttInfo *utt, char *datafn, const float *want, int T)
    for (sw = 1; sw >= 0 && tmp; sw--) {                     /* HTK files are big-endian unless NATURALREADORDER */
       unsigned int ns = *(unsigned int *)h; unsigned short ss = *(unsigned short *)(h + 8), kd = *(unsigned short *)(h + 10);
       if (sw) { ns = __builtin_bswap32(ns); ss = __builtin_bswap16(ss); kd = __builtin_bswap16(kd); }
+      if (kd & HASVQ) continue;                              /* VQ files stay with HParm */
+      if (kd & HASCOMPX) {
+         /* compressed: nSamples counts the A / B vectors as 4 rows; decode as HParm does and compare */
+         Job j;
+         float *A, *Bv;
+         short *sp;
+         int ok, e;
+         if ((long)ns != (long)T + 4 || (int)ss != D * (int)sizeof(short)) continue;
+         A = (float *)malloc(sizeof(float) * 2 * (size_t)D); Bv = A + D;
+         sp = (short *)malloc(sizeof(short) * (size_t)T * D);
+         memset(&j, 0, sizeof(j));
+         j.fd = fd; j.dst = (float *)sp; j.swap = sw; j.comp = 1; j.crc = (kd & HASCRCC) ? 1 : 0; j.cols = D; j.rows = T; j.A = A; j.Bv = Bv;
+         ok = A && sp && read_compressed(&j) == 0;
+         for (e = 0; ok && e < T * D; e++) tmp[e] = ((float)sp[e] + Bv[e % D]) / A[e % D];   /* HParm.c:3492-3493 */
+         ok = ok && memcmp(tmp, want, (size_t)T * D * sizeof(float)) == 0;
+         free(A); free(sp);
+         if (!ok) continue;
+         B.fastState = 1; B.fastSwap = sw; B.fastKind = (short)kd; B.fastSize = (short)ss; B.fastComp = 1; B.fastCrc = (kd & HASCRCC) ? 1 : 0;
+         break;
+      }
       if ((long)ns != (long)T || (int)ss != D * (int)sizeof(float)) continue;
-      if (kd & (HASCOMPX | HASCRCC | HASVQ)) continue;       /* compressed / CRC-checked / VQ files stay with HParm */
+      if (kd & HASCRCC) continue;                            /* uncompressed files with a check sum stay with HParm */
       if (read_payload(fd, tmp, (size_t)T * D * sizeof(float), sw) != 0) continue;
       if (memcmp(tmp, want, (size_t)T * D * sizeof(float)) != 0) continue;
       B.fastState = 1; B.fastSwap = sw; B.fastKind = (short)kd; B.fastSize = (short)ss;
@@ -523,8 +592,9 @@ static void FastValidate(UttInfo *utt, char *datafn, const float *want, int T)
    free(tmp);
    close(fd);
    if (B.trace & 1) {
-      printf("hfbgpu: fast loader %s\n", B.fastState == 1 ? "on (file kind = target kind; payload verified against HParm on the first file)"
-                                                            : "off (files need HParm's conversions)");
+      printf("hfbgpu: fast loader %s\n", B.fastState != 1 ? "off (files need HParm's conversions)" :
+             B.fastComp ? "on (compressed files of the target kind: integers to the device, decoded there; first file verified against HParm)"
+                        : "on (file kind = target kind; payload verified against HParm on the first file)");
       fflush(stdout);
    }
 }
@@ -546,6 +616,7 @@ Boolean HFBGPU_FastLoad(UttInfo *utt, char *datafn, char *datafn2)
    ns = *(unsigned int *)h; ss = *(unsigned short *)(h + 8); kd = *(unsigned short *)(h + 10);
    if (B.fastSwap) { ns = __builtin_bswap32(ns); ss = __builtin_bswap16(ss); kd = __builtin_bswap16(kd); }
    if ((short)kd != B.fastKind || (short)ss != B.fastSize || ns == 0 || ns > 100000000u) { close(fd); return FALSE; }
+   if (B.fastComp) { if (ns <= 4) { close(fd); return FALSE; } ns -= 4; }   /* A and B count as 4 rows (HParm.c:3643-3644, :3686) */
    utt->T = (int)ns;
    B.fastFd = fd; B.fastT = (long)ns;
    B.tLast = now_s(); B.sFastLoad += B.tLast - t0;
@@ -561,8 +632,11 @@ Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
    Pending *p = &P[cur];
    int q, t, k, T = utt->T, Q = utt->Q, D = B.D;
    double tq0 = now_s();
+   const int comp = (B.fastFd >= 0 && B.fastComp) ? 1 : 0;
    B.sOutside += tq0 - B.tLast;
    B.twoData = utt->twoDataFiles ? 1 : 0;
+   if (p->nUtt > 0 && p->comp != comp) { Flush(); p = &P[cur]; }   /* a batch is all floats or all integers */
+   p->comp = comp;
    if (!p->frameOff) {
       p->frameOff = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (B.batchUtts + 2));
       p->labOff = (int32_t *)xrealloc(NULL, sizeof(int32_t) * (B.batchUtts + 2));
@@ -625,10 +699,23 @@ Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
       p->lab[p->nLab + q] = ph;
       if (B.alHset != NULL) p->labAl[p->nLab + q] = pa;
    }
+   if (comp && p->nUtt + 1 > p->abCap) {
+      long ncap = (p->nUtt + 1) * 2 + B.batchUtts + 16;
+      reader_wait(p);                                       /* readers write into the rows */
+      p->scaleA = (float *)xrealloc(p->scaleA, sizeof(float) * (size_t)ncap * D);
+      p->scaleB = (float *)xrealloc(p->scaleB, sizeof(float) * (size_t)ncap * D);
+      p->abCap = ncap;
+   }
    if (B.fastFd >= 0) {
       /* HFBGPU_FastLoad opened the file: a reader thread brings the payload into the pinned rows */
       Job j;
+      memset(&j, 0, sizeof(j));
       j.fd = B.fastFd; j.bytes = (size_t)T * D * sizeof(float); j.dst = p->feat + (size_t)p->nFrames * D;
+      if (comp) {                                           /* the same pinned buffer, viewed as 16-bit integers */
+         j.dst = (float *)((short *)p->feat + (size_t)p->nFrames * D);
+         j.comp = 1; j.crc = B.fastCrc; j.cols = D; j.rows = T;
+         j.A = p->scaleA + (size_t)p->nUtt * D; j.Bv = p->scaleB + (size_t)p->nUtt * D;
+      }
       j.swap = B.fastSwap; j.owner = p;
       B.fastFd = -1;
       reader_push(j);
@@ -719,6 +806,7 @@ void HFBGPU_Finish(int *totalT, LogDouble *totalPr)
    for (i = 0; i < 2; i++) {
       hfbgpu_host_free(P[i].feat); hfbgpu_host_free(P[i].feat2);
       free(P[i].frameOff); free(P[i].labOff); free(P[i].lab); free(P[i].labAl); free(P[i].names); free(P[i].res);
+      free(P[i].scaleA); free(P[i].scaleB);
       memset(&P[i], 0, sizeof(P[i]));
    }
    hfbgpu_destroy(B.ctx);

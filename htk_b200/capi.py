@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from .flat import (hfb_acc_layout, hfb_batch, hfb_beams, hfb_model, hfb_options, hfb_stats,
+from .flat import (hfb_acc_layout, hfb_batch, hfb_beams, hfb_compressed, hfb_model, hfb_options, hfb_stats,
                    hfb_utt_result)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -22,6 +22,7 @@ EXPORTS = [
     "hfbgpu_get_stats", "hfbgpu_reset_stats", "hfbgpu_set_timing", "hfbgpu_set_stream", "hfbgpu_submit", "hfbgpu_wait",
     "hfbgpu_last_ticket", "hfbgpu_wait_ticket", "hfbgpu_create_multi", "hfbgpu_num_devices", "hfbgpu_reduce_accs",
     "hfbgpu_host_alloc", "hfbgpu_host_free", "hfbgpu_mstep", "hfbgpu_set_qualifiers", "hfbgpu_expand_features", "hfbgpu_accumulate_retrain",
+    "hfbgpu_submit_compressed", "hfbgpu_accumulate_compressed", "hfbgpu_decompress_features",
 ]
 
 _lib = None
@@ -67,6 +68,9 @@ def load():
     l.hfbgpu_last_ticket.restype = i64
     l.hfbgpu_wait_ticket.argtypes = [vp, i64]
     l.hfbgpu_accumulate_retrain.argtypes = [vp, C.POINTER(hfb_batch), vp, C.POINTER(hfb_utt_result), C.POINTER(hfb_beams), C.c_int]
+    l.hfbgpu_submit_compressed.argtypes = [vp, C.POINTER(hfb_batch), C.POINTER(hfb_compressed), C.POINTER(hfb_utt_result), C.POINTER(hfb_beams)]
+    l.hfbgpu_accumulate_compressed.argtypes = l.hfbgpu_submit_compressed.argtypes
+    l.hfbgpu_decompress_features.argtypes = [vp, C.POINTER(hfb_compressed), vp, i32, i32, vp]
     l.hfbgpu_acc_device_ptr.argtypes = [vp]
     l.hfbgpu_acc_device_ptr.restype = vp
     l.hfbgpu_acc_count.argtypes = [vp]

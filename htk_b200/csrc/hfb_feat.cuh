@@ -90,6 +90,34 @@ __global__ void __launch_bounds__(256) feat_zeromean_kernel(const UttDesc *__res
 }
 
 // Enqueues the passes for nU utterances described by utt[] (device; only featOff and T are read).
+// HTK compressed parameter files (`_C`, HASCOMPX): the file holds 16-bit integers and two float vectors A, B per file;
+// the reference's loader turns every value back into a float as  v[j] = ((float)s[j] + B[j]) / A[j]
+// (HTKLib/HParm.c:3489-3494; A, B read at :3683-3694; written by CalcCompress / the save path, :4892-4960).  Here the
+// caller uploads the integers as they are (half the bytes of the float table) and this kernel does the same two
+// separately rounded FP32 operations per value: bit-identical to what ReadAsTable yields.  A, B: [utterance][cols].
+__global__ void __launch_bounds__(256) feat_decompress_kernel(const UttDesc *__restrict__ utt, const short *__restrict__ src,
+                                                              const float *__restrict__ A, const float *__restrict__ B,
+                                                              float *__restrict__ dst, int cols)
+{
+   const UttDesc &u = utt[blockIdx.y];
+   const short *s0 = src + (size_t)u.featOff * cols;
+   float *d0 = dst + (size_t)u.featOff * cols;
+   const float *a = A + (size_t)blockIdx.y * cols, *b = B + (size_t)blockIdx.y * cols;
+   const long long n = (long long)u.T * cols;
+   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n; e += (long long)gridDim.x * 256) {
+      const int c = (int)(e % cols);
+      d0[e] = __fdiv_rn(__fadd_rn((float)s0[e], b[c]), a[c]);
+   }
+}
+
+static inline void feat_decompress_launch(const UttDesc *utt, int nU, int maxT, const short *src, const float *A, const float *B,
+                                          float *dst, int cols, cudaStream_t st)
+{
+   if (nU <= 0) return;
+   const dim3 grid((unsigned)std::max(1, std::min(32, (int)(((long long)maxT * cols + 2047) / 2048))), (unsigned)nU);
+   feat_decompress_kernel<<<grid, 256, 0, st>>>(utt, src, A, B, dst, cols);
+}
+
 static inline int feat_expand_launch(const FeatQual &q, const UttDesc *utt, int nU, int maxT, const float *src, float *dst, int D,
                                      cudaStream_t st, int *launches)
 {

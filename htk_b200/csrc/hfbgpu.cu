@@ -144,6 +144,7 @@ struct hfbgpu_ctx {
       DevBuf<float> dFeat;              // only for host-feature calls and for expanded features
       DevBuf<float> dFeatSrc;           // host static coefficients before the qualifier expansion
       DevBuf<float> dFeat2;             // host second data stream (single-pass retraining)
+      DevBuf<short> dFeatC;             // host 16-bit integers of `_C` compressed files before feat_decompress_kernel
       DevBuf<float> dB;
       DevBuf<double> dBeta, dOcc, dAent;
       DevBuf<short> dBeams;             // 4 * frames
@@ -719,7 +720,8 @@ struct ScratchLayout {
 // one wave: launch (asynchronous) and finish (synchronise + hand results to the caller)
 // ------------------------------------------------------------------------------------------
 static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBase, const int32_t *labUpBase, const float *feat, const float *feat2,
-                            bool featOnDevice, long long waveFrame0, long long waveFrames, bool wantBeams)
+                            bool featOnDevice, long long waveFrame0, long long waveFrames, bool wantBeams,
+                            const hfb_compressed *cf = nullptr, int cfUtt0 = 0)
 {
    WaveTables &w = *S.w;
    const int nU = (int)w.utt.size();
@@ -732,8 +734,17 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
    const FeatQual &fq = c->qual;
    const int Dsrc = fq.enabled ? fq.numStatic : D;
    const float *dFeat, *dFeatSrc = nullptr;
+   float *dStage = nullptr;                           // where feat_decompress_kernel writes (compressed input only)
    if (featOnDevice) dFeat = feat + (size_t)waveFrame0 * Dsrc;
-   else {
+   else if (cf) {
+      // `_C` files: the 16-bit integers travel (half the bytes), the floats are formed on the device below
+      DevBuf<float> &stage = fq.enabled ? S.dFeatSrc : S.dFeat;
+      if ((rc = stage.reserve((size_t)waveFrames * Dsrc + 4)) || (rc = S.dFeatC.reserve((size_t)waveFrames * Dsrc + 8))) return rc;
+      CK(cudaMemcpyAsync(S.dFeatC.p, cf->feat + (size_t)waveFrame0 * Dsrc, (size_t)waveFrames * Dsrc * sizeof(int16_t),
+                         cudaMemcpyHostToDevice, st));
+      c->stats.h2dBytes += (int64_t)waveFrames * Dsrc * sizeof(int16_t);
+      dFeat = dStage = stage.p;
+   } else {
       DevBuf<float> &stage = fq.enabled ? S.dFeatSrc : S.dFeat;
       if ((rc = stage.reserve((size_t)waveFrames * Dsrc + 4))) return rc;
       CK(cudaMemcpyAsync(stage.p, feat + (size_t)waveFrame0 * Dsrc, (size_t)waveFrames * Dsrc * sizeof(float),
@@ -766,6 +777,8 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
    const size_t nLab = (size_t)w.utt.back().labOff + (size_t)w.utt.back().Q;
    size_t oLab = blob_put(blob, labBase, nLab);
    const size_t oLabUp = labUpBase ? blob_put(blob, labUpBase, nLab) : 0;     // two-model re-estimation: up_qList
+   const size_t oCA = cf ? blob_put(blob, cf->scaleA + (size_t)cfUtt0 * Dsrc, (size_t)nU * Dsrc) : 0;   // vectors A, B of the wave's files
+   const size_t oCB = cf ? blob_put(blob, cf->scaleB + (size_t)cfUtt0 * Dsrc, (size_t)nU * Dsrc) : 0;
    if (blob.size() > S.hTablesCap) {
       if (S.hTables) cudaFreeHost(S.hTables);
       S.hTablesCap = blob.size() * 2;
@@ -796,6 +809,10 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
    W.tileIv = (int2 *)(sc + sl.tileIv);
    W.posSlot = (int *)(sc + sl.posSlot); W.posState = (int *)(sc + sl.posState); W.posQ = (int *)(sc + sl.posQ);
    W.feat = dFeat; W.feat2 = dFeat2;
+   if (cf) {
+      feat_decompress_launch(W.utt, nU, w.maxT, S.dFeatC.p, (const float *)(base + oCA), (const float *)(base + oCB), dStage, Dsrc, st);
+      c->stats.launches++; c->stats.launchesMisc++;
+   }
    if (fq.enabled) {
       int nl = 0;
       feat_expand_launch(fq, W.utt, nU, w.maxT, dFeatSrc, S.dFeat.p, D, st, &nl);
@@ -1028,9 +1045,10 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
 // A wave that failed part-way (out of memory, unsupported shape, launch error) must not stay "in flight": whatever it
 // enqueued is drained and the slot is released, so that a later wait / finish never reads results that were not produced.
 static int launch_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *labBase, const int32_t *labUpBase, const float *feat, const float *feat2,
-                       bool featOnDevice, long long waveFrame0, long long waveFrames, bool wantBeams)
+                       bool featOnDevice, long long waveFrame0, long long waveFrames, bool wantBeams,
+                       const hfb_compressed *cf = nullptr, int cfUtt0 = 0)
 {
-   const int rc = launch_wave_impl(c, S, labBase, labUpBase, feat, feat2, featOnDevice, waveFrame0, waveFrames, wantBeams);
+   const int rc = launch_wave_impl(c, S, labBase, labUpBase, feat, feat2, featOnDevice, waveFrame0, waveFrames, wantBeams, cf, cfUtt0);
    if (rc) {
       cudaStreamSynchronize(S.stream);
       cudaGetLastError();
@@ -1093,10 +1111,11 @@ static int finish_wave(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S)
 // waves to aim at (the blocking call splits a batch over the streams; the asynchronous one keeps
 // a batch in one wave so that consecutive calls overlap instead).
 static int submit_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, const hfb_beams *beams,
-                       bool featOnDevice, int splitWaves, const float *feat2 = nullptr)
+                       bool featOnDevice, int splitWaves, const float *feat2 = nullptr, const hfb_compressed *cf = nullptr)
 {
    if (!c || !b || !res) return HFB_EINVAL;
-   if (b->numUtt < 0 || (b->numUtt > 0 && (!b->frameOff || !b->feat || !b->labOff || !b->lab))) return HFB_EINVAL;
+   if (b->numUtt < 0 || (b->numUtt > 0 && (!b->frameOff || (!b->feat && !cf) || !b->labOff || !b->lab))) return HFB_EINVAL;
+   if (cf && (featOnDevice || feat2 || (b->numUtt > 0 && (!cf->feat || !cf->scaleA || !cf->scaleB)))) return HFB_EINVAL;
    CK(cudaSetDevice(c->device));
    CK(cudaStreamSynchronize(c->stream));               // accumulator zeroing / model uploads are done
    const HostModel &h = c->hm;
@@ -1170,7 +1189,7 @@ static int submit_impl(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *res, c
       const long long waveFrames = b->frameOff[u1] - waveFrame0;
       S.res = res; S.ticket = c->submitSeq;
       if (wantBeams) S.beams = *beams; else memset(&S.beams, 0, sizeof(S.beams));
-      rc = launch_wave(c, S, labA + w.lab0, c->upd ? b->lab + w.lab0 : nullptr, b->feat, feat2, featOnDevice, waveFrame0, waveFrames, wantBeams);
+      rc = launch_wave(c, S, labA + w.lab0, c->upd ? b->lab + w.lab0 : nullptr, b->feat, feat2, featOnDevice, waveFrame0, waveFrames, wantBeams, cf, u0);
       if (rc) { rcAll = rc; break; }
       u0 = u1; c->nextSlot++;
       if (c->timing) { rc = finish_wave(c, S); if (rc) { rcAll = rc; break; } }
@@ -1276,11 +1295,12 @@ static void group_split(const hfb_batch *b, int n, std::vector<int> &cut)
    cut[n] = b->numUtt;
 }
 
-static int group_submit(hfbgpu_ctx *g, const hfb_batch *b, const float *feat2, hfb_utt_result *res, const hfb_beams *beams, int mode)
+static int group_submit(hfbgpu_ctx *g, const hfb_batch *b, const float *feat2, hfb_utt_result *res, const hfb_beams *beams, int mode,
+                        const hfb_compressed *cf = nullptr)
 {
    // mode 0 = hfbgpu_submit (asynchronous), 1 = hfbgpu_accumulate (blocking), 2 = hfbgpu_accumulate_retrain
    if (!b || !res) return HFB_EINVAL;
-   if (b->numUtt < 0 || (b->numUtt > 0 && (!b->frameOff || !b->feat || !b->labOff || !b->lab))) return HFB_EINVAL;
+   if (b->numUtt < 0 || (b->numUtt > 0 && (!b->frameOff || (!b->feat && !cf) || !b->labOff || !b->lab))) return HFB_EINVAL;
    const int n = (int)g->kids.size();
    std::vector<int> cut;
    group_split(b, n, cut);
@@ -1295,7 +1315,12 @@ static int group_submit(hfbgpu_ctx *g, const hfb_batch *b, const float *feat2, h
       hfb_batch sub = *b;                               // offsets stay absolute: the children index feat / lab with them
       sub.numUtt = cut[k + 1] - cut[k]; sub.frameOff = b->frameOff + cut[k]; sub.labOff = b->labOff + cut[k];
       kid->submitSeq++;
-      int rc = submit_impl(kid, &sub, res + cut[k], beams, false, mode == 0 ? 1 : (int)hfbgpu_ctx::NSLOT, feat2);
+      hfb_compressed subc;
+      if (cf) {                                         // A, B are indexed by utterance: move them with the range
+         const size_t cols = (size_t)(kid->qual.enabled ? kid->qual.numStatic : kid->hm.D);
+         subc = *cf; subc.scaleA = cf->scaleA + (size_t)cut[k] * cols; subc.scaleB = cf->scaleB + (size_t)cut[k] * cols;
+      }
+      int rc = submit_impl(kid, &sub, res + cut[k], beams, false, mode == 0 ? 1 : (int)hfbgpu_ctx::NSLOT, feat2, cf ? &subc : nullptr);
       tk[k] = kid->submitSeq;
       if (rc && !rcAll) rcAll = rc;
    }
@@ -1370,6 +1395,24 @@ extern "C" int hfbgpu_submit(hfbgpu_ctx *c, const hfb_batch *b, hfb_utt_result *
    if (is_group(c)) return featOnDevice ? HFB_EUNSUPPORTED : group_submit(c, b, nullptr, res, beams, 0);
    if (c) c->submitSeq++;
    return submit_impl(c, b, res, beams, featOnDevice != 0, 1);
+}
+
+// `_C` compressed parameter files: the batch's features are the files' 16-bit integers + the vectors A, B of every file
+extern "C" int hfbgpu_submit_compressed(hfbgpu_ctx *c, const hfb_batch *b, const hfb_compressed *cf, hfb_utt_result *res, const hfb_beams *beams)
+{
+   if (!cf) return HFB_EINVAL;
+   if (is_group(c)) return group_submit(c, b, nullptr, res, beams, 0, cf);
+   if (c) c->submitSeq++;
+   return submit_impl(c, b, res, beams, false, 1, nullptr, cf);
+}
+
+extern "C" int hfbgpu_accumulate_compressed(hfbgpu_ctx *c, const hfb_batch *b, const hfb_compressed *cf, hfb_utt_result *res, const hfb_beams *beams)
+{
+   if (!cf) return HFB_EINVAL;
+   if (is_group(c)) return group_submit(c, b, nullptr, res, beams, 1, cf);
+   int rc = submit_impl(c, b, res, beams, false, hfbgpu_ctx::NSLOT, nullptr, cf);
+   int rc2 = wait_impl(c);
+   return rc ? rc : rc2;
 }
 
 extern "C" int64_t hfbgpu_last_ticket(hfbgpu_ctx *c) { return c ? c->submitSeq : 0; }
@@ -1534,6 +1577,47 @@ extern "C" int hfbgpu_expand_features(hfbgpu_ctx *c, const float *src, const int
    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
    c->stats.launches += nl; c->stats.launchesMisc += nl;
    dSrc.release(); dDst.release(); dUtt.release();
+   if (e != cudaSuccess) { g_lastError = cudaGetErrorString(e); cudaGetLastError(); return HFB_ECUDA; }
+   return HFB_OK;
+}
+
+// The decompression alone: what ReadAsTable yields for `_C` files (HParm.c:3489-3494)
+extern "C" int hfbgpu_decompress_features(hfbgpu_ctx *c, const hfb_compressed *cf, const int64_t *frameOff, int32_t numUtt, int32_t cols, float *dst)
+{
+   if (!c || !cf || !cf->feat || !cf->scaleA || !cf->scaleB || !frameOff || !dst || numUtt < 0 || cols < 1) return HFB_EINVAL;
+   if (is_group(c)) return hfbgpu_decompress_features(c->kids[0], cf, frameOff, numUtt, cols, dst);
+   if (numUtt == 0) return HFB_OK;
+   CK(cudaSetDevice(c->device));
+   { int rc = wait_impl(c); if (rc) return rc; }
+   std::vector<UttDesc> utt((size_t)numUtt);
+   int maxT = 0;
+   for (int u = 0; u < numUtt; u++) {
+      const long long T = frameOff[u + 1] - frameOff[u];
+      if (T < 0 || T > 0x7fffffff) return HFB_EINVAL;
+      memset(&utt[u], 0, sizeof(UttDesc));
+      utt[u].T = (int)T; utt[u].featOff = frameOff[u] - frameOff[0];
+      maxT = std::max(maxT, (int)T);
+   }
+   const size_t frames = (size_t)(frameOff[numUtt] - frameOff[0]);
+   DevBuf<short> dSrc;
+   DevBuf<float> dDst, dAB;
+   DevBuf<UttDesc> dUtt;
+   int rc;
+   if ((rc = dSrc.reserve(frames * cols + 8)) || (rc = dDst.reserve(frames * cols + 4)) || (rc = dAB.reserve(2 * (size_t)numUtt * cols)) ||
+       (rc = dUtt.reserve((size_t)numUtt))) {
+      dSrc.release(); dDst.release(); dAB.release(); dUtt.release(); return rc;
+   }
+   cudaStream_t st = c->stream;
+   const size_t nab = (size_t)numUtt * cols;
+   cudaError_t e = cudaMemcpyAsync(dSrc.p, cf->feat + (size_t)frameOff[0] * cols, frames * cols * sizeof(int16_t), cudaMemcpyHostToDevice, st);
+   if (e == cudaSuccess) e = cudaMemcpyAsync(dAB.p, cf->scaleA, nab * sizeof(float), cudaMemcpyHostToDevice, st);
+   if (e == cudaSuccess) e = cudaMemcpyAsync(dAB.p + nab, cf->scaleB, nab * sizeof(float), cudaMemcpyHostToDevice, st);
+   if (e == cudaSuccess) e = cudaMemcpyAsync(dUtt.p, utt.data(), utt.size() * sizeof(UttDesc), cudaMemcpyHostToDevice, st);
+   if (e == cudaSuccess) { feat_decompress_launch(dUtt.p, numUtt, maxT, dSrc.p, dAB.p, dAB.p + nab, dDst.p, cols, st); e = cudaGetLastError(); }
+   if (e == cudaSuccess) e = cudaMemcpyAsync(dst + (size_t)frameOff[0] * cols, dDst.p, frames * cols * sizeof(float), cudaMemcpyDeviceToHost, st);
+   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+   c->stats.launches++; c->stats.launchesMisc++;
+   dSrc.release(); dDst.release(); dAB.release(); dUtt.release();
    if (e != cudaSuccess) { g_lastError = cudaGetErrorString(e); cudaGetLastError(); return HFB_ECUDA; }
    return HFB_OK;
 }

@@ -16,7 +16,7 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 from . import capi
-from .flat import (Batch, Beams, FlatModel, hfb_mstep_options, hfb_mstep_result, hfb_stats, hfb_utt_result,
+from .flat import (Batch, Beams, CompressedFeatures, FlatModel, hfb_mstep_options, hfb_mstep_result, hfb_stats, hfb_utt_result,
                    make_options)
 
 
@@ -88,6 +88,40 @@ class ForwardBackward:
         if rc != 0:
             raise capi.HfbError(rc, "hfbgpu_accumulate")
         return [UttResult((r.status, r.retries, r.pr, r.pruneThresh)) for r in res[:batch.numUtt]], beams
+
+    def FBFileCompressed(self, batch: Batch, cf: CompressedFeatures, want_beams: bool = False):
+        """FBFile over utterances whose parameter files are `_C` compressed: the files' 16-bit integers and A / B vectors go
+        to the device as they are and are decoded there exactly as HParm does (HParm.c:3489-3494); batch.feat is ignored."""
+        res = (hfb_utt_result * max(1, batch.numUtt))()
+        beams = Beams(batch.totalT) if want_beams else None
+        bs = beams.c_struct() if beams is not None else None
+        b, c = batch.c_struct(), cf.c_struct()
+        rc = self.lib.hfbgpu_accumulate_compressed(self.h, C.byref(b), C.byref(c), res, C.byref(bs) if bs is not None else None)
+        if rc != 0:
+            raise capi.HfbError(rc, "hfbgpu_accumulate_compressed")
+        return [UttResult((r.status, r.retries, r.pr, r.pruneThresh)) for r in res[:batch.numUtt]], beams
+
+    def SubmitCompressed(self, batch: Batch, cf: CompressedFeatures):
+        """Asynchronous form of FBFileCompressed (hfbgpu_submit_compressed); ticket as for Submit."""
+        res = (hfb_utt_result * max(1, batch.numUtt))()
+        b, c = batch.c_struct(), cf.c_struct()
+        rc = self.lib.hfbgpu_submit_compressed(self.h, C.byref(b), C.byref(c), res, None)
+        if rc != 0:
+            raise capi.HfbError(rc, "hfbgpu_submit_compressed")
+        tk = _Ticket(batch, (b, c, cf), res, None, None)
+        self._inflight.append(tk)
+        return tk
+
+    def DecompressFeatures(self, cf: CompressedFeatures) -> np.ndarray:
+        """The decoding alone: [totalT][cols] floats, what ReadAsTable yields for those files."""
+        cols = cf.feat.shape[1]
+        dst = np.zeros(cf.feat.shape, np.float32)
+        c = cf.c_struct()
+        rc = self.lib.hfbgpu_decompress_features(self.h, C.byref(c), cf.frameOff.ctypes.data, len(cf.frameOff) - 1, cols,
+                                                 dst.ctypes.data)
+        if rc != 0:
+            raise capi.HfbError(rc, "hfbgpu_decompress_features")
+        return dst
 
     def FBFileRetrain(self, batch: Batch, feat2: np.ndarray, want_beams: bool = False):
         """HERest -r (single-pass retraining): alignment on batch.feat, mean / variance statistics on feat2

@@ -116,6 +116,10 @@ class hfb_batch(C.Structure):
     ]
 
 
+class hfb_compressed(C.Structure):
+    _fields_ = [("feat", C.c_void_p), ("scaleA", C.c_void_p), ("scaleB", C.c_void_p)]
+
+
 class hfb_utt_result(C.Structure):
     _fields_ = [("status", C.c_int32), ("retries", C.c_int32),
                 ("pr", C.c_double), ("pruneThresh", C.c_double)]
@@ -380,6 +384,33 @@ class Batch:
         la = getattr(self, "labAlign", None)
         b.labAlign = la.ctypes.data if la is not None else None
         return b
+
+
+class CompressedFeatures:
+    """The feature side of a batch whose files are `_C` compressed (include/hfbgpu.h hfb_compressed): the files' 16-bit
+    integers [totalT][cols] in the batch's frame order and the vectors A, B of every file ([numUtt][cols])."""
+
+    def __init__(self, shorts: Sequence[np.ndarray], A: Sequence[np.ndarray], B: Sequence[np.ndarray]):
+        self.feat = np.ascontiguousarray(np.concatenate(shorts, axis=0), dtype=np.int16)
+        self.scaleA = np.ascontiguousarray(np.stack(A), dtype=np.float32)
+        self.scaleB = np.ascontiguousarray(np.stack(B), dtype=np.float32)
+        self.frameOff = np.concatenate([[0], np.cumsum([x.shape[0] for x in shorts])]).astype(np.int64)
+        assert self.scaleA.shape == self.scaleB.shape == (len(shorts), self.feat.shape[1])
+
+    @classmethod
+    def from_arrays(cls, feat, scaleA, scaleB, feat_ptr=None):
+        """Arrays already in place (e.g. views of pinned memory); feat_ptr overrides the address of the integers."""
+        c = cls.__new__(cls)
+        c.feat, c.scaleA, c.scaleB, c._ptr = feat, scaleA, scaleB, feat_ptr
+        return c
+
+    def c_struct(self) -> hfb_compressed:
+        c = hfb_compressed()
+        p = getattr(self, "_ptr", None)
+        c.feat = p if p is not None else self.feat.ctypes.data
+        c.scaleA = self.scaleA.ctypes.data
+        c.scaleB = self.scaleB.ctypes.data
+        return c
 
 
 class Beams:

@@ -72,6 +72,74 @@ def read_htk_features(path: str) -> Tuple[np.ndarray, int, int]:
     return feat, period, kind
 
 
+# ---- `_C` compressed parameter files (HASCOMPX) and the `_K` check sum (HASCRCC) -----------------------------------
+# Layout (HTKLib/HParm.c SaveBuffer; read side OpenParmChannel :3680-3699): 12-byte header whose nSamples counts 4 extra
+# rows, sampSize = 2 * cols; then vector A[cols], vector B[cols] (floats), then T rows of cols 16-bit integers; with _K a
+# 16-bit check sum over every 16-bit word after the header, in file order (UpdateCRCC, :3357-3380).  All big-endian.
+
+def htk_crc(words_be: np.ndarray, crc: int = 0) -> int:
+    """UpdateCRCC (HParm.c:3357-3380) over 16-bit words taken in FILE order (`>u2` view of the payload)."""
+    for w in np.asarray(words_be, dtype=np.uint64).tolist():
+        crc = (crc * 65536 + w) % 36897
+    return crc
+
+
+def compress_params(feat: np.ndarray):
+    """CalcCompress + CompressPBlock (HParm.c:4892-4960) in the reference's arithmetic: float min / max and differences,
+    the quotients in double rounded to float, `x = f * A - B` in float, rounding half away from zero.
+    Returns (shorts[T, cols] int16, A[cols], B[cols])."""
+    f = np.ascontiguousarray(feat, dtype=np.float32)
+    mx, mn = f.max(axis=0), f.min(axis=0)
+    rng = (mx - mn).astype(np.float32)
+    flat = rng == 0
+    safe = np.where(flat, np.float32(1), rng).astype(np.float64)
+    A = np.where(flat, 1.0, 2.0 * 32767.0 / safe).astype(np.float32)
+    B = np.where(flat, mx.astype(np.float64), (mx + mn).astype(np.float32).astype(np.float64) * 32767.0 / safe).astype(np.float32)
+    x = (f * A).astype(np.float32) - B                      # float products and differences, each rounded (no FMA in the reference build)
+    x = x.astype(np.float32).astype(np.float64)
+    ix = np.where(x < 0.0, x - 0.5, x + 0.5).astype(np.int64)   # C's (int) truncates toward zero
+    if ix.min() < -32767 or ix.max() > 32767:
+        raise ValueError("CompressPBlock: short out of range (HError 6393)")
+    return ix.astype(np.int16), A, B
+
+
+def decompress_params(shorts: np.ndarray, A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """What the reference's loader makes of a compressed row: v[j] = ((float)s[j] + B[j]) / A[j] (HParm.c:3489-3494)."""
+    return ((shorts.astype(np.float32) + B.astype(np.float32)).astype(np.float32) / A.astype(np.float32)).astype(np.float32)
+
+
+def write_htk_compressed(path: str, feat: np.ndarray, parm_kind: str = "MFCC_0_D_A", samp_period: int = 100000,
+                         with_crc: bool = True) -> None:
+    """`feat` saved as HCopy with SAVECOMPRESSED = T (and SAVEWITHCRC) saves it; parm_kind WITHOUT _C / _K."""
+    s, A, B = compress_params(feat)
+    T, D = s.shape
+    kind = parm_kind_code(parm_kind) | _QUAL["C"] | (_QUAL["K"] if with_crc else 0)
+    body = A.astype(">f4").tobytes() + B.astype(">f4").tobytes() + s.astype(">i2").tobytes()
+    with open(path, "wb") as f:
+        f.write(struct.pack(">iihH", T + 4, samp_period, D * 2, kind))
+        f.write(body)
+        if with_crc:
+            f.write(struct.pack(">H", htk_crc(np.frombuffer(body, dtype=">u2"))))
+
+
+def read_htk_compressed(path: str):
+    """Returns (shorts[T, cols] int16, A, B, sampPeriod, parmKind, crc_ok or None) of a `_C` file, nothing decoded."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    n, period, size, kind = struct.unpack(">iihH", raw[:12])
+    if not kind & _QUAL["C"]:
+        raise ValueError("%s is not a compressed parameter file" % path)
+    D, T = size // 2, n - 4
+    A = np.frombuffer(raw, dtype=">f4", count=D, offset=12).astype(np.float32)
+    B = np.frombuffer(raw, dtype=">f4", count=D, offset=12 + 4 * D).astype(np.float32)
+    s = np.frombuffer(raw, dtype=">i2", count=T * D, offset=12 + 8 * D).astype(np.int16).reshape(T, D)
+    ok = None
+    if kind & _QUAL["K"]:
+        end = 12 + 8 * D + 2 * T * D
+        ok = htk_crc(np.frombuffer(raw[12:end], dtype=">u2")) == struct.unpack(">H", raw[end:end + 2])[0]
+    return s, A, B, period, kind, ok
+
+
 def write_mlf(path: str, labels: Dict[str, Sequence[str]]) -> None:
     with open(path, "w") as f:
         f.write("#!MLF!#\n")

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HFBGPU_ABI_VERSION 2
+#define HFBGPU_ABI_VERSION 3
 
 /* log-arithmetic constants, HTKLib/HMath.h:42-45 and HTKLib/HModel.h:52-53 */
 #define HFB_LZERO   (-1.0E10)
@@ -268,6 +268,29 @@ int hfbgpu_set_qualifiers(hfbgpu_ctx *ctx, const hfb_qualifiers *q);
 /* The expansion alone (what HCopy with that TARGETKIND writes): src = [frames][numStatic] host
  * floats, frameOff[numUtt + 1] as in hfb_batch, dst = [frames][vecSize] host floats.          */
 int hfbgpu_expand_features(hfbgpu_ctx *ctx, const float *src, const int64_t *frameOff, int32_t numUtt, float *dst);
+
+/* ---- HTK compressed parameter files (`_C`, HASCOMPX) on the device ---------------------------------------
+ * A compressed file holds, after the 12-byte header, two float vectors A and B (one value per column; they count as
+ * 4 of the header's nSamples) and then nSamples - 4 rows of 16-bit integers (+ a 16-bit check sum with `_K`).  The
+ * reference's loader turns every integer back into a float as  v[j] = ((float)s[j] + B[j]) / A[j]
+ * (HTKLib/HParm.c:3489-3494; A and B are read at :3683-3694; CalcCompress, :4892-4960, wrote them).  These calls take
+ * the integers as they are in the file (host byte order) -- half the bytes of the float table ReadAsTable yields cross
+ * the PCIe link -- and perform exactly those two FP32 operations on the device: the observations are bit-identical
+ * to the reference's.  cols = numStatic with qualifiers set (the files hold static coefficients), else vecSize.
+ * batch->feat is ignored (may be NULL); everything else is as for hfbgpu_submit / hfbgpu_accumulate (host buffers,
+ * tickets, device groups).  Not combined with device-resident features or -r (two data files).                  */
+typedef struct hfb_compressed {
+   const int16_t *feat;    /* [totalT][cols] row-major, indexed by batch->frameOff like hfb_batch.feat          */
+   const float   *scaleA;  /* [numUtt][cols] vector A of each utterance's file                                   */
+   const float   *scaleB;  /* [numUtt][cols] vector B                                                            */
+} hfb_compressed;
+int hfbgpu_submit_compressed(hfbgpu_ctx *ctx, const hfb_batch *batch, const hfb_compressed *cf,
+                             hfb_utt_result *res, const hfb_beams *beams);
+int hfbgpu_accumulate_compressed(hfbgpu_ctx *ctx, const hfb_batch *batch, const hfb_compressed *cf,
+                                 hfb_utt_result *res, const hfb_beams *beams);
+/* The decompression alone (what HList / HCopy print for such a file): dst = [frames][cols] host floats. */
+int hfbgpu_decompress_features(hfbgpu_ctx *ctx, const hfb_compressed *cf, const int64_t *frameOff, int32_t numUtt,
+                               int32_t cols, float *dst);
 
 /* Pinned (page-locked) host memory for the feature matrix of a batch: uploads from it are
  * asynchronous DMAs that overlap the kernels of the previous batch.  Replaces nothing in the

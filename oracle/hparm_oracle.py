@@ -5,10 +5,27 @@ Follows HTKLib/HParm.c:1618-1722 (AddQualifiers), :1552-1599 (AddDiffs, tables: 
 not V1COMPAT), HTKLib/HSigP.c:827-857 (Regress) and HSigP.c:803-823 (FZeroMean), in float32 with the reference's
 order of operations.  Pinned: bit-identical to the unmodified reference's HCopy (oracle/_ref/bin/HCopy) on
 tests/golden/qualifiers_*.npz (tests/golden/make_qualifier_golden.py; tests/test_oracle_golden.py).
+
+`decompress` restates the loader's treatment of `_C` compressed files (HParm.c:3489-3494) and `crc` the `_K` check sum
+(UpdateCRCC, HParm.c:3357-3380).  Pinned: bit-identical to what the unmodified reference's HCopy reads back from the
+compressed files it wrote itself (tests/golden/compressed_*.npz, tests/golden/make_compressed_golden.py).
 """
 import numpy as np
 
 F = np.float32
+
+
+def decompress(shorts: np.ndarray, A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """HParm.c:3492-3493: v[j] = ((float)s[j] + cf->B[j]) / cf->A[j], two float operations, each rounded."""
+    return ((shorts.astype(F) + np.asarray(B, F)).astype(F) / np.asarray(A, F)).astype(F)
+
+
+def crc(words) -> int:
+    """HParm.c:3357-3380 over the file's 16-bit words after the header, in file order, starting from 0."""
+    c = 0
+    for w in np.asarray(words, dtype=np.uint64).tolist():
+        c = (c * 65536 + w) % 36897                       # :3368-3373
+    return c
 
 
 def regress(src: np.ndarray, win: int, simple: bool) -> np.ndarray:

@@ -473,3 +473,49 @@ def test_two_model_single_pass_retraining_matches_stock_herest(tmp_path, comp_le
     assert max(e.values()) < 1e-4, e
     L = fmU.layout
     assert not np.allclose(plain[L.muSum:L.muOcc], acc[L.muSum:L.muOcc], rtol=1e-3, atol=1e-3)    # -r changes the sums
+
+
+@pytest.mark.parametrize("crc,corrupt", [(True, False), (False, False), (True, True)])
+def test_herest_gpu_on_compressed_files_matches_stock_herest(tmp_path, crc, corrupt, monkeypatch):
+    """`_C` compressed parameter files (HCopy with SAVECOMPRESSED = T, the HTK book's default): the stock tool decodes them
+    in HParm (HParm.c:3489-3494), HERest_gpu's readers hand the 16-bit integers to the library, which decodes them on the
+    device -- same accumulators, same per-utterance lines; a `_K` file whose check sum does not match is HError 6350 in
+    both tools (HParm.c:4515)."""
+    if not (os.path.exists(HEREST) and os.path.exists(HEREST_GPU)):
+        pytest.skip("reference binaries not built (bridge/make_herest_gpu.sh needs /root/reference)")
+    import re
+    tmp = str(tmp_path)
+    monkeypatch.setenv("HFBGPU_BATCH_UTTS", "4")                  # 1 float batch (the verified first file) + 3 integer batches
+    hs = synth.make_tied_triphone_set(n_states=50, M=4, n_phys=30, n_logical=45, n_centre=6, seed=31, spread=0.2)
+    hs2, fm = _setup(tmp, hs, n_utts=10, T=300, Q=30, seed=4)
+    scp = open(os.path.join(tmp, "scp")).read().split()
+    for fn in scp:                                                # rewrite every file the way HCopy saves it compressed
+        x, _, _ = htkio.read_htk_features(fn)
+        htkio.write_htk_compressed(fn, x, hs.parm_kind, with_crc=crc)
+    if corrupt:
+        raw = bytearray(open(scp[5], "rb").read()); raw[2000] ^= 0x04; open(scp[5], "wb").write(bytes(raw))
+    base = ["-T", "1", "-u", "tmvw", "-p", "1", "-H", "mmf", "-I", "labs.mlf", "-S", "scp"]
+    outs = {}
+    for exe, d in ((HEREST, "accA"), (HEREST_GPU, "accB")):
+        os.makedirs(os.path.join(tmp, d))
+        p = subprocess.run([exe] + base + ["-M", d, "list"], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        outs[d] = p.stdout
+        if corrupt:
+            assert p.returncode != 0 and "6350" in p.stdout, p.stdout[-1500:]
+        else:
+            assert p.returncode == 0, p.stdout[-3000:]
+    if corrupt:
+        return
+    out = outs["accB"]
+    assert "fast loader on (compressed" in out, out[-1500:]
+    m = re.search(r"(\d+) utterances through the fast loader, (\d+) through HParm", out)
+    assert m and int(m.group(2)) == 1 and int(m.group(1)) == 9, out[-600:]
+    pa = [float(v) for v in re.findall(r"Utterance prob per frame = (\S+)", outs["accA"])]
+    pb = [float(v) for v in re.findall(r"Utterance prob per frame = (\S+)", out)]
+    assert len(pa) == len(pb) == 10 and np.allclose(pa, pb, rtol=1e-4, atol=0)
+    a, prA, tA = htkio.read_acc_dump(os.path.join(tmp, "accA", "HER1.acc"), hs2, fm)
+    b, prB, tB = htkio.read_acc_dump(os.path.join(tmp, "accB", "HER1.acc"), hs2, fm)
+    assert tA == tB and abs(prA - prB) <= 1e-6 * abs(prA)
+    e = acc_errors(b, a, fm)
+    e.pop("totalPr"); e.pop("totalT")
+    assert max(e.values()) < 1e-4, e

@@ -82,7 +82,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), s
     assert set(syms) == set(capi.EXPORTS)
-    assert lib.hfbgpu_abi_version() == 2
+    assert lib.hfbgpu_abi_version() == 3
 
 
 def test_layout_agrees_between_library_and_python():
