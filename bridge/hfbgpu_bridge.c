@@ -81,6 +81,9 @@ static struct {
    int fastState;                        /* 0 = first file not seen yet, 1 = validated, -1 = off */
    int fastSwap;                         /* payload is byte-swapped on this host */
    int fastComp, fastCrc;                /* the validated files are `_C` compressed (16-bit integers + A / B) / carry a `_K` check sum */
+   int fastStatic, cols;                 /* the files hold `cols` static coefficients; the library forms the target kind's
+                                            differentials / normalisation on the device (hfbgpu_set_qualifiers) */
+   hfb_qualifiers qual; int qualActive;  /* ... with this description; what the context is currently set to */
    short fastKind, fastSize;             /* header fields every fast-loaded file must carry */
    int fastFd; long fastT;               /* file opened by HFBGPU_FastLoad, consumed by HFBGPU_Queue */
    long nFast, nSlow;
@@ -105,6 +108,7 @@ typedef struct {
    char **names;
    hfb_utt_result *res;
    int comp;                             /* this batch holds the 16-bit integers of `_C` files in `feat` (hfb_compressed) */
+   int stat;                             /* this batch's rows hold B.cols static coefficients (device qualifiers) */
    float *scaleA, *scaleB; long abCap;   /* their A / B vectors, [nUtt][D] */
    int inflight;
    int64_t ticket;                       /* of the hfbgpu_submit that took this batch */
@@ -403,7 +407,7 @@ void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pr
       HError(7399, "hfbgpu bridge: input / parent transforms (-a, -J, -E) are not accelerated");
    if (!hset->logWt) HError(7399, "hfbgpu bridge: expected log weights (ConvLogWt)");
    Flatten(hset, &B.u);
-   B.D = hset->vecSize;
+   B.D = B.cols = hset->vecSize;
    pm_init(&B.pmLab, hset->numLogHMM + (B.alHset ? B.alHset->numLogHMM : 0) + 1024);
    hfbgpu_default_options(&opt);
    if (B.alHset != NULL) {
@@ -521,6 +525,11 @@ static void Flush(void)
    b.numUtt = p->nUtt; b.frameOff = p->frameOff; b.feat = p->feat; b.labOff = p->labOff; b.lab = p->lab;
    b.labAlign = (B.alHset != NULL) ? p->labAl : NULL;
    p->res = (hfb_utt_result *)calloc(p->nUtt, sizeof(hfb_utt_result));
+   if (p->stat != B.qualActive) {                           /* static-coefficient batches and full-width ones never mix */
+      rc = hfbgpu_set_qualifiers(B.ctx, p->stat ? &B.qual : NULL);
+      if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_set_qualifiers failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
+      B.qualActive = p->stat;
+   }
    if (B.twoData) {
       /* -r: alignment on the first file of each pair, mean / variance sums from the second (HFB.c:1603-1611);
          the library's entry for it is blocking, so the batch is completed and reported right away */
@@ -546,55 +555,118 @@ static void Flush(void)
                                                                just submitted keeps the GPU busy meanwhile */
 }
 
+/* The rows of an open parameter file as floats [T][cols], `_C` rows decoded as HParm does (HParm.c:3492-3493); 0 = ok */
+static int read_rows(int fd, int sw, unsigned short kd, int T, int cols, float *out)
+{
+   Job j;
+   float *A;
+   short *sp;
+   int ok, e;
+   if (!(kd & HASCOMPX)) return read_payload(fd, out, (size_t)T * cols * sizeof(float), sw);
+   A = (float *)malloc(sizeof(float) * 2 * (size_t)cols);
+   sp = (short *)malloc(sizeof(short) * (size_t)T * cols + 2);
+   memset(&j, 0, sizeof(j));
+   j.fd = fd; j.dst = (float *)sp; j.swap = sw; j.comp = 1; j.crc = (kd & HASCRCC) ? 1 : 0; j.cols = cols; j.rows = T; j.A = A; j.Bv = A + cols;
+   ok = A && sp && read_compressed(&j) == 0;
+   for (e = 0; ok && e < T * cols; e++) out[e] = ((float)sp[e] + A[cols + e % cols]) / A[e % cols];
+   free(A); free(sp);
+   return ok ? 0 : -1;
+}
+
+/* From the files' kind to the set's kind with qualifiers the library can add on the device (HParm.c:1618-1722 AddQualifiers:
+   _D _A _T from DELTAWINDOW / ACCWINDOW / THIRDWINDOW / SIMPLEDIFFS, _Z, _N); FALSE = HParm has to do it. */
+static Boolean MakeQualifiers(unsigned short fileKind, unsigned short tgtKind, int cols, int D, hfb_qualifiers *q)
+{
+   const unsigned short added = (unsigned short)(HASDELTA | HASACCS | HASTHIRD | HASZEROM | HASNULLE);
+   const unsigned short fk = (unsigned short)(fileKind & ~(HASCOMPX | HASCRCC)), tk = (unsigned short)(tgtKind & ~(HASCOMPX | HASCRCC));
+   ConfParam *cParm[MAXGLOBS];
+   int nParm, iv, orders;
+   Boolean bv;
+   if ((fk & BASEMASK) != (tk & BASEMASK) || (fk & added) || (fk & ~tk) || ((tk & ~fk) & ~added) || (tk & HASVQ)) return FALSE;
+   if ((tk & HASNULLE) && (!(tk & HASDELTA) || !(tk & (HASENERGY | HASZEROC)) || ((tk & HASENERGY) && (tk & HASZEROC)))) return FALSE;
+   memset(q, 0, sizeof(*q));
+   q->numStatic = cols;
+   q->delWin = q->accWin = q->thirdWin = 2;                 /* HParm.c:838-871 defaults */
+   nParm = GetConfig("HPARM", TRUE, cParm, MAXGLOBS);
+   if (nParm > 0) {
+      if (GetConfInt(cParm, nParm, "DELTAWINDOW", &iv)) q->delWin = iv;
+      if (GetConfInt(cParm, nParm, "ACCWINDOW", &iv)) q->accWin = iv;
+      if (GetConfInt(cParm, nParm, "THIRDWINDOW", &iv)) q->thirdWin = iv;
+      if (GetConfBool(cParm, nParm, "SIMPLEDIFFS", &bv)) q->simpleDiffs = bv ? 1 : 0;
+   }
+   if (!(tk & HASDELTA)) q->delWin = 0;
+   if (!(tk & HASACCS)) q->accWin = 0;
+   if (!(tk & HASTHIRD)) q->thirdWin = 0;
+   q->suppressEnergy = (tk & HASNULLE) ? 1 : 0;
+   if (tk & HASZEROM) {                                      /* cepstra and c0, not the energy (HParm.c:1709-1712) */
+      q->zeroMeanCols = cols - ((tk & HASENERGY) ? 1 : 0);
+      if (q->suppressEnergy && q->zeroMeanCols > cols - 1) q->zeroMeanCols = cols - 1;
+   }
+   orders = 1 + (q->delWin > 0) + (q->accWin > 0) + (q->thirdWin > 0);
+   return (cols * orders - q->suppressEnergy == D) ? TRUE : FALSE;
+}
+
 /* First utterance (loaded by the reference's own LoadData): does the raw payload of the file reproduce, bit for bit,
-   the observations HParm delivered?  Only then may later files with the same header skip HParm. */
-static void FastValidate(UttInfo *utt, char *datafn, const float *want, int T)
+   the observations HParm delivered -- as it is (files of the target kind, plain or `_C` compressed), or after the
+   library's own qualifier expansion (files holding the static coefficients of the target kind)?  Only then may later
+   files with the same header skip HParm.  `p`, `want`: the batch and the rows HParm's observations were copied to. */
+static void FastValidate(UttInfo *utt, char *datafn, Pending *p, float *want, int T)
 {
    unsigned char h[12];
    int fd, sw, D = B.D;
-   float *tmp;
+   float *tmp, *raw;
    B.fastState = -1;
    if (R.nTh == 0 || utt->twoDataFiles) return;
    fd = open(datafn, O_RDONLY);
    if (fd < 0) return;
    if (pread(fd, h, 12, 0) != 12) { close(fd); return; }
    tmp = (float *)malloc((size_t)T * D * sizeof(float));
-   for (sw = 1; sw >= 0 && tmp; sw--) {                     /* HTK files are big-endian unless NATURALREADORDER */
+   raw = (float *)malloc((size_t)T * D * sizeof(float));
+   for (sw = 1; sw >= 0 && tmp && raw; sw--) {              /* HTK files are big-endian unless NATURALREADORDER */
       unsigned int ns = *(unsigned int *)h; unsigned short ss = *(unsigned short *)(h + 8), kd = *(unsigned short *)(h + 10);
+      const int64_t one[2] = {0, T};
+      hfb_qualifiers q;
+      int comp, esz, cols, useQ = 0, ok;
       if (sw) { ns = __builtin_bswap32(ns); ss = __builtin_bswap16(ss); kd = __builtin_bswap16(kd); }
       if (kd & HASVQ) continue;                              /* VQ files stay with HParm */
-      if (kd & HASCOMPX) {
-         /* compressed: nSamples counts the A / B vectors as 4 rows; decode as HParm does and compare */
-         Job j;
-         float *A, *Bv;
-         short *sp;
-         int ok, e;
-         if ((long)ns != (long)T + 4 || (int)ss != D * (int)sizeof(short)) continue;
-         A = (float *)malloc(sizeof(float) * 2 * (size_t)D); Bv = A + D;
-         sp = (short *)malloc(sizeof(short) * (size_t)T * D);
-         memset(&j, 0, sizeof(j));
-         j.fd = fd; j.dst = (float *)sp; j.swap = sw; j.comp = 1; j.crc = (kd & HASCRCC) ? 1 : 0; j.cols = D; j.rows = T; j.A = A; j.Bv = Bv;
-         ok = A && sp && read_compressed(&j) == 0;
-         for (e = 0; ok && e < T * D; e++) tmp[e] = ((float)sp[e] + Bv[e % D]) / A[e % D];   /* HParm.c:3492-3493 */
-         ok = ok && memcmp(tmp, want, (size_t)T * D * sizeof(float)) == 0;
-         free(A); free(sp);
-         if (!ok) continue;
-         B.fastState = 1; B.fastSwap = sw; B.fastKind = (short)kd; B.fastSize = (short)ss; B.fastComp = 1; B.fastCrc = (kd & HASCRCC) ? 1 : 0;
-         break;
+      comp = (kd & HASCOMPX) ? 1 : 0;
+      if (!comp && (kd & HASCRCC)) continue;                 /* uncompressed files with a check sum stay with HParm */
+      esz = comp ? (int)sizeof(short) : (int)sizeof(float);
+      if (ss == 0 || ss % esz != 0) continue;
+      cols = ss / esz;
+      if ((long)ns != (long)T + (comp ? 4 : 0)) continue;    /* compressed: nSamples counts the A / B vectors as 4 rows */
+      if (cols > D) continue;
+      if (cols < D) {
+         if (p->nUtt != 0 || !MakeQualifiers(kd, (unsigned short)B.hset->pkind, cols, D, &q)) continue;
+         useQ = 1;
       }
-      if ((long)ns != (long)T || (int)ss != D * (int)sizeof(float)) continue;
-      if (kd & HASCRCC) continue;                            /* uncompressed files with a check sum stay with HParm */
-      if (read_payload(fd, tmp, (size_t)T * D * sizeof(float), sw) != 0) continue;
-      if (memcmp(tmp, want, (size_t)T * D * sizeof(float)) != 0) continue;
+      if (read_rows(fd, sw, kd, T, cols, raw) != 0) continue;
+      if (!useQ) ok = memcmp(raw, want, (size_t)T * D * sizeof(float)) == 0;
+      else {
+         ok = hfbgpu_set_qualifiers(B.ctx, &q) == HFB_OK && hfbgpu_expand_features(B.ctx, raw, one, 1, tmp) == HFB_OK &&
+              memcmp(tmp, want, (size_t)T * D * sizeof(float)) == 0;
+         if (!ok) hfbgpu_set_qualifiers(B.ctx, NULL);
+      }
+      if (!ok) continue;
       B.fastState = 1; B.fastSwap = sw; B.fastKind = (short)kd; B.fastSize = (short)ss;
+      B.fastComp = comp; B.fastCrc = (kd & HASCRCC) ? 1 : 0;
+      if (useQ) {
+         /* from here on every fast-loaded batch holds `cols` columns; so does this one: the rows HParm expanded are
+            replaced by the file's own static coefficients (this is the first utterance of its batch) */
+         B.fastStatic = 1; B.cols = cols; B.qual = q; B.qualActive = 1;
+         memcpy(want, raw, (size_t)T * cols * sizeof(float));
+         p->stat = 1;
+      }
       break;
    }
-   free(tmp);
+   free(tmp); free(raw);
    close(fd);
    if (B.trace & 1) {
-      printf("hfbgpu: fast loader %s\n", B.fastState != 1 ? "off (files need HParm's conversions)" :
-             B.fastComp ? "on (compressed files of the target kind: integers to the device, decoded there; first file verified against HParm)"
-                        : "on (file kind = target kind; payload verified against HParm on the first file)");
+      printf("hfbgpu: fast loader %s%s\n", B.fastState != 1 ? "off (files need HParm's conversions)" :
+             B.fastComp ? "on (compressed files: integers to the device, decoded there; first file verified against HParm)"
+                        : "on (payload verified against HParm on the first file)",
+             B.fastState != 1 ? "" : B.fastStatic ? "; files hold static coefficients, the target kind's qualifiers are formed on the device"
+                                                  : "; file kind = target kind");
       fflush(stdout);
    }
 }
@@ -632,11 +704,13 @@ Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
    Pending *p = &P[cur];
    int q, t, k, T = utt->T, Q = utt->Q, D = B.D;
    double tq0 = now_s();
-   const int comp = (B.fastFd >= 0 && B.fastComp) ? 1 : 0;
+   const int comp = (B.fastFd >= 0 && B.fastComp) ? 1 : 0, stat = (B.fastFd >= 0 && B.fastStatic) ? 1 : 0;
+   const int W = stat ? B.cols : D;                         /* columns of this utterance's rows in the batch buffer */
    B.sOutside += tq0 - B.tLast;
    B.twoData = utt->twoDataFiles ? 1 : 0;
-   if (p->nUtt > 0 && p->comp != comp) { Flush(); p = &P[cur]; }   /* a batch is all floats or all integers */
-   p->comp = comp;
+   /* a batch is all floats or all integers, all static coefficients or all full width */
+   if (p->nUtt > 0 && (p->comp != comp || p->stat != stat)) { Flush(); p = &P[cur]; }
+   p->comp = comp; p->stat = stat;
    if (!p->frameOff) {
       p->frameOff = (int64_t *)xrealloc(NULL, sizeof(int64_t) * (B.batchUtts + 2));
       p->labOff = (int32_t *)xrealloc(NULL, sizeof(int32_t) * (B.batchUtts + 2));
@@ -710,11 +784,11 @@ Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
       /* HFBGPU_FastLoad opened the file: a reader thread brings the payload into the pinned rows */
       Job j;
       memset(&j, 0, sizeof(j));
-      j.fd = B.fastFd; j.bytes = (size_t)T * D * sizeof(float); j.dst = p->feat + (size_t)p->nFrames * D;
+      j.fd = B.fastFd; j.bytes = (size_t)T * W * sizeof(float); j.dst = p->feat + (size_t)p->nFrames * W;
       if (comp) {                                           /* the same pinned buffer, viewed as 16-bit integers */
-         j.dst = (float *)((short *)p->feat + (size_t)p->nFrames * D);
-         j.comp = 1; j.crc = B.fastCrc; j.cols = D; j.rows = T;
-         j.A = p->scaleA + (size_t)p->nUtt * D; j.Bv = p->scaleB + (size_t)p->nUtt * D;
+         j.dst = (float *)((short *)p->feat + (size_t)p->nFrames * W);
+         j.comp = 1; j.crc = B.fastCrc; j.cols = W; j.rows = T;
+         j.A = p->scaleA + (size_t)p->nUtt * W; j.Bv = p->scaleB + (size_t)p->nUtt * W;
       }
       j.swap = B.fastSwap; j.owner = p;
       B.fastFd = -1;
@@ -731,7 +805,7 @@ Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
          }
       }
       B.nSlow++;
-      if (B.fastState == 0) FastValidate(utt, datafn, p->feat + (size_t)p->nFrames * D, T);
+      if (B.fastState == 0) FastValidate(utt, datafn, p, p->feat + (size_t)p->nFrames * D, T);
    }
    p->names[p->nUtt] = strdup(datafn);
    p->nFrames += T; p->nLab += Q; p->nUtt++;

@@ -103,10 +103,12 @@ __global__ void __launch_bounds__(256) feat_decompress_kernel(const UttDesc *__r
    const short *s0 = src + (size_t)u.featOff * cols;
    float *d0 = dst + (size_t)u.featOff * cols;
    const float *a = A + (size_t)blockIdx.y * cols, *b = B + (size_t)blockIdx.y * cols;
-   const long long n = (long long)u.T * cols;
-   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n; e += (long long)gridDim.x * 256) {
-      const int c = (int)(e % cols);
-      d0[e] = __fdiv_rn(__fadd_rn((float)s0[e], b[c]), a[c]);
+   const int n = u.T * cols;                             // T <= HFB_MAX_FRAMES: fits 31 bits for any real vector size
+   const int stride = (int)gridDim.x * 256, dc = stride % cols;
+   int e = (int)blockIdx.x * 256 + (int)threadIdx.x, c = e % cols;
+   for (; e < n; e += stride) {                          // the column follows incrementally: no division in the loop
+      d0[e] = __fdiv_rn(__fadd_rn((float)s0[e], __ldg(b + c)), __ldg(a + c));
+      c += dc; if (c >= cols) c -= cols;
    }
 }
 

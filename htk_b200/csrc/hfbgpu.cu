@@ -1593,7 +1593,7 @@ extern "C" int hfbgpu_decompress_features(hfbgpu_ctx *c, const hfb_compressed *c
    int maxT = 0;
    for (int u = 0; u < numUtt; u++) {
       const long long T = frameOff[u + 1] - frameOff[u];
-      if (T < 0 || T > 0x7fffffff) return HFB_EINVAL;
+      if (T < 0 || T * cols > 0x7fffffffLL) return HFB_EINVAL;
       memset(&utt[u], 0, sizeof(UttDesc));
       utt[u].T = (int)T; utt[u].featOff = frameOff[u] - frameOff[0];
       maxT = std::max(maxT, (int)T);

@@ -268,17 +268,42 @@ def test_device_qualifiers_match_stock_herest_loader(tmp_path, src_kind, tgt_kin
     e = acc_errors(b, a, fm)
     e.pop("totalPr"); e.pop("totalT")
     assert max(e.values()) < 1e-4, e
-    # the drop-in tool on the same files: HParm has to expand them, so the raw-file fast loader must stay off
+    # the drop-in tool on the same files.  The first one goes through HParm (which expands it); the bridge derives the
+    # qualifier description from the files' kind, the set's kind and the HPARM configuration, lets the library expand the
+    # file's static coefficients and compares with HParm's observations bit for bit -- afterwards the reader threads feed
+    # 13-column rows and the device forms the rest.  The same with the files saved compressed + check sum (the HTK book's
+    # recipe: MFCC_0 `_C_K` on disk, TARGETKIND = MFCC_0_D_A_Z in the training configuration) and with the loader forced
+    # off (every file through HParm, full-width rows).
     if os.path.exists(HEREST_GPU):
-        os.makedirs(os.path.join(tmp, "accG"))
-        out = _run([HEREST_GPU, "-C", "cfg", "-T", "1", "-u", "tmvw", "-p", "1", "-H", "mmf", "-I", "labs.mlf", "-S", "scp",
-                    "-M", "accG", "list"], tmp)
-        assert "fast loader off" in out and "0 utterances through the fast loader" in out, out[-800:]
-        g, prG, tG = htkio.read_acc_dump(os.path.join(tmp, "accG", "HER1.acc"), hs2, fm)
-        assert tG == tA and abs(prG - prA) <= 1e-4 * abs(prA)
-        e = acc_errors(g, a, fm)
-        e.pop("totalPr"); e.pop("totalT")
-        assert max(e.values()) < 1e-4, e
+        for tag, env, compress in (("accG", {}, False), ("accH", {}, True), ("accI", {"HFBGPU_READERS": "0"}, False)):
+            if compress:
+                for f, x in zip(scp, static):
+                    htkio.write_htk_compressed(f, x, src_kind, with_crc=True)
+                os.makedirs(os.path.join(tmp, "accA2"))
+                _run([HEREST, "-C", "cfg", "-T", "1", "-u", "tmvw", "-p", "1", "-H", "mmf", "-I", "labs.mlf", "-S", "scp",
+                      "-M", "accA2", "list"], tmp)
+                ref, prR, tR = htkio.read_acc_dump(os.path.join(tmp, "accA2", "HER1.acc"), hs2, fm)
+            else:
+                for f, x in zip(scp, static):
+                    htkio.write_htk_features(f, x, src_kind)
+                ref, prR, tR = a, prA, tA
+            os.makedirs(os.path.join(tmp, tag))
+            pr = subprocess.run([HEREST_GPU, "-C", "cfg", "-T", "1", "-u", "tmvw", "-p", "1", "-H", "mmf", "-I", "labs.mlf", "-S", "scp",
+                                 "-M", tag, "list"], cwd=tmp, env=dict(os.environ, HFBGPU_BATCH_UTTS="3", **env),
+                                stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            out = pr.stdout
+            assert pr.returncode == 0, out[-3000:]
+            if env:
+                assert "0 utterances through the fast loader" in out, out[-800:]
+            else:
+                assert "fast loader on" in out and "static coefficients" in out, out[-1500:]
+                assert ("compressed files" in out) == compress
+                assert "%d utterances through the fast loader, 1 through HParm" % (len(scp) - 1) in out, out[-800:]
+            g, prG, tG = htkio.read_acc_dump(os.path.join(tmp, tag, "HER1.acc"), hs2, fm)
+            assert tG == tR and abs(prG - prR) <= 1e-4 * abs(prR)
+            e = acc_errors(g, ref, fm)
+            e.pop("totalPr"); e.pop("totalT")
+            assert max(e.values()) < 1e-4, (tag, e)
 
 
 def test_single_pass_retraining_matches_stock_herest(tmp_path):
