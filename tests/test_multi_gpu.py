@@ -101,3 +101,34 @@ def test_two_model_reestimation_on_a_device_group():
     assert max(e.values()) < 1e-4, e
     L = fu.layout
     assert np.array_equal(a2[L.numEgs:L.totalT], z["ref_acc"][L.numEgs:L.totalT])
+
+
+def test_compressed_features_on_a_device_group():
+    """hfbgpu_accumulate_compressed / hfbgpu_submit_compressed through hfbgpu_create_multi: the batch is cut into one
+    utterance range per GPU and every range must take its own files' A / B vectors along (uneven utterance lengths, so
+    the cut is not in the middle) -- same log-likelihoods as one device on the decoded floats, same accumulators."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from conftest import acc_errors
+    from htk_b200 import htkio, synth
+    from htk_b200.estep import ForwardBackward
+    from htk_b200.flat import Batch, CompressedFeatures, flatten
+    from oracle import hparm_oracle as H
+    hs = synth.make_tied_triphone_set(n_states=40, M=4, n_phys=30, n_logical=30, n_centre=5, D=39, seed=12, spread=0.25)
+    fm = flatten(hs)
+    feats, labs = synth.sample_corpus(fm, n_utts=11, T=170, Q=13, seed=35, T_jitter=60)
+    comp = [htkio.compress_params(f) for f in feats]
+    dec = [H.decompress(s, A, B) for s, A, B in comp]
+    cf = CompressedFeatures([c[0] for c in comp], [c[1] for c in comp], [c[2] for c in comp])
+    b = Batch(dec, labs, 39)
+    one = ForwardBackward(fm); r1, _ = one.FBFile(b); a1 = one.GetAccs(); one.close()
+    grp = ForwardBackward(fm, devices=[0, 1])
+    r2, _ = grp.FBFileCompressed(b, cf)
+    tk = grp.SubmitCompressed(b, cf); grp.Wait()
+    a2 = grp.GetAccs()
+    grp.close()
+    assert [tuple(r) for r in r1] == [tuple(r) for r in r2] == [tuple(r) for r in tk.results()]
+    e = acc_errors(a2 / 2.0, a1, fm)
+    assert max(e.values()) < 1e-5, e
