@@ -42,6 +42,10 @@ WORKLOADS = {
     "cfg5": dict(desc="long utterances, 8k states x 16 mix, beam on", kind="tied", n_states=8000, M=16,
                  n_phys=12000, T=6000, Q=667, prune=(250.0, 150.0, 1000.0), utts=96, workspace_gb=136),
 }
+# utterances per step and GPU: 8 per SM x 148 SMs -- the recursion kernels run one warp per utterance and are bound by the
+# latency of their T-step chains, so a wave should fill the register file (beta: 245 registers = 8 warps per SM); measured
+# on cfg3, M frames/s from HBM / end to end: 740: 209 / 180, 888: 212 / 195, 1024: 214 / 198, 1184: 220 / 207, 1480: 221 / 210
+DEFAULT_UTTS = 1184
 RESULT_DTYPE = np.dtype([("status", "<i4"), ("retries", "<i4"), ("pr", "<f8"), ("pruneThresh", "<f8")])   # hfb_utt_result
 ALG_FLOP_PER_GAUSS_FRAME = lambda D: 2 * (2 * D + 1)      # 158 for D = 39
 
@@ -63,7 +67,7 @@ def read_peaks():
 
 
 def gmm_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the tensor-core GMM kernel (cfg3, 1024 utterances)
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the tensor-core GMM kernel (cfg3, DEFAULT_UTTS utterances)
     from the newest `ncu --set full` summary committed under profiles/ (tools/export_profiles.sh writes them);
     returns (bytes, file name) or (None, None)."""
     import glob
@@ -457,7 +461,7 @@ def run_workload(name, args, rank, world, local_rank, dev, K, full):
     else:
         prune = cfg.get("prune")
     T, Q = cfg["T"], cfg["Q"]
-    n_utts = args.utts or cfg.get("utts") or (1024 if T <= 1000 else 64)
+    n_utts = args.utts or cfg.get("utts") or (DEFAULT_UTTS if T <= 1000 else 64)
     fm = make_model(cfg)
     # long utterances: 0.33 GB of workspace each -- a wave should hold the whole step, so that the T-step chains of the
     # recursions run once per step and not once per fragment of it
@@ -609,7 +613,7 @@ def run_workload(name, args, rank, world, local_rank, dev, K, full):
             ach = gmm_flop / (ms_gemm * 1e-3) / 1e12
             rl["gmm"] = {"bound": "tensor", "kernel": "gmm_tc4_kernel (tcgen05 cta_group::2, A operand in tensor memory, 3xFP16 split, FP32 accumulate in TMEM)",
                          "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": ach / peaks["tensor"],
-                         "traffic": traffic if (name == "cfg3" and n_utts == 1024) else None, "traffic_source": traffic_src,
+                         "traffic": traffic if (name == "cfg3" and n_utts == DEFAULT_UTTS) else None, "traffic_source": traffic_src,
                          "ms_per_launch": ms_gemm, "launches_per_step": 1,
                          "frac_of_peak_over_3": ach / (peaks["tensor"] / 3.0),
                          "frac_of_burst_peak": ach / peaks["tensor_burst"],
@@ -682,7 +686,7 @@ def main():
     else:
         prune = cfg.get("prune")
     T, Q = cfg["T"], cfg["Q"]
-    n_utts = args.utts or cfg.get("utts") or (1024 if T <= 1000 else 64)
+    n_utts = args.utts or cfg.get("utts") or (DEFAULT_UTTS if T <= 1000 else 64)
     cores = os.cpu_count() or 1
     config = {"workload": "%s: %s; %d utterances x %d frames x %d labels per step per GPU; pruning %s; minFrwdP 10; -u tmvw"
                           % (args.workload, cfg["desc"], n_utts, T, Q, ("-t %g %g %g" % prune) if prune else "off (HERest default)"),

@@ -440,7 +440,13 @@ void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pr
    if (uFlags & UPTRANS) opt.uFlags |= HFB_UPTRANS;
    if (uFlags & UPMIXES) opt.uFlags |= HFB_UPMIXES;
    env = getenv("HFBGPU_DEVICE"); opt.device = env ? atoi(env) : 0;
-   env = getenv("HFBGPU_BATCH_UTTS"); B.batchUtts = env ? atoi(env) : 2048;
+   /* 1184 = 8 utterances per SM: the recursion kernels run one warp per utterance and 8 of them fill an SM's register
+      file (bench.py DEFAULT_UTTS has the sweep); larger batches only enlarge the wave workspace (8.4 MB per
+      1000-frame utterance), whose first-use cudaMalloc a short run pays in full */
+   env = getenv("HFBGPU_BATCH_UTTS"); B.batchUtts = env ? atoi(env) : 1184;
+   /* two batches are in flight at most (P[0], P[1]): two wave slots, not the library's four, so that only two
+      workspaces are ever allocated */
+   setenv("HFBGPU_STREAMS", "2", 0);
    env = getenv("HFBGPU_BATCH_FRAMES"); B.batchFrames = env ? atol(env) : 4000000L;
    {
       long nc = sysconf(_SC_NPROCESSORS_ONLN);
@@ -461,6 +467,11 @@ void HFBGPU_Init(HMMSet *hset, FBInfo *fbInfo, LogDouble pruneInit, LogDouble pr
       rc = hfbgpu_create(&B.ctx, &B.u.m, &opt);
    if (rc != HFB_OK) HError(7399, "hfbgpu bridge: hfbgpu_create failed: %s (%s)", hfbgpu_strerror(rc), hfbgpu_last_error());
    hfbgpu_acc_layout(&B.u.m, &B.L);
+   {  /* a device group cuts every batch into one range per GPU: keep the per-GPU share at the default */
+      const int nd = hfbgpu_num_devices(B.ctx);
+      if (nd > 1 && getenv("HFBGPU_BATCH_UTTS") == NULL) B.batchUtts *= nd;
+      if (nd > 1 && getenv("HFBGPU_BATCH_FRAMES") == NULL) B.batchFrames *= nd;
+   }
    printf("hfbgpu: %d physical HMMs, %d tied states, %d Gaussians, %d transition matrices on %d GPU(s)\n",
           B.u.nHmm, B.u.nSte, B.u.nMp, B.u.nTr, hfbgpu_num_devices(B.ctx));
    fflush(stdout);

@@ -26,6 +26,14 @@ for f in legs.values():
     for _ in range(5):
         f()
     fb.Wait()
+# host cost of a submit when a wave slot is free (nothing to wait for): three submits after an idle point
+for k, f in legs.items():
+    fb.Wait(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter(); f(); ts.append(1e3 * (time.perf_counter() - t0))
+    fb.Wait()
+    print("%-10s host ms of three unblocked submits: %s" % (k, " ".join("%.3f" % t for t in ts)), flush=True)
 for rep in range(5):
     sampler = None
     if rep >= 3:                      # the last two repetitions with bench.py's nvidia-smi sampler running beside them
