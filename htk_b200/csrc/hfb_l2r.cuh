@@ -195,6 +195,9 @@ __global__ void __launch_bounds__(MAXT, MAXT == 128 ? 7 : 1024 / MAXT) beta_l2r_
 // 128 below when its model has left the beam for good (the beta beam only ever moves towards the start of the
 // transcription).  No shared memory, no barrier -- the 256-thread sliding block kernel (beta_l2r_slide_kernel) needs two
 // barriers per frame.  A beam wider than 124 models flags the utterance HFB_UTT_BETAWIDE and beta_l2r_kernel<1024> redoes it.
+// (245 registers = 8 warps per SM.  Capped at 168 registers -- __launch_bounds__(32, 12), 300 bytes of spills -- for 12 warps
+// per SM the pass is slower at every wave size: 1.44 against 1.13 ms per 1 024 000 frames at 1184 utterances, 1.57 against
+// 1.38 at 1776; the spills sit on the dependent chain.)
 template <bool ALUCVT, bool RING>
 __global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
 {
