@@ -163,6 +163,25 @@ static int read_payload(int fd, float *dst, size_t bytes, int swap)
    return 0;
 }
 
+/* Uncompressed file with a `_K` check sum (HCopy's default, SAVEWITHCRC = T): the payload as read_payload delivers it plus
+   the reference's check -- the sum runs over the 16-bit words in FILE order, i.e. the most significant half of every
+   (host-order) float first (UpdateCRCC, HParm.c:3357-3380); 0 = ok, -1 short read, -2 mismatch (HParm.c:4515) */
+static int read_payload_crc(int fd, float *dst, size_t bytes, int swap)
+{
+   const unsigned int *u = (const unsigned int *)dst;
+   unsigned int crc = 0;
+   unsigned char tail[2];
+   size_t i;
+   if (read_payload(fd, dst, bytes, swap) != 0) return -1;
+   if (!swap) {                                             /* NATURALREADORDER on a little-endian host: file order = low half first */
+      for (i = 0; i < bytes / 4; i++) { crc = (crc * 65536 + (u[i] & 0xffff)) % 36897; crc = (crc * 65536 + (u[i] >> 16)) % 36897; }
+   } else
+      for (i = 0; i < bytes / 4; i++) { crc = (crc * 65536 + (u[i] >> 16)) % 36897; crc = (crc * 65536 + (u[i] & 0xffff)) % 36897; }
+   if (pread(fd, tail, 2, (off_t)(12 + bytes)) != 2) return -1;
+   if (crc != (unsigned int)(swap ? ((tail[0] << 8) | tail[1]) : ((tail[1] << 8) | tail[0]))) return -2;
+   return 0;
+}
+
 /* `_C` file: A, B into the batch's scale rows, the integers into the pinned rows, all in host byte order; returns 0, -1
    (short read) or -2 (check sum of a `_K` file does not match, HParm.c:4515) */
 static int read_compressed(const Job *j)
@@ -187,11 +206,12 @@ static int read_compressed(const Job *j)
       /* the sum runs over the 16-bit words in FILE order: most significant half of every float first */
       const unsigned int *a = (const unsigned int *)j->A, *b = (const unsigned int *)j->Bv;
       const unsigned short *u = (const unsigned short *)sp;
-      for (i = 0; i < (size_t)j->cols; i++) { crc = (crc * 65536 + (a[i] >> 16)) % 36897; crc = (crc * 65536 + (a[i] & 0xffff)) % 36897; }
-      for (i = 0; i < (size_t)j->cols; i++) { crc = (crc * 65536 + (b[i] >> 16)) % 36897; crc = (crc * 65536 + (b[i] & 0xffff)) % 36897; }
+      const int hs = j->swap ? 16 : 0, ls = j->swap ? 0 : 16;   /* which half of a host-order float comes first in the file */
+      for (i = 0; i < (size_t)j->cols; i++) { crc = (crc * 65536 + ((a[i] >> hs) & 0xffff)) % 36897; crc = (crc * 65536 + ((a[i] >> ls) & 0xffff)) % 36897; }
+      for (i = 0; i < (size_t)j->cols; i++) { crc = (crc * 65536 + ((b[i] >> hs) & 0xffff)) % 36897; crc = (crc * 65536 + ((b[i] >> ls) & 0xffff)) % 36897; }
       for (i = 0; i < (size_t)j->rows * j->cols; i++) crc = (crc * 65536 + u[i]) % 36897;
       if (pread(j->fd, tail, 2, (off_t)(12 + 2 * ab + body)) != 2) return -1;
-      if (crc != (unsigned int)((tail[0] << 8) | tail[1])) return -2;
+      if (crc != (unsigned int)(j->swap ? ((tail[0] << 8) | tail[1]) : ((tail[1] << 8) | tail[0]))) return -2;
    }
    return 0;
 }
@@ -207,7 +227,7 @@ static void *reader_main(void *arg)
       j = R.q[R.head]; R.head = (R.head + 1) % R.cap; R.n--;
       pthread_mutex_unlock(&R.mu);
       {
-         int bad = j.comp ? read_compressed(&j) : read_payload(j.fd, j.dst, j.bytes, j.swap);
+         int bad = j.comp ? read_compressed(&j) : j.crc ? read_payload_crc(j.fd, j.dst, j.bytes, j.swap) : read_payload(j.fd, j.dst, j.bytes, j.swap);
          close(j.fd);
          pthread_mutex_lock(&R.mu);
          if (bad == -2) R.failed = 2; else if (bad && !R.failed) R.failed = 1;
@@ -573,7 +593,8 @@ static int read_rows(int fd, int sw, unsigned short kd, int T, int cols, float *
    float *A;
    short *sp;
    int ok, e;
-   if (!(kd & HASCOMPX)) return read_payload(fd, out, (size_t)T * cols * sizeof(float), sw);
+   if (!(kd & HASCOMPX))
+      return (kd & HASCRCC) ? read_payload_crc(fd, out, (size_t)T * cols * sizeof(float), sw) : read_payload(fd, out, (size_t)T * cols * sizeof(float), sw);
    A = (float *)malloc(sizeof(float) * 2 * (size_t)cols);
    sp = (short *)malloc(sizeof(short) * (size_t)T * cols + 2);
    memset(&j, 0, sizeof(j));
@@ -641,7 +662,6 @@ static void FastValidate(UttInfo *utt, char *datafn, Pending *p, float *want, in
       if (sw) { ns = __builtin_bswap32(ns); ss = __builtin_bswap16(ss); kd = __builtin_bswap16(kd); }
       if (kd & HASVQ) continue;                              /* VQ files stay with HParm */
       comp = (kd & HASCOMPX) ? 1 : 0;
-      if (!comp && (kd & HASCRCC)) continue;                 /* uncompressed files with a check sum stay with HParm */
       esz = comp ? (int)sizeof(short) : (int)sizeof(float);
       if (ss == 0 || ss % esz != 0) continue;
       cols = ss / esz;
@@ -796,6 +816,7 @@ Boolean HFBGPU_Queue(FBInfo *fbInfo, UttInfo *utt, char *datafn)
       Job j;
       memset(&j, 0, sizeof(j));
       j.fd = B.fastFd; j.bytes = (size_t)T * W * sizeof(float); j.dst = p->feat + (size_t)p->nFrames * W;
+      j.crc = B.fastCrc;
       if (comp) {                                           /* the same pinned buffer, viewed as 16-bit integers */
          j.dst = (float *)((short *)p->feat + (size_t)p->nFrames * W);
          j.comp = 1; j.crc = B.fastCrc; j.cols = W; j.rows = T;

@@ -52,12 +52,17 @@ def parm_kind_code(name: str) -> int:
 # --------------------------------------------------------------------------- features
 
 def write_htk_features(path: str, feat: np.ndarray, parm_kind: str = "MFCC_0_D_A",
-                       samp_period: int = 100000) -> None:
+                       samp_period: int = 100000, with_crc: bool = False) -> None:
+    """with_crc: the `_K` form HCopy writes by default (SAVEWITHCRC = T): kind | HASCRCC and a 16-bit check sum over the
+    payload's 16-bit words in file order (UpdateCRCC, HParm.c:3357-3380) after the last row."""
     feat = np.ascontiguousarray(feat, dtype=np.float32)
     T, D = feat.shape
+    body = feat.astype(">f4").tobytes()
     with open(path, "wb") as f:
-        f.write(struct.pack(">iihh", T, samp_period, D * 4, parm_kind_code(parm_kind)))
-        f.write(feat.astype(">f4").tobytes())
+        f.write(struct.pack(">iihH", T, samp_period, D * 4, parm_kind_code(parm_kind) | (_QUAL["K"] if with_crc else 0)))
+        f.write(body)
+        if with_crc:
+            f.write(struct.pack(">H", htk_crc(np.frombuffer(body, dtype=">u2"))))
 
 
 def read_htk_features(path: str) -> Tuple[np.ndarray, int, int]:

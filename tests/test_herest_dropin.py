@@ -500,12 +500,14 @@ def test_two_model_single_pass_retraining_matches_stock_herest(tmp_path, comp_le
     assert not np.allclose(plain[L.muSum:L.muOcc], acc[L.muSum:L.muOcc], rtol=1e-3, atol=1e-3)    # -r changes the sums
 
 
-@pytest.mark.parametrize("crc,corrupt", [(True, False), (False, False), (True, True)])
-def test_herest_gpu_on_compressed_files_matches_stock_herest(tmp_path, crc, corrupt, monkeypatch):
+@pytest.mark.parametrize("compressed,crc,corrupt", [(True, True, False), (True, False, False), (True, True, True),
+                                                    (False, True, False), (False, True, True)])
+def test_herest_gpu_on_compressed_files_matches_stock_herest(tmp_path, compressed, crc, corrupt, monkeypatch):
     """`_C` compressed parameter files (HCopy with SAVECOMPRESSED = T, the HTK book's default): the stock tool decodes them
     in HParm (HParm.c:3489-3494), HERest_gpu's readers hand the 16-bit integers to the library, which decodes them on the
     device -- same accumulators, same per-utterance lines; a `_K` file whose check sum does not match is HError 6350 in
-    both tools (HParm.c:4515)."""
+    both tools (HParm.c:4515).  Also plain float files WITH the check sum (HCopy's default, SAVEWITHCRC = T): the reader
+    threads verify it."""
     if not (os.path.exists(HEREST) and os.path.exists(HEREST_GPU)):
         pytest.skip("reference binaries not built (bridge/make_herest_gpu.sh needs /root/reference)")
     import re
@@ -516,7 +518,10 @@ def test_herest_gpu_on_compressed_files_matches_stock_herest(tmp_path, crc, corr
     scp = open(os.path.join(tmp, "scp")).read().split()
     for fn in scp:                                                # rewrite every file the way HCopy saves it compressed
         x, _, _ = htkio.read_htk_features(fn)
-        htkio.write_htk_compressed(fn, x, hs.parm_kind, with_crc=crc)
+        if compressed:
+            htkio.write_htk_compressed(fn, x, hs.parm_kind, with_crc=crc)
+        else:                                                     # HCopy's default: plain floats + `_K` check sum
+            htkio.write_htk_features(fn, x, hs.parm_kind, with_crc=crc)
     if corrupt:
         raw = bytearray(open(scp[5], "rb").read()); raw[2000] ^= 0x04; open(scp[5], "wb").write(bytes(raw))
     base = ["-T", "1", "-u", "tmvw", "-p", "1", "-H", "mmf", "-I", "labs.mlf", "-S", "scp"]
@@ -532,7 +537,7 @@ def test_herest_gpu_on_compressed_files_matches_stock_herest(tmp_path, crc, corr
     if corrupt:
         return
     out = outs["accB"]
-    assert "fast loader on (compressed" in out, out[-1500:]
+    assert ("fast loader on (compressed" in out) if compressed else ("fast loader on (payload" in out), out[-1500:]
     m = re.search(r"(\d+) utterances through the fast loader, (\d+) through HParm", out)
     assert m and int(m.group(2)) == 1 and int(m.group(1)) == 9, out[-600:]
     pa = [float(v) for v in re.findall(r"Utterance prob per frame = (\S+)", outs["accA"])]
