@@ -667,7 +667,9 @@ def main():
     ap.add_argument("--also", default="cfg2,cfg4,cfg5",
                     help="other BASELINE configs measured after the headline one, few steps each, as sub-records under "
                          "`workloads` ('' = none)")
-    ap.add_argument("--also-steps", type=int, default=5)
+    # 20, not 5: with four wave slots in flight the first steps of a leg fill the pipeline -- config #5 (one 17 ms wave per step)
+    # reads 50 M frames/s over 5 steps and 60 M over 20 or 60
+    ap.add_argument("--also-steps", type=int, default=20)
     ap.add_argument("--utts", type=int, default=0, help="utterances per step per GPU (0 = workload default)")
     ap.add_argument("--prune", default="", help="'off' or 'init,inc,lim' (default: workload's; HERest default is off)")
     ap.add_argument("--gmm-kernel", type=int, default=0)

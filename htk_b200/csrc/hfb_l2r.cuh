@@ -190,6 +190,11 @@ __global__ void __launch_bounds__(MAXT, MAXT == 128 ? 7 : 1024 / MAXT) beta_l2r_
 // instruction and cost 0.26 of the 1.19 ms; staging them through shared memory for 256-byte contiguous stores cost more
 // than it saved: 1.69 ms.)
 #define BW_NM 4
+// -DBW_RING_MINB=9 compiles the ring-window variant for 9 CTAs per SM = 165 registers without spills (left alone the
+// compiler takes 224); part of the "small waves" experiment in launch_wave (hfbgpu.cu), 2.5 % slower on config #5: off.
+#ifndef BW_RING_MINB
+#define BW_RING_MINB 1
+#endif
 // RING: transcriptions of any length under a beam (config #5: 667 labels, beam ~40 models).  The 128 (lane, slot) pairs
 // form a ring: pair (L, k) holds the model q = L + 32 k (mod 128) nearest below the beam's upper end and takes the one
 // 128 below when its model has left the beam for good (the beta beam only ever moves towards the start of the
@@ -199,7 +204,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 128 ? 7 : 1024 / MAXT) beta_l2r_
 // per SM the pass is slower at every wave size: 1.44 against 1.13 ms per 1 024 000 frames at 1184 utterances, 1.57 against
 // 1.38 at 1776; the spills sit on the dependent chain.)
 template <bool ALUCVT, bool RING>
-__global__ void __launch_bounds__(32) beta_l2r_warp_kernel(DevModel M, Wave W)
+__global__ void __launch_bounds__(32, RING ? BW_RING_MINB : 1) beta_l2r_warp_kernel(DevModel M, Wave W)
 {
    const UttDesc &u = W.utt[blockIdx.x];
    UttOut *out = &W.out[blockIdx.x];

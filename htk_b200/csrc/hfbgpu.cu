@@ -837,7 +837,18 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
    // the kernels do overlap, but every one of them slows down by about the overlap gained (alpha, one warp
    // per utterance, 0.9 -> 4-6 ms; gmm 2.2 -> 3.6 ms) -- 110-112 M frames/s either way -- so the default
    // keeps each wave on its own stream and lets the hardware overlap only copies and kernel tails.
-   cudaStream_t sg = (!tm && getenv("HFBGPU_GMM_STREAM")) ? c->gmmStream : st;
+   // Small waves (long utterances, config #5: 96 per wave, four waves in flight).  On private streams the four K1 launches
+   // interleave CTA by CTA, all end together, and the waves then march in lockstep -- K1 x 4 (19 ms), every beta pass at once
+   // (8), every alpha pass (5), the statistics (3): 9.5 ms per wave (HFBGPU_TRACE_KERNELS).  Experiment behind
+   // HFBGPU_SMALL_FIFO=1: the K1 launches of such waves through ONE stream in submission order, so that wave w's recursions
+   // -- a handful of warps bound by the latency of their T-step chains -- run under K1 of wave w + 1; with it
+   // HFBGPU_K1_RESERVE=1 (K1 leaves one SM per 8 utterances of the wave free) and -DBW_RING_MINB=9 (ring-window beta kernel
+   // at 165 instead of 224 registers, no spills, so that a K1 CTA, a beta and an alpha warp fit one SM's register file).
+   // Measured on config #5: the waves do stagger, but K1 then takes 10.9 ms instead of 5.6 next to the ~200 recursion warps
+   // of its predecessors, whatever the two other switches say: 47 M frames/s against 61 M in lockstep.  Left off.
+   static const bool smallFifoOn = getenv("HFBGPU_SMALL_FIFO") && atoi(getenv("HFBGPU_SMALL_FIFO")) != 0;
+   const bool smallWave = ((nU + 7) / 8) * 4 <= c->smCount;
+   cudaStream_t sg = (!tm && (getenv("HFBGPU_GMM_STREAM") || (smallFifoOn && smallWave && c->useV3))) ? c->gmmStream : st;
    if (sg != st) { CK(cudaEventRecord(S.evIn, st)); CK(cudaStreamWaitEvent(sg, S.evIn, 0)); }
    // ---- K0: tables
    const bool tr = tm || c->trace;
@@ -856,8 +867,15 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
    const bool expRows = tcStats && (c->tc3.MP > 1 || !getenv("HFBGPU_NO_PAD")) && !getenv("HFBGPU_NO_EXPA");
    if (gk == 2 && c->useV3) {
       int nl = 0;
+      // HFBGPU_K1_RESERVE=1 (experiment, see "small waves" above): K1 leaves one SM per 8 utterances of a small wave free
+      int smK1 = c->smCount;
+      {
+         static const bool reserveOn = getenv("HFBGPU_K1_RESERVE") && atoi(getenv("HFBGPU_K1_RESERVE")) != 0;
+         const int need = (nU + 7) / 8;
+         if (reserveOn && !tm && need * 4 <= c->smCount) smK1 = std::max(2, (c->smCount - need) & ~1);
+      }
       if ((rc = gmm_tc3_launch(c->tc3, S.tcw, c->dm, W, waveFrames, (const int2 *)(base + oIt), (int)w.tcItems.size(),
-                               (const int2 *)(base + oIt4), (int)w.tcItems4.size(), c->smCount, sg, &nl, expRows))) return rc;
+                               (const int2 *)(base + oIt4), (int)w.tcItems4.size(), smK1, sg, &nl, expRows))) return rc;
       c->stats.launches += nl; c->stats.launchesGmm += nl;
    } else if (gk == 2) {
       int nl = 0;
