@@ -491,6 +491,18 @@ static int create_one(hfbgpu_ctx **out, const hfb_model *m, const hfb_options *o
    cudaFuncSetAttribute(beta_l2r_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(stats5_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
    cudaFuncSetAttribute(stats5_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOpt);
+   // HFBGPU_CARVEOUT=1 (experiment, "small waves" in launch_wave): the recursion kernels ask for the same shared-memory /
+   // L1 split as the tensor-core kernel (maximum shared memory), because CTAs of kernels whose splits differ cannot share an SM
+   if (getenv("HFBGPU_CARVEOUT") && atoi(getenv("HFBGPU_CARVEOUT")) != 0) {
+      const int co = cudaSharedmemCarveoutMaxShared;
+      cudaFuncSetAttribute(beta_l2r_warp_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+      cudaFuncSetAttribute(beta_l2r_warp_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+      cudaFuncSetAttribute(beta_l2r_kernel<1024>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+      cudaFuncSetAttribute(alpha_l2r_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+      cudaFuncSetAttribute(alpha_warp_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+      cudaFuncSetAttribute(prep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+      cudaGetLastError();
+   }
    stats_tc_set_attributes();
    gmm_tc4_set_attributes();
    CK(cudaStreamSynchronize(c->stream));
