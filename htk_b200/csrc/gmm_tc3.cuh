@@ -31,6 +31,7 @@ struct GmmTc3Model {
    int MP = 0;
    long long rows = 0;
    __half *dBhi = nullptr, *dBlo = nullptr;
+   size_t bBytes = 0;          // bytes of the operand (hi + lo), starting at dBhi
    float *dOffset = nullptr, *dScale = nullptr;
    CUtensorMap mapBhi, mapBlo;
    float C0 = 0.f;             // what the epilogue subtracts: C0H - C1H
@@ -531,8 +532,7 @@ gmm_tc3_pad_kernel(const float *__restrict__ feat, const float *__restrict__ off
 // ------------------------------------------------------------------------------------------
 static inline void gmm_tc3_release(GmmTc3Model &t)
 {
-   if (t.dBhi) cudaFree(t.dBhi);
-   if (t.dBlo) cudaFree(t.dBlo);
+   if (t.dBhi) cudaFree(t.dBhi);                         // dBlo lives in the same allocation
    if (t.dOffset) cudaFree(t.dOffset);
    if (t.dScale) cudaFree(t.dScale);
    t = GmmTc3Model();
@@ -623,7 +623,9 @@ static inline int gmm_tc3_prepare(GmmTc3Model &t, const hfb_model *m, cudaStream
    for (long long r = 0; r < t.rows; r++) hh[(size_t)r * TC_KH] = __float2half_rn(C0H);
    t.C0 = C0H - (float)c1;
    const size_t hb = hh.size() * sizeof(__half);
-   if (cudaMalloc(&t.dBhi, hb) != cudaSuccess || cudaMalloc(&t.dBlo, hb) != cudaSuccess ||
+   // hi and lo halves in ONE allocation: a single L2 access-policy window can cover the whole operand (hfbgpu.cu)
+   t.bBytes = 2 * hb;
+   if (cudaMalloc(&t.dBhi, 2 * hb) != cudaSuccess || (t.dBlo = (__half *)((char *)t.dBhi + hb), false) ||
        cudaMalloc(&t.dOffset, D * sizeof(float)) != cudaSuccess || cudaMalloc(&t.dScale, D * sizeof(float)) != cudaSuccess) {
       cudaGetLastError(); gmm_tc3_release(t); return HFB_ENOMEM;
    }

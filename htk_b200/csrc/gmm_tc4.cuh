@@ -16,6 +16,12 @@
 #include "gmm_tc3.cuh"
 
 #define TC4_NST 4
+// Launch bound of the kernel: TC3_THREADS (448) lets the compiler use up to 144 registers per thread (it takes 127);
+// -DTC4_LB_THREADS=576 caps it at 112 -- experiment for running the recursion warps of small waves beside a K1 CTA
+// ("small waves" in launch_wave, hfbgpu.cu; profiles/README.md r2e)
+#ifndef TC4_LB_THREADS
+#define TC4_LB_THREADS TC3_THREADS
+#endif
 #define TC4_SMEM_BYTES (TC4_NST * 32768 + 512 + 1024)
 
 __device__ __forceinline__ void tc4_mma_ts(uint32_t tmemD, uint32_t tmemA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
@@ -89,7 +95,7 @@ __device__ __forceinline__ void tc4_issue_block(uint32_t dAcc, uint32_t aHi, uin
 }
 
 template <int MP, int DP>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC4_LB_THREADS, 1)
 gmm_tc4_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, Tc3Params p)
 {
    extern __shared__ uint8_t tc_smem_raw[];

@@ -469,6 +469,28 @@ static int create_one(hfbgpu_ctx **out, const hfb_model *m, const hfb_options *o
           (rc = gmm_tc3_prepare(c->tc3, m, c->stream, fn))) { hfbgpu_destroy(c); return rc; }
       c->useV3 = c->tc3.ready && c->smCount >= 2;
    }
+   // HFBGPU_L2_PERSIST=1 (experiment): the Gaussian operand of K1 (41 MB for config #3, 66 MB for #5) is read once per
+   // 512-frame work item by every CTA pair and should live in the 126 MB L2; the output probabilities K1 writes and the
+   // arrays the recursion kernels of other waves stream through it compete for the same lines.  The window asks the L2 to
+   // keep the operand (persisting) on every stream the library launches on.
+   if (c->useV3 && getenv("HFBGPU_L2_PERSIST") && atoi(getenv("HFBGPU_L2_PERSIST")) != 0 && c->tc3.bBytes > 0) {
+      cudaDeviceProp pr2;
+      cudaGetDeviceProperties(&pr2, c->device);
+      const size_t want = std::min((size_t)pr2.persistingL2CacheMaxSize, c->tc3.bBytes);
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      cudaStreamAttrValue av;
+      memset(&av, 0, sizeof(av));
+      av.accessPolicyWindow.base_ptr = c->tc3.dBhi;
+      av.accessPolicyWindow.num_bytes = std::min((size_t)pr2.accessPolicyMaxWindowSize, c->tc3.bBytes);
+      av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)av.accessPolicyWindow.num_bytes);
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(c->gmmStream, cudaStreamAttributeAccessPolicyWindow, &av);
+      for (auto &sl : c->slot) cudaStreamSetAttribute(sl.stream, cudaStreamAttributeAccessPolicyWindow, &av);
+      fprintf(stderr, "[hfbgpu] L2 window: %zu MB of the %zu MB operand persisting (device maximum %zu MB)\n", want >> 20,
+              c->tc3.bBytes >> 20, (size_t)pr2.persistingL2CacheMaxSize >> 20);
+      cudaGetLastError();
+   }
    if (opt->gmmKernel == 2 && !gmm_tc_available(c->tc) && !c->useV3) {
       hfbgpu_destroy(c); g_lastError = "tcgen05 GMM kernel requested but not available for this model";
       return HFB_EUNSUPPORTED;
