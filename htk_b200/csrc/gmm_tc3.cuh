@@ -648,11 +648,11 @@ static inline int gmm_tc3_prepare(GmmTc3Model &t, const hfb_model *m, cudaStream
 }
 
 // gmm_tc4.cuh: the same work with the A operand in tensor memory (the default; HFBGPU_GMM_V3 keeps this file's kernel)
-static inline void gmm_tc4_go(const GmmTc3Model &t, const Tc3Params &p, int D, int grid2, cudaStream_t st);
+static inline void gmm_tc4_go(const GmmTc3Model &t, const Tc3Params &p, int D, int grid2, cudaStream_t st, bool lean);
 
 static inline int gmm_tc3_launch(GmmTc3Model &t, GmmTcWork &wk, const DevModel &dm, const Wave &W, long long waveFrames,
                                  const int2 *dItems128, int nItems128, const int2 *dItems4, int nItems4, int smCount,
-                                 cudaStream_t st, int *launches, bool wantExp = false)
+                                 cudaStream_t st, int *launches, bool wantExp = false, bool lean = false)
 {
    if (!t.ready) return HFB_EUNSUPPORTED;
    if (nItems4 == 0) return HFB_OK;
@@ -712,7 +712,7 @@ static inline int gmm_tc3_launch(GmmTc3Model &t, GmmTcWork &wk, const DevModel &
 #define TC3_GO(MPV) do { if (dm.D <= 40) gmm_tc3_kernel<MPV, 40><<<grid2, TC3_THREADS, TC3_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p); \
                           else gmm_tc3_kernel<MPV, 64><<<grid2, TC3_THREADS, TC3_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p); } while (0)
    const bool ssMode = getenv("HFBGPU_GMM_V3") != nullptr;
-   if (!ssMode) gmm_tc4_go(t, p, dm.D, grid2, st);
+   if (!ssMode) gmm_tc4_go(t, p, dm.D, grid2, st, lean);
    else
    switch (t.MP) {
    case 1: TC3_GO(1); break;

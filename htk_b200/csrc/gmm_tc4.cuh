@@ -16,12 +16,13 @@
 #include "gmm_tc3.cuh"
 
 #define TC4_NST 4
-// Launch bound of the kernel: TC3_THREADS (448) lets the compiler use up to 144 registers per thread (it takes 127);
-// -DTC4_LB_THREADS=576 caps it at 112 -- experiment for running the recursion warps of small waves beside a K1 CTA
-// ("small waves" in launch_wave, hfbgpu.cu; profiles/README.md r2e)
-#ifndef TC4_LB_THREADS
-#define TC4_LB_THREADS TC3_THREADS
-#endif
+// Launch bound of the kernel (template parameter LB): TC3_THREADS (448) lets the compiler use up to 144 registers per thread
+// (it takes 127); 576 makes it budget five warps per register sub-partition = 96 registers (400 bytes of spills): the "lean"
+// build for SMALL waves, whose recursion warps should run beside the next wave's K1 ("small waves" in launch_wave, hfbgpu.cu).
+// A CTA's warps go to the four sub-partitions of the register file by warp number, so the 14 warps load them 4 / 4 / 3 / 3:
+// at 128 registers two partitions are full and nothing else fits the SM; at 96 every partition keeps >= 4 096 registers
+// and two of them 7 168 -- room for a ring-window beta warp (165 registers = 5 376) placed AFTER the CTA.
+#define TC4_LB_LEAN 576
 #define TC4_SMEM_BYTES (TC4_NST * 32768 + 512 + 1024)
 
 __device__ __forceinline__ void tc4_mma_ts(uint32_t tmemD, uint32_t tmemA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
@@ -94,8 +95,8 @@ __device__ __forceinline__ void tc4_issue_block(uint32_t dAcc, uint32_t aHi, uin
    }
 }
 
-template <int MP, int DP>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC4_LB_THREADS, 1)
+template <int MP, int DP, int LB = TC3_THREADS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LB, 1)
 gmm_tc4_kernel(const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, Tc3Params p)
 {
    extern __shared__ uint8_t tc_smem_raw[];
@@ -478,11 +479,20 @@ static inline void gmm_tc4_set_attributes()
                      cudaFuncSetAttribute(gmm_tc4_kernel<MPV, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC4_SMEM_BYTES)
    TC4_SET(1); TC4_SET(8); TC4_SET(16); TC4_SET(32); TC4_SET(64); TC4_SET(128);
 #undef TC4_SET
+   cudaFuncSetAttribute(gmm_tc4_kernel<8, 40, TC4_LB_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC4_SMEM_BYTES);
+   cudaFuncSetAttribute(gmm_tc4_kernel<16, 40, TC4_LB_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC4_SMEM_BYTES);
+   cudaFuncSetAttribute(gmm_tc4_kernel<32, 40, TC4_LB_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC4_SMEM_BYTES);
 }
 
 // the launch of the kernel alone (gmm_tc3_launch prepares Tc3Params, the flags, the optional outputs and the fix-up)
-static inline void gmm_tc4_go(const GmmTc3Model &t, const Tc3Params &p, int D, int grid2, cudaStream_t st)
+static inline void gmm_tc4_go(const GmmTc3Model &t, const Tc3Params &p, int D, int grid2, cudaStream_t st, bool lean)
 {
+   if (lean && D <= 40 && (t.MP == 8 || t.MP == 16 || t.MP == 32)) {      // the 96-register build (mixture sets, D <= 40)
+      if (t.MP == 8) gmm_tc4_kernel<8, 40, TC4_LB_LEAN><<<grid2, TC3_THREADS, TC4_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p);
+      else if (t.MP == 16) gmm_tc4_kernel<16, 40, TC4_LB_LEAN><<<grid2, TC3_THREADS, TC4_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p);
+      else gmm_tc4_kernel<32, 40, TC4_LB_LEAN><<<grid2, TC3_THREADS, TC4_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p);
+      return;
+   }
 #define TC4_GO(MPV) do { if (D <= 40) gmm_tc4_kernel<MPV, 40><<<grid2, TC3_THREADS, TC4_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p); \
                           else gmm_tc4_kernel<MPV, 64><<<grid2, TC3_THREADS, TC4_SMEM_BYTES, st>>>(t.mapBhi, t.mapBlo, p); } while (0)
    switch (t.MP) {

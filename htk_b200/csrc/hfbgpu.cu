@@ -879,17 +879,22 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
    // HFBGPU_K1_RESERVE=1 (K1 leaves one SM per 8 utterances of the wave free) and -DBW_RING_MINB=9 (ring-window beta kernel
    // at 165 instead of 224 registers, no spills, so that a K1 CTA, a beta and an alpha warp fit one SM's register file).
    // Measured on config #5: the waves do stagger, but K1 then takes 10.9 ms instead of 5.6 next to the ~200 recursion warps
-   // of its predecessors, whatever the two other switches say: 47 M frames/s against 61 M in lockstep.  Left off.
+   // of its predecessors, whatever the two other switches say: 47 M frames/s against 61 M in lockstep.  With the 96-register
+   // ("lean") build of K1, which this switch also selects, and the tables built on the wave's own stream, K1 keeps its 5.8 ms
+   // beside the recursion warps -- but then THEY slow down (beta 13-18 ms instead of 6.5: a latency-bound chain that shares
+   // its SM's issue slots with 14 busy warps): 53-58 M.  What is left is spatial separation (an SM partition per kernel
+   // family, i.e. green contexts).  Left off.
    static const bool smallFifoOn = getenv("HFBGPU_SMALL_FIFO") && atoi(getenv("HFBGPU_SMALL_FIFO")) != 0;
    const bool smallWave = ((nU + 7) / 8) * 4 <= c->smCount;
    cudaStream_t sg = (!tm && (getenv("HFBGPU_GMM_STREAM") || (smallFifoOn && smallWave && c->useV3))) ? c->gmmStream : st;
-   if (sg != st) { CK(cudaEventRecord(S.evIn, st)); CK(cudaStreamWaitEvent(sg, S.evIn, 0)); }
-   // ---- K0: tables
+   // ---- K0: tables (on the wave's own stream: with a shared K1 stream the tables of wave w + 1 are built under K1 of wave w,
+   // so that K1 of wave w + 1 is ready to go the moment its predecessor ends -- and is placed before the recursion warps)
    const bool tr = tm || c->trace;
-   if (c->trace) cudaEventRecord(S.ev[5], sg);
-   prep_kernel<<<nU, 128, 0, sg>>>(c->dm, W);
+   if (c->trace) cudaEventRecord(S.ev[5], st);
+   prep_kernel<<<nU, 128, 0, st>>>(c->dm, W);
    c->stats.launches++; c->stats.launchesMisc++;
-   if (tr) cudaEventRecord(S.ev[0], sg);
+   if (tr) cudaEventRecord(S.ev[0], st);
+   if (sg != st) { CK(cudaEventRecord(S.evIn, st)); CK(cudaStreamWaitEvent(sg, S.evIn, 0)); }
    // ---- K1
    int gk = c->opt.gmmKernel;
    if (gk == 0) gk = (c->useV3 || gmm_tc_available(c->tc)) ? 2 : 1;
@@ -909,7 +914,8 @@ static int launch_wave_impl(hfbgpu_ctx *c, hfbgpu_ctx::Slot &S, const int32_t *l
          if (reserveOn && !tm && need * 4 <= c->smCount) smK1 = std::max(2, (c->smCount - need) & ~1);
       }
       if ((rc = gmm_tc3_launch(c->tc3, S.tcw, c->dm, W, waveFrames, (const int2 *)(base + oIt), (int)w.tcItems.size(),
-                               (const int2 *)(base + oIt4), (int)w.tcItems4.size(), smK1, sg, &nl, expRows))) return rc;
+                               (const int2 *)(base + oIt4), (int)w.tcItems4.size(), smK1, sg, &nl, expRows,
+                               /* lean (96-register) build */ sg != st && smallFifoOn && smallWave))) return rc;
       c->stats.launches += nl; c->stats.launchesGmm += nl;
    } else if (gk == 2) {
       int nl = 0;
